@@ -1,0 +1,107 @@
+"""Python driver over the C ABI (tests and bench only; the product host code is
+the C++ above libsigk).  Mirrors the two reference calls it replaces:
+
+    builder.extract_kmers(deleted_fids); builder.process_kmers();
+    (reference src/kmers-build-signatures.cc:194-196)
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import KeptTable, PackedProteins, SigkConfig, SigkError, SigkTable, SigkTimings
+
+
+class GpuSignatureBuilder:
+    """One libsigk handle on one GPU."""
+
+    def __init__(self, device: int = 0, rank: int = 0, world: int = 1, flags: int = 0):
+        self.lib = capi.load_library()
+        cfg = SigkConfig(capi.SIGK_ABI_VERSION, capi.SIGK_K, device, rank, world, flags)
+        h = C.c_void_p()
+        rc = self.lib.sigk_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise SigkError(f"sigk_create failed ({rc}): {self.lib.sigk_last_error(None).decode()}")
+        self.h = h
+        self._proteins = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sigk_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise SigkError(f"{what} failed ({rc}): {self.lib.sigk_last_error(self.h).decode()}")
+
+    def set_proteins(self, p: PackedProteins):
+        self._proteins = p  # keep the arrays alive
+        st = p.as_struct()
+        self._check(self.lib.sigk_set_proteins(self.h, C.byref(st)), "sigk_set_proteins")
+
+    def build(self) -> KeptTable:
+        """extract_kmers + process_kmers: host arrays in, kept table out."""
+        self._check(self.lib.sigk_build(self.h), "sigk_build")
+        return self.result()
+
+    def upload(self):
+        self._check(self.lib.sigk_upload(self.h), "sigk_upload")
+
+    def build_device(self):
+        self._check(self.lib.sigk_build_device(self.h), "sigk_build_device")
+
+    def download(self):
+        self._check(self.lib.sigk_download(self.h), "sigk_download")
+
+    def result(self, copy: bool = True) -> KeptTable:
+        t = SigkTable()
+        self._check(self.lib.sigk_result(self.h, C.byref(t)), "sigk_result")
+        return capi.table_to_numpy(t, copy=copy)
+
+    def result_counts(self):
+        t = SigkTable()
+        self._check(self.lib.sigk_result(self.h, C.byref(t)), "sigk_result")
+        return dict(n_kept=int(t.n_kept), n_occurrences=int(t.n_occurrences), n_distinct_kmers=int(t.n_distinct_kmers),
+                    num_seqs_with_a_signature=int(t.num_seqs_with_a_signature))
+
+    def timings(self) -> dict:
+        t = SigkTimings()
+        self._check(self.lib.sigk_get_timings(self.h, C.byref(t)), "sigk_get_timings")
+        return t.as_dict()
+
+    # ---- stand-alone stages (parity tests) ----
+    def dbg_encode(self, p: PackedProteins):
+        cap = max(1, len(p.residues))
+        code = np.zeros(cap, dtype=np.uint64)
+        ordinal = np.zeros(cap, dtype=np.uint32)
+        offset = np.zeros(cap, dtype=np.uint16)
+        n = C.c_uint64()
+        st = p.as_struct()
+        self._proteins = p
+        self._check(self.lib.sigk_dbg_encode(self.h, C.byref(st), code.ctypes.data, ordinal.ctypes.data, offset.ctypes.data, cap, C.byref(n)), "sigk_dbg_encode")
+        k = int(n.value)
+        return code[:k], ordinal[:k], offset[:k]
+
+    def dbg_sort_pairs(self, keys: np.ndarray, vals: np.ndarray, bit_lo: int, bit_hi: int):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64).copy()
+        vals = np.ascontiguousarray(vals, dtype=np.uint32).copy()
+        self._check(self.lib.sigk_dbg_sort_pairs(self.h, keys.ctypes.data, vals.ctypes.data, len(keys), bit_lo, bit_hi), "sigk_dbg_sort_pairs")
+        return keys, vals
+
+
+def kmer_encode(kmer: str) -> int:
+    return capi.load_library().sigk_kmer_encode(kmer.encode("latin-1"))
+
+
+def kmer_decode(code: int) -> str:
+    buf = C.create_string_buffer(8)
+    capi.load_library().sigk_kmer_decode(code, buf)
+    return buf.raw.decode("latin-1")

@@ -1,0 +1,180 @@
+// encode.cu — stage 1: slide the 8-residue window over the packed protein
+// buffer, drop windows the reference drops, emit one 12-byte record per valid
+// window in canonical (insertion) order.
+//
+// Replaces the window loop of SignatureBuilder<K>::load_kmers_from_sequence
+// (reference src/signature_build.tcc:162-180):
+//   - a window is valid iff all 8 bytes are in ok_prot_ (src/signature_build.h:102-103)
+//     and it lies inside one protein (it < seq.end()-K+1);
+//   - offset = (unsigned short)(len - p)   (:164);
+//   - records are emitted in increasing position, proteins in input order, which
+//     is the multimap insertion order of the reference's serial branch (:50-56).
+//
+// Layout: each thread owns 16 consecutive window positions and reads its 16
+// residues with one 128-bit load (a warp reads 512 contiguous bytes); the 7
+// look-ahead residues come from the next lane by shuffle.  The 43-bit base-40
+// code is rolled (one multiply-add per window).  Valid windows are compacted
+// through shared memory and leave the CTA as coalesced 8-byte / 4-byte stores;
+// the CTA's place in the output is a single-pass chained scan over tile totals
+// (tiles are tickets, so the record order is the position order).
+//
+// HBM traffic per valid window: ~1 byte read, 12 bytes written.
+#include "kernels.h"
+#include "sigk_common.cuh"
+
+namespace sigk {
+
+namespace {
+
+constexpr int ENC_WARPS = ENC_THREADS / 32;
+// compacted records are staged with one pad slot per 16 so that the
+// thread-contiguous writes (stride ~16 records between lanes) spread over banks
+constexpr int ENC_STAGE = ENC_TILE + ENC_TILE / 16;
+SIGK_D int stage_slot(int o) { return o + (o >> 4); }
+
+struct EncSmem {
+    uint64_t keys[ENC_STAGE];
+    uint32_t vals[ENC_STAGE];
+    uint32_t scan[ENC_WARPS + 2];
+    uint32_t tile;
+    uint32_t lo, hi;
+    uint64_t base;
+};
+
+// largest i in [lo, hi] with starts[i] <= g   (starts[lo] <= g is guaranteed)
+SIGK_D uint32_t find_protein(const uint64_t *__restrict__ starts, uint32_t lo, uint32_t hi, uint64_t g) {
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo + 1) >> 1);
+        if (__ldg(starts + mid) <= g) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(ENC_THREADS)
+encode_kernel(EncodeArgs a, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
+              uint64_t *__restrict__ scan_state, uint32_t *__restrict__ ticket, uint64_t *__restrict__ n_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EncSmem &sm = *reinterpret_cast<EncSmem *>(smem_raw);
+
+    const unsigned tid = threadIdx.x, lane = tid & 31u;
+    if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = sm.tile;
+    const uint64_t g0 = (uint64_t)tile * ENC_TILE;
+    const uint32_t last_tile = (uint32_t)((a.total_res + ENC_TILE - 1) / ENC_TILE) - 1;
+
+    // protein range of this tile: two searches over the whole starts[] by two threads
+    if (tid < 2) {
+        uint64_t g = tid == 0 ? g0 : g0 + ENC_TILE - 1;
+        if (g >= a.total_res) g = a.total_res - 1;
+        const uint32_t i = find_protein(a.starts, 0, a.n_prot - 1, g);
+        if (tid == 0) sm.lo = i; else sm.hi = i;
+    }
+
+    // residues: 16 of my own + 8 of the next lane's
+    const uint64_t g_first = g0 + (uint64_t)tid * ENC_PPT;
+    const uint4 w = ld_stream_u128(reinterpret_cast<const uint4 *>(a.res + g_first));
+    uint32_t n0 = __shfl_down_sync(0xffffffffu, w.x, 1);
+    uint32_t n1 = __shfl_down_sync(0xffffffffu, w.y, 1);
+    if (lane == 31) {
+        const uint2 nx = *reinterpret_cast<const uint2 *>(a.res + g_first + ENC_PPT);
+        n0 = nx.x; n1 = nx.y;
+    }
+    const uint32_t words[6] = {w.x, w.y, w.z, w.w, n0, n1};
+
+    int s[ENC_PPT + 7];
+    uint32_t bad = 0;
+#pragma unroll
+    for (int j = 0; j < ENC_PPT + 7; ++j) {
+        const unsigned c = (words[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+        int sy = sigk_symbol(c);
+        if (sy < 0) { bad |= 1u << j; sy = 0; }
+        s[j] = sy;
+    }
+    __syncthreads();    // sm.lo / sm.hi
+
+    // pass A: which of my 16 windows are valid
+    const uint32_t p_first = find_protein(a.starts, sm.lo, sm.hi, g_first < a.total_res ? g_first : a.total_res - 1);
+    uint32_t valid_mask = 0;
+    {
+        uint32_t i = p_first;
+        uint64_t prot_end = __ldg(a.starts + i + 1);
+#pragma unroll
+        for (int j = 0; j < ENC_PPT; ++j) {
+            const uint64_t g = g_first + j;
+            while (g >= prot_end && i + 1 < a.n_prot) { ++i; prot_end = __ldg(a.starts + i + 1); }
+            if (((bad >> j) & 0xFFu) == 0 && g + SIGK_K_DEV <= prot_end) valid_mask |= 1u << j;
+        }
+    }
+    uint32_t total;
+    const uint32_t excl = block_exclusive_scan<ENC_THREADS>((uint32_t)__popc(valid_mask), sm.scan, &total);
+
+    if (tid == 0) {
+        const uint64_t base = chained_scan_exclusive(scan_state, tile, total);
+        sm.base = base;
+        if (tile == last_tile) *n_out = base + total;
+    }
+
+    // pass B: roll the code, emit valid windows to their compacted slots
+    {
+        uint32_t i = p_first;
+        uint64_t prot_end = __ldg(a.starts + i + 1);
+        uint64_t code = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) code = code * 40u + (uint64_t)s[j];
+        int o = (int)excl;
+#pragma unroll
+        for (int j = 0; j < ENC_PPT; ++j) {
+            const uint64_t g = g_first + j;
+            if (j > 0) code = (code - (uint64_t)s[j - 1] * SIGK_P7) * 40u + (uint64_t)s[j + 7];
+            while (g >= prot_end && i + 1 < a.n_prot) { ++i; prot_end = __ldg(a.starts + i + 1); }
+            if ((valid_mask >> j) & 1u) {
+                const int slot = stage_slot(o++);
+                sm.keys[slot] = sigk_pack_key(code, (unsigned)(prot_end - g));
+                sm.vals[slot] = a.ordinal_base + i;
+            }
+        }
+    }
+    __syncthreads();
+
+    const uint64_t base = sm.base;
+    for (uint32_t o = tid; o < total; o += ENC_THREADS) {
+        const int slot = stage_slot((int)o);
+        keys[base + o] = sm.keys[slot];
+        vals[base + o] = sm.vals[slot];
+    }
+}
+
+__global__ void protein_meta_kernel(const uint64_t *__restrict__ starts, const uint16_t *__restrict__ func, uint32_t n_prot,
+                                    uint32_t *__restrict__ len_out, uint32_t *__restrict__ seqs_with_func) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_prot) return;
+    len_out[i] = (uint32_t)(starts[i + 1] - starts[i]);     // static_cast<unsigned int>(seq.length()), tcc:178
+    atomicAdd(seqs_with_func + func[i], 1u);                // kmer_stats_.seqs_with_func[function_index]++, tcc:160
+}
+
+}  // namespace
+
+cudaError_t launch_encode(const EncodeArgs &a, uint64_t *keys, uint32_t *vals, uint64_t *scan_state,
+                          uint32_t *ticket, uint64_t *n_out, cudaStream_t stream) {
+    if (a.total_res == 0 || a.n_prot == 0) return cudaSuccess;   // n_out stays 0
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const uint64_t tiles = encode_tiles(a.total_res);
+    encode_kernel<<<(unsigned)tiles, ENC_THREADS, sizeof(EncSmem), stream>>>(a, keys, vals, scan_state, ticket, n_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_protein_meta(const uint64_t *starts, const uint16_t *func, uint32_t n_prot, uint32_t *len_out,
+                                uint32_t *seqs_with_func, cudaStream_t stream) {
+    if (n_prot == 0) return cudaSuccess;
+    protein_meta_kernel<<<(n_prot + 255) / 256, 256, 0, stream>>>(starts, func, n_prot, len_out, seqs_with_func);
+    return cudaGetLastError();
+}
+
+}  // namespace sigk

@@ -1,0 +1,266 @@
+// onesweep.cu — stage 2: stable least-significant-digit radix sort of the
+// (key u64, value u32) records on the 43 k-mer-code bits, onesweep style:
+//   - one histogram kernel counts the digits of every pass in a single read of
+//     the keys (shared-memory atomics, one global flush per CTA);
+//   - each pass is ONE kernel: a CTA takes a tile by ticket, ranks its keys with
+//     warp match-any (no atomics, stable), publishes its per-digit counts,
+//     resolves its global offsets by decoupled look-back over the previous
+//     tiles, reorders the tile in shared memory and writes each digit's run with
+//     coalesced stores.
+//
+// This replaces the grouping the reference gets from hashing every occurrence
+// into tbb::concurrent_unordered_multimap (src/signature_build.tcc:178) and
+// walking the buckets (:186-208): after the last pass equal k-mers are adjacent
+// and, because every pass is stable, still in insertion order.
+//
+// HBM traffic per record: 8 B (histogram) + 24 B per pass (12 read + 12 written).
+#include "kernels.h"
+#include "sigk_common.cuh"
+
+namespace sigk {
+
+PassPlan make_pass_plan(int bit_lo, int bit_hi) {
+    PassPlan p{};
+    const int total = bit_hi - bit_lo;
+    int npass = (total + SIGK_RADIX_BITS - 1) / SIGK_RADIX_BITS;
+    if (npass < 1) npass = 1;
+    p.npass = npass;
+    int lo = bit_lo;
+    for (int i = 0; i < npass; ++i) {
+        // spread the bits evenly: the first (total % npass) passes get one more
+        const int bits = total / npass + (i < total % npass ? 1 : 0);
+        p.lo[i] = lo;
+        p.bits[i] = bits;
+        lo += bits;
+    }
+    return p;
+}
+
+namespace {
+
+constexpr int OS_WARPS = OS_THREADS / 32;
+
+// look-back word: flag in the two top bits, value below
+template <typename LB> struct LBTraits;
+template <> struct LBTraits<uint32_t> {
+    static constexpr uint32_t AGG = 1u << 30, PRE = 2u << 30, VAL = (1u << 30) - 1;
+    static constexpr int SHIFT = 30;
+    static SIGK_D uint32_t ld(const uint32_t *p) { return ld_volatile_u32(p); }
+    static SIGK_D void st(uint32_t *p, uint32_t v) { st_volatile_u32(p, v); }
+};
+template <> struct LBTraits<uint64_t> {
+    static constexpr uint64_t AGG = 1ull << 62, PRE = 2ull << 62, VAL = (1ull << 62) - 1;
+    static constexpr int SHIFT = 62;
+    static SIGK_D uint64_t ld(const uint64_t *p) { return ld_volatile_u64(p); }
+    static SIGK_D void st(uint64_t *p, uint64_t v) { st_volatile_u64(p, v); }
+};
+
+struct OsSmem {
+    uint64_t keys[OS_TILE];
+    uint32_t vals[OS_TILE];
+    uint32_t cnt[OS_WARPS * SIGK_RADIX];    // per-warp digit counters -> exclusive prefix over warps
+    uint64_t goff[SIGK_RADIX];              // global position of sorted slot 0 of each digit, minus its tile base
+    uint32_t dbase[SIGK_RADIX];             // exclusive scan of the tile histogram
+    uint32_t scan[OS_WARPS + 2];
+    uint32_t tile;
+};
+
+template <typename LB>
+__global__ void __launch_bounds__(OS_THREADS, 2)
+onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                     uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
+                     const uint64_t *__restrict__ n_ptr, int bit_lo, uint32_t digit_mask,
+                     const uint64_t *__restrict__ bin_base, LB *__restrict__ lookback, uint32_t *__restrict__ ticket) {
+    using T = LBTraits<LB>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    OsSmem &sm = *reinterpret_cast<OsSmem *>(smem_raw);
+
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint64_t n = *n_ptr;
+    if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = sm.tile;
+    const uint64_t tile_start = (uint64_t)tile * OS_TILE;
+    if (tile_start >= n) return;
+    const uint32_t tile_n = (uint32_t)((n - tile_start) < (uint64_t)OS_TILE ? (n - tile_start) : (uint64_t)OS_TILE);
+
+    // ---- load keys, warp-striped: item i of lane l is record wbase + 32 i + l.
+    // Padding of the last tile gets key ~0: it ranks after every real record of
+    // the top digit and is never written.
+    const uint32_t wbase = warp * (OS_ITEMS * 32);
+    uint64_t key[OS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < OS_ITEMS; ++i) {
+        const uint32_t idx = wbase + i * 32 + lane;
+        key[i] = idx < tile_n ? ld_stream_u64(keys_in + tile_start + idx) : ~0ull;
+    }
+    for (uint32_t j = tid; j < OS_WARPS * SIGK_RADIX; j += OS_THREADS) sm.cnt[j] = 0;
+    __syncthreads();
+
+    // ---- rank inside the warp: match-any groups equal digits, the group leader
+    // bumps the warp's counter, everyone takes counter + (peers below me).
+    uint32_t *wcnt = sm.cnt + warp * SIGK_RADIX;
+    uint16_t rank[OS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < OS_ITEMS; ++i) {
+        const uint32_t d = (uint32_t)(key[i] >> bit_lo) & digit_mask;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if ((int)lane == leader) { old = wcnt[d]; wcnt[d] = old + __popc(peers); }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[i] = (uint16_t)(old + __popc(peers & ((1u << lane) - 1u)));
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per digit: exclusive prefix over warps, tile count, publish, look back
+    uint32_t my_count = 0;
+    if (tid < SIGK_RADIX) {
+        uint32_t sum = 0;
+#pragma unroll
+        for (int w = 0; w < OS_WARPS; ++w) {
+            const uint32_t c = sm.cnt[w * SIGK_RADIX + tid];
+            sm.cnt[w * SIGK_RADIX + tid] = sum;
+            sum += c;
+        }
+        my_count = sum;
+        T::st(lookback + (size_t)tile * SIGK_RADIX + tid, (tile == 0 ? T::PRE : T::AGG) | (LB)sum);
+    }
+    uint32_t total;
+    const uint32_t dbase = block_exclusive_scan<OS_THREADS>(my_count, sm.scan, &total);
+    if (tid < SIGK_RADIX) {
+        sm.dbase[tid] = dbase;
+        LB excl = 0;
+        if (tile > 0) {
+            int64_t t = (int64_t)tile - 1;
+            for (;;) {
+                const LB v = T::ld(lookback + (size_t)t * SIGK_RADIX + tid);
+                const LB flag = v >> T::SHIFT;
+                if (flag == 0) continue;
+                excl += v & T::VAL;
+                if (flag == 2) break;
+                --t;
+            }
+            T::st(lookback + (size_t)tile * SIGK_RADIX + tid, T::PRE | (excl + (LB)my_count));
+        }
+        sm.goff[tid] = bin_base[tid] + (uint64_t)excl - (uint64_t)dbase;
+    }
+    __syncthreads();
+
+    // ---- reorder the tile in shared memory (keys, then values by the same slots)
+#pragma unroll
+    for (int i = 0; i < OS_ITEMS; ++i) {
+        const uint32_t d = (uint32_t)(key[i] >> bit_lo) & digit_mask;
+        const uint32_t slot = sm.dbase[d] + wcnt[d] + rank[i];
+        rank[i] = (uint16_t)slot;
+        sm.keys[slot] = key[i];
+    }
+#pragma unroll
+    for (int i = 0; i < OS_ITEMS; ++i) {
+        const uint32_t idx = wbase + i * 32 + lane;
+        const uint32_t v = idx < tile_n ? ld_stream_u32(vals_in + tile_start + idx) : 0u;
+        sm.vals[rank[i]] = v;
+    }
+    __syncthreads();
+
+    // ---- coalesced write-out: consecutive slots of one digit are consecutive in HBM
+    for (uint32_t j = tid; j < tile_n; j += OS_THREADS) {
+        const uint64_t k = sm.keys[j];
+        const uint32_t d = (uint32_t)(k >> bit_lo) & digit_mask;
+        const uint64_t pos = sm.goff[d] + j;
+        keys_out[pos] = k;
+        vals_out[pos] = sm.vals[j];
+    }
+}
+
+constexpr int HIST_THREADS = 512;
+constexpr int HIST_UNROLL = 4;
+
+__global__ void __launch_bounds__(HIST_THREADS)
+histogram_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ n_ptr, PassPlan plan,
+                 uint64_t *__restrict__ hist) {
+    __shared__ uint32_t sh[SORT_MAX_PASSES * SIGK_RADIX];
+    for (int j = threadIdx.x; j < plan.npass * SIGK_RADIX; j += HIST_THREADS) sh[j] = 0;
+    __syncthreads();
+    const uint64_t n = *n_ptr;
+    const uint64_t stride = (uint64_t)gridDim.x * HIST_THREADS * HIST_UNROLL;
+    for (uint64_t base = (uint64_t)blockIdx.x * HIST_THREADS * HIST_UNROLL; base < n; base += stride) {
+        uint64_t k[HIST_UNROLL];
+        bool ok[HIST_UNROLL];
+#pragma unroll
+        for (int u = 0; u < HIST_UNROLL; ++u) {
+            const uint64_t idx = base + (uint64_t)u * HIST_THREADS + threadIdx.x;
+            ok[u] = idx < n;
+            k[u] = ok[u] ? ld_stream_u64(keys + idx) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < HIST_UNROLL; ++u) {
+            if (!ok[u]) continue;
+            for (int p = 0; p < plan.npass; ++p)
+                atomicAdd(&sh[p * SIGK_RADIX + ((uint32_t)(k[u] >> plan.lo[p]) & ((1u << plan.bits[p]) - 1u))], 1u);
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < plan.npass * SIGK_RADIX; j += HIST_THREADS)
+        if (sh[j]) atomicAdd(reinterpret_cast<unsigned long long *>(hist + j), (unsigned long long)sh[j]);
+}
+
+__global__ void scan_bins_kernel(const uint64_t *__restrict__ hist, uint64_t *__restrict__ bin_base) {
+    __shared__ uint64_t s[SIGK_RADIX];
+    const int p = blockIdx.x, d = threadIdx.x;
+    s[d] = hist[p * SIGK_RADIX + d];
+    __syncthreads();
+    // 256 bins: a serial scan by one thread is a few hundred cycles
+    if (d == 0) {
+        uint64_t run = 0;
+        for (int i = 0; i < SIGK_RADIX; ++i) { const uint64_t c = s[i]; s[i] = run; run += c; }
+    }
+    __syncthreads();
+    bin_base[p * SIGK_RADIX + d] = s[d];
+}
+
+}  // namespace
+
+size_t onesweep_lookback_bytes(uint64_t capacity) {
+    const size_t word = capacity >= (1ull << 30) ? 8 : 4;
+    return (size_t)onesweep_tiles(capacity) * SIGK_RADIX * word;
+}
+
+cudaError_t onesweep_configure() {
+    cudaError_t e = cudaFuncSetAttribute(onesweep_pass_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(onesweep_pass_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem));
+}
+
+cudaError_t launch_histogram(const uint64_t *keys, const uint64_t *n_ptr, uint64_t capacity, const PassPlan &plan,
+                             uint64_t *hist, int sm_count, cudaStream_t stream) {
+    if (capacity == 0) return cudaSuccess;
+    uint64_t want = (capacity + (uint64_t)HIST_THREADS * HIST_UNROLL - 1) / ((uint64_t)HIST_THREADS * HIST_UNROLL);
+    const uint64_t cap = (uint64_t)sm_count * 4;
+    if (want > cap) want = cap;
+    histogram_kernel<<<(unsigned)want, HIST_THREADS, 0, stream>>>(keys, n_ptr, plan, hist);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan_bins(const uint64_t *hist, uint64_t *bin_base, int npass, cudaStream_t stream) {
+    scan_bins_kernel<<<npass, SIGK_RADIX, 0, stream>>>(hist, bin_base);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_onesweep_pass(const uint64_t *keys_in, const uint32_t *vals_in, uint64_t *keys_out,
+                                 uint32_t *vals_out, const uint64_t *n_ptr, uint64_t capacity, int bit_lo, int nbits,
+                                 const uint64_t *bin_base, void *lookback, uint32_t *ticket, cudaStream_t stream) {
+    if (capacity == 0) return cudaSuccess;
+    const unsigned tiles = (unsigned)onesweep_tiles(capacity);
+    const uint32_t mask = (1u << nbits) - 1u;
+    if (capacity >= (1ull << 30))
+        onesweep_pass_kernel<uint64_t><<<tiles, OS_THREADS, sizeof(OsSmem), stream>>>(
+            keys_in, vals_in, keys_out, vals_out, n_ptr, bit_lo, mask, bin_base, (uint64_t *)lookback, ticket);
+    else
+        onesweep_pass_kernel<uint32_t><<<tiles, OS_THREADS, sizeof(OsSmem), stream>>>(
+            keys_in, vals_in, keys_out, vals_out, n_ptr, bit_lo, mask, bin_base, (uint32_t *)lookback, ticket);
+    return cudaGetLastError();
+}
+
+}  // namespace sigk

@@ -1,0 +1,520 @@
+// sigk_api.cu — the C ABI of include/sigk.h over the kernels of this directory.
+//
+// One handle owns one CUDA stream, the device copies of the packed proteins,
+// the two record buffers the radix sort ping-pongs between, and the kept-table
+// columns.  sigk_build() = extract_kmers + process_kmers of the reference
+// (src/kmers-build-signatures.cc:194-196).  No CPU fallback exists: every
+// compute entry point needs a CUDA device and fails with SIGK_E_CUDA otherwise.
+#include "../../include/sigk.h"
+#include "kernels.h"
+#include "sigk_common.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace sigk;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DeviceScalars {
+    uint64_t n_records;
+    uint64_t n_segments;
+    uint64_t n_kept;
+    uint64_t n_seqs_sig;
+    uint32_t ticket[16];
+};
+
+enum { TK_ENCODE = 0, TK_HEADS = 1, TK_COMPACT = 2, TK_SORT0 = 4 };
+
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;     // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <typename T> struct PinnedBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMallocHost(&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+enum { EV_START, EV_H2D, EV_DEV0, EV_ENCODE, EV_HIST, EV_SORT, EV_REDUCE, EV_D2H, EV_PASS0, EV_COUNT = EV_PASS0 + SORT_MAX_PASSES + 1 };
+
+}  // namespace
+
+struct sigk_handle {
+    sigk_config cfg{};
+    std::string error;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[EV_COUNT] = {};
+    int sm_count = 148;
+
+    sigk_proteins in{};
+    bool have_input = false, uploaded = false, built = false, downloaded = false;
+    uint64_t total_res = 0;
+    uint32_t max_seq_id = 0;
+
+    DevBuf<uint8_t> d_res;
+    DevBuf<uint64_t> d_starts;
+    DevBuf<uint16_t> d_func;
+    DevBuf<uint32_t> d_seqid, d_len;
+    DevBuf<uint64_t> d_keys[2];
+    DevBuf<uint32_t> d_vals[2];
+    DevBuf<uint8_t> d_lookback;
+    DevBuf<uint64_t> d_hist, d_binbase, d_scan_state;
+    DevBuf<uint32_t> d_seg_start;
+    DevBuf<uint4> d_seg_rows;
+    DevBuf<uint64_t> d_out_kmer;
+    DevBuf<uint16_t> d_out_cols;       // 5 columns of capacity rows
+    DevBuf<uint32_t> d_bitmap, d_distinct, d_swf;
+    DevBuf<DeviceScalars> d_scalars;
+    uint64_t capacity = 0;             // records the buffers are sized for
+    int sorted_in = 0;                 // which ping-pong buffer holds the sorted records
+
+    PinnedBuf<uint64_t> h_kmer;
+    PinnedBuf<uint16_t> h_cols;
+    PinnedBuf<uint32_t> h_distinct, h_swf;
+    PinnedBuf<DeviceScalars> h_scalars;
+    uint64_t h_rows = 0;
+
+    sigk_timings tm{};
+    float h2d_ms = 0;
+    PassPlan plan{};
+
+    int fail(int code, const char *fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        error = buf;
+        return code;
+    }
+};
+
+#define CU(h, call)                                                                                          \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess)                                                                               \
+            return (h)->fail(e_ == cudaErrorMemoryAllocation ? SIGK_E_NOMEM : SIGK_E_CUDA, "%s: %s (%s:%d)", #call, \
+                             cudaGetErrorString(e_), __FILE__, __LINE__);                                    \
+    } while (0)
+
+namespace {
+
+int ensure_device(sigk_handle *h) {
+    CU(h, cudaSetDevice(h->cfg.device));
+    return SIGK_OK;
+}
+
+uint16_t *out_col(sigk_handle *h, int c) { return h->d_out_cols.p + (size_t)c * h->capacity; }
+
+int do_upload(sigk_handle *h) {
+    if (!h->have_input) return h->fail(SIGK_E_INVALID, "sigk_set_proteins has not been called");
+    if (int rc = ensure_device(h)) return rc;
+    const sigk_proteins &p = h->in;
+    const uint64_t np = p.n_proteins;
+    const uint64_t total = h->total_res;
+    const uint64_t padded = encode_tiles(total) * ENC_TILE + ENC_PAD;
+
+    CU(h, h->d_res.reserve(padded));
+    CU(h, h->d_starts.reserve(np + 1));
+    CU(h, h->d_func.reserve(np));
+    CU(h, h->d_seqid.reserve(np));
+    CU(h, h->d_len.reserve(np));
+    // one record per residue position is the ceiling (every window valid)
+    const uint64_t cap = total;
+    if (cap > h->capacity) {
+        for (int i = 0; i < 2; ++i) { CU(h, h->d_keys[i].reserve(cap)); CU(h, h->d_vals[i].reserve(cap)); }
+        CU(h, h->d_lookback.reserve(onesweep_lookback_bytes(cap)));
+        CU(h, h->d_seg_start.reserve(cap));
+        CU(h, h->d_seg_rows.reserve(cap));
+        CU(h, h->d_out_kmer.reserve(cap));
+        CU(h, h->d_out_cols.reserve(cap * 5));
+        const uint64_t tiles = std::max({encode_tiles(padded), seg_tiles(cap), cmp_tiles(cap)}) + 1;
+        CU(h, h->d_scan_state.reserve(tiles));
+        h->capacity = cap;
+    }
+    CU(h, h->d_hist.reserve(SORT_MAX_PASSES * SIGK_RADIX));
+    CU(h, h->d_binbase.reserve(SORT_MAX_PASSES * SIGK_RADIX));
+    CU(h, h->d_bitmap.reserve(((uint64_t)h->max_seq_id >> 5) + 1));
+    CU(h, h->d_distinct.reserve(SIGK_N_FUNCTION_SLOTS));
+    CU(h, h->d_swf.reserve(SIGK_N_FUNCTION_SLOTS));
+    CU(h, h->d_scalars.reserve(1));
+    CU(h, h->h_scalars.reserve(1));
+    CU(h, h->h_distinct.reserve(SIGK_N_FUNCTION_SLOTS));
+    CU(h, h->h_swf.reserve(SIGK_N_FUNCTION_SLOTS));
+
+    cudaStream_t st = h->stream;
+    CU(h, cudaEventRecord(h->ev[EV_START], st));
+    if (total) CU(h, cudaMemcpyAsync(h->d_res.p, p.residues, total, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemsetAsync(h->d_res.p + total, 0, padded - total, st));
+    CU(h, cudaMemcpyAsync(h->d_starts.p, p.starts, (np + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    if (np) {
+        CU(h, cudaMemcpyAsync(h->d_func.p, p.function_index, np * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+        CU(h, cudaMemcpyAsync(h->d_seqid.p, p.seq_id, np * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    }
+    CU(h, cudaEventRecord(h->ev[EV_H2D], st));
+    CU(h, cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&h->h2d_ms, h->ev[EV_START], h->ev[EV_H2D]);
+    h->uploaded = true;
+    h->built = h->downloaded = false;
+    return SIGK_OK;
+}
+
+int do_build_device(sigk_handle *h) {
+    if (!h->uploaded) return h->fail(SIGK_E_INVALID, "sigk_upload has not been called");
+    if (int rc = ensure_device(h)) return rc;
+    cudaStream_t st = h->stream;
+    const uint64_t np = h->in.n_proteins;
+    const uint64_t cap = h->capacity;
+    DeviceScalars *sc = h->d_scalars.p;
+    uint32_t launches = 0;
+
+    CU(h, cudaEventRecord(h->ev[EV_DEV0], st));
+    CU(h, cudaMemsetAsync(sc, 0, sizeof(DeviceScalars), st));
+    CU(h, cudaMemsetAsync(h->d_swf.p, 0, SIGK_N_FUNCTION_SLOTS * sizeof(uint32_t), st));
+    CU(h, cudaMemsetAsync(h->d_distinct.p, 0, SIGK_N_FUNCTION_SLOTS * sizeof(uint32_t), st));
+    CU(h, cudaMemsetAsync(h->d_bitmap.p, 0, (((uint64_t)h->max_seq_id >> 5) + 1) * sizeof(uint32_t), st));
+    CU(h, cudaMemsetAsync(h->d_hist.p, 0, SORT_MAX_PASSES * SIGK_RADIX * sizeof(uint64_t), st));
+
+    // ---- stage 1: encode
+    CU(h, launch_protein_meta(h->d_starts.p, h->d_func.p, (uint32_t)np, h->d_len.p, h->d_swf.p, st)); ++launches;
+    CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, (encode_tiles(h->total_res) + 1) * sizeof(uint64_t), st));
+    EncodeArgs ea{h->d_res.p, h->total_res, h->d_starts.p, (uint32_t)np, 0u};
+    CU(h, launch_encode(ea, h->d_keys[0].p, h->d_vals[0].p, h->d_scan_state.p, sc->ticket + TK_ENCODE, &sc->n_records, st)); ++launches;
+    CU(h, cudaEventRecord(h->ev[EV_ENCODE], st));
+
+    // ---- stage 2: onesweep sort on the 43 code bits
+    h->plan = make_pass_plan(SIGK_KEY_CODE_SHIFT, SIGK_KEY_CODE_SHIFT + SIGK_CODE_BITS);
+    CU(h, launch_histogram(h->d_keys[0].p, &sc->n_records, cap, h->plan, h->d_hist.p, h->sm_count, st)); ++launches;
+    CU(h, launch_scan_bins(h->d_hist.p, h->d_binbase.p, h->plan.npass, st)); ++launches;
+    CU(h, cudaEventRecord(h->ev[EV_HIST], st));
+    int cur = 0;
+    const size_t lb_bytes = onesweep_lookback_bytes(cap);
+    for (int p = 0; p < h->plan.npass; ++p) {
+        CU(h, cudaEventRecord(h->ev[EV_PASS0 + p], st));
+        CU(h, cudaMemsetAsync(h->d_lookback.p, 0, lb_bytes, st));
+        CU(h, launch_onesweep_pass(h->d_keys[cur].p, h->d_vals[cur].p, h->d_keys[cur ^ 1].p, h->d_vals[cur ^ 1].p,
+                                   &sc->n_records, cap, h->plan.lo[p], h->plan.bits[p],
+                                   h->d_binbase.p + (size_t)p * SIGK_RADIX, h->d_lookback.p, sc->ticket + TK_SORT0 + p, st));
+        ++launches;
+        cur ^= 1;
+    }
+    CU(h, cudaEventRecord(h->ev[EV_PASS0 + h->plan.npass], st));
+    CU(h, cudaEventRecord(h->ev[EV_SORT], st));
+    h->sorted_in = cur;
+
+    // ---- stages 3+4: run-length, reduce, keep/reject, compact
+    CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, (seg_tiles(cap) + 1) * sizeof(uint64_t), st));
+    CU(h, launch_segment_heads(h->d_keys[cur].p, &sc->n_records, cap, h->d_seg_start.p, h->d_scan_state.p,
+                               sc->ticket + TK_HEADS, &sc->n_segments, st)); ++launches;
+    ProteinMeta meta{h->d_func.p, h->d_len.p, h->d_seqid.p};
+    const int order_stats = (h->cfg.flags & SIGK_F_NO_ORDER_STATS) ? 0 : 1;
+    CU(h, launch_segment_process(h->d_keys[cur].p, h->d_vals[cur].p, &sc->n_records, h->d_seg_start.p, &sc->n_segments,
+                                 cap, meta, order_stats, h->d_seg_rows.p, h->d_bitmap.p, h->d_distinct.p, st)); ++launches;
+    CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, (cmp_tiles(cap) + 1) * sizeof(uint64_t), st));
+    KeptColumns kc{h->d_out_kmer.p, out_col(h, 0), out_col(h, 1), out_col(h, 2), out_col(h, 3), out_col(h, 4)};
+    CU(h, launch_compact_rows(h->d_seg_rows.p, &sc->n_segments, cap, kc, h->d_scan_state.p, sc->ticket + TK_COMPACT,
+                              &sc->n_kept, st)); ++launches;
+    CU(h, launch_popcount(h->d_bitmap.p, ((uint64_t)h->max_seq_id >> 5) + 1, &sc->n_seqs_sig, st)); ++launches;
+    CU(h, cudaEventRecord(h->ev[EV_REDUCE], st));
+
+    h->tm.kernel_launches = launches;
+    h->built = true;
+    h->downloaded = false;
+    return SIGK_OK;
+}
+
+int do_download(sigk_handle *h) {
+    if (!h->built) return h->fail(SIGK_E_INVALID, "sigk_build_device has not been called");
+    if (int rc = ensure_device(h)) return rc;
+    cudaStream_t st = h->stream;
+    CU(h, cudaMemcpyAsync(h->h_scalars.p, h->d_scalars.p, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(h->h_distinct.p, h->d_distinct.p, SIGK_N_FUNCTION_SLOTS * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(h->h_swf.p, h->d_swf.p, SIGK_N_FUNCTION_SLOTS * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    const uint64_t nk = h->h_scalars.p->n_kept;
+    if (nk > h->capacity) return h->fail(SIGK_E_CUDA, "kept count %llu exceeds capacity", (unsigned long long)nk);
+    if (nk > h->h_rows) {
+        // grow-only pinned result buffers (page-locking is slow; first build pays it)
+        CU(h, h->h_kmer.reserve(nk));
+        CU(h, h->h_cols.reserve(nk * 5));
+        h->h_rows = nk;
+    }
+    if (nk) {
+        CU(h, cudaMemcpyAsync(h->h_kmer.p, h->d_out_kmer.p, nk * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        for (int c = 0; c < 5; ++c)
+            CU(h, cudaMemcpyAsync(h->h_cols.p + (size_t)c * h->h_rows, out_col(h, c), nk * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+    }
+    CU(h, cudaEventRecord(h->ev[EV_D2H], st));
+    CU(h, cudaStreamSynchronize(st));
+
+    // timings of this build
+    sigk_timings &t = h->tm;
+    const uint32_t launches = t.kernel_launches;
+    std::memset(&t, 0, sizeof t);
+    t.kernel_launches = launches;
+    auto ms = [&](int a, int b) { float v = 0; cudaEventElapsedTime(&v, h->ev[a], h->ev[b]); return v; };
+    t.h2d_ms = h->h2d_ms;
+    t.encode_ms = ms(EV_DEV0, EV_ENCODE);
+    t.histogram_ms = ms(EV_ENCODE, EV_HIST);
+    t.sort_ms = ms(EV_HIST, EV_SORT);
+    t.reduce_ms = ms(EV_SORT, EV_REDUCE);
+    t.d2h_ms = ms(EV_REDUCE, EV_D2H);
+    t.device_total_ms = ms(EV_DEV0, EV_REDUCE);
+    t.sort_passes = (uint32_t)h->plan.npass;
+    t.record_bytes = 12;
+    t.key_bytes = 8;
+    for (int p = 0; p < h->plan.npass && p < 8; ++p) t.pass_ms[p] = ms(EV_PASS0 + p, EV_PASS0 + p + 1);
+    h->downloaded = true;
+    return SIGK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *sigk_version(void) { return "libsigk 0.1 (sm_100a; record 12 B; onesweep 8-bit digits)"; }
+
+int sigk_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int sigk_create(const sigk_config *cfg, sigk_handle **out) {
+    if (!cfg || !out) { g_create_error = "null argument"; return SIGK_E_INVALID; }
+    *out = nullptr;
+    if (cfg->abi_version != SIGK_ABI_VERSION) { g_create_error = "ABI version mismatch"; return SIGK_E_INVALID; }
+    if (cfg->k != SIGK_K) { g_create_error = "only K = 8 is supported (src/kmers-build-signatures.cc:17)"; return SIGK_E_UNSUPPORTED; }
+    if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) { g_create_error = "bad rank/world"; return SIGK_E_INVALID; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no usable CUDA device (libsigk has no CPU fallback): ") + cudaGetErrorString(e);
+        return SIGK_E_CUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "device ordinal out of range"; return SIGK_E_INVALID; }
+    sigk_handle *h = new sigk_handle;
+    h->cfg = *cfg;
+    if ((e = cudaSetDevice(cfg->device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e);
+        delete h;
+        return SIGK_E_CUDA;
+    }
+    for (auto &ev : h->ev) cudaEventCreate(&ev);
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
+    if ((e = onesweep_configure()) != cudaSuccess) {
+        g_create_error = std::string("kernel configuration failed (is this an sm_100a device?): ") + cudaGetErrorString(e);
+        sigk_destroy(h);
+        return SIGK_E_CUDA;
+    }
+    *out = h;
+    return SIGK_OK;
+}
+
+void sigk_destroy(sigk_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    h->d_res.release(); h->d_starts.release(); h->d_func.release(); h->d_seqid.release(); h->d_len.release();
+    for (int i = 0; i < 2; ++i) { h->d_keys[i].release(); h->d_vals[i].release(); }
+    h->d_lookback.release(); h->d_hist.release(); h->d_binbase.release(); h->d_scan_state.release();
+    h->d_seg_start.release(); h->d_seg_rows.release(); h->d_out_kmer.release(); h->d_out_cols.release();
+    h->d_bitmap.release(); h->d_distinct.release(); h->d_swf.release(); h->d_scalars.release();
+    h->h_kmer.release(); h->h_cols.release(); h->h_distinct.release(); h->h_swf.release(); h->h_scalars.release();
+    for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char *sigk_last_error(const sigk_handle *h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+void *sigk_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+void sigk_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int sigk_set_proteins(sigk_handle *h, const sigk_proteins *p) {
+    if (!h) return SIGK_E_INVALID;
+    if (!p || !p->starts) return h->fail(SIGK_E_INVALID, "null protein arrays");
+    const uint64_t np = p->n_proteins;
+    if (np >= 0xFFFFFFFFull) return h->fail(SIGK_E_UNSUPPORTED, "more than 2^32-2 proteins");
+    if (p->starts[0] != 0) return h->fail(SIGK_E_INVALID, "starts[0] must be 0");
+    const uint64_t total = p->starts[np];
+    if (total >= 0xFFFFFFFFull) return h->fail(SIGK_E_UNSUPPORTED, "more than 2^32-2 residues on one GPU");
+    if (np && (!p->function_index || !p->seq_id || (total && !p->residues))) return h->fail(SIGK_E_INVALID, "null protein arrays");
+    uint32_t max_sid = 0;
+    for (uint64_t i = 0; i < np; ++i) {
+        if (p->starts[i + 1] < p->starts[i]) return h->fail(SIGK_E_INVALID, "starts must be non-decreasing (protein %llu)", (unsigned long long)i);
+        if (p->function_index[i] == SIGK_UNDEFINED_FUNCTION)
+            return h->fail(SIGK_E_INVALID, "protein %llu has UndefinedFunction; the host must skip it (src/signature_build.tcc:155)", (unsigned long long)i);
+        max_sid = std::max(max_sid, p->seq_id[i]);
+    }
+    h->in = *p;
+    h->total_res = total;
+    h->max_seq_id = max_sid;
+    h->have_input = true;
+    h->uploaded = h->built = h->downloaded = false;
+    return SIGK_OK;
+}
+
+int sigk_upload(sigk_handle *h) { return h ? do_upload(h) : SIGK_E_INVALID; }
+int sigk_build_device(sigk_handle *h) { return h ? do_build_device(h) : SIGK_E_INVALID; }
+int sigk_download(sigk_handle *h) { return h ? do_download(h) : SIGK_E_INVALID; }
+
+int sigk_build(sigk_handle *h) {
+    if (!h) return SIGK_E_INVALID;
+    if (int rc = do_upload(h)) return rc;
+    if (int rc = do_build_device(h)) return rc;
+    if (int rc = do_download(h)) return rc;
+    return SIGK_OK;
+}
+
+int sigk_result(sigk_handle *h, sigk_table *out) {
+    if (!h) return SIGK_E_INVALID;
+    if (!out) return h->fail(SIGK_E_INVALID, "null table");
+    if (!h->downloaded) return h->fail(SIGK_E_INVALID, "no result: call sigk_build or sigk_download first");
+    const DeviceScalars &s = *h->h_scalars.p;
+    out->n_kept = s.n_kept;
+    out->kmer = reinterpret_cast<const char *>(h->h_kmer.p);
+    out->avg_from_end = h->h_cols.p + 0 * h->h_rows;
+    out->function_index = h->h_cols.p + 1 * h->h_rows;
+    out->mean = h->h_cols.p + 2 * h->h_rows;
+    out->median = h->h_cols.p + 3 * h->h_rows;
+    out->var = h->h_cols.p + 4 * h->h_rows;
+    out->n_occurrences = s.n_records;
+    out->n_distinct_kmers = s.n_segments;
+    out->distinct_signatures = s.n_kept;
+    out->num_seqs_with_a_signature = s.n_seqs_sig;
+    out->distinct_functions = h->h_distinct.p;
+    out->seqs_with_func = h->h_swf.p;
+    return SIGK_OK;
+}
+
+int sigk_get_timings(const sigk_handle *h, sigk_timings *out) {
+    if (!h || !out) return SIGK_E_INVALID;
+    *out = h->tm;
+    return SIGK_OK;
+}
+
+int sigk_comm_make_id(void *id128) {
+    (void)id128;
+    return SIGK_E_UNSUPPORTED;
+}
+int sigk_comm_join(sigk_handle *h, const void *id128) {
+    (void)id128;
+    return h ? h->fail(SIGK_E_UNSUPPORTED, "multi-GPU exchange is not built yet") : SIGK_E_INVALID;
+}
+
+int sigk_dbg_encode(sigk_handle *h, const sigk_proteins *p, uint64_t *out_code, uint32_t *out_ordinal,
+                    uint16_t *out_offset, uint64_t capacity, uint64_t *n_out) {
+    if (!h) return SIGK_E_INVALID;
+    if (int rc = sigk_set_proteins(h, p)) return rc;
+    if (int rc = do_upload(h)) return rc;
+    cudaStream_t st = h->stream;
+    DeviceScalars *sc = h->d_scalars.p;
+    CU(h, cudaMemsetAsync(sc, 0, sizeof(DeviceScalars), st));
+    CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, (encode_tiles(h->total_res) + 1) * sizeof(uint64_t), st));
+    EncodeArgs ea{h->d_res.p, h->total_res, h->d_starts.p, (uint32_t)p->n_proteins, 0u};
+    CU(h, launch_encode(ea, h->d_keys[0].p, h->d_vals[0].p, h->d_scan_state.p, sc->ticket + TK_ENCODE, &sc->n_records, st));
+    uint64_t n = 0;
+    CU(h, cudaMemcpyAsync(&n, &sc->n_records, sizeof n, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    if (n_out) *n_out = n;
+    if (n > capacity) return h->fail(SIGK_E_INVALID, "output capacity %llu < %llu records", (unsigned long long)capacity, (unsigned long long)n);
+    std::vector<uint64_t> keys(n);
+    std::vector<uint32_t> vals(n);
+    if (n) {
+        CU(h, cudaMemcpy(keys.data(), h->d_keys[0].p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        CU(h, cudaMemcpy(vals.data(), h->d_vals[0].p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    }
+    for (uint64_t i = 0; i < n; ++i) {
+        out_code[i] = sigk_key_code(keys[i]);
+        out_offset[i] = (uint16_t)sigk_key_offset(keys[i]);
+        out_ordinal[i] = vals[i];
+    }
+    return SIGK_OK;
+}
+
+int sigk_dbg_sort_pairs(sigk_handle *h, uint64_t *keys, uint32_t *vals, uint64_t n, int bit_lo, int bit_hi) {
+    if (!h) return SIGK_E_INVALID;
+    if (bit_lo < 0 || bit_hi > 64 || bit_lo >= bit_hi) return h->fail(SIGK_E_INVALID, "bad bit range");
+    if (n >= 0xFFFFFFFFull) return h->fail(SIGK_E_UNSUPPORTED, "too many records");
+    if (int rc = ensure_device(h)) return rc;
+    if (n == 0) return SIGK_OK;
+    cudaStream_t st = h->stream;
+    DevBuf<uint64_t> k[2], hist, base, nbuf;
+    DevBuf<uint32_t> v[2], ticket;
+    DevBuf<uint8_t> lb;
+    auto cleanup = [&]() { for (int i = 0; i < 2; ++i) { k[i].release(); v[i].release(); } hist.release(); base.release(); nbuf.release(); ticket.release(); lb.release(); };
+    const PassPlan plan = make_pass_plan(bit_lo, bit_hi);
+    if (plan.npass > SORT_MAX_PASSES) return h->fail(SIGK_E_INVALID, "too many passes");
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t x) { if (e == cudaSuccess) e = x; return e == cudaSuccess; };
+    for (int i = 0; i < 2; ++i) { ok(k[i].reserve(n)); ok(v[i].reserve(n)); }
+    ok(hist.reserve(SORT_MAX_PASSES * SIGK_RADIX)); ok(base.reserve(SORT_MAX_PASSES * SIGK_RADIX));
+    ok(nbuf.reserve(1)); ok(ticket.reserve(SORT_MAX_PASSES)); ok(lb.reserve(onesweep_lookback_bytes(n)));
+    if (e == cudaSuccess) {
+        ok(cudaMemcpyAsync(k[0].p, keys, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        ok(cudaMemcpyAsync(v[0].p, vals, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        ok(cudaMemcpyAsync(nbuf.p, &n, sizeof n, cudaMemcpyHostToDevice, st));
+        ok(cudaMemsetAsync(hist.p, 0, SORT_MAX_PASSES * SIGK_RADIX * sizeof(uint64_t), st));
+        ok(cudaMemsetAsync(ticket.p, 0, SORT_MAX_PASSES * sizeof(uint32_t), st));
+        ok(launch_histogram(k[0].p, nbuf.p, n, plan, hist.p, h->sm_count, st));
+        ok(launch_scan_bins(hist.p, base.p, plan.npass, st));
+        int cur = 0;
+        for (int p = 0; p < plan.npass && e == cudaSuccess; ++p) {
+            ok(cudaMemsetAsync(lb.p, 0, onesweep_lookback_bytes(n), st));
+            ok(launch_onesweep_pass(k[cur].p, v[cur].p, k[cur ^ 1].p, v[cur ^ 1].p, nbuf.p, n, plan.lo[p], plan.bits[p],
+                                    base.p + (size_t)p * SIGK_RADIX, lb.p, ticket.p + p, st));
+            cur ^= 1;
+        }
+        ok(cudaMemcpyAsync(keys, k[cur].p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        ok(cudaMemcpyAsync(vals, v[cur].p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        ok(cudaStreamSynchronize(st));
+    }
+    cleanup();
+    if (e != cudaSuccess) return h->fail(e == cudaErrorMemoryAllocation ? SIGK_E_NOMEM : SIGK_E_CUDA, "sort: %s", cudaGetErrorString(e));
+    return SIGK_OK;
+}
+
+uint64_t sigk_kmer_encode(const char kmer[8]) {
+    uint64_t code = 0;
+    for (int i = 0; i < 8; ++i) {
+        const int s = sigk_symbol((unsigned char)kmer[i]);
+        if (s < 0) return UINT64_MAX;
+        code = code * 40u + (uint64_t)s;
+    }
+    return code;
+}
+
+void sigk_kmer_decode(uint64_t code, char kmer[8]) {
+    const uint64_t a = sigk_code_to_ascii(code);
+    std::memcpy(kmer, &a, 8);
+}
+
+}  // extern "C"

@@ -1,0 +1,170 @@
+// sigk_common.cuh — shared definitions for the libsigk kernels (sm_100a).
+//
+// Record layout in HBM (struct-of-arrays, 12 bytes per k-mer occurrence):
+//   key  u64 = code43 << 21 | offset16 << 5      (low 5 bits zero)
+//   val  u32 = protein ordinal (index into the packed input, canonical order)
+// code43 is the base-40 value of the 8 residues over the reference's 40 valid
+// symbols (src/signature_build.h:102-103) ranked in ASCII order, so integer
+// order of codes == unsigned-byte order of the k-mers.  offset16 is the
+// reference's `unsigned short n = distance(it, seq.end())`
+// (src/signature_build.tcc:164).  Everything else KmerAttributes carries
+// (func_index, seq_id, protein_length; src/kmer_data.h:105-112) is looked up by
+// ordinal in L2-resident per-protein arrays.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define SIGK_CODE_BITS 43
+#define SIGK_KEY_CODE_SHIFT 21
+#define SIGK_KEY_OFFSET_SHIFT 5
+#define SIGK_K_DEV 8
+#define SIGK_RADIX_BITS 8
+#define SIGK_RADIX 256
+
+#define SIGK_HD __host__ __device__ __forceinline__
+#define SIGK_D __device__ __forceinline__
+
+// Letters A C D E F G H I K L M N P Q R S T V W Y as a bit set over 'A'+bit.
+#define SIGK_AA_MASK 0x016FBDFDu
+
+// Symbol rank 0..39 of a residue byte (upper case 0..19, lower case 20..39), or
+// -1 for anything outside ok_prot_ (B J O U X Z * digits ...).
+SIGK_HD int sigk_symbol(unsigned c) {
+    const unsigned idx = (c & 0xDFu) - 0x41u;
+    const bool letter = ((c & 0xC0u) == 0x40u) && idx < 26u && ((SIGK_AA_MASK >> idx) & 1u);
+    if (!letter) return -1;
+#ifdef __CUDA_ARCH__
+    const int rank = __popc(SIGK_AA_MASK & ((1u << idx) - 1u));
+#else
+    const int rank = __builtin_popcount(SIGK_AA_MASK & ((1u << idx) - 1u));
+#endif
+    return rank + ((c & 0x20u) ? 20 : 0);
+}
+
+// 40^7
+#define SIGK_P7 163840000000ULL
+
+SIGK_HD uint64_t sigk_pack_key(uint64_t code, unsigned offset16) {
+    return (code << SIGK_KEY_CODE_SHIFT) | ((uint64_t)(offset16 & 0xFFFFu) << SIGK_KEY_OFFSET_SHIFT);
+}
+SIGK_HD uint64_t sigk_key_code(uint64_t key) { return key >> SIGK_KEY_CODE_SHIFT; }
+SIGK_HD unsigned sigk_key_offset(uint64_t key) { return (unsigned)(key >> SIGK_KEY_OFFSET_SHIFT) & 0xFFFFu; }
+
+// code -> 8 ASCII bytes packed little-endian (first residue in the low byte),
+// ready for one 8-byte store into the kmer column.
+SIGK_HD uint64_t sigk_code_to_ascii(uint64_t code) {
+    const char *tab = "ACDEFGHIKLMNPQRSTVWYacdefghiklmnpqrstvwy";
+    uint64_t out = 0;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+        const unsigned s = (unsigned)(code % 40u);
+        code /= 40u;
+        out |= (uint64_t)(unsigned char)tab[s] << (8 * i);
+    }
+    return out;
+}
+
+#ifdef __CUDACC__
+
+SIGK_D unsigned lane_id() { return threadIdx.x & 31u; }
+
+SIGK_D uint64_t ld_volatile_u64(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+SIGK_D void st_volatile_u64(uint64_t *p, uint64_t v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+SIGK_D uint32_t ld_volatile_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+SIGK_D void st_volatile_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Streaming (read-once) loads: keep them out of L1.
+SIGK_D uint64_t ld_stream_u64(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+SIGK_D uint32_t ld_stream_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+SIGK_D uint4 ld_stream_u128(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+// ---- single-value chained scan (decoupled look-back) ------------------------
+// state[t] = flag << 62 | value.  flag 0 = not ready, 1 = tile aggregate,
+// 2 = inclusive prefix.  Tiles are tickets taken in launch order, so every
+// predecessor of a running tile is running or done and publishes its aggregate
+// before it waits on anything: the spin below always terminates.
+#define SIGK_CS_AGG (1ULL << 62)
+#define SIGK_CS_PRE (2ULL << 62)
+#define SIGK_CS_VAL ((1ULL << 62) - 1)
+
+// Called by ONE thread of the tile.  Returns the exclusive prefix of `aggregate`.
+SIGK_D uint64_t chained_scan_exclusive(uint64_t *state, uint32_t tile, uint64_t aggregate) {
+    if (tile == 0) {
+        st_volatile_u64(state, SIGK_CS_PRE | aggregate);
+        return 0;
+    }
+    st_volatile_u64(state + tile, SIGK_CS_AGG | aggregate);
+    uint64_t excl = 0;
+    int64_t t = (int64_t)tile - 1;
+    for (;;) {
+        const uint64_t v = ld_volatile_u64(state + t);
+        const uint64_t flag = v >> 62;
+        if (flag == 0) continue;
+        excl += v & SIGK_CS_VAL;
+        if (flag == 2) break;
+        --t;
+    }
+    st_volatile_u64(state + tile, SIGK_CS_PRE | (excl + aggregate));
+    return excl;
+}
+
+// Block-wide exclusive scan of one uint32 per thread; returns the exclusive
+// prefix, writes the block total to *total (valid in every thread).
+template <int THREADS>
+SIGK_D uint32_t block_exclusive_scan(uint32_t x, uint32_t *s_warp /* THREADS/32 + 1 words */, uint32_t *total) {
+    constexpr int WARPS = THREADS / 32;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t incl = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += y;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < WARPS ? s_warp[lane] : 0;
+        uint32_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= (unsigned)o) wi += y;
+        }
+        if (lane < WARPS) s_warp[lane] = wi - w;
+        if (lane == WARPS - 1) s_warp[WARPS] = wi;
+    }
+    __syncthreads();
+    const uint32_t res = s_warp[warp] + incl - x;
+    *total = s_warp[WARPS];
+    __syncthreads();   // s_warp may be reused by the caller
+    return res;
+}
+
+#endif  // __CUDACC__

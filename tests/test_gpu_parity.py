@@ -1,0 +1,155 @@
+"""GPU parity tests: every stage of the CUDA path, through the C ABI, against
+the CPU oracle / numpy on the same seeded inputs (bit-exact: integer work).
+Run on the B200 box with `pytest -m gpu`."""
+import numpy as np
+import pytest
+
+from tests.util import assert_tables_equal, pack, random_proteins
+
+pytestmark = pytest.mark.gpu
+
+ALPHABET = "ACDEFGHIKLMNPQRSTVWYacdefghiklmnpqrstvwy"
+SYM = {ord(c): i for i, c in enumerate(ALPHABET)}
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from signature_kmers_b200.builder import GpuSignatureBuilder
+
+    b = GpuSignatureBuilder(device=0)
+    yield b
+    b.close()
+
+
+def encode_reference(seqs):
+    """Window enumeration of src/signature_build.tcc:162-180 in pure Python."""
+    codes, ords, offs = [], [], []
+    for i, s in enumerate(seqs):
+        L = len(s)
+        for p in range(L - 7):
+            w = s[p:p + 8]
+            if all(c in SYM for c in w):
+                code = 0
+                for c in w:
+                    code = code * 40 + SYM[c]
+                codes.append(code)
+                ords.append(i)
+                offs.append((L - p) & 0xFFFF)
+    return np.array(codes, dtype=np.uint64), np.array(ords, dtype=np.uint32), np.array(offs, dtype=np.uint16)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_encode_matches_window_loop(gpu, seed):
+    seqs, funcs = random_proteins(seed, n_families=40, members=(1, 8), length=(0, 300), ambig_rate=0.02, lower_rate=0.03)
+    seqs = seqs + [b"", b"ACDEFGH", b"ACDEFGHI", b"X" * 40, b"acdefghiklmnpqrstvwy" * 300]  # empty, short, exact, all-bad, > 4096 tile
+    funcs = funcs + [0] * 5
+    code, ordinal, offset = gpu.dbg_encode(pack(seqs, funcs))
+    rc, ro, rf = encode_reference(seqs)
+    np.testing.assert_array_equal(code, rc)
+    np.testing.assert_array_equal(ordinal, ro)
+    np.testing.assert_array_equal(offset, rf)
+
+
+def test_encode_long_protein_offset_wraps(gpu):
+    L = 70000
+    rng = np.random.default_rng(5)
+    s = bytes(rng.choice(np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8), L))
+    code, ordinal, offset = gpu.dbg_encode(pack([b"ACDEFGHIK", s, b"ACDEFGHIK"], [0, 1, 2]))
+    rc, ro, rf = encode_reference([b"ACDEFGHIK", s, b"ACDEFGHIK"])
+    np.testing.assert_array_equal(code, rc)
+    np.testing.assert_array_equal(ordinal, ro)
+    np.testing.assert_array_equal(offset, rf)
+
+
+@pytest.mark.parametrize("n,lo,hi", [(1, 21, 64), (7680, 21, 64), (7681, 21, 64), (100_000, 0, 64), (5_000_000, 21, 64), (1_000_003, 5, 13)])
+def test_radix_sort_is_stable_and_sorted(gpu, n, lo, hi):
+    rng = np.random.default_rng(n)
+    # heavy duplication in the sorted bits so that stability is visible
+    pool = rng.integers(0, 1 << 62, size=max(1, n // 7), dtype=np.uint64)
+    keys = pool[rng.integers(0, len(pool), size=n)]
+    keys[: n // 10] = keys[0]                      # one huge run (skewed digit)
+    vals = np.arange(n, dtype=np.uint32)
+    gk, gv = gpu.dbg_sort_pairs(keys, vals, lo, hi)
+    field = (keys >> np.uint64(lo)) & np.uint64((1 << (hi - lo)) - 1) if hi - lo < 64 else keys
+    order = np.argsort(field, kind="stable")
+    np.testing.assert_array_equal(gk, keys[order])
+    np.testing.assert_array_equal(gv, vals[order])
+
+
+def test_known_answers_on_gpu(gpu, oracle):
+    aa = "ACDEFGHIKLMNPQRSTVWY"
+    gpu.set_proteins(pack([aa] * 3, [0, 0, 0]))
+    t = gpu.build()
+    assert t.n_occurrences == 39 and t.n_kept == 13 and t.num_seqs_with_a_signature == 3
+    assert t.row("ACDEFGHI") == dict(avg_from_end=20, function_index=0, mean=20, median=20, var=0)
+    # K4: the 16-bit sum wraps
+    s2 = "WWWWWWWW" + "A" * 292
+    gpu.set_proteins(pack([s2] * 300, [0] * 300))
+    t = gpu.build()
+    assert t.row("WWWWWWWW")["mean"] == 81 and t.row("WWWWWWWW")["avg_from_end"] == 300
+    # K2: 4 of 5 kept, 3 of 4 rejected
+    gpu.set_proteins(pack([aa[:8]] * 5, [0, 0, 0, 0, 1]))
+    assert gpu.build().n_kept == 1
+    gpu.set_proteins(pack([aa[:8]] * 4, [0, 0, 0, 1]))
+    assert gpu.build().n_kept == 0
+
+
+def test_empty_and_degenerate_inputs(gpu, oracle):
+    for seqs, funcs in ([], []), ([b""], [0]), ([b"ACDEFGH"], [3]), ([b"XXXXXXXXXXXX"], [1]):
+        p = pack(seqs, funcs)
+        gpu.set_proteins(p)
+        got = gpu.build()
+        want, _ = oracle.oracle_build(p)
+        assert_tables_equal(got, want, what=f"{seqs}")
+        assert got.n_kept == 0
+
+
+@pytest.mark.parametrize("seed,kw", [
+    (11, dict(n_families=30, members=(1, 9), length=(5, 120))),
+    (12, dict(n_families=8, members=(20, 60), length=(30, 200), sub_rate=0.02, alphabet=b"ACDE")),     # big groups, P^2 active
+    (13, dict(n_families=200, members=(1, 20), length=(8, 400), sub_rate=0.15, n_functions=17)),         # mixed functions
+    (14, dict(n_families=3, members=(300, 400), length=(300, 330), sub_rate=0.01, ambig_rate=0.0)),      # sums wrap, groups > 255
+])
+def test_full_build_matches_oracle(gpu, oracle, seed, kw):
+    seqs, funcs = random_proteins(seed, **kw)
+    p = pack(seqs, funcs)
+    gpu.set_proteins(p)
+    got = gpu.build()
+    want, _ = oracle.oracle_build(p)
+    assert_tables_equal(got, want, tier_b=True, what=f"seed {seed}")
+    # rows are sorted by k-mer bytes and unique
+    k = got.kmer_strings()
+    assert k == sorted(k) and len(set(k)) == len(k)
+
+
+def test_seq_id_collisions_and_gaps(gpu, oracle):
+    seqs, funcs = random_proteins(21, n_families=20, members=(1, 6), length=(20, 90))
+    sid = (np.arange(len(seqs)) // 2 * 1000).astype(np.uint32)       # pairs share an id, ids are sparse
+    p = pack(seqs, funcs, sid)
+    gpu.set_proteins(p)
+    got = gpu.build()
+    want, _ = oracle.oracle_build(p)
+    assert_tables_equal(got, want)
+
+
+def test_medium_build_many_tiles(gpu, oracle):
+    # ~3 M occurrences: several hundred sort tiles, look-back chains across waves
+    seqs, funcs = random_proteins(31, n_families=400, members=(10, 40), length=(200, 500), sub_rate=0.12, n_functions=300)
+    p = pack(seqs, funcs)
+    gpu.set_proteins(p)
+    got = gpu.build()
+    want, _ = oracle.oracle_build(p, n_threads=1)
+    assert got.n_occurrences > 2_000_000
+    assert_tables_equal(got, want, tier_b=True)
+    # idempotence: a second build on the same handle gives the same table
+    again = gpu.build()
+    assert_tables_equal(got, again)
+
+
+def test_split_calls_equal_one_call(gpu):
+    seqs, funcs = random_proteins(41, n_families=50, members=(2, 10), length=(50, 150))
+    p = pack(seqs, funcs)
+    gpu.set_proteins(p)
+    a = gpu.build()
+    gpu.upload(); gpu.build_device(); gpu.build_device(); gpu.download()
+    assert_tables_equal(a, gpu.result())
