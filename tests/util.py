@@ -30,7 +30,7 @@ def random_proteins(seed: int, n_families: int = 12, members=(1, 9), length=(5, 
             s[amb] = np.frombuffer(AMBIG, dtype=np.uint8)[rng.integers(0, len(AMBIG), int(amb.sum()))]
             low = rng.random(L) < lower_rate
             s[low] = s[low] | 0x20
-            if rng.random() < 0.3:  # indel: drop a run of residues (ragged lengths inside a family)
+            if L > 0 and rng.random() < 0.3:  # indel: drop a run of residues (ragged lengths inside a family)
                 cut = int(rng.integers(0, L))
                 s = np.delete(s, slice(cut, cut + int(rng.integers(1, 12))))
             seqs.append(s.tobytes())
