@@ -155,6 +155,12 @@ int sigk_download(sigk_handle *h);
 int sigk_result(sigk_handle *h, sigk_table *out);
 int sigk_get_timings(const sigk_handle *h, sigk_timings *out);
 
+/* The library enqueues on its own stream; these let a caller bracket any
+ * number of sigk_build_device calls with CUDA events on that stream.        */
+int sigk_synchronize(sigk_handle *h);
+int sigk_event_record(sigk_handle *h, int slot /* 0..3 */);
+int sigk_event_elapsed_ms(sigk_handle *h, int slot_a, int slot_b, float *ms);
+
 /* Multi-GPU (one process per GPU): rank 0 makes an id, the launcher ships the
  * 128 bytes to every rank, every rank joins.  After that sigk_build routes
  * each record to the rank that owns its k-mer range (one all-to-all) and

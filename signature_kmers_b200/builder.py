@@ -72,6 +72,25 @@ class GpuSignatureBuilder:
         return dict(n_kept=int(t.n_kept), n_occurrences=int(t.n_occurrences), n_distinct_kmers=int(t.n_distinct_kmers),
                     num_seqs_with_a_signature=int(t.num_seqs_with_a_signature))
 
+    def synchronize(self):
+        self._check(self.lib.sigk_synchronize(self.h), "sigk_synchronize")
+
+    def event_record(self, slot: int):
+        self._check(self.lib.sigk_event_record(self.h, slot), "sigk_event_record")
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        self._check(self.lib.sigk_event_elapsed_ms(self.h, a, b, C.byref(ms)), "sigk_event_elapsed_ms")
+        return float(ms.value)
+
+    def host_alloc(self, nbytes: int) -> np.ndarray:
+        """Pinned host buffer as a uint8 numpy array (freed with the process)."""
+        ptr = self.lib.sigk_host_alloc(max(1, nbytes))
+        if not ptr:
+            raise SigkError("sigk_host_alloc failed")
+        buf = (C.c_uint8 * max(1, nbytes)).from_address(ptr)
+        return np.frombuffer(buf, dtype=np.uint8, count=nbytes)
+
     def timings(self) -> dict:
         t = SigkTimings()
         self._check(self.lib.sigk_get_timings(self.h, C.byref(t)), "sigk_get_timings")

@@ -226,6 +226,9 @@ EXPORTED_SYMBOLS = [
     "sigk_download",
     "sigk_result",
     "sigk_get_timings",
+    "sigk_synchronize",
+    "sigk_event_record",
+    "sigk_event_elapsed_ms",
     "sigk_comm_make_id",
     "sigk_comm_join",
     "sigk_dbg_encode",
@@ -271,6 +274,9 @@ def load_library(path: str | None = None) -> C.CDLL:
         getattr(lib, name).restype = C.c_int
     lib.sigk_result.argtypes = [C.c_void_p, C.POINTER(SigkTable)]
     lib.sigk_get_timings.argtypes = [C.c_void_p, C.POINTER(SigkTimings)]
+    lib.sigk_synchronize.argtypes = [C.c_void_p]
+    lib.sigk_event_record.argtypes = [C.c_void_p, C.c_int]
+    lib.sigk_event_elapsed_ms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
     lib.sigk_comm_make_id.argtypes = [C.c_void_p]
     lib.sigk_comm_join.argtypes = [C.c_void_p, C.c_void_p]
     lib.sigk_dbg_encode.argtypes = [

@@ -146,14 +146,6 @@ encode_kernel(EncodeArgs a, uint64_t *__restrict__ keys, uint32_t *__restrict__ 
     }
 }
 
-__global__ void protein_meta_kernel(const uint64_t *__restrict__ starts, const uint16_t *__restrict__ func, uint32_t n_prot,
-                                    uint32_t *__restrict__ len_out, uint32_t *__restrict__ seqs_with_func) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_prot) return;
-    len_out[i] = (uint32_t)(starts[i + 1] - starts[i]);     // static_cast<unsigned int>(seq.length()), tcc:178
-    atomicAdd(seqs_with_func + func[i], 1u);                // kmer_stats_.seqs_with_func[function_index]++, tcc:160
-}
-
 }  // namespace
 
 cudaError_t launch_encode(const EncodeArgs &a, uint64_t *keys, uint32_t *vals, uint64_t *scan_state,
@@ -167,13 +159,6 @@ cudaError_t launch_encode(const EncodeArgs &a, uint64_t *keys, uint32_t *vals, u
     }
     const uint64_t tiles = encode_tiles(a.total_res);
     encode_kernel<<<(unsigned)tiles, ENC_THREADS, sizeof(EncSmem), stream>>>(a, keys, vals, scan_state, ticket, n_out);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_protein_meta(const uint64_t *starts, const uint16_t *func, uint32_t n_prot, uint32_t *len_out,
-                                uint32_t *seqs_with_func, cudaStream_t stream) {
-    if (n_prot == 0) return cudaSuccess;
-    protein_meta_kernel<<<(n_prot + 255) / 256, 256, 0, stream>>>(starts, func, n_prot, len_out, seqs_with_func);
     return cudaGetLastError();
 }
 

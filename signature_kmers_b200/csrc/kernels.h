@@ -30,9 +30,6 @@ inline uint64_t encode_tiles(uint64_t total_res) { return (total_res + ENC_TILE 
 cudaError_t launch_encode(const EncodeArgs &a, uint64_t *keys, uint32_t *vals, uint64_t *scan_state,
                           uint32_t *ticket, uint64_t *n_out, cudaStream_t stream);
 
-// seqs_with_func[f]++ per protein (src/signature_build.tcc:160) and len[i] = starts[i+1]-starts[i].
-cudaError_t launch_protein_meta(const uint64_t *starts, const uint16_t *func, uint32_t n_prot,
-                                uint32_t *len_out, uint32_t *seqs_with_func, cudaStream_t stream);
 
 // ---- stage 2: onesweep LSD radix sort (onesweep.cu) ------------------------
 constexpr int SORT_MAX_PASSES = 8;
@@ -61,34 +58,36 @@ cudaError_t launch_onesweep_pass(const uint64_t *keys_in, const uint32_t *vals_i
                                  const uint64_t *bin_base, void *lookback, uint32_t *ticket, cudaStream_t stream);
 cudaError_t onesweep_configure();   // opt in to the dynamic shared memory the pass kernel needs
 
-// ---- stages 3+4: segment reduce, keep/reject, compaction (reduce.cu) -------
-struct ProteinMeta {
-    const uint16_t *func;      // [n_prot_global]
-    const uint32_t *len;       // [n_prot_global]
-    const uint32_t *seq_id;    // [n_prot_global]
-};
-
+// ---- stages 3+4: segment reduce, keep/reject, compaction, order statistics (reduce.cu)
 struct KeptColumns {           // device, capacity rows each
     uint64_t *kmer;            // 8 ASCII bytes per row
     uint16_t *avg_from_end, *function_index, *mean, *median, *var;
 };
+struct OrderWork { uint32_t row, start, count; };   // kept group whose median/var need the ordered walk
 
-constexpr int SEG_TILE = 4096;     // records per CTA in the head scan
-constexpr int CMP_TILE = 2048;     // segments per CTA in the compaction
-inline uint64_t seg_tiles(uint64_t capacity) { return (capacity + SEG_TILE - 1) / SEG_TILE; }
-inline uint64_t cmp_tiles(uint64_t capacity) { return (capacity + CMP_TILE - 1) / CMP_TILE; }
+constexpr int REDUCE_TILE = 2048;   // records per CTA of the fused reduce
+inline uint64_t reduce_tiles(uint64_t capacity) { return (capacity + REDUCE_TILE - 1) / REDUCE_TILE; }
+size_t reduce_side_entries(uint64_t capacity);    // uint4 entries of the giant side table
+size_t reduce_giant_entries(uint64_t capacity);   // 8-byte entries of the giant list
+size_t reduce_work_entries(uint64_t capacity);    // OrderWork entries
+cudaError_t reduce_configure();
 
-// Run-length pass: seg_start[s] = index of the first record of k-mer group s.
-cudaError_t launch_segment_heads(const uint64_t *keys, const uint64_t *n_ptr, uint64_t capacity, uint32_t *seg_start,
-                                 uint64_t *scan_state, uint32_t *ticket, uint64_t *n_seg_out, cudaStream_t stream);
-// Per-group tally, 80 % rule, offset median, length statistics (one thread per group).
-cudaError_t launch_segment_process(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr,
-                                   const uint32_t *seg_start, const uint64_t *n_seg_ptr, uint64_t capacity,
-                                   ProteinMeta meta, int order_stats, uint4 *seg_rows, uint32_t *seq_bitmap,
-                                   uint32_t *distinct_functions, cudaStream_t stream);
-// Keep/compact: kept groups -> table columns in k-mer order.
-cudaError_t launch_compact_rows(const uint4 *seg_rows, const uint64_t *n_seg_ptr, uint64_t capacity, KeptColumns out,
-                                uint64_t *scan_state, uint32_t *ticket, uint64_t *n_kept_out, cudaStream_t stream);
+// meta[i] = {protein_length, seq_id, function_index, 0}; seqs_with_func[f]++ (src/signature_build.tcc:160)
+cudaError_t launch_protein_meta(const uint64_t *starts, const uint16_t *func, const uint32_t *seq_id, uint32_t n_prot,
+                                uint4 *meta, uint32_t *seqs_with_func, cudaStream_t stream);
+// Pre-pass: groups of >= 513 records (found by sampling) are reduced ahead of the ordered kernel.
+cudaError_t launch_giant_prepass(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
+                                 const uint4 *meta, void *giant_list, uint32_t *n_giant, uint32_t *next_giant,
+                                 uint4 *giant_side, uint32_t *bitmap, int sm_count, cudaStream_t stream);
+// Run-length + per-group reduce + keep/reject + ordered compaction in one pass over the sorted records.
+cudaError_t launch_fused_reduce(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
+                                const uint4 *meta, const uint4 *giant_side, KeptColumns out, OrderWork *work,
+                                uint32_t *n_work, uint32_t *bitmap, uint32_t *distinct_functions, uint64_t *scan_state,
+                                uint32_t *ticket, uint64_t *n_kept_out, uint64_t *n_seg_out, int order_stats,
+                                cudaStream_t stream);
+// median / var columns of the kept groups listed in `work`.
+cudaError_t launch_order_stats(const uint32_t *vals, const uint4 *meta, const OrderWork *work, const uint32_t *n_work,
+                               uint64_t capacity, KeptColumns out, int sm_count, cudaStream_t stream);
 cudaError_t launch_popcount(const uint32_t *bitmap, uint64_t n_words, uint64_t *out, cudaStream_t stream);
 
 }  // namespace sigk

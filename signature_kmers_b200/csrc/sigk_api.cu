@@ -28,9 +28,10 @@ struct DeviceScalars {
     uint64_t n_kept;
     uint64_t n_seqs_sig;
     uint32_t ticket[16];
+    uint32_t n_giant, next_giant, n_work, pad;
 };
 
-enum { TK_ENCODE = 0, TK_HEADS = 1, TK_COMPACT = 2, TK_SORT0 = 4 };
+enum { TK_ENCODE = 0, TK_REDUCE = 1, TK_SORT0 = 4 };
 
 template <typename T> struct DevBuf {
     T *p = nullptr;
@@ -58,7 +59,7 @@ template <typename T> struct PinnedBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-enum { EV_START, EV_H2D, EV_DEV0, EV_ENCODE, EV_HIST, EV_SORT, EV_REDUCE, EV_D2H, EV_PASS0, EV_COUNT = EV_PASS0 + SORT_MAX_PASSES + 1 };
+enum { EV_START, EV_H2D, EV_DEV0, EV_ENCODE, EV_HIST, EV_SORT, EV_REDUCE, EV_ORDER, EV_D2H, EV_USER0, EV_USER1, EV_USER2, EV_USER3, EV_PASS0, EV_COUNT = EV_PASS0 + SORT_MAX_PASSES + 1 };
 
 }  // namespace
 
@@ -77,13 +78,14 @@ struct sigk_handle {
     DevBuf<uint8_t> d_res;
     DevBuf<uint64_t> d_starts;
     DevBuf<uint16_t> d_func;
-    DevBuf<uint32_t> d_seqid, d_len;
+    DevBuf<uint32_t> d_seqid;
+    DevBuf<uint4> d_meta, d_giant_side;
+    DevBuf<uint64_t> d_giant_list;
+    DevBuf<OrderWork> d_work;
     DevBuf<uint64_t> d_keys[2];
     DevBuf<uint32_t> d_vals[2];
     DevBuf<uint8_t> d_lookback;
     DevBuf<uint64_t> d_hist, d_binbase, d_scan_state;
-    DevBuf<uint32_t> d_seg_start;
-    DevBuf<uint4> d_seg_rows;
     DevBuf<uint64_t> d_out_kmer;
     DevBuf<uint16_t> d_out_cols;       // 5 columns of capacity rows
     DevBuf<uint32_t> d_bitmap, d_distinct, d_swf;
@@ -141,17 +143,18 @@ int do_upload(sigk_handle *h) {
     CU(h, h->d_starts.reserve(np + 1));
     CU(h, h->d_func.reserve(np));
     CU(h, h->d_seqid.reserve(np));
-    CU(h, h->d_len.reserve(np));
+    CU(h, h->d_meta.reserve(np));
     // one record per residue position is the ceiling (every window valid)
     const uint64_t cap = total;
     if (cap > h->capacity) {
         for (int i = 0; i < 2; ++i) { CU(h, h->d_keys[i].reserve(cap)); CU(h, h->d_vals[i].reserve(cap)); }
-        CU(h, h->d_lookback.reserve(onesweep_lookback_bytes(cap)));
-        CU(h, h->d_seg_start.reserve(cap));
-        CU(h, h->d_seg_rows.reserve(cap));
+        CU(h, h->d_lookback.reserve(onesweep_lookback_bytes(cap) * SORT_MAX_PASSES));
+        CU(h, h->d_giant_side.reserve(reduce_side_entries(cap)));
+        CU(h, h->d_giant_list.reserve(reduce_giant_entries(cap)));
+        CU(h, h->d_work.reserve(reduce_work_entries(cap)));
         CU(h, h->d_out_kmer.reserve(cap));
         CU(h, h->d_out_cols.reserve(cap * 5));
-        const uint64_t tiles = std::max({encode_tiles(padded), seg_tiles(cap), cmp_tiles(cap)}) + 1;
+        const uint64_t tiles = std::max(encode_tiles(padded), reduce_tiles(cap)) + 1;
         CU(h, h->d_scan_state.reserve(tiles));
         h->capacity = cap;
     }
@@ -199,7 +202,7 @@ int do_build_device(sigk_handle *h) {
     CU(h, cudaMemsetAsync(h->d_hist.p, 0, SORT_MAX_PASSES * SIGK_RADIX * sizeof(uint64_t), st));
 
     // ---- stage 1: encode
-    CU(h, launch_protein_meta(h->d_starts.p, h->d_func.p, (uint32_t)np, h->d_len.p, h->d_swf.p, st)); ++launches;
+    CU(h, launch_protein_meta(h->d_starts.p, h->d_func.p, h->d_seqid.p, (uint32_t)np, h->d_meta.p, h->d_swf.p, st)); ++launches;
     CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, (encode_tiles(h->total_res) + 1) * sizeof(uint64_t), st));
     EncodeArgs ea{h->d_res.p, h->total_res, h->d_starts.p, (uint32_t)np, 0u};
     CU(h, launch_encode(ea, h->d_keys[0].p, h->d_vals[0].p, h->d_scan_state.p, sc->ticket + TK_ENCODE, &sc->n_records, st)); ++launches;
@@ -212,12 +215,12 @@ int do_build_device(sigk_handle *h) {
     CU(h, cudaEventRecord(h->ev[EV_HIST], st));
     int cur = 0;
     const size_t lb_bytes = onesweep_lookback_bytes(cap);
+    CU(h, cudaMemsetAsync(h->d_lookback.p, 0, lb_bytes * h->plan.npass, st));
     for (int p = 0; p < h->plan.npass; ++p) {
         CU(h, cudaEventRecord(h->ev[EV_PASS0 + p], st));
-        CU(h, cudaMemsetAsync(h->d_lookback.p, 0, lb_bytes, st));
         CU(h, launch_onesweep_pass(h->d_keys[cur].p, h->d_vals[cur].p, h->d_keys[cur ^ 1].p, h->d_vals[cur ^ 1].p,
                                    &sc->n_records, cap, h->plan.lo[p], h->plan.bits[p],
-                                   h->d_binbase.p + (size_t)p * SIGK_RADIX, h->d_lookback.p, sc->ticket + TK_SORT0 + p, st));
+                                   h->d_binbase.p + (size_t)p * SIGK_RADIX, h->d_lookback.p + lb_bytes * p, sc->ticket + TK_SORT0 + p, st));
         ++launches;
         cur ^= 1;
     }
@@ -225,20 +228,21 @@ int do_build_device(sigk_handle *h) {
     CU(h, cudaEventRecord(h->ev[EV_SORT], st));
     h->sorted_in = cur;
 
-    // ---- stages 3+4: run-length, reduce, keep/reject, compact
-    CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, (seg_tiles(cap) + 1) * sizeof(uint64_t), st));
-    CU(h, launch_segment_heads(h->d_keys[cur].p, &sc->n_records, cap, h->d_seg_start.p, h->d_scan_state.p,
-                               sc->ticket + TK_HEADS, &sc->n_segments, st)); ++launches;
-    ProteinMeta meta{h->d_func.p, h->d_len.p, h->d_seqid.p};
+    // ---- stages 3+4: run-length, reduce, keep/reject, compact; then the order-dependent columns
+    CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, (reduce_tiles(cap) + 1) * sizeof(uint64_t), st));
+    CU(h, cudaMemsetAsync(h->d_giant_side.p, 0, reduce_side_entries(cap) * sizeof(uint4), st));
     const int order_stats = (h->cfg.flags & SIGK_F_NO_ORDER_STATS) ? 0 : 1;
-    CU(h, launch_segment_process(h->d_keys[cur].p, h->d_vals[cur].p, &sc->n_records, h->d_seg_start.p, &sc->n_segments,
-                                 cap, meta, order_stats, h->d_seg_rows.p, h->d_bitmap.p, h->d_distinct.p, st)); ++launches;
-    CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, (cmp_tiles(cap) + 1) * sizeof(uint64_t), st));
     KeptColumns kc{h->d_out_kmer.p, out_col(h, 0), out_col(h, 1), out_col(h, 2), out_col(h, 3), out_col(h, 4)};
-    CU(h, launch_compact_rows(h->d_seg_rows.p, &sc->n_segments, cap, kc, h->d_scan_state.p, sc->ticket + TK_COMPACT,
-                              &sc->n_kept, st)); ++launches;
+    CU(h, launch_giant_prepass(h->d_keys[cur].p, h->d_vals[cur].p, &sc->n_records, cap, h->d_meta.p, h->d_giant_list.p,
+                               &sc->n_giant, &sc->next_giant, h->d_giant_side.p, h->d_bitmap.p, h->sm_count, st));
+    launches += cap > 512 ? 2 : 0;
+    CU(h, launch_fused_reduce(h->d_keys[cur].p, h->d_vals[cur].p, &sc->n_records, cap, h->d_meta.p, h->d_giant_side.p, kc,
+                              h->d_work.p, &sc->n_work, h->d_bitmap.p, h->d_distinct.p, h->d_scan_state.p,
+                              sc->ticket + TK_REDUCE, &sc->n_kept, &sc->n_segments, order_stats, st)); ++launches;
     CU(h, launch_popcount(h->d_bitmap.p, ((uint64_t)h->max_seq_id >> 5) + 1, &sc->n_seqs_sig, st)); ++launches;
     CU(h, cudaEventRecord(h->ev[EV_REDUCE], st));
+    if (order_stats) { CU(h, launch_order_stats(h->d_vals[cur].p, h->d_meta.p, h->d_work.p, &sc->n_work, cap, kc, h->sm_count, st)); ++launches; }
+    CU(h, cudaEventRecord(h->ev[EV_ORDER], st));
 
     h->tm.kernel_launches = launches;
     h->built = true;
@@ -281,8 +285,9 @@ int do_download(sigk_handle *h) {
     t.histogram_ms = ms(EV_ENCODE, EV_HIST);
     t.sort_ms = ms(EV_HIST, EV_SORT);
     t.reduce_ms = ms(EV_SORT, EV_REDUCE);
-    t.d2h_ms = ms(EV_REDUCE, EV_D2H);
-    t.device_total_ms = ms(EV_DEV0, EV_REDUCE);
+    t.order_stats_ms = ms(EV_REDUCE, EV_ORDER);
+    t.d2h_ms = ms(EV_ORDER, EV_D2H);
+    t.device_total_ms = ms(EV_DEV0, EV_ORDER);
     t.sort_passes = (uint32_t)h->plan.npass;
     t.record_bytes = 12;
     t.key_bytes = 8;
@@ -325,7 +330,7 @@ int sigk_create(const sigk_config *cfg, sigk_handle **out) {
     }
     for (auto &ev : h->ev) cudaEventCreate(&ev);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
-    if ((e = onesweep_configure()) != cudaSuccess) {
+    if ((e = onesweep_configure()) != cudaSuccess || (e = reduce_configure()) != cudaSuccess) {
         g_create_error = std::string("kernel configuration failed (is this an sm_100a device?): ") + cudaGetErrorString(e);
         sigk_destroy(h);
         return SIGK_E_CUDA;
@@ -338,10 +343,10 @@ void sigk_destroy(sigk_handle *h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    h->d_res.release(); h->d_starts.release(); h->d_func.release(); h->d_seqid.release(); h->d_len.release();
+    h->d_res.release(); h->d_starts.release(); h->d_func.release(); h->d_seqid.release(); h->d_meta.release();
     for (int i = 0; i < 2; ++i) { h->d_keys[i].release(); h->d_vals[i].release(); }
     h->d_lookback.release(); h->d_hist.release(); h->d_binbase.release(); h->d_scan_state.release();
-    h->d_seg_start.release(); h->d_seg_rows.release(); h->d_out_kmer.release(); h->d_out_cols.release();
+    h->d_giant_side.release(); h->d_giant_list.release(); h->d_work.release(); h->d_out_kmer.release(); h->d_out_cols.release();
     h->d_bitmap.release(); h->d_distinct.release(); h->d_swf.release(); h->d_scalars.release();
     h->h_kmer.release(); h->h_cols.release(); h->h_distinct.release(); h->h_swf.release(); h->h_scalars.release();
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
@@ -418,6 +423,29 @@ int sigk_result(sigk_handle *h, sigk_table *out) {
 int sigk_get_timings(const sigk_handle *h, sigk_timings *out) {
     if (!h || !out) return SIGK_E_INVALID;
     *out = h->tm;
+    return SIGK_OK;
+}
+
+int sigk_synchronize(sigk_handle *h) {
+    if (!h) return SIGK_E_INVALID;
+    if (int rc = ensure_device(h)) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return SIGK_OK;
+}
+
+int sigk_event_record(sigk_handle *h, int slot) {
+    if (!h) return SIGK_E_INVALID;
+    if (slot < 0 || slot > 3) return h->fail(SIGK_E_INVALID, "event slot must be 0..3");
+    if (int rc = ensure_device(h)) return rc;
+    CU(h, cudaEventRecord(h->ev[EV_USER0 + slot], h->stream));
+    return SIGK_OK;
+}
+
+int sigk_event_elapsed_ms(sigk_handle *h, int slot_a, int slot_b, float *ms) {
+    if (!h) return SIGK_E_INVALID;
+    if (slot_a < 0 || slot_a > 3 || slot_b < 0 || slot_b > 3 || !ms) return h->fail(SIGK_E_INVALID, "bad event slots");
+    CU(h, cudaEventSynchronize(h->ev[EV_USER0 + slot_b]));
+    CU(h, cudaEventElapsedTime(ms, h->ev[EV_USER0 + slot_a], h->ev[EV_USER0 + slot_b]));
     return SIGK_OK;
 }
 

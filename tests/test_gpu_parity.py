@@ -153,3 +153,61 @@ def test_split_calls_equal_one_call(gpu):
     a = gpu.build()
     gpu.upload(); gpu.build_device(); gpu.build_device(); gpu.download()
     assert_tables_equal(a, gpu.result())
+
+
+def test_long_and_giant_groups(gpu, oracle):
+    """Groups of 33 .. >1024 records (whole-warp walks, the sampled giant pre-pass),
+    mixed functions inside long groups, lengths that differ so P^2 and the
+    variance recurrence run for thousands of samples."""
+    seqs, funcs = [], []
+    # one homopolymer per size: a run of L identical residues gives L-7 windows of one k-mer
+    for letter, k in zip("WYFHKMNQ", (33, 64, 512, 513, 1023, 1024, 1025, 3000)):
+        seqs.append(letter * (k + 7)); funcs.append(1)
+    # a giant shared by many proteins of different lengths, 90 % one function
+    rng = np.random.default_rng(3)
+    for i in range(60):
+        seqs.append("A" * int(rng.integers(200, 2500))); funcs.append(0 if i % 10 else 2)
+    # a long group that is rejected (60/40)
+    for i in range(50):
+        seqs.append("C" * 40 + "DEFGHIKL"); funcs.append(3 if i % 5 < 3 else 4)
+    # filler so that groups straddle chunk and tile boundaries at odd places
+    fs, ff = random_proteins(77, n_families=40, members=(2, 12), length=(30, 200))
+    seqs += [x.decode() for x in fs]; funcs += [5 + f for f in ff]
+    p = pack(seqs, funcs)
+    gpu.set_proteins(p)
+    got = gpu.build()
+    want, _ = oracle.oracle_build(p)
+    assert_tables_equal(got, want, tier_b=True)
+    assert got.row("AAAAAAAA") is not None and got.row("CCCCCCCC") is None
+    assert got.row("WWWWWWWW")["avg_from_end"] == want.row("WWWWWWWW")["avg_from_end"]
+
+
+@pytest.mark.parametrize("seed", [51, 52, 53])
+def test_boundary_alignment_sweep(gpu, oracle, seed):
+    """Many small inputs whose group boundaries fall on every alignment of the
+    32-record windows, 256-record chunks and 2048-record tiles."""
+    rng = np.random.default_rng(seed)
+    for _ in range(6):
+        seqs, funcs = random_proteins(int(rng.integers(1 << 30)), n_families=int(rng.integers(1, 30)), members=(1, 40),
+                                      length=(8, 120), sub_rate=float(rng.choice([0.0, 0.02, 0.2])), alphabet=b"ACDEFG",
+                                      n_functions=int(rng.integers(1, 6)))
+        p = pack(seqs, funcs)
+        gpu.set_proteins(p)
+        got = gpu.build()
+        want, _ = oracle.oracle_build(p)
+        assert_tables_equal(got, want, tier_b=True)
+
+
+def test_no_order_stats_flag(oracle):
+    from signature_kmers_b200 import capi
+    from signature_kmers_b200.builder import GpuSignatureBuilder
+
+    seqs, funcs = random_proteins(61, n_families=20, members=(2, 30), length=(30, 200), sub_rate=0.05)
+    p = pack(seqs, funcs)
+    b = GpuSignatureBuilder(device=0, flags=capi.SIGK_F_NO_ORDER_STATS)
+    b.set_proteins(p)
+    got = b.build()
+    want, _ = oracle.oracle_build(p)
+    assert_tables_equal(got, want, tier_b=False)
+    assert not got.median.any() and not got.var.any()
+    b.close()
