@@ -117,8 +117,9 @@ typedef struct sigk_timings {
     float encode_ms;        /* count + encode (+ first radix pass when fused) */
     float histogram_ms;
     float sort_ms;          /* all onesweep passes */
-    float reduce_ms;        /* segment reduce + keep/compact */
-    float order_stats_ms;   /* tier-B median/var worklist */
+    float reduce_ms;        /* giant pre-pass + streaming segment reduce + keep/reject */
+    float order_stats_ms;   /* median/var worklist */
+    float squeeze_ms;       /* ordered compaction of kept rows into the table columns */
     float exchange_ms;      /* multi-GPU partition + all-to-all */
     float d2h_ms;
     float device_total_ms;  /* first kernel start -> last kernel end */

@@ -47,10 +47,11 @@ class GpuSignatureBuilder:
         st = p.as_struct()
         self._check(self.lib.sigk_set_proteins(self.h, C.byref(st)), "sigk_set_proteins")
 
-    def build(self) -> KeptTable:
-        """extract_kmers + process_kmers: host arrays in, kept table out."""
+    def build(self, fetch: bool = True):
+        """extract_kmers + process_kmers: host arrays in, kept table out (in host memory
+        owned by the handle; fetch=True also copies it into numpy arrays)."""
         self._check(self.lib.sigk_build(self.h), "sigk_build")
-        return self.result()
+        return self.result() if fetch else None
 
     def upload(self):
         self._check(self.lib.sigk_upload(self.h), "sigk_upload")

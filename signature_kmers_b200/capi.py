@@ -71,6 +71,7 @@ class SigkTimings(C.Structure):
         ("sort_ms", C.c_float),
         ("reduce_ms", C.c_float),
         ("order_stats_ms", C.c_float),
+        ("squeeze_ms", C.c_float),
         ("exchange_ms", C.c_float),
         ("d2h_ms", C.c_float),
         ("device_total_ms", C.c_float),

@@ -65,29 +65,35 @@ struct KeptColumns {           // device, capacity rows each
 };
 struct OrderWork { uint32_t row, start, count; };   // kept group whose median/var need the ordered walk
 
-constexpr int REDUCE_TILE = 2048;   // records per CTA of the fused reduce
-inline uint64_t reduce_tiles(uint64_t capacity) { return (capacity + REDUCE_TILE - 1) / REDUCE_TILE; }
-size_t reduce_side_entries(uint64_t capacity);    // uint4 entries of the giant side table
-size_t reduce_giant_entries(uint64_t capacity);   // 8-byte entries of the giant list
-size_t reduce_work_entries(uint64_t capacity);    // OrderWork entries
+constexpr int RED_BATCH = 2048;     // sorted records one warp takes per ticket in the streaming reduce
+inline uint64_t reduce_batches(uint64_t capacity) { return (capacity + RED_BATCH - 1) / RED_BATCH; }
+inline uint64_t squeeze_tiles(uint64_t capacity) { return (capacity + 2047) / 2048; }
+inline uint64_t reduce_scan_entries(uint64_t capacity) { return reduce_batches(capacity) + squeeze_tiles(capacity) + 2; }
+size_t reduce_side_entries(uint64_t capacity);                 // uint4 entries of the giant side table
+size_t reduce_giant_entries(uint64_t capacity);                // 8-byte entries of the giant list
+size_t reduce_work_entries(uint64_t capacity, int sm_count);   // OrderWork entries
 cudaError_t reduce_configure();
 
 // meta[i] = {protein_length, seq_id, function_index, 0}; seqs_with_func[f]++ (src/signature_build.tcc:160)
 cudaError_t launch_protein_meta(const uint64_t *starts, const uint16_t *func, const uint32_t *seq_id, uint32_t n_prot,
                                 uint4 *meta, uint32_t *seqs_with_func, cudaStream_t stream);
-// Pre-pass: groups of >= 513 records (found by sampling) are reduced ahead of the ordered kernel.
+// Pre-pass: groups of >= 513 records (found by sampling) are reduced ahead of the streaming kernel.
 cudaError_t launch_giant_prepass(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
                                  const uint4 *meta, void *giant_list, uint32_t *n_giant, uint32_t *next_giant,
                                  uint4 *giant_side, uint32_t *bitmap, int sm_count, cudaStream_t stream);
-// Run-length + per-group reduce + keep/reject + ordered compaction in one pass over the sorted records.
-cudaError_t launch_fused_reduce(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
-                                const uint4 *meta, const uint4 *giant_side, KeptColumns out, OrderWork *work,
-                                uint32_t *n_work, uint32_t *bitmap, uint32_t *distinct_functions, uint64_t *scan_state,
-                                uint32_t *ticket, uint64_t *n_kept_out, uint64_t *n_seg_out, int order_stats,
-                                cudaStream_t stream);
-// median / var columns of the kept groups listed in `work`.
+// Run-length + per-group reduce + keep/reject in one pass over the sorted records: one packed row per
+// group in k-mer order (rejected groups leave a tombstone), plus the list of groups whose median/var
+// need the ordered walk.  scan_state: reduce_batches()+1 zeroed words.
+cudaError_t launch_stream_reduce(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
+                                 const uint4 *meta, const uint4 *giant_side, uint4 *rows, OrderWork *work, uint32_t *n_work,
+                                 uint32_t *bitmap, uint32_t *distinct_functions, uint64_t *scan_state, uint32_t *ticket,
+                                 uint64_t *n_seg_out, int order_stats, int sm_count, cudaStream_t stream);
+// median / var of the groups listed in `work`, patched into their rows.
 cudaError_t launch_order_stats(const uint32_t *vals, const uint4 *meta, const OrderWork *work, const uint32_t *n_work,
-                               uint64_t capacity, KeptColumns out, int sm_count, cudaStream_t stream);
+                               uint64_t capacity, uint4 *rows, int sm_count, cudaStream_t stream);
+// Compaction: kept rows -> table columns (tombstones dropped, order kept).  scan_state: squeeze_tiles()+1 zeroed words.
+cudaError_t launch_squeeze_rows(const uint4 *rows, const uint64_t *n_seg_ptr, uint64_t capacity, KeptColumns out,
+                                uint64_t *scan_state, uint32_t *ticket, uint64_t *n_kept_out, cudaStream_t stream);
 cudaError_t launch_popcount(const uint32_t *bitmap, uint64_t n_words, uint64_t *out, cudaStream_t stream);
 
 }  // namespace sigk

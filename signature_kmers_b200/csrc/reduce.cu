@@ -52,8 +52,12 @@ SIGK_D unsigned mask_range(unsigned lo, unsigned hi) {                     // bi
 
 SIGK_D bool keep_rule(uint32_t best_count, uint32_t count) {
     if (2ull * best_count <= count) return false;                          // no strict majority (see header)
-    const float thresh = __fmul_rn(__int2float_rn((int)count), 0.8f);      // tcc:250
-    return !(__int2float_rn((int)best_count) < thresh);                    // tcc:254
+    // reject iff (float)best_count < float(count) * 0.8f (tcc:250-257).  0.8*count is at least 0.2
+    // away from any integer it does not equal and the float product is off by < count * 6e-8, so
+    // below 2^20 the float test is exactly 5*best >= 4*count; above, run the float ops themselves.
+    if (count < (1u << 20)) return 5u * best_count >= 4u * count;
+    const float thresh = __fmul_rn(__int2float_rn((int)count), 0.8f);
+    return !(__int2float_rn((int)best_count) < thresh);
 }
 
 SIGK_D void mark_sequence(uint32_t *bitmap, uint32_t sid) {                // seqs_with_a_signature.insert, tcc:274
@@ -198,249 +202,335 @@ giant_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
     }
 }
 
-// ---- the fused streaming reduce ---------------------------------------------
-constexpr int RED_THREADS = 256;
-constexpr int RED_WARPS = RED_THREADS / 32;
-constexpr int RED_CHUNK = REDUCE_TILE / RED_WARPS;      // records per warp
+// ---- the streaming reduce ----------------------------------------------------
+// Persistent warps.  A warp takes a batch of RED_BATCH sorted records by ticket,
+// counts the group heads in it and publishes that count at once (chained scan
+// over batches), so later batches never wait for this one's work: every group,
+// kept or not, owns the row slot of its index, and rejected groups leave a
+// tombstone (function_index 0xFFFF) that squeeze_rows_kernel removes.
+//
+// rows[g] (uint4): x = code[31:0]; y = code[42:32] | avg_from_end << 11;
+//                  z = function_index | mean << 16; w = median | var << 16
+constexpr int RED_THREADS = 128;
+constexpr int WORK_BLOCK = 64;          // order-statistics work slots a warp reserves at a time
 
-struct RedSmem {
-    uint64_t code[RED_WARPS][RED_CHUNK];
-    uint32_t start[RED_WARPS][RED_CHUNK];
-    uint32_t count[RED_WARPS][RED_CHUNK];               // group size; bit 31: needs order statistics
-    uint16_t avg[RED_WARPS][RED_CHUNK];
-    uint16_t func[RED_WARPS][RED_CHUNK];
-    uint16_t mean[RED_WARPS][RED_CHUNK];
-    uint32_t warp_rows[RED_WARPS];
-    uint32_t warp_work[RED_WARPS];
-    uint32_t warp_segs[RED_WARPS];
-    uint32_t tile;
-    uint32_t work_base;
-    uint64_t base;
-};
+struct WorkCursor { uint32_t base, free; };
+
+SIGK_D void work_reserve(WorkCursor &wc, uint32_t need, OrderWork *__restrict__ work, uint32_t *__restrict__ n_work) {
+    const unsigned lane = threadIdx.x & 31u;
+    if (wc.free >= need) return;
+    for (uint32_t i = lane; i < wc.free; i += 32) work[wc.base + i] = OrderWork{0u, 0u, 0u};   // unused tail: count 0 = skip
+    uint32_t b = 0;
+    if (lane == 0) b = atomicAdd(n_work, (uint32_t)WORK_BLOCK);
+    wc.base = __shfl_sync(FULL, b, 0);
+    wc.free = WORK_BLOCK;
+}
 
 __global__ void __launch_bounds__(RED_THREADS)
-fused_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-                    const uint64_t *__restrict__ n_ptr, const uint4 *__restrict__ meta,
-                    const uint4 *__restrict__ giant_side, KeptColumns out, OrderWork *__restrict__ work,
-                    uint32_t *__restrict__ n_work, uint32_t *__restrict__ bitmap, uint32_t *__restrict__ distinct_functions,
-                    uint64_t *__restrict__ scan_state, uint32_t *__restrict__ ticket,
-                    uint64_t *__restrict__ n_kept_out, uint64_t *__restrict__ n_seg_out, int order_stats) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    RedSmem &sm = *reinterpret_cast<RedSmem *>(smem_raw);
-    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+stream_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                     const uint64_t *__restrict__ n_ptr, const uint4 *__restrict__ meta,
+                     const uint4 *__restrict__ giant_side, uint4 *__restrict__ rows, OrderWork *__restrict__ work,
+                     uint32_t *__restrict__ n_work, uint32_t *__restrict__ bitmap, uint32_t *__restrict__ distinct_functions,
+                     uint64_t *__restrict__ scan_state, uint32_t *__restrict__ ticket, uint64_t *__restrict__ n_seg_out,
+                     int order_stats) {
+    const unsigned lane = threadIdx.x & 31u;
     const uint64_t n = *n_ptr;
-    if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = sm.tile;
-    const uint64_t tile_start = (uint64_t)tile * REDUCE_TILE;
-    if (tile_start >= n) return;
+    WorkCursor wc{0u, 0u};
 
-    const uint64_t c0 = tile_start + (uint64_t)warp * RED_CHUNK;
-    const uint64_t c1 = (c0 + RED_CHUNK < n) ? c0 + RED_CHUNK : n;
-    uint32_t rows = 0, segs = 0, nwork = 0;
+    for (;;) {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(ticket, 1u);
+        t = __shfl_sync(FULL, t, 0);
+        const uint64_t b0 = (uint64_t)t * RED_BATCH;
+        if (b0 >= n) break;
+        const uint64_t b1 = (b0 + RED_BATCH < n) ? b0 + RED_BATCH : n;
 
-    // first group head at or after c0
-    uint64_t cur = c1;
-    for (uint64_t p0 = c0; p0 < c1; p0 += 32) {
-        const uint64_t p = p0 + lane;
-        bool head = false;
-        if (p < c1) head = (p == 0) || (sigk_key_code(__ldg(keys + p)) != sigk_key_code(__ldg(keys + p - 1)));   // kmer != cur, tcc:194
-        const unsigned hb = __ballot_sync(FULL, head);
-        if (hb) { cur = p0 + __ffs(hb) - 1; break; }
-    }
+        // ---- group heads of the batch: count, first head; publish the count
+        uint32_t hc = 0;
+        uint64_t cur = b1;
+        for (uint64_t p0 = b0; p0 < b1; p0 += 32) {
+            const uint64_t p = p0 + lane;
+            bool head = false;
+            if (p < b1) head = (p == 0) || (sigk_key_code(__ldg(keys + p)) != sigk_key_code(__ldg(keys + p - 1)));   // kmer != cur, tcc:194
+            const unsigned hb = __ballot_sync(FULL, head);
+            if (hb && cur == b1) cur = p0 + __ffs(hb) - 1;
+            hc += __popc(hb);
+        }
+        uint64_t g = chained_scan_exclusive_warp(scan_state, t, hc);        // index of the batch's first group
+        if (b1 == n && lane == 0) *n_seg_out = g + hc;
 
-    while (cur < c1) {
-        // ---- one window: records cur .. cur+31, cur is a group head
-        const uint64_t p = cur + lane;
-        const bool valid = p < n;
-        const uint64_t key = valid ? __ldg(keys + p) : 0ull;
-        const uint64_t code = sigk_key_code(key);
-        const uint64_t prev = __shfl_up_sync(FULL, code, 1);
-        const bool head = valid && (lane == 0 || code != prev);
-        unsigned H = __ballot_sync(FULL, head);
-        const unsigned V = __ballot_sync(FULL, valid);
-        // is the record after the window a head (or the end)?
-        uint64_t nxt = 0;
-        if (lane == 31) nxt = (cur + 32 < n) ? sigk_key_code(__ldg(keys + cur + 32)) : ~0ull;
-        const bool closed = __shfl_sync(FULL, (lane == 31) && (!valid || nxt != code), 31);
-        uint32_t wlen = __popc(V);
-        if (!closed) {
-            const int last = 31 - __clz(H);             // head of the group that runs past the window
-            if (last == 0) {
-                // ---- a group longer than 32 records: pre-reduced (giant) or walked now.
-                // At most one long group can have its head in a 32-record block, so a
-                // valid side entry under cur >> 5 is this group's.
-                SegResult r;
-                uint32_t glen;
-                const uint4 g = __ldg(giant_side + (cur >> 5));
-                if (g.x & 1u) {
-                    glen = g.z;
-                    r.keep = (g.x & 2u) != 0; r.func = g.y & 0xFFFFu; r.avg = g.y >> 16; r.mean = g.x >> 16; r.best_count = g.w;
-                } else {
-                    uint64_t e = cur + 32;              // the first 33 records are known to match
-                    for (;;) {
-                        const uint64_t q = e + lane;
-                        const bool same = q < n && sigk_key_code(__ldg(keys + q)) == code;
-                        const unsigned sb = __ballot_sync(FULL, same);
-                        if (sb != FULL) { e += (uint64_t)(__ffs(~sb) - 1); break; }
-                        e += 32;
+        while (cur < b1) {
+            // ---- one window: records cur .. cur+31, cur is a group head
+            const uint64_t p = cur + lane;
+            const bool valid = p < n;
+            const uint64_t key = valid ? __ldg(keys + p) : 0ull;
+            const uint64_t code = sigk_key_code(key);
+            const uint64_t prev = __shfl_up_sync(FULL, code, 1);
+            const bool head = valid && (lane == 0 || code != prev);
+            unsigned H = __ballot_sync(FULL, head);
+            const unsigned V = __ballot_sync(FULL, valid);
+            // is the record after the window a head (or the end)?
+            uint64_t nxt = 0;
+            if (lane == 31) nxt = (cur + 32 < n) ? sigk_key_code(__ldg(keys + cur + 32)) : ~0ull;
+            const bool closed = __shfl_sync(FULL, (lane == 31) && (!valid || nxt != code), 31);
+            uint32_t wlen = __popc(V);
+            if (!closed) {
+                const int last = 31 - __clz(H);         // head of the group that runs past the window
+                if (last == 0) {
+                    // ---- a group longer than 32 records: pre-reduced (giant) or walked now.
+                    // At most one long group can have its head in a 32-record block, so a
+                    // valid side entry under cur >> 5 is this group's.
+                    SegResult r;
+                    uint32_t glen;
+                    const uint4 gs = __ldg(giant_side + (cur >> 5));
+                    if (gs.x & 1u) {
+                        glen = gs.z;
+                        r.keep = (gs.x & 2u) != 0; r.func = gs.y & 0xFFFFu; r.avg = gs.y >> 16; r.mean = gs.x >> 16; r.best_count = gs.w;
+                    } else {
+                        uint64_t e = cur + 32;          // the first 33 records are known to match
+                        for (;;) {
+                            const uint64_t q = e + lane;
+                            const bool same = q < n && sigk_key_code(__ldg(keys + q)) == code;
+                            const unsigned sb = __ballot_sync(FULL, same);
+                            if (sb != FULL) { e += (uint64_t)(__ffs(~sb) - 1); break; }
+                            e += 32;
+                        }
+                        glen = (uint32_t)(e - cur);
+                        r = reduce_long_segment(keys, vals, meta, cur, glen, bitmap);
                     }
-                    glen = (uint32_t)(e - cur);
-                    r = reduce_long_segment(keys, vals, meta, cur, glen, bitmap);
+                    const bool walk = r.keep && order_stats;          // best_count >= 27 here
+                    if (walk) work_reserve(wc, 1u, work, n_work);
+                    if (lane == 0) {
+                        if (r.keep) {
+                            rows[g] = make_uint4((uint32_t)code, (uint32_t)(code >> 32) | (r.avg << 11), r.func | (r.mean << 16), 0u);
+                            atomicAdd(distinct_functions + r.func, 1u);                 // tcc:286
+                            if (walk) work[wc.base] = OrderWork{(uint32_t)g, (uint32_t)cur, glen};
+                        } else rows[g] = make_uint4(0u, 0u, 0xFFFFu, 0u);
+                    }
+                    if (walk) { wc.base += 1; wc.free -= 1; }
+                    g += 1;
+                    cur += glen;
+                    continue;
                 }
-                const uint64_t code0 = __shfl_sync(FULL, code, 0);
-                ++segs;
-                if (r.keep && lane == 0) {
-                    sm.code[warp][rows] = code0;
-                    sm.start[warp][rows] = (uint32_t)cur;
-                    sm.count[warp][rows] = glen | (r.best_count >= 2 ? 0x80000000u : 0u);
-                    sm.avg[warp][rows] = (uint16_t)r.avg;
-                    sm.func[warp][rows] = (uint16_t)r.func;
-                    sm.mean[warp][rows] = (uint16_t)r.mean;
-                    atomicAdd(distinct_functions + r.func, 1u);           // tcc:286
+                wlen = (uint32_t)last;                  // drop the unfinished group from this window
+                H &= mask_lt((unsigned)last);
+            }
+            // groups headed at or beyond b1 belong to the next batch
+            if (cur + wlen > b1) {
+                const unsigned beyond = H & ~mask_lt((unsigned)(b1 - cur));
+                if (beyond) { wlen = (uint32_t)(__ffs(beyond) - 1); H &= mask_lt(wlen); }
+            }
+            const bool act = lane < wlen;
+            const uint32_t ord = act ? __ldg(vals + p) : 0u;
+            const uint4 m = act ? __ldg(meta + ord) : make_uint4(0, 0, 0, 0);      // len, seq_id, func
+            const uint32_t f = m.z;
+            const uint32_t off = sigk_key_offset(key);
+
+            // my group's lanes
+            const unsigned s_lane = 31u - (unsigned)__clz(H & mask_le(lane));
+            const unsigned above = H & ~mask_le(lane);
+            const unsigned e_lane = above ? (unsigned)(__ffs(above) - 1) : wlen;
+            const uint32_t cnt = e_lane - s_lane;
+            const unsigned segmask = mask_range(s_lane, e_lane);
+
+            // function vote (func_count + arg-max, tcc:203, :228-248).  A group with two
+            // different functions and fewer than 5 records cannot reach 80 % (1/2, 2/3, 3/4),
+            // so the bit-sliced vote only runs when a mixed group has 5 or more records.
+            uint32_t cand = __shfl_sync(FULL, f, s_lane);
+            const bool mixed = (__ballot_sync(FULL, act && f != cand) & segmask) != 0;
+            if (__any_sync(FULL, act && mixed && cnt >= 5)) {
+                uint32_t c = 0;
+#pragma unroll
+                for (int b = 0; b < 16; ++b) {
+                    const unsigned bal = __ballot_sync(FULL, act && ((f >> b) & 1u)) & segmask;
+                    c |= (2u * (uint32_t)__popc(bal) > cnt ? 1u : 0u) << b;
                 }
-                if (r.keep) { ++rows; if (r.best_count >= 2) ++nwork; }
-                cur += glen;
-                continue;
+                if (mixed) cand = c;
             }
-            wlen = (uint32_t)last;                      // drop the unfinished group from this window
-            H &= mask_lt((unsigned)last);
-        }
-        // groups headed at or beyond c1 belong to the next chunk
-        if (cur + wlen > c1) {
-            const unsigned beyond = H & ~mask_lt((unsigned)(c1 - cur));
-            if (beyond) { wlen = (uint32_t)(__ffs(beyond) - 1); H &= mask_lt(wlen); }
-        }
-        const bool act = lane < wlen;
-        const uint32_t ord = act ? __ldg(vals + p) : 0u;
-        const uint4 m = act ? __ldg(meta + ord) : make_uint4(0, 0, 0, 0);      // len, seq_id, func
-        const uint32_t f = m.z;
-        const uint32_t off = sigk_key_offset(key);
+            const bool is_best = act && f == cand;
+            const unsigned best_mask = __ballot_sync(FULL, is_best) & segmask;
+            const uint32_t best_count = __popc(best_mask);
+            const bool keep = act && !(mixed && cnt < 5) && keep_rule(best_count, cnt);
 
-        // my group's lanes
-        const unsigned s_lane = 31u - (unsigned)__clz(H & mask_le(lane));
-        const unsigned above = H & ~mask_le(lane);
-        const unsigned e_lane = above ? (unsigned)(__ffs(above) - 1) : wlen;
-        const uint32_t cnt = e_lane - s_lane;
-        const unsigned segmask = mask_range(s_lane, e_lane);
-
-        // function vote (func_count + arg-max, tcc:203, :228-248)
-        uint32_t cand = __shfl_sync(FULL, f, s_lane);
-        if (!__all_sync(FULL, !act || f == cand)) {
-            uint32_t c = 0;
+            // avg_from_end: rank cnt/2 of the group's offsets (tcc:273, :281-282), radix select
+            // over the bits on which some group of the window disagrees
+            const uint32_t off_head = __shfl_sync(FULL, off, s_lane);
+            uint32_t vary = __reduce_or_sync(FULL, act ? (off ^ off_head) : 0u);
+            uint32_t sel = off & ~vary;
+            {
+                unsigned cm = segmask;
+                uint32_t rk = cnt >> 1;
+                while (vary) {
+                    const int b = 31 - __clz(vary);
+                    vary &= ~(1u << b);
+                    const unsigned onesb = __ballot_sync(FULL, act && ((off >> b) & 1u)) & cm;
+                    const unsigned zeros = cm & ~onesb;
+                    const uint32_t cz = __popc(zeros);
+                    if (rk < cz) cm = zeros;
+                    else { rk -= cz; cm = onesb; sel |= 1u << b; }
+                }
+            }
+            // sum of the best function's lengths mod 65536 (sum_impl<unsigned short>)
+            uint32_t x = is_best ? (m.x & 0xFFFFu) : 0u;
 #pragma unroll
-            for (int b = 0; b < 16; ++b) {
-                const unsigned bal = __ballot_sync(FULL, act && ((f >> b) & 1u)) & segmask;
-                c |= (2u * (uint32_t)__popc(bal) > cnt ? 1u : 0u) << b;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(FULL, x, o);
+                if (lane >= s_lane + (unsigned)o) x += y;
             }
-            cand = c;
-        }
-        const bool is_best = act && f == cand;
-        const unsigned best_mask = __ballot_sync(FULL, is_best) & segmask;
-        const uint32_t best_count = __popc(best_mask);
-        const bool keep = act && keep_rule(best_count, cnt);
-        const unsigned K = __ballot_sync(FULL, keep && head);
+            const uint32_t S = __shfl_sync(FULL, x, (e_lane - 1u) & 31u) & 0xFFFFu;
 
-        // avg_from_end: rank cnt/2 of the group's offsets (tcc:273, :281-282), radix select
-        // over the bits on which some group of the window disagrees
-        const uint32_t off_head = __shfl_sync(FULL, off, s_lane);
-        uint32_t vary = __reduce_or_sync(FULL, act ? (off ^ off_head) : 0u);
-        uint32_t sel = off & ~vary;
-        {
-            unsigned cm = segmask;
-            uint32_t rk = cnt >> 1;
-            while (vary) {
-                const int b = 31 - __clz(vary);
-                vary &= ~(1u << b);
-                const unsigned onesb = __ballot_sync(FULL, act && ((off >> b) & 1u)) & cm;
-                const unsigned zeros = cm & ~onesb;
-                const uint32_t cz = __popc(zeros);
-                if (rk < cz) cm = zeros;
-                else { rk -= cz; cm = onesb; sel |= 1u << b; }
+            // two best items: median stays 0 (heights[2] untouched) and the variance recurrence collapses to
+            // var = (x2 - S/2)^2 with x2 the second sample visited = the earlier of the two in sorted order;
+            // every operation is exact in double, so no division is needed.
+            uint32_t var2 = 0;
+            if (order_stats && __any_sync(FULL, keep && head && best_count == 2)) {
+                const uint32_t x2 = __shfl_sync(FULL, m.x, (__ffs(best_mask) - 1) & 31);
+                const double tmp = __dsub_rn((double)x2, __dmul_rn((double)S, 0.5));
+                var2 = best_count == 2 ? u16_from_double(__dmul_rn(tmp, tmp)) : 0u;
             }
-        }
-        // sum of the best function's lengths mod 65536 (sum_impl<unsigned short>)
-        uint32_t x = is_best ? (m.x & 0xFFFFu) : 0u;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(FULL, x, o);
-            if (lane >= s_lane + (unsigned)o) x += y;
-        }
-        const uint32_t S = __shfl_sync(FULL, x, (e_lane - 1u) & 31u) & 0xFFFFu;
+            if (keep) mark_sequence(bitmap, m.y);
 
-        if (keep) mark_sequence(bitmap, m.y);
-        if (keep && head) {
-            const uint32_t slot = rows + __popc(K & mask_lt(lane));
-            sm.code[warp][slot] = code;
-            sm.start[warp][slot] = (uint32_t)p;
-            sm.count[warp][slot] = cnt | (best_count >= 2 ? 0x80000000u : 0u);
-            sm.avg[warp][slot] = (uint16_t)sel;
-            sm.func[warp][slot] = (uint16_t)cand;
-            sm.mean[warp][slot] = (uint16_t)(S / best_count);             // u16((double)S / n), exact
-            atomicAdd(distinct_functions + cand, 1u);                      // tcc:286
+            const bool walk = keep && head && order_stats && best_count >= 3;
+            const unsigned wb = __ballot_sync(FULL, walk);
+            if (wb) work_reserve(wc, (uint32_t)__popc(wb), work, n_work);
+            if (head && act) {
+                const uint64_t gi = g + __popc(H & mask_lt(lane));
+                if (keep) {
+                    const uint32_t mean = best_count == 1 ? S : S / best_count;                 // u16((double)S / n), exact
+                    rows[gi] = make_uint4((uint32_t)code, (uint32_t)(code >> 32) | (sel << 11), cand | (mean << 16), var2 << 16);
+                    atomicAdd(distinct_functions + cand, 1u);                                   // tcc:286
+                    if (walk) work[wc.base + __popc(wb & mask_lt(lane))] = OrderWork{(uint32_t)gi, (uint32_t)p, cnt};
+                } else rows[gi] = make_uint4(0u, 0u, 0xFFFFu, 0u);
+            }
+            if (wb) { const uint32_t k = __popc(wb); wc.base += k; wc.free -= k; }
+            g += __popc(H);
+            cur += wlen;
         }
-        rows += __popc(K);
-        nwork += __popc(__ballot_sync(FULL, keep && head && best_count >= 2));
-        segs += __popc(H);
-        cur += wlen;
     }
+    // the reserved slots this warp never used
+    for (uint32_t i = lane; i < wc.free; i += 32) work[wc.base + i] = OrderWork{0u, 0u, 0u};
+}
 
-    // ---- ordered write-out: warp totals -> tile base by chained scan -> rows
-    if (lane == 0) { sm.warp_rows[warp] = rows; sm.warp_work[warp] = nwork; sm.warp_segs[warp] = segs; }
+// ---- squeeze: drop the tombstones, keep k-mer order, expand rows into the table columns
+constexpr int SQ_THREADS = 256;
+constexpr int SQ_ITEMS = 8;
+constexpr int SQ_TILE = SQ_THREADS * SQ_ITEMS;
+constexpr int SQ_WARPS = SQ_THREADS / 32;
+
+// two residues at a time: pair_ascii[40 a + b] = letter(a) | letter(b) << 8
+__device__ uint16_t g_pair_ascii[1600];
+__global__ void init_pair_ascii_kernel() {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 1600) g_pair_ascii[i] = (uint16_t)(sigk_symbol_ascii(i / 40) | (sigk_symbol_ascii(i % 40) << 8));
+}
+SIGK_D uint64_t code_to_ascii_pairs(uint64_t code) {
+    const uint32_t hi = (uint32_t)(code / 2560000ull);                      // 40^4
+    const uint32_t lo = (uint32_t)(code - (uint64_t)hi * 2560000ull);
+    const uint32_t w0 = __ldg(g_pair_ascii + hi / 1600u) | ((uint32_t)__ldg(g_pair_ascii + hi % 1600u) << 16);
+    const uint32_t w1 = __ldg(g_pair_ascii + lo / 1600u) | ((uint32_t)__ldg(g_pair_ascii + lo % 1600u) << 16);
+    return (uint64_t)w0 | ((uint64_t)w1 << 32);
+}
+
+__global__ void __launch_bounds__(SQ_THREADS)
+squeeze_rows_kernel(const uint4 *__restrict__ rows, const uint64_t *__restrict__ n_seg_ptr, KeptColumns out,
+                    uint64_t *__restrict__ scan_state, uint32_t *__restrict__ ticket, uint64_t *__restrict__ n_kept_out) {
+    __shared__ uint32_t s_scan[SQ_WARPS + 2];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_base;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint64_t n_seg = *n_seg_ptr;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t tile_start = (uint64_t)tile * SQ_TILE;
+    if (tile_start >= n_seg) return;
+
+    uint4 row[SQ_ITEMS];
+    unsigned ball[SQ_ITEMS];
+    uint32_t warp_total = 0;
+    const uint64_t wbase = tile_start + (uint64_t)warp * (SQ_ITEMS * 32);
+#pragma unroll
+    for (int i = 0; i < SQ_ITEMS; ++i) {
+        const uint64_t s = wbase + i * 32 + lane;
+        row[i] = s < n_seg ? __ldcs(rows + s) : make_uint4(0u, 0u, 0xFFFFu, 0u);
+        ball[i] = __ballot_sync(FULL, (row[i].z & 0xFFFFu) != 0xFFFFu);
+        warp_total += __popc(ball[i]);
+    }
+    uint32_t total;
+    const uint32_t excl = block_exclusive_scan<SQ_THREADS>(lane == 0 ? warp_total : 0u, s_scan, &total);
+    uint32_t run = __shfl_sync(FULL, excl, 0);
     if (tid == 0) {
-        uint32_t run = 0, sg = 0, wk = 0;
-        for (int w = 0; w < RED_WARPS; ++w) {
-            const uint32_t v = sm.warp_rows[w]; sm.warp_rows[w] = run; run += v;
-            const uint32_t u = sm.warp_work[w]; sm.warp_work[w] = wk; wk += u;
-            sg += sm.warp_segs[w];
-        }
-        const uint64_t excl = chained_scan_exclusive(scan_state, tile, run);
-        sm.base = excl;
-        sm.work_base = (order_stats && wk) ? atomicAdd(n_work, wk) : 0u;
-        if (sg) atomicAdd(reinterpret_cast<unsigned long long *>(n_seg_out), (unsigned long long)sg);
-        if (tile_start + REDUCE_TILE >= n) *n_kept_out = excl + run;
+        const uint64_t base = chained_scan_exclusive(scan_state, tile, total);
+        s_base = base;
+        if (tile_start + SQ_TILE >= n_seg) *n_kept_out = base + total;
     }
     __syncthreads();
-    const uint64_t obase = sm.base + sm.warp_rows[warp];
-    uint32_t wslot = sm.work_base + sm.warp_work[warp];
-    for (uint32_t i0 = 0; i0 < rows; i0 += 32) {
-        const uint32_t i = i0 + lane;
-        const bool have = i < rows;
-        uint32_t cw = 0;
-        if (have) {
-            const uint64_t o = obase + i;
-            cw = sm.count[warp][i];
-            out.kmer[o] = sigk_code_to_ascii(sm.code[warp][i]);
-            out.avg_from_end[o] = sm.avg[warp][i];
-            out.function_index[o] = sm.func[warp][i];
-            out.mean[o] = sm.mean[warp][i];
-            out.median[o] = 0;
-            out.var[o] = 0;
+    const uint64_t base = s_base;
+#pragma unroll
+    for (int i = 0; i < SQ_ITEMS; ++i) {
+        if ((ball[i] >> lane) & 1u) {
+            const uint64_t o = base + run + __popc(ball[i] & mask_lt(lane));
+            const uint64_t code = (uint64_t)row[i].x | ((uint64_t)(row[i].y & 0x7FFu) << 32);
+            out.kmer[o] = code_to_ascii_pairs(code);
+            out.avg_from_end[o] = (uint16_t)(row[i].y >> 11);
+            out.function_index[o] = (uint16_t)(row[i].z & 0xFFFFu);
+            out.mean[o] = (uint16_t)(row[i].z >> 16);
+            out.median[o] = (uint16_t)(row[i].w & 0xFFFFu);
+            out.var[o] = (uint16_t)(row[i].w >> 16);
         }
-        const bool need = have && order_stats && (cw & 0x80000000u);
-        const unsigned nb = __ballot_sync(FULL, need);
-        if (need) work[wslot + __popc(nb & mask_lt(lane))] = OrderWork{(uint32_t)(obase + i), sm.start[warp][i], cw & 0x7FFFFFFFu};
-        wslot += __popc(nb);
+        run += __popc(ball[i]);
     }
 }
 
-// ---- order-dependent columns: median (P^2) and var (iterative), one thread per kept group
-__global__ void __launch_bounds__(128)
+// ---- order-dependent columns: median (P^2) and var (iterative) of the kept groups in `work`.
+// The recurrences are sequential per group, so a lane owns one group at a time and a lane
+// that finishes takes the next entry of its warp's block at once (groups differ in length by
+// orders of magnitude; waiting for the slowest lane left 13 % of the lanes busy in the v2 profile).
+constexpr int ORD_THREADS = 128;
+constexpr int ORD_BLOCK = 256;      // work entries one warp owns at a time
+
+__global__ void __launch_bounds__(ORD_THREADS)
 order_stats_kernel(const uint32_t *__restrict__ vals, const uint4 *__restrict__ meta, const OrderWork *__restrict__ work,
-                   const uint32_t *__restrict__ n_work, KeptColumns out) {
+                   const uint32_t *__restrict__ n_work, uint4 *__restrict__ rows) {
     const uint32_t total = *n_work;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const OrderWork w = work[i];
-        const uint32_t cand = out.function_index[w.row];
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t warp_global = (blockIdx.x * ORD_THREADS + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * ORD_THREADS) >> 5;
+    for (uint64_t b0 = (uint64_t)warp_global * ORD_BLOCK; b0 < total; b0 += (uint64_t)n_warps * ORD_BLOCK) {
+        uint32_t cursor = (uint32_t)b0;
+        const uint32_t b1 = (uint32_t)((b0 + ORD_BLOCK < total) ? b0 + ORD_BLOCK : total);
+        bool active = false;
+        uint32_t row = 0, cand = 0, left = 0;
+        uint64_t start = 0;
         LengthAcc acc;
-        // newest first: the multimap iterates a key's items in reverse insertion order
-        for (uint32_t j = w.count; j-- > 0;) {
-            const uint4 m = __ldg(meta + vals[(uint64_t)w.start + j]);
-            if (m.z == cand) acc.push(m.x);                               // acc(item.protein_length), tcc:271
+        for (;;) {
+            const unsigned idle = __ballot_sync(FULL, !active);
+            if (idle && cursor < b1) {
+                const uint32_t take = min((uint32_t)__popc(idle), b1 - cursor);
+                const uint32_t r = __popc(idle & mask_lt(lane));
+                if (!active && r < take) {
+                    const OrderWork w = work[cursor + r];
+                    if (w.count) {                                         // count 0: an unused reserved slot
+                        row = w.row; start = w.start; left = w.count;
+                        cand = rows[w.row].z & 0xFFFFu;
+                        acc = LengthAcc();
+                        active = true;
+                    }
+                }
+                cursor += take;
+            }
+            if (!__any_sync(FULL, active)) { if (cursor >= b1) break; else continue; }
+            if (active) {
+                // newest first: the multimap iterates a key's items in reverse insertion order
+                --left;
+                const uint4 m = __ldg(meta + __ldg(vals + start + left));
+                if (m.z == cand) acc.push(m.x);                            // acc(item.protein_length), tcc:271
+                if (left == 0) {
+                    rows[row].w = u16_from_double(acc.q2) | (u16_from_double(acc.var) << 16);   // tcc:278-279
+                    active = false;
+                }
+            }
         }
-        out.median[w.row] = (uint16_t)u16_from_double(acc.q2);            // tcc:278
-        out.var[w.row] = (uint16_t)u16_from_double(acc.var);              // tcc:279
     }
 }
 
@@ -467,10 +557,15 @@ __global__ void protein_meta_kernel(const uint64_t *__restrict__ starts, const u
 
 size_t reduce_side_entries(uint64_t capacity) { return (size_t)(capacity / 32 + 2); }
 size_t reduce_giant_entries(uint64_t capacity) { return (size_t)(capacity / GIANT_STRIDE + 2); }
-size_t reduce_work_entries(uint64_t capacity) { return (size_t)(capacity / 2 + 2); }
+static int reduce_grid(int sm_count) { return sm_count * 12; }
+size_t reduce_work_entries(uint64_t capacity, int sm_count) {
+    // a walked group has >= 3 records; every warp of the persistent grid can strand one reserved block
+    return (size_t)(capacity / 3 + 2) + (size_t)reduce_grid(sm_count) * (RED_THREADS / 32) * WORK_BLOCK;
+}
 
 cudaError_t reduce_configure() {
-    return cudaFuncSetAttribute(fused_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RedSmem));
+    init_pair_ascii_kernel<<<(1600 + 255) / 256, 256>>>();
+    return cudaGetLastError();
 }
 
 cudaError_t launch_protein_meta(const uint64_t *starts, const uint16_t *func, const uint32_t *seq_id, uint32_t n_prot,
@@ -493,22 +588,31 @@ cudaError_t launch_giant_prepass(const uint64_t *keys, const uint32_t *vals, con
     return cudaGetLastError();
 }
 
-cudaError_t launch_fused_reduce(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
-                                const uint4 *meta, const uint4 *giant_side, KeptColumns out, OrderWork *work,
-                                uint32_t *n_work, uint32_t *bitmap, uint32_t *distinct_functions, uint64_t *scan_state,
-                                uint32_t *ticket, uint64_t *n_kept_out, uint64_t *n_seg_out, int order_stats,
-                                cudaStream_t stream) {
+cudaError_t launch_stream_reduce(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
+                                 const uint4 *meta, const uint4 *giant_side, uint4 *rows, OrderWork *work, uint32_t *n_work,
+                                 uint32_t *bitmap, uint32_t *distinct_functions, uint64_t *scan_state, uint32_t *ticket,
+                                 uint64_t *n_seg_out, int order_stats, int sm_count, cudaStream_t stream) {
     if (capacity == 0) return cudaSuccess;
-    fused_reduce_kernel<<<(unsigned)reduce_tiles(capacity), RED_THREADS, sizeof(RedSmem), stream>>>(
-        keys, vals, n_ptr, meta, giant_side, out, work, n_work, bitmap, distinct_functions, scan_state, ticket, n_kept_out,
-        n_seg_out, order_stats);
+    uint64_t grid = reduce_grid(sm_count);
+    const uint64_t want = (reduce_batches(capacity) + RED_THREADS / 32 - 1) / (RED_THREADS / 32);
+    if (grid > want) grid = want;
+    stream_reduce_kernel<<<(unsigned)grid, RED_THREADS, 0, stream>>>(keys, vals, n_ptr, meta, giant_side, rows, work, n_work,
+                                                                     bitmap, distinct_functions, scan_state, ticket, n_seg_out,
+                                                                     order_stats);
     return cudaGetLastError();
 }
 
 cudaError_t launch_order_stats(const uint32_t *vals, const uint4 *meta, const OrderWork *work, const uint32_t *n_work,
-                               uint64_t capacity, KeptColumns out, int sm_count, cudaStream_t stream) {
+                               uint64_t capacity, uint4 *rows, int sm_count, cudaStream_t stream) {
     if (capacity == 0) return cudaSuccess;
-    order_stats_kernel<<<sm_count * 16, 128, 0, stream>>>(vals, meta, work, n_work, out);
+    order_stats_kernel<<<sm_count * 16, ORD_THREADS, 0, stream>>>(vals, meta, work, n_work, rows);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_squeeze_rows(const uint4 *rows, const uint64_t *n_seg_ptr, uint64_t capacity, KeptColumns out,
+                                uint64_t *scan_state, uint32_t *ticket, uint64_t *n_kept_out, cudaStream_t stream) {
+    if (capacity == 0) return cudaSuccess;
+    squeeze_rows_kernel<<<(unsigned)squeeze_tiles(capacity), SQ_THREADS, 0, stream>>>(rows, n_seg_ptr, out, scan_state, ticket, n_kept_out);
     return cudaGetLastError();
 }
 

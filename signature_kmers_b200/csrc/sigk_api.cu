@@ -31,7 +31,7 @@ struct DeviceScalars {
     uint32_t n_giant, next_giant, n_work, pad;
 };
 
-enum { TK_ENCODE = 0, TK_REDUCE = 1, TK_SORT0 = 4 };
+enum { TK_ENCODE = 0, TK_REDUCE = 1, TK_SQUEEZE = 2, TK_SORT0 = 4 };
 
 template <typename T> struct DevBuf {
     T *p = nullptr;
@@ -59,7 +59,7 @@ template <typename T> struct PinnedBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-enum { EV_START, EV_H2D, EV_DEV0, EV_ENCODE, EV_HIST, EV_SORT, EV_REDUCE, EV_ORDER, EV_D2H, EV_USER0, EV_USER1, EV_USER2, EV_USER3, EV_PASS0, EV_COUNT = EV_PASS0 + SORT_MAX_PASSES + 1 };
+enum { EV_START, EV_H2D, EV_DEV0, EV_ENCODE, EV_HIST, EV_SORT, EV_REDUCE, EV_ORDER, EV_SQUEEZE, EV_D2H, EV_USER0, EV_USER1, EV_USER2, EV_USER3, EV_PASS0, EV_COUNT = EV_PASS0 + SORT_MAX_PASSES + 1 };
 
 }  // namespace
 
@@ -79,7 +79,7 @@ struct sigk_handle {
     DevBuf<uint64_t> d_starts;
     DevBuf<uint16_t> d_func;
     DevBuf<uint32_t> d_seqid;
-    DevBuf<uint4> d_meta, d_giant_side;
+    DevBuf<uint4> d_meta, d_giant_side, d_rows;
     DevBuf<uint64_t> d_giant_list;
     DevBuf<OrderWork> d_work;
     DevBuf<uint64_t> d_keys[2];
@@ -151,10 +151,11 @@ int do_upload(sigk_handle *h) {
         CU(h, h->d_lookback.reserve(onesweep_lookback_bytes(cap) * SORT_MAX_PASSES));
         CU(h, h->d_giant_side.reserve(reduce_side_entries(cap)));
         CU(h, h->d_giant_list.reserve(reduce_giant_entries(cap)));
-        CU(h, h->d_work.reserve(reduce_work_entries(cap)));
+        CU(h, h->d_work.reserve(reduce_work_entries(cap, h->sm_count)));
+        CU(h, h->d_rows.reserve(cap));
         CU(h, h->d_out_kmer.reserve(cap));
         CU(h, h->d_out_cols.reserve(cap * 5));
-        const uint64_t tiles = std::max(encode_tiles(padded), reduce_tiles(cap)) + 1;
+        const uint64_t tiles = std::max(encode_tiles(padded) + 1, reduce_scan_entries(cap));
         CU(h, h->d_scan_state.reserve(tiles));
         h->capacity = cap;
     }
@@ -228,21 +229,25 @@ int do_build_device(sigk_handle *h) {
     CU(h, cudaEventRecord(h->ev[EV_SORT], st));
     h->sorted_in = cur;
 
-    // ---- stages 3+4: run-length, reduce, keep/reject, compact; then the order-dependent columns
-    CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, (reduce_tiles(cap) + 1) * sizeof(uint64_t), st));
+    // ---- stages 3+4: run-length + reduce + keep/reject, the order-dependent columns, compaction
+    const uint64_t scan_words = reduce_scan_entries(cap);
+    CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, scan_words * sizeof(uint64_t), st));
     CU(h, cudaMemsetAsync(h->d_giant_side.p, 0, reduce_side_entries(cap) * sizeof(uint4), st));
     const int order_stats = (h->cfg.flags & SIGK_F_NO_ORDER_STATS) ? 0 : 1;
     KeptColumns kc{h->d_out_kmer.p, out_col(h, 0), out_col(h, 1), out_col(h, 2), out_col(h, 3), out_col(h, 4)};
     CU(h, launch_giant_prepass(h->d_keys[cur].p, h->d_vals[cur].p, &sc->n_records, cap, h->d_meta.p, h->d_giant_list.p,
                                &sc->n_giant, &sc->next_giant, h->d_giant_side.p, h->d_bitmap.p, h->sm_count, st));
     launches += cap > 512 ? 2 : 0;
-    CU(h, launch_fused_reduce(h->d_keys[cur].p, h->d_vals[cur].p, &sc->n_records, cap, h->d_meta.p, h->d_giant_side.p, kc,
-                              h->d_work.p, &sc->n_work, h->d_bitmap.p, h->d_distinct.p, h->d_scan_state.p,
-                              sc->ticket + TK_REDUCE, &sc->n_kept, &sc->n_segments, order_stats, st)); ++launches;
+    CU(h, launch_stream_reduce(h->d_keys[cur].p, h->d_vals[cur].p, &sc->n_records, cap, h->d_meta.p, h->d_giant_side.p,
+                               h->d_rows.p, h->d_work.p, &sc->n_work, h->d_bitmap.p, h->d_distinct.p, h->d_scan_state.p,
+                               sc->ticket + TK_REDUCE, &sc->n_segments, order_stats, h->sm_count, st)); ++launches;
     CU(h, launch_popcount(h->d_bitmap.p, ((uint64_t)h->max_seq_id >> 5) + 1, &sc->n_seqs_sig, st)); ++launches;
     CU(h, cudaEventRecord(h->ev[EV_REDUCE], st));
-    if (order_stats) { CU(h, launch_order_stats(h->d_vals[cur].p, h->d_meta.p, h->d_work.p, &sc->n_work, cap, kc, h->sm_count, st)); ++launches; }
+    if (order_stats) { CU(h, launch_order_stats(h->d_vals[cur].p, h->d_meta.p, h->d_work.p, &sc->n_work, cap, h->d_rows.p, h->sm_count, st)); ++launches; }
     CU(h, cudaEventRecord(h->ev[EV_ORDER], st));
+    CU(h, launch_squeeze_rows(h->d_rows.p, &sc->n_segments, cap, kc, h->d_scan_state.p + reduce_batches(cap) + 1,
+                              sc->ticket + TK_SQUEEZE, &sc->n_kept, st)); ++launches;
+    CU(h, cudaEventRecord(h->ev[EV_SQUEEZE], st));
 
     h->tm.kernel_launches = launches;
     h->built = true;
@@ -286,8 +291,9 @@ int do_download(sigk_handle *h) {
     t.sort_ms = ms(EV_HIST, EV_SORT);
     t.reduce_ms = ms(EV_SORT, EV_REDUCE);
     t.order_stats_ms = ms(EV_REDUCE, EV_ORDER);
-    t.d2h_ms = ms(EV_ORDER, EV_D2H);
-    t.device_total_ms = ms(EV_DEV0, EV_ORDER);
+    t.squeeze_ms = ms(EV_ORDER, EV_SQUEEZE);
+    t.d2h_ms = ms(EV_SQUEEZE, EV_D2H);
+    t.device_total_ms = ms(EV_DEV0, EV_SQUEEZE);
     t.sort_passes = (uint32_t)h->plan.npass;
     t.record_bytes = 12;
     t.key_bytes = 8;
@@ -346,7 +352,7 @@ void sigk_destroy(sigk_handle *h) {
     h->d_res.release(); h->d_starts.release(); h->d_func.release(); h->d_seqid.release(); h->d_meta.release();
     for (int i = 0; i < 2; ++i) { h->d_keys[i].release(); h->d_vals[i].release(); }
     h->d_lookback.release(); h->d_hist.release(); h->d_binbase.release(); h->d_scan_state.release();
-    h->d_giant_side.release(); h->d_giant_list.release(); h->d_work.release(); h->d_out_kmer.release(); h->d_out_cols.release();
+    h->d_giant_side.release(); h->d_giant_list.release(); h->d_work.release(); h->d_rows.release(); h->d_out_kmer.release(); h->d_out_cols.release();
     h->d_bitmap.release(); h->d_distinct.release(); h->d_swf.release(); h->d_scalars.release();
     h->h_kmer.release(); h->h_cols.release(); h->h_distinct.release(); h->h_swf.release(); h->h_scalars.release();
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);

@@ -51,18 +51,38 @@ SIGK_HD uint64_t sigk_pack_key(uint64_t code, unsigned offset16) {
 SIGK_HD uint64_t sigk_key_code(uint64_t key) { return key >> SIGK_KEY_CODE_SHIFT; }
 SIGK_HD unsigned sigk_key_offset(uint64_t key) { return (unsigned)(key >> SIGK_KEY_OFFSET_SHIFT) & 0xFFFFu; }
 
+// residue letter of symbol 0..39
+SIGK_HD unsigned sigk_symbol_ascii(unsigned s) {
+#ifdef __CUDA_ARCH__
+    // "ACDEFGHIKLMNPQRSTVWY" as little-endian words; byte select by __byte_perm
+    const unsigned u = s >= 20u ? s - 20u : s;
+    unsigned c;
+    if (u < 8u) c = __byte_perm(0x45444341u, 0x49484746u, u);             // A C D E | F G H I
+    else if (u < 16u) c = __byte_perm(0x4E4D4C4Bu, 0x53525150u, u - 8u);   // K L M N | P Q R S
+    else c = __byte_perm(0x59575654u, 0u, u - 16u);                        // T V W Y
+    return (c & 0xFFu) | (s >= 20u ? 0x20u : 0u);
+#else
+    return (unsigned char)"ACDEFGHIKLMNPQRSTVWYacdefghiklmnpqrstvwy"[s];
+#endif
+}
+
 // code -> 8 ASCII bytes packed little-endian (first residue in the low byte),
-// ready for one 8-byte store into the kmer column.
+// ready for one 8-byte store into the kmer column.  One 64-bit division splits
+// the code into two base-40 halves; the rest is 32-bit arithmetic.
 SIGK_HD uint64_t sigk_code_to_ascii(uint64_t code) {
-    const char *tab = "ACDEFGHIKLMNPQRSTVWYacdefghiklmnpqrstvwy";
-    uint64_t out = 0;
+    const uint32_t hi = (uint32_t)(code / 2560000ull);                      // 40^4
+    const uint32_t lo = (uint32_t)(code - (uint64_t)hi * 2560000ull);
+    uint32_t w[2];
+    uint32_t v[2] = {hi, lo};
 #pragma unroll
-    for (int i = 7; i >= 0; --i) {
-        const unsigned s = (unsigned)(code % 40u);
-        code /= 40u;
-        out |= (uint64_t)(unsigned char)tab[s] << (8 * i);
+    for (int h = 0; h < 2; ++h) {
+        uint32_t x = v[h];
+        const uint32_t s3 = x % 40u; x /= 40u;
+        const uint32_t s2 = x % 40u; x /= 40u;
+        const uint32_t s1 = x % 40u; x /= 40u;
+        w[h] = sigk_symbol_ascii(x) | (sigk_symbol_ascii(s1) << 8) | (sigk_symbol_ascii(s2) << 16) | (sigk_symbol_ascii(s3) << 24);
     }
-    return out;
+    return (uint64_t)w[0] | ((uint64_t)w[1] << 32);
 }
 
 #ifdef __CUDACC__
@@ -132,6 +152,37 @@ SIGK_D uint64_t chained_scan_exclusive(uint64_t *state, uint32_t tile, uint64_t 
         --t;
     }
     st_volatile_u64(state + tile, SIGK_CS_PRE | (excl + aggregate));
+    return excl;
+}
+
+// The same scan, called by a FULL WARP for its own tile: 32 predecessors are
+// inspected per round trip instead of one.  All lanes return the exclusive prefix.
+SIGK_D uint64_t chained_scan_exclusive_warp(uint64_t *state, uint32_t tile, uint64_t aggregate) {
+    const unsigned lane = threadIdx.x & 31u;
+    if (tile == 0) {
+        if (lane == 0) st_volatile_u64(state, SIGK_CS_PRE | aggregate);
+        return 0;
+    }
+    if (lane == 0) st_volatile_u64(state + tile, SIGK_CS_AGG | aggregate);
+    uint64_t excl = 0;
+    int64_t base = (int64_t)tile - 1;           // lane l looks at tile base - l
+    for (;;) {
+        const int64_t t = base - (int64_t)lane;
+        uint64_t v = t >= 0 ? ld_volatile_u64(state + t) : SIGK_CS_PRE;     // before tile 0: prefix 0
+        // the nearest inclusive prefix ends the walk; everything nearer must be published first
+        unsigned pre = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+        unsigned none = __ballot_sync(0xffffffffu, (v >> 62) == 0);
+        const unsigned upto = pre ? (pre & (0u - pre)) : 0u;               // lowest lane holding a prefix
+        const unsigned needed = upto ? ((upto << 1) - 1u) : 0xffffffffu;    // lanes 0 .. that lane
+        if (none & needed) continue;                                        // somebody nearer is not ready: reread
+        uint64_t c = ((1u << lane) & needed) ? (v & SIGK_CS_VAL) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        excl += c;
+        if (pre) break;
+        base -= 32;
+    }
+    if (lane == 0) st_volatile_u64(state + tile, SIGK_CS_PRE | (excl + aggregate));
     return excl;
 }
 
