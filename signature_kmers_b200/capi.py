@@ -14,7 +14,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsigk.so")
+LIB_PATH = os.environ.get("SIGK_LIB") or os.path.join(_HERE, "libsigk.so")   # SIGK_LIB: a tuning variant
 
 SIGK_ABI_VERSION = 1
 SIGK_K = 8

@@ -16,7 +16,8 @@
 // code is rolled (one multiply-add per window).  Valid windows are compacted
 // through shared memory and leave the CTA as coalesced 8-byte / 4-byte stores;
 // the CTA's place in the output is a single-pass chained scan over tile totals
-// (tiles are tickets, so the record order is the position order).
+// (tiles are tickets, so the record order is the position order); every warp
+// owns its own slice and scan entry, so there is no block barrier after the ticket.
 //
 // HBM traffic per valid window: ~1 byte read, 12 bytes written.
 #include "kernels.h"
@@ -27,18 +28,16 @@ namespace sigk {
 namespace {
 
 constexpr int ENC_WARPS = ENC_THREADS / 32;
+constexpr int ENC_SUB = 32 * ENC_PPT;                 // window positions one warp owns: 512
 // compacted records are staged with one pad slot per 16 so that the
 // thread-contiguous writes (stride ~16 records between lanes) spread over banks
-constexpr int ENC_STAGE = ENC_TILE + ENC_TILE / 16;
+constexpr int ENC_STAGE = ENC_SUB + ENC_SUB / 16;
 SIGK_D int stage_slot(int o) { return o + (o >> 4); }
 
 struct EncSmem {
-    uint64_t keys[ENC_STAGE];
-    uint32_t vals[ENC_STAGE];
-    uint32_t scan[ENC_WARPS + 2];
+    uint64_t keys[ENC_WARPS][ENC_STAGE];
+    uint32_t vals[ENC_WARPS][ENC_STAGE];
     uint32_t tile;
-    uint32_t lo, hi;
-    uint64_t base;
 };
 
 // largest i in [lo, hi] with starts[i] <= g   (starts[lo] <= g is guaranteed)
@@ -51,29 +50,28 @@ SIGK_D uint32_t find_protein(const uint64_t *__restrict__ starts, uint32_t lo, u
     return lo;
 }
 
-__global__ void __launch_bounds__(ENC_THREADS)
+// The warps of a CTA are independent after the ticket: each owns ENC_SUB positions and
+// its own entry in the chained scan, so nothing waits at a block barrier.
+__global__ void __launch_bounds__(ENC_THREADS, 4)
 encode_kernel(EncodeArgs a, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
               uint64_t *__restrict__ scan_state, uint32_t *__restrict__ ticket, uint64_t *__restrict__ n_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EncSmem &sm = *reinterpret_cast<EncSmem *>(smem_raw);
 
-    const unsigned tid = threadIdx.x, lane = tid & 31u;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
     __syncthreads();
-    const uint32_t tile = sm.tile;
-    const uint64_t g0 = (uint64_t)tile * ENC_TILE;
-    const uint32_t last_tile = (uint32_t)((a.total_res + ENC_TILE - 1) / ENC_TILE) - 1;
+    const uint32_t sub = sm.tile * ENC_WARPS + warp;                 // this warp's entry in the chained scan
+    const uint64_t g0 = (uint64_t)sub * ENC_SUB;
+    if (g0 >= a.total_res) return;
+    const bool last_sub = g0 + ENC_SUB >= a.total_res;
 
-    // protein range of this tile: two searches over the whole starts[] by two threads
-    if (tid < 2) {
-        uint64_t g = tid == 0 ? g0 : g0 + ENC_TILE - 1;
-        if (g >= a.total_res) g = a.total_res - 1;
-        const uint32_t i = find_protein(a.starts, 0, a.n_prot - 1, g);
-        if (tid == 0) sm.lo = i; else sm.hi = i;
-    }
+    // protein range of the warp's positions, from the per-slice index built by slice_index_kernel
+    const uint32_t p_lo = __ldg(a.slice_prot + sub);
+    const uint32_t p_hi = last_sub ? a.n_prot - 1 : __ldg(a.slice_prot + sub + 1);
 
     // residues: 16 of my own + 8 of the next lane's
-    const uint64_t g_first = g0 + (uint64_t)tid * ENC_PPT;
+    const uint64_t g_first = g0 + (uint64_t)lane * ENC_PPT;
     const uint4 w = ld_stream_u128(reinterpret_cast<const uint4 *>(a.res + g_first));
     uint32_t n0 = __shfl_down_sync(0xffffffffu, w.x, 1);
     uint32_t n1 = __shfl_down_sync(0xffffffffu, w.y, 1);
@@ -92,10 +90,9 @@ encode_kernel(EncodeArgs a, uint64_t *__restrict__ keys, uint32_t *__restrict__ 
         if (sy < 0) { bad |= 1u << j; sy = 0; }
         s[j] = sy;
     }
-    __syncthreads();    // sm.lo / sm.hi
 
     // pass A: which of my 16 windows are valid
-    const uint32_t p_first = find_protein(a.starts, sm.lo, sm.hi, g_first < a.total_res ? g_first : a.total_res - 1);
+    const uint32_t p_first = find_protein(a.starts, p_lo, p_hi, g_first < a.total_res ? g_first : a.total_res - 1);
     uint32_t valid_mask = 0;
     {
         uint32_t i = p_first;
@@ -107,14 +104,16 @@ encode_kernel(EncodeArgs a, uint64_t *__restrict__ keys, uint32_t *__restrict__ 
             if (((bad >> j) & 0xFFu) == 0 && g + SIGK_K_DEV <= prot_end) valid_mask |= 1u << j;
         }
     }
-    uint32_t total;
-    const uint32_t excl = block_exclusive_scan<ENC_THREADS>((uint32_t)__popc(valid_mask), sm.scan, &total);
-
-    if (tid == 0) {
-        const uint64_t base = chained_scan_exclusive(scan_state, tile, total);
-        sm.base = base;
-        if (tile == last_tile) *n_out = base + total;
+    const uint32_t mine = (uint32_t)__popc(valid_mask);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += y;
     }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint64_t base = chained_scan_exclusive_warp(scan_state, sub, total);
+    if (last_sub && lane == 0) *n_out = base + total;
 
     // pass B: roll the code, emit valid windows to their compacted slots
     {
@@ -123,7 +122,7 @@ encode_kernel(EncodeArgs a, uint64_t *__restrict__ keys, uint32_t *__restrict__ 
         uint64_t code = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) code = code * 40u + (uint64_t)s[j];
-        int o = (int)excl;
+        int o = (int)(incl - mine);
 #pragma unroll
         for (int j = 0; j < ENC_PPT; ++j) {
             const uint64_t g = g_first + j;
@@ -131,22 +130,39 @@ encode_kernel(EncodeArgs a, uint64_t *__restrict__ keys, uint32_t *__restrict__ 
             while (g >= prot_end && i + 1 < a.n_prot) { ++i; prot_end = __ldg(a.starts + i + 1); }
             if ((valid_mask >> j) & 1u) {
                 const int slot = stage_slot(o++);
-                sm.keys[slot] = sigk_pack_key(code, (unsigned)(prot_end - g));
-                sm.vals[slot] = a.ordinal_base + i;
+                sm.keys[warp][slot] = sigk_pack_key(code, (unsigned)(prot_end - g));
+                sm.vals[warp][slot] = a.ordinal_base + i;
             }
         }
     }
-    __syncthreads();
-
-    const uint64_t base = sm.base;
-    for (uint32_t o = tid; o < total; o += ENC_THREADS) {
+    __syncwarp();
+    for (uint32_t o = lane; o < total; o += 32) {
         const int slot = stage_slot((int)o);
-        keys[base + o] = sm.keys[slot];
-        vals[base + o] = sm.vals[slot];
+        keys[base + o] = sm.keys[warp][slot];
+        vals[base + o] = sm.vals[warp][slot];
     }
 }
 
+// slice_prot[b] = protein holding position b * ENC_SUB: one binary search per slice, done
+// once per upload instead of once per warp per build.
+__global__ void slice_index_kernel(const uint64_t *__restrict__ starts, uint32_t n_prot, uint64_t total_res,
+                                   uint32_t *__restrict__ slice_prot, uint64_t n_slices) {
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_slices) return;
+    uint64_t g = b * ENC_SUB;
+    if (g >= total_res) g = total_res - 1;
+    slice_prot[b] = find_protein(starts, 0, n_prot - 1, g);
+}
+
 }  // namespace
+
+cudaError_t launch_slice_index(const uint64_t *starts, uint32_t n_prot, uint64_t total_res, uint32_t *slice_prot,
+                               cudaStream_t stream) {
+    if (total_res == 0 || n_prot == 0) return cudaSuccess;
+    const uint64_t n = encode_slices(total_res);
+    slice_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(starts, n_prot, total_res, slice_prot, n);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_encode(const EncodeArgs &a, uint64_t *keys, uint32_t *vals, uint64_t *scan_state,
                           uint32_t *ticket, uint64_t *n_out, cudaStream_t stream) {

@@ -22,11 +22,15 @@ struct EncodeArgs {
     const uint64_t *starts;    // device, n_prot + 1
     uint32_t n_prot;
     uint32_t ordinal_base;     // ordinal of local protein 0 in the whole job (multi-GPU)
+    const uint32_t *slice_prot; // device, encode_slices()+1: protein holding the first position of each 512-position slice
 };
 
 inline uint64_t encode_tiles(uint64_t total_res) { return (total_res + ENC_TILE - 1) / ENC_TILE; }
+inline uint64_t encode_slices(uint64_t total_res) { return encode_tiles(total_res) * (ENC_THREADS / 32); }
+cudaError_t launch_slice_index(const uint64_t *starts, uint32_t n_prot, uint64_t total_res, uint32_t *slice_prot, cudaStream_t stream);
+inline uint64_t encode_scan_entries(uint64_t total_res) { return encode_tiles(total_res) * (ENC_THREADS / 32) + 1; }
 
-// scan_state: encode_tiles() u64 words, zeroed; ticket: one zeroed u32; n_out: u64.
+// scan_state: encode_scan_entries() u64 words, zeroed; ticket: one zeroed u32; n_out: u64.
 cudaError_t launch_encode(const EncodeArgs &a, uint64_t *keys, uint32_t *vals, uint64_t *scan_state,
                           uint32_t *ticket, uint64_t *n_out, cudaStream_t stream);
 
@@ -40,14 +44,20 @@ struct PassPlan {
 };
 PassPlan make_pass_plan(int bit_lo, int bit_hi);
 
-constexpr int OS_THREADS = 512;
-constexpr int OS_ITEMS = 15;
-constexpr int OS_TILE = OS_THREADS * OS_ITEMS;    // 7680 records per CTA
+#ifndef SIGK_OS_THREADS          // tuning knobs; the defaults are the measured best (profiles/)
+#define SIGK_OS_THREADS 512     // sweep on B200, config2 (gpurun_out/sweep_*, profiles/): 512x15 beats 256x13, 384x14, 512x11, 1024x15
+#define SIGK_OS_ITEMS 15
+#define SIGK_OS_MIN_BLOCKS 2
+#endif
+constexpr int OS_THREADS = SIGK_OS_THREADS;
+constexpr int OS_ITEMS = SIGK_OS_ITEMS;
+constexpr int OS_MIN_BLOCKS = SIGK_OS_MIN_BLOCKS;  // CTAs per SM the pass kernel is sized for
+constexpr int OS_TILE = OS_THREADS * OS_ITEMS;    // 3328 records per CTA
 inline uint64_t onesweep_tiles(uint64_t capacity) { return (capacity + OS_TILE - 1) / OS_TILE; }
 // bytes of look-back state one pass needs for `capacity` records
 size_t onesweep_lookback_bytes(uint64_t capacity);
 
-// hist: [npass][256] u64, zeroed.  Counts the digit of every pass in one read of the keys.
+// hist: [npass][SIGK_RADIX] u64, zeroed.  Counts the digit of every pass in one read of the keys.
 cudaError_t launch_histogram(const uint64_t *keys, const uint64_t *n_ptr, uint64_t capacity, const PassPlan &plan,
                              uint64_t *hist, int sm_count, cudaStream_t stream);
 // bin_base[p][d] = exclusive scan over d of hist[p][d]

@@ -39,6 +39,9 @@ PassPlan make_pass_plan(int bit_lo, int bit_hi) {
 namespace {
 
 constexpr int OS_WARPS = OS_THREADS / 32;
+constexpr int OS_DPT = (SIGK_RADIX + OS_THREADS - 1) / OS_THREADS;   // digits one thread owns in the scan / look-back
+static_assert(OS_DPT * OS_THREADS >= SIGK_RADIX, "every digit has an owner");
+static_assert(OS_TILE < 65536, "tile slots are kept in 16 bits");
 
 // look-back word: flag in the two top bits, value below
 template <typename LB> struct LBTraits;
@@ -58,15 +61,15 @@ template <> struct LBTraits<uint64_t> {
 struct OsSmem {
     uint64_t keys[OS_TILE];
     uint32_t vals[OS_TILE];
-    uint32_t cnt[OS_WARPS * SIGK_RADIX];    // per-warp digit counters -> exclusive prefix over warps
     uint64_t goff[SIGK_RADIX];              // global position of sorted slot 0 of each digit, minus its tile base
-    uint32_t dbase[SIGK_RADIX];             // exclusive scan of the tile histogram
+    // per-warp digit counters; after the scan: tile slot of the warp's first record of each digit
+    uint16_t cnt[OS_WARPS][SIGK_RADIX];
     uint32_t scan[OS_WARPS + 2];
     uint32_t tile;
 };
 
 template <typename LB>
-__global__ void __launch_bounds__(OS_THREADS, 2)
+__global__ void __launch_bounds__(OS_THREADS, OS_MIN_BLOCKS)
 onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                      uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
                      const uint64_t *__restrict__ n_ptr, int bit_lo, uint32_t digit_mask,
@@ -78,6 +81,11 @@ onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__res
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint64_t n = *n_ptr;
     if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+    // zero the warp counters (as 32-bit words)
+    {
+        uint32_t *c32 = reinterpret_cast<uint32_t *>(&sm.cnt[0][0]);
+        for (uint32_t j = tid; j < OS_WARPS * SIGK_RADIX / 2; j += OS_THREADS) c32[j] = 0;
+    }
     __syncthreads();
     const uint32_t tile = sm.tile;
     const uint64_t tile_start = (uint64_t)tile * OS_TILE;
@@ -94,18 +102,16 @@ onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__res
         const uint32_t idx = wbase + i * 32 + lane;
         key[i] = idx < tile_n ? ld_stream_u64(keys_in + tile_start + idx) : ~0ull;
     }
-    for (uint32_t j = tid; j < OS_WARPS * SIGK_RADIX; j += OS_THREADS) sm.cnt[j] = 0;
-    __syncthreads();
 
-    // ---- rank inside the warp: match-any groups equal digits, the group leader
-    // bumps the warp's counter, everyone takes counter + (peers below me).
-    uint32_t *wcnt = sm.cnt + warp * SIGK_RADIX;
+    // ---- rank inside the warp: lanes with my digit are found with one ballot per digit
+    // bit (MATCH.ANY runs on the ADU pipe at ~64 cycles per warp instruction: 70 % pipe
+    // utilisation in the round-1 v1 profile); the group's first lane bumps the warp's counter,
+    // everyone takes counter + (peers below me).  No atomics, stable.
+    uint16_t *wcnt = sm.cnt[warp];
     uint16_t rank[OS_ITEMS];
 #pragma unroll
     for (int i = 0; i < OS_ITEMS; ++i) {
         const uint32_t d = (uint32_t)(key[i] >> bit_lo) & digit_mask;
-        // lanes with my digit: one ballot per digit bit (MATCH.ANY runs on the slow ADU pipe:
-        // ~64 cycles per warp instruction, 70 % pipe utilisation in the round-1 v1 profile)
         unsigned peers = 0xffffffffu;
 #pragma unroll
         for (int b = 0; b < SIGK_RADIX_BITS; ++b) {
@@ -115,44 +121,58 @@ onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__res
         }
         const int leader = __ffs(peers) - 1;
         uint32_t old = 0;
-        if ((int)lane == leader) { old = wcnt[d]; wcnt[d] = old + __popc(peers); }
+        if ((int)lane == leader) { old = wcnt[d]; wcnt[d] = (uint16_t)(old + __popc(peers)); }
         old = __shfl_sync(0xffffffffu, old, leader);
         rank[i] = (uint16_t)(old + __popc(peers & ((1u << lane) - 1u)));
         __syncwarp();
     }
     __syncthreads();
 
-    // ---- per digit: exclusive prefix over warps, tile count, publish, look back
-    uint32_t my_count = 0;
-    if (tid < SIGK_RADIX) {
-        uint32_t sum = 0;
+    // ---- per digit: exclusive prefix over warps, tile count, publish, look back.
+    // Thread t owns digits t*DPT .. t*DPT+DPT-1.
+    uint32_t my_count[OS_DPT], my_sum = 0;
 #pragma unroll
-        for (int w = 0; w < OS_WARPS; ++w) {
-            const uint32_t c = sm.cnt[w * SIGK_RADIX + tid];
-            sm.cnt[w * SIGK_RADIX + tid] = sum;
-            sum += c;
+    for (int k = 0; k < OS_DPT; ++k) {
+        const uint32_t d = tid * OS_DPT + k;
+        uint32_t sum = 0;
+        if (d < SIGK_RADIX) {
+#pragma unroll
+            for (int w = 0; w < OS_WARPS; ++w) sum += sm.cnt[w][d];
+            T::st(lookback + (size_t)tile * SIGK_RADIX + d, (tile == 0 ? T::PRE : T::AGG) | (LB)sum);
         }
-        my_count = sum;
-        T::st(lookback + (size_t)tile * SIGK_RADIX + tid, (tile == 0 ? T::PRE : T::AGG) | (LB)sum);
+        my_count[k] = sum;
+        my_sum += sum;
     }
     uint32_t total;
-    const uint32_t dbase = block_exclusive_scan<OS_THREADS>(my_count, sm.scan, &total);
-    if (tid < SIGK_RADIX) {
-        sm.dbase[tid] = dbase;
-        LB excl = 0;
-        if (tile > 0) {
-            int64_t t = (int64_t)tile - 1;
-            for (;;) {
-                const LB v = T::ld(lookback + (size_t)t * SIGK_RADIX + tid);
-                const LB flag = v >> T::SHIFT;
-                if (flag == 0) continue;
-                excl += v & T::VAL;
-                if (flag == 2) break;
-                --t;
+    uint32_t dbase = block_exclusive_scan<OS_THREADS>(my_sum, sm.scan, &total);
+#pragma unroll
+    for (int k = 0; k < OS_DPT; ++k) {
+        const uint32_t d = tid * OS_DPT + k;
+        if (d < SIGK_RADIX) {
+            // fold the digit's tile base into the per-warp prefixes: slot = cnt[warp][d] + rank
+            uint32_t run = dbase;
+#pragma unroll
+            for (int w = 0; w < OS_WARPS; ++w) {
+                const uint32_t c = sm.cnt[w][d];
+                sm.cnt[w][d] = (uint16_t)run;
+                run += c;
             }
-            T::st(lookback + (size_t)tile * SIGK_RADIX + tid, T::PRE | (excl + (LB)my_count));
+            LB excl = 0;
+            if (tile > 0) {
+                int64_t t = (int64_t)tile - 1;
+                for (;;) {
+                    const LB v = T::ld(lookback + (size_t)t * SIGK_RADIX + d);
+                    const LB flag = v >> T::SHIFT;
+                    if (flag == 0) continue;
+                    excl += v & T::VAL;
+                    if (flag == 2) break;
+                    --t;
+                }
+                T::st(lookback + (size_t)tile * SIGK_RADIX + d, T::PRE | (excl + (LB)my_count[k]));
+            }
+            sm.goff[d] = bin_base[d] + (uint64_t)excl - (uint64_t)dbase;
         }
-        sm.goff[tid] = bin_base[tid] + (uint64_t)excl - (uint64_t)dbase;
+        dbase += my_count[k];
     }
     __syncthreads();
 
@@ -160,7 +180,7 @@ onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__res
 #pragma unroll
     for (int i = 0; i < OS_ITEMS; ++i) {
         const uint32_t d = (uint32_t)(key[i] >> bit_lo) & digit_mask;
-        const uint32_t slot = sm.dbase[d] + wcnt[d] + rank[i];
+        const uint32_t slot = (uint32_t)wcnt[d] + rank[i];
         rank[i] = (uint16_t)slot;
         sm.keys[slot] = key[i];
     }

@@ -78,7 +78,7 @@ struct sigk_handle {
     DevBuf<uint8_t> d_res;
     DevBuf<uint64_t> d_starts;
     DevBuf<uint16_t> d_func;
-    DevBuf<uint32_t> d_seqid;
+    DevBuf<uint32_t> d_seqid, d_slice_prot;
     DevBuf<uint4> d_meta, d_giant_side, d_rows;
     DevBuf<uint64_t> d_giant_list;
     DevBuf<OrderWork> d_work;
@@ -144,6 +144,7 @@ int do_upload(sigk_handle *h) {
     CU(h, h->d_func.reserve(np));
     CU(h, h->d_seqid.reserve(np));
     CU(h, h->d_meta.reserve(np));
+    CU(h, h->d_slice_prot.reserve(encode_slices(total) + 2));
     // one record per residue position is the ceiling (every window valid)
     const uint64_t cap = total;
     if (cap > h->capacity) {
@@ -155,7 +156,7 @@ int do_upload(sigk_handle *h) {
         CU(h, h->d_rows.reserve(cap));
         CU(h, h->d_out_kmer.reserve(cap));
         CU(h, h->d_out_cols.reserve(cap * 5));
-        const uint64_t tiles = std::max(encode_tiles(padded) + 1, reduce_scan_entries(cap));
+        const uint64_t tiles = std::max(encode_scan_entries(padded), reduce_scan_entries(cap));
         CU(h, h->d_scan_state.reserve(tiles));
         h->capacity = cap;
     }
@@ -178,6 +179,7 @@ int do_upload(sigk_handle *h) {
         CU(h, cudaMemcpyAsync(h->d_func.p, p.function_index, np * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
         CU(h, cudaMemcpyAsync(h->d_seqid.p, p.seq_id, np * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     }
+    CU(h, launch_slice_index(h->d_starts.p, (uint32_t)np, total, h->d_slice_prot.p, st));
     CU(h, cudaEventRecord(h->ev[EV_H2D], st));
     CU(h, cudaStreamSynchronize(st));
     cudaEventElapsedTime(&h->h2d_ms, h->ev[EV_START], h->ev[EV_H2D]);
@@ -204,8 +206,8 @@ int do_build_device(sigk_handle *h) {
 
     // ---- stage 1: encode
     CU(h, launch_protein_meta(h->d_starts.p, h->d_func.p, h->d_seqid.p, (uint32_t)np, h->d_meta.p, h->d_swf.p, st)); ++launches;
-    CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, (encode_tiles(h->total_res) + 1) * sizeof(uint64_t), st));
-    EncodeArgs ea{h->d_res.p, h->total_res, h->d_starts.p, (uint32_t)np, 0u};
+    CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, encode_scan_entries(h->total_res) * sizeof(uint64_t), st));
+    EncodeArgs ea{h->d_res.p, h->total_res, h->d_starts.p, (uint32_t)np, 0u, h->d_slice_prot.p};
     CU(h, launch_encode(ea, h->d_keys[0].p, h->d_vals[0].p, h->d_scan_state.p, sc->ticket + TK_ENCODE, &sc->n_records, st)); ++launches;
     CU(h, cudaEventRecord(h->ev[EV_ENCODE], st));
 
@@ -349,7 +351,7 @@ void sigk_destroy(sigk_handle *h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    h->d_res.release(); h->d_starts.release(); h->d_func.release(); h->d_seqid.release(); h->d_meta.release();
+    h->d_res.release(); h->d_starts.release(); h->d_func.release(); h->d_seqid.release(); h->d_meta.release(); h->d_slice_prot.release();
     for (int i = 0; i < 2; ++i) { h->d_keys[i].release(); h->d_vals[i].release(); }
     h->d_lookback.release(); h->d_hist.release(); h->d_binbase.release(); h->d_scan_state.release();
     h->d_giant_side.release(); h->d_giant_list.release(); h->d_work.release(); h->d_rows.release(); h->d_out_kmer.release(); h->d_out_cols.release();
@@ -472,8 +474,8 @@ int sigk_dbg_encode(sigk_handle *h, const sigk_proteins *p, uint64_t *out_code, 
     cudaStream_t st = h->stream;
     DeviceScalars *sc = h->d_scalars.p;
     CU(h, cudaMemsetAsync(sc, 0, sizeof(DeviceScalars), st));
-    CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, (encode_tiles(h->total_res) + 1) * sizeof(uint64_t), st));
-    EncodeArgs ea{h->d_res.p, h->total_res, h->d_starts.p, (uint32_t)p->n_proteins, 0u};
+    CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, encode_scan_entries(h->total_res) * sizeof(uint64_t), st));
+    EncodeArgs ea{h->d_res.p, h->total_res, h->d_starts.p, (uint32_t)p->n_proteins, 0u, h->d_slice_prot.p};
     CU(h, launch_encode(ea, h->d_keys[0].p, h->d_vals[0].p, h->d_scan_state.p, sc->ticket + TK_ENCODE, &sc->n_records, st));
     uint64_t n = 0;
     CU(h, cudaMemcpyAsync(&n, &sc->n_records, sizeof n, cudaMemcpyDeviceToHost, st));

@@ -19,8 +19,10 @@
 #define SIGK_KEY_CODE_SHIFT 21
 #define SIGK_KEY_OFFSET_SHIFT 5
 #define SIGK_K_DEV 8
-#define SIGK_RADIX_BITS 8
-#define SIGK_RADIX 256
+#ifndef SIGK_RADIX_BITS
+#define SIGK_RADIX_BITS 9         // 43 code bits in 5 passes (9,9,9,8,8): 21.5 ms vs 23.4 ms for 6 passes of 8 bits
+#endif
+#define SIGK_RADIX (1 << SIGK_RADIX_BITS)
 
 #define SIGK_HD __host__ __device__ __forceinline__
 #define SIGK_D __device__ __forceinline__

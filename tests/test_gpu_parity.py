@@ -61,7 +61,7 @@ def test_encode_long_protein_offset_wraps(gpu):
     np.testing.assert_array_equal(offset, rf)
 
 
-@pytest.mark.parametrize("n,lo,hi", [(1, 21, 64), (7680, 21, 64), (7681, 21, 64), (100_000, 0, 64), (5_000_000, 21, 64), (1_000_003, 5, 13)])
+@pytest.mark.parametrize("n,lo,hi", [(1, 21, 64), (3328, 21, 64), (3329, 21, 64), (7681, 21, 64), (100_000, 0, 64), (5_000_000, 21, 64), (1_000_003, 5, 13), (300_000, 30, 39)])
 def test_radix_sort_is_stable_and_sorted(gpu, n, lo, hi):
     rng = np.random.default_rng(n)
     # heavy duplication in the sorted bits so that stability is visible
