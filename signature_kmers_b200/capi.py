@@ -278,8 +278,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.sigk_synchronize.argtypes = [C.c_void_p]
     lib.sigk_event_record.argtypes = [C.c_void_p, C.c_int]
     lib.sigk_event_elapsed_ms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
-    lib.sigk_comm_make_id.argtypes = [C.c_void_p]
-    lib.sigk_comm_join.argtypes = [C.c_void_p, C.c_void_p]
+    lib.sigk_comm_make_id.argtypes = [C.c_char_p]
+    lib.sigk_comm_join.argtypes = [C.c_void_p, C.c_char_p]
     lib.sigk_dbg_encode.argtypes = [
         C.c_void_p, C.POINTER(SigkProteins), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64),
     ]

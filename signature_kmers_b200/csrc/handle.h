@@ -1,0 +1,145 @@
+// handle.h — the libsigk handle (private to csrc/): device buffers, stream,
+// events, and the multi-GPU communicator state.
+#pragma once
+
+#include "../../include/sigk.h"
+#include "kernels.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace sigk {
+
+struct DeviceScalars {
+    uint64_t n_records;
+    uint64_t n_segments;
+    uint64_t n_kept;
+    uint64_t n_seqs_sig;
+    uint32_t ticket[16];
+    uint32_t n_giant, next_giant, n_work, pad;
+    uint64_t reduce_in[4];      // multi-GPU: {occurrences, groups, kept, -} of this rank -> summed over ranks
+};
+
+enum { TK_ENCODE = 0, TK_REDUCE = 1, TK_SQUEEZE = 2, TK_PARTITION = 3, TK_SORT0 = 4 };
+
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;     // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <typename T> struct PinnedBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMallocHost(&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+enum { EV_START, EV_H2D, EV_DEV0, EV_ENCODE, EV_EXCHANGE, EV_HIST, EV_SORT, EV_REDUCE, EV_ORDER, EV_SQUEEZE, EV_D2H,
+       EV_USER0, EV_USER1, EV_USER2, EV_USER3, EV_PASS0, EV_COUNT = EV_PASS0 + SORT_MAX_PASSES + 1 };
+
+struct Comm;    // comm.cu
+
+}  // namespace sigk
+
+struct sigk_handle {
+    sigk_config cfg{};
+    std::string error;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[sigk::EV_COUNT] = {};
+    int sm_count = 148;
+
+    sigk_proteins in{};
+    bool have_input = false, uploaded = false, built = false, downloaded = false;
+    uint64_t total_res = 0;
+    uint32_t max_seq_id = 0;            // over the whole job once a communicator is joined
+    uint32_t local_max_seq_id = 0;
+
+    sigk::DevBuf<uint8_t> d_res;
+    sigk::DevBuf<uint64_t> d_starts;
+    sigk::DevBuf<uint16_t> d_func;
+    sigk::DevBuf<uint32_t> d_seqid, d_slice_prot;
+    sigk::DevBuf<uint4> d_meta, d_giant_side, d_rows;
+    sigk::DevBuf<uint64_t> d_giant_list;
+    sigk::DevBuf<sigk::OrderWork> d_work;
+    sigk::DevBuf<uint64_t> d_keys[2];
+    sigk::DevBuf<uint32_t> d_vals[2];
+    sigk::DevBuf<uint8_t> d_lookback;
+    sigk::DevBuf<uint64_t> d_hist, d_binbase, d_scan_state;
+    sigk::DevBuf<uint64_t> d_out_kmer;
+    sigk::DevBuf<uint16_t> d_out_cols;       // 5 columns of capacity rows
+    sigk::DevBuf<uint32_t> d_bitmap, d_distinct, d_swf;
+    sigk::DevBuf<sigk::DeviceScalars> d_scalars;
+    uint64_t capacity = 0;             // records the buffers are sized for
+    int sorted_in = 0;                 // which ping-pong buffer holds the sorted records
+
+    sigk::PinnedBuf<uint64_t> h_kmer;
+    sigk::PinnedBuf<uint16_t> h_cols;
+    sigk::PinnedBuf<uint32_t> h_distinct, h_swf;
+    sigk::PinnedBuf<sigk::DeviceScalars> h_scalars;
+    uint64_t h_rows = 0;
+
+    sigk_timings tm{};
+    float h2d_ms = 0;
+    sigk::PassPlan plan{};
+
+    // multi-GPU
+    sigk::Comm *comm = nullptr;
+    uint64_t n_prot_global = 0;         // proteins of the whole job
+    uint64_t ordinal_base = 0;          // ordinal of this rank's first protein
+    uint64_t n_recv = 0;                // records this rank owns after the exchange
+
+    int fail(int code, const char *fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        error = buf;
+        return code;
+    }
+};
+
+#define CU(h, call)                                                                                          \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess)                                                                               \
+            return (h)->fail(e_ == cudaErrorMemoryAllocation ? SIGK_E_NOMEM : SIGK_E_CUDA, "%s: %s (%s:%d)", #call, \
+                             cudaGetErrorString(e_), __FILE__, __LINE__);                                    \
+    } while (0)
+
+namespace sigk {
+
+// (re)size every record-proportional buffer for `cap` records; keep_pingpong1 leaves keys[1]/vals[1] alone
+int ensure_capacity(sigk_handle *h, uint64_t cap, bool keep_pingpong1);
+
+// comm.cu
+int comm_make_id(void *id128, std::string *err);
+int comm_join(sigk_handle *h, const void *id128);
+void comm_destroy(sigk_handle *h);
+// after upload: learn every rank's protein count, the job-wide max seq_id
+int comm_exchange_shapes(sigk_handle *h);
+// share the per-protein meta of every rank (h->d_meta holds n_prot_global entries afterwards)
+int comm_allgather_meta(sigk_handle *h);
+// encode output in keys[0]/vals[0] -> records of this rank's k-mer range in keys[0]/vals[0], n_records updated
+int comm_partition_exchange(sigk_handle *h, uint32_t *launches);
+// sum the per-rank statistics so that every rank's result carries whole-job counters
+int comm_reduce_stats(sigk_handle *h);
+
+}  // namespace sigk

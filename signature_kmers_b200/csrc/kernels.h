@@ -37,6 +37,7 @@ cudaError_t launch_encode(const EncodeArgs &a, uint64_t *keys, uint32_t *vals, u
 
 // ---- stage 2: onesweep LSD radix sort (onesweep.cu) ------------------------
 constexpr int SORT_MAX_PASSES = 8;
+constexpr int SORT_MAX_SPLIT = 15;    // the partition pass routes to at most 16 ranks
 struct PassPlan {
     int npass;
     int lo[SORT_MAX_PASSES];
@@ -67,6 +68,12 @@ cudaError_t launch_onesweep_pass(const uint64_t *keys_in, const uint32_t *vals_i
                                  uint32_t *vals_out, const uint64_t *n_ptr, uint64_t capacity, int bit_lo, int nbits,
                                  const uint64_t *bin_base, void *lookback, uint32_t *ticket, cudaStream_t stream);
 cudaError_t onesweep_configure();   // opt in to the dynamic shared memory the pass kernel needs
+// The same kernel as a stable multi-way split: digit = number of split_codes <= the record's k-mer code
+// (the rank owning the record).  bin_base[d] = first output slot of rank d (SIGK_RADIX entries).
+cudaError_t launch_onesweep_partition(const uint64_t *keys_in, const uint32_t *vals_in, uint64_t *keys_out,
+                                      uint32_t *vals_out, const uint64_t *n_ptr, uint64_t capacity,
+                                      const uint64_t *split_codes, int n_split, const uint64_t *bin_base, void *lookback,
+                                      uint32_t *ticket, cudaStream_t stream);
 
 // ---- stages 3+4: segment reduce, keep/reject, compaction, order statistics (reduce.cu)
 struct KeptColumns {           // device, capacity rows each

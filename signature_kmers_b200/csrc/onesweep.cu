@@ -66,14 +66,27 @@ struct OsSmem {
     uint16_t cnt[OS_WARPS][SIGK_RADIX];
     uint32_t scan[OS_WARPS + 2];
     uint32_t tile;
+    uint64_t split[SORT_MAX_SPLIT];         // SPLIT mode: first k-mer code of ranks 1..n_split
 };
 
-template <typename LB>
+// The "digit" of a record: a bit field of the key, or (SPLIT, the multi-GPU partition pass)
+// the rank that owns the record's k-mer range = number of splitter codes <= its code.
+template <bool SPLIT>
+SIGK_D uint32_t digit_of(uint64_t key, int bit_lo, uint32_t digit_mask, const uint64_t *split) {
+    if (!SPLIT) return (uint32_t)(key >> bit_lo) & digit_mask;
+    const uint64_t code = sigk_key_code(key);
+    uint32_t d = 0;
+    for (uint32_t k = 0; k < digit_mask; ++k) d += code >= split[k] ? 1u : 0u;   // digit_mask = n_split
+    return d;
+}
+
+template <typename LB, bool SPLIT>
 __global__ void __launch_bounds__(OS_THREADS, OS_MIN_BLOCKS)
 onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                      uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
                      const uint64_t *__restrict__ n_ptr, int bit_lo, uint32_t digit_mask,
-                     const uint64_t *__restrict__ bin_base, LB *__restrict__ lookback, uint32_t *__restrict__ ticket) {
+                     const uint64_t *__restrict__ bin_base, LB *__restrict__ lookback, uint32_t *__restrict__ ticket,
+                     const uint64_t *__restrict__ split_codes) {
     using T = LBTraits<LB>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     OsSmem &sm = *reinterpret_cast<OsSmem *>(smem_raw);
@@ -81,6 +94,7 @@ onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__res
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint64_t n = *n_ptr;
     if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+    if (SPLIT && tid < digit_mask) sm.split[tid] = split_codes[tid];
     // zero the warp counters (as 32-bit words)
     {
         uint32_t *c32 = reinterpret_cast<uint32_t *>(&sm.cnt[0][0]);
@@ -111,7 +125,7 @@ onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__res
     uint16_t rank[OS_ITEMS];
 #pragma unroll
     for (int i = 0; i < OS_ITEMS; ++i) {
-        const uint32_t d = (uint32_t)(key[i] >> bit_lo) & digit_mask;
+        const uint32_t d = digit_of<SPLIT>(key[i], bit_lo, digit_mask, sm.split);
         unsigned peers = 0xffffffffu;
 #pragma unroll
         for (int b = 0; b < SIGK_RADIX_BITS; ++b) {
@@ -179,7 +193,7 @@ onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__res
     // ---- reorder the tile in shared memory (keys, then values by the same slots)
 #pragma unroll
     for (int i = 0; i < OS_ITEMS; ++i) {
-        const uint32_t d = (uint32_t)(key[i] >> bit_lo) & digit_mask;
+        const uint32_t d = digit_of<SPLIT>(key[i], bit_lo, digit_mask, sm.split);
         const uint32_t slot = (uint32_t)wcnt[d] + rank[i];
         rank[i] = (uint16_t)slot;
         sm.keys[slot] = key[i];
@@ -195,7 +209,7 @@ onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__res
     // ---- coalesced write-out: consecutive slots of one digit are consecutive in HBM
     for (uint32_t j = tid; j < tile_n; j += OS_THREADS) {
         const uint64_t k = sm.keys[j];
-        const uint32_t d = (uint32_t)(k >> bit_lo) & digit_mask;
+        const uint32_t d = digit_of<SPLIT>(k, bit_lo, digit_mask, sm.split);
         const uint64_t pos = sm.goff[d] + j;
         keys_out[pos] = k;
         vals_out[pos] = sm.vals[j];
@@ -256,9 +270,11 @@ size_t onesweep_lookback_bytes(uint64_t capacity) {
 }
 
 cudaError_t onesweep_configure() {
-    cudaError_t e = cudaFuncSetAttribute(onesweep_pass_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem));
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(onesweep_pass_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem));
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(onesweep_pass_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(onesweep_pass_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(onesweep_pass_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem))) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(onesweep_pass_kernel<uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem));
 }
 
 cudaError_t launch_histogram(const uint64_t *keys, const uint64_t *n_ptr, uint64_t capacity, const PassPlan &plan,
@@ -283,11 +299,27 @@ cudaError_t launch_onesweep_pass(const uint64_t *keys_in, const uint32_t *vals_i
     const unsigned tiles = (unsigned)onesweep_tiles(capacity);
     const uint32_t mask = (1u << nbits) - 1u;
     if (capacity >= (1ull << 30))
-        onesweep_pass_kernel<uint64_t><<<tiles, OS_THREADS, sizeof(OsSmem), stream>>>(
-            keys_in, vals_in, keys_out, vals_out, n_ptr, bit_lo, mask, bin_base, (uint64_t *)lookback, ticket);
+        onesweep_pass_kernel<uint64_t, false><<<tiles, OS_THREADS, sizeof(OsSmem), stream>>>(
+            keys_in, vals_in, keys_out, vals_out, n_ptr, bit_lo, mask, bin_base, (uint64_t *)lookback, ticket, nullptr);
     else
-        onesweep_pass_kernel<uint32_t><<<tiles, OS_THREADS, sizeof(OsSmem), stream>>>(
-            keys_in, vals_in, keys_out, vals_out, n_ptr, bit_lo, mask, bin_base, (uint32_t *)lookback, ticket);
+        onesweep_pass_kernel<uint32_t, false><<<tiles, OS_THREADS, sizeof(OsSmem), stream>>>(
+            keys_in, vals_in, keys_out, vals_out, n_ptr, bit_lo, mask, bin_base, (uint32_t *)lookback, ticket, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_onesweep_partition(const uint64_t *keys_in, const uint32_t *vals_in, uint64_t *keys_out,
+                                      uint32_t *vals_out, const uint64_t *n_ptr, uint64_t capacity,
+                                      const uint64_t *split_codes, int n_split, const uint64_t *bin_base, void *lookback,
+                                      uint32_t *ticket, cudaStream_t stream) {
+    if (capacity == 0) return cudaSuccess;
+    if (n_split < 1 || n_split > SORT_MAX_SPLIT) return cudaErrorInvalidValue;
+    const unsigned tiles = (unsigned)onesweep_tiles(capacity);
+    if (capacity >= (1ull << 30))
+        onesweep_pass_kernel<uint64_t, true><<<tiles, OS_THREADS, sizeof(OsSmem), stream>>>(
+            keys_in, vals_in, keys_out, vals_out, n_ptr, 0, (uint32_t)n_split, bin_base, (uint64_t *)lookback, ticket, split_codes);
+    else
+        onesweep_pass_kernel<uint32_t, true><<<tiles, OS_THREADS, sizeof(OsSmem), stream>>>(
+            keys_in, vals_in, keys_out, vals_out, n_ptr, 0, (uint32_t)n_split, bin_base, (uint32_t *)lookback, ticket, split_codes);
     return cudaGetLastError();
 }
 

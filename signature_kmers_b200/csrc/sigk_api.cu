@@ -5,8 +5,7 @@
 // columns.  sigk_build() = extract_kmers + process_kmers of the reference
 // (src/kmers-build-signatures.cc:194-196).  No CPU fallback exists: every
 // compute entry point needs a CUDA device and fails with SIGK_E_CUDA otherwise.
-#include "../../include/sigk.h"
-#include "kernels.h"
+#include "handle.h"
 #include "sigk_common.cuh"
 
 #include <algorithm>
@@ -19,108 +18,8 @@
 using namespace sigk;
 
 namespace {
-
 thread_local std::string g_create_error;
-
-struct DeviceScalars {
-    uint64_t n_records;
-    uint64_t n_segments;
-    uint64_t n_kept;
-    uint64_t n_seqs_sig;
-    uint32_t ticket[16];
-    uint32_t n_giant, next_giant, n_work, pad;
-};
-
-enum { TK_ENCODE = 0, TK_REDUCE = 1, TK_SQUEEZE = 2, TK_SORT0 = 4 };
-
-template <typename T> struct DevBuf {
-    T *p = nullptr;
-    size_t cap = 0;     // elements
-    cudaError_t reserve(size_t n) {
-        if (n <= cap) return cudaSuccess;
-        if (p) { cudaFree(p); p = nullptr; cap = 0; }
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
-        if (e == cudaSuccess) cap = n;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
-template <typename T> struct PinnedBuf {
-    T *p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t n) {
-        if (n <= cap) return cudaSuccess;
-        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
-        cudaError_t e = cudaMallocHost(&p, std::max<size_t>(n, 1) * sizeof(T));
-        if (e == cudaSuccess) cap = n;
-        return e;
-    }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
-};
-
-enum { EV_START, EV_H2D, EV_DEV0, EV_ENCODE, EV_HIST, EV_SORT, EV_REDUCE, EV_ORDER, EV_SQUEEZE, EV_D2H, EV_USER0, EV_USER1, EV_USER2, EV_USER3, EV_PASS0, EV_COUNT = EV_PASS0 + SORT_MAX_PASSES + 1 };
-
 }  // namespace
-
-struct sigk_handle {
-    sigk_config cfg{};
-    std::string error;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[EV_COUNT] = {};
-    int sm_count = 148;
-
-    sigk_proteins in{};
-    bool have_input = false, uploaded = false, built = false, downloaded = false;
-    uint64_t total_res = 0;
-    uint32_t max_seq_id = 0;
-
-    DevBuf<uint8_t> d_res;
-    DevBuf<uint64_t> d_starts;
-    DevBuf<uint16_t> d_func;
-    DevBuf<uint32_t> d_seqid, d_slice_prot;
-    DevBuf<uint4> d_meta, d_giant_side, d_rows;
-    DevBuf<uint64_t> d_giant_list;
-    DevBuf<OrderWork> d_work;
-    DevBuf<uint64_t> d_keys[2];
-    DevBuf<uint32_t> d_vals[2];
-    DevBuf<uint8_t> d_lookback;
-    DevBuf<uint64_t> d_hist, d_binbase, d_scan_state;
-    DevBuf<uint64_t> d_out_kmer;
-    DevBuf<uint16_t> d_out_cols;       // 5 columns of capacity rows
-    DevBuf<uint32_t> d_bitmap, d_distinct, d_swf;
-    DevBuf<DeviceScalars> d_scalars;
-    uint64_t capacity = 0;             // records the buffers are sized for
-    int sorted_in = 0;                 // which ping-pong buffer holds the sorted records
-
-    PinnedBuf<uint64_t> h_kmer;
-    PinnedBuf<uint16_t> h_cols;
-    PinnedBuf<uint32_t> h_distinct, h_swf;
-    PinnedBuf<DeviceScalars> h_scalars;
-    uint64_t h_rows = 0;
-
-    sigk_timings tm{};
-    float h2d_ms = 0;
-    PassPlan plan{};
-
-    int fail(int code, const char *fmt, ...) {
-        char buf[512];
-        va_list ap;
-        va_start(ap, fmt);
-        vsnprintf(buf, sizeof buf, fmt, ap);
-        va_end(ap);
-        error = buf;
-        return code;
-    }
-};
-
-#define CU(h, call)                                                                                          \
-    do {                                                                                                     \
-        cudaError_t e_ = (call);                                                                             \
-        if (e_ != cudaSuccess)                                                                               \
-            return (h)->fail(e_ == cudaErrorMemoryAllocation ? SIGK_E_NOMEM : SIGK_E_CUDA, "%s: %s (%s:%d)", #call, \
-                             cudaGetErrorString(e_), __FILE__, __LINE__);                                    \
-    } while (0)
 
 namespace {
 
@@ -131,9 +30,38 @@ int ensure_device(sigk_handle *h) {
 
 uint16_t *out_col(sigk_handle *h, int c) { return h->d_out_cols.p + (size_t)c * h->capacity; }
 
+}  // namespace
+
+namespace sigk {
+
+int ensure_capacity(sigk_handle *h, uint64_t cap, bool keep_pingpong1) {
+    // the multi-GPU path also sorts 16384 samples per rank through the same buffers
+    const uint64_t cap_lb = h->comm ? std::max<uint64_t>(cap, 16384ull * 16) : cap;
+    for (int i = 0; i < 2; ++i) {
+        if (i == 1 && keep_pingpong1) continue;
+        CU(h, h->d_keys[i].reserve(cap)); CU(h, h->d_vals[i].reserve(cap));
+    }
+    CU(h, h->d_lookback.reserve(onesweep_lookback_bytes(cap_lb) * SORT_MAX_PASSES));
+    CU(h, h->d_giant_side.reserve(reduce_side_entries(cap)));
+    CU(h, h->d_giant_list.reserve(reduce_giant_entries(cap)));
+    CU(h, h->d_work.reserve(reduce_work_entries(cap, h->sm_count)));
+    CU(h, h->d_rows.reserve(cap));
+    CU(h, h->d_out_kmer.reserve(cap));
+    CU(h, h->d_out_cols.reserve(cap * 5));
+    const uint64_t padded = encode_tiles(h->total_res) * ENC_TILE + ENC_PAD;
+    CU(h, h->d_scan_state.reserve(std::max(encode_scan_entries(padded), reduce_scan_entries(cap))));
+    if (cap > h->capacity) h->capacity = cap;
+    return SIGK_OK;
+}
+
+}  // namespace sigk
+
+namespace {
+
 int do_upload(sigk_handle *h) {
     if (!h->have_input) return h->fail(SIGK_E_INVALID, "sigk_set_proteins has not been called");
     if (int rc = ensure_device(h)) return rc;
+    if (h->cfg.world > 1 && !h->comm) return h->fail(SIGK_E_INVALID, "world > 1: call sigk_comm_join before building");
     const sigk_proteins &p = h->in;
     const uint64_t np = p.n_proteins;
     const uint64_t total = h->total_res;
@@ -143,32 +71,17 @@ int do_upload(sigk_handle *h) {
     CU(h, h->d_starts.reserve(np + 1));
     CU(h, h->d_func.reserve(np));
     CU(h, h->d_seqid.reserve(np));
-    CU(h, h->d_meta.reserve(np));
     CU(h, h->d_slice_prot.reserve(encode_slices(total) + 2));
-    // one record per residue position is the ceiling (every window valid)
-    const uint64_t cap = total;
-    if (cap > h->capacity) {
-        for (int i = 0; i < 2; ++i) { CU(h, h->d_keys[i].reserve(cap)); CU(h, h->d_vals[i].reserve(cap)); }
-        CU(h, h->d_lookback.reserve(onesweep_lookback_bytes(cap) * SORT_MAX_PASSES));
-        CU(h, h->d_giant_side.reserve(reduce_side_entries(cap)));
-        CU(h, h->d_giant_list.reserve(reduce_giant_entries(cap)));
-        CU(h, h->d_work.reserve(reduce_work_entries(cap, h->sm_count)));
-        CU(h, h->d_rows.reserve(cap));
-        CU(h, h->d_out_kmer.reserve(cap));
-        CU(h, h->d_out_cols.reserve(cap * 5));
-        const uint64_t tiles = std::max(encode_scan_entries(padded), reduce_scan_entries(cap));
-        CU(h, h->d_scan_state.reserve(tiles));
-        h->capacity = cap;
-    }
     CU(h, h->d_hist.reserve(SORT_MAX_PASSES * SIGK_RADIX));
     CU(h, h->d_binbase.reserve(SORT_MAX_PASSES * SIGK_RADIX));
-    CU(h, h->d_bitmap.reserve(((uint64_t)h->max_seq_id >> 5) + 1));
     CU(h, h->d_distinct.reserve(SIGK_N_FUNCTION_SLOTS));
     CU(h, h->d_swf.reserve(SIGK_N_FUNCTION_SLOTS));
     CU(h, h->d_scalars.reserve(1));
     CU(h, h->h_scalars.reserve(1));
     CU(h, h->h_distinct.reserve(SIGK_N_FUNCTION_SLOTS));
     CU(h, h->h_swf.reserve(SIGK_N_FUNCTION_SLOTS));
+    // one record per residue position is the ceiling (every window valid)
+    if (int rc = ensure_capacity(h, std::max<uint64_t>(total, h->capacity), false)) return rc;
 
     cudaStream_t st = h->stream;
     CU(h, cudaEventRecord(h->ev[EV_START], st));
@@ -183,6 +96,12 @@ int do_upload(sigk_handle *h) {
     CU(h, cudaEventRecord(h->ev[EV_H2D], st));
     CU(h, cudaStreamSynchronize(st));
     cudaEventElapsedTime(&h->h2d_ms, h->ev[EV_START], h->ev[EV_H2D]);
+    h->n_prot_global = np;
+    h->ordinal_base = 0;
+    h->max_seq_id = h->local_max_seq_id;
+    if (h->comm) { if (int rc = comm_exchange_shapes(h)) return rc; }
+    CU(h, h->d_meta.reserve(h->n_prot_global));
+    CU(h, h->d_bitmap.reserve(((uint64_t)h->max_seq_id >> 5) + 1));
     h->uploaded = true;
     h->built = h->downloaded = false;
     return SIGK_OK;
@@ -193,7 +112,6 @@ int do_build_device(sigk_handle *h) {
     if (int rc = ensure_device(h)) return rc;
     cudaStream_t st = h->stream;
     const uint64_t np = h->in.n_proteins;
-    const uint64_t cap = h->capacity;
     DeviceScalars *sc = h->d_scalars.p;
     uint32_t launches = 0;
 
@@ -205,11 +123,20 @@ int do_build_device(sigk_handle *h) {
     CU(h, cudaMemsetAsync(h->d_hist.p, 0, SORT_MAX_PASSES * SIGK_RADIX * sizeof(uint64_t), st));
 
     // ---- stage 1: encode
-    CU(h, launch_protein_meta(h->d_starts.p, h->d_func.p, h->d_seqid.p, (uint32_t)np, h->d_meta.p, h->d_swf.p, st)); ++launches;
+    CU(h, launch_protein_meta(h->d_starts.p, h->d_func.p, h->d_seqid.p, (uint32_t)np, h->d_meta.p + h->ordinal_base, h->d_swf.p, st)); ++launches;
+    if (h->comm) { if (int rc = comm_allgather_meta(h)) return rc; }
     CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, encode_scan_entries(h->total_res) * sizeof(uint64_t), st));
-    EncodeArgs ea{h->d_res.p, h->total_res, h->d_starts.p, (uint32_t)np, 0u, h->d_slice_prot.p};
+    EncodeArgs ea{h->d_res.p, h->total_res, h->d_starts.p, (uint32_t)np, (uint32_t)h->ordinal_base, h->d_slice_prot.p};
     CU(h, launch_encode(ea, h->d_keys[0].p, h->d_vals[0].p, h->d_scan_state.p, sc->ticket + TK_ENCODE, &sc->n_records, st)); ++launches;
     CU(h, cudaEventRecord(h->ev[EV_ENCODE], st));
+
+    // ---- multi-GPU: route every record to the rank that owns its k-mer range
+    if (h->comm) {
+        if (int rc = comm_partition_exchange(h, &launches)) return rc;
+        CU(h, cudaMemsetAsync(h->d_hist.p, 0, SORT_MAX_PASSES * SIGK_RADIX * sizeof(uint64_t), st));
+    }
+    CU(h, cudaEventRecord(h->ev[EV_EXCHANGE], st));
+    const uint64_t cap = h->capacity;
 
     // ---- stage 2: onesweep sort on the 43 code bits
     h->plan = make_pass_plan(SIGK_KEY_CODE_SHIFT, SIGK_KEY_CODE_SHIFT + SIGK_CODE_BITS);
@@ -249,6 +176,7 @@ int do_build_device(sigk_handle *h) {
     CU(h, cudaEventRecord(h->ev[EV_ORDER], st));
     CU(h, launch_squeeze_rows(h->d_rows.p, &sc->n_segments, cap, kc, h->d_scan_state.p + reduce_batches(cap) + 1,
                               sc->ticket + TK_SQUEEZE, &sc->n_kept, st)); ++launches;
+    if (h->comm) { if (int rc = comm_reduce_stats(h)) return rc; }
     CU(h, cudaEventRecord(h->ev[EV_SQUEEZE], st));
 
     h->tm.kernel_launches = launches;
@@ -289,7 +217,8 @@ int do_download(sigk_handle *h) {
     auto ms = [&](int a, int b) { float v = 0; cudaEventElapsedTime(&v, h->ev[a], h->ev[b]); return v; };
     t.h2d_ms = h->h2d_ms;
     t.encode_ms = ms(EV_DEV0, EV_ENCODE);
-    t.histogram_ms = ms(EV_ENCODE, EV_HIST);
+    t.exchange_ms = ms(EV_ENCODE, EV_EXCHANGE);
+    t.histogram_ms = ms(EV_EXCHANGE, EV_HIST);
     t.sort_ms = ms(EV_HIST, EV_SORT);
     t.reduce_ms = ms(EV_SORT, EV_REDUCE);
     t.order_stats_ms = ms(EV_REDUCE, EV_ORDER);
@@ -351,6 +280,7 @@ void sigk_destroy(sigk_handle *h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    comm_destroy(h);
     h->d_res.release(); h->d_starts.release(); h->d_func.release(); h->d_seqid.release(); h->d_meta.release(); h->d_slice_prot.release();
     for (int i = 0; i < 2; ++i) { h->d_keys[i].release(); h->d_vals[i].release(); }
     h->d_lookback.release(); h->d_hist.release(); h->d_binbase.release(); h->d_scan_state.release();
@@ -390,6 +320,7 @@ int sigk_set_proteins(sigk_handle *h, const sigk_proteins *p) {
     h->in = *p;
     h->total_res = total;
     h->max_seq_id = max_sid;
+    h->local_max_seq_id = max_sid;
     h->have_input = true;
     h->uploaded = h->built = h->downloaded = false;
     return SIGK_OK;
@@ -419,9 +350,10 @@ int sigk_result(sigk_handle *h, sigk_table *out) {
     out->mean = h->h_cols.p + 2 * h->h_rows;
     out->median = h->h_cols.p + 3 * h->h_rows;
     out->var = h->h_cols.p + 4 * h->h_rows;
-    out->n_occurrences = s.n_records;
-    out->n_distinct_kmers = s.n_segments;
-    out->distinct_signatures = s.n_kept;
+    // with a communicator the counters are whole-job sums; n_kept stays this rank's slice
+    out->n_occurrences = h->comm ? s.reduce_in[0] : s.n_records;
+    out->n_distinct_kmers = h->comm ? s.reduce_in[1] : s.n_segments;
+    out->distinct_signatures = h->comm ? s.reduce_in[2] : s.n_kept;
     out->num_seqs_with_a_signature = s.n_seqs_sig;
     out->distinct_functions = h->h_distinct.p;
     out->seqs_with_func = h->h_swf.p;
@@ -458,12 +390,15 @@ int sigk_event_elapsed_ms(sigk_handle *h, int slot_a, int slot_b, float *ms) {
 }
 
 int sigk_comm_make_id(void *id128) {
-    (void)id128;
-    return SIGK_E_UNSUPPORTED;
+    std::string err;
+    const int rc = comm_make_id(id128, &err);
+    if (rc) g_create_error = err;
+    return rc;
 }
 int sigk_comm_join(sigk_handle *h, const void *id128) {
-    (void)id128;
-    return h ? h->fail(SIGK_E_UNSUPPORTED, "multi-GPU exchange is not built yet") : SIGK_E_INVALID;
+    if (!h) return SIGK_E_INVALID;
+    h->uploaded = h->built = h->downloaded = false;
+    return comm_join(h, id128);
 }
 
 int sigk_dbg_encode(sigk_handle *h, const sigk_proteins *p, uint64_t *out_code, uint32_t *out_ordinal,
@@ -476,6 +411,7 @@ int sigk_dbg_encode(sigk_handle *h, const sigk_proteins *p, uint64_t *out_code, 
     CU(h, cudaMemsetAsync(sc, 0, sizeof(DeviceScalars), st));
     CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, encode_scan_entries(h->total_res) * sizeof(uint64_t), st));
     EncodeArgs ea{h->d_res.p, h->total_res, h->d_starts.p, (uint32_t)p->n_proteins, 0u, h->d_slice_prot.p};
+    if (h->comm) return h->fail(SIGK_E_UNSUPPORTED, "sigk_dbg_encode is single-GPU");
     CU(h, launch_encode(ea, h->d_keys[0].p, h->d_vals[0].p, h->d_scan_state.p, sc->ticket + TK_ENCODE, &sc->n_records, st));
     uint64_t n = 0;
     CU(h, cudaMemcpyAsync(&n, &sc->n_records, sizeof n, cudaMemcpyDeviceToHost, st));

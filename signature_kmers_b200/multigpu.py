@@ -1,0 +1,174 @@
+"""One process per GPU: launcher-side plumbing for the range-partitioned build.
+
+The data path (sampled splitters, stable partition, NCCL all-to-all, per-rank
+sort/reduce) lives in csrc/comm.cu behind sigk_comm_join + sigk_build;
+torch.distributed is used here only to ship the 128-byte communicator id,
+for barriers, and to combine timings.  Test/bench driver, not the product.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import time
+
+import numpy as np
+
+from . import capi
+from .capi import KeptTable, PackedProteins
+
+
+def rank_slice(n: int, rank: int, world: int):
+    """Contiguous chunk `rank` of n canonical positions (chunks in rank order = canonical order)."""
+    return n * rank // world, n * (rank + 1) // world
+
+
+def init_process_group():
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        backend = "cpu:gloo,cuda:nccl" if torch.cuda.is_available() else "gloo"
+        dist.init_process_group(backend=backend)
+    return dist
+
+
+def join_communicator(builder, rank: int, world: int):
+    """Rank 0 makes the NCCL id, everybody joins (sigk_comm_make_id / sigk_comm_join)."""
+    import torch.distributed as dist
+
+    lib = capi.load_library()
+    ident = [None]
+    if rank == 0:
+        buf = C.create_string_buffer(capi.SIGK_COMM_ID_BYTES)
+        rc = lib.sigk_comm_make_id(buf)
+        if rc != 0:
+            raise capi.SigkError(f"sigk_comm_make_id failed ({rc}): {lib.sigk_last_error(None).decode()}")
+        ident[0] = buf.raw
+    dist.broadcast_object_list(ident, src=0)
+    keep = C.create_string_buffer(ident[0], capi.SIGK_COMM_ID_BYTES)
+    rc = lib.sigk_comm_join(builder.h, keep)
+    if rc != 0:
+        raise capi.SigkError(f"sigk_comm_join failed ({rc}): {lib.sigk_last_error(builder.h).decode()}")
+
+
+def concat_tables(tables) -> KeptTable:
+    """Per-rank slices in rank order -> the whole kept table (counters are already job-wide)."""
+    t0 = tables[0]
+    cat = lambda name: np.concatenate([getattr(t, name) for t in tables])
+    return KeptTable(
+        kmer=np.concatenate([t.kmer for t in tables]).reshape(-1, 8),
+        avg_from_end=cat("avg_from_end"), function_index=cat("function_index"), mean=cat("mean"),
+        median=cat("median"), var=cat("var"),
+        n_occurrences=t0.n_occurrences, n_distinct_kmers=t0.n_distinct_kmers,
+        distinct_signatures=t0.distinct_signatures, num_seqs_with_a_signature=t0.num_seqs_with_a_signature,
+        distinct_functions=t0.distinct_functions, seqs_with_func=t0.seqs_with_func,
+    )
+
+
+def weak_scaling_params(workload: str, world: int) -> dict:
+    """Per-GPU work fixed at the single-GPU workload: world x the proteins and genomes; the
+    function count grows with it up to 60 000 (FunctionIndex is 16 bits, src/kmer_data.h:18)."""
+    from .synth import CONFIGS
+
+    kw = dict(CONFIGS[workload])
+    kw["n_functions"] = min(kw["n_functions"] * world, 60_000)
+    kw["n_proteins"] = kw["n_proteins"] * world
+    kw["n_genomes"] = kw["n_genomes"] * world
+    return kw
+
+
+def run_bench(args, rank, world, local_rank, metric, unit):
+    import torch
+    import torch.distributed as dist
+
+    from .builder import GpuSignatureBuilder
+    from .synth import Synth
+
+    dist = init_process_group()
+    torch.cuda.set_device(local_rank)
+    kw = weak_scaling_params(args.workload, world)
+    synth = Synth(**kw)
+    lo, hi = rank_slice(synth.n_proteins, rank, world)
+    builder = GpuSignatureBuilder(device=local_rank, rank=rank, world=world)
+    join_communicator(builder, rank, world)
+    proteins = synth.packed(lo, hi, out_alloc=builder.host_alloc)
+    builder.set_proteins(proteins)
+    builder.upload()
+    for _ in range(args.warmup):
+        builder.build_device()
+    builder.synchronize()
+    dist.barrier()
+
+    sampler = None
+    if rank == 0:
+        from bench import ClockSampler  # the launcher script
+
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        time.sleep(0.3)
+    dist.barrier()
+    torch.cuda.synchronize()
+    builder.event_record(0)
+    for _ in range(args.steps):
+        builder.build_device()
+    builder.event_record(1)
+    builder.synchronize()
+    dist.barrier()
+    dev_ms = builder.event_elapsed_ms(0, 1)
+    builder.download()
+    counts = builder.result_counts()
+    tm = builder.timings()
+
+    # end to end: pinned host arrays in, this rank's slice of the kept table back in host memory
+    builder.build(fetch=False)
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        builder.build(fetch=False)
+    dist.barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+
+    stats = torch.tensor([dev_ms, e2e_s, float(counts["n_kept"]), float(proteins.residues.nbytes + proteins.starts.nbytes
+                          + proteins.function_index.nbytes + proteins.seq_id.nbytes)], dtype=torch.float64)
+    mx = stats.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    sm = stats.clone()
+    dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    clk = sampler.stop() if sampler else None
+    if rank == 0:
+        occ = counts["n_occurrences"]          # job-wide after the statistics reduction
+        ms_per_step = float(mx[0]) / args.steps
+        passes = int(tm["sort_passes"])
+        line = {
+            "metric": metric, "value": occ / (ms_per_step * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"{args.workload} x {world} (weak scaling: {kw['n_proteins']} proteins, {kw['n_functions']} functions, "
+                                   f"{kw['n_genomes']} genomes; rank r encodes canonical chunk r)",
+                       "occurrences_per_step": occ, "distinct_kmers": counts["n_distinct_kmers"],
+                       "partition": "k-mer code ranges by sampled splitters, one NCCL all-to-all of 12-byte records",
+                       "K": 8, "record_bytes": 12, "sort_passes": passes,
+                       "l2": "inputs larger than L2", "timed": "max over ranks of CUDA-event time on the library stream"},
+            "clocks": clk,
+            "e2e": {"value": occ / float(mx[1]), "unit": unit, "h2d_bytes_per_step": int(sm[3]),
+                    "d2h_bytes_per_step": int(sm[2]) * 18, "ms_per_step": 1e3 * float(mx[1]),
+                    "api": "sigk_build per rank (C ABI, pinned host buffers)"},
+            "gpu_launches": int(tm["kernel_launches"]) * args.steps * world,
+            "roofline": None,
+            "rank0_stage_ms": {k: tm[k] for k in ("encode_ms", "exchange_ms", "histogram_ms", "sort_ms", "reduce_ms",
+                                                   "order_stats_ms", "squeeze_ms", "device_total_ms")},
+            "cpu_baseline": None,
+        }
+        pass_ms = list(tm["pass_ms"][:passes])
+        if pass_ms and tm["sort_ms"] > 0:
+            from bench import measured_peak_gbs
+
+            peak, src = measured_peak_gbs()
+            # rank 0's share of the records is what its pass kernel moved
+            line["roofline"] = {"bound": "hbm", "kernel": "onesweep_pass_kernel (rank 0)", "peak": peak, "unit": "GB/s",
+                                "peak_source": src, "pass_ms": pass_ms, "achieved": None, "frac": None, "traffic": None}
+        print(json.dumps(line), flush=True)
+    builder.close()
+    dist.barrier()
+    dist.destroy_process_group()

@@ -1,0 +1,68 @@
+"""Launched by torchrun (one process per GPU): the NCCL range-partitioned build
+against the CPU oracle and against the single-GPU build of the same proteins.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multigpu_check.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from signature_kmers_b200 import multigpu  # noqa: E402
+from signature_kmers_b200.builder import GpuSignatureBuilder  # noqa: E402
+from signature_kmers_b200.synth import Synth  # noqa: E402
+from tests.util import assert_tables_equal, pack, random_proteins  # noqa: E402
+
+
+def build_distributed(p_all, rank, world, local_rank):
+    import torch.distributed as dist
+
+    lo, hi = multigpu.rank_slice(p_all.n_proteins, rank, world)
+    b = GpuSignatureBuilder(device=local_rank, rank=rank, world=world)
+    multigpu.join_communicator(b, rank, world)
+    b.set_proteins(p_all.slice(lo, hi))
+    t = b.build()
+    again = b.build()                  # a second build on the same communicator gives the same slice
+    assert_tables_equal(t, again, what=f"rank {rank} rebuild")
+    parts = [None] * world
+    dist.all_gather_object(parts, t)
+    b.close()
+    return multigpu.concat_tables(parts), [x.n_kept for x in parts]
+
+
+def main():
+    import torch
+
+    rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    dist = multigpu.init_process_group()
+    torch.cuda.set_device(local_rank)
+    cases = []
+    seqs, funcs = random_proteins(71, n_families=60, members=(2, 30), length=(20, 300), sub_rate=0.08, n_functions=40)
+    cases.append(("random", pack(seqs, funcs)))
+    seqs, funcs = random_proteins(72, n_families=5, members=(100, 200), length=(100, 400), sub_rate=0.01, alphabet=b"ACDEF")
+    cases.append(("heavy duplication", pack(seqs, funcs)))
+    cases.append(("tiny", pack(["ACDEFGHIKLMNPQ", "ACDEFGHIKLMNPQ", "ACDEFGHIKLMNPQ", "WWWWWWWWWW"], [0, 0, 0, 1])))
+    cases.append(("synthetic 40K proteins", Synth(n_proteins=40_000, n_functions=400, n_genomes=8, seed=9).packed()))
+    for name, p_all in cases:
+        got, per_rank = build_distributed(p_all, rank, world, local_rank)
+        if rank == 0:
+            from oracle import oracle_c
+
+            want, _ = oracle_c.oracle_build(p_all)
+            assert_tables_equal(got, want, tier_b=True, what=name)
+            single = GpuSignatureBuilder(device=local_rank)
+            single.set_proteins(p_all)
+            assert_tables_equal(got, single.build(), tier_b=True, what=name + " vs one GPU")
+            single.close()
+            print(f"multigpu_check ok: {name}: {got.n_occurrences} occurrences, kept per rank {per_rank}", flush=True)
+        dist.barrier()
+    if rank == 0:
+        print("MULTIGPU_CHECK_PASSED", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
