@@ -256,7 +256,7 @@ def load_library(path: str | None = None) -> C.CDLL:
             f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(libsigk has no CPU fallback)"
         )
-    lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(p)
     lib.sigk_version.restype = C.c_char_p
     lib.sigk_device_count.restype = C.c_int
     lib.sigk_create.argtypes = [C.POINTER(SigkConfig), C.POINTER(C.c_void_p)]

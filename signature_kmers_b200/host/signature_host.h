@@ -1,0 +1,424 @@
+// signature_host.h — host side of the drop-in kmers-build-signatures: the
+// reference's input conventions restated in plain C++17 (no Boost, no TBB).
+//
+//   FastaReader          src/fasta_parser.{h,cc}  (same state machine, same quirks)
+//   FunctionMap          src/function_map.h:62-411
+//   path helpers         src/path_utils.h:17-101
+//   HostSignatureBuilder src/signature_build.{h,tcc}: the SignatureBuilder<K> API that
+//                        kmers-build-signatures.cc calls; extract_kmers packs the gated
+//                        proteins (tcc:83-160), process_kmers hands them to libsigk.
+#pragma once
+
+#include "../../include/sigk.h"
+#include "seed_text.h"
+
+#include <cctype>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <filesystem>
+#include <fstream>
+#include <functional>
+#include <iostream>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+namespace sigk_host {
+
+namespace fs = std::filesystem;
+
+// ---------------------------------------------------------------------------
+// FASTA: one record per '>' header; id = up to the first blank, def = the rest
+// of the header line INCLUDING its leading blank, seq = letters and '*'.
+// Quirks kept: CR dropped; '*' accepted mid-line but a line that
+// STARTS with a non-letter is reported and the character dropped; a blank
+// line keeps the record open; after a header-only record the next '>' is seen in
+// the "data" state and is reported as a bad character, so that header's letters
+// fall into the open record's sequence; the callback fires once more at end of
+// input with whatever is pending (an empty id when nothing is).
+class FastaReader {
+public:
+    using Callback = std::function<void(const std::string &id, const std::string &def, const std::string &seq)>;
+    explicit FastaReader(Callback cb, bool quiet = false) : cb_(std::move(cb)), quiet_(quiet) {}
+
+    void feed(const char *p, size_t n) { for (size_t i = 0; i < n; ++i) step(p[i]); }
+    void parse(std::istream &in) {
+        reset();
+        char buf[1 << 16];
+        while (in.read(buf, sizeof buf) || in.gcount()) feed(buf, (size_t)in.gcount());
+        finish();
+    }
+    // parse() of the reference ends with parse_complete(), and its callers call it again
+    void finish() { emit(); }
+
+private:
+    enum State { START, ID, DEF, DATA, LINE_START } st_ = START;
+    std::string id_, def_, seq_;
+    int line_ = 1;
+    Callback cb_;
+    bool quiet_;
+
+    void reset() { st_ = START; id_.clear(); def_.clear(); seq_.clear(); }
+    void emit() { cb_(id_, def_, seq_); id_.clear(); def_.clear(); seq_.clear(); }
+    void complain(const std::string &what) {
+        if (!quiet_) std::cerr << "Error found: " << what << " at line " << line_ << " id='" << id_ << "'" << std::endl;
+    }
+    void step(char c) {
+        if (c == '\n') ++line_;
+        if (c == '\r') return;
+        switch (st_) {
+        case START:
+            if (c == '>') st_ = ID; else complain("Missing >");
+            break;
+        case ID:
+            if (c == ' ' || c == '\t') { def_.push_back(c); st_ = DEF; }
+            else if (c == '\n') st_ = DATA;
+            else id_.push_back(c);
+            break;
+        case DEF:
+            if (c == '\n') st_ = DATA; else def_.push_back(c);
+            break;
+        case DATA:
+            if (c == '\n') st_ = LINE_START;
+            else if (std::isalpha((unsigned char)c) || c == '*') seq_.push_back(c);
+            else complain(std::string("Bad data character '") + c + "'");
+            break;
+        case LINE_START:
+            if (c == '>') { emit(); st_ = ID; }
+            else if (c == '\n') {}
+            else if (std::isalpha((unsigned char)c)) { seq_.push_back(c); st_ = DATA; }
+            else complain(std::string("Bad id or data character '") + c + "'");
+            break;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------
+// src/path_utils.h
+inline void populate_path_list(const std::vector<std::string> &dirs, std::vector<fs::path> &paths, bool sorted = false) {
+    for (const auto &dir : dirs) {
+        std::vector<fs::path> here;
+        for (const auto &ent : fs::directory_iterator(dir))        // readdir order, like boost::filesystem (:17-31)
+            if (fs::is_regular_file(ent.path())) here.push_back(ent.path());
+        if (sorted) std::sort(here.begin(), here.end());
+        paths.insert(paths.end(), here.begin(), here.end());
+    }
+}
+inline void load_strings(const std::vector<std::string> &files, std::vector<std::string> &out) {
+    for (const auto &f : files) {
+        std::ifstream in(f);
+        if (!in.good()) { std::cerr << "could not open " << f << "\n"; continue; }
+        std::string line;
+        while (std::getline(in, line, '\n')) out.push_back(line);
+    }
+}
+inline std::set<std::string> load_set_from_file(const fs::path &file) {
+    std::set<std::string> s;
+    if (!file.empty()) {
+        std::ifstream in(file);
+        std::string line;
+        while (std::getline(in, line, '\n')) s.insert(line);
+    }
+    return s;
+}
+inline void ensure_directory(const fs::path &dir) {
+    if (!dir.empty() && !fs::is_directory(dir) && !fs::create_directory(dir)) {
+        std::cerr << "Error creating " << dir << "\n";
+        std::exit(1);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// accumulator_set<float, stats<mean, median, variance, count>> of function_map.h:463 —
+// the per-function length statistics written to function.index (columns 3-7).  Same
+// algorithms as the hot path's accumulator but with float state (sample type float).
+struct FloatStats {
+    size_t n = 0;
+    float sum = 0, var = 0;
+    float q[5] = {0, 0, 0, 0, 0}, pos[5] = {1, 2, 3, 4, 5}, des[5] = {1, 2, 3, 4, 5};
+    void push(double x) {
+        static const float inc[5] = {0.f, 0.25f, 0.5f, 0.75f, 1.f};
+        ++n;
+        sum = (float)(sum + x);
+        if (n <= 5) {
+            q[n - 1] = (float)x;
+            if (n == 5) std::sort(q, q + 5);
+        } else {
+            size_t k;
+            if (x < q[0]) { q[0] = (float)x; k = 1; }
+            else if (q[4] <= x) { q[4] = (float)x; k = 4; }
+            else k = (size_t)(std::upper_bound(q, q + 5, x, [](double a, float b) { return a < b; }) - q);
+            for (size_t i = k; i < 5; ++i) pos[i] += 1.f;
+            for (size_t i = 0; i < 5; ++i) des[i] += inc[i];
+            for (size_t i = 1; i <= 3; ++i) {
+                const float d = des[i] - pos[i], dp = pos[i + 1] - pos[i], dm = pos[i - 1] - pos[i];
+                const float hp = (q[i + 1] - q[i]) / dp, hm = (q[i - 1] - q[i]) / dm;
+                if ((d >= 1.f && dp > 1.f) || (d <= -1.f && dm < -1.f)) {
+                    const short s = (short)(d / std::fabs(d));
+                    const float h = q[i] + s / (dp - dm) * ((s - dm) * hp + (dp - s) * hm);
+                    if (q[i - 1] < h && h < q[i + 1]) q[i] = h;
+                    else { if (d > 0) q[i] += hp; if (d < 0) q[i] -= hm; }
+                    pos[i] += s;
+                }
+            }
+        }
+        if (n > 1) {
+            const float tmp = (float)(x - (double)(sum / (float)n));
+            var = (var * (float)(n - 1)) / (float)n + (tmp * tmp) / (float)(n - 1);
+        }
+    }
+    double mean() const { return n ? sum / (float)n : 0.0; }
+    double median() const { return q[2]; }
+};
+
+// ---------------------------------------------------------------------------
+// src/function_map.h
+class FunctionMap {
+public:
+    void add_good_roles(const std::vector<std::string> &r) { good_roles_.insert(r.begin(), r.end()); }
+    void add_good_functions(const std::vector<std::string> &r) { good_functions_.insert(r.begin(), r.end()); }
+
+    // :62-104
+    void load_id_assignments(const fs::path &file) {
+        std::ifstream in(file);
+        std::string line;
+        int lineno = 0;
+        while (std::getline(in, line)) {
+            ++lineno;
+            const size_t s = line.find('\t');
+            if (s == std::string::npos) { std::cerr << "bad line " << lineno << " in file " << file << "\n"; continue; }
+            const size_t s2 = line.find('\t', s + 1);
+            const std::string id = line.substr(0, s);
+            const std::string func = s2 == std::string::npos ? line.substr(s + 1) : line.substr(s + 1, s2 - s - 1);
+            std::string stripped, delim, comment;
+            split_func_comment(func, stripped, delim, comment);
+            original_assignment_stripped_[id] = stripped;
+            original_assignment_[id] = func;
+            if (delim == "#" && is_truncated_comment(comment)) continue;     // keeps any earlier assignment (:93-98)
+            id_function_map_[id] = stripped;
+        }
+    }
+
+    // :120-238 — genome / function evidence from one FASTA file
+    void load_fasta_file(const fs::path &file, bool keep_function_flag, const std::set<std::string> &deleted_fids) {
+        std::ifstream in(file);
+        std::string genome;
+        FastaReader reader([&](const std::string &id, const std::string &def, const std::string &seq) {
+            if (id.empty() || deleted_fids.count(id)) return;
+            std::string func;
+            if (!def.empty()) {
+                const size_t x = def.find_first_not_of(" \t");
+                func = def.substr(x);           // npos -> throws like the reference would; defs are never all blank in practice
+            }
+            std::string genome_loc, m1;
+            if (match_genome_def(def, m1, genome_loc)) {        // "\s+(.*)\s+\[([^]]+)\]$"
+                std::string delim, comment;
+                split_func_comment(m1, func, delim, comment);
+                if (delim == "#" && is_truncated_comment(comment)) return;
+            } else genome_loc.clear();
+            if (genome.empty()) {
+                if (def.empty()) { std::string g; if (find_fig_genome(id, g)) genome = g; }
+                else if (!genome_loc.empty()) genome = genome_loc;
+            }
+            if (genome.empty()) {
+                genome = file.filename().string();
+                if (!is_genome_id(genome)) std::cerr << "cannot determine genome from file " << file << "\n";
+            }
+            const std::string cur = id_function_map_[id];       // operator[]: inserts an empty entry like the reference
+            if (cur.empty()) { if (!func.empty()) id_function_map_[id] = func; }
+            else func = cur;
+            if (!func.empty()) {
+                function_genome_map_[func].insert(genome);
+                if (keep_function_flag) good_functions_.insert(func);
+                function_stats_[func].push((double)seq.length());
+            }
+        });
+        reader.parse(in);
+        reader.finish();
+    }
+
+    // :257-332
+    void process_kept_functions(int min_reps_required, const std::set<std::string> &ignored) {
+        std::set<std::string> kept;
+        for (const auto &entry : function_genome_map_) {
+            const std::string &function = entry.first;
+            bool ok = (int)entry.second.size() >= min_reps_required || good_functions_.count(function);
+            if (!ok)
+                for (const auto &role : roles_of_function(function))
+                    if (good_roles_.count(role)) { ok = true; break; }
+            if (ok) kept.insert(function);
+        }
+        kept.insert("hypothetical protein");
+        for (const auto &fn : ignored) { std::cerr << "Ignore '" << fn << "'\n"; kept.erase(fn); }
+        unsigned short next = 0;                                  // wraps at 65536 like the reference (:324-330)
+        for (const auto &f : kept) {
+            const unsigned short id = next++;
+            function_index_map_[f] = id;
+            index_function_map_[id] = f;
+        }
+        std::cout << "kept " << next << " functions\n";
+    }
+
+    std::string lookup_function(const std::string &id) const {
+        auto it = id_function_map_.find(id);
+        return it == id_function_map_.end() ? std::string() : it->second;
+    }
+    std::string lookup_function(uint16_t idx) const {
+        auto it = index_function_map_.find(idx);
+        return it == index_function_map_.end() ? std::string() : it->second;
+    }
+    uint16_t lookup_index(const std::string &func) const {
+        auto it = function_index_map_.find(func);
+        return it == function_index_map_.end() ? (uint16_t)0xFFFF : it->second;
+    }
+
+    // :389-411  idx \t function \t count \t mean \t median \t var \t dev
+    void write_function_index(const fs::path &dir) {
+        std::ofstream of(dir / "function.index");
+        std::map<int, std::string> by_index;
+        for (const auto &e : function_index_map_) by_index.insert({e.second, e.first});
+        for (const auto &e : by_index) {
+            const FloatStats &a = function_stats_[e.second];
+            const double mean = a.mean(), median = a.median(), var = a.var;
+            of << e.first << "\t" << e.second << "\t" << (int)a.n << "\t" << mean << "\t" << median << "\t" << var << "\t"
+               << std::sqrt(var) << "\n";
+        }
+    }
+
+private:
+    // regex_match(def, "\\s+(.*)\\s+\\[([^]]+)\\]$"): leading blanks (all of them, greedy), greedy (.*),
+    // one blank, "[genome]" at the very end; the greedy (.*) makes the rightmost usable '[' win.
+    static bool match_genome_def(const std::string &def, std::string &m1, std::string &genome) {
+        const size_t n = def.size();
+        if (n < 4 || def[n - 1] != ']') return false;
+        size_t a = 0;
+        while (a < n && is_space(def[a])) ++a;
+        if (a == 0) return false;
+        for (size_t lb = n - 2; lb >= 1; --lb) {
+            if (def[lb] == ']') return false;                     // the bracket body may not hold a ']'
+            if (def[lb] != '[') continue;
+            if (lb + 1 == n - 1) continue;                        // empty body: [^]]+ needs a character
+            if (!is_space(def[lb - 1])) continue;
+            if (a >= lb) {                                        // nothing but blanks before '[': two \s+ need two blanks
+                if (lb < 2) return false;
+                m1.clear();
+            } else m1 = def.substr(a, lb - 1 - a);
+            genome = def.substr(lb + 1, n - lb - 2);
+            return true;
+        }
+        return false;
+    }
+    static bool find_fig_genome(const std::string &id, std::string &g) {      // "fig\|(\d+\.\d+)"
+        for (size_t p = id.find("fig|"); p != std::string::npos; p = id.find("fig|", p + 1)) {
+            size_t a = p + 4, b = a;
+            while (b < id.size() && std::isdigit((unsigned char)id[b])) ++b;
+            if (b == a || b >= id.size() || id[b] != '.') continue;
+            size_t c = b + 1, d = c;
+            while (d < id.size() && std::isdigit((unsigned char)id[d])) ++d;
+            if (d == c) continue;
+            g = id.substr(a, d - a);
+            return true;
+        }
+        return false;
+    }
+    static bool is_genome_id(const std::string &s) {                          // "\d+\.\d+" full match
+        size_t b = 0;
+        while (b < s.size() && std::isdigit((unsigned char)s[b])) ++b;
+        if (b == 0 || b >= s.size() || s[b] != '.') return false;
+        size_t d = b + 1;
+        while (d < s.size() && std::isdigit((unsigned char)s[d])) ++d;
+        return d > b + 1 && d == s.size();
+    }
+
+    std::map<std::string, std::set<std::string>> function_genome_map_;
+    std::map<std::string, std::string> id_function_map_;
+    std::map<std::string, uint16_t> function_index_map_;
+    std::map<uint16_t, std::string> index_function_map_;
+    std::set<std::string> good_roles_, good_functions_;
+    std::map<std::string, std::string> original_assignment_stripped_, original_assignment_;
+    std::map<std::string, FloatStats> function_stats_;
+};
+
+// ---------------------------------------------------------------------------
+// src/signature_build.{h,tcc}: same public calls, in the order main() makes them.
+class HostSignatureBuilder {
+public:
+    HostSignatureBuilder(int n_threads, int max_seqs_per_file) : max_seqs_per_file_(max_seqs_per_file) { (void)n_threads; }
+
+    void load_function_data(const std::vector<std::string> &good_functions, const std::vector<std::string> &good_roles,
+                            const std::vector<fs::path> &defs) {
+        fm_.add_good_roles(good_roles);
+        fm_.add_good_functions(good_functions);
+        for (const auto &d : defs) fm_.load_id_assignments(d);
+    }
+    void load_fasta(const std::vector<fs::path> &files, bool /*keep_functions: dropped by the reference, tcc:32*/,
+                    const std::set<std::string> &deleted) {
+        for (const auto &f : files) { fm_.load_fasta_file(f, false, deleted); all_fasta_data_.push_back(f); }
+    }
+    void process_kept_functions(int min_reps, const fs::path &out_dir, const std::set<std::string> &ignored) {
+        fm_.process_kept_functions(min_reps, ignored);
+        if (!out_dir.empty()) fm_.write_function_index(out_dir);
+    }
+
+    // tcc:47-160 with the window loop removed: the gated proteins are packed in canonical order
+    void extract_kmers(const std::set<std::string> &deleted) {
+        residues_.clear(); starts_.assign(1, 0); func_.clear(); seq_id_.clear();
+        for (unsigned i = 0; i < all_fasta_data_.size(); ++i) {
+            std::ifstream in(all_fasta_data_[i]);
+            unsigned next_sequence_id = i * (unsigned)max_seqs_per_file_;                  // :91
+            FastaReader reader([&](const std::string &id, const std::string &, const std::string &seq) {
+                if (deleted.count(id)) return;                                              // :94
+                if (id.empty()) return;                                                     // :122
+                const std::string func = fm_.lookup_function(id);
+                if (func.empty()) return;                                                   // :133
+                const unsigned seq_id = next_sequence_id++;                                 // :138
+                const uint16_t fi = fm_.lookup_index(func);
+                if (fi == 0xFFFF) return;                                                   // :155
+                residues_.insert(residues_.end(), seq.begin(), seq.end());
+                starts_.push_back(residues_.size());
+                func_.push_back(fi);
+                seq_id_.push_back(seq_id);
+            }, true);
+            reader.parse(in);
+            reader.finish();
+        }
+    }
+
+    sigk_proteins packed() const {
+        return sigk_proteins{residues_.data(), starts_.data(), func_.data(), seq_id_.data(), (uint64_t)func_.size()};
+    }
+
+    // tcc:183-213 on the GPU
+    int process_kmers(int device, sigk_table *table) {
+        sigk_config cfg{SIGK_ABI_VERSION, SIGK_K, device, 0, 1, 0};
+        if (int rc = sigk_create(&cfg, &h_)) { std::cerr << "sigk_create: " << sigk_last_error(nullptr) << "\n"; return rc; }
+        const sigk_proteins p = packed();
+        int rc = sigk_set_proteins(h_, &p);
+        if (!rc) rc = sigk_build(h_);
+        if (!rc) rc = sigk_result(h_, table);
+        if (rc) { std::cerr << "libsigk: " << sigk_last_error(h_) << "\n"; return rc; }
+        std::cout << "Kept " << table->n_kept << " kmers\n";
+        std::cout << "distinct_signatures=" << table->distinct_signatures << "\n";
+        std::cout << "num_seqs_with_a_signature=" << table->num_seqs_with_a_signature << "\n";
+        return 0;
+    }
+    ~HostSignatureBuilder() { if (h_) sigk_destroy(h_); }
+
+    std::string lookup_function(uint16_t idx) const { return fm_.lookup_function(idx); }
+    const std::vector<fs::path> &all_fasta_data() const { return all_fasta_data_; }
+    const FunctionMap &function_map() const { return fm_; }
+
+private:
+    int max_seqs_per_file_;
+    FunctionMap fm_;
+    std::vector<fs::path> all_fasta_data_;
+    std::vector<uint8_t> residues_;
+    std::vector<uint64_t> starts_;
+    std::vector<uint16_t> func_;
+    std::vector<uint32_t> seq_id_;
+    sigk_handle *h_ = nullptr;
+};
+
+}  // namespace sigk_host

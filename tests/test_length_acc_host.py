@@ -15,7 +15,7 @@ HARNESS = os.path.join(ROOT, "tests", "host_harness")
 @pytest.fixture(scope="module")
 def hostacc():
     so = os.path.join(HARNESS, "liblength_acc_host.so")
-    subprocess.run(["g++", "-O3", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I/usr/local/cuda/include",
+    subprocess.run(["g++", "-O3", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wl,--exclude-libs,ALL", "-I/usr/local/cuda/include",
                     "-I" + os.path.join(ROOT, "signature_kmers_b200", "csrc"), "-o", so,
                     os.path.join(HARNESS, "length_acc_host.cpp")], check=True)
     lib = C.CDLL(so)
