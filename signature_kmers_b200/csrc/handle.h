@@ -19,7 +19,7 @@ struct DeviceScalars {
     uint64_t n_kept;
     uint64_t n_seqs_sig;
     uint32_t ticket[16];
-    uint32_t n_giant, next_giant, n_work, pad;
+    uint32_t n_giant, next_giant, n_work, n_work_long, next_work_long, pad[3];
     uint64_t reduce_in[4];      // multi-GPU: {occurrences, groups, kept, -} of this rank -> summed over ranks
 };
 
@@ -77,7 +77,7 @@ struct sigk_handle {
     sigk::DevBuf<uint32_t> d_seqid, d_slice_prot;
     sigk::DevBuf<uint4> d_meta, d_giant_side, d_rows;
     sigk::DevBuf<uint64_t> d_giant_list;
-    sigk::DevBuf<sigk::OrderWork> d_work;
+    sigk::DevBuf<sigk::OrderWork> d_work, d_work_long;
     sigk::DevBuf<uint64_t> d_keys[2];
     sigk::DevBuf<uint32_t> d_vals[2];
     sigk::DevBuf<uint8_t> d_lookback;

@@ -89,6 +89,7 @@ inline uint64_t reduce_scan_entries(uint64_t capacity) { return reduce_batches(c
 size_t reduce_side_entries(uint64_t capacity);                 // uint4 entries of the giant side table
 size_t reduce_giant_entries(uint64_t capacity);                // 8-byte entries of the giant list
 size_t reduce_work_entries(uint64_t capacity, int sm_count);   // OrderWork entries
+size_t reduce_long_work_entries(uint64_t capacity);            // OrderWork entries of groups walked by a whole warp
 cudaError_t reduce_configure();
 
 // meta[i] = {protein_length, seq_id, function_index, 0}; seqs_with_func[f]++ (src/signature_build.tcc:160)
@@ -103,10 +104,12 @@ cudaError_t launch_giant_prepass(const uint64_t *keys, const uint32_t *vals, con
 // need the ordered walk.  scan_state: reduce_batches()+1 zeroed words.
 cudaError_t launch_stream_reduce(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
                                  const uint4 *meta, const uint4 *giant_side, uint4 *rows, OrderWork *work, uint32_t *n_work,
+                                 OrderWork *work_long, uint32_t *n_work_long,
                                  uint32_t *bitmap, uint32_t *distinct_functions, uint64_t *scan_state, uint32_t *ticket,
                                  uint64_t *n_seg_out, int order_stats, int sm_count, cudaStream_t stream);
 // median / var of the groups listed in `work`, patched into their rows.
 cudaError_t launch_order_stats(const uint32_t *vals, const uint4 *meta, const OrderWork *work, const uint32_t *n_work,
+                               const OrderWork *work_long, const uint32_t *n_work_long, uint32_t *next_long,
                                uint64_t capacity, uint4 *rows, int sm_count, cudaStream_t stream);
 // Compaction: kept rows -> table columns (tombstones dropped, order kept).  scan_state: squeeze_tiles()+1 zeroed words.
 cudaError_t launch_squeeze_rows(const uint4 *rows, const uint64_t *n_seg_ptr, uint64_t capacity, KeptColumns out,

@@ -213,6 +213,7 @@ giant_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
 //                  z = function_index | mean << 16; w = median | var << 16
 constexpr int RED_THREADS = 128;
 constexpr int WORK_BLOCK = 64;          // order-statistics work slots a warp reserves at a time
+constexpr uint32_t ORD_LONG = 4096;     // groups above this are walked by a whole warp (the tail); below, a lane each
 
 struct WorkCursor { uint32_t base, free; };
 
@@ -230,7 +231,8 @@ __global__ void __launch_bounds__(RED_THREADS)
 stream_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                      const uint64_t *__restrict__ n_ptr, const uint4 *__restrict__ meta,
                      const uint4 *__restrict__ giant_side, uint4 *__restrict__ rows, OrderWork *__restrict__ work,
-                     uint32_t *__restrict__ n_work, uint32_t *__restrict__ bitmap, uint32_t *__restrict__ distinct_functions,
+                     uint32_t *__restrict__ n_work, OrderWork *__restrict__ work_long, uint32_t *__restrict__ n_work_long,
+                     uint32_t *__restrict__ bitmap, uint32_t *__restrict__ distinct_functions,
                      uint64_t *__restrict__ scan_state, uint32_t *__restrict__ ticket, uint64_t *__restrict__ n_seg_out,
                      int order_stats) {
     const unsigned lane = threadIdx.x & 31u;
@@ -299,15 +301,17 @@ stream_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restri
                         r = reduce_long_segment(keys, vals, meta, cur, glen, bitmap);
                     }
                     const bool walk = r.keep && order_stats;          // best_count >= 27 here
-                    if (walk) work_reserve(wc, 1u, work, n_work);
+                    const bool walk_long = walk && glen > ORD_LONG;   // whole-warp walk (order_stats_long_kernel)
+                    if (walk && !walk_long) work_reserve(wc, 1u, work, n_work);
                     if (lane == 0) {
                         if (r.keep) {
                             rows[g] = make_uint4((uint32_t)code, (uint32_t)(code >> 32) | (r.avg << 11), r.func | (r.mean << 16), 0u);
                             atomicAdd(distinct_functions + r.func, 1u);                 // tcc:286
-                            if (walk) work[wc.base] = OrderWork{(uint32_t)g, (uint32_t)cur, glen};
+                            if (walk_long) work_long[atomicAdd(n_work_long, 1u)] = OrderWork{(uint32_t)g, (uint32_t)cur, glen};
+                            else if (walk) work[wc.base] = OrderWork{(uint32_t)g, (uint32_t)cur, glen};
                         } else rows[g] = make_uint4(0u, 0u, 0xFFFFu, 0u);
                     }
-                    if (walk) { wc.base += 1; wc.free -= 1; }
+                    if (walk && !walk_long) { wc.base += 1; wc.free -= 1; }
                     g += 1;
                     cur += glen;
                     continue;
@@ -534,6 +538,42 @@ order_stats_kernel(const uint32_t *__restrict__ vals, const uint4 *__restrict__ 
     }
 }
 
+// Groups of more than ORD_LONG records: one warp per group.  The recurrences stay sequential, but
+// the warp fetches 32 records at a time (coalesced values, 32 meta gathers in flight, the next
+// batch prefetched) and every lane runs the same accumulator on shuffled samples, so a group no
+// longer pays two dependent memory latencies per record (524 ms -> see profiles/ on the Zipf set).
+__global__ void __launch_bounds__(128)
+order_stats_long_kernel(const uint32_t *__restrict__ vals, const uint4 *__restrict__ meta, const OrderWork *__restrict__ work,
+                        const uint32_t *__restrict__ n_work, uint32_t *__restrict__ next, uint4 *__restrict__ rows) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t total = *n_work;
+    for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(next, 1u);
+        i = __shfl_sync(FULL, i, 0);
+        if (i >= total) return;
+        const OrderWork w = work[i];
+        const uint32_t cand = rows[w.row].z & 0xFFFFu;
+        LengthAcc acc;
+        // newest first: batch b covers records count-1-32b-lane
+        int64_t j = (int64_t)w.count - 1 - (int64_t)lane;
+        uint4 m = j >= 0 ? __ldg(meta + __ldg(vals + (uint64_t)w.start + j)) : make_uint4(0, 0, 0xFFFFFFFFu, 0);
+        for (int64_t left = w.count; left > 0; left -= 32) {
+            const int64_t jn = j - 32;
+            const uint4 mn = (left > 32 && jn >= 0) ? __ldg(meta + __ldg(vals + (uint64_t)w.start + jn)) : make_uint4(0, 0, 0xFFFFFFFFu, 0);
+            const int take = left < 32 ? (int)left : 32;
+            for (int l = 0; l < take; ++l) {
+                const uint32_t f = __shfl_sync(FULL, m.z, l);
+                const uint32_t x = __shfl_sync(FULL, m.x, l);
+                if (f == cand) acc.push(x);                                 // acc(item.protein_length), tcc:271
+            }
+            m = mn;
+            j = jn;
+        }
+        if (lane == 0) rows[w.row].w = u16_from_double(acc.q2) | (u16_from_double(acc.var) << 16);
+    }
+}
+
 __global__ void popcount_kernel(const uint32_t *__restrict__ bitmap, uint64_t n_words, uint64_t *__restrict__ out) {
     uint64_t c = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (uint64_t)gridDim.x * blockDim.x)
@@ -557,6 +597,7 @@ __global__ void protein_meta_kernel(const uint64_t *__restrict__ starts, const u
 
 size_t reduce_side_entries(uint64_t capacity) { return (size_t)(capacity / 32 + 2); }
 size_t reduce_giant_entries(uint64_t capacity) { return (size_t)(capacity / GIANT_STRIDE + 2); }
+size_t reduce_long_work_entries(uint64_t capacity) { return (size_t)(capacity / ORD_LONG + 2); }
 static int reduce_grid(int sm_count) { return sm_count * 12; }
 size_t reduce_work_entries(uint64_t capacity, int sm_count) {
     // a walked group has >= 3 records; every warp of the persistent grid can strand one reserved block
@@ -590,6 +631,7 @@ cudaError_t launch_giant_prepass(const uint64_t *keys, const uint32_t *vals, con
 
 cudaError_t launch_stream_reduce(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
                                  const uint4 *meta, const uint4 *giant_side, uint4 *rows, OrderWork *work, uint32_t *n_work,
+                                 OrderWork *work_long, uint32_t *n_work_long,
                                  uint32_t *bitmap, uint32_t *distinct_functions, uint64_t *scan_state, uint32_t *ticket,
                                  uint64_t *n_seg_out, int order_stats, int sm_count, cudaStream_t stream) {
     if (capacity == 0) return cudaSuccess;
@@ -597,14 +639,19 @@ cudaError_t launch_stream_reduce(const uint64_t *keys, const uint32_t *vals, con
     const uint64_t want = (reduce_batches(capacity) + RED_THREADS / 32 - 1) / (RED_THREADS / 32);
     if (grid > want) grid = want;
     stream_reduce_kernel<<<(unsigned)grid, RED_THREADS, 0, stream>>>(keys, vals, n_ptr, meta, giant_side, rows, work, n_work,
-                                                                     bitmap, distinct_functions, scan_state, ticket, n_seg_out,
+                                                                     work_long, n_work_long, bitmap, distinct_functions, scan_state, ticket, n_seg_out,
                                                                      order_stats);
     return cudaGetLastError();
 }
 
 cudaError_t launch_order_stats(const uint32_t *vals, const uint4 *meta, const OrderWork *work, const uint32_t *n_work,
+                               const OrderWork *work_long, const uint32_t *n_work_long, uint32_t *next_long,
                                uint64_t capacity, uint4 *rows, int sm_count, cudaStream_t stream) {
     if (capacity == 0) return cudaSuccess;
+    // the long groups first: they are the tail
+    order_stats_long_kernel<<<sm_count * 8, 128, 0, stream>>>(vals, meta, work_long, n_work_long, next_long, rows);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
     order_stats_kernel<<<sm_count * 16, ORD_THREADS, 0, stream>>>(vals, meta, work, n_work, rows);
     return cudaGetLastError();
 }

@@ -45,6 +45,7 @@ int ensure_capacity(sigk_handle *h, uint64_t cap, bool keep_pingpong1) {
     CU(h, h->d_giant_side.reserve(reduce_side_entries(cap)));
     CU(h, h->d_giant_list.reserve(reduce_giant_entries(cap)));
     CU(h, h->d_work.reserve(reduce_work_entries(cap, h->sm_count)));
+    CU(h, h->d_work_long.reserve(reduce_long_work_entries(cap)));
     CU(h, h->d_rows.reserve(cap));
     CU(h, h->d_out_kmer.reserve(cap));
     CU(h, h->d_out_cols.reserve(cap * 5));
@@ -168,11 +169,11 @@ int do_build_device(sigk_handle *h) {
                                &sc->n_giant, &sc->next_giant, h->d_giant_side.p, h->d_bitmap.p, h->sm_count, st));
     launches += cap > 512 ? 2 : 0;
     CU(h, launch_stream_reduce(h->d_keys[cur].p, h->d_vals[cur].p, &sc->n_records, cap, h->d_meta.p, h->d_giant_side.p,
-                               h->d_rows.p, h->d_work.p, &sc->n_work, h->d_bitmap.p, h->d_distinct.p, h->d_scan_state.p,
+                               h->d_rows.p, h->d_work.p, &sc->n_work, h->d_work_long.p, &sc->n_work_long, h->d_bitmap.p, h->d_distinct.p, h->d_scan_state.p,
                                sc->ticket + TK_REDUCE, &sc->n_segments, order_stats, h->sm_count, st)); ++launches;
     CU(h, launch_popcount(h->d_bitmap.p, ((uint64_t)h->max_seq_id >> 5) + 1, &sc->n_seqs_sig, st)); ++launches;
     CU(h, cudaEventRecord(h->ev[EV_REDUCE], st));
-    if (order_stats) { CU(h, launch_order_stats(h->d_vals[cur].p, h->d_meta.p, h->d_work.p, &sc->n_work, cap, h->d_rows.p, h->sm_count, st)); ++launches; }
+    if (order_stats) { CU(h, launch_order_stats(h->d_vals[cur].p, h->d_meta.p, h->d_work.p, &sc->n_work, h->d_work_long.p, &sc->n_work_long, &sc->next_work_long, cap, h->d_rows.p, h->sm_count, st)); launches += 2; }
     CU(h, cudaEventRecord(h->ev[EV_ORDER], st));
     CU(h, launch_squeeze_rows(h->d_rows.p, &sc->n_segments, cap, kc, h->d_scan_state.p + reduce_batches(cap) + 1,
                               sc->ticket + TK_SQUEEZE, &sc->n_kept, st)); ++launches;
@@ -284,7 +285,7 @@ void sigk_destroy(sigk_handle *h) {
     h->d_res.release(); h->d_starts.release(); h->d_func.release(); h->d_seqid.release(); h->d_meta.release(); h->d_slice_prot.release();
     for (int i = 0; i < 2; ++i) { h->d_keys[i].release(); h->d_vals[i].release(); }
     h->d_lookback.release(); h->d_hist.release(); h->d_binbase.release(); h->d_scan_state.release();
-    h->d_giant_side.release(); h->d_giant_list.release(); h->d_work.release(); h->d_rows.release(); h->d_out_kmer.release(); h->d_out_cols.release();
+    h->d_giant_side.release(); h->d_giant_list.release(); h->d_work.release(); h->d_work_long.release(); h->d_rows.release(); h->d_out_kmer.release(); h->d_out_cols.release();
     h->d_bitmap.release(); h->d_distinct.release(); h->d_swf.release(); h->d_scalars.release();
     h->h_kmer.release(); h->h_cols.release(); h->h_distinct.release(); h->h_swf.release(); h->h_scalars.release();
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);

@@ -41,6 +41,8 @@ def streams():
     yield list(range(1, 200))
     yield list(range(200, 0, -1))
     yield [5, 5, 5, 5, 5, 1, 9, 5, 5, 1, 9, 9, 9, 1, 1]
+    yield [0] * 40 + [3] + [0] * 40                     # zero heights: signed zeros in the equal-neighbour shortcut
+    yield [300] * 200 + [290] + [300] * 300 + [310, 310] + [300] * 100
     for n in (1, 2, 3, 4, 5, 6, 7, 8, 9, 17, 100, 1000, 5000):
         yield rng.integers(50, 3000, n)
         yield rng.integers(290, 310, n)                 # many ties: upper_bound and <= paths
