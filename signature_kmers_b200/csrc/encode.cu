@@ -112,8 +112,7 @@ encode_kernel(EncodeArgs a, uint64_t *__restrict__ keys, uint32_t *__restrict__ 
         if (lane >= (unsigned)o) incl += y;
     }
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    const uint64_t base = chained_scan_exclusive_warp(scan_state, sub, total);
-    if (last_sub && lane == 0) *n_out = base + total;
+    chained_scan_publish_warp(scan_state, sub, total);     // resolved after pass B: the predecessors publish meanwhile
 
     // pass B: roll the code, emit valid windows to their compacted slots
     {
@@ -136,6 +135,8 @@ encode_kernel(EncodeArgs a, uint64_t *__restrict__ keys, uint32_t *__restrict__ 
         }
     }
     __syncwarp();
+    const uint64_t base = chained_scan_resolve_warp(scan_state, sub, total);
+    if (last_sub && lane == 0) *n_out = base + total;
     for (uint32_t o = lane; o < total; o += 32) {
         const int slot = stage_slot((int)o);
         keys[base + o] = sm.keys[warp][slot];

@@ -400,7 +400,10 @@ stream_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restri
             if (head && act) {
                 const uint64_t gi = g + __popc(H & mask_lt(lane));
                 if (keep) {
-                    const uint32_t mean = best_count == 1 ? S : S / best_count;                 // u16((double)S / n), exact
+                    // u16((double)S / n) = floor(S / best_count), S < 65536, best_count <= 32: float quotient, fixed up
+                    uint32_t mean = (uint32_t)__float2uint_rz(__fmul_rn((float)S, __frcp_rn((float)best_count)));
+                    if (mean * best_count > S) --mean;
+                    else if ((mean + 1u) * best_count <= S) ++mean;
                     rows[gi] = make_uint4((uint32_t)code, (uint32_t)(code >> 32) | (sel << 11), cand | (mean << 16), var2 << 16);
                     atomicAdd(distinct_functions + cand, 1u);                                   // tcc:286
                     if (walk) work[wc.base + __popc(wb & mask_lt(lane))] = OrderWork{(uint32_t)gi, (uint32_t)p, cnt};
@@ -463,8 +466,14 @@ squeeze_rows_kernel(const uint4 *__restrict__ rows, const uint64_t *__restrict__
     uint32_t total;
     const uint32_t excl = block_exclusive_scan<SQ_THREADS>(lane == 0 ? warp_total : 0u, s_scan, &total);
     uint32_t run = __shfl_sync(FULL, excl, 0);
+    if (tid == 0) chained_scan_publish(scan_state, tile, total);
+    // the code -> ASCII expansion needs nothing from the other tiles: do it while they publish
+    uint64_t ascii[SQ_ITEMS];
+#pragma unroll
+    for (int i = 0; i < SQ_ITEMS; ++i)
+        ascii[i] = code_to_ascii_pairs((uint64_t)row[i].x | ((uint64_t)(row[i].y & 0x7FFu) << 32));
     if (tid == 0) {
-        const uint64_t base = chained_scan_exclusive(scan_state, tile, total);
+        const uint64_t base = chained_scan_resolve(scan_state, tile, total);
         s_base = base;
         if (tile_start + SQ_TILE >= n_seg) *n_kept_out = base + total;
     }
@@ -474,8 +483,7 @@ squeeze_rows_kernel(const uint4 *__restrict__ rows, const uint64_t *__restrict__
     for (int i = 0; i < SQ_ITEMS; ++i) {
         if ((ball[i] >> lane) & 1u) {
             const uint64_t o = base + run + __popc(ball[i] & mask_lt(lane));
-            const uint64_t code = (uint64_t)row[i].x | ((uint64_t)(row[i].y & 0x7FFu) << 32);
-            out.kmer[o] = code_to_ascii_pairs(code);
+            out.kmer[o] = ascii[i];
             out.avg_from_end[o] = (uint16_t)(row[i].y >> 11);
             out.function_index[o] = (uint16_t)(row[i].z & 0xFFFFu);
             out.mean[o] = (uint16_t)(row[i].z >> 16);

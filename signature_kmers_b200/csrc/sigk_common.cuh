@@ -136,13 +136,12 @@ SIGK_D uint4 ld_stream_u128(const uint4 *p) {
 #define SIGK_CS_PRE (2ULL << 62)
 #define SIGK_CS_VAL ((1ULL << 62) - 1)
 
-// Called by ONE thread of the tile.  Returns the exclusive prefix of `aggregate`.
-SIGK_D uint64_t chained_scan_exclusive(uint64_t *state, uint32_t tile, uint64_t aggregate) {
-    if (tile == 0) {
-        st_volatile_u64(state, SIGK_CS_PRE | aggregate);
-        return 0;
-    }
-    st_volatile_u64(state + tile, SIGK_CS_AGG | aggregate);
+// Called by ONE thread of the tile.  publish, then (after any independent work) resolve.
+SIGK_D void chained_scan_publish(uint64_t *state, uint32_t tile, uint64_t aggregate) {
+    st_volatile_u64(state + tile, (tile == 0 ? SIGK_CS_PRE : SIGK_CS_AGG) | aggregate);
+}
+SIGK_D uint64_t chained_scan_resolve(uint64_t *state, uint32_t tile, uint64_t aggregate) {
+    if (tile == 0) return 0;
     uint64_t excl = 0;
     int64_t t = (int64_t)tile - 1;
     for (;;) {
@@ -156,16 +155,23 @@ SIGK_D uint64_t chained_scan_exclusive(uint64_t *state, uint32_t tile, uint64_t 
     st_volatile_u64(state + tile, SIGK_CS_PRE | (excl + aggregate));
     return excl;
 }
+// Returns the exclusive prefix of `aggregate`.
+SIGK_D uint64_t chained_scan_exclusive(uint64_t *state, uint32_t tile, uint64_t aggregate) {
+    chained_scan_publish(state, tile, aggregate);
+    return chained_scan_resolve(state, tile, aggregate);
+}
 
 // The same scan, called by a FULL WARP for its own tile: 32 predecessors are
-// inspected per round trip instead of one.  All lanes return the exclusive prefix.
-SIGK_D uint64_t chained_scan_exclusive_warp(uint64_t *state, uint32_t tile, uint64_t aggregate) {
+// inspected per round trip instead of one.  Split in two so that the caller can
+// put independent work between publishing its aggregate and needing the prefix
+// (by then the predecessors have usually published too).
+SIGK_D void chained_scan_publish_warp(uint64_t *state, uint32_t tile, uint64_t aggregate) {
+    if ((threadIdx.x & 31u) == 0) st_volatile_u64(state + tile, (tile == 0 ? SIGK_CS_PRE : SIGK_CS_AGG) | aggregate);
+}
+// All lanes return the exclusive prefix.
+SIGK_D uint64_t chained_scan_resolve_warp(uint64_t *state, uint32_t tile, uint64_t aggregate) {
     const unsigned lane = threadIdx.x & 31u;
-    if (tile == 0) {
-        if (lane == 0) st_volatile_u64(state, SIGK_CS_PRE | aggregate);
-        return 0;
-    }
-    if (lane == 0) st_volatile_u64(state + tile, SIGK_CS_AGG | aggregate);
+    if (tile == 0) return 0;
     uint64_t excl = 0;
     int64_t base = (int64_t)tile - 1;           // lane l looks at tile base - l
     for (;;) {
@@ -176,7 +182,7 @@ SIGK_D uint64_t chained_scan_exclusive_warp(uint64_t *state, uint32_t tile, uint
         unsigned none = __ballot_sync(0xffffffffu, (v >> 62) == 0);
         const unsigned upto = pre ? (pre & (0u - pre)) : 0u;               // lowest lane holding a prefix
         const unsigned needed = upto ? ((upto << 1) - 1u) : 0xffffffffu;    // lanes 0 .. that lane
-        if (none & needed) continue;                                        // somebody nearer is not ready: reread
+        if (none & needed) { __nanosleep(40); continue; }                   // somebody nearer is not ready: reread
         uint64_t c = ((1u << lane) & needed) ? (v & SIGK_CS_VAL) : 0ull;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -186,6 +192,10 @@ SIGK_D uint64_t chained_scan_exclusive_warp(uint64_t *state, uint32_t tile, uint
     }
     if (lane == 0) st_volatile_u64(state + tile, SIGK_CS_PRE | (excl + aggregate));
     return excl;
+}
+SIGK_D uint64_t chained_scan_exclusive_warp(uint64_t *state, uint32_t tile, uint64_t aggregate) {
+    chained_scan_publish_warp(state, tile, aggregate);
+    return chained_scan_resolve_warp(state, tile, aggregate);
 }
 
 // Block-wide exclusive scan of one uint32 per thread; returns the exclusive

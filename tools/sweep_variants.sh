@@ -1,7 +1,7 @@
 #!/bin/bash
 # Run bench.py once per built tuning variant (signature_kmers_b200/libsigk*.so) and print the stage times.
 mkdir -p gpurun_out
-for so in signature_kmers_b200/libsigk*.so; do
+for so in signature_kmers_b200/libsigk.so signature_kmers_b200/libsigk_[a-z].so; do [ -f $so ] || continue
   name=$(basename $so .so)
   SIGK_LIB=$PWD/$so timeout 300 python bench.py --steps 2 --warmup 2 --no-cpu-baseline > gpurun_out/sweep_$name.json 2> gpurun_out/sweep_$name.log || { echo "$name FAILED"; tail -3 gpurun_out/sweep_$name.log; continue; }
   python - "$name" <<'PY'
