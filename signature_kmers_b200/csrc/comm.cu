@@ -315,6 +315,12 @@ int comm_partition_exchange(sigk_handle *h, uint32_t *launches) {
     return SIGK_OK;
 }
 
+int comm_reduce_rejected(sigk_handle *h) {
+    Comm *c = h->comm;
+    NC(h, g_nccl.AllReduce(h->d_prot_rejected.p, h->d_prot_rejected.p, h->n_prot_global, ncclUint32, ncclSum, c->comm, h->stream));
+    return SIGK_OK;
+}
+
 int comm_reduce_stats(sigk_handle *h) {
     Comm *c = h->comm;
     cudaStream_t st = h->stream;

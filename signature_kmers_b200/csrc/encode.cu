@@ -122,6 +122,7 @@ encode_kernel(EncodeArgs a, uint64_t *__restrict__ keys, uint32_t *__restrict__ 
 #pragma unroll
         for (int j = 0; j < 8; ++j) code = code * 40u + (uint64_t)s[j];
         int o = (int)(incl - mine);
+        uint32_t run_i = 0, run_c = 0;              // occurrences of the protein I am inside
 #pragma unroll
         for (int j = 0; j < ENC_PPT; ++j) {
             const uint64_t g = g_first + j;
@@ -131,8 +132,14 @@ encode_kernel(EncodeArgs a, uint64_t *__restrict__ keys, uint32_t *__restrict__ 
                 const int slot = stage_slot(o++);
                 sm.keys[warp][slot] = sigk_pack_key(code, (unsigned)(prot_end - g));
                 sm.vals[warp][slot] = a.ordinal_base + i;
+                if (i != run_i) {
+                    if (run_c && a.prot_windows) atomicAdd(a.prot_windows + run_i, run_c);
+                    run_i = i; run_c = 0;
+                }
+                ++run_c;
             }
         }
+        if (run_c && a.prot_windows) atomicAdd(a.prot_windows + run_i, run_c);
     }
     __syncwarp();
     const uint64_t base = chained_scan_resolve_warp(scan_state, sub, total);

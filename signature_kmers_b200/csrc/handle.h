@@ -19,7 +19,7 @@ struct DeviceScalars {
     uint64_t n_kept;
     uint64_t n_seqs_sig;
     uint32_t ticket[16];
-    uint32_t n_giant, next_giant, n_work, n_work_long, next_work_long, pad[3];
+    uint32_t n_groups, next_group, n_long, next_long, n_work, n_work_long, next_work_long, pad[1];
     uint64_t reduce_in[4];      // multi-GPU: {occurrences, groups, kept, -} of this rank -> summed over ranks
 };
 
@@ -75,16 +75,15 @@ struct sigk_handle {
     sigk::DevBuf<uint64_t> d_starts;
     sigk::DevBuf<uint16_t> d_func;
     sigk::DevBuf<uint32_t> d_seqid, d_slice_prot;
-    sigk::DevBuf<uint4> d_meta, d_giant_side, d_rows;
-    sigk::DevBuf<uint64_t> d_giant_list;
-    sigk::DevBuf<sigk::OrderWork> d_work, d_work_long;
+    sigk::DevBuf<uint4> d_meta, d_rows;
+    sigk::DevBuf<sigk::OrderWork> d_groups, d_long_groups, d_work, d_work_long;
     sigk::DevBuf<uint64_t> d_keys[2];
     sigk::DevBuf<uint32_t> d_vals[2];
     sigk::DevBuf<uint8_t> d_lookback;
     sigk::DevBuf<uint64_t> d_hist, d_binbase, d_scan_state;
     sigk::DevBuf<uint64_t> d_out_kmer;
     sigk::DevBuf<uint16_t> d_out_cols;       // 5 columns of capacity rows
-    sigk::DevBuf<uint32_t> d_bitmap, d_distinct, d_swf;
+    sigk::DevBuf<uint32_t> d_bitmap, d_distinct, d_swf, d_prot_windows, d_prot_rejected;
     sigk::DevBuf<sigk::DeviceScalars> d_scalars;
     uint64_t capacity = 0;             // records the buffers are sized for
     int sorted_in = 0;                 // which ping-pong buffer holds the sorted records
@@ -139,6 +138,8 @@ int comm_exchange_shapes(sigk_handle *h);
 int comm_allgather_meta(sigk_handle *h);
 // encode output in keys[0]/vals[0] -> records of this rank's k-mer range in keys[0]/vals[0], n_records updated
 int comm_partition_exchange(sigk_handle *h, uint32_t *launches);
+// sum over ranks of the per-protein rejected-occurrence counts (before signature_flags)
+int comm_reduce_rejected(sigk_handle *h);
 // sum the per-rank statistics so that every rank's result carries whole-job counters
 int comm_reduce_stats(sigk_handle *h);
 

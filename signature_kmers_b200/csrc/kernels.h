@@ -23,6 +23,7 @@ struct EncodeArgs {
     uint32_t n_prot;
     uint32_t ordinal_base;     // ordinal of local protein 0 in the whole job (multi-GPU)
     const uint32_t *slice_prot; // device, encode_slices()+1: protein holding the first position of each 512-position slice
+    uint32_t *prot_windows;     // device, n_prot, zeroed: valid windows per protein (may be null)
 };
 
 inline uint64_t encode_tiles(uint64_t total_res) { return (total_res + ENC_TILE - 1) / ENC_TILE; }
@@ -86,27 +87,31 @@ constexpr int RED_BATCH = 2048;     // sorted records one warp takes per ticket 
 inline uint64_t reduce_batches(uint64_t capacity) { return (capacity + RED_BATCH - 1) / RED_BATCH; }
 inline uint64_t squeeze_tiles(uint64_t capacity) { return (capacity + 2047) / 2048; }
 inline uint64_t reduce_scan_entries(uint64_t capacity) { return reduce_batches(capacity) + squeeze_tiles(capacity) + 2; }
-size_t reduce_side_entries(uint64_t capacity);                 // uint4 entries of the giant side table
-size_t reduce_giant_entries(uint64_t capacity);                // 8-byte entries of the giant list
-size_t reduce_work_entries(uint64_t capacity, int sm_count);   // OrderWork entries
-size_t reduce_long_work_entries(uint64_t capacity);            // OrderWork entries of groups walked by a whole warp
+size_t reduce_group_entries(uint64_t capacity, int sm_count);  // OrderWork entries: groups of 2..32 records
+size_t reduce_long_group_entries(uint64_t capacity);           // OrderWork entries: groups of more than 32 records
+size_t reduce_work_entries(uint64_t capacity, int sm_count);   // OrderWork entries: groups whose median/var need the ordered walk
+size_t reduce_long_work_entries(uint64_t capacity);            // ... of those, the ones a whole warp walks
 cudaError_t reduce_configure();
 
 // meta[i] = {protein_length, seq_id, function_index, 0}; seqs_with_func[f]++ (src/signature_build.tcc:160)
 cudaError_t launch_protein_meta(const uint64_t *starts, const uint16_t *func, const uint32_t *seq_id, uint32_t n_prot,
                                 uint4 *meta, uint32_t *seqs_with_func, cudaStream_t stream);
-// Pre-pass: groups of >= 513 records (found by sampling) are reduced ahead of the streaming kernel.
-cudaError_t launch_giant_prepass(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
-                                 const uint4 *meta, void *giant_list, uint32_t *n_giant, uint32_t *next_giant,
-                                 uint4 *giant_side, uint32_t *bitmap, int sm_count, cudaStream_t stream);
-// Run-length + per-group reduce + keep/reject in one pass over the sorted records: one packed row per
-// group in k-mer order (rejected groups leave a tombstone), plus the list of groups whose median/var
-// need the ordered walk.  scan_state: reduce_batches()+1 zeroed words.
-cudaError_t launch_stream_reduce(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
-                                 const uint4 *meta, const uint4 *giant_side, uint4 *rows, OrderWork *work, uint32_t *n_work,
-                                 OrderWork *work_long, uint32_t *n_work_long,
-                                 uint32_t *bitmap, uint32_t *distinct_functions, uint64_t *scan_state, uint32_t *ticket,
-                                 uint64_t *n_seg_out, int order_stats, int sm_count, cudaStream_t stream);
+
+// device lists and counters of the segment reduce (counters zeroed before the launch)
+struct ReduceLists {
+    OrderWork *groups;      uint32_t *n_groups, *next_group;
+    OrderWork *long_groups; uint32_t *n_long, *next_long;
+    OrderWork *work;        uint32_t *n_work;
+    OrderWork *work_long;   uint32_t *n_work_long;
+};
+// Run-length + per-group reduce + keep/reject over the sorted records (head_scan_kernel, then
+// group_reduce_kernel): one packed row per group in k-mer order (rejected groups
+// leave a tombstone), plus the lists of groups whose median/var need the ordered walk.
+// scan_state: reduce_batches()+1 zeroed words.
+cudaError_t launch_segment_reduce(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
+                                  const uint4 *meta, uint4 *rows, const ReduceLists &l, uint32_t *prot_rejected,
+                                  uint32_t *distinct_functions, uint64_t *scan_state, uint32_t *ticket, uint64_t *n_seg_out,
+                                  int order_stats, int sm_count, cudaStream_t stream);
 // median / var of the groups listed in `work`, patched into their rows.
 cudaError_t launch_order_stats(const uint32_t *vals, const uint4 *meta, const OrderWork *work, const uint32_t *n_work,
                                const OrderWork *work_long, const uint32_t *n_work_long, uint32_t *next_long,
@@ -114,6 +119,10 @@ cudaError_t launch_order_stats(const uint32_t *vals, const uint4 *meta, const Or
 // Compaction: kept rows -> table columns (tombstones dropped, order kept).  scan_state: squeeze_tiles()+1 zeroed words.
 cudaError_t launch_squeeze_rows(const uint4 *rows, const uint64_t *n_seg_ptr, uint64_t capacity, KeptColumns out,
                                 uint64_t *scan_state, uint32_t *ticket, uint64_t *n_kept_out, cudaStream_t stream);
+// bitmap bit seq_id[i] is set iff protein i has more occurrences (prot_windows, from encode) than occurrences in
+// rejected groups (prot_rejected, from the reduce): kmer_stats_.seqs_with_a_signature, src/signature_build.tcc:274
+cudaError_t launch_signature_flags(const uint32_t *prot_windows, const uint32_t *prot_rejected, const uint32_t *seq_id,
+                                   uint32_t n_prot, uint32_t *bitmap, cudaStream_t stream);
 cudaError_t launch_popcount(const uint32_t *bitmap, uint64_t n_words, uint64_t *out, cudaStream_t stream);
 
 }  // namespace sigk

@@ -12,7 +12,7 @@
 //   mean                  :268-271, :277   -> 16-bit wrapping sum / best_count
 //   median / var          :262-264, :278-279 -> order_stats_kernel (length_acc.cuh)
 //   kept row              :288             -> StoredKmerData columns, k-mer order
-//   statistics            :274, :285-286   -> seq bitmap, per-function counts
+//   statistics            :274, :285-286   -> per-protein kept-occurrence test, per-function counts
 //
 // Majority vote instead of a tally: a group is kept only if best_count >=
 // 0.8*count, so a kept group's best function is a strict majority.  For a strict
@@ -37,6 +37,8 @@
 #include "sigk_common.cuh"
 #include "length_acc.cuh"
 
+#include <algorithm>
+
 namespace sigk {
 
 namespace {
@@ -60,21 +62,23 @@ SIGK_D bool keep_rule(uint32_t best_count, uint32_t count) {
     return !(__int2float_rn((int)best_count) < thresh);
 }
 
-SIGK_D void mark_sequence(uint32_t *bitmap, uint32_t sid) {                // seqs_with_a_signature.insert, tcc:274
-    const uint32_t bit = 1u << (sid & 31u);
-    uint32_t *w = bitmap + (sid >> 5);
-    if (!(__ldcg(w) & bit)) atomicOr(w, bit);
-}
+// seqs_with_a_signature (tcc:274) without touching a bitmap per record: a protein has a signature iff
+// at least one of its occurrences lies in a kept group.  encode counts each protein's occurrences,
+// the reduce kernels count the (rare) occurrences that fall into rejected groups, and
+// signature_flags_kernel compares the two per protein.
+SIGK_D void count_rejected(uint32_t *prot_rejected, uint32_t ordinal) { atomicAdd(prot_rejected + ordinal, 1u); }
 
 struct SegResult {
     bool keep;
     uint32_t func, best_count, avg, mean;
 };
 
-// A group of n > 32 records starting at `start`, reduced by the whole warp in
-// strides of 32 (six walks over the group: vote, count+sum, four select rounds).
+// A group of n > 32 records starting at `start`, reduced by the whole warp in strides of 32:
+// walk 1 votes, walk 2 counts the candidate, sums its lengths and finds the offset bits that vary,
+// then one walk per varying offset bit for the radix select (inside a family the offsets rarely
+// differ in more than a few bits; none when they are all equal).
 SIGK_D SegResult reduce_long_segment(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-                                     const uint4 *__restrict__ meta, uint64_t start, uint32_t n, uint32_t *bitmap) {
+                                     const uint4 *__restrict__ meta, uint64_t start, uint32_t n, uint32_t *prot_rejected) {
     const unsigned lane = threadIdx.x & 31u;
     SegResult r{false, 0, 0, 0, 0};
     // walk 1: bit-sliced majority vote over func_index; lane b owns bit b
@@ -90,154 +94,97 @@ SIGK_D SegResult reduce_long_segment(const uint64_t *__restrict__ keys, const ui
         }
     }
     const uint32_t cand = __ballot_sync(FULL, lane < 16 && 2ull * ones > n) & 0xFFFFu;
-    // walk 2: count the candidate, sum its lengths (mod 65536)
-    uint32_t best = 0, S = 0;
+    // walk 2: count the candidate, sum its lengths (mod 65536), OR of offset differences
+    const uint32_t off0 = sigk_key_offset(keys[start]);
+    uint32_t best = 0, S = 0, vary = 0;
     for (uint32_t base = 0; base < n; base += 32) {
         const uint32_t j = base + lane;
         if (j < n) {
             const uint4 m = __ldg(&meta[vals[start + j]]);
             if (m.z == cand) { ++best; S += m.x; }
+            vary |= sigk_key_offset(keys[start + j]) ^ off0;
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { best += __shfl_xor_sync(FULL, best, o); S += __shfl_xor_sync(FULL, S, o); }
+    vary = __reduce_or_sync(FULL, vary);
     r.func = cand;
     r.best_count = best;
     r.keep = keep_rule(best, n);
-    if (!r.keep) return r;
+    if (!r.keep) {
+        for (uint32_t j = lane; j < n; j += 32) count_rejected(prot_rejected, vals[start + j]);
+        return r;
+    }
     r.mean = (S & 0xFFFFu) / best;
-    // walks 3-6: offset of rank n/2 by radix select, 4 bits per round; lane v owns nibble value v
-    uint32_t rank = n / 2, prefix = 0, pmask = 0;
-#pragma unroll 1
-    for (int shift = 12; shift >= 0; shift -= 4) {
-        uint32_t cnt = 0;
-        for (uint32_t base = 0; base < n; base += 32) {
-            const uint32_t j = base + lane;
-            const bool act = j < n;
-            uint32_t off = 0;
-            if (act) {
-                off = sigk_key_offset(keys[start + j]);
-                if (shift == 12) mark_sequence(bitmap, __ldg(&meta[vals[start + j]]).y);
-            }
-            const bool match = act && ((off & pmask) == prefix);
-            const uint32_t nib = (off >> shift) & 15u;
-#pragma unroll
-            for (int v = 0; v < 16; ++v) {
-                const unsigned bal = __ballot_sync(FULL, match && nib == (uint32_t)v);
-                if ((int)lane == v) cnt += __popc(bal);
-            }
+    // offset of rank n/2 by radix select over the varying bits, most significant first: one walk per bit
+    uint32_t rank = n / 2, prefix = off0 & ~vary, pmask = ~vary & 0xFFFFu;
+    while (vary) {
+        const int b = 31 - __clz(vary);
+        uint32_t zeros = 0;
+        for (uint32_t j = lane; j < n; j += 32) {
+            const uint32_t off = sigk_key_offset(keys[start + j]);
+            zeros += ((off & pmask) == prefix && !((off >> b) & 1u)) ? 1u : 0u;
         }
-        uint32_t incl = lane < 16 ? cnt : 0u;
 #pragma unroll
-        for (int o = 1; o < 16; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(FULL, incl, o);
-            if (lane >= (unsigned)o) incl += y;
-        }
-        const unsigned over = __ballot_sync(FULL, lane < 16 && incl > rank);
-        const int sel = __ffs(over) - 1;
-        const uint32_t below = __shfl_sync(FULL, incl - (lane < 16 ? cnt : 0u), sel);
-        rank -= below;
-        prefix |= (uint32_t)sel << shift;
-        pmask |= 15u << shift;
+        for (int o = 16; o > 0; o >>= 1) zeros += __shfl_xor_sync(FULL, zeros, o);
+        if (rank >= zeros) { rank -= zeros; prefix |= 1u << b; }
+        pmask |= 1u << b;
+        vary &= ~(1u << b);
     }
     r.avg = prefix;
     return r;
 }
 
-// ---- giant groups: found by sampling every GIANT_STRIDE records -------------
-constexpr int GIANT_STRIDE = 512;
-
-struct GiantEntry { uint32_t start, n; };
-
-// giant_side[start >> 5]: x = 1 (valid) | keep << 1 | mean << 16, y = func | avg << 16, z = n, w = best_count
-__global__ void giant_find_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ n_ptr,
-                                  GiantEntry *__restrict__ list, uint32_t *__restrict__ n_list) {
-    const uint64_t n = *n_ptr;
-    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t q = j * GIANT_STRIDE;
-    if (q + GIANT_STRIDE >= n) return;
-    const uint64_t c = sigk_key_code(keys[q]);
-    if (sigk_key_code(keys[q + GIANT_STRIDE]) != c) return;              // does not span two samples
-    if (j > 0 && sigk_key_code(keys[q - GIANT_STRIDE]) == c) return;     // an earlier sample owns it
-    // head: first p in (q - STRIDE, q] with code == c (codes are sorted)
-    uint64_t lo = j > 0 ? q - GIANT_STRIDE + 1 : 0, hi = q;
-    while (lo < hi) {
-        const uint64_t mid = (lo + hi) >> 1;
-        if (sigk_key_code(keys[mid]) >= c) hi = mid; else lo = mid + 1;
-    }
-    const uint64_t start = lo;
-    // end: gallop, then bisect, for the first e with code != c
-    uint64_t step = GIANT_STRIDE, a = q + GIANT_STRIDE, b;
-    for (;;) {
-        b = a + step;
-        if (b >= n) { b = n; break; }
-        if (sigk_key_code(keys[b]) != c) break;
-        a = b;
-        step <<= 1;
-    }
-    // invariant: code[a] == c, (b == n or code[b] != c)
-    while (a + 1 < b) {
-        const uint64_t mid = (a + b) >> 1;
-        if (sigk_key_code(keys[mid]) == c) a = mid; else b = mid;
-    }
-    const uint32_t slot = atomicAdd(n_list, 1u);
-    list[slot] = GiantEntry{(uint32_t)start, (uint32_t)(b - start)};
-}
-
-__global__ void __launch_bounds__(256)
-giant_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, const uint4 *__restrict__ meta,
-                    const GiantEntry *__restrict__ list, const uint32_t *__restrict__ n_list, uint32_t *__restrict__ next,
-                    uint4 *__restrict__ giant_side, uint32_t *__restrict__ bitmap) {
-    const unsigned lane = threadIdx.x & 31u;
-    const uint32_t total = *n_list;
-    for (;;) {
-        uint32_t i = 0;
-        if (lane == 0) i = atomicAdd(next, 1u);
-        i = __shfl_sync(FULL, i, 0);
-        if (i >= total) return;
-        const GiantEntry g = list[i];
-        const SegResult r = reduce_long_segment(keys, vals, meta, g.start, g.n, bitmap);
-        if (lane == 0)
-            giant_side[g.start >> 5] = make_uint4(1u | (r.keep ? 2u : 0u) | (r.mean << 16), r.func | (r.avg << 16), g.n, r.best_count);
-    }
-}
-
-// ---- the streaming reduce ----------------------------------------------------
-// Persistent warps.  A warp takes a batch of RED_BATCH sorted records by ticket,
-// counts the group heads in it and publishes that count at once (chained scan
-// over batches), so later batches never wait for this one's work: every group,
-// kept or not, owns the row slot of its index, and rejected groups leave a
-// tombstone (function_index 0xFFFF) that squeeze_rows_kernel removes.
+// ---- stage 3a: run-length ---------------------------------------------------------------------
+// Persistent warps.  A warp takes a batch of RED_BATCH sorted records by ticket, counts the group
+// heads in it and publishes that count at once (chained scan over batches): every group, kept or
+// not, owns the row slot of its index, so nothing downstream waits for a keep decision; rejected
+// groups leave a tombstone (function_index 0xFFFF) that squeeze_rows_kernel removes.
+// Single-record groups (92 % of the groups of the 2 M-protein set, always kept: 1 >= 0.8) are
+// finished here; groups of 2..32 records go to `groups`, longer ones to `long_groups`.
 //
 // rows[g] (uint4): x = code[31:0]; y = code[42:32] | avg_from_end << 11;
 //                  z = function_index | mean << 16; w = median | var << 16
 constexpr int RED_THREADS = 128;
-constexpr int WORK_BLOCK = 64;          // order-statistics work slots a warp reserves at a time
+constexpr int HS_AHEAD = 4;             // rows of keys/values the run-length pass keeps in flight
+constexpr int WORK_BLOCK = 64;          // list slots a warp reserves at a time (groups / order-statistics work)
+constexpr int GR_CHUNK = 256;           // group descriptors a warp takes per fetch
 constexpr uint32_t ORD_LONG = 4096;     // groups above this are walked by a whole warp (the tail); below, a lane each
 
 struct WorkCursor { uint32_t base, free; };
 
+// Slots are reserved in blocks so that the shared counter sees one atomic per 64 entries; the unused
+// tail of a block is filled with count-0 entries (consumers skip them).  Inside a block the used
+// entries are a prefix.
 SIGK_D void work_reserve(WorkCursor &wc, uint32_t need, OrderWork *__restrict__ work, uint32_t *__restrict__ n_work) {
     const unsigned lane = threadIdx.x & 31u;
     if (wc.free >= need) return;
-    for (uint32_t i = lane; i < wc.free; i += 32) work[wc.base + i] = OrderWork{0u, 0u, 0u};   // unused tail: count 0 = skip
+    for (uint32_t i = lane; i < wc.free; i += 32) work[wc.base + i] = OrderWork{0u, 0u, 0u};
     uint32_t b = 0;
     if (lane == 0) b = atomicAdd(n_work, (uint32_t)WORK_BLOCK);
     wc.base = __shfl_sync(FULL, b, 0);
     wc.free = WORK_BLOCK;
 }
+SIGK_D void work_flush(WorkCursor &wc, OrderWork *__restrict__ work) {
+    for (uint32_t i = threadIdx.x & 31u; i < wc.free; i += 32) work[wc.base + i] = OrderWork{0u, 0u, 0u};
+}
+
+SIGK_D uint4 singleton_row(uint64_t key, const uint4 m) {
+    const uint64_t code = sigk_key_code(key);
+    // one item: avg_from_end = its offset, best = its function, sum = its length mod 65536, median = var = 0
+    return make_uint4((uint32_t)code, (uint32_t)(code >> 32) | (sigk_key_offset(key) << 11), m.z | ((m.x & 0xFFFFu) << 16), 0u);
+}
 
 __global__ void __launch_bounds__(RED_THREADS)
-stream_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-                     const uint64_t *__restrict__ n_ptr, const uint4 *__restrict__ meta,
-                     const uint4 *__restrict__ giant_side, uint4 *__restrict__ rows, OrderWork *__restrict__ work,
-                     uint32_t *__restrict__ n_work, OrderWork *__restrict__ work_long, uint32_t *__restrict__ n_work_long,
-                     uint32_t *__restrict__ bitmap, uint32_t *__restrict__ distinct_functions,
-                     uint64_t *__restrict__ scan_state, uint32_t *__restrict__ ticket, uint64_t *__restrict__ n_seg_out,
-                     int order_stats) {
+head_scan_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, const uint64_t *__restrict__ n_ptr,
+                 const uint4 *__restrict__ meta, uint4 *__restrict__ rows, OrderWork *__restrict__ groups,
+                 uint32_t *__restrict__ n_groups, OrderWork *__restrict__ long_groups, uint32_t *__restrict__ n_long,
+                 uint32_t *__restrict__ distinct_functions, uint64_t *__restrict__ scan_state,
+                 uint32_t *__restrict__ ticket, uint64_t *__restrict__ n_seg_out) {
     const unsigned lane = threadIdx.x & 31u;
     const uint64_t n = *n_ptr;
-    WorkCursor wc{0u, 0u};
+    constexpr uint64_t NO_CODE = ~0ull;                  // codes are < 2^43
+    WorkCursor gc{0u, 0u};
 
     for (;;) {
         uint32_t t = 0;
@@ -247,95 +194,223 @@ stream_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restri
         if (b0 >= n) break;
         const uint64_t b1 = (b0 + RED_BATCH < n) ? b0 + RED_BATCH : n;
 
-        // ---- group heads of the batch: count, first head; publish the count
+        // ---- pass 1: heads of the batch -> publish (four rows of keys in flight)
         uint32_t hc = 0;
-        uint64_t cur = b1;
-        for (uint64_t p0 = b0; p0 < b1; p0 += 32) {
-            const uint64_t p = p0 + lane;
-            bool head = false;
-            if (p < b1) head = (p == 0) || (sigk_key_code(__ldg(keys + p)) != sigk_key_code(__ldg(keys + p - 1)));   // kmer != cur, tcc:194
-            const unsigned hb = __ballot_sync(FULL, head);
-            if (hb && cur == b1) cur = p0 + __ffs(hb) - 1;
-            hc += __popc(hb);
+        const uint64_t before = b0 ? sigk_key_code(__ldg(keys + b0 - 1)) : NO_CODE;
+        {
+            uint64_t carry = before;
+            for (uint64_t q0 = b0; q0 < b1; q0 += 128) {
+                uint64_t c[4];
+#pragma unroll
+                for (int s4 = 0; s4 < 4; ++s4) {
+                    const uint64_t p = q0 + (uint64_t)s4 * 32 + lane;
+                    c[s4] = p < b1 ? sigk_key_code(__ldg(keys + p)) : NO_CODE;
+                }
+#pragma unroll
+                for (int s4 = 0; s4 < 4; ++s4) {
+                    const uint64_t p = q0 + (uint64_t)s4 * 32 + lane;
+                    uint64_t prev = __shfl_up_sync(FULL, c[s4], 1);
+                    if (lane == 0) prev = carry;
+                    hc += __popc(__ballot_sync(FULL, p < b1 && c[s4] != prev));            // kmer != cur, tcc:194
+                    carry = __shfl_sync(FULL, c[s4], 31);
+                }
+            }
         }
         uint64_t g = chained_scan_exclusive_warp(scan_state, t, hc);        // index of the batch's first group
         if (b1 == n && lane == 0) *n_seg_out = g + hc;
 
-        while (cur < b1) {
-            // ---- one window: records cur .. cur+31, cur is a group head
-            const uint64_t p = cur + lane;
-            const bool valid = p < n;
-            const uint64_t key = valid ? __ldg(keys + p) : 0ull;
-            const uint64_t code = sigk_key_code(key);
-            const uint64_t prev = __shfl_up_sync(FULL, code, 1);
-            const bool head = valid && (lane == 0 || code != prev);
-            unsigned H = __ballot_sync(FULL, head);
-            const unsigned V = __ballot_sync(FULL, valid);
-            // is the record after the window a head (or the end)?
-            uint64_t nxt = 0;
-            if (lane == 31) nxt = (cur + 32 < n) ? sigk_key_code(__ldg(keys + cur + 32)) : ~0ull;
-            const bool closed = __shfl_sync(FULL, (lane == 31) && (!valid || nxt != code), 31);
-            uint32_t wlen = __popc(V);
-            if (!closed) {
-                const int last = 31 - __clz(H);         // head of the group that runs past the window
-                if (last == 0) {
-                    // ---- a group longer than 32 records: pre-reduced (giant) or walked now.
-                    // At most one long group can have its head in a 32-record block, so a
-                    // valid side entry under cur >> 5 is this group's.
-                    SegResult r;
-                    uint32_t glen;
-                    const uint4 gs = __ldg(giant_side + (cur >> 5));
-                    if (gs.x & 1u) {
-                        glen = gs.z;
-                        r.keep = (gs.x & 2u) != 0; r.func = gs.y & 0xFFFFu; r.avg = gs.y >> 16; r.mean = gs.x >> 16; r.best_count = gs.w;
-                    } else {
-                        uint64_t e = cur + 32;          // the first 33 records are known to match
-                        for (;;) {
-                            const uint64_t q = e + lane;
-                            const bool same = q < n && sigk_key_code(__ldg(keys + q)) == code;
-                            const unsigned sb = __ballot_sync(FULL, same);
-                            if (sb != FULL) { e += (uint64_t)(__ffs(~sb) - 1); break; }
-                            e += 32;
-                        }
-                        glen = (uint32_t)(e - cur);
-                        r = reduce_long_segment(keys, vals, meta, cur, glen, bitmap);
-                    }
-                    const bool walk = r.keep && order_stats;          // best_count >= 27 here
-                    const bool walk_long = walk && glen > ORD_LONG;   // whole-warp walk (order_stats_long_kernel)
-                    if (walk && !walk_long) work_reserve(wc, 1u, work, n_work);
-                    if (lane == 0) {
-                        if (r.keep) {
-                            rows[g] = make_uint4((uint32_t)code, (uint32_t)(code >> 32) | (r.avg << 11), r.func | (r.mean << 16), 0u);
-                            atomicAdd(distinct_functions + r.func, 1u);                 // tcc:286
-                            if (walk_long) work_long[atomicAdd(n_work_long, 1u)] = OrderWork{(uint32_t)g, (uint32_t)cur, glen};
-                            else if (walk) work[wc.base] = OrderWork{(uint32_t)g, (uint32_t)cur, glen};
-                        } else rows[g] = make_uint4(0u, 0u, 0xFFFFu, 0u);
-                    }
-                    if (walk && !walk_long) { wc.base += 1; wc.free -= 1; }
-                    g += 1;
-                    cur += glen;
-                    continue;
+        // ---- pass 2: close groups row by row
+        bool open = false;                  // a group whose end has not been seen yet
+        uint64_t open_start = 0, open_g = 0, open_code = 0, open_key = 0;
+        unsigned open_lane = 0;
+        uint4 open_m = make_uint4(0, 0, 0, 0);
+        uint64_t prev_last = before;
+
+        // the open group ends at `end`: one record -> finished here; 2..32 -> groups; more -> long_groups
+        auto close_open = [&](uint64_t end) {
+            const uint64_t cnt = end - open_start;
+            if (cnt == 1) {
+                if (lane == open_lane) {            // its meta was requested when the group was opened
+                    rows[open_g] = singleton_row(open_key, open_m);
+                    atomicAdd(distinct_functions + open_m.z, 1u);           // tcc:286
                 }
-                wlen = (uint32_t)last;                  // drop the unfinished group from this window
-                H &= mask_lt((unsigned)last);
+            } else if (cnt <= 32) {
+                work_reserve(gc, 1u, groups, n_groups);
+                if (lane == 0) groups[gc.base] = OrderWork{(uint32_t)open_g, (uint32_t)open_start, (uint32_t)cnt};
+                gc.base += 1; gc.free -= 1;
+            } else if (lane == 0) {
+                long_groups[atomicAdd(n_long, 1u)] = OrderWork{(uint32_t)open_g, (uint32_t)open_start, (uint32_t)cnt};
             }
-            // groups headed at or beyond b1 belong to the next batch
-            if (cur + wlen > b1) {
-                const unsigned beyond = H & ~mask_lt((unsigned)(b1 - cur));
-                if (beyond) { wlen = (uint32_t)(__ffs(beyond) - 1); H &= mask_lt(wlen); }
+            open = false;
+        };
+
+        // Rows are software-pipelined: the keys and values of the next HS_AHEAD rows are already in
+        // flight, and a row's single-record groups are finished one row later, when their meta gather
+        // has landed — one warp no longer pays three dependent memory latencies per 32 records.
+        uint64_t kq[HS_AHEAD];
+        uint32_t vq[HS_AHEAD];
+#pragma unroll
+        for (int s = 0; s < HS_AHEAD; ++s) {
+            const uint64_t q = b0 + (uint64_t)s * 32 + lane;
+            kq[s] = q < b1 ? __ldg(keys + q) : 0ull;
+            vq[s] = q < b1 ? __ldg(vals + q) : 0u;
+        }
+        bool pend = false;                  // this lane has a single-record group waiting for its meta
+        uint4 pend_m = make_uint4(0, 0, 0, 0);
+        uint64_t pend_key = 0, pend_g = 0;
+        auto finish_pending = [&]() {
+            if (pend) {
+                rows[pend_g] = singleton_row(pend_key, pend_m);
+                atomicAdd(distinct_functions + pend_m.z, 1u);               // tcc:286
+                pend = false;
             }
+        };
+        for (uint64_t q0 = b0; q0 < b1; q0 += 32 * HS_AHEAD) {
+#pragma unroll
+            for (int s = 0; s < HS_AHEAD; ++s) {
+                const uint64_t p0 = q0 + (uint64_t)s * 32;
+                if (p0 >= b1) break;
+                const uint64_t p = p0 + lane;
+                const bool valid = p < b1;
+                const uint64_t key = kq[s];
+                const uint32_t val = vq[s];
+                {   // refill this slot with the row HS_AHEAD further on
+                    const uint64_t q = p + 32ull * HS_AHEAD;
+                    kq[s] = q < b1 ? __ldg(keys + q) : 0ull;
+                    vq[s] = q < b1 ? __ldg(vals + q) : 0u;
+                }
+                const uint64_t code = sigk_key_code(key);
+                uint64_t prev = __shfl_up_sync(FULL, code, 1);
+                if (lane == 0) prev = prev_last;
+                const bool head = valid && code != prev;
+                const unsigned H = __ballot_sync(FULL, head);
+                prev_last = __shfl_sync(FULL, code, 31);
+                if (!H) { finish_pending(); continue; }
+                const unsigned first = (unsigned)__ffs(H) - 1u, last = 31u - (unsigned)__clz(H);
+                if (open) close_open(p0 + first);
+
+                const unsigned above = H & ~mask_le(lane);
+                const bool known = head && lane != last;                 // the next head is in this row
+                const uint32_t cnt = known ? (uint32_t)(__ffs(above) - 1) - lane : 0u;
+                const uint64_t gi = g + __popc(H & mask_lt(lane));
+                finish_pending();                                   // the previous row's single-record groups
+                if (known && cnt == 1) {
+                    pend = true; pend_m = __ldg(meta + val); pend_key = key; pend_g = gi;
+                }
+                const unsigned M = __ballot_sync(FULL, known && cnt >= 2);
+                if (M) {
+                    const uint32_t k = __popc(M);
+                    work_reserve(gc, k, groups, n_groups);
+                    if (known && cnt >= 2) groups[gc.base + __popc(M & mask_lt(lane))] = OrderWork{(uint32_t)gi, (uint32_t)p, cnt};
+                    gc.base += k; gc.free -= k;
+                }
+                open = true;
+                open_start = p0 + last;
+                open_g = g + __popc(H) - 1;
+                open_code = __shfl_sync(FULL, code, last);
+                open_lane = last;
+                if (lane == last) { open_m = __ldg(meta + val); open_key = key; }   // in case it closes as a single record
+                g += __popc(H);
+            }
+        }
+        finish_pending();
+        if (open) {
+            // the last group of the batch may run into the following batches
+            uint64_t e = b1;
+            for (;;) {
+                const uint64_t q = e + lane;
+                const bool same = q < n && sigk_key_code(__ldg(keys + q)) == open_code;
+                const unsigned sb = __ballot_sync(FULL, same);
+                if (sb != FULL) { e += (uint64_t)(__ffs(~sb) - 1); break; }
+                e += 32;
+            }
+            close_open(e);
+        }
+    }
+    work_flush(gc, groups);
+}
+
+// ---- stage 3b: groups of 2..32 records, packed 32 records to a warp ---------------------------
+// A warp takes 32 descriptors, lays their records side by side (lane = record, whole groups only)
+// and reduces all groups of the window at once with ballots and segmented shuffles.
+__global__ void __launch_bounds__(RED_THREADS)
+group_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, const uint4 *__restrict__ meta,
+                    const OrderWork *__restrict__ groups, const uint32_t *__restrict__ n_groups, uint32_t *__restrict__ next_group,
+                    const OrderWork *__restrict__ long_groups, const uint32_t *__restrict__ n_long, uint32_t *__restrict__ next_long,
+                    uint4 *__restrict__ rows, OrderWork *__restrict__ work, uint32_t *__restrict__ n_work,
+                    OrderWork *__restrict__ work_long, uint32_t *__restrict__ n_work_long, uint32_t *__restrict__ prot_rejected,
+                    uint32_t *__restrict__ distinct_functions, int order_stats) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t total = *n_groups;
+    WorkCursor wc{0u, 0u};
+
+    // ---- groups of more than 32 records first (they are the tail), one warp each
+    {
+        const uint32_t total_long = *n_long;
+        for (;;) {
+            uint32_t i = 0;
+            if (lane == 0) i = atomicAdd(next_long, 1u);
+            i = __shfl_sync(FULL, i, 0);
+            if (i >= total_long) break;
+            const OrderWork d = long_groups[i];
+            const SegResult r = reduce_long_segment(keys, vals, meta, d.start, d.count, prot_rejected);
+            const bool walk = r.keep && order_stats;            // best_count >= 27 here
+            const bool walk_long = walk && d.count > ORD_LONG;  // whole-warp walk (order_stats_long_kernel)
+            if (walk && !walk_long) work_reserve(wc, 1u, work, n_work);
+            if (lane == 0) {
+                if (r.keep) {
+                    const uint64_t code = sigk_key_code(keys[d.start]);
+                    rows[d.row] = make_uint4((uint32_t)code, (uint32_t)(code >> 32) | (r.avg << 11), r.func | (r.mean << 16), 0u);
+                    atomicAdd(distinct_functions + r.func, 1u);                 // tcc:286
+                    if (walk_long) work_long[atomicAdd(n_work_long, 1u)] = d;
+                    else if (walk) work[wc.base] = d;
+                } else rows[d.row] = make_uint4(0u, 0u, 0xFFFFu, 0u);
+            }
+            if (walk && !walk_long) { wc.base += 1; wc.free -= 1; }
+        }
+    }
+
+    // ---- then the packed groups, GR_CHUNK descriptors per fetch
+    for (;;) {
+      uint32_t c0 = 0;
+      if (lane == 0) c0 = atomicAdd(next_group, (uint32_t)GR_CHUNK);
+      c0 = __shfl_sync(FULL, c0, 0);
+      if (c0 >= total) break;
+      for (uint64_t d0 = c0; d0 < (uint64_t)c0 + GR_CHUNK && d0 < total; d0 += 32) {
+        const uint64_t di = d0 + lane;
+        OrderWork d = di < total ? groups[di] : OrderWork{0u, 0u, 0u};
+        // used descriptors are a prefix of the 32 (work_reserve pads block tails)
+        uint32_t incl = d.count;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL, incl, o);
+            if (lane >= (unsigned)o) incl += y;
+        }
+        const uint32_t excl = incl - d.count;
+        const uint32_t tot = __shfl_sync(FULL, incl, 31);
+        uint32_t base = 0, j0 = 0;
+        while (base < tot) {
+            // ---- one window: descriptors j0.. whose records fit into 32 lanes
+            const bool fits = lane >= j0 && d.count && incl - base <= 32u;
+            const unsigned F = __ballot_sync(FULL, fits);
+            const uint32_t nd = __popc(F);
+            const uint32_t wlen = __shfl_sync(FULL, incl, j0 + nd - 1) - base;
+            const unsigned H = __reduce_or_sync(FULL, fits ? (1u << (excl - base)) : 0u);
             const bool act = lane < wlen;
+            const unsigned s_lane = 31u - (unsigned)__clz(H & mask_le(lane));
+            const uint32_t dj = j0 + __popc(H & mask_le(lane)) - 1u;        // my group's descriptor lane
+            const uint32_t cnt = __shfl_sync(FULL, d.count, dj);
+            const uint32_t gstart = __shfl_sync(FULL, d.start, dj);
+            const uint32_t grow = __shfl_sync(FULL, d.row, dj);
+            const unsigned e_lane = s_lane + cnt;
+            const unsigned segmask = mask_range(s_lane, e_lane);
+            const bool head = act && lane == s_lane;
+            const uint64_t p = (uint64_t)gstart + (lane - s_lane);
+            const uint64_t key = act ? __ldg(keys + p) : 0ull;
             const uint32_t ord = act ? __ldg(vals + p) : 0u;
             const uint4 m = act ? __ldg(meta + ord) : make_uint4(0, 0, 0, 0);      // len, seq_id, func
             const uint32_t f = m.z;
             const uint32_t off = sigk_key_offset(key);
-
-            // my group's lanes
-            const unsigned s_lane = 31u - (unsigned)__clz(H & mask_le(lane));
-            const unsigned above = H & ~mask_le(lane);
-            const unsigned e_lane = above ? (unsigned)(__ffs(above) - 1) : wlen;
-            const uint32_t cnt = e_lane - s_lane;
-            const unsigned segmask = mask_range(s_lane, e_lane);
 
             // function vote (func_count + arg-max, tcc:203, :228-248).  A group with two
             // different functions and fewer than 5 records cannot reach 80 % (1/2, 2/3, 3/4),
@@ -392,30 +467,30 @@ stream_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restri
                 const double tmp = __dsub_rn((double)x2, __dmul_rn((double)S, 0.5));
                 var2 = best_count == 2 ? u16_from_double(__dmul_rn(tmp, tmp)) : 0u;
             }
-            if (keep) mark_sequence(bitmap, m.y);
+            if (act && !keep) count_rejected(prot_rejected, ord);
 
             const bool walk = keep && head && order_stats && best_count >= 3;
             const unsigned wb = __ballot_sync(FULL, walk);
             if (wb) work_reserve(wc, (uint32_t)__popc(wb), work, n_work);
-            if (head && act) {
-                const uint64_t gi = g + __popc(H & mask_lt(lane));
+            if (head) {
                 if (keep) {
+                    const uint64_t code = sigk_key_code(key);
                     // u16((double)S / n) = floor(S / best_count), S < 65536, best_count <= 32: float quotient, fixed up
                     uint32_t mean = (uint32_t)__float2uint_rz(__fmul_rn((float)S, __frcp_rn((float)best_count)));
                     if (mean * best_count > S) --mean;
                     else if ((mean + 1u) * best_count <= S) ++mean;
-                    rows[gi] = make_uint4((uint32_t)code, (uint32_t)(code >> 32) | (sel << 11), cand | (mean << 16), var2 << 16);
+                    rows[grow] = make_uint4((uint32_t)code, (uint32_t)(code >> 32) | (sel << 11), cand | (mean << 16), var2 << 16);
                     atomicAdd(distinct_functions + cand, 1u);                                   // tcc:286
-                    if (walk) work[wc.base + __popc(wb & mask_lt(lane))] = OrderWork{(uint32_t)gi, (uint32_t)p, cnt};
-                } else rows[gi] = make_uint4(0u, 0u, 0xFFFFu, 0u);
+                    if (walk) work[wc.base + __popc(wb & mask_lt(lane))] = OrderWork{grow, (uint32_t)p, cnt};
+                } else rows[grow] = make_uint4(0u, 0u, 0xFFFFu, 0u);
             }
             if (wb) { const uint32_t k = __popc(wb); wc.base += k; wc.free -= k; }
-            g += __popc(H);
-            cur += wlen;
+            base += wlen;
+            j0 += nd;
         }
+      }
     }
-    // the reserved slots this warp never used
-    for (uint32_t i = lane; i < wc.free; i += 32) work[wc.base + i] = OrderWork{0u, 0u, 0u};
+    work_flush(wc, work);
 }
 
 // ---- squeeze: drop the tombstones, keep k-mer order, expand rows into the table columns
@@ -582,6 +657,17 @@ order_stats_long_kernel(const uint32_t *__restrict__ vals, const uint4 *__restri
     }
 }
 
+// seq_bitmap bit seq_id[i] = protein i has an occurrence in a kept group
+__global__ void signature_flags_kernel(const uint32_t *__restrict__ prot_windows, const uint32_t *__restrict__ prot_rejected,
+                                       const uint32_t *__restrict__ seq_id, uint32_t n_prot, uint32_t *__restrict__ bitmap) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_prot) return;
+    if (prot_windows[i] > prot_rejected[i]) {
+        const uint32_t sid = seq_id[i];
+        atomicOr(bitmap + (sid >> 5), 1u << (sid & 31u));
+    }
+}
+
 __global__ void popcount_kernel(const uint32_t *__restrict__ bitmap, uint64_t n_words, uint64_t *__restrict__ out) {
     uint64_t c = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (uint64_t)gridDim.x * blockDim.x)
@@ -603,14 +689,17 @@ __global__ void protein_meta_kernel(const uint64_t *__restrict__ starts, const u
 
 }  // namespace
 
-size_t reduce_side_entries(uint64_t capacity) { return (size_t)(capacity / 32 + 2); }
-size_t reduce_giant_entries(uint64_t capacity) { return (size_t)(capacity / GIANT_STRIDE + 2); }
-size_t reduce_long_work_entries(uint64_t capacity) { return (size_t)(capacity / ORD_LONG + 2); }
 static int reduce_grid(int sm_count) { return sm_count * 12; }
-size_t reduce_work_entries(uint64_t capacity, int sm_count) {
-    // a walked group has >= 3 records; every warp of the persistent grid can strand one reserved block
-    return (size_t)(capacity / 3 + 2) + (size_t)reduce_grid(sm_count) * (RED_THREADS / 32) * WORK_BLOCK;
+size_t reduce_group_entries(uint64_t capacity, int sm_count) {
+    // a listed group has >= 2 records; every warp of a persistent grid can strand one reserved block
+    return (size_t)(capacity / 2 + 2) + (size_t)reduce_grid(sm_count) * (RED_THREADS / 32) * WORK_BLOCK;
 }
+size_t reduce_long_group_entries(uint64_t capacity) { return (size_t)(capacity / 33 + 2); }
+size_t reduce_work_entries(uint64_t capacity, int sm_count) {
+    // a walked group has >= 3 records; two kernels push into the list
+    return (size_t)(capacity / 3 + 2) + 2 * (size_t)reduce_grid(sm_count) * (RED_THREADS / 32) * WORK_BLOCK;
+}
+size_t reduce_long_work_entries(uint64_t capacity) { return (size_t)(capacity / ORD_LONG + 2); }
 
 cudaError_t reduce_configure() {
     init_pair_ascii_kernel<<<(1600 + 255) / 256, 256>>>();
@@ -624,31 +713,21 @@ cudaError_t launch_protein_meta(const uint64_t *starts, const uint16_t *func, co
     return cudaGetLastError();
 }
 
-cudaError_t launch_giant_prepass(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
-                                 const uint4 *meta, void *giant_list, uint32_t *n_giant, uint32_t *next_giant,
-                                 uint4 *giant_side, uint32_t *bitmap, int sm_count, cudaStream_t stream) {
-    if (capacity <= GIANT_STRIDE) return cudaSuccess;
-    const uint64_t samples = capacity / GIANT_STRIDE + 1;
-    giant_find_kernel<<<(unsigned)((samples + 255) / 256), 256, 0, stream>>>(keys, n_ptr, (GiantEntry *)giant_list, n_giant);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    giant_reduce_kernel<<<sm_count * 2, 256, 0, stream>>>(keys, vals, meta, (const GiantEntry *)giant_list, n_giant, next_giant,
-                                                          giant_side, bitmap);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_stream_reduce(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
-                                 const uint4 *meta, const uint4 *giant_side, uint4 *rows, OrderWork *work, uint32_t *n_work,
-                                 OrderWork *work_long, uint32_t *n_work_long,
-                                 uint32_t *bitmap, uint32_t *distinct_functions, uint64_t *scan_state, uint32_t *ticket,
-                                 uint64_t *n_seg_out, int order_stats, int sm_count, cudaStream_t stream) {
+cudaError_t launch_segment_reduce(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
+                                  const uint4 *meta, uint4 *rows, const ReduceLists &l, uint32_t *prot_rejected,
+                                  uint32_t *distinct_functions, uint64_t *scan_state, uint32_t *ticket, uint64_t *n_seg_out,
+                                  int order_stats, int sm_count, cudaStream_t stream) {
     if (capacity == 0) return cudaSuccess;
     uint64_t grid = reduce_grid(sm_count);
     const uint64_t want = (reduce_batches(capacity) + RED_THREADS / 32 - 1) / (RED_THREADS / 32);
-    if (grid > want) grid = want;
-    stream_reduce_kernel<<<(unsigned)grid, RED_THREADS, 0, stream>>>(keys, vals, n_ptr, meta, giant_side, rows, work, n_work,
-                                                                     work_long, n_work_long, bitmap, distinct_functions, scan_state, ticket, n_seg_out,
-                                                                     order_stats);
+    head_scan_kernel<<<(unsigned)std::min(grid, want), RED_THREADS, 0, stream>>>(
+        keys, vals, n_ptr, meta, rows, l.groups, l.n_groups, l.long_groups, l.n_long, distinct_functions, scan_state,
+        ticket, n_seg_out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    group_reduce_kernel<<<(unsigned)grid, RED_THREADS, 0, stream>>>(keys, vals, meta, l.groups, l.n_groups, l.next_group, l.long_groups,
+                                                                    l.n_long, l.next_long, rows, l.work, l.n_work, l.work_long,
+                                                                    l.n_work_long, prot_rejected, distinct_functions, order_stats);
     return cudaGetLastError();
 }
 
@@ -668,6 +747,13 @@ cudaError_t launch_squeeze_rows(const uint4 *rows, const uint64_t *n_seg_ptr, ui
                                 uint64_t *scan_state, uint32_t *ticket, uint64_t *n_kept_out, cudaStream_t stream) {
     if (capacity == 0) return cudaSuccess;
     squeeze_rows_kernel<<<(unsigned)squeeze_tiles(capacity), SQ_THREADS, 0, stream>>>(rows, n_seg_ptr, out, scan_state, ticket, n_kept_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_signature_flags(const uint32_t *prot_windows, const uint32_t *prot_rejected, const uint32_t *seq_id,
+                                   uint32_t n_prot, uint32_t *bitmap, cudaStream_t stream) {
+    if (n_prot == 0) return cudaSuccess;
+    signature_flags_kernel<<<(n_prot + 255) / 256, 256, 0, stream>>>(prot_windows, prot_rejected, seq_id, n_prot, bitmap);
     return cudaGetLastError();
 }
 

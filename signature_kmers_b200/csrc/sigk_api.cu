@@ -42,8 +42,8 @@ int ensure_capacity(sigk_handle *h, uint64_t cap, bool keep_pingpong1) {
         CU(h, h->d_keys[i].reserve(cap)); CU(h, h->d_vals[i].reserve(cap));
     }
     CU(h, h->d_lookback.reserve(onesweep_lookback_bytes(cap_lb) * SORT_MAX_PASSES));
-    CU(h, h->d_giant_side.reserve(reduce_side_entries(cap)));
-    CU(h, h->d_giant_list.reserve(reduce_giant_entries(cap)));
+    CU(h, h->d_groups.reserve(reduce_group_entries(cap, h->sm_count)));
+    CU(h, h->d_long_groups.reserve(reduce_long_group_entries(cap)));
     CU(h, h->d_work.reserve(reduce_work_entries(cap, h->sm_count)));
     CU(h, h->d_work_long.reserve(reduce_long_work_entries(cap)));
     CU(h, h->d_rows.reserve(cap));
@@ -103,6 +103,8 @@ int do_upload(sigk_handle *h) {
     if (h->comm) { if (int rc = comm_exchange_shapes(h)) return rc; }
     CU(h, h->d_meta.reserve(h->n_prot_global));
     CU(h, h->d_bitmap.reserve(((uint64_t)h->max_seq_id >> 5) + 1));
+    CU(h, h->d_prot_windows.reserve(np));
+    CU(h, h->d_prot_rejected.reserve(h->n_prot_global));
     h->uploaded = true;
     h->built = h->downloaded = false;
     return SIGK_OK;
@@ -121,13 +123,15 @@ int do_build_device(sigk_handle *h) {
     CU(h, cudaMemsetAsync(h->d_swf.p, 0, SIGK_N_FUNCTION_SLOTS * sizeof(uint32_t), st));
     CU(h, cudaMemsetAsync(h->d_distinct.p, 0, SIGK_N_FUNCTION_SLOTS * sizeof(uint32_t), st));
     CU(h, cudaMemsetAsync(h->d_bitmap.p, 0, (((uint64_t)h->max_seq_id >> 5) + 1) * sizeof(uint32_t), st));
+    CU(h, cudaMemsetAsync(h->d_prot_windows.p, 0, std::max<uint64_t>(np, 1) * sizeof(uint32_t), st));
+    CU(h, cudaMemsetAsync(h->d_prot_rejected.p, 0, std::max<uint64_t>(h->n_prot_global, 1) * sizeof(uint32_t), st));
     CU(h, cudaMemsetAsync(h->d_hist.p, 0, SORT_MAX_PASSES * SIGK_RADIX * sizeof(uint64_t), st));
 
     // ---- stage 1: encode
     CU(h, launch_protein_meta(h->d_starts.p, h->d_func.p, h->d_seqid.p, (uint32_t)np, h->d_meta.p + h->ordinal_base, h->d_swf.p, st)); ++launches;
     if (h->comm) { if (int rc = comm_allgather_meta(h)) return rc; }
     CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, encode_scan_entries(h->total_res) * sizeof(uint64_t), st));
-    EncodeArgs ea{h->d_res.p, h->total_res, h->d_starts.p, (uint32_t)np, (uint32_t)h->ordinal_base, h->d_slice_prot.p};
+    EncodeArgs ea{h->d_res.p, h->total_res, h->d_starts.p, (uint32_t)np, (uint32_t)h->ordinal_base, h->d_slice_prot.p, h->d_prot_windows.p};
     CU(h, launch_encode(ea, h->d_keys[0].p, h->d_vals[0].p, h->d_scan_state.p, sc->ticket + TK_ENCODE, &sc->n_records, st)); ++launches;
     CU(h, cudaEventRecord(h->ev[EV_ENCODE], st));
 
@@ -162,15 +166,15 @@ int do_build_device(sigk_handle *h) {
     // ---- stages 3+4: run-length + reduce + keep/reject, the order-dependent columns, compaction
     const uint64_t scan_words = reduce_scan_entries(cap);
     CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, scan_words * sizeof(uint64_t), st));
-    CU(h, cudaMemsetAsync(h->d_giant_side.p, 0, reduce_side_entries(cap) * sizeof(uint4), st));
     const int order_stats = (h->cfg.flags & SIGK_F_NO_ORDER_STATS) ? 0 : 1;
     KeptColumns kc{h->d_out_kmer.p, out_col(h, 0), out_col(h, 1), out_col(h, 2), out_col(h, 3), out_col(h, 4)};
-    CU(h, launch_giant_prepass(h->d_keys[cur].p, h->d_vals[cur].p, &sc->n_records, cap, h->d_meta.p, h->d_giant_list.p,
-                               &sc->n_giant, &sc->next_giant, h->d_giant_side.p, h->d_bitmap.p, h->sm_count, st));
-    launches += cap > 512 ? 2 : 0;
-    CU(h, launch_stream_reduce(h->d_keys[cur].p, h->d_vals[cur].p, &sc->n_records, cap, h->d_meta.p, h->d_giant_side.p,
-                               h->d_rows.p, h->d_work.p, &sc->n_work, h->d_work_long.p, &sc->n_work_long, h->d_bitmap.p, h->d_distinct.p, h->d_scan_state.p,
-                               sc->ticket + TK_REDUCE, &sc->n_segments, order_stats, h->sm_count, st)); ++launches;
+    ReduceLists rl{h->d_groups.p, &sc->n_groups, &sc->next_group, h->d_long_groups.p, &sc->n_long, &sc->next_long,
+                   h->d_work.p, &sc->n_work, h->d_work_long.p, &sc->n_work_long};
+    CU(h, launch_segment_reduce(h->d_keys[cur].p, h->d_vals[cur].p, &sc->n_records, cap, h->d_meta.p, h->d_rows.p, rl,
+                                h->d_prot_rejected.p, h->d_distinct.p, h->d_scan_state.p, sc->ticket + TK_REDUCE, &sc->n_segments,
+                                order_stats, h->sm_count, st)); launches += 2;
+    if (h->comm) { if (int rc = comm_reduce_rejected(h)) return rc; }
+    CU(h, launch_signature_flags(h->d_prot_windows.p, h->d_prot_rejected.p + h->ordinal_base, h->d_seqid.p, (uint32_t)np, h->d_bitmap.p, st)); ++launches;
     CU(h, launch_popcount(h->d_bitmap.p, ((uint64_t)h->max_seq_id >> 5) + 1, &sc->n_seqs_sig, st)); ++launches;
     CU(h, cudaEventRecord(h->ev[EV_REDUCE], st));
     if (order_stats) { CU(h, launch_order_stats(h->d_vals[cur].p, h->d_meta.p, h->d_work.p, &sc->n_work, h->d_work_long.p, &sc->n_work_long, &sc->next_work_long, cap, h->d_rows.p, h->sm_count, st)); launches += 2; }
@@ -285,8 +289,9 @@ void sigk_destroy(sigk_handle *h) {
     h->d_res.release(); h->d_starts.release(); h->d_func.release(); h->d_seqid.release(); h->d_meta.release(); h->d_slice_prot.release();
     for (int i = 0; i < 2; ++i) { h->d_keys[i].release(); h->d_vals[i].release(); }
     h->d_lookback.release(); h->d_hist.release(); h->d_binbase.release(); h->d_scan_state.release();
-    h->d_giant_side.release(); h->d_giant_list.release(); h->d_work.release(); h->d_work_long.release(); h->d_rows.release(); h->d_out_kmer.release(); h->d_out_cols.release();
+    h->d_groups.release(); h->d_long_groups.release(); h->d_work.release(); h->d_work_long.release(); h->d_rows.release(); h->d_out_kmer.release(); h->d_out_cols.release();
     h->d_bitmap.release(); h->d_distinct.release(); h->d_swf.release(); h->d_scalars.release();
+    h->d_prot_windows.release(); h->d_prot_rejected.release();
     h->h_kmer.release(); h->h_cols.release(); h->h_distinct.release(); h->h_swf.release(); h->h_scalars.release();
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -411,7 +416,7 @@ int sigk_dbg_encode(sigk_handle *h, const sigk_proteins *p, uint64_t *out_code, 
     DeviceScalars *sc = h->d_scalars.p;
     CU(h, cudaMemsetAsync(sc, 0, sizeof(DeviceScalars), st));
     CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, encode_scan_entries(h->total_res) * sizeof(uint64_t), st));
-    EncodeArgs ea{h->d_res.p, h->total_res, h->d_starts.p, (uint32_t)p->n_proteins, 0u, h->d_slice_prot.p};
+    EncodeArgs ea{h->d_res.p, h->total_res, h->d_starts.p, (uint32_t)p->n_proteins, 0u, h->d_slice_prot.p, nullptr};
     if (h->comm) return h->fail(SIGK_E_UNSUPPORTED, "sigk_dbg_encode is single-GPU");
     CU(h, launch_encode(ea, h->d_keys[0].p, h->d_vals[0].p, h->d_scan_state.p, sc->ticket + TK_ENCODE, &sc->n_records, st));
     uint64_t n = 0;
