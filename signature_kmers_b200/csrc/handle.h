@@ -19,7 +19,7 @@ struct DeviceScalars {
     uint64_t n_kept;
     uint64_t n_seqs_sig;
     uint32_t ticket[16];
-    uint32_t n_groups, next_group, n_long, next_long, n_work, n_work_long, next_work_long, pad[1];
+    uint32_t n_groups, next_group, n_long, next_long, n_work, next_work, n_work_long, next_work_long;
     uint64_t reduce_in[4];      // multi-GPU: {occurrences, groups, kept, -} of this rank -> summed over ranks
 };
 

@@ -114,7 +114,7 @@ cudaError_t launch_segment_reduce(const uint64_t *keys, const uint32_t *vals, co
                                   int order_stats, int sm_count, cudaStream_t stream);
 // median / var of the groups listed in `work`, patched into their rows.
 cudaError_t launch_order_stats(const uint32_t *vals, const uint4 *meta, const OrderWork *work, const uint32_t *n_work,
-                               const OrderWork *work_long, const uint32_t *n_work_long, uint32_t *next_long,
+                               uint32_t *next_work, const OrderWork *work_long, const uint32_t *n_work_long, uint32_t *next_long,
                                uint64_t capacity, uint4 *rows, int sm_count, cudaStream_t stream);
 // Compaction: kept rows -> table columns (tombstones dropped, order kept).  scan_state: squeeze_tiles()+1 zeroed words.
 cudaError_t launch_squeeze_rows(const uint4 *rows, const uint64_t *n_seg_ptr, uint64_t capacity, KeptColumns out,

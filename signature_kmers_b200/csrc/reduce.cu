@@ -70,7 +70,8 @@ SIGK_D void count_rejected(uint32_t *prot_rejected, uint32_t ordinal) { atomicAd
 
 struct SegResult {
     bool keep;
-    uint32_t func, best_count, avg, mean;
+    bool closed;            // all best lengths equal and the 16-bit sum did not wrap: median = that length, var = 0
+    uint32_t func, best_count, avg, mean, len0;
 };
 
 // A group of n > 32 records starting at `start`, reduced by the whole warp in strides of 32:
@@ -80,7 +81,7 @@ struct SegResult {
 SIGK_D SegResult reduce_long_segment(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                                      const uint4 *__restrict__ meta, uint64_t start, uint32_t n, uint32_t *prot_rejected) {
     const unsigned lane = threadIdx.x & 31u;
-    SegResult r{false, 0, 0, 0, 0};
+    SegResult r{false, false, 0, 0, 0, 0, 0};
     // walk 1: bit-sliced majority vote over func_index; lane b owns bit b
     uint32_t ones = 0;
     for (uint32_t base = 0; base < n; base += 32) {
@@ -96,18 +97,20 @@ SIGK_D SegResult reduce_long_segment(const uint64_t *__restrict__ keys, const ui
     const uint32_t cand = __ballot_sync(FULL, lane < 16 && 2ull * ones > n) & 0xFFFFu;
     // walk 2: count the candidate, sum its lengths (mod 65536), OR of offset differences
     const uint32_t off0 = sigk_key_offset(keys[start]);
-    uint32_t best = 0, S = 0, vary = 0;
+    uint32_t best = 0, S = 0, vary = 0, lmin = 0xFFFFFFFFu, lmax = 0;
     for (uint32_t base = 0; base < n; base += 32) {
         const uint32_t j = base + lane;
         if (j < n) {
             const uint4 m = __ldg(&meta[vals[start + j]]);
-            if (m.z == cand) { ++best; S += m.x; }
+            if (m.z == cand) { ++best; S += m.x; lmin = min(lmin, m.x); lmax = max(lmax, m.x); }
             vary |= sigk_key_offset(keys[start + j]) ^ off0;
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { best += __shfl_xor_sync(FULL, best, o); S += __shfl_xor_sync(FULL, S, o); }
     vary = __reduce_or_sync(FULL, vary);
+    lmin = __reduce_min_sync(FULL, lmin);
+    lmax = __reduce_max_sync(FULL, lmax);
     r.func = cand;
     r.best_count = best;
     r.keep = keep_rule(best, n);
@@ -116,6 +119,8 @@ SIGK_D SegResult reduce_long_segment(const uint64_t *__restrict__ keys, const ui
         return r;
     }
     r.mean = (S & 0xFFFFu) / best;
+    r.len0 = lmin;
+    r.closed = lmin == lmax && (uint64_t)best * lmin < 65536ull;
     // offset of rank n/2 by radix select over the varying bits, most significant first: one walk per bit
     uint32_t rank = n / 2, prefix = off0 & ~vary, pmask = ~vary & 0xFFFFu;
     while (vary) {
@@ -149,7 +154,7 @@ constexpr int RED_THREADS = 128;
 constexpr int HS_AHEAD = 4;             // rows of keys/values the run-length pass keeps in flight
 constexpr int WORK_BLOCK = 64;          // list slots a warp reserves at a time (groups / order-statistics work)
 constexpr int GR_CHUNK = 256;           // group descriptors a warp takes per fetch
-constexpr uint32_t ORD_LONG = 4096;     // groups above this are walked by a whole warp (the tail); below, a lane each
+constexpr uint32_t ORD_LONG = 32768;    // groups above this are walked by a whole warp (the tail); below, a lane each
 
 struct WorkCursor { uint32_t base, free; };
 
@@ -354,13 +359,14 @@ group_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
             if (i >= total_long) break;
             const OrderWork d = long_groups[i];
             const SegResult r = reduce_long_segment(keys, vals, meta, d.start, d.count, prot_rejected);
-            const bool walk = r.keep && order_stats;            // best_count >= 27 here
-            const bool walk_long = walk && d.count > ORD_LONG;  // whole-warp walk (order_stats_long_kernel)
+            const bool walk = r.keep && order_stats && !r.closed;   // best_count >= 27 here
+            const bool walk_long = walk && d.count > ORD_LONG;      // whole-warp walk (order_stats_long_kernel)
             if (walk && !walk_long) work_reserve(wc, 1u, work, n_work);
             if (lane == 0) {
                 if (r.keep) {
                     const uint64_t code = sigk_key_code(keys[d.start]);
-                    rows[d.row] = make_uint4((uint32_t)code, (uint32_t)(code >> 32) | (r.avg << 11), r.func | (r.mean << 16), 0u);
+                    rows[d.row] = make_uint4((uint32_t)code, (uint32_t)(code >> 32) | (r.avg << 11), r.func | (r.mean << 16),
+                                             (order_stats && r.closed) ? r.len0 : 0u);
                     atomicAdd(distinct_functions + r.func, 1u);                 // tcc:286
                     if (walk_long) work_long[atomicAdd(n_work_long, 1u)] = d;
                     else if (walk) work[wc.base] = d;
@@ -469,7 +475,15 @@ group_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
             }
             if (act && !keep) count_rejected(prot_rejected, ord);
 
-            const bool walk = keep && head && order_stats && best_count >= 3;
+            // Three or more best items: if they all have the same length L and best_count * L < 65536
+            // (the 16-bit sum has not wrapped), every P^2 height is L and every variance step adds
+            // (L - (n L)/n)^2 = 0 exactly, so median = L and var = 0 without walking the group.
+            const uint32_t len0 = __shfl_sync(FULL, m.x, (__ffs(best_mask) - 1) & 31);
+            const bool uneven = (__ballot_sync(FULL, is_best && m.x != len0) & segmask) != 0;
+            const bool closed = !uneven && (uint64_t)best_count * len0 < 65536ull;
+            if (best_count >= 3 && closed) var2 = 0;
+            const uint32_t median_now = (best_count >= 3 && closed) ? len0 : 0u;
+            const bool walk = keep && head && order_stats && best_count >= 3 && !closed;
             const unsigned wb = __ballot_sync(FULL, walk);
             if (wb) work_reserve(wc, (uint32_t)__popc(wb), work, n_work);
             if (head) {
@@ -479,7 +493,8 @@ group_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
                     uint32_t mean = (uint32_t)__float2uint_rz(__fmul_rn((float)S, __frcp_rn((float)best_count)));
                     if (mean * best_count > S) --mean;
                     else if ((mean + 1u) * best_count <= S) ++mean;
-                    rows[grow] = make_uint4((uint32_t)code, (uint32_t)(code >> 32) | (sel << 11), cand | (mean << 16), var2 << 16);
+                    rows[grow] = make_uint4((uint32_t)code, (uint32_t)(code >> 32) | (sel << 11), cand | (mean << 16),
+                                            (order_stats ? median_now : 0u) | (var2 << 16));
                     atomicAdd(distinct_functions + cand, 1u);                                   // tcc:286
                     if (walk) work[wc.base + __popc(wb & mask_lt(lane))] = OrderWork{grow, (uint32_t)p, cnt};
                 } else rows[grow] = make_uint4(0u, 0u, 0xFFFFu, 0u);
@@ -574,25 +589,35 @@ squeeze_rows_kernel(const uint4 *__restrict__ rows, const uint64_t *__restrict__
 // that finishes takes the next entry of its warp's block at once (groups differ in length by
 // orders of magnitude; waiting for the slowest lane left 13 % of the lanes busy in the v2 profile).
 constexpr int ORD_THREADS = 128;
-constexpr int ORD_BLOCK = 256;      // work entries one warp owns at a time
+constexpr int ORD_BLOCK = 64;       // work entries a warp takes per fetch
 
 __global__ void __launch_bounds__(ORD_THREADS)
 order_stats_kernel(const uint32_t *__restrict__ vals, const uint4 *__restrict__ meta, const OrderWork *__restrict__ work,
-                   const uint32_t *__restrict__ n_work, uint4 *__restrict__ rows) {
+                   const uint32_t *__restrict__ n_work, uint32_t *__restrict__ next, uint4 *__restrict__ rows) {
     const uint32_t total = *n_work;
     const unsigned lane = threadIdx.x & 31u;
-    const uint32_t warp_global = (blockIdx.x * ORD_THREADS + threadIdx.x) >> 5;
-    const uint32_t n_warps = (gridDim.x * ORD_THREADS) >> 5;
-    for (uint64_t b0 = (uint64_t)warp_global * ORD_BLOCK; b0 < total; b0 += (uint64_t)n_warps * ORD_BLOCK) {
-        uint32_t cursor = (uint32_t)b0;
-        const uint32_t b1 = (uint32_t)((b0 + ORD_BLOCK < total) ? b0 + ORD_BLOCK : total);
-        bool active = false;
-        uint32_t row = 0, cand = 0, left = 0;
-        uint64_t start = 0;
-        LengthAcc acc;
-        for (;;) {
-            const unsigned idle = __ballot_sync(FULL, !active);
-            if (idle && cursor < b1) {
+    // Blocks of ORD_BLOCK entries are handed out dynamically, and a warp takes its next block as soon as
+    // one of its lanes is idle — not when all of them are: entries of one family sit together in the list
+    // and range from 3 to tens of thousands of samples, so waiting for a block's longest group idled
+    // three lanes in four on the Zipf set.
+    uint32_t cursor = 0, b1 = 0;
+    bool drained = false;                       // the global list is exhausted
+    bool active = false;
+    uint32_t row = 0, cand = 0, left = 0;
+    uint64_t start = 0;
+    uint4 m_next = make_uint4(0, 0, 0, 0);      // meta of the sample to visit next, already in flight
+    LengthAcc acc;
+    for (;;) {
+        const unsigned idle = __ballot_sync(FULL, !active);
+        if (idle) {
+            if (cursor >= b1 && !drained) {
+                uint32_t nb = 0;
+                if (lane == 0) nb = atomicAdd(next, (uint32_t)ORD_BLOCK);
+                nb = __shfl_sync(FULL, nb, 0);
+                if (nb >= total) drained = true;
+                else { cursor = nb; b1 = (nb + ORD_BLOCK < total) ? nb + ORD_BLOCK : total; }
+            }
+            if (cursor < b1) {
                 const uint32_t take = min((uint32_t)__popc(idle), b1 - cursor);
                 const uint32_t r = __popc(idle & mask_lt(lane));
                 if (!active && r < take) {
@@ -600,22 +625,24 @@ order_stats_kernel(const uint32_t *__restrict__ vals, const uint4 *__restrict__ 
                     if (w.count) {                                         // count 0: an unused reserved slot
                         row = w.row; start = w.start; left = w.count;
                         cand = rows[w.row].z & 0xFFFFu;
+                        m_next = __ldg(meta + __ldg(vals + start + left - 1));
                         acc = LengthAcc();
                         active = true;
                     }
                 }
                 cursor += take;
             }
-            if (!__any_sync(FULL, active)) { if (cursor >= b1) break; else continue; }
-            if (active) {
-                // newest first: the multimap iterates a key's items in reverse insertion order
-                --left;
-                const uint4 m = __ldg(meta + __ldg(vals + start + left));
-                if (m.z == cand) acc.push(m.x);                            // acc(item.protein_length), tcc:271
-                if (left == 0) {
-                    rows[row].w = u16_from_double(acc.q2) | (u16_from_double(acc.var) << 16);   // tcc:278-279
-                    active = false;
-                }
+        }
+        if (!__any_sync(FULL, active)) { if (drained && cursor >= b1) break; else continue; }
+        if (active) {
+            // newest first: the multimap iterates a key's items in reverse insertion order
+            --left;
+            const uint4 m = m_next;
+            if (left) m_next = __ldg(meta + __ldg(vals + start + left - 1));
+            if (m.z == cand) acc.push(m.x);                            // acc(item.protein_length), tcc:271
+            if (left == 0) {
+                rows[row].w = u16_from_double(acc.q2) | (u16_from_double(acc.var) << 16);   // tcc:278-279
+                active = false;
             }
         }
     }
@@ -637,18 +664,40 @@ order_stats_long_kernel(const uint32_t *__restrict__ vals, const uint4 *__restri
         if (i >= total) return;
         const OrderWork w = work[i];
         const uint32_t cand = rows[w.row].z & 0xFFFFu;
-        LengthAcc acc;
+        LengthAcc acc;          // every lane carries the same state
         // newest first: batch b covers records count-1-32b-lane
         int64_t j = (int64_t)w.count - 1 - (int64_t)lane;
         uint4 m = j >= 0 ? __ldg(meta + __ldg(vals + (uint64_t)w.start + j)) : make_uint4(0, 0, 0xFFFFFFFFu, 0);
         for (int64_t left = w.count; left > 0; left -= 32) {
             const int64_t jn = j - 32;
             const uint4 mn = (left > 32 && jn >= 0) ? __ldg(meta + __ldg(vals + (uint64_t)w.start + jn)) : make_uint4(0, 0, 0xFFFFFFFFu, 0);
-            const int take = left < 32 ? (int)left : 32;
-            for (int l = 0; l < take; ++l) {
-                const uint32_t f = __shfl_sync(FULL, m.z, l);
-                const uint32_t x = __shfl_sync(FULL, m.x, l);
-                if (f == cand) acc.push(x);                                 // acc(item.protein_length), tcc:271
+            // Per batch of 32 samples the lanes work in parallel on everything that does not depend on
+            // the running state: which samples count (func == best), their running count n_i and wrapped
+            // sum S_i (prefix scans), and the variance term tmp_i^2/(n_i-1) with its two divisions.  Only
+            // var = var (n-1)/n + term_i and the P^2 marker update remain sequential.
+            const bool match = m.z == cand;
+            const unsigned mb = __ballot_sync(FULL, match);
+            if (mb) {
+                uint32_t sx = match ? m.x : 0u;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(FULL, sx, o);
+                    if (lane >= (unsigned)o) sx += y;
+                }
+                const uint32_t n_i = acc.n + __popc(mb & mask_le(lane));
+                const uint32_t S_i = (acc.S + sx) & 0xFFFFu;
+                const double term = (match && n_i > 1) ? LengthAcc::variance_term(m.x, S_i, n_i) : 0.0;
+                unsigned todo = mb;
+                while (todo) {
+                    const int l = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const uint32_t x = __shfl_sync(FULL, m.x, l);
+                    const double t = __shfl_sync(FULL, term, l);
+                    acc.n += 1;
+                    acc.quantile_step((double)x);                       // acc(item.protein_length), tcc:271
+                    if (acc.n > 1) acc.variance_step(acc.n, t);
+                }
+                acc.S = (acc.S + __shfl_sync(FULL, sx, 31)) & 0xFFFFu;
             }
             m = mn;
             j = jn;
@@ -732,14 +781,14 @@ cudaError_t launch_segment_reduce(const uint64_t *keys, const uint32_t *vals, co
 }
 
 cudaError_t launch_order_stats(const uint32_t *vals, const uint4 *meta, const OrderWork *work, const uint32_t *n_work,
-                               const OrderWork *work_long, const uint32_t *n_work_long, uint32_t *next_long,
+                               uint32_t *next_work, const OrderWork *work_long, const uint32_t *n_work_long, uint32_t *next_long,
                                uint64_t capacity, uint4 *rows, int sm_count, cudaStream_t stream) {
     if (capacity == 0) return cudaSuccess;
     // the long groups first: they are the tail
     order_stats_long_kernel<<<sm_count * 8, 128, 0, stream>>>(vals, meta, work_long, n_work_long, next_long, rows);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    order_stats_kernel<<<sm_count * 16, ORD_THREADS, 0, stream>>>(vals, meta, work, n_work, rows);
+    order_stats_kernel<<<sm_count * 16, ORD_THREADS, 0, stream>>>(vals, meta, work, n_work, next_work, rows);
     return cudaGetLastError();
 }
 

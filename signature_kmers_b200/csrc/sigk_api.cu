@@ -177,7 +177,7 @@ int do_build_device(sigk_handle *h) {
     CU(h, launch_signature_flags(h->d_prot_windows.p, h->d_prot_rejected.p + h->ordinal_base, h->d_seqid.p, (uint32_t)np, h->d_bitmap.p, st)); ++launches;
     CU(h, launch_popcount(h->d_bitmap.p, ((uint64_t)h->max_seq_id >> 5) + 1, &sc->n_seqs_sig, st)); ++launches;
     CU(h, cudaEventRecord(h->ev[EV_REDUCE], st));
-    if (order_stats) { CU(h, launch_order_stats(h->d_vals[cur].p, h->d_meta.p, h->d_work.p, &sc->n_work, h->d_work_long.p, &sc->n_work_long, &sc->next_work_long, cap, h->d_rows.p, h->sm_count, st)); launches += 2; }
+    if (order_stats) { CU(h, launch_order_stats(h->d_vals[cur].p, h->d_meta.p, h->d_work.p, &sc->n_work, &sc->next_work, h->d_work_long.p, &sc->n_work_long, &sc->next_work_long, cap, h->d_rows.p, h->sm_count, st)); launches += 2; }
     CU(h, cudaEventRecord(h->ev[EV_ORDER], st));
     CU(h, launch_squeeze_rows(h->d_rows.p, &sc->n_segments, cap, kc, h->d_scan_state.p + reduce_batches(cap) + 1,
                               sc->ticket + TK_SQUEEZE, &sc->n_kept, st)); ++launches;
