@@ -30,6 +30,9 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
+if __name__ == "__main__":
+    sys.modules.setdefault("bench", sys.modules["__main__"])   # multigpu.py imports helpers from this script
+
 METRIC = "kmer occurrences/s into kept-signature table"
 UNIT = "occurrences/s"
 RECORD_BYTES = 12
@@ -38,6 +41,25 @@ KEY_BYTES = 8
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+# stdout carries exactly one JSON line: everything else that writes to fd 1 (NCCL's version banner, library
+# chatter) is sent to stderr, and emit_json() writes to the saved descriptor.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_json(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def measured_peak_gbs():
@@ -160,7 +182,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -260,7 +282,7 @@ def run_gpu(args, rank, world, local_rank):
                      "stage_ms": {k: tm[k] for k in ("encode_ms", "histogram_ms", "sort_ms", "reduce_ms", "order_stats_ms", "squeeze_ms", "device_total_ms", "h2d_ms", "d2h_ms")}},
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
     builder.close()
 
 
@@ -277,6 +299,7 @@ def main():
     if args.warmup < 3 and args.impl == "sigk":
         log("[bench] note: fewer than 3 warm-up steps")
 
+    capture_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -168,7 +168,9 @@ def run_bench(args, rank, world, local_rank, metric, unit):
             # rank 0's share of the records is what its pass kernel moved
             line["roofline"] = {"bound": "hbm", "kernel": "onesweep_pass_kernel (rank 0)", "peak": peak, "unit": "GB/s",
                                 "peak_source": src, "pass_ms": pass_ms, "achieved": None, "frac": None, "traffic": None}
-        print(json.dumps(line), flush=True)
+        from bench import emit_json
+
+        emit_json(line)
     builder.close()
     dist.barrier()
     dist.destroy_process_group()
