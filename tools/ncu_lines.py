@@ -17,7 +17,7 @@ import tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def sass_lines(cubin_name, kernel_regex):
+def sass_lines(cubin_name, kernel_regex, want_len=None):
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "signature_kmers_b200", "libsigk.so")], cwd=tmp, capture_output=True)
     cubin = [f for f in os.listdir(tmp) if f.startswith(cubin_name + ".")][0]
@@ -33,10 +33,13 @@ def sass_lines(cubin_name, kernel_regex):
         m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
         if m and cur_fn:
             res[cur_fn].append((cur_line, m.group(2).strip()))
-    for fn, v in res.items():
-        if re.search(kernel_regex, fn):
-            return v
-    raise SystemExit("kernel not found in cubin")
+    cands = [v for fn, v in res.items() if re.search(kernel_regex, fn)]
+    if not cands:
+        raise SystemExit("kernel not found in cubin")
+    if want_len is None:
+        return cands[0]
+    # several template instantiations can match: take the one whose SASS length fits the report
+    return min(cands, key=lambda v: abs(len(v) - want_len))
 
 
 def main():
@@ -57,7 +60,7 @@ def main():
             body.append((r[si].strip(), int(r[ii]), int(r[sa])))
         except ValueError:
             pass
-    sass = sass_lines(cubin, kre)
+    sass = sass_lines(cubin, kre, len(body))
     if len(sass) != len(body):
         print(f"warning: {len(sass)} SASS instructions in cubin vs {len(body)} in report", file=sys.stderr)
     agg = {}
