@@ -81,15 +81,17 @@ encode_kernel(EncodeArgs a, uint64_t *__restrict__ keys, uint32_t *__restrict__ 
     }
     const uint32_t words[6] = {w.x, w.y, w.z, w.w, n0, n1};
 
-    int s[ENC_PPT + 7];
+    // symbols stay packed four to a register (23 ints would not fit the register budget)
+    uint32_t sw[6] = {0, 0, 0, 0, 0, 0};
     uint32_t bad = 0;
 #pragma unroll
     for (int j = 0; j < ENC_PPT + 7; ++j) {
         const unsigned c = (words[j >> 2] >> (8 * (j & 3))) & 0xFFu;
         int sy = sigk_symbol(c);
         if (sy < 0) { bad |= 1u << j; sy = 0; }
-        s[j] = sy;
+        sw[j >> 2] |= (uint32_t)sy << (8 * (j & 3));
     }
+#define SIGK_SYM(j) ((uint64_t)((sw[(j) >> 2] >> (8 * ((j) & 3))) & 0xFFu))
 
     // pass A: which of my 16 windows are valid
     const uint32_t p_first = find_protein(a.starts, p_lo, p_hi, g_first < a.total_res ? g_first : a.total_res - 1);
@@ -120,13 +122,13 @@ encode_kernel(EncodeArgs a, uint64_t *__restrict__ keys, uint32_t *__restrict__ 
         uint64_t prot_end = __ldg(a.starts + i + 1);
         uint64_t code = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) code = code * 40u + (uint64_t)s[j];
+        for (int j = 0; j < 8; ++j) code = code * 40u + SIGK_SYM(j);
         int o = (int)(incl - mine);
         uint32_t run_i = 0, run_c = 0;              // occurrences of the protein I am inside
 #pragma unroll
         for (int j = 0; j < ENC_PPT; ++j) {
             const uint64_t g = g_first + j;
-            if (j > 0) code = (code - (uint64_t)s[j - 1] * SIGK_P7) * 40u + (uint64_t)s[j + 7];
+            if (j > 0) code = (code - SIGK_SYM(j - 1) * SIGK_P7) * 40u + SIGK_SYM(j + 7);
             while (g >= prot_end && i + 1 < a.n_prot) { ++i; prot_end = __ldg(a.starts + i + 1); }
             if ((valid_mask >> j) & 1u) {
                 const int slot = stage_slot(o++);
@@ -151,6 +153,204 @@ encode_kernel(EncodeArgs a, uint64_t *__restrict__ keys, uint32_t *__restrict__ 
     }
 }
 
+// ---- multi-GPU: encode and route in one pass ---------------------------------------------------
+// The same window loop, but every record is written straight into the output region of the rank
+// that owns its k-mer range (owner = number of splitter codes <= code), in canonical order inside
+// each region: one chained scan per owner over the warp slices (a lane per owner walks back, as in
+// the onesweep look-back).  This replaces encode + owner histogram + split pass.
+// Per-owner 16-bit counters live four to a 64-bit word; the kernel is instantiated for 1, 2 or 4
+// words (up to 4, 8, 16 ranks) so that the common small worlds keep a small register footprint.
+
+struct EncSplitSmem {
+    uint64_t keys[ENC_WARPS][ENC_STAGE];
+    uint32_t vals[ENC_WARPS][ENC_STAGE];
+    uint8_t owner[ENC_WARPS][ENC_STAGE];
+    uint32_t obase[ENC_WARPS][16];          // first staging slot of each owner inside the warp
+    uint64_t gbase[ENC_WARPS][16];          // position in the owner's region of staging slot 0 of that owner, minus obase
+    uint64_t split[16];
+    uint64_t *dkeys[16];
+    uint32_t *dvals[16];
+    uint32_t tile;
+};
+
+template <int WORDS>
+SIGK_D uint32_t field16(const uint64_t (&w)[WORDS], uint32_t d) {
+    uint64_t x = w[0];
+#pragma unroll
+    for (int k = 1; k < WORDS; ++k) x = (d >> 2) == (uint32_t)k ? w[k] : x;
+    return (uint32_t)(x >> (16u * (d & 3u))) & 0xFFFFu;
+}
+template <int WORDS>
+SIGK_D void bump16(uint64_t (&w)[WORDS], uint32_t d) {
+    const uint64_t one = 1ull << (16u * (d & 3u));
+    if (WORDS == 1) { w[0] += one; return; }
+#pragma unroll
+    for (int k = 0; k < WORDS; ++k) w[k] += (d >> 2) == (uint32_t)k ? one : 0ull;
+}
+
+template <int SPLIT_WORDS>
+__global__ void __launch_bounds__(ENC_THREADS, 3)
+encode_split_kernel(EncodeArgs a, const __grid_constant__ EncodeSplitArgs sp, uint32_t *__restrict__ ticket) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EncSplitSmem &sm = *reinterpret_cast<EncSplitSmem *>(smem_raw);
+
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t W = (uint32_t)sp.n_split + 1u;
+    if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+    if (tid < (unsigned)sp.n_split) sm.split[tid] = sp.split_codes[tid];
+    if (tid < 16) { sm.dkeys[tid] = sp.dst_keys[tid]; sm.dvals[tid] = sp.dst_vals[tid]; }
+    __syncthreads();
+    const uint32_t sub = sm.tile * ENC_WARPS + warp;
+    const uint64_t g0 = (uint64_t)sub * ENC_SUB;
+    if (g0 >= a.total_res) return;
+    const bool last_sub = g0 + ENC_SUB >= a.total_res;
+    const uint32_t p_lo = __ldg(a.slice_prot + sub);
+    const uint32_t p_hi = last_sub ? a.n_prot - 1 : __ldg(a.slice_prot + sub + 1);
+
+    const uint64_t g_first = g0 + (uint64_t)lane * ENC_PPT;
+    const uint4 w = ld_stream_u128(reinterpret_cast<const uint4 *>(a.res + g_first));
+    uint32_t n0 = __shfl_down_sync(0xffffffffu, w.x, 1);
+    uint32_t n1 = __shfl_down_sync(0xffffffffu, w.y, 1);
+    if (lane == 31) {
+        const uint2 nx = *reinterpret_cast<const uint2 *>(a.res + g_first + ENC_PPT);
+        n0 = nx.x; n1 = nx.y;
+    }
+    const uint32_t words[6] = {w.x, w.y, w.z, w.w, n0, n1};
+    // symbols stay packed four to a register (23 ints would not fit the register budget)
+    uint32_t sw[6] = {0, 0, 0, 0, 0, 0};
+    uint32_t bad = 0;
+#pragma unroll
+    for (int j = 0; j < ENC_PPT + 7; ++j) {
+        const unsigned c = (words[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+        int sy = sigk_symbol(c);
+        if (sy < 0) { bad |= 1u << j; sy = 0; }
+        sw[j >> 2] |= (uint32_t)sy << (8 * (j & 3));
+    }
+#define SIGK_SYM(j) ((uint64_t)((sw[(j) >> 2] >> (8 * ((j) & 3))) & 0xFFu))
+
+    // pass A: valid windows, their owners (4 bits each), per-owner counts
+    const uint32_t p_first = find_protein(a.starts, p_lo, p_hi, g_first < a.total_res ? g_first : a.total_res - 1);
+    uint32_t valid_mask = 0;
+    uint64_t owners = 0;
+    uint64_t cnt[SPLIT_WORDS];
+#pragma unroll
+    for (int k = 0; k < SPLIT_WORDS; ++k) cnt[k] = 0;
+    {
+        uint32_t i = p_first;
+        uint64_t prot_end = __ldg(a.starts + i + 1);
+        uint64_t code = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) code = code * 40u + SIGK_SYM(j);
+#pragma unroll
+        for (int j = 0; j < ENC_PPT; ++j) {
+            const uint64_t g = g_first + j;
+            if (j > 0) code = (code - SIGK_SYM(j - 1) * SIGK_P7) * 40u + SIGK_SYM(j + 7);
+            while (g >= prot_end && i + 1 < a.n_prot) { ++i; prot_end = __ldg(a.starts + i + 1); }
+            if (((bad >> j) & 0xFFu) == 0 && g + SIGK_K_DEV <= prot_end) {
+                valid_mask |= 1u << j;
+                uint32_t d = 0;
+                for (int k = 0; k < sp.n_split; ++k) d += code >= sm.split[k] ? 1u : 0u;
+                owners |= (uint64_t)d << (4 * j);
+                bump16(cnt, d);
+            }
+        }
+    }
+    // warp scan of the packed counters (a slice has at most 512 records: 16-bit fields never carry)
+    uint64_t incl[SPLIT_WORDS];
+#pragma unroll
+    for (int k = 0; k < SPLIT_WORDS; ++k) {
+        uint64_t v = cnt[k];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t y = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= (unsigned)o) v += y;
+        }
+        incl[k] = v;
+    }
+    uint64_t excl[SPLIT_WORDS], tot[SPLIT_WORDS];
+#pragma unroll
+    for (int k = 0; k < SPLIT_WORDS; ++k) { excl[k] = incl[k] - cnt[k]; tot[k] = __shfl_sync(0xffffffffu, incl[k], 31); }
+    // lane d: this slice's record count for owner d; staging base of owner d; publish
+    const uint32_t t_d = lane < W ? field16(tot, lane) : 0u;
+    uint32_t ob = t_d;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, ob, o);
+        if (lane >= (unsigned)o) ob += y;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, ob, 15);
+    ob -= t_d;
+    if (lane < 16) sm.obase[warp][lane] = ob;
+    uint64_t *my_state = sp.owner_state + (size_t)sub * W + lane;
+    if (lane < W) st_volatile_u64(my_state, (sub == 0 ? SIGK_CS_PRE : SIGK_CS_AGG) | (uint64_t)t_d);
+    __syncwarp();
+
+    // pass B: roll the code again, emit every valid window to its owner's part of the staging area
+    // (the empty asm makes the symbols opaque so that pass A's partial products are not kept live)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) asm volatile("" : "+r"(sw[k]));
+    {
+        uint32_t i = p_first;
+        uint64_t prot_end = __ldg(a.starts + i + 1);
+        uint64_t code = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) code = code * 40u + SIGK_SYM(j);
+        uint64_t run[SPLIT_WORDS];
+#pragma unroll
+        for (int k = 0; k < SPLIT_WORDS; ++k) run[k] = excl[k];
+        uint32_t run_i = 0, run_c = 0;
+#pragma unroll
+        for (int j = 0; j < ENC_PPT; ++j) {
+            const uint64_t g = g_first + j;
+            if (j > 0) code = (code - SIGK_SYM(j - 1) * SIGK_P7) * 40u + SIGK_SYM(j + 7);
+            while (g >= prot_end && i + 1 < a.n_prot) { ++i; prot_end = __ldg(a.starts + i + 1); }
+            if ((valid_mask >> j) & 1u) {
+                const uint32_t d = (uint32_t)(owners >> (4 * j)) & 15u;
+                const int slot = stage_slot((int)(sm.obase[warp][d] + field16(run, d)));
+                bump16(run, d);
+                sm.keys[warp][slot] = sigk_pack_key(code, (unsigned)(prot_end - g));
+                sm.vals[warp][slot] = a.ordinal_base + i;
+                sm.owner[warp][slot] = (uint8_t)d;
+                if (i != run_i) {
+                    if (run_c && a.prot_windows) atomicAdd(a.prot_windows + run_i, run_c);
+                    run_i = i; run_c = 0;
+                }
+                ++run_c;
+            }
+        }
+        if (run_c && a.prot_windows) atomicAdd(a.prot_windows + run_i, run_c);
+    }
+
+    // resolve: lane d walks back over the earlier slices of owner d
+    if (lane < W) {
+        uint64_t before = 0;
+        if (sub > 0) {
+            int64_t t = (int64_t)sub - 1;
+            for (;;) {
+                const uint64_t v = ld_volatile_u64(sp.owner_state + (size_t)t * W + lane);
+                const uint64_t flag = v >> 62;
+                if (flag == 0) continue;
+                before += v & SIGK_CS_VAL;
+                if (flag == 2) break;
+                --t;
+            }
+            st_volatile_u64(my_state, SIGK_CS_PRE | (before + t_d));
+        }
+        if (before + t_d > sp.region_stride) atomicOr(sp.overflow, 1u);
+        if (last_sub) sp.owner_totals[lane] = before + t_d;
+        sm.gbase[warp][lane] = before - ob;
+    }
+    __syncwarp();
+    if (*reinterpret_cast<volatile uint32_t *>(sp.overflow)) return;      // regions too small: the caller falls back
+    for (uint32_t o = lane; o < total; o += 32) {
+        const int slot = stage_slot((int)o);
+        const uint32_t d = sm.owner[warp][slot];
+        const uint64_t pos = sm.gbase[warp][d] + o;
+        sm.dkeys[d][pos] = sm.keys[warp][slot];
+        sm.dvals[d][pos] = sm.vals[warp][slot];
+    }
+}
+
 // slice_prot[b] = protein holding position b * ENC_SUB: one binary search per slice, done
 // once per upload instead of once per warp per build.
 __global__ void slice_index_kernel(const uint64_t *__restrict__ starts, uint32_t n_prot, uint64_t total_res,
@@ -169,6 +369,16 @@ cudaError_t launch_slice_index(const uint64_t *starts, uint32_t n_prot, uint64_t
     if (total_res == 0 || n_prot == 0) return cudaSuccess;
     const uint64_t n = encode_slices(total_res);
     slice_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(starts, n_prot, total_res, slice_prot, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_encode_split(const EncodeArgs &a, const EncodeSplitArgs &sp, uint32_t *ticket, cudaStream_t stream) {
+    if (a.total_res == 0 || a.n_prot == 0) return cudaSuccess;
+    if (sp.n_split < 1 || sp.n_split > 15) return cudaErrorInvalidValue;
+    auto kernel = sp.n_split < 4 ? encode_split_kernel<1> : sp.n_split < 8 ? encode_split_kernel<2> : encode_split_kernel<4>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSplitSmem));
+    if (e != cudaSuccess) return e;
+    kernel<<<(unsigned)encode_tiles(a.total_res), ENC_THREADS, sizeof(EncSplitSmem), stream>>>(a, sp, ticket);
     return cudaGetLastError();
 }
 

@@ -138,6 +138,8 @@ int comm_exchange_shapes(sigk_handle *h);
 int comm_allgather_meta(sigk_handle *h);
 // encode output in keys[0]/vals[0] -> records of this rank's k-mer range in keys[0]/vals[0], n_records updated
 int comm_partition_exchange(sigk_handle *h, uint32_t *launches);
+// multi-GPU stage 1: encode + route + all-to-all (fused kernel, falls back to encode + split pass)
+int comm_encode_exchange(sigk_handle *h, const EncodeArgs &ea, uint32_t *launches);
 // sum over ranks of the per-protein rejected-occurrence counts (before signature_flags)
 int comm_reduce_rejected(sigk_handle *h);
 // sum the per-rank statistics so that every rank's result carries whole-job counters

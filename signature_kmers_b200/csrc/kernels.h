@@ -36,6 +36,23 @@ cudaError_t launch_encode(const EncodeArgs &a, uint64_t *keys, uint32_t *vals, u
                           uint32_t *ticket, uint64_t *n_out, cudaStream_t stream);
 
 
+// Multi-GPU: encode and route in one pass.  Owner d's records go, in canonical order, to
+// dst_keys[d][0...] / dst_vals[d][0...] (this rank's region on owner d: a local send region, or — with
+// peer mappings — memory of GPU d written over NVLink); owner_totals[d] receives their number; *overflow is
+// set (and the output is incomplete) if a region is too small.  owner_state: encode_slices() * (n_split + 1)
+// zeroed u64 words.
+struct EncodeSplitArgs {
+    const uint64_t *split_codes;   // device, n_split ascending codes: owner = number of codes <= the record's code
+    int n_split;
+    uint64_t region_stride;        // records each region can hold
+    uint64_t *owner_state;
+    uint64_t *owner_totals;        // device, n_split + 1
+    uint32_t *overflow;            // device, zeroed
+    uint64_t *dst_keys[16];
+    uint32_t *dst_vals[16];
+};
+cudaError_t launch_encode_split(const EncodeArgs &a, const EncodeSplitArgs &sp, uint32_t *ticket, cudaStream_t stream);
+
 // ---- stage 2: onesweep LSD radix sort (onesweep.cu) ------------------------
 constexpr int SORT_MAX_PASSES = 8;
 constexpr int SORT_MAX_SPLIT = 15;    // the partition pass routes to at most 16 ranks

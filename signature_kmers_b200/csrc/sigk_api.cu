@@ -132,12 +132,13 @@ int do_build_device(sigk_handle *h) {
     if (h->comm) { if (int rc = comm_allgather_meta(h)) return rc; }
     CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, encode_scan_entries(h->total_res) * sizeof(uint64_t), st));
     EncodeArgs ea{h->d_res.p, h->total_res, h->d_starts.p, (uint32_t)np, (uint32_t)h->ordinal_base, h->d_slice_prot.p, h->d_prot_windows.p};
-    CU(h, launch_encode(ea, h->d_keys[0].p, h->d_vals[0].p, h->d_scan_state.p, sc->ticket + TK_ENCODE, &sc->n_records, st)); ++launches;
-    CU(h, cudaEventRecord(h->ev[EV_ENCODE], st));
-
-    // ---- multi-GPU: route every record to the rank that owns its k-mer range
-    if (h->comm) {
-        if (int rc = comm_partition_exchange(h, &launches)) return rc;
+    if (!h->comm) {
+        CU(h, launch_encode(ea, h->d_keys[0].p, h->d_vals[0].p, h->d_scan_state.p, sc->ticket + TK_ENCODE, &sc->n_records, st)); ++launches;
+        CU(h, cudaEventRecord(h->ev[EV_ENCODE], st));
+    } else {
+        // ---- multi-GPU: every record goes to the rank that owns its k-mer range
+        CU(h, cudaEventRecord(h->ev[EV_ENCODE], st));
+        if (int rc = comm_encode_exchange(h, ea, &launches)) return rc;
         CU(h, cudaMemsetAsync(h->d_hist.p, 0, SORT_MAX_PASSES * SIGK_RADIX * sizeof(uint64_t), st));
     }
     CU(h, cudaEventRecord(h->ev[EV_EXCHANGE], st));
