@@ -134,7 +134,7 @@ const char *sigk_version(void);
 int sigk_device_count(void);
 
 int  sigk_create(const sigk_config *cfg, sigk_handle **out);
-void sigk_destroy(sigk_handle *h);
+void sigk_destroy(sigk_handle *h);   /* collective after sigk_comm_join: every rank calls it (peer mappings are torn down together) */
 const char *sigk_last_error(const sigk_handle *h);   /* h may be NULL: last create error */
 
 /* Pinned host memory for input arrays (optional but needed for full PCIe rate). */

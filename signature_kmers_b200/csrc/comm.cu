@@ -317,6 +317,13 @@ int comm_join(sigk_handle *h, const void *id128) {
 void comm_destroy(sigk_handle *h) {
     Comm *c = h->comm;
     if (!c) return;
+    if (c->peer_ok) {
+        // exported memory must not be freed while a peer still has it mapped: close the imports, wait
+        // for every rank to have done the same (sigk_destroy is collective when world > 1), then free
+        close_imports(c);
+        uint64_t dummy = 0;
+        agree(h, 1, &dummy);
+    }
     release_landing(c);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     c->d_samples.release(); c->d_samples_alt.release(); c->d_split.release(); c->d_counts.release(); c->d_shape.release(); c->d_owner_state.release(); c->d_ipc.release();
@@ -361,7 +368,7 @@ int comm_allgather_meta(sigk_handle *h) {
     uint64_t base = 0;
     for (int r = 0; r < c->world; ++r) {
         if (c->prot_count[r])
-            NC(h, g_nccl.Broadcast(h->d_meta.p + base, h->d_meta.p + base, c->prot_count[r] * sizeof(uint4), ncclUint8, r, c->comm, st));
+            NC(h, g_nccl.Broadcast(h->d_meta.p + base, h->d_meta.p + base, c->prot_count[r] * sizeof(ProtMeta), ncclUint8, r, c->comm, st));
         base += c->prot_count[r];
     }
     NC(h, g_nccl.GroupEnd());

@@ -29,7 +29,7 @@ template <typename T> struct DevBuf {
     T *p = nullptr;
     size_t cap = 0;     // elements
     cudaError_t reserve(size_t n) {
-        if (n <= cap) return cudaSuccess;
+        if (p && n <= cap) return cudaSuccess;      // reserve(0) still yields a valid pointer (empty ranks, empty inputs)
         if (p) { cudaFree(p); p = nullptr; cap = 0; }
         cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
         if (e == cudaSuccess) cap = n;
@@ -42,7 +42,7 @@ template <typename T> struct PinnedBuf {
     T *p = nullptr;
     size_t cap = 0;
     cudaError_t reserve(size_t n) {
-        if (n <= cap) return cudaSuccess;
+        if (p && n <= cap) return cudaSuccess;
         if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
         cudaError_t e = cudaMallocHost(&p, std::max<size_t>(n, 1) * sizeof(T));
         if (e == cudaSuccess) cap = n;
@@ -75,7 +75,8 @@ struct sigk_handle {
     sigk::DevBuf<uint64_t> d_starts;
     sigk::DevBuf<uint16_t> d_func;
     sigk::DevBuf<uint32_t> d_seqid, d_slice_prot;
-    sigk::DevBuf<uint4> d_meta, d_rows;
+    sigk::DevBuf<sigk::ProtMeta> d_meta;
+    sigk::DevBuf<uint4> d_rows;
     sigk::DevBuf<sigk::OrderWork> d_groups, d_long_groups, d_work, d_work_long;
     sigk::DevBuf<uint64_t> d_keys[2];
     sigk::DevBuf<uint32_t> d_vals[2];

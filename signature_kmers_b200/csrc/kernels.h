@@ -100,19 +100,27 @@ struct KeptColumns {           // device, capacity rows each
 };
 struct OrderWork { uint32_t row, start, count; };   // kept group whose median/var need the ordered walk
 
-constexpr int RED_BATCH = 2048;     // sorted records one warp takes per ticket in the streaming reduce
+constexpr int RED_BATCH = 2048;     // sorted records per run-length tile
 inline uint64_t reduce_batches(uint64_t capacity) { return (capacity + RED_BATCH - 1) / RED_BATCH; }
 inline uint64_t squeeze_tiles(uint64_t capacity) { return (capacity + 2047) / 2048; }
-inline uint64_t reduce_scan_entries(uint64_t capacity) { return reduce_batches(capacity) + squeeze_tiles(capacity) + 2; }
+// scan_state words: chained scan of the run-length tiles, chained scan of the squeeze tiles, then per
+// run-length tile one u64 (group left open at the tile end) and one u32 (first head of the tile)
+inline uint64_t reduce_tile_open_offset(uint64_t capacity) { return reduce_batches(capacity) + squeeze_tiles(capacity) + 2; }
+inline uint64_t reduce_scan_entries(uint64_t capacity) {
+    return reduce_tile_open_offset(capacity) + reduce_batches(capacity) + reduce_batches(capacity) / 2 + 2;
+}
 size_t reduce_group_entries(uint64_t capacity, int sm_count);  // OrderWork entries: groups of 2..32 records
 size_t reduce_long_group_entries(uint64_t capacity);           // OrderWork entries: groups of more than 32 records
 size_t reduce_work_entries(uint64_t capacity, int sm_count);   // OrderWork entries: groups whose median/var need the ordered walk
 size_t reduce_long_work_entries(uint64_t capacity);            // ... of those, the ones a whole warp walks
 cudaError_t reduce_configure();
 
-// meta[i] = {protein_length, seq_id, function_index, 0}; seqs_with_func[f]++ (src/signature_build.tcc:160)
+// What a record's protein ordinal is looked up for: 8 bytes, so that the job-wide table stays in L2 as long
+// as possible (2 M proteins = 16 MB).  x = protein_length, y = function_index.
+using ProtMeta = uint2;
+// meta[i] = {protein_length, function_index}; seqs_with_func[f]++ (src/signature_build.tcc:160)
 cudaError_t launch_protein_meta(const uint64_t *starts, const uint16_t *func, const uint32_t *seq_id, uint32_t n_prot,
-                                uint4 *meta, uint32_t *seqs_with_func, cudaStream_t stream);
+                                ProtMeta *meta, uint32_t *seqs_with_func, cudaStream_t stream);
 
 // device lists and counters of the segment reduce (counters zeroed before the launch)
 struct ReduceLists {
@@ -124,13 +132,13 @@ struct ReduceLists {
 // Run-length + per-group reduce + keep/reject over the sorted records (head_scan_kernel, then
 // group_reduce_kernel): one packed row per group in k-mer order (rejected groups
 // leave a tombstone), plus the lists of groups whose median/var need the ordered walk.
-// scan_state: reduce_batches()+1 zeroed words.
+// scan_state: reduce_scan_entries() zeroed words (the squeeze uses its own part of them).
 cudaError_t launch_segment_reduce(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
-                                  const uint4 *meta, uint4 *rows, const ReduceLists &l, uint32_t *prot_rejected,
+                                  const ProtMeta *meta, uint4 *rows, const ReduceLists &l, uint32_t *prot_rejected,
                                   uint32_t *distinct_functions, uint64_t *scan_state, uint32_t *ticket, uint64_t *n_seg_out,
                                   int order_stats, int sm_count, cudaStream_t stream);
 // median / var of the groups listed in `work`, patched into their rows.
-cudaError_t launch_order_stats(const uint32_t *vals, const uint4 *meta, const OrderWork *work, const uint32_t *n_work,
+cudaError_t launch_order_stats(const uint32_t *vals, const ProtMeta *meta, const OrderWork *work, const uint32_t *n_work,
                                uint32_t *next_work, const OrderWork *work_long, const uint32_t *n_work_long, uint32_t *next_long,
                                uint64_t capacity, uint4 *rows, int sm_count, cudaStream_t stream);
 // Compaction: kept rows -> table columns (tombstones dropped, order kept).  scan_state: squeeze_tiles()+1 zeroed words.

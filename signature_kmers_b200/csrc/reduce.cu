@@ -79,7 +79,7 @@ struct SegResult {
 // then one walk per varying offset bit for the radix select (inside a family the offsets rarely
 // differ in more than a few bits; none when they are all equal).
 SIGK_D SegResult reduce_long_segment(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-                                     const uint4 *__restrict__ meta, uint64_t start, uint32_t n, uint32_t *prot_rejected) {
+                                     const ProtMeta *__restrict__ meta, uint64_t start, uint32_t n, uint32_t *prot_rejected) {
     const unsigned lane = threadIdx.x & 31u;
     SegResult r{false, false, 0, 0, 0, 0, 0};
     // walk 1: bit-sliced majority vote over func_index; lane b owns bit b
@@ -87,7 +87,7 @@ SIGK_D SegResult reduce_long_segment(const uint64_t *__restrict__ keys, const ui
     for (uint32_t base = 0; base < n; base += 32) {
         const uint32_t j = base + lane;
         const bool act = j < n;
-        const uint32_t f = act ? __ldg(&meta[vals[start + j]]).z : 0u;
+        const uint32_t f = act ? __ldg(&meta[vals[start + j]]).y : 0u;
 #pragma unroll
         for (int b = 0; b < 16; ++b) {
             const unsigned bal = __ballot_sync(FULL, act && ((f >> b) & 1u));
@@ -101,8 +101,8 @@ SIGK_D SegResult reduce_long_segment(const uint64_t *__restrict__ keys, const ui
     for (uint32_t base = 0; base < n; base += 32) {
         const uint32_t j = base + lane;
         if (j < n) {
-            const uint4 m = __ldg(&meta[vals[start + j]]);
-            if (m.z == cand) { ++best; S += m.x; lmin = min(lmin, m.x); lmax = max(lmax, m.x); }
+            const ProtMeta m = __ldg(&meta[vals[start + j]]);
+            if (m.y == cand) { ++best; S += m.x; lmin = min(lmin, m.x); lmax = max(lmax, m.x); }
             vary |= sigk_key_offset(keys[start + j]) ^ off0;
         }
     }
@@ -141,20 +141,29 @@ SIGK_D SegResult reduce_long_segment(const uint64_t *__restrict__ keys, const ui
 }
 
 // ---- stage 3a: run-length ---------------------------------------------------------------------
-// Persistent warps.  A warp takes a batch of RED_BATCH sorted records by ticket, counts the group
-// heads in it and publishes that count at once (chained scan over batches): every group, kept or
-// not, owns the row slot of its index, so nothing downstream waits for a keep decision; rejected
-// groups leave a tombstone (function_index 0xFFFF) that squeeze_rows_kernel removes.
-// Single-record groups (92 % of the groups of the 2 M-protein set, always kept: 1 >= 0.8) are
-// finished here; groups of 2..32 records go to `groups`, longer ones to `long_groups`.
+// One tile of RED_BATCH sorted records per block (tiles by ticket), HS_ITEMS consecutive records per
+// thread: head flags by neighbour compare, block scan of the head counts, chained scan over the tiles
+// (published before anything else happens).  Every group, kept or not, owns the row slot of its index,
+// so nothing downstream waits for a keep decision; rejected groups leave a tombstone (function_index
+// 0xFFFF) that squeeze_rows_kernel removes.
+// A head's group ends at the next head; a suffix-min over the block gives it to every thread.
+// Single-record groups (92 % of the groups of the 2 M-protein set, always kept: 1 >= 0.8) are finished
+// here; groups of 2..32 records go to `groups`, longer ones to `long_groups`.  The last group of a tile
+// may run into the following tiles: the tile leaves {row, start} in tile_open, every tile leaves the
+// position of its first head in tile_first, and resolve_open_kernel closes those groups afterwards
+// (no look-ahead here, so a group of millions of records costs nothing extra).
 //
 // rows[g] (uint4): x = code[31:0]; y = code[42:32] | avg_from_end << 11;
 //                  z = function_index | mean << 16; w = median | var << 16
 constexpr int RED_THREADS = 128;
-constexpr int HS_AHEAD = 4;             // rows of keys/values the run-length pass keeps in flight
-constexpr int WORK_BLOCK = 64;          // list slots a warp reserves at a time (groups / order-statistics work)
+constexpr int HS_THREADS = 256;
+constexpr int HS_ITEMS = 8;
+constexpr int HS_WARPS = HS_THREADS / 32;
+static_assert(HS_THREADS * HS_ITEMS == RED_BATCH, "one tile per chained-scan entry");
+constexpr int WORK_BLOCK = 64;          // list slots a warp reserves at a time (order-statistics work)
 constexpr int GR_CHUNK = 256;           // group descriptors a warp takes per fetch
 constexpr uint32_t ORD_LONG = 32768;    // groups above this are walked by a whole warp (the tail); below, a lane each
+constexpr uint32_t HS_NONE = 0xFFFFFFFFu;
 
 struct WorkCursor { uint32_t base, free; };
 
@@ -174,172 +183,186 @@ SIGK_D void work_flush(WorkCursor &wc, OrderWork *__restrict__ work) {
     for (uint32_t i = threadIdx.x & 31u; i < wc.free; i += 32) work[wc.base + i] = OrderWork{0u, 0u, 0u};
 }
 
-SIGK_D uint4 singleton_row(uint64_t key, const uint4 m) {
+SIGK_D uint4 singleton_row(uint64_t key, const ProtMeta m) {
     const uint64_t code = sigk_key_code(key);
     // one item: avg_from_end = its offset, best = its function, sum = its length mod 65536, median = var = 0
-    return make_uint4((uint32_t)code, (uint32_t)(code >> 32) | (sigk_key_offset(key) << 11), m.z | ((m.x & 0xFFFFu) << 16), 0u);
+    return make_uint4((uint32_t)code, (uint32_t)(code >> 32) | (sigk_key_offset(key) << 11), m.y | ((m.x & 0xFFFFu) << 16), 0u);
 }
 
-__global__ void __launch_bounds__(RED_THREADS)
+__global__ void __launch_bounds__(HS_THREADS)
 head_scan_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, const uint64_t *__restrict__ n_ptr,
-                 const uint4 *__restrict__ meta, uint4 *__restrict__ rows, OrderWork *__restrict__ groups,
+                 const ProtMeta *__restrict__ meta, uint4 *__restrict__ rows, OrderWork *__restrict__ groups,
                  uint32_t *__restrict__ n_groups, OrderWork *__restrict__ long_groups, uint32_t *__restrict__ n_long,
                  uint32_t *__restrict__ distinct_functions, uint64_t *__restrict__ scan_state,
+                 uint64_t *__restrict__ tile_open, uint32_t *__restrict__ tile_first,
                  uint32_t *__restrict__ ticket, uint64_t *__restrict__ n_seg_out) {
-    const unsigned lane = threadIdx.x & 31u;
+    __shared__ uint32_t s_scan[HS_WARPS + 2];
+    __shared__ uint64_t s_last[HS_WARPS];
+    __shared__ uint32_t s_wfirst[HS_WARPS];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_base;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint64_t n = *n_ptr;
     constexpr uint64_t NO_CODE = ~0ull;                  // codes are < 2^43
-    WorkCursor gc{0u, 0u};
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t tile_start = (uint64_t)tile * RED_BATCH;
+    if (tile_start >= n) return;
+    const uint32_t tile_n = (uint32_t)(n - tile_start < (uint64_t)RED_BATCH ? n - tile_start : (uint64_t)RED_BATCH);
+    const bool last_tile = tile_start + tile_n == n;
+    const uint32_t t0 = tid * HS_ITEMS;
 
-    for (;;) {
-        uint32_t t = 0;
-        if (lane == 0) t = atomicAdd(ticket, 1u);
-        t = __shfl_sync(FULL, t, 0);
-        const uint64_t b0 = (uint64_t)t * RED_BATCH;
-        if (b0 >= n) break;
-        const uint64_t b1 = (b0 + RED_BATCH < n) ? b0 + RED_BATCH : n;
-
-        // ---- pass 1: heads of the batch -> publish (four rows of keys in flight)
-        uint32_t hc = 0;
-        const uint64_t before = b0 ? sigk_key_code(__ldg(keys + b0 - 1)) : NO_CODE;
-        {
-            uint64_t carry = before;
-            for (uint64_t q0 = b0; q0 < b1; q0 += 128) {
-                uint64_t c[4];
+    uint64_t before = NO_CODE;                           // code of the record in front of the tile
+    if (tid == 0 && tile_start) before = sigk_key_code(__ldg(keys + tile_start - 1));
+    uint64_t k[HS_ITEMS];
+    uint32_t v[HS_ITEMS];
+    if (tile_n == RED_BATCH) {
+        const ulonglong2 *kp = reinterpret_cast<const ulonglong2 *>(keys + tile_start + t0);
+        const uint4 *vp = reinterpret_cast<const uint4 *>(vals + tile_start + t0);
 #pragma unroll
-                for (int s4 = 0; s4 < 4; ++s4) {
-                    const uint64_t p = q0 + (uint64_t)s4 * 32 + lane;
-                    c[s4] = p < b1 ? sigk_key_code(__ldg(keys + p)) : NO_CODE;
-                }
+        for (int i = 0; i < HS_ITEMS / 2; ++i) { const ulonglong2 x = __ldg(kp + i); k[2 * i] = x.x; k[2 * i + 1] = x.y; }
 #pragma unroll
-                for (int s4 = 0; s4 < 4; ++s4) {
-                    const uint64_t p = q0 + (uint64_t)s4 * 32 + lane;
-                    uint64_t prev = __shfl_up_sync(FULL, c[s4], 1);
-                    if (lane == 0) prev = carry;
-                    hc += __popc(__ballot_sync(FULL, p < b1 && c[s4] != prev));            // kmer != cur, tcc:194
-                    carry = __shfl_sync(FULL, c[s4], 31);
-                }
-            }
+        for (int i = 0; i < HS_ITEMS / 4; ++i) {
+            const uint4 x = __ldg(vp + i);
+            v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
         }
-        uint64_t g = chained_scan_exclusive_warp(scan_state, t, hc);        // index of the batch's first group
-        if (b1 == n && lane == 0) *n_seg_out = g + hc;
-
-        // ---- pass 2: close groups row by row
-        bool open = false;                  // a group whose end has not been seen yet
-        uint64_t open_start = 0, open_g = 0, open_code = 0, open_key = 0;
-        unsigned open_lane = 0;
-        uint4 open_m = make_uint4(0, 0, 0, 0);
-        uint64_t prev_last = before;
-
-        // the open group ends at `end`: one record -> finished here; 2..32 -> groups; more -> long_groups
-        auto close_open = [&](uint64_t end) {
-            const uint64_t cnt = end - open_start;
-            if (cnt == 1) {
-                if (lane == open_lane) {            // its meta was requested when the group was opened
-                    rows[open_g] = singleton_row(open_key, open_m);
-                    atomicAdd(distinct_functions + open_m.z, 1u);           // tcc:286
-                }
-            } else if (cnt <= 32) {
-                work_reserve(gc, 1u, groups, n_groups);
-                if (lane == 0) groups[gc.base] = OrderWork{(uint32_t)open_g, (uint32_t)open_start, (uint32_t)cnt};
-                gc.base += 1; gc.free -= 1;
-            } else if (lane == 0) {
-                long_groups[atomicAdd(n_long, 1u)] = OrderWork{(uint32_t)open_g, (uint32_t)open_start, (uint32_t)cnt};
-            }
-            open = false;
-        };
-
-        // Rows are software-pipelined: the keys and values of the next HS_AHEAD rows are already in
-        // flight, and a row's single-record groups are finished one row later, when their meta gather
-        // has landed — one warp no longer pays three dependent memory latencies per 32 records.
-        uint64_t kq[HS_AHEAD];
-        uint32_t vq[HS_AHEAD];
+    } else {
 #pragma unroll
-        for (int s = 0; s < HS_AHEAD; ++s) {
-            const uint64_t q = b0 + (uint64_t)s * 32 + lane;
-            kq[s] = q < b1 ? __ldg(keys + q) : 0ull;
-            vq[s] = q < b1 ? __ldg(vals + q) : 0u;
-        }
-        bool pend = false;                  // this lane has a single-record group waiting for its meta
-        uint4 pend_m = make_uint4(0, 0, 0, 0);
-        uint64_t pend_key = 0, pend_g = 0;
-        auto finish_pending = [&]() {
-            if (pend) {
-                rows[pend_g] = singleton_row(pend_key, pend_m);
-                atomicAdd(distinct_functions + pend_m.z, 1u);               // tcc:286
-                pend = false;
-            }
-        };
-        for (uint64_t q0 = b0; q0 < b1; q0 += 32 * HS_AHEAD) {
-#pragma unroll
-            for (int s = 0; s < HS_AHEAD; ++s) {
-                const uint64_t p0 = q0 + (uint64_t)s * 32;
-                if (p0 >= b1) break;
-                const uint64_t p = p0 + lane;
-                const bool valid = p < b1;
-                const uint64_t key = kq[s];
-                const uint32_t val = vq[s];
-                {   // refill this slot with the row HS_AHEAD further on
-                    const uint64_t q = p + 32ull * HS_AHEAD;
-                    kq[s] = q < b1 ? __ldg(keys + q) : 0ull;
-                    vq[s] = q < b1 ? __ldg(vals + q) : 0u;
-                }
-                const uint64_t code = sigk_key_code(key);
-                uint64_t prev = __shfl_up_sync(FULL, code, 1);
-                if (lane == 0) prev = prev_last;
-                const bool head = valid && code != prev;
-                const unsigned H = __ballot_sync(FULL, head);
-                prev_last = __shfl_sync(FULL, code, 31);
-                if (!H) { finish_pending(); continue; }
-                const unsigned first = (unsigned)__ffs(H) - 1u, last = 31u - (unsigned)__clz(H);
-                if (open) close_open(p0 + first);
-
-                const unsigned above = H & ~mask_le(lane);
-                const bool known = head && lane != last;                 // the next head is in this row
-                const uint32_t cnt = known ? (uint32_t)(__ffs(above) - 1) - lane : 0u;
-                const uint64_t gi = g + __popc(H & mask_lt(lane));
-                finish_pending();                                   // the previous row's single-record groups
-                if (known && cnt == 1) {
-                    pend = true; pend_m = __ldg(meta + val); pend_key = key; pend_g = gi;
-                }
-                const unsigned M = __ballot_sync(FULL, known && cnt >= 2);
-                if (M) {
-                    const uint32_t k = __popc(M);
-                    work_reserve(gc, k, groups, n_groups);
-                    if (known && cnt >= 2) groups[gc.base + __popc(M & mask_lt(lane))] = OrderWork{(uint32_t)gi, (uint32_t)p, cnt};
-                    gc.base += k; gc.free -= k;
-                }
-                open = true;
-                open_start = p0 + last;
-                open_g = g + __popc(H) - 1;
-                open_code = __shfl_sync(FULL, code, last);
-                open_lane = last;
-                if (lane == last) { open_m = __ldg(meta + val); open_key = key; }   // in case it closes as a single record
-                g += __popc(H);
-            }
-        }
-        finish_pending();
-        if (open) {
-            // the last group of the batch may run into the following batches
-            uint64_t e = b1;
-            for (;;) {
-                const uint64_t q = e + lane;
-                const bool same = q < n && sigk_key_code(__ldg(keys + q)) == open_code;
-                const unsigned sb = __ballot_sync(FULL, same);
-                if (sb != FULL) { e += (uint64_t)(__ffs(~sb) - 1); break; }
-                e += 32;
-            }
-            close_open(e);
+        for (int i = 0; i < HS_ITEMS; ++i) {
+            const bool ok = t0 + i < tile_n;
+            k[i] = ok ? __ldg(keys + tile_start + t0 + i) : ~0ull;
+            v[i] = ok ? __ldg(vals + tile_start + t0 + i) : 0u;
         }
     }
-    work_flush(gc, groups);
+    if (lane == 31) s_last[warp] = sigk_key_code(k[HS_ITEMS - 1]);
+    __syncthreads();
+    uint64_t prev = __shfl_up_sync(FULL, sigk_key_code(k[HS_ITEMS - 1]), 1);
+    if (lane == 0) prev = warp ? s_last[warp - 1] : before;
+    uint32_t hmask = 0;
+#pragma unroll
+    for (int i = 0; i < HS_ITEMS; ++i) {
+        const uint64_t c = sigk_key_code(k[i]);
+        if (t0 + i < tile_n && c != prev) hmask |= 1u << i;             // kmer != cur, tcc:194
+        prev = c;
+    }
+    const uint32_t hc = __popc(hmask);
+    uint32_t total;
+    const uint32_t excl = block_exclusive_scan<HS_THREADS>(hc, s_scan, &total);
+    if (tid == 0) chained_scan_publish(scan_state, tile, total);
+
+    // next head after this thread's records (local position), HS_NONE if the tile has none
+    uint32_t fh = hmask ? t0 + (uint32_t)__ffs(hmask) - 1u : HS_NONE;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_down_sync(FULL, fh, o);
+        if (lane + o < 32) fh = min(fh, y);
+    }
+    uint32_t nh = __shfl_down_sync(FULL, fh, 1);
+    if (lane == 31) nh = HS_NONE;
+    if (lane == 0) s_wfirst[warp] = fh;
+    __syncthreads();
+#pragma unroll
+    for (int w = 1; w < HS_WARPS; ++w) nh = min(nh, (int)warp + w < HS_WARPS ? s_wfirst[(warp + w) & (HS_WARPS - 1)] : HS_NONE);
+    if (nh == HS_NONE && last_tile) nh = tile_n;         // the last group of the job ends with the records
+
+    // length of every group that starts here (0 = runs past the tile), meta of the single-record ones
+    uint32_t cnt[HS_ITEMS];
+    ProtMeta m[HS_ITEMS];
+    uint32_t mc = 0;
+#pragma unroll
+    for (int i = 0; i < HS_ITEMS; ++i) {
+        cnt[i] = 0;
+        m[i] = make_uint2(0, 0);
+        if ((hmask >> i) & 1u) {
+            const uint32_t above = hmask >> (i + 1);
+            const uint32_t next = above ? t0 + (uint32_t)i + (uint32_t)__ffs(above) : nh;
+            cnt[i] = next == HS_NONE ? 0u : next - (t0 + (uint32_t)i);
+            if (cnt[i] == 1) m[i] = __ldg(meta + v[i]);
+            mc += (cnt[i] >= 2 && cnt[i] <= 32) ? 1u : 0u;
+        }
+    }
+    // list slots for the groups of 2..32 records: one reservation per warp
+    uint32_t mx = mc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(FULL, mx, o);
+        if (lane >= (unsigned)o) mx += y;
+    }
+    uint32_t gslot = 0;
+    const uint32_t wtotal = __shfl_sync(FULL, mx, 31);
+    if (lane == 31 && wtotal) gslot = atomicAdd(n_groups, wtotal);
+    gslot = __shfl_sync(FULL, gslot, 31) + mx - mc;
+
+    if (warp == 0) {                                     // 32 predecessors per round trip
+        const uint64_t base = chained_scan_resolve_warp(scan_state, tile, total);
+        if (lane == 0) {
+            s_base = base;
+            if (last_tile) *n_seg_out = base + total;
+            uint32_t first = HS_NONE;
+#pragma unroll
+            for (int w = 0; w < HS_WARPS; ++w) first = min(first, s_wfirst[w]);
+            if (first != HS_NONE) tile_first[tile] = (uint32_t)(tile_start + first) + 1u;
+        }
+    }
+    __syncthreads();
+    uint64_t g = s_base + excl;
+#pragma unroll
+    for (int i = 0; i < HS_ITEMS; ++i) {
+        if ((hmask >> i) & 1u) {
+            const uint32_t p = (uint32_t)(tile_start + t0 + i);
+            if (cnt[i] == 1) {
+                rows[g] = singleton_row(k[i], m[i]);
+                atomicAdd(distinct_functions + m[i].y, 1u);                 // tcc:286
+            } else if (cnt[i] == 0) {
+                tile_open[tile] = ((uint64_t)(p + 1u) << 32) | (uint64_t)(uint32_t)g;
+            } else if (cnt[i] <= 32) {
+                groups[gslot++] = OrderWork{(uint32_t)g, p, cnt[i]};
+            } else {
+                long_groups[atomicAdd(n_long, 1u)] = OrderWork{(uint32_t)g, p, cnt[i]};
+            }
+            ++g;
+        }
+    }
+}
+
+// Groups that ran past the end of their tile: the next head is the first head of the next tile that
+// has one (tile_first, 0 = none), or the end of the records.
+__global__ void resolve_open_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                    const uint64_t *__restrict__ n_ptr, const ProtMeta *__restrict__ meta,
+                                    const uint64_t *__restrict__ tile_open, const uint32_t *__restrict__ tile_first,
+                                    uint4 *__restrict__ rows, OrderWork *__restrict__ groups, uint32_t *__restrict__ n_groups,
+                                    OrderWork *__restrict__ long_groups, uint32_t *__restrict__ n_long,
+                                    uint32_t *__restrict__ distinct_functions) {
+    const uint64_t n = *n_ptr;
+    const uint64_t n_tiles = (n + RED_BATCH - 1) / RED_BATCH;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const uint64_t o = tile_open[t];
+    if (!o) return;
+    const uint32_t start = (uint32_t)(o >> 32) - 1u, g = (uint32_t)o;
+    uint64_t end = n;
+    for (uint64_t u = t + 1; u < n_tiles; ++u) {
+        const uint32_t f = __ldg(tile_first + u);
+        if (f) { end = f - 1u; break; }
+    }
+    const uint32_t cnt = (uint32_t)(end - start);
+    if (cnt == 1) {
+        const ProtMeta m = __ldg(meta + __ldg(vals + start));
+        rows[g] = singleton_row(__ldg(keys + start), m);
+        atomicAdd(distinct_functions + m.y, 1u);                            // tcc:286
+    } else if (cnt <= 32) {
+        groups[atomicAdd(n_groups, 1u)] = OrderWork{g, start, cnt};
+    } else {
+        long_groups[atomicAdd(n_long, 1u)] = OrderWork{g, start, cnt};
+    }
 }
 
 // ---- stage 3b: groups of 2..32 records, packed 32 records to a warp ---------------------------
 // A warp takes 32 descriptors, lays their records side by side (lane = record, whole groups only)
 // and reduces all groups of the window at once with ballots and segmented shuffles.
 __global__ void __launch_bounds__(RED_THREADS)
-group_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, const uint4 *__restrict__ meta,
+group_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, const ProtMeta *__restrict__ meta,
                     const OrderWork *__restrict__ groups, const uint32_t *__restrict__ n_groups, uint32_t *__restrict__ next_group,
                     const OrderWork *__restrict__ long_groups, const uint32_t *__restrict__ n_long, uint32_t *__restrict__ next_long,
                     uint4 *__restrict__ rows, OrderWork *__restrict__ work, uint32_t *__restrict__ n_work,
@@ -414,8 +437,8 @@ group_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
             const uint64_t p = (uint64_t)gstart + (lane - s_lane);
             const uint64_t key = act ? __ldg(keys + p) : 0ull;
             const uint32_t ord = act ? __ldg(vals + p) : 0u;
-            const uint4 m = act ? __ldg(meta + ord) : make_uint4(0, 0, 0, 0);      // len, seq_id, func
-            const uint32_t f = m.z;
+            const ProtMeta m = act ? __ldg(meta + ord) : make_uint2(0, 0);          // len, func
+            const uint32_t f = m.y;
             const uint32_t off = sigk_key_offset(key);
 
             // function vote (func_count + arg-max, tcc:203, :228-248).  A group with two
@@ -562,10 +585,12 @@ squeeze_rows_kernel(const uint4 *__restrict__ rows, const uint64_t *__restrict__
 #pragma unroll
     for (int i = 0; i < SQ_ITEMS; ++i)
         ascii[i] = code_to_ascii_pairs((uint64_t)row[i].x | ((uint64_t)(row[i].y & 0x7FFu) << 32));
-    if (tid == 0) {
-        const uint64_t base = chained_scan_resolve(scan_state, tile, total);
-        s_base = base;
-        if (tile_start + SQ_TILE >= n_seg) *n_kept_out = base + total;
+    if (warp == 0) {                                     // 32 predecessors per round trip
+        const uint64_t base = chained_scan_resolve_warp(scan_state, tile, total);
+        if (lane == 0) {
+            s_base = base;
+            if (tile_start + SQ_TILE >= n_seg) *n_kept_out = base + total;
+        }
     }
     __syncthreads();
     const uint64_t base = s_base;
@@ -592,7 +617,7 @@ constexpr int ORD_THREADS = 128;
 constexpr int ORD_BLOCK = 64;       // work entries a warp takes per fetch
 
 __global__ void __launch_bounds__(ORD_THREADS)
-order_stats_kernel(const uint32_t *__restrict__ vals, const uint4 *__restrict__ meta, const OrderWork *__restrict__ work,
+order_stats_kernel(const uint32_t *__restrict__ vals, const ProtMeta *__restrict__ meta, const OrderWork *__restrict__ work,
                    const uint32_t *__restrict__ n_work, uint32_t *__restrict__ next, uint4 *__restrict__ rows) {
     const uint32_t total = *n_work;
     const unsigned lane = threadIdx.x & 31u;
@@ -605,7 +630,7 @@ order_stats_kernel(const uint32_t *__restrict__ vals, const uint4 *__restrict__ 
     bool active = false;
     uint32_t row = 0, cand = 0, left = 0;
     uint64_t start = 0;
-    uint4 m_next = make_uint4(0, 0, 0, 0);      // meta of the sample to visit next, already in flight
+    ProtMeta m_next = make_uint2(0, 0);         // meta of the sample to visit next, already in flight
     LengthAcc acc;
     for (;;) {
         const unsigned idle = __ballot_sync(FULL, !active);
@@ -637,9 +662,9 @@ order_stats_kernel(const uint32_t *__restrict__ vals, const uint4 *__restrict__ 
         if (active) {
             // newest first: the multimap iterates a key's items in reverse insertion order
             --left;
-            const uint4 m = m_next;
+            const ProtMeta m = m_next;
             if (left) m_next = __ldg(meta + __ldg(vals + start + left - 1));
-            if (m.z == cand) acc.push(m.x);                            // acc(item.protein_length), tcc:271
+            if (m.y == cand) acc.push(m.x);                            // acc(item.protein_length), tcc:271
             if (left == 0) {
                 rows[row].w = u16_from_double(acc.q2) | (u16_from_double(acc.var) << 16);   // tcc:278-279
                 active = false;
@@ -653,7 +678,7 @@ order_stats_kernel(const uint32_t *__restrict__ vals, const uint4 *__restrict__ 
 // batch prefetched) and every lane runs the same accumulator on shuffled samples, so a group no
 // longer pays two dependent memory latencies per record (524 ms -> see profiles/ on the Zipf set).
 __global__ void __launch_bounds__(128)
-order_stats_long_kernel(const uint32_t *__restrict__ vals, const uint4 *__restrict__ meta, const OrderWork *__restrict__ work,
+order_stats_long_kernel(const uint32_t *__restrict__ vals, const ProtMeta *__restrict__ meta, const OrderWork *__restrict__ work,
                         const uint32_t *__restrict__ n_work, uint32_t *__restrict__ next, uint4 *__restrict__ rows) {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t total = *n_work;
@@ -667,15 +692,15 @@ order_stats_long_kernel(const uint32_t *__restrict__ vals, const uint4 *__restri
         LengthAcc acc;          // every lane carries the same state
         // newest first: batch b covers records count-1-32b-lane
         int64_t j = (int64_t)w.count - 1 - (int64_t)lane;
-        uint4 m = j >= 0 ? __ldg(meta + __ldg(vals + (uint64_t)w.start + j)) : make_uint4(0, 0, 0xFFFFFFFFu, 0);
+        ProtMeta m = j >= 0 ? __ldg(meta + __ldg(vals + (uint64_t)w.start + j)) : make_uint2(0, 0xFFFFFFFFu);
         for (int64_t left = w.count; left > 0; left -= 32) {
             const int64_t jn = j - 32;
-            const uint4 mn = (left > 32 && jn >= 0) ? __ldg(meta + __ldg(vals + (uint64_t)w.start + jn)) : make_uint4(0, 0, 0xFFFFFFFFu, 0);
+            const ProtMeta mn = (left > 32 && jn >= 0) ? __ldg(meta + __ldg(vals + (uint64_t)w.start + jn)) : make_uint2(0, 0xFFFFFFFFu);
             // Per batch of 32 samples the lanes work in parallel on everything that does not depend on
             // the running state: which samples count (func == best), their running count n_i and wrapped
             // sum S_i (prefix scans), and the variance term tmp_i^2/(n_i-1) with its two divisions.  Only
             // var = var (n-1)/n + term_i and the P^2 marker update remain sequential.
-            const bool match = m.z == cand;
+            const bool match = m.y == cand;
             const unsigned mb = __ballot_sync(FULL, match);
             if (mb) {
                 uint32_t sx = match ? m.x : 0u;
@@ -727,21 +752,20 @@ __global__ void popcount_kernel(const uint32_t *__restrict__ bitmap, uint64_t n_
 }
 
 __global__ void protein_meta_kernel(const uint64_t *__restrict__ starts, const uint16_t *__restrict__ func,
-                                    const uint32_t *__restrict__ seq_id, uint32_t n_prot, uint4 *__restrict__ meta,
+                                    const uint32_t *__restrict__ seq_id, uint32_t n_prot, ProtMeta *__restrict__ meta,
                                     uint32_t *__restrict__ seqs_with_func) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_prot) return;
     // protein_length = static_cast<unsigned int>(seq.length()), tcc:178
-    meta[i] = make_uint4((uint32_t)(starts[i + 1] - starts[i]), seq_id[i], func[i], 0u);
+    meta[i] = make_uint2((uint32_t)(starts[i + 1] - starts[i]), func[i]);
     if (seqs_with_func) atomicAdd(seqs_with_func + func[i], 1u);          // seqs_with_func[function_index]++, tcc:160
 }
 
 }  // namespace
 
 static int reduce_grid(int sm_count) { return sm_count * 12; }
-size_t reduce_group_entries(uint64_t capacity, int sm_count) {
-    // a listed group has >= 2 records; every warp of a persistent grid can strand one reserved block
-    return (size_t)(capacity / 2 + 2) + (size_t)reduce_grid(sm_count) * (RED_THREADS / 32) * WORK_BLOCK;
+size_t reduce_group_entries(uint64_t capacity, int) {
+    return (size_t)(capacity / 2 + 2);      // a listed group has >= 2 records
 }
 size_t reduce_long_group_entries(uint64_t capacity) { return (size_t)(capacity / 33 + 2); }
 size_t reduce_work_entries(uint64_t capacity, int sm_count) {
@@ -756,23 +780,29 @@ cudaError_t reduce_configure() {
 }
 
 cudaError_t launch_protein_meta(const uint64_t *starts, const uint16_t *func, const uint32_t *seq_id, uint32_t n_prot,
-                                uint4 *meta, uint32_t *seqs_with_func, cudaStream_t stream) {
+                                ProtMeta *meta, uint32_t *seqs_with_func, cudaStream_t stream) {
     if (n_prot == 0) return cudaSuccess;
     protein_meta_kernel<<<(n_prot + 255) / 256, 256, 0, stream>>>(starts, func, seq_id, n_prot, meta, seqs_with_func);
     return cudaGetLastError();
 }
 
 cudaError_t launch_segment_reduce(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
-                                  const uint4 *meta, uint4 *rows, const ReduceLists &l, uint32_t *prot_rejected,
+                                  const ProtMeta *meta, uint4 *rows, const ReduceLists &l, uint32_t *prot_rejected,
                                   uint32_t *distinct_functions, uint64_t *scan_state, uint32_t *ticket, uint64_t *n_seg_out,
                                   int order_stats, int sm_count, cudaStream_t stream) {
     if (capacity == 0) return cudaSuccess;
-    uint64_t grid = reduce_grid(sm_count);
-    const uint64_t want = (reduce_batches(capacity) + RED_THREADS / 32 - 1) / (RED_THREADS / 32);
-    head_scan_kernel<<<(unsigned)std::min(grid, want), RED_THREADS, 0, stream>>>(
+    const uint64_t grid = reduce_grid(sm_count);
+    const uint64_t tiles = reduce_batches(capacity);
+    uint64_t *tile_open = scan_state + reduce_tile_open_offset(capacity);
+    uint32_t *tile_first = reinterpret_cast<uint32_t *>(tile_open + tiles);
+    head_scan_kernel<<<(unsigned)tiles, HS_THREADS, 0, stream>>>(
         keys, vals, n_ptr, meta, rows, l.groups, l.n_groups, l.long_groups, l.n_long, distinct_functions, scan_state,
-        ticket, n_seg_out);
+        tile_open, tile_first, ticket, n_seg_out);
     cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    resolve_open_kernel<<<(unsigned)((tiles + 255) / 256), 256, 0, stream>>>(
+        keys, vals, n_ptr, meta, tile_open, tile_first, rows, l.groups, l.n_groups, l.long_groups, l.n_long, distinct_functions);
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     group_reduce_kernel<<<(unsigned)grid, RED_THREADS, 0, stream>>>(keys, vals, meta, l.groups, l.n_groups, l.next_group, l.long_groups,
                                                                     l.n_long, l.next_long, rows, l.work, l.n_work, l.work_long,
@@ -780,7 +810,7 @@ cudaError_t launch_segment_reduce(const uint64_t *keys, const uint32_t *vals, co
     return cudaGetLastError();
 }
 
-cudaError_t launch_order_stats(const uint32_t *vals, const uint4 *meta, const OrderWork *work, const uint32_t *n_work,
+cudaError_t launch_order_stats(const uint32_t *vals, const ProtMeta *meta, const OrderWork *work, const uint32_t *n_work,
                                uint32_t *next_work, const OrderWork *work_long, const uint32_t *n_work_long, uint32_t *next_long,
                                uint64_t capacity, uint4 *rows, int sm_count, cudaStream_t stream) {
     if (capacity == 0) return cudaSuccess;

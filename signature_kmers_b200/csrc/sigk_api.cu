@@ -173,7 +173,7 @@ int do_build_device(sigk_handle *h) {
                    h->d_work.p, &sc->n_work, h->d_work_long.p, &sc->n_work_long};
     CU(h, launch_segment_reduce(h->d_keys[cur].p, h->d_vals[cur].p, &sc->n_records, cap, h->d_meta.p, h->d_rows.p, rl,
                                 h->d_prot_rejected.p, h->d_distinct.p, h->d_scan_state.p, sc->ticket + TK_REDUCE, &sc->n_segments,
-                                order_stats, h->sm_count, st)); launches += 2;
+                                order_stats, h->sm_count, st)); launches += 3;
     if (h->comm) { if (int rc = comm_reduce_rejected(h)) return rc; }
     CU(h, launch_signature_flags(h->d_prot_windows.p, h->d_prot_rejected.p + h->ordinal_base, h->d_seqid.p, (uint32_t)np, h->d_bitmap.p, st)); ++launches;
     CU(h, launch_popcount(h->d_bitmap.p, ((uint64_t)h->max_seq_id >> 5) + 1, &sc->n_seqs_sig, st)); ++launches;

@@ -21,15 +21,21 @@ def build_distributed(p_all, rank, world, local_rank):
     import torch.distributed as dist
 
     lo, hi = multigpu.rank_slice(p_all.n_proteins, rank, world)
+    say = lambda what: print(f"[rank {rank}] {what}", file=sys.stderr, flush=True)
+    say(f"proteins {lo}..{hi}")
     b = GpuSignatureBuilder(device=local_rank, rank=rank, world=world)
     multigpu.join_communicator(b, rank, world)
+    say("joined")
     b.set_proteins(p_all.slice(lo, hi))
     t = b.build()
+    say("built")
     again = b.build()                  # a second build on the same communicator gives the same slice
     assert_tables_equal(t, again, what=f"rank {rank} rebuild")
     parts = [None] * world
     dist.all_gather_object(parts, t)
+    say("gathered")
     b.close()
+    say("closed")
     return multigpu.concat_tables(parts), [x.n_kept for x in parts]
 
 
@@ -45,8 +51,12 @@ def main():
     seqs, funcs = random_proteins(72, n_families=5, members=(100, 200), length=(100, 400), sub_rate=0.01, alphabet=b"ACDEF")
     cases.append(("heavy duplication", pack(seqs, funcs)))
     cases.append(("tiny", pack(["ACDEFGHIKLMNPQ", "ACDEFGHIKLMNPQ", "ACDEFGHIKLMNPQ", "WWWWWWWWWW"], [0, 0, 0, 1])))
+    # fewer proteins than ranks: some ranks encode nothing, some k-mer ranges may be empty
+    cases.append(("one protein", pack(["ACDEFGHIKLMNPQRSTVWY"], [3])))
+    cases.append(("no valid window", pack(["ACDXFGHIKL", "ACD"], [1, 2])))
     cases.append(("synthetic 40K proteins", Synth(n_proteins=40_000, n_functions=400, n_genomes=8, seed=9).packed()))
     for name, p_all in cases:
+        print(f"[rank {rank}] case: {name}", file=sys.stderr, flush=True)
         got, per_rank = build_distributed(p_all, rank, world, local_rank)
         if rank == 0:
             from oracle import oracle_c
@@ -57,7 +67,7 @@ def main():
             single.set_proteins(p_all)
             assert_tables_equal(got, single.build(), tier_b=True, what=name + " vs one GPU")
             single.close()
-            print(f"multigpu_check ok: {name}: {got.n_occurrences} occurrences, kept per rank {per_rank}", flush=True)
+            print(f"multigpu_check ok ({world} ranks): {name}: {got.n_occurrences} occurrences, kept per rank {per_rank}", flush=True)
         dist.barrier()
     if rank == 0:
         print("MULTIGPU_CHECK_PASSED", flush=True)
