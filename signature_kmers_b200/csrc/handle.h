@@ -70,6 +70,7 @@ struct sigk_handle {
     uint64_t total_res = 0;
     uint32_t max_seq_id = 0;            // over the whole job once a communicator is joined
     uint32_t local_max_seq_id = 0;
+    uint32_t local_max_function = 0;    // largest function_index among this rank's proteins
 
     sigk::DevBuf<uint8_t> d_res;
     sigk::DevBuf<uint64_t> d_starts;

@@ -103,12 +103,16 @@ struct OrderWork { uint32_t row, start, count; };   // kept group whose median/v
 constexpr int RED_BATCH = 2048;     // sorted records per run-length tile
 inline uint64_t reduce_batches(uint64_t capacity) { return (capacity + RED_BATCH - 1) / RED_BATCH; }
 inline uint64_t squeeze_tiles(uint64_t capacity) { return (capacity + 2047) / 2048; }
-// scan_state words: chained scan of the run-length tiles, chained scan of the squeeze tiles, then per
-// run-length tile one u64 (group left open at the tile end) and one u32 (first head of the tile)
-inline uint64_t reduce_tile_open_offset(uint64_t capacity) { return reduce_batches(capacity) + squeeze_tiles(capacity) + 2; }
-inline uint64_t reduce_scan_entries(uint64_t capacity) {
-    return reduce_tile_open_offset(capacity) + reduce_batches(capacity) + reduce_batches(capacity) / 2 + 2;
-}
+// Scratch of the reduce stage, carved out of one zeroed u64 buffer of reduce_scan_entries() words
+// (reduce_scratch() in reduce.cu): per run-length tile its {heads, listed groups} pair, the scanned bases,
+// the group left open at the tile end and the tile's first head; per squeeze tile the tombstones in it
+// and before it.
+struct ReduceScratch {
+    uint64_t *tile_counts, *tile_base;
+    uint32_t *tile_open, *tile_first;
+    uint32_t *rej_tile, *rej_before;
+};
+inline uint64_t reduce_scan_entries(uint64_t capacity) { return 3 * (reduce_batches(capacity) + 1) + squeeze_tiles(capacity) + 2; }
 size_t reduce_group_entries(uint64_t capacity, int sm_count);  // OrderWork entries: groups of 2..32 records
 size_t reduce_long_group_entries(uint64_t capacity);           // OrderWork entries: groups of more than 32 records
 size_t reduce_work_entries(uint64_t capacity, int sm_count);   // OrderWork entries: groups whose median/var need the ordered walk
@@ -129,21 +133,25 @@ struct ReduceLists {
     OrderWork *work;        uint32_t *n_work;
     OrderWork *work_long;   uint32_t *n_work_long;
 };
-// Run-length + per-group reduce + keep/reject over the sorted records (head_scan_kernel, then
-// group_reduce_kernel): one packed row per group in k-mer order (rejected groups
+// Run-length + per-group reduce + keep/reject over the sorted records (head_tile_kernel count and emit
+// passes, then group_reduce_kernel): one packed row per group in k-mer order (rejected groups
 // leave a tombstone), plus the lists of groups whose median/var need the ordered walk.
-// scan_state: reduce_scan_entries() zeroed words (the squeeze uses its own part of them).
+// scratch_words: reduce_scan_entries() zeroed words, shared with launch_squeeze_rows of the same build.
 cudaError_t launch_segment_reduce(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
                                   const ProtMeta *meta, uint4 *rows, const ReduceLists &l, uint32_t *prot_rejected,
-                                  uint32_t *distinct_functions, uint64_t *scan_state, uint32_t *ticket, uint64_t *n_seg_out,
-                                  int order_stats, int sm_count, cudaStream_t stream);
+                                  uint64_t *scratch_words, uint64_t *n_seg_out, int order_stats, int sm_count, cudaStream_t stream);
+// distinct_functions[f] += kept rows whose function_index is f (src/signature_build.tcc:286), from the finished
+// table's column; max_function = largest function index any protein of the job carries.
+cudaError_t launch_function_histogram(const uint16_t *function_index, const uint64_t *n_kept_ptr, uint64_t capacity,
+                                      uint32_t max_function, uint32_t *distinct_functions, int sm_count, cudaStream_t stream);
 // median / var of the groups listed in `work`, patched into their rows.
 cudaError_t launch_order_stats(const uint32_t *vals, const ProtMeta *meta, const OrderWork *work, const uint32_t *n_work,
                                uint32_t *next_work, const OrderWork *work_long, const uint32_t *n_work_long, uint32_t *next_long,
                                uint64_t capacity, uint4 *rows, int sm_count, cudaStream_t stream);
-// Compaction: kept rows -> table columns (tombstones dropped, order kept).  scan_state: squeeze_tiles()+1 zeroed words.
+// Compaction: kept rows -> table columns (tombstones dropped, order kept).  scratch_words: the buffer the
+// segment reduce of this build used (it holds the per-tile tombstone counts).
 cudaError_t launch_squeeze_rows(const uint4 *rows, const uint64_t *n_seg_ptr, uint64_t capacity, KeptColumns out,
-                                uint64_t *scan_state, uint32_t *ticket, uint64_t *n_kept_out, cudaStream_t stream);
+                                uint64_t *scratch_words, uint64_t *n_kept_out, cudaStream_t stream);
 // bitmap bit seq_id[i] is set iff protein i has more occurrences (prot_windows, from encode) than occurrences in
 // rejected groups (prot_rejected, from the reduce): kmer_stats_.seqs_with_a_signature, src/signature_build.tcc:274
 cudaError_t launch_signature_flags(const uint32_t *prot_windows, const uint32_t *prot_rejected, const uint32_t *seq_id,

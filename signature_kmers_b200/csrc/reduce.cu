@@ -141,17 +141,23 @@ SIGK_D SegResult reduce_long_segment(const uint64_t *__restrict__ keys, const ui
 }
 
 // ---- stage 3a: run-length ---------------------------------------------------------------------
-// One tile of RED_BATCH sorted records per block (tiles by ticket), HS_ITEMS consecutive records per
-// thread: head flags by neighbour compare, block scan of the head counts, chained scan over the tiles
-// (published before anything else happens).  Every group, kept or not, owns the row slot of its index,
-// so nothing downstream waits for a keep decision; rejected groups leave a tombstone (function_index
-// 0xFFFF) that squeeze_rows_kernel removes.
-// A head's group ends at the next head; a suffix-min over the block gives it to every thread.
+// One tile of RED_BATCH sorted records per block, HS_ITEMS consecutive records per thread: head
+// flags by neighbour compare; a head's group ends at the next head, which a suffix-min over the block
+// gives to every thread.  Every group, kept or not, owns the row slot of its index, so nothing
+// downstream waits for a keep decision; rejected groups leave a tombstone (function_index 0xFFFF)
+// that squeeze_rows_kernel removes.
+//
+// The kernel runs twice.  The COUNT pass reads the keys only and leaves per tile {heads, groups of
+// 2..32 records}; tile_scan_kernel turns the counts into row and list bases; the EMIT pass recomputes
+// the flags and writes.  Reading the keys a second time (8 of the 153 algorithmic bytes per record)
+// buys tiles that are independent of each other: the single-pass version with a chained scan over
+// the tiles spent most of its time waiting for predecessors (profiles/r1_ncu_full_reduce_v9.txt).
 // Single-record groups (92 % of the groups of the 2 M-protein set, always kept: 1 >= 0.8) are finished
-// here; groups of 2..32 records go to `groups`, longer ones to `long_groups`.  The last group of a tile
-// may run into the following tiles: the tile leaves {row, start} in tile_open, every tile leaves the
-// position of its first head in tile_first, and resolve_open_kernel closes those groups afterwards
-// (no look-ahead here, so a group of millions of records costs nothing extra).
+// in the EMIT pass; groups of 2..32 records go to `groups` (in position order), longer ones to
+// `long_groups`.  The last group of a tile may run into the following tiles: the COUNT pass leaves
+// its position in tile_open and the position of every tile's first head in tile_first, and
+// resolve_open_kernel closes those groups afterwards (no look-ahead, so a group of millions of
+// records costs nothing extra).
 //
 // rows[g] (uint4): x = code[31:0]; y = code[42:32] | avg_from_end << 11;
 //                  z = function_index | mean << 16; w = median | var << 16
@@ -159,11 +165,18 @@ constexpr int RED_THREADS = 128;
 constexpr int HS_THREADS = 256;
 constexpr int HS_ITEMS = 8;
 constexpr int HS_WARPS = HS_THREADS / 32;
-static_assert(HS_THREADS * HS_ITEMS == RED_BATCH, "one tile per chained-scan entry");
+static_assert(HS_THREADS * HS_ITEMS == RED_BATCH, "one tile per scan entry");
 constexpr int WORK_BLOCK = 64;          // list slots a warp reserves at a time (order-statistics work)
 constexpr int GR_CHUNK = 256;           // group descriptors a warp takes per fetch
 constexpr uint32_t ORD_LONG = 32768;    // groups above this are walked by a whole warp (the tail); below, a lane each
 constexpr uint32_t HS_NONE = 0xFFFFFFFFu;
+constexpr int SCAN_THREADS = 1024;      // the single block that scans the per-tile counters
+constexpr int SQ_THREADS = 256;
+constexpr int SQ_ITEMS = 8;
+constexpr int SQ_TILE = SQ_THREADS * SQ_ITEMS;
+constexpr int SQ_TILE_SHIFT = 11;
+constexpr int SQ_WARPS = SQ_THREADS / 32;
+static_assert(SQ_TILE == 1 << SQ_TILE_SHIFT, "squeeze tile");
 
 struct WorkCursor { uint32_t base, free; };
 
@@ -189,29 +202,27 @@ SIGK_D uint4 singleton_row(uint64_t key, const ProtMeta m) {
     return make_uint4((uint32_t)code, (uint32_t)(code >> 32) | (sigk_key_offset(key) << 11), m.y | ((m.x & 0xFFFFu) << 16), 0u);
 }
 
-__global__ void __launch_bounds__(HS_THREADS)
-head_scan_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, const uint64_t *__restrict__ n_ptr,
+#ifndef SIGK_HS_MIN_BLOCKS
+#define SIGK_HS_MIN_BLOCKS 4
+#endif
+template <bool EMIT>
+__global__ void __launch_bounds__(HS_THREADS, SIGK_HS_MIN_BLOCKS)
+head_tile_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, const uint64_t *__restrict__ n_ptr,
                  const ProtMeta *__restrict__ meta, uint4 *__restrict__ rows, OrderWork *__restrict__ groups,
-                 uint32_t *__restrict__ n_groups, OrderWork *__restrict__ long_groups, uint32_t *__restrict__ n_long,
-                 uint32_t *__restrict__ distinct_functions, uint64_t *__restrict__ scan_state,
-                 uint64_t *__restrict__ tile_open, uint32_t *__restrict__ tile_first,
-                 uint32_t *__restrict__ ticket, uint64_t *__restrict__ n_seg_out) {
+                 OrderWork *__restrict__ long_groups, uint32_t *__restrict__ n_long, ReduceScratch sx) {
     __shared__ uint32_t s_scan[HS_WARPS + 2];
     __shared__ uint64_t s_last[HS_WARPS];
     __shared__ uint32_t s_wfirst[HS_WARPS];
-    __shared__ uint32_t s_tile;
-    __shared__ uint64_t s_base;
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint64_t n = *n_ptr;
     constexpr uint64_t NO_CODE = ~0ull;                  // codes are < 2^43
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
+    const uint32_t tile = blockIdx.x;
     const uint64_t tile_start = (uint64_t)tile * RED_BATCH;
     if (tile_start >= n) return;
     const uint32_t tile_n = (uint32_t)(n - tile_start < (uint64_t)RED_BATCH ? n - tile_start : (uint64_t)RED_BATCH);
     const bool last_tile = tile_start + tile_n == n;
     const uint32_t t0 = tid * HS_ITEMS;
+    const uint64_t base = EMIT ? __ldg(sx.tile_base + tile) : 0ull;      // rows | list slots << 32
 
     uint64_t before = NO_CODE;                           // code of the record in front of the tile
     if (tid == 0 && tile_start) before = sigk_key_code(__ldg(keys + tile_start - 1));
@@ -219,20 +230,22 @@ head_scan_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__
     uint32_t v[HS_ITEMS];
     if (tile_n == RED_BATCH) {
         const ulonglong2 *kp = reinterpret_cast<const ulonglong2 *>(keys + tile_start + t0);
-        const uint4 *vp = reinterpret_cast<const uint4 *>(vals + tile_start + t0);
 #pragma unroll
         for (int i = 0; i < HS_ITEMS / 2; ++i) { const ulonglong2 x = __ldg(kp + i); k[2 * i] = x.x; k[2 * i + 1] = x.y; }
+        if (EMIT) {
+            const uint4 *vp = reinterpret_cast<const uint4 *>(vals + tile_start + t0);
 #pragma unroll
-        for (int i = 0; i < HS_ITEMS / 4; ++i) {
-            const uint4 x = __ldg(vp + i);
-            v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+            for (int i = 0; i < HS_ITEMS / 4; ++i) {
+                const uint4 x = __ldg(vp + i);
+                v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+            }
         }
     } else {
 #pragma unroll
         for (int i = 0; i < HS_ITEMS; ++i) {
             const bool ok = t0 + i < tile_n;
             k[i] = ok ? __ldg(keys + tile_start + t0 + i) : ~0ull;
-            v[i] = ok ? __ldg(vals + tile_start + t0 + i) : 0u;
+            if (EMIT) v[i] = ok ? __ldg(vals + tile_start + t0 + i) : 0u;
         }
     }
     if (lane == 31) s_last[warp] = sigk_key_code(k[HS_ITEMS - 1]);
@@ -247,9 +260,13 @@ head_scan_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__
         prev = c;
     }
     const uint32_t hc = __popc(hmask);
-    uint32_t total;
-    const uint32_t excl = block_exclusive_scan<HS_THREADS>(hc, s_scan, &total);
-    if (tid == 0) chained_scan_publish(scan_state, tile, total);
+    // meta of every head's protein, requested now so that the gathers fly during the scan below (only the
+    // single-record groups, 92 % of them, use it)
+    ProtMeta m[HS_ITEMS];
+    if (EMIT) {
+#pragma unroll
+        for (int i = 0; i < HS_ITEMS; ++i) m[i] = ((hmask >> i) & 1u) ? __ldg(meta + v[i]) : make_uint2(0, 0);
+    }
 
     // next head after this thread's records (local position), HS_NONE if the tile has none
     uint32_t fh = hmask ? t0 + (uint32_t)__ffs(hmask) - 1u : HS_NONE;
@@ -266,56 +283,44 @@ head_scan_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__
     for (int w = 1; w < HS_WARPS; ++w) nh = min(nh, (int)warp + w < HS_WARPS ? s_wfirst[(warp + w) & (HS_WARPS - 1)] : HS_NONE);
     if (nh == HS_NONE && last_tile) nh = tile_n;         // the last group of the job ends with the records
 
-    // length of every group that starts here (0 = runs past the tile), meta of the single-record ones
+    // length of every group that starts here (0 = runs past the tile)
     uint32_t cnt[HS_ITEMS];
-    ProtMeta m[HS_ITEMS];
     uint32_t mc = 0;
 #pragma unroll
     for (int i = 0; i < HS_ITEMS; ++i) {
         cnt[i] = 0;
-        m[i] = make_uint2(0, 0);
         if ((hmask >> i) & 1u) {
             const uint32_t above = hmask >> (i + 1);
             const uint32_t next = above ? t0 + (uint32_t)i + (uint32_t)__ffs(above) : nh;
             cnt[i] = next == HS_NONE ? 0u : next - (t0 + (uint32_t)i);
-            if (cnt[i] == 1) m[i] = __ldg(meta + v[i]);
             mc += (cnt[i] >= 2 && cnt[i] <= 32) ? 1u : 0u;
+            if (!EMIT && cnt[i] == 0) sx.tile_open[tile] = (uint32_t)(tile_start + t0 + i) + 1u;
         }
     }
-    // list slots for the groups of 2..32 records: one reservation per warp
-    uint32_t mx = mc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(FULL, mx, o);
-        if (lane >= (unsigned)o) mx += y;
-    }
-    uint32_t gslot = 0;
-    const uint32_t wtotal = __shfl_sync(FULL, mx, 31);
-    if (lane == 31 && wtotal) gslot = atomicAdd(n_groups, wtotal);
-    gslot = __shfl_sync(FULL, gslot, 31) + mx - mc;
-
-    if (warp == 0) {                                     // 32 predecessors per round trip
-        const uint64_t base = chained_scan_resolve_warp(scan_state, tile, total);
-        if (lane == 0) {
-            s_base = base;
-            if (last_tile) *n_seg_out = base + total;
+    // one scan for both counters: heads in the low half, listed groups in the high half (a tile has at
+    // most 2048 of either)
+    uint32_t total;
+    const uint32_t excl = block_exclusive_scan<HS_THREADS>(hc | (mc << 16), s_scan, &total);
+    if (!EMIT) {
+        if (tid == 0) {
+            sx.tile_counts[tile] = (uint64_t)(total & 0xFFFFu) | ((uint64_t)(total >> 16) << 32);
             uint32_t first = HS_NONE;
 #pragma unroll
             for (int w = 0; w < HS_WARPS; ++w) first = min(first, s_wfirst[w]);
-            if (first != HS_NONE) tile_first[tile] = (uint32_t)(tile_start + first) + 1u;
+            if (first != HS_NONE) sx.tile_first[tile] = (uint32_t)(tile_start + first) + 1u;
         }
+        return;
     }
-    __syncthreads();
-    uint64_t g = s_base + excl;
+    uint64_t g = (base & 0xFFFFFFFFull) + (excl & 0xFFFFu);
+    uint32_t gslot = (uint32_t)(base >> 32) + (excl >> 16);
 #pragma unroll
     for (int i = 0; i < HS_ITEMS; ++i) {
         if ((hmask >> i) & 1u) {
             const uint32_t p = (uint32_t)(tile_start + t0 + i);
             if (cnt[i] == 1) {
                 rows[g] = singleton_row(k[i], m[i]);
-                atomicAdd(distinct_functions + m[i].y, 1u);                 // tcc:286
             } else if (cnt[i] == 0) {
-                tile_open[tile] = ((uint64_t)(p + 1u) << 32) | (uint64_t)(uint32_t)g;
+                // closed by resolve_open_kernel
             } else if (cnt[i] <= 32) {
                 groups[gslot++] = OrderWork{(uint32_t)g, p, cnt[i]};
             } else {
@@ -326,31 +331,69 @@ head_scan_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__
     }
 }
 
-// Groups that ran past the end of their tile: the next head is the first head of the next tile that
-// has one (tile_first, 0 = none), or the end of the records.
+// Exclusive scan of the per-tile {heads, listed groups} pairs by one block (a few hundred thousand
+// entries): tile_base[t] = pairs before tile t; the totals are the number of groups and of list entries.
+__global__ void __launch_bounds__(SCAN_THREADS)
+tile_scan_kernel(const uint64_t *__restrict__ n_ptr, ReduceScratch sx, uint64_t *__restrict__ n_seg_out, uint32_t *__restrict__ n_groups) {
+    __shared__ uint64_t s_part[SCAN_THREADS / 32 + 1];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint64_t n = *n_ptr;
+    const uint64_t tiles = (n + RED_BATCH - 1) / RED_BATCH;
+    const uint64_t per = (tiles + SCAN_THREADS - 1) / SCAN_THREADS;
+    const uint64_t lo = min(tiles, (uint64_t)tid * per), hi = min(tiles, lo + per);
+    uint64_t sum = 0;
+    for (uint64_t t = lo; t < hi; ++t) sum += sx.tile_counts[t];
+    uint64_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t y = __shfl_up_sync(FULL, incl, o);
+        if (lane >= (unsigned)o) incl += y;
+    }
+    if (lane == 31) s_part[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint64_t w = s_part[lane];
+        uint64_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t y = __shfl_up_sync(FULL, wi, o);
+            if (lane >= (unsigned)o) wi += y;
+        }
+        s_part[lane] = wi - w;
+        if (lane == 31) s_part[32] = wi;
+    }
+    __syncthreads();
+    uint64_t run = s_part[warp] + incl - sum;
+    for (uint64_t t = lo; t < hi; ++t) { sx.tile_base[t] = run; run += sx.tile_counts[t]; }
+    if (tid == 0) {
+        *n_seg_out = s_part[32] & 0xFFFFFFFFull;
+        *n_groups = (uint32_t)(s_part[32] >> 32);
+    }
+}
+
+// Groups that ran past the end of their tile (always the tile's last head): the next head is the first
+// head of the next tile that has one (tile_first, 0 = none), or the end of the records.
 __global__ void resolve_open_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-                                    const uint64_t *__restrict__ n_ptr, const ProtMeta *__restrict__ meta,
-                                    const uint64_t *__restrict__ tile_open, const uint32_t *__restrict__ tile_first,
+                                    const uint64_t *__restrict__ n_ptr, const ProtMeta *__restrict__ meta, ReduceScratch sx,
                                     uint4 *__restrict__ rows, OrderWork *__restrict__ groups, uint32_t *__restrict__ n_groups,
-                                    OrderWork *__restrict__ long_groups, uint32_t *__restrict__ n_long,
-                                    uint32_t *__restrict__ distinct_functions) {
+                                    OrderWork *__restrict__ long_groups, uint32_t *__restrict__ n_long) {
     const uint64_t n = *n_ptr;
     const uint64_t n_tiles = (n + RED_BATCH - 1) / RED_BATCH;
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
-    const uint64_t o = tile_open[t];
+    const uint32_t o = sx.tile_open[t];
     if (!o) return;
-    const uint32_t start = (uint32_t)(o >> 32) - 1u, g = (uint32_t)o;
+    const uint32_t start = o - 1u;
+    const uint32_t g = (uint32_t)sx.tile_base[t] + (uint32_t)sx.tile_counts[t] - 1u;
     uint64_t end = n;
     for (uint64_t u = t + 1; u < n_tiles; ++u) {
-        const uint32_t f = __ldg(tile_first + u);
+        const uint32_t f = __ldg(sx.tile_first + u);
         if (f) { end = f - 1u; break; }
     }
     const uint32_t cnt = (uint32_t)(end - start);
     if (cnt == 1) {
         const ProtMeta m = __ldg(meta + __ldg(vals + start));
         rows[g] = singleton_row(__ldg(keys + start), m);
-        atomicAdd(distinct_functions + m.y, 1u);                            // tcc:286
     } else if (cnt <= 32) {
         groups[atomicAdd(n_groups, 1u)] = OrderWork{g, start, cnt};
     } else {
@@ -367,7 +410,7 @@ group_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
                     const OrderWork *__restrict__ long_groups, const uint32_t *__restrict__ n_long, uint32_t *__restrict__ next_long,
                     uint4 *__restrict__ rows, OrderWork *__restrict__ work, uint32_t *__restrict__ n_work,
                     OrderWork *__restrict__ work_long, uint32_t *__restrict__ n_work_long, uint32_t *__restrict__ prot_rejected,
-                    uint32_t *__restrict__ distinct_functions, int order_stats) {
+                    uint32_t *__restrict__ rej_tile, int order_stats) {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t total = *n_groups;
     WorkCursor wc{0u, 0u};
@@ -390,10 +433,12 @@ group_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
                     const uint64_t code = sigk_key_code(keys[d.start]);
                     rows[d.row] = make_uint4((uint32_t)code, (uint32_t)(code >> 32) | (r.avg << 11), r.func | (r.mean << 16),
                                              (order_stats && r.closed) ? r.len0 : 0u);
-                    atomicAdd(distinct_functions + r.func, 1u);                 // tcc:286
                     if (walk_long) work_long[atomicAdd(n_work_long, 1u)] = d;
                     else if (walk) work[wc.base] = d;
-                } else rows[d.row] = make_uint4(0u, 0u, 0xFFFFu, 0u);
+                } else {
+                    rows[d.row] = make_uint4(0u, 0u, 0xFFFFu, 0u);
+                    atomicAdd(rej_tile + (d.row >> SQ_TILE_SHIFT), 1u);         // the squeeze's per-tile tombstone count
+                }
             }
             if (walk && !walk_long) { wc.base += 1; wc.free -= 1; }
         }
@@ -518,9 +563,11 @@ group_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
                     else if ((mean + 1u) * best_count <= S) ++mean;
                     rows[grow] = make_uint4((uint32_t)code, (uint32_t)(code >> 32) | (sel << 11), cand | (mean << 16),
                                             (order_stats ? median_now : 0u) | (var2 << 16));
-                    atomicAdd(distinct_functions + cand, 1u);                                   // tcc:286
                     if (walk) work[wc.base + __popc(wb & mask_lt(lane))] = OrderWork{grow, (uint32_t)p, cnt};
-                } else rows[grow] = make_uint4(0u, 0u, 0xFFFFu, 0u);
+                } else {
+                    rows[grow] = make_uint4(0u, 0u, 0xFFFFu, 0u);
+                    atomicAdd(rej_tile + (grow >> SQ_TILE_SHIFT), 1u);          // the squeeze's per-tile tombstone count
+                }
             }
             if (wb) { const uint32_t k = __popc(wb); wc.base += k; wc.free -= k; }
             base += wlen;
@@ -532,10 +579,9 @@ group_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
 }
 
 // ---- squeeze: drop the tombstones, keep k-mer order, expand rows into the table columns
-constexpr int SQ_THREADS = 256;
-constexpr int SQ_ITEMS = 8;
-constexpr int SQ_TILE = SQ_THREADS * SQ_ITEMS;
-constexpr int SQ_WARPS = SQ_THREADS / 32;
+// Only rejected groups of two or more records leave tombstones, and group_reduce_kernel counts them per
+// squeeze tile as it writes them; one small scan later every tile knows where its kept rows go, so the
+// tiles are independent of each other (no chained scan, no tickets).
 
 // two residues at a time: pair_ascii[40 a + b] = letter(a) | letter(b) << 8
 __device__ uint16_t g_pair_ascii[1600];
@@ -551,19 +597,37 @@ SIGK_D uint64_t code_to_ascii_pairs(uint64_t code) {
     return (uint64_t)w0 | ((uint64_t)w1 << 32);
 }
 
-__global__ void __launch_bounds__(SQ_THREADS)
+// rej_before[t] = tombstones in the squeeze tiles before t; n_kept = groups - all tombstones.  One block.
+__global__ void __launch_bounds__(SCAN_THREADS)
+tombstone_scan_kernel(const uint64_t *__restrict__ n_seg_ptr, const uint32_t *__restrict__ rej_tile,
+                      uint32_t *__restrict__ rej_before, uint64_t *__restrict__ n_kept_out) {
+    __shared__ uint32_t s_part[SCAN_THREADS / 32 + 2];
+    const unsigned tid = threadIdx.x;
+    const uint64_t n_seg = *n_seg_ptr;
+    const uint64_t tiles = (n_seg + SQ_TILE - 1) / SQ_TILE;
+    const uint64_t per = (tiles + SCAN_THREADS - 1) / SCAN_THREADS;
+    const uint64_t lo = min(tiles, (uint64_t)tid * per), hi = min(tiles, lo + per);
+    uint32_t sum = 0;
+    for (uint64_t t = lo; t < hi; ++t) sum += rej_tile[t];
+    uint32_t total;
+    uint32_t run = block_exclusive_scan<SCAN_THREADS>(sum, s_part, &total);
+    for (uint64_t t = lo; t < hi; ++t) { rej_before[t] = run; run += rej_tile[t]; }
+    if (tid == 0) *n_kept_out = n_seg - total;
+}
+
+#ifndef SIGK_SQ_MIN_BLOCKS
+#define SIGK_SQ_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(SQ_THREADS, SIGK_SQ_MIN_BLOCKS)
 squeeze_rows_kernel(const uint4 *__restrict__ rows, const uint64_t *__restrict__ n_seg_ptr, KeptColumns out,
-                    uint64_t *__restrict__ scan_state, uint32_t *__restrict__ ticket, uint64_t *__restrict__ n_kept_out) {
+                    const uint32_t *__restrict__ rej_before) {
     __shared__ uint32_t s_scan[SQ_WARPS + 2];
-    __shared__ uint32_t s_tile;
-    __shared__ uint64_t s_base;
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint64_t n_seg = *n_seg_ptr;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
+    const uint32_t tile = blockIdx.x;
     const uint64_t tile_start = (uint64_t)tile * SQ_TILE;
     if (tile_start >= n_seg) return;
+    const uint64_t base = tile_start - __ldg(rej_before + tile);
 
     uint4 row[SQ_ITEMS];
     unsigned ball[SQ_ITEMS];
@@ -579,26 +643,11 @@ squeeze_rows_kernel(const uint4 *__restrict__ rows, const uint64_t *__restrict__
     uint32_t total;
     const uint32_t excl = block_exclusive_scan<SQ_THREADS>(lane == 0 ? warp_total : 0u, s_scan, &total);
     uint32_t run = __shfl_sync(FULL, excl, 0);
-    if (tid == 0) chained_scan_publish(scan_state, tile, total);
-    // the code -> ASCII expansion needs nothing from the other tiles: do it while they publish
-    uint64_t ascii[SQ_ITEMS];
-#pragma unroll
-    for (int i = 0; i < SQ_ITEMS; ++i)
-        ascii[i] = code_to_ascii_pairs((uint64_t)row[i].x | ((uint64_t)(row[i].y & 0x7FFu) << 32));
-    if (warp == 0) {                                     // 32 predecessors per round trip
-        const uint64_t base = chained_scan_resolve_warp(scan_state, tile, total);
-        if (lane == 0) {
-            s_base = base;
-            if (tile_start + SQ_TILE >= n_seg) *n_kept_out = base + total;
-        }
-    }
-    __syncthreads();
-    const uint64_t base = s_base;
 #pragma unroll
     for (int i = 0; i < SQ_ITEMS; ++i) {
         if ((ball[i] >> lane) & 1u) {
             const uint64_t o = base + run + __popc(ball[i] & mask_lt(lane));
-            out.kmer[o] = ascii[i];
+            out.kmer[o] = code_to_ascii_pairs((uint64_t)row[i].x | ((uint64_t)(row[i].y & 0x7FFu) << 32));
             out.avg_from_end[o] = (uint16_t)(row[i].y >> 11);
             out.function_index[o] = (uint16_t)(row[i].z & 0xFFFFu);
             out.mean[o] = (uint16_t)(row[i].z >> 16);
@@ -731,6 +780,44 @@ order_stats_long_kernel(const uint32_t *__restrict__ vals, const ProtMeta *__res
     }
 }
 
+// ---- distinct_functions[best]++ per kept k-mer (tcc:286) --------------------------------------
+// One global atomic per kept row (hundreds of millions on a few ten thousand counters) is what bounded the
+// run-length kernel, so the tally is taken afterwards from the function_index column of the finished table:
+// every block owns a range of 32768 counters in shared memory, walks its share of the column with 16-byte
+// loads and flushes what it counted once.
+constexpr int FH_THREADS = 1024;
+constexpr int FH_BINS = 32768;
+
+__global__ void __launch_bounds__(FH_THREADS)
+function_histogram_kernel(const uint16_t *__restrict__ func, const uint64_t *__restrict__ n_ptr, int n_ranges,
+                          uint32_t *__restrict__ distinct_functions) {
+    extern __shared__ uint32_t fh_bins[];
+    const uint32_t range = blockIdx.x % (uint32_t)n_ranges, chunk = blockIdx.x / (uint32_t)n_ranges;
+    const uint32_t n_chunks = gridDim.x / (uint32_t)n_ranges;
+    if (chunk >= n_chunks) return;
+    for (int b = threadIdx.x; b < FH_BINS; b += FH_THREADS) fh_bins[b] = 0;
+    __syncthreads();
+    const uint64_t n = *n_ptr;
+    auto tally = [&](uint32_t f) { if ((f >> 15) == range) atomicAdd(&fh_bins[f & (FH_BINS - 1)], 1u); };
+    // scalar head up to 16-byte alignment, 8 rows per load in the body, scalar tail
+    const uint64_t mis = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(func) & 15u)) & 15u;
+    const uint64_t head = min(n, mis / 2);
+    const uint64_t n8 = (n - head) / 8;
+    const uint4 *body = reinterpret_cast<const uint4 *>(func + head);
+    for (uint64_t i = (uint64_t)chunk * FH_THREADS + threadIdx.x; i < n8; i += (uint64_t)n_chunks * FH_THREADS) {
+        const uint4 v = __ldg(body + i);
+        tally(v.x & 0xFFFFu); tally(v.x >> 16); tally(v.y & 0xFFFFu); tally(v.y >> 16);
+        tally(v.z & 0xFFFFu); tally(v.z >> 16); tally(v.w & 0xFFFFu); tally(v.w >> 16);
+    }
+    if (chunk == 0) {
+        for (uint64_t i = threadIdx.x; i < head; i += FH_THREADS) tally(func[i]);
+        for (uint64_t i = head + n8 * 8 + threadIdx.x; i < n; i += FH_THREADS) tally(func[i]);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < FH_BINS; b += FH_THREADS)
+        if (fh_bins[b]) atomicAdd(distinct_functions + (size_t)range * FH_BINS + b, fh_bins[b]);
+}
+
 // seq_bitmap bit seq_id[i] = protein i has an occurrence in a kept group
 __global__ void signature_flags_kernel(const uint32_t *__restrict__ prot_windows, const uint32_t *__restrict__ prot_rejected,
                                        const uint32_t *__restrict__ seq_id, uint32_t n_prot, uint32_t *__restrict__ bitmap) {
@@ -786,27 +873,41 @@ cudaError_t launch_protein_meta(const uint64_t *starts, const uint16_t *func, co
     return cudaGetLastError();
 }
 
+ReduceScratch reduce_scratch(uint64_t *words, uint64_t capacity) {
+    const uint64_t b = reduce_batches(capacity) + 1, q = squeeze_tiles(capacity) + 1;
+    ReduceScratch sx;
+    sx.tile_counts = words;
+    sx.tile_base = words + b;
+    sx.tile_open = reinterpret_cast<uint32_t *>(words + 2 * b);
+    sx.tile_first = sx.tile_open + b;
+    sx.rej_tile = reinterpret_cast<uint32_t *>(words + 3 * b);
+    sx.rej_before = sx.rej_tile + q;
+    return sx;
+}
+
 cudaError_t launch_segment_reduce(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
                                   const ProtMeta *meta, uint4 *rows, const ReduceLists &l, uint32_t *prot_rejected,
-                                  uint32_t *distinct_functions, uint64_t *scan_state, uint32_t *ticket, uint64_t *n_seg_out,
-                                  int order_stats, int sm_count, cudaStream_t stream) {
+                                  uint64_t *scratch_words, uint64_t *n_seg_out, int order_stats, int sm_count, cudaStream_t stream) {
     if (capacity == 0) return cudaSuccess;
     const uint64_t grid = reduce_grid(sm_count);
     const uint64_t tiles = reduce_batches(capacity);
-    uint64_t *tile_open = scan_state + reduce_tile_open_offset(capacity);
-    uint32_t *tile_first = reinterpret_cast<uint32_t *>(tile_open + tiles);
-    head_scan_kernel<<<(unsigned)tiles, HS_THREADS, 0, stream>>>(
-        keys, vals, n_ptr, meta, rows, l.groups, l.n_groups, l.long_groups, l.n_long, distinct_functions, scan_state,
-        tile_open, tile_first, ticket, n_seg_out);
+    const ReduceScratch sx = reduce_scratch(scratch_words, capacity);
+    head_tile_kernel<false><<<(unsigned)tiles, HS_THREADS, 0, stream>>>(keys, vals, n_ptr, meta, rows, l.groups, l.long_groups, l.n_long, sx);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    resolve_open_kernel<<<(unsigned)((tiles + 255) / 256), 256, 0, stream>>>(
-        keys, vals, n_ptr, meta, tile_open, tile_first, rows, l.groups, l.n_groups, l.long_groups, l.n_long, distinct_functions);
+    tile_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(n_ptr, sx, n_seg_out, l.n_groups);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    head_tile_kernel<true><<<(unsigned)tiles, HS_THREADS, 0, stream>>>(keys, vals, n_ptr, meta, rows, l.groups, l.long_groups, l.n_long, sx);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    resolve_open_kernel<<<(unsigned)((tiles + 255) / 256), 256, 0, stream>>>(keys, vals, n_ptr, meta, sx, rows, l.groups, l.n_groups,
+                                                                              l.long_groups, l.n_long);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     group_reduce_kernel<<<(unsigned)grid, RED_THREADS, 0, stream>>>(keys, vals, meta, l.groups, l.n_groups, l.next_group, l.long_groups,
                                                                     l.n_long, l.next_long, rows, l.work, l.n_work, l.work_long,
-                                                                    l.n_work_long, prot_rejected, distinct_functions, order_stats);
+                                                                    l.n_work_long, prot_rejected, sx.rej_tile, order_stats);
     return cudaGetLastError();
 }
 
@@ -823,9 +924,30 @@ cudaError_t launch_order_stats(const uint32_t *vals, const ProtMeta *meta, const
 }
 
 cudaError_t launch_squeeze_rows(const uint4 *rows, const uint64_t *n_seg_ptr, uint64_t capacity, KeptColumns out,
-                                uint64_t *scan_state, uint32_t *ticket, uint64_t *n_kept_out, cudaStream_t stream) {
+                                uint64_t *scratch_words, uint64_t *n_kept_out, cudaStream_t stream) {
     if (capacity == 0) return cudaSuccess;
-    squeeze_rows_kernel<<<(unsigned)squeeze_tiles(capacity), SQ_THREADS, 0, stream>>>(rows, n_seg_ptr, out, scan_state, ticket, n_kept_out);
+    const ReduceScratch sx = reduce_scratch(scratch_words, capacity);
+    tombstone_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(n_seg_ptr, sx.rej_tile, sx.rej_before, n_kept_out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    squeeze_rows_kernel<<<(unsigned)squeeze_tiles(capacity), SQ_THREADS, 0, stream>>>(rows, n_seg_ptr, out, sx.rej_before);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_function_histogram(const uint16_t *function_index, const uint64_t *n_kept_ptr, uint64_t capacity,
+                                      uint32_t max_function, uint32_t *distinct_functions, int sm_count, cudaStream_t stream) {
+    if (capacity == 0) return cudaSuccess;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(function_histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_BINS * (int)sizeof(uint32_t));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int n_ranges = max_function >= (uint32_t)FH_BINS ? 2 : 1;
+    const uint64_t want = (capacity / 8 + FH_THREADS - 1) / FH_THREADS + 1;
+    const unsigned chunks = (unsigned)std::min<uint64_t>((uint64_t)sm_count, want);
+    function_histogram_kernel<<<chunks * n_ranges, FH_THREADS, FH_BINS * sizeof(uint32_t), stream>>>(function_index, n_kept_ptr, n_ranges,
+                                                                                                  distinct_functions);
     return cudaGetLastError();
 }
 

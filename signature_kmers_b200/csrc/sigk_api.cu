@@ -172,16 +172,18 @@ int do_build_device(sigk_handle *h) {
     ReduceLists rl{h->d_groups.p, &sc->n_groups, &sc->next_group, h->d_long_groups.p, &sc->n_long, &sc->next_long,
                    h->d_work.p, &sc->n_work, h->d_work_long.p, &sc->n_work_long};
     CU(h, launch_segment_reduce(h->d_keys[cur].p, h->d_vals[cur].p, &sc->n_records, cap, h->d_meta.p, h->d_rows.p, rl,
-                                h->d_prot_rejected.p, h->d_distinct.p, h->d_scan_state.p, sc->ticket + TK_REDUCE, &sc->n_segments,
-                                order_stats, h->sm_count, st)); launches += 3;
+                                h->d_prot_rejected.p, h->d_scan_state.p, &sc->n_segments, order_stats, h->sm_count, st)); launches += 5;
     if (h->comm) { if (int rc = comm_reduce_rejected(h)) return rc; }
     CU(h, launch_signature_flags(h->d_prot_windows.p, h->d_prot_rejected.p + h->ordinal_base, h->d_seqid.p, (uint32_t)np, h->d_bitmap.p, st)); ++launches;
     CU(h, launch_popcount(h->d_bitmap.p, ((uint64_t)h->max_seq_id >> 5) + 1, &sc->n_seqs_sig, st)); ++launches;
     CU(h, cudaEventRecord(h->ev[EV_REDUCE], st));
     if (order_stats) { CU(h, launch_order_stats(h->d_vals[cur].p, h->d_meta.p, h->d_work.p, &sc->n_work, &sc->next_work, h->d_work_long.p, &sc->n_work_long, &sc->next_work_long, cap, h->d_rows.p, h->sm_count, st)); launches += 2; }
     CU(h, cudaEventRecord(h->ev[EV_ORDER], st));
-    CU(h, launch_squeeze_rows(h->d_rows.p, &sc->n_segments, cap, kc, h->d_scan_state.p + reduce_batches(cap) + 1,
-                              sc->ticket + TK_SQUEEZE, &sc->n_kept, st)); ++launches;
+    CU(h, launch_squeeze_rows(h->d_rows.p, &sc->n_segments, cap, kc, h->d_scan_state.p, &sc->n_kept, st)); launches += 2;
+    // distinct_functions[best]++ per kept row (tcc:286), from the finished function_index column; with a
+    // communicator the other ranks' functions are not known here, so both counter ranges are walked
+    CU(h, launch_function_histogram(out_col(h, 1), &sc->n_kept, cap, h->comm ? 0xFFFFu : h->local_max_function, h->d_distinct.p,
+                                    h->sm_count, st)); ++launches;
     if (h->comm) { if (int rc = comm_reduce_stats(h)) return rc; }
     CU(h, cudaEventRecord(h->ev[EV_SQUEEZE], st));
 
@@ -317,13 +319,15 @@ int sigk_set_proteins(sigk_handle *h, const sigk_proteins *p) {
     const uint64_t total = p->starts[np];
     if (total >= 0xFFFFFFFFull) return h->fail(SIGK_E_UNSUPPORTED, "more than 2^32-2 residues on one GPU");
     if (np && (!p->function_index || !p->seq_id || (total && !p->residues))) return h->fail(SIGK_E_INVALID, "null protein arrays");
-    uint32_t max_sid = 0;
+    uint32_t max_sid = 0, max_func = 0;
     for (uint64_t i = 0; i < np; ++i) {
         if (p->starts[i + 1] < p->starts[i]) return h->fail(SIGK_E_INVALID, "starts must be non-decreasing (protein %llu)", (unsigned long long)i);
         if (p->function_index[i] == SIGK_UNDEFINED_FUNCTION)
             return h->fail(SIGK_E_INVALID, "protein %llu has UndefinedFunction; the host must skip it (src/signature_build.tcc:155)", (unsigned long long)i);
         max_sid = std::max(max_sid, p->seq_id[i]);
+        max_func = std::max<uint32_t>(max_func, p->function_index[i]);
     }
+    h->local_max_function = max_func;
     h->in = *p;
     h->total_res = total;
     h->max_seq_id = max_sid;
