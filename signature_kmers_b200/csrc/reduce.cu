@@ -331,43 +331,57 @@ head_tile_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__
     }
 }
 
-// Exclusive scan of the per-tile {heads, listed groups} pairs by one block (a few hundred thousand
-// entries): tile_base[t] = pairs before tile t; the totals are the number of groups and of list entries.
-__global__ void __launch_bounds__(SCAN_THREADS)
-tile_scan_kernel(const uint64_t *__restrict__ n_ptr, ReduceScratch sx, uint64_t *__restrict__ n_seg_out, uint32_t *__restrict__ n_groups) {
-    __shared__ uint64_t s_part[SCAN_THREADS / 32 + 1];
+// Exclusive scan of `count` per-tile counters by one block, written for coalesced access: warp w owns the
+// contiguous chunk w of the tiles and walks it 32 entries at a time (once for the chunk total, once to
+// write the prefixes).  Returns the grand total in every thread.
+template <typename T>
+SIGK_D T block_scan_tiles(const T *__restrict__ in, T *__restrict__ out, uint64_t count, T *s_part /* 33 */) {
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint64_t n = *n_ptr;
-    const uint64_t tiles = (n + RED_BATCH - 1) / RED_BATCH;
-    const uint64_t per = (tiles + SCAN_THREADS - 1) / SCAN_THREADS;
-    const uint64_t lo = min(tiles, (uint64_t)tid * per), hi = min(tiles, lo + per);
-    uint64_t sum = 0;
-    for (uint64_t t = lo; t < hi; ++t) sum += sx.tile_counts[t];
-    uint64_t incl = sum;
+    const uint64_t per = ((count + SCAN_THREADS / 32 - 1) / (SCAN_THREADS / 32) + 31) & ~31ull;    // chunk, a multiple of 32
+    const uint64_t lo = min(count, (uint64_t)warp * per), hi = min(count, lo + per);
+    T sum = 0;
+    for (uint64_t t = lo + lane; t < hi; t += 32) sum += in[t];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint64_t y = __shfl_up_sync(FULL, incl, o);
-        if (lane >= (unsigned)o) incl += y;
-    }
-    if (lane == 31) s_part[warp] = incl;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+    if (lane == 0) s_part[warp] = sum;
     __syncthreads();
     if (warp == 0) {
-        const uint64_t w = s_part[lane];
-        uint64_t wi = w;
+        const T w = s_part[lane];
+        T wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint64_t y = __shfl_up_sync(FULL, wi, o);
+            const T y = __shfl_up_sync(FULL, wi, o);
             if (lane >= (unsigned)o) wi += y;
         }
         s_part[lane] = wi - w;
         if (lane == 31) s_part[32] = wi;
     }
     __syncthreads();
-    uint64_t run = s_part[warp] + incl - sum;
-    for (uint64_t t = lo; t < hi; ++t) { sx.tile_base[t] = run; run += sx.tile_counts[t]; }
-    if (tid == 0) {
-        *n_seg_out = s_part[32] & 0xFFFFFFFFull;
-        *n_groups = (uint32_t)(s_part[32] >> 32);
+    T run = s_part[warp];
+    for (uint64_t t0 = lo; t0 < hi; t0 += 32) {
+        const uint64_t t = t0 + lane;
+        const T x = t < hi ? in[t] : (T)0;
+        T incl = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const T y = __shfl_up_sync(FULL, incl, o);
+            if (lane >= (unsigned)o) incl += y;
+        }
+        if (t < hi) out[t] = run + incl - x;
+        run += __shfl_sync(FULL, incl, 31);
+    }
+    return s_part[32];
+}
+
+// tile_base[t] = {heads, listed groups} before tile t; the totals are the number of groups and of list entries.
+__global__ void __launch_bounds__(SCAN_THREADS)
+tile_scan_kernel(const uint64_t *__restrict__ n_ptr, ReduceScratch sx, uint64_t *__restrict__ n_seg_out, uint32_t *__restrict__ n_groups) {
+    __shared__ uint64_t s_part[SCAN_THREADS / 32 + 1];
+    const uint64_t n = *n_ptr;
+    const uint64_t total = block_scan_tiles<uint64_t>(sx.tile_counts, sx.tile_base, (n + RED_BATCH - 1) / RED_BATCH, s_part);
+    if (threadIdx.x == 0) {
+        *n_seg_out = total & 0xFFFFFFFFull;
+        *n_groups = (uint32_t)(total >> 32);
     }
 }
 
@@ -601,18 +615,10 @@ SIGK_D uint64_t code_to_ascii_pairs(uint64_t code) {
 __global__ void __launch_bounds__(SCAN_THREADS)
 tombstone_scan_kernel(const uint64_t *__restrict__ n_seg_ptr, const uint32_t *__restrict__ rej_tile,
                       uint32_t *__restrict__ rej_before, uint64_t *__restrict__ n_kept_out) {
-    __shared__ uint32_t s_part[SCAN_THREADS / 32 + 2];
-    const unsigned tid = threadIdx.x;
+    __shared__ uint32_t s_part[SCAN_THREADS / 32 + 1];
     const uint64_t n_seg = *n_seg_ptr;
-    const uint64_t tiles = (n_seg + SQ_TILE - 1) / SQ_TILE;
-    const uint64_t per = (tiles + SCAN_THREADS - 1) / SCAN_THREADS;
-    const uint64_t lo = min(tiles, (uint64_t)tid * per), hi = min(tiles, lo + per);
-    uint32_t sum = 0;
-    for (uint64_t t = lo; t < hi; ++t) sum += rej_tile[t];
-    uint32_t total;
-    uint32_t run = block_exclusive_scan<SCAN_THREADS>(sum, s_part, &total);
-    for (uint64_t t = lo; t < hi; ++t) { rej_before[t] = run; run += rej_tile[t]; }
-    if (tid == 0) *n_kept_out = n_seg - total;
+    const uint32_t total = block_scan_tiles<uint32_t>(rej_tile, rej_before, (n_seg + SQ_TILE - 1) / SQ_TILE, s_part);
+    if (threadIdx.x == 0) *n_kept_out = n_seg - total;
 }
 
 #ifndef SIGK_SQ_MIN_BLOCKS
