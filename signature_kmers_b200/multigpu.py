@@ -1,7 +1,7 @@
 """One process per GPU: launcher-side plumbing for the range-partitioned build.
 
-The data path (sampled splitters, stable partition, NCCL all-to-all, per-rank
-sort/reduce) lives in csrc/comm.cu behind sigk_comm_join + sigk_build;
+The data path (sampled splitters, encode + route into the owners' landing zones
+over NVLink, per-rank sort/reduce) lives in csrc/comm.cu behind sigk_comm_join + sigk_build;
 torch.distributed is used here only to ship the 128-byte communicator id,
 for barriers, and to combine timings.  Test/bench driver, not the product.
 """
@@ -147,7 +147,7 @@ def run_bench(args, rank, world, local_rank, metric, unit):
             "config": {"workload": f"{args.workload} x {world} (weak scaling: {kw['n_proteins']} proteins, {kw['n_functions']} functions, "
                                    f"{kw['n_genomes']} genomes; rank r encodes canonical chunk r)",
                        "occurrences_per_step": occ, "distinct_kmers": counts["n_distinct_kmers"],
-                       "partition": "k-mer code ranges by sampled splitters, one NCCL all-to-all of 12-byte records",
+                       "partition": "k-mer code ranges by sampled splitters; the encode kernel stores each 12-byte record into its owner GPU's landing zone over NVLink (CUDA IPC), NCCL for the small collectives",
                        "K": 8, "record_bytes": 12, "sort_passes": passes,
                        "l2": "inputs larger than L2", "timed": "max over ranks of CUDA-event time on the library stream"},
             "clocks": clk,
