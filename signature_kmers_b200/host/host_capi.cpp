@@ -1,6 +1,6 @@
 // host_capi.cpp — C exports of the host-side pieces for the CPU test-suite
-// (no GPU, no libsigk calls): FASTA reader, SEED text helpers.
-#include "signature_host.h"
+// (no GPU, no libsigk calls): FASTA reader, SEED text helpers, function caller.
+#include "function_caller.h"
 
 #include <cstring>
 
@@ -38,5 +38,56 @@ uint64_t sigk_host_roles(const char *s, char *out, uint64_t cap) {
 }
 
 int sigk_host_is_truncated(const char *s) { return is_truncated_comment(s) ? 1 : 0; }
+
+
+// The function caller over a caller-supplied kept table (rows sorted by k-mer bytes).  function_names: one
+// name per line, index = line number.  Writes, per FASTA record, "id \t function \t index \t score \n" and, when
+// want_calls != 0, one "#call \t start \t end \t count \t function_index \t median \t mad" line per region call
+// before it.  Returns the bytes needed.
+uint64_t sigk_host_call_functions(uint64_t n_rows, const char *kmers, const uint16_t *avg_from_end, const uint16_t *function_index,
+                                  const uint16_t *mean, const uint16_t *median, const uint16_t *var, const char *function_names,
+                                  const char *fasta, uint64_t fasta_len, int ignore_hypo, int want_calls, char *out, uint64_t cap) {
+    sigk_table t{};
+    t.n_kept = n_rows; t.kmer = kmers; t.avg_from_end = avg_from_end; t.function_index = function_index;
+    t.mean = mean; t.median = median; t.var = var;
+    const SortedKmerDb db(t);
+    std::vector<std::string> names;
+    {
+        std::istringstream in(function_names);
+        std::string line;
+        while (std::getline(in, line)) names.push_back(line);
+    }
+    FunctionCaller<SortedKmerDb> caller(db, names);
+    caller.ignore_hypothetical(ignore_hypo != 0);
+    std::ostringstream buf;
+    FastaReader reader([&](const std::string &id, const std::string &, const std::string &seq) {
+        if (id.empty()) return;
+        std::vector<KmerCall> calls;
+        auto hit_cb = [](const std::string &, const std::array<char, kCallK> &, size_t, double, const StoredKmerData &) {};
+        caller.process_aa_seq(id, seq, &calls, hit_cb);
+        if (want_calls)
+            for (const auto &c : calls)
+                buf << "#call\t" << c.start << "\t" << c.end << "\t" << c.count << "\t" << c.function_index << "\t"
+                    << c.protein_length_median << "\t" << c.protein_length_med_avg_dev << "\n";
+        const BestCall best = caller.find_best_call(calls);
+        buf << id << "\t" << best.function << "\t" << best.function_index << "\t" << best.score << "\n";
+    }, true);
+    std::istringstream in(std::string(fasta, fasta_len));
+    reader.parse(in);
+    reader.finish();
+    const std::string s = buf.str();
+    if (s.size() <= cap) std::memcpy(out, s.data(), s.size());
+    return s.size();
+}
+
+// windows for_each_kmer visits: offsets as u32; returns their number
+uint64_t sigk_host_call_windows(const char *seq, uint64_t len, uint32_t *offsets, uint64_t cap) {
+    uint64_t n = 0;
+    for_each_kmer(std::string(seq, len), [&](const std::array<char, kCallK> &, size_t off) {
+        if (n < cap) offsets[n] = (uint32_t)off;
+        ++n;
+    });
+    return n;
+}
 
 }

@@ -7,15 +7,20 @@
 // (KMER \t avg_from_end \t function_index \t \n, :213-217), distinct_functions,
 // the stdout counters.  Rows of final.kmers are in k-mer order (the reference's
 // order is TBB hash order; write-cmph-from-kmers.cc:28-38 indexes by k-mer, so
-// no consumer depends on it).  Not done here: the recall pass
-// (recall.report.d is created empty), cmph and NuDB outputs (libraries absent).
+// no consumer depends on it), recall.report.d/<fasta file> (:266-349, through
+// function_caller.h).  --perfect-hash writes kmer_data.sigk (the sorted kept
+// table, what this repo's kmers-call-functions opens) instead of a cmph hash;
+// the NuDB output is not built (libraries absent).
 //
 // Extra options: --device N, --sorted-files (deterministic file order instead
 // of readdir order), --dump-packed FILE (write the gated packed proteins and
-// stop before the GPU: host-logic tests).
-#include "signature_host.h"
+// stop before the GPU: host-logic tests), --sigk-table FILE (write the table
+// file without --perfect-hash), --no-recall (skip the recall pass).
+#include "function_caller.h"
 
+#include <atomic>
 #include <cstring>
+#include <thread>
 
 using namespace sigk_host;
 
@@ -23,7 +28,8 @@ namespace {
 
 struct Options {
     std::vector<std::string> definition_dirs, fasta_dirs, fasta_keep_dirs, good_function_files, good_role_files;
-    fs::path deleted_fids_file, ignored_functions_file, kmer_data_dir, final_kmers, perfect_hash, perfect_hash_data, dump_packed;
+    fs::path deleted_fids_file, ignored_functions_file, kmer_data_dir, final_kmers, perfect_hash, perfect_hash_data, dump_packed, sigk_table;
+    bool no_recall = false;
     std::string nudb_file;
     int min_reps_required = 3, n_threads = 1, device = 0;
     bool sorted_files = false, help = false;
@@ -44,7 +50,7 @@ void usage(const char *argv0) {
               << "  --final-kmers arg                    Write final.kmers file\n"
               << "  --n-threads arg                      (accepted; the build runs on the GPU)\n"
               << "  --perfect-hash arg / --perfect-hash-data arg  (accepted; cmph output is not built)\n"
-              << "  --device arg / --sorted-files / --dump-packed arg\n"
+              << "  --device arg / --sorted-files / --dump-packed arg / --sigk-table arg / --no-recall\n"
               << "  -h [ --help ]                        show this help message\n";
 }
 
@@ -83,6 +89,8 @@ bool parse(int argc, char **argv, Options &o) {
         else if (a == "--device") o.device = std::stoi(next());
         else if (a == "--sorted-files") o.sorted_files = true;
         else if (a == "--dump-packed") o.dump_packed = next();
+        else if (a == "--sigk-table") o.sigk_table = next();
+        else if (a == "--no-recall") o.no_recall = true;
         else { std::cerr << "unrecognised option '" << a << "'\n"; return false; }
     }
     return true;
@@ -165,8 +173,51 @@ int main(int argc, char **argv) {
     const fs::path report_dir = o.kmer_data_dir / "recall.report.d";
     std::error_code ec;
     if (!fs::create_directory(report_dir, ec)) std::cerr << "mkdir " << report_dir << " failed\n";
-    if (!o.perfect_hash.empty() || !o.nudb_file.empty())
-        std::cerr << "note: cmph / NuDB outputs are not built in this drop-in (libraries absent); final.kmers carries the table\n";
+
+    // the table in the form this repo's kmers-call-functions opens (stands in for the cmph pair, :256-265)
+    if (!o.perfect_hash.empty() || !o.sigk_table.empty()) {
+        fs::path tf = o.sigk_table.empty() ? fs::path("kmer_data.sigk") : o.sigk_table;
+        if (tf.is_relative()) tf = o.kmer_data_dir / tf;
+        if (!SortedKmerDb::write_file(tf, t)) { std::cerr << "cannot write " << tf << "\n"; return 1; }
+        if (!o.perfect_hash.empty())
+            std::cerr << "note: cmph is not available; wrote the sorted kept table to " << tf << " instead of a perfect hash\n";
+    }
+    if (!o.nudb_file.empty()) std::cerr << "note: the NuDB output is not built in this drop-in (library absent)\n";
+
+    // recall of the source data with the new k-mers (:266-349): every call that differs from the stripped
+    // original assignment goes to recall.report.d/<fasta file name>, ordered by id
+    if (!o.no_recall) {
+        const SortedKmerDb kdb(t);
+        const FunctionCaller<SortedKmerDb> kmer_caller(kdb, o.kmer_data_dir / "function.index");
+        std::cerr << "Begin recall\n";
+        const auto &files = builder.all_fasta_data();
+        std::atomic<size_t> next{0};
+        auto worker = [&] {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= files.size()) break;
+                struct Row { std::string old_func, old_stripped, new_func; int func_index; float score; };
+                std::map<std::string, Row> rows;
+                auto hit_cb = [](const std::string &, const std::array<char, kCallK> &, size_t, double, const StoredKmerData &) {};
+                auto call_cb = [&](const std::string &id, const std::string &func, uint16_t fi, float score, size_t) {
+                    std::string orig, orig_stripped;
+                    builder.function_map().lookup_original_assignment(id, orig, orig_stripped);
+                    if (orig_stripped != func) rows.emplace(id, Row{orig, orig_stripped, func, (int)fi, score});
+                };
+                std::ifstream in(files[i]);
+                kmer_caller.process_fasta_stream(in, hit_cb, call_cb);
+                std::ofstream rep(report_dir / files[i].filename());
+                for (const auto &e : rows)
+                    rep << e.first << "\t" << e.second.old_func << "\t" << e.second.old_stripped << "\t" << e.second.new_func << "\t"
+                        << e.second.func_index << "\t" << e.second.score << "\n";
+            }
+        };
+        const int nt = std::max(1, std::min<int>(o.n_threads, (int)files.size()));
+        std::vector<std::thread> pool;
+        for (int k = 1; k < nt; ++k) pool.emplace_back(worker);
+        worker();
+        for (auto &th : pool) th.join();
+    }
     std::cerr << "all done\n";
     return 0;
 }

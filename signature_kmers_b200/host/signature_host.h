@@ -265,6 +265,11 @@ public:
         auto it = id_function_map_.find(id);
         return it == id_function_map_.end() ? std::string() : it->second;
     }
+    // src/function_map.h:351-358 (outputs untouched when the id was never assigned)
+    void lookup_original_assignment(const std::string &id, std::string &func, std::string &stripped) const {
+        auto it = original_assignment_.find(id);
+        if (it != original_assignment_.end()) { func = it->second; stripped = original_assignment_stripped_.at(id); }
+    }
     std::string lookup_function(uint16_t idx) const {
         auto it = index_function_map_.find(idx);
         return it == index_function_map_.end() ? std::string() : it->second;
