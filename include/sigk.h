@@ -187,6 +187,20 @@ int sigk_dbg_encode(sigk_handle *h, const sigk_proteins *p,
 int sigk_dbg_sort_pairs(sigk_handle *h, uint64_t *keys, uint32_t *vals, uint64_t n,
                         int bit_lo, int bit_hi);
 
+/* ---- consumer side of the table --------------------------------------------
+ * Batch form of what FunctionCaller::process_aa_seq does per window (src/call_functions.tcc:276-282):
+ * for_each_kmer (src/kmer_data.h:76-102: a window is skipped when '*' or 'X' lies in it or right behind it)
+ * + KeptKmerDB::fetch (src/kept_kmer_db.h:20-28: exact membership) for every window of every query protein.
+ * rows[g] (host, starts[n_proteins] entries) = row of the window starting at residue position g in the table
+ * that is resident on the device — the last build's, or the one given to sigk_set_table — or 0xFFFFFFFF.
+ * The caller reads avg_from_end / function_index / mean of a hit from its host copy of the table (sigk_result
+ * or the file it loaded) and feeds the hits, in position order, to the call logic.  With a communicator each
+ * rank looks up in its own slice of the table. */
+int sigk_lookup(sigk_handle *h, const uint8_t *residues, const uint64_t *starts, uint64_t n_proteins, uint32_t *rows);
+/* Make a table the lookup target without building it here: only t->kmer (8 bytes per row, sorted by bytes,
+ * as sigk_result returns them) and t->n_kept are read. */
+int sigk_set_table(sigk_handle *h, const sigk_table *t);
+
 /* 43-bit code <-> 8 ASCII bytes (host side, no GPU). */
 uint64_t sigk_kmer_encode(const char kmer[8]);          /* UINT64_MAX if any residue invalid */
 void     sigk_kmer_decode(uint64_t code, char kmer[8]);

@@ -117,6 +117,23 @@ class GpuSignatureBuilder:
         return keys, vals
 
 
+    def lookup(self, residues: np.ndarray, starts: np.ndarray) -> np.ndarray:
+        """rows[g] = table row of the call-side window at residue position g, or 0xFFFFFFFF (sigk_lookup)."""
+        residues = np.ascontiguousarray(residues, dtype=np.uint8)
+        starts = np.ascontiguousarray(starts, dtype=np.uint64)
+        rows = np.full(int(starts[-1]) if len(starts) else 0, 0xFFFFFFFF, dtype=np.uint32)
+        self._check(self.lib.sigk_lookup(self.h, residues.ctypes.data, starts.ctypes.data, len(starts) - 1, rows.ctypes.data), "sigk_lookup")
+        return rows
+
+    def set_table(self, kmers: np.ndarray):
+        """Make a sorted k-mer column (uint8 [n,8]) the lookup target (sigk_set_table)."""
+        kmers = np.ascontiguousarray(kmers, dtype=np.uint8)
+        t = capi.SigkTable()
+        t.n_kept = len(kmers)
+        t.kmer = kmers.ctypes.data
+        self._check(self.lib.sigk_set_table(self.h, C.byref(t)), "sigk_set_table")
+
+
 def kmer_encode(kmer: str) -> int:
     return capi.load_library().sigk_kmer_encode(kmer.encode("latin-1"))
 

@@ -234,6 +234,8 @@ EXPORTED_SYMBOLS = [
     "sigk_comm_join",
     "sigk_dbg_encode",
     "sigk_dbg_sort_pairs",
+    "sigk_lookup",
+    "sigk_set_table",
     "sigk_kmer_encode",
     "sigk_kmer_decode",
 ]
@@ -284,6 +286,8 @@ def load_library(path: str | None = None) -> C.CDLL:
         C.c_void_p, C.POINTER(SigkProteins), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64),
     ]
     lib.sigk_dbg_sort_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]
+    lib.sigk_lookup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.sigk_set_table.argtypes = [C.c_void_p, C.POINTER(SigkTable)]
     lib.sigk_kmer_encode.argtypes = [C.c_char_p]
     lib.sigk_kmer_encode.restype = C.c_uint64
     lib.sigk_kmer_decode.argtypes = [C.c_uint64, C.c_char_p]

@@ -84,6 +84,11 @@ struct sigk_handle {
     sigk::DevBuf<uint8_t> d_lookback;
     sigk::DevBuf<uint64_t> d_hist, d_binbase, d_scan_state;
     sigk::DevBuf<uint64_t> d_out_kmer;
+    // sigk_lookup: query batch and its result, grow-only; table_on_device = a table (built or set) is resident
+    sigk::DevBuf<uint8_t> d_q_res;
+    sigk::DevBuf<uint64_t> d_q_starts;
+    sigk::DevBuf<uint32_t> d_q_rows;
+    bool table_on_device = false;
     sigk::DevBuf<uint16_t> d_out_cols;       // 5 columns of capacity rows
     sigk::DevBuf<uint32_t> d_bitmap, d_distinct, d_swf, d_prot_windows, d_prot_rejected;
     sigk::DevBuf<sigk::DeviceScalars> d_scalars;

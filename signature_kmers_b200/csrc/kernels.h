@@ -158,4 +158,10 @@ cudaError_t launch_signature_flags(const uint32_t *prot_windows, const uint32_t 
                                    uint32_t n_prot, uint32_t *bitmap, cudaStream_t stream);
 cudaError_t launch_popcount(const uint32_t *bitmap, uint64_t n_words, uint64_t *out, cudaStream_t stream);
 
+// ---- consumer side: batch lookups against the resident table (lookup.cu) ----
+// rows[g] = table row of the window starting at residue position g (for_each_kmer + KeptKmerDB::fetch), else 0xFFFFFFFF.
+// table_kmers: the table's k-mer column (8 ASCII bytes per row, sorted by bytes), *n_rows_ptr rows.
+cudaError_t launch_lookup(const uint8_t *res, const uint64_t *starts, uint32_t n_prot, uint64_t total, const uint64_t *table_kmers,
+                          const uint64_t *n_rows_ptr, uint32_t *rows, cudaStream_t stream);
+
 }  // namespace sigk

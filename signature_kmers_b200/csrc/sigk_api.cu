@@ -118,6 +118,7 @@ int do_build_device(sigk_handle *h) {
     DeviceScalars *sc = h->d_scalars.p;
     uint32_t launches = 0;
 
+    h->table_on_device = false;                 // the table buffers are rewritten from here on
     CU(h, cudaEventRecord(h->ev[EV_DEV0], st));
     CU(h, cudaMemsetAsync(sc, 0, sizeof(DeviceScalars), st));
     CU(h, cudaMemsetAsync(h->d_swf.p, 0, SIGK_N_FUNCTION_SLOTS * sizeof(uint32_t), st));
@@ -188,6 +189,7 @@ int do_build_device(sigk_handle *h) {
     CU(h, cudaEventRecord(h->ev[EV_SQUEEZE], st));
 
     h->tm.kernel_launches = launches;
+    h->table_on_device = true;
     h->built = true;
     h->downloaded = false;
     return SIGK_OK;
@@ -289,6 +291,7 @@ void sigk_destroy(sigk_handle *h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     comm_destroy(h);
+    h->d_q_res.release(); h->d_q_starts.release(); h->d_q_rows.release();
     h->d_res.release(); h->d_starts.release(); h->d_func.release(); h->d_seqid.release(); h->d_meta.release(); h->d_slice_prot.release();
     for (int i = 0; i < 2; ++i) { h->d_keys[i].release(); h->d_vals[i].release(); }
     h->d_lookback.release(); h->d_hist.release(); h->d_binbase.release(); h->d_scan_state.release();
@@ -346,6 +349,45 @@ int sigk_build(sigk_handle *h) {
     if (int rc = do_upload(h)) return rc;
     if (int rc = do_build_device(h)) return rc;
     if (int rc = do_download(h)) return rc;
+    return SIGK_OK;
+}
+
+int sigk_set_table(sigk_handle *h, const sigk_table *t) {
+    if (!h) return SIGK_E_INVALID;
+    if (!t || (t->n_kept && !t->kmer)) return h->fail(SIGK_E_INVALID, "null table");
+    if (t->n_kept >= 0xFFFFFFFFull) return h->fail(SIGK_E_UNSUPPORTED, "more than 2^32-2 rows");
+    if (int rc = ensure_device(h)) return rc;
+    cudaStream_t st = h->stream;
+    CU(h, h->d_scalars.reserve(1));
+    CU(h, h->d_out_kmer.reserve(t->n_kept));
+    if (t->n_kept) CU(h, cudaMemcpyAsync(h->d_out_kmer.p, t->kmer, t->n_kept * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    const uint64_t n = t->n_kept;
+    CU(h, cudaMemcpyAsync(&h->d_scalars.p->n_kept, &n, sizeof n, cudaMemcpyHostToDevice, st));
+    CU(h, cudaStreamSynchronize(st));
+    h->table_on_device = true;
+    h->built = h->downloaded = false;           // the columns of a previous build no longer match the k-mers
+    return SIGK_OK;
+}
+
+int sigk_lookup(sigk_handle *h, const uint8_t *residues, const uint64_t *starts, uint64_t n_proteins, uint32_t *rows) {
+    if (!h) return SIGK_E_INVALID;
+    if (!h->table_on_device) return h->fail(SIGK_E_INVALID, "no table on the device: call sigk_build / sigk_build_device or sigk_set_table first");
+    if (!starts || (n_proteins && starts[0] != 0)) return h->fail(SIGK_E_INVALID, "starts[0] must be 0");
+    if (n_proteins >= 0xFFFFFFFFull) return h->fail(SIGK_E_UNSUPPORTED, "more than 2^32-2 proteins");
+    const uint64_t total = n_proteins ? starts[n_proteins] : 0;
+    if (total == 0) return SIGK_OK;
+    if (!residues || !rows) return h->fail(SIGK_E_INVALID, "null query arrays");
+    if (int rc = ensure_device(h)) return rc;
+    cudaStream_t st = h->stream;
+    CU(h, h->d_q_res.reserve(total));
+    CU(h, h->d_q_starts.reserve(n_proteins + 1));
+    CU(h, h->d_q_rows.reserve(total));
+    CU(h, cudaMemcpyAsync(h->d_q_res.p, residues, total, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(h->d_q_starts.p, starts, (n_proteins + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CU(h, launch_lookup(h->d_q_res.p, h->d_q_starts.p, (uint32_t)n_proteins, total, h->d_out_kmer.p, &h->d_scalars.p->n_kept,
+                        h->d_q_rows.p, st));
+    CU(h, cudaMemcpyAsync(rows, h->d_q_rows.p, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
     return SIGK_OK;
 }
 

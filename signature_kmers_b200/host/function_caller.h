@@ -15,7 +15,7 @@
 // published algorithms (mean: four running means, Boost.Math >= 1.72 single_pass.hpp; median and MAD by
 // selection, exact for any order).  Only the mean can differ from another Boost version, and only in the
 // last ulp of a cut-off compared with the protein length — parity for this piece is UNPINNED against a
-// reference run; tests compare against an independent Python restatement (oracle/call_oracle.py).
+// reference run; tests/test_function_caller.py compares against an independent Python restatement.
 #pragma once
 
 #include "signature_host.h"
@@ -49,6 +49,7 @@ public:
     explicit SortedKmerDb(const sigk_table &t) { attach(t.n_kept, t.kmer, t.avg_from_end, t.function_index, t.mean, t.median, t.var); }
 
     uint64_t size() const { return n_; }
+    const char *kmer_bytes() const { return kmer_; }
 
     // kmer_data.sigk: "SIGKTBL1", u64 rows, 8 rows bytes of k-mers, then the five u16 columns
     static bool write_file(const fs::path &file, const sigk_table &t) {
@@ -255,34 +256,27 @@ public:
     // src/call_functions.tcc:262-343.  hit_cb(id, kmer, offset, seqlen, kdata) sees every accepted hit.
     template <class HitCB>
     void process_aa_seq(const std::string &id, const std::string &seq, std::vector<KmerCall> *calls, HitCB hit_cb) const {
-        if (hypo_pos_ < 0) {
-            std::cerr << "Cannot find hypothetical protein index\n";
-            std::exit(1);
-        }
-        std::vector<Hit> hits;
-        uint16_t current = kUndefinedFunction;
-        const double seqlen = (double)seq.size();
+        HitRun run(*this, id, (double)seq.size(), calls);
         for_each_kmer(seq, [&](const std::array<char, kCallK> &kmer, size_t offset) {
             int ec = 0;
-            db_.fetch(kmer, [&](const StoredKmerData &kd) {
-                if (ignore_hypothetical_ && kd.function_index == hypo_pos_) return;
-                hit_cb(id, kmer, offset, seqlen, kd);
-                // a hit further than max_gap from the last one closes the current run of hits
-                if (!hits.empty() && hits.back().pos + (unsigned long)max_gap_ < offset) {
-                    if ((int)hits.size() >= min_hits_) process_hits(hits, seqlen, current, calls);
-                    else hits.clear();
-                }
-                if (hits.empty()) current = kd.function_index;
-                // order_constraint_ is hard-wired false (:115), so every hit is taken
-                hits.push_back(Hit{kd, (unsigned long)offset});
-                // two hits in a row for another function: close the run, start the next with those two
-                if (hits.size() > 1 && current != kd.function_index) {
-                    const size_t m = hits.size();
-                    if (hits[m - 2].kd.function_index == hits[m - 1].kd.function_index) process_hits(hits, seqlen, current, calls);
-                }
-            }, ec);
+            db_.fetch(kmer, [&](const StoredKmerData &kd) { run.add(kmer, offset, kd, hit_cb); }, ec);
         });
-        if ((int)hits.size() >= min_hits_) process_hits(hits, seqlen, current, calls);
+        run.finish();
+    }
+
+    // The same with the lookups already done in a batch (libsigk's sigk_lookup): rows[p] = table row of the window
+    // at position p of this protein, or 0xFFFFFFFF when the window is not visited or not in the table.
+    template <class HitCB>
+    void process_looked_up(const std::string &id, const std::string &seq, const uint32_t *rows, std::vector<KmerCall> *calls,
+                           HitCB hit_cb) const {
+        HitRun run(*this, id, (double)seq.size(), calls);
+        std::array<char, kCallK> kmer;
+        for (size_t p = 0; p + kCallK <= seq.size(); ++p) {
+            if (rows[p] == 0xFFFFFFFFu) continue;
+            std::memcpy(kmer.data(), seq.data() + p, kCallK);
+            run.add(kmer, p, db_.row(rows[p]), hit_cb);
+        }
+        run.finish();
     }
 
     // src/call_functions.tcc:352-659
@@ -364,6 +358,32 @@ public:
         reader.finish();
     }
 
+    // process_fasta_stream with the lookups of the whole stream done in one batch: lookup(residues, starts,
+    // n_proteins, rows) fills rows as libsigk's sigk_lookup does and returns 0 on success.  Returns its status.
+    template <class Lookup, class HitCB, class CallCB>
+    int process_fasta_stream_batched(std::istream &in, Lookup &&lookup, HitCB &hit_cb, CallCB &call_cb) const {
+        std::vector<std::string> ids, seqs;
+        FastaReader reader([&](const std::string &id, const std::string &, const std::string &seq) {
+            if (id.empty()) return;
+            ids.push_back(id);
+            seqs.push_back(seq);
+        }, true);
+        reader.parse(in);
+        reader.finish();
+        std::vector<uint8_t> residues;
+        std::vector<uint64_t> starts(1, 0);
+        for (const auto &s : seqs) { residues.insert(residues.end(), s.begin(), s.end()); starts.push_back(residues.size()); }
+        std::vector<uint32_t> rows(residues.size() + 1, 0xFFFFFFFFu);
+        if (const int rc = lookup(residues.data(), starts.data(), (uint64_t)seqs.size(), rows.data())) return rc;
+        for (size_t i = 0; i < seqs.size(); ++i) {
+            std::vector<KmerCall> calls;
+            process_looked_up(ids[i], seqs[i], rows.data() + starts[i], &calls, hit_cb);
+            const BestCall best = find_best_call(calls);
+            call_cb(ids[i], best.function, best.function_index, best.score, seqs[i].size());
+        }
+        return 0;
+    }
+
 private:
     struct Hit { StoredKmerData kd; unsigned long pos; };
 
@@ -373,6 +393,47 @@ private:
     std::vector<std::string> function_index_;
     std::string undefined_function_;
     int hypo_pos_ = -1;
+
+    // the per-hit state machine of process_aa_seq (:276-339), shared by both hit sources
+    class HitRun {
+    public:
+        HitRun(const FunctionCaller &fc, const std::string &id, double seqlen, std::vector<KmerCall> *calls)
+            : fc_(fc), id_(id), seqlen_(seqlen), calls_(calls) {
+            if (fc.hypo_pos_ < 0) {
+                std::cerr << "Cannot find hypothetical protein index\n";
+                std::exit(1);
+            }
+        }
+        template <class HitCB>
+        void add(const std::array<char, kCallK> &kmer, size_t offset, const StoredKmerData &kd, HitCB &hit_cb) {
+            if (fc_.ignore_hypothetical_ && kd.function_index == fc_.hypo_pos_) return;
+            hit_cb(id_, kmer, offset, seqlen_, kd);
+            // a hit further than max_gap from the last one closes the current run of hits
+            if (!hits_.empty() && hits_.back().pos + (unsigned long)fc_.max_gap_ < offset) {
+                if ((int)hits_.size() >= fc_.min_hits_) fc_.process_hits(hits_, seqlen_, current_, calls_);
+                else hits_.clear();
+            }
+            if (hits_.empty()) current_ = kd.function_index;
+            // order_constraint_ is hard-wired false (:115), so every hit is taken
+            hits_.push_back(Hit{kd, (unsigned long)offset});
+            // two hits in a row for another function: close the run, start the next with those two
+            if (hits_.size() > 1 && current_ != kd.function_index) {
+                const size_t m = hits_.size();
+                if (hits_[m - 2].kd.function_index == hits_[m - 1].kd.function_index) fc_.process_hits(hits_, seqlen_, current_, calls_);
+            }
+        }
+        void finish() {
+            if ((int)hits_.size() >= fc_.min_hits_) fc_.process_hits(hits_, seqlen_, current_, calls_);
+        }
+
+    private:
+        const FunctionCaller &fc_;
+        const std::string &id_;
+        double seqlen_;
+        std::vector<KmerCall> *calls_;
+        std::vector<Hit> hits_;
+        uint16_t current_ = kUndefinedFunction;
+    };
 
     void find_hypothetical() {
         hypo_pos_ = -1;

@@ -15,11 +15,13 @@
 // Extra options: --device N, --sorted-files (deterministic file order instead
 // of readdir order), --dump-packed FILE (write the gated packed proteins and
 // stop before the GPU: host-logic tests), --sigk-table FILE (write the table
-// file without --perfect-hash), --no-recall (skip the recall pass).
+// file without --perfect-hash), --no-recall (skip the recall pass),
+// --host-recall (recall lookups on the host instead of sigk_lookup).
 #include "function_caller.h"
 
 #include <atomic>
 #include <cstring>
+#include <mutex>
 #include <thread>
 
 using namespace sigk_host;
@@ -29,7 +31,7 @@ namespace {
 struct Options {
     std::vector<std::string> definition_dirs, fasta_dirs, fasta_keep_dirs, good_function_files, good_role_files;
     fs::path deleted_fids_file, ignored_functions_file, kmer_data_dir, final_kmers, perfect_hash, perfect_hash_data, dump_packed, sigk_table;
-    bool no_recall = false;
+    bool no_recall = false, host_recall = false;
     std::string nudb_file;
     int min_reps_required = 3, n_threads = 1, device = 0;
     bool sorted_files = false, help = false;
@@ -50,7 +52,7 @@ void usage(const char *argv0) {
               << "  --final-kmers arg                    Write final.kmers file\n"
               << "  --n-threads arg                      (accepted; the build runs on the GPU)\n"
               << "  --perfect-hash arg / --perfect-hash-data arg  (accepted; cmph output is not built)\n"
-              << "  --device arg / --sorted-files / --dump-packed arg / --sigk-table arg / --no-recall\n"
+              << "  --device arg / --sorted-files / --dump-packed arg / --sigk-table arg / --no-recall / --host-recall\n"
               << "  -h [ --help ]                        show this help message\n";
 }
 
@@ -91,6 +93,7 @@ bool parse(int argc, char **argv, Options &o) {
         else if (a == "--dump-packed") o.dump_packed = next();
         else if (a == "--sigk-table") o.sigk_table = next();
         else if (a == "--no-recall") o.no_recall = true;
+        else if (a == "--host-recall") o.host_recall = true;
         else { std::cerr << "unrecognised option '" << a << "'\n"; return false; }
     }
     return true;
@@ -192,6 +195,8 @@ int main(int argc, char **argv) {
         std::cerr << "Begin recall\n";
         const auto &files = builder.all_fasta_data();
         std::atomic<size_t> next{0};
+        std::atomic<bool> failed{false};
+        std::mutex lookup_mutex;
         auto worker = [&] {
             for (;;) {
                 const size_t i = next.fetch_add(1);
@@ -205,7 +210,16 @@ int main(int argc, char **argv) {
                     if (orig_stripped != func) rows.emplace(id, Row{orig, orig_stripped, func, (int)fi, score});
                 };
                 std::ifstream in(files[i]);
-                kmer_caller.process_fasta_stream(in, hit_cb, call_cb);
+                if (o.host_recall) {
+                    kmer_caller.process_fasta_stream(in, hit_cb, call_cb);
+                } else {
+                    // every window of the file looked up in one batch on the GPU (one handle: one caller at a time)
+                    auto lookup = [&](const uint8_t *res, const uint64_t *starts, uint64_t n, uint32_t *rows) {
+                        std::lock_guard<std::mutex> g(lookup_mutex);
+                        return builder.lookup(res, starts, n, rows);
+                    };
+                    if (kmer_caller.process_fasta_stream_batched(in, lookup, hit_cb, call_cb)) failed = true;
+                }
                 std::ofstream rep(report_dir / files[i].filename());
                 for (const auto &e : rows)
                     rep << e.first << "\t" << e.second.old_func << "\t" << e.second.old_stripped << "\t" << e.second.new_func << "\t"
@@ -217,6 +231,7 @@ int main(int argc, char **argv) {
         for (int k = 1; k < nt; ++k) pool.emplace_back(worker);
         worker();
         for (auto &th : pool) th.join();
+        if (failed) return 1;
     }
     std::cerr << "all done\n";
     return 0;

@@ -9,6 +9,13 @@
 // kmers-build-signatures) instead of the cmph pair kmer_data.{mph,dat}: cmph is not available in this image,
 // and a perfect hash adds nothing over a sorted table for correctness (the KmerDb concept only needs fetch,
 // src/call_functions.h:60-66).  function.index is read from the data directory as in the reference.
+// NOTE on semantics: the reference's CmphKmerDb::fetch (src/cmph_kmer.h:138-147) calls back for EVERY key,
+// member or not — a minimal perfect hash maps a foreign k-mer to some unrelated slot — so its calls depend
+// on cmph's seeded hash functions and cannot be reproduced without that library and that .mph file.  This
+// tool uses exact membership, i.e. the semantics of KeptKmerDB (src/kept_kmer_db.h:20-28) that the
+// reference's own recall pass runs with (src/kmers-build-signatures.cc:260-270).
+// Extra option: --gpu DEVICE looks the windows of each input file up in one batch through libsigk
+// (sigk_set_table + sigk_lookup); the calls are the same, only the lookups move.
 
 #include "function_caller.h"
 
@@ -25,6 +32,7 @@ struct Options {
     std::vector<fs::path> input_files;
     bool debug_hits = false, ignore_hypo = false, help = false;
     int n_threads = 1;
+    int gpu = -1;
 };
 
 void usage(const char *argv0) {
@@ -35,6 +43,7 @@ void usage(const char *argv0) {
               << "  -j [ --n-threads ] arg     Number of threads\n"
               << "  --ignore-hypo              Ignore hypothetical protein kmers when making calls\n"
               << "  --debug-hits               Debug kmer hits\n"
+              << "  --gpu arg                  (extra) batch the k-mer lookups on this CUDA device\n"
               << "  -h [ --help ]              show this help message\n\n";
 }
 
@@ -54,6 +63,7 @@ bool parse(int argc, char **argv, Options &o) {
         else if (a == "-d" || a == "--data-dir") { if (!value(v)) return false; o.data_dir = v; }
         else if (a == "-o" || a == "--output-files") { if (!value(v)) return false; o.output_file = v; }
         else if (a == "-j" || a == "--n-threads") { if (!value(v)) return false; o.n_threads = std::stoi(v); }
+        else if (a == "--gpu") { if (!value(v)) return false; o.gpu = std::stoi(v); }
         else if (a == "-i" || a == "--input-files") {           // multitoken: up to the next option
             while (i + 1 < argc && argv[i + 1][0] != '-') o.input_files.emplace_back(argv[++i]);
         } else if (!a.empty() && a[0] == '-') { std::cerr << "unrecognised option '" << a << "'\n"; return false; }
@@ -99,6 +109,18 @@ int main(int argc, char **argv) {
         std::cout << line.str();
     };
 
+    sigk_handle *gpu = nullptr;
+    std::mutex gpu_mutex;
+    if (o.gpu >= 0) {
+        sigk_config cfg{SIGK_ABI_VERSION, SIGK_K, o.gpu, 0, 1, 0};
+        sigk_table t{};
+        t.n_kept = db.size();
+        t.kmer = db.kmer_bytes();
+        if (sigk_create(&cfg, &gpu)) { std::cerr << "sigk_create: " << sigk_last_error(nullptr) << "\n"; return 1; }
+        if (sigk_set_table(gpu, &t)) { std::cerr << "libsigk: " << sigk_last_error(gpu) << "\n"; return 1; }
+    }
+    std::atomic<bool> failed{false};
+
     // one task per input file; every file's calls are written as one block (the reference's writer queue)
     std::atomic<size_t> next{0};
     auto worker = [&] {
@@ -110,7 +132,17 @@ int main(int argc, char **argv) {
             auto call_cb = [&](const std::string &id, const std::string &func, uint16_t fi, float score, size_t) {
                 buf << id << "\t" << func << "\t" << fi << "\t" << score << "\n";
             };
-            caller.process_fasta_stream(in, hit_cb, call_cb);
+            if (gpu) {
+                auto lookup = [&](const uint8_t *res, const uint64_t *starts, uint64_t n, uint32_t *rows) {
+                    std::lock_guard<std::mutex> g(gpu_mutex);            // one handle: one caller at a time
+                    const int rc = sigk_lookup(gpu, res, starts, n, rows);
+                    if (rc) std::cerr << "libsigk: " << sigk_last_error(gpu) << "\n";
+                    return rc;
+                };
+                if (caller.process_fasta_stream_batched(in, lookup, hit_cb, call_cb)) failed = true;
+            } else {
+                caller.process_fasta_stream(in, hit_cb, call_cb);
+            }
             const std::string text = buf.str();
             if (!text.empty()) {
                 std::lock_guard<std::mutex> g(out_mutex);
@@ -124,5 +156,6 @@ int main(int argc, char **argv) {
     worker();
     for (auto &t : pool) t.join();
     anno_out.flush();
-    return 0;
+    if (gpu) sigk_destroy(gpu);
+    return failed ? 1 : 0;
 }

@@ -409,6 +409,12 @@ public:
         std::cout << "num_seqs_with_a_signature=" << table->num_seqs_with_a_signature << "\n";
         return 0;
     }
+    // batch lookups against the table the build left on the device (the recall pass, function_caller.h)
+    int lookup(const uint8_t *residues, const uint64_t *starts, uint64_t n_proteins, uint32_t *rows) {
+        const int rc = sigk_lookup(h_, residues, starts, n_proteins, rows);
+        if (rc) std::cerr << "libsigk: " << sigk_last_error(h_) << "\n";
+        return rc;
+    }
     ~HostSignatureBuilder() { if (h_) sigk_destroy(h_); }
 
     std::string lookup_function(uint16_t idx) const { return fm_.lookup_function(idx); }

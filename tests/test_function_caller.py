@@ -20,6 +20,9 @@ AA = "ACDEFGHIKLMNPQRSTVWY"
 
 @pytest.fixture(scope="module")
 def host():
+    if not os.path.exists(os.path.join(PKG, "libsigk.so")):
+        import __graft_entry__ as g
+        g.build()
     subprocess.run(["make", "-C", os.path.join(PKG, "host"), "../libsigk_host.so", "../kmers-call-functions"], check=True, capture_output=True)
     lib = C.CDLL(os.path.join(PKG, "libsigk_host.so"))
     u16p = np.ctypeslib.ndpointer(dtype=np.uint16, flags="C_CONTIGUOUS")
@@ -300,3 +303,109 @@ def test_command_line(host, tmp_path):
     r = subprocess.run([exe, str(tmp_path), str(fa1)], capture_output=True, text=True)
     assert r.returncode == 1 and "does not exist" in r.stderr
     assert subprocess.run([exe, "-h"], capture_output=True).returncode == 0
+
+
+# ---- GPU: batch lookups and the whole chain ---------------------------------------------------------
+@pytest.mark.gpu
+def test_gpu_lookup_matches_host_windows_and_membership():
+    """sigk_lookup on the table of a real build == for_each_kmer + dictionary membership, position by position."""
+    from signature_kmers_b200.builder import GpuSignatureBuilder
+
+    seqs, funcs = random_proteins(41, n_families=30, members=(3, 10), length=(30, 300), sub_rate=0.06, n_functions=15)
+    b = GpuSignatureBuilder(device=0)
+    b.set_proteins(pack(seqs, funcs))
+    table = b.build()
+    index = {k: i for i, k in enumerate(table.kmer_strings())}
+    rng = random.Random(3)
+    queries = []
+    for s in seqs[:60]:
+        s = s.decode("latin-1") if isinstance(s, bytes) else s
+        queries.append("".join(c if rng.random() > 0.02 else rng.choice("X*bz" + AA) for c in s))
+    queries += ["", "ACDEF", "X" * 20, "ACDEFGHI", "ACDEFGHIX"]
+    starts = np.zeros(len(queries) + 1, dtype=np.uint64)
+    starts[1:] = np.cumsum([len(q) for q in queries])
+    res = np.frombuffer("".join(queries).encode("latin-1"), dtype=np.uint8)
+    rows = b.lookup(res, starts)
+    want = np.full(len(res), 0xFFFFFFFF, dtype=np.uint32)
+    for q, s0 in zip(queries, starts[:-1]):
+        for kmer, off in co.for_each_kmer(q):
+            if kmer in index:
+                want[int(s0) + off] = index[kmer]
+    np.testing.assert_array_equal(rows, want)
+    assert (rows != 0xFFFFFFFF).sum() > 1000
+    # a table given from outside: same answers
+    b2 = GpuSignatureBuilder(device=0)
+    b2.set_table(table.kmer)
+    np.testing.assert_array_equal(b2.lookup(res, starts), want)
+    b.close(); b2.close()
+
+
+@pytest.mark.gpu
+def test_chain_build_store_call(tmp_path):
+    """config 5 in small: kmers-build-signatures (GPU) with --perfect-hash -> kmer_data.sigk + recall.report.d,
+    then kmers-call-functions (host lookups and --gpu lookups) on the training FASTA; calls equal the Python
+    oracle run on the table the CPU oracle of the build produces from the same packed proteins."""
+    from oracle import oracle_c
+    from signature_kmers_b200.capi import PackedProteins
+    from signature_kmers_b200.synth import Synth
+    from tests.test_host_dropin import read_packed
+
+    subprocess.run(["make", "-C", os.path.join(PKG, "host")], check=True, capture_output=True)
+    s = Synth(n_proteins=1500, n_functions=60, n_genomes=5, seed=17)
+    tree = tmp_path / "tree"
+    s.write_tree(str(tree))
+    out = tmp_path / "out"
+    cmd = [os.path.join(PKG, "kmers-build-signatures"), "-D", str(tree / "Annotations" / "0"), "-F", str(tree / "Seqs"),
+           "--kmer-data-dir", str(out), "--final-kmers", "final.kmers", "--perfect-hash", "kmer_data.mph", "--sorted-files", "--n-threads", "3"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    dump = tmp_path / "packed.bin"
+    subprocess.run(cmd + ["--dump-packed", str(dump)], check=True, capture_output=True)
+    res, starts, func, sid = read_packed(dump)
+    table, _ = oracle_c.oracle_build(PackedProteins(res.copy(), starts.copy(), func.copy(), sid.copy()))
+    rows = {k: (int(table.avg_from_end[i]), int(table.function_index[i]), int(table.mean[i]), int(table.median[i]), int(table.var[i]))
+            for i, k in enumerate(table.kmer_strings())}
+    names = {}
+    for line in open(out / "function.index").read().splitlines():
+        idx, name = line.split("\t")[:2]
+        names[int(idx)] = name
+    names = [names.get(i, "") for i in range(max(names) + 1)]
+    fc = co.FunctionCaller(rows, names)
+
+    fasta_files = sorted((tree / "Seqs").iterdir())
+    want = []
+    for f in fasta_files:
+        recs = [(blk.split("\n", 1)[0].split()[0], "".join(blk.split("\n")[1:])) for blk in f.read_text().split(">")[1:]]
+        for rid, seq in recs:
+            fi, fn, score = fc.call(seq)
+            want.append("%s\t%s\t%d\t%s" % (rid, fn, fi, co.format_score(score)))
+    exe = os.path.join(PKG, "kmers-call-functions")
+    host_run = subprocess.run([exe, str(out)] + [str(f) for f in fasta_files], capture_output=True, text=True)
+    assert host_run.returncode == 0, host_run.stderr
+    assert host_run.stdout.splitlines() == want
+    gpu_run = subprocess.run([exe, "--gpu", "0", str(out)] + [str(f) for f in fasta_files], capture_output=True, text=True)
+    assert gpu_run.returncode == 0, gpu_run.stderr
+    assert gpu_run.stdout == host_run.stdout
+    called = [l for l in want if not l.endswith("\t65535\t0")]
+    assert len(called) > 0.8 * len(want)                # the training set is recalled
+    # recall.report.d (GPU lookups) == the --host-recall variant; every reported row is a call that differs
+    rep = {f.name: f.read_text() for f in (out / "recall.report.d").iterdir()}
+    assert set(rep) == {f.name for f in fasta_files}
+    out2 = tmp_path / "out2"
+    r2 = subprocess.run([c if c != str(out) else str(out2) for c in cmd] + ["--host-recall"], capture_output=True, text=True)
+    assert r2.returncode == 0, r2.stderr
+    assert rep == {f.name: f.read_text() for f in (out2 / "recall.report.d").iterdir()}
+    calls_by_id = {l.split("\t")[0]: l.split("\t") for l in want}
+    n_rows = 0
+    for text in rep.values():
+        for line in text.splitlines():
+            rid, old, old_stripped, new, idx, score = line.split("\t")
+            assert calls_by_id[rid][1:] == [new, idx, score] and old_stripped != new
+            n_rows += 1
+    # ... and every call that differs from the assignment is reported
+    assigned = {}
+    for f in (tree / "Annotations" / "0").iterdir():
+        for line in f.read_text().splitlines():
+            rid, fn = line.split("\t")[:2]
+            assigned[rid] = fn
+    assert n_rows == sum(1 for rid, c in calls_by_id.items() if assigned.get(rid, "") != c[1])
