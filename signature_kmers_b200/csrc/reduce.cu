@@ -22,17 +22,18 @@
 // <= count/2 and the float test rejects for every count — ties never reach a
 // kept row, so the std::map walk's "lowest index wins" cannot matter.
 //
-// Work mapping (fused_reduce_kernel): a warp streams its chunk of the sorted
-// records in windows of <= 32 records that start at a group head and contain
-// only whole groups; lane = record, and every group in the window is reduced at
-// once with ballots and segmented shuffles.  Groups longer than 32 records are
-// walked 32 at a time by the whole warp; groups long enough to stall a tile
-// (>= 513 records) are found by sampling and reduced by a pre-pass.  Rows are
-// staged in shared memory and written in k-mer order through a chained scan of
-// kept counts over the tiles.
+// Work mapping: head_tile_kernel (count pass, emit pass) run-lengths the records in independent
+// 2048-record tiles and finishes single-record groups; group_reduce_kernel packs the groups of
+// 2..32 records 32 records to a warp (lane = record, every group of the window reduced at once
+// with ballots and segmented shuffles) and walks longer groups with a whole warp; every group
+// writes the row slot of its index (a tombstone when rejected); order_stats_kernel patches median
+// and var into the rows that need the ordered walk; squeeze_rows_kernel drops the tombstones and
+// expands the rows into the table columns; function_histogram_kernel tallies distinct_functions.
+// No kernel of this stage waits for another tile: bases come from two one-block scans of per-tile
+// counters (tile_scan_kernel, tombstone_scan_kernel).
 //
-// HBM traffic per record: 12 B read (+ a 16-byte L2 gather of the protein's
-// meta); per kept row 18 B written.
+// HBM traffic per record: 8 B (count pass) + 12 B read (+ an 8-byte L2 gather of the protein's
+// meta); per group a 16-byte row written and read once; per kept row 18 B written.
 #include "kernels.h"
 #include "sigk_common.cuh"
 #include "length_acc.cuh"
