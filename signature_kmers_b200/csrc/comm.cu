@@ -336,23 +336,25 @@ int comm_exchange_shapes(sigk_handle *h) {
     Comm *c = h->comm;
     cudaStream_t st = h->stream;
     const int W = c->world;
-    CU(h, c->d_shape.reserve(3 + 3 * (size_t)W));
+    CU(h, c->d_shape.reserve(4 + 4 * (size_t)W));
     CU(h, c->h_counts.reserve(std::max<size_t>(IPC_WORDS * (size_t)W, (size_t)W * (W + 1) + 4)));
-    uint64_t mine[3] = {h->in.n_proteins, h->max_seq_id, h->total_res};
+    uint64_t mine[4] = {h->in.n_proteins, h->max_seq_id, h->total_res, h->local_max_len};
     CU(h, cudaMemcpyAsync(c->d_shape.p, mine, sizeof mine, cudaMemcpyHostToDevice, st));
-    NC(h, g_nccl.AllGather(c->d_shape.p, c->d_shape.p + 3, 3, ncclUint64, c->comm, st));
-    CU(h, cudaMemcpyAsync(c->h_counts.p, c->d_shape.p + 3, 3 * (size_t)W * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    NC(h, g_nccl.AllGather(c->d_shape.p, c->d_shape.p + 4, 4, ncclUint64, c->comm, st));
+    CU(h, cudaMemcpyAsync(c->h_counts.p, c->d_shape.p + 4, 4 * (size_t)W * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
     c->prot_count.assign(W, 0);
-    uint64_t total = 0, base = 0, max_sid = 0;
+    uint64_t total = 0, base = 0, max_sid = 0, max_len = 0;
     c->max_total_res = 0;
     for (int r = 0; r < W; ++r) {
-        c->prot_count[r] = c->h_counts.p[3 * r];
+        c->prot_count[r] = c->h_counts.p[4 * r];
         if (r < c->rank) base += c->prot_count[r];
         total += c->prot_count[r];
-        max_sid = std::max(max_sid, c->h_counts.p[3 * r + 1]);
-        c->max_total_res = std::max(c->max_total_res, c->h_counts.p[3 * r + 2]);
+        max_sid = std::max(max_sid, c->h_counts.p[4 * r + 1]);
+        c->max_total_res = std::max(c->max_total_res, c->h_counts.p[4 * r + 2]);
+        max_len = std::max(max_len, c->h_counts.p[4 * r + 3]);
     }
+    h->max_len = max_len;
     if (total >= 0xFFFFFFFFull) return h->fail(SIGK_E_UNSUPPORTED, "more than 2^32-2 proteins in the job");
     h->n_prot_global = total;
     h->ordinal_base = base;
@@ -368,7 +370,8 @@ int comm_allgather_meta(sigk_handle *h) {
     uint64_t base = 0;
     for (int r = 0; r < c->world; ++r) {
         if (c->prot_count[r])
-            NC(h, g_nccl.Broadcast(h->d_meta.p + base, h->d_meta.p + base, c->prot_count[r] * sizeof(ProtMeta), ncclUint8, r, c->comm, st));
+            NC(h, g_nccl.Broadcast(h->d_meta.p + meta_bytes(base, h->meta_compact), h->d_meta.p + meta_bytes(base, h->meta_compact),
+                                   meta_bytes(c->prot_count[r], h->meta_compact), ncclUint8, r, c->comm, st));
         base += c->prot_count[r];
     }
     NC(h, g_nccl.GroupEnd());

@@ -76,7 +76,9 @@ struct sigk_handle {
     sigk::DevBuf<uint64_t> d_starts;
     sigk::DevBuf<uint16_t> d_func;
     sigk::DevBuf<uint32_t> d_seqid, d_slice_prot;
-    sigk::DevBuf<sigk::ProtMeta> d_meta;
+    sigk::DevBuf<uint8_t> d_meta;          // per-protein {length, function}: 4 or 8 bytes each (meta_compact)
+    bool meta_compact = false;
+    uint64_t local_max_len = 0, max_len = 0;   // longest protein: this rank's / the job's
     sigk::DevBuf<uint4> d_rows;
     sigk::DevBuf<sigk::OrderWork> d_groups, d_long_groups, d_work, d_work_long;
     sigk::DevBuf<uint64_t> d_keys[2];

@@ -119,12 +119,15 @@ size_t reduce_work_entries(uint64_t capacity, int sm_count);   // OrderWork entr
 size_t reduce_long_work_entries(uint64_t capacity);            // ... of those, the ones a whole warp walks
 cudaError_t reduce_configure();
 
-// What a record's protein ordinal is looked up for: 8 bytes, so that the job-wide table stays in L2 as long
-// as possible (2 M proteins = 16 MB).  x = protein_length, y = function_index.
+// What a record's protein ordinal is looked up for.  x = protein_length, y = function_index: 8 bytes per
+// protein, or — when every protein of the job is shorter than 65 535 residues — 4 bytes, length | function << 16
+// (compact), so that the job-wide table stays in L2 as long as possible (2 M proteins = 8 MB).
 using ProtMeta = uint2;
-// meta[i] = {protein_length, function_index}; seqs_with_func[f]++ (src/signature_build.tcc:160)
+struct MetaTable { void *p; bool compact; };
+inline size_t meta_bytes(uint64_t n_proteins, bool compact) { return (size_t)n_proteins * (compact ? sizeof(uint32_t) : sizeof(ProtMeta)); }
+// meta[first + i] for the n_prot local proteins; seqs_with_func[f]++ (src/signature_build.tcc:160)
 cudaError_t launch_protein_meta(const uint64_t *starts, const uint16_t *func, const uint32_t *seq_id, uint32_t n_prot,
-                                ProtMeta *meta, uint32_t *seqs_with_func, cudaStream_t stream);
+                                MetaTable meta, uint64_t first, uint32_t *seqs_with_func, cudaStream_t stream);
 
 // device lists and counters of the segment reduce (counters zeroed before the launch)
 struct ReduceLists {
@@ -138,14 +141,14 @@ struct ReduceLists {
 // leave a tombstone), plus the lists of groups whose median/var need the ordered walk.
 // scratch_words: reduce_scan_entries() zeroed words, shared with launch_squeeze_rows of the same build.
 cudaError_t launch_segment_reduce(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
-                                  const ProtMeta *meta, uint4 *rows, const ReduceLists &l, uint32_t *prot_rejected,
+                                  MetaTable meta, uint4 *rows, const ReduceLists &l, uint32_t *prot_rejected,
                                   uint64_t *scratch_words, uint64_t *n_seg_out, int order_stats, int sm_count, cudaStream_t stream);
 // distinct_functions[f] += kept rows whose function_index is f (src/signature_build.tcc:286), from the finished
 // table's column; max_function = largest function index any protein of the job carries.
 cudaError_t launch_function_histogram(const uint16_t *function_index, const uint64_t *n_kept_ptr, uint64_t capacity,
                                       uint32_t max_function, uint32_t *distinct_functions, int sm_count, cudaStream_t stream);
 // median / var of the groups listed in `work`, patched into their rows.
-cudaError_t launch_order_stats(const uint32_t *vals, const ProtMeta *meta, const OrderWork *work, const uint32_t *n_work,
+cudaError_t launch_order_stats(const uint32_t *vals, MetaTable meta, const OrderWork *work, const uint32_t *n_work,
                                uint32_t *next_work, const OrderWork *work_long, const uint32_t *n_work_long, uint32_t *next_long,
                                uint64_t capacity, uint4 *rows, int sm_count, cudaStream_t stream);
 // Compaction: kept rows -> table columns (tombstones dropped, order kept).  scratch_words: the buffer the

@@ -53,6 +53,16 @@ SIGK_D unsigned mask_range(unsigned lo, unsigned hi) {                     // bi
     return upper & ~((1u << lo) - 1u);
 }
 
+// The per-protein table comes in two widths (kernels.h): 8 bytes {length, function}, or 4 bytes
+// length | function << 16 when every protein of the job is shorter than 65 535 residues (half the
+// footprint: what decides whether the gathers stay in L2 once several ranks' proteins are in it).
+template <typename MetaT> SIGK_D ProtMeta load_meta(const MetaT *__restrict__ meta, uint32_t ordinal);
+template <> SIGK_D ProtMeta load_meta<ProtMeta>(const ProtMeta *__restrict__ meta, uint32_t ordinal) { return __ldg(meta + ordinal); }
+template <> SIGK_D ProtMeta load_meta<uint32_t>(const uint32_t *__restrict__ meta, uint32_t ordinal) {
+    const uint32_t v = __ldg(meta + ordinal);
+    return make_uint2(v & 0xFFFFu, v >> 16);
+}
+
 SIGK_D bool keep_rule(uint32_t best_count, uint32_t count) {
     if (2ull * best_count <= count) return false;                          // no strict majority (see header)
     // reject iff (float)best_count < float(count) * 0.8f (tcc:250-257).  0.8*count is at least 0.2
@@ -79,8 +89,9 @@ struct SegResult {
 // walk 1 votes, walk 2 counts the candidate, sums its lengths and finds the offset bits that vary,
 // then one walk per varying offset bit for the radix select (inside a family the offsets rarely
 // differ in more than a few bits; none when they are all equal).
+template <typename MetaT>
 SIGK_D SegResult reduce_long_segment(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-                                     const ProtMeta *__restrict__ meta, uint64_t start, uint32_t n, uint32_t *prot_rejected) {
+                                     const MetaT *__restrict__ meta, uint64_t start, uint32_t n, uint32_t *prot_rejected) {
     const unsigned lane = threadIdx.x & 31u;
     SegResult r{false, false, 0, 0, 0, 0, 0};
     // walk 1: bit-sliced majority vote over func_index; lane b owns bit b
@@ -88,7 +99,7 @@ SIGK_D SegResult reduce_long_segment(const uint64_t *__restrict__ keys, const ui
     for (uint32_t base = 0; base < n; base += 32) {
         const uint32_t j = base + lane;
         const bool act = j < n;
-        const uint32_t f = act ? __ldg(&meta[vals[start + j]]).y : 0u;
+        const uint32_t f = act ? load_meta(meta, vals[start + j]).y : 0u;
 #pragma unroll
         for (int b = 0; b < 16; ++b) {
             const unsigned bal = __ballot_sync(FULL, act && ((f >> b) & 1u));
@@ -102,7 +113,7 @@ SIGK_D SegResult reduce_long_segment(const uint64_t *__restrict__ keys, const ui
     for (uint32_t base = 0; base < n; base += 32) {
         const uint32_t j = base + lane;
         if (j < n) {
-            const ProtMeta m = __ldg(&meta[vals[start + j]]);
+            const ProtMeta m = load_meta(meta, vals[start + j]);
             if (m.y == cand) { ++best; S += m.x; lmin = min(lmin, m.x); lmax = max(lmax, m.x); }
             vary |= sigk_key_offset(keys[start + j]) ^ off0;
         }
@@ -206,10 +217,10 @@ SIGK_D uint4 singleton_row(uint64_t key, const ProtMeta m) {
 #ifndef SIGK_HS_MIN_BLOCKS
 #define SIGK_HS_MIN_BLOCKS 4
 #endif
-template <bool EMIT>
+template <bool EMIT, typename MetaT>
 __global__ void __launch_bounds__(HS_THREADS, SIGK_HS_MIN_BLOCKS)
 head_tile_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, const uint64_t *__restrict__ n_ptr,
-                 const ProtMeta *__restrict__ meta, uint4 *__restrict__ rows, OrderWork *__restrict__ groups,
+                 const MetaT *__restrict__ meta, uint4 *__restrict__ rows, OrderWork *__restrict__ groups,
                  OrderWork *__restrict__ long_groups, uint32_t *__restrict__ n_long, ReduceScratch sx) {
     __shared__ uint32_t s_scan[HS_WARPS + 2];
     __shared__ uint64_t s_last[HS_WARPS];
@@ -266,7 +277,7 @@ head_tile_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__
     ProtMeta m[HS_ITEMS];
     if (EMIT) {
 #pragma unroll
-        for (int i = 0; i < HS_ITEMS; ++i) m[i] = ((hmask >> i) & 1u) ? __ldg(meta + v[i]) : make_uint2(0, 0);
+        for (int i = 0; i < HS_ITEMS; ++i) m[i] = ((hmask >> i) & 1u) ? load_meta(meta, v[i]) : make_uint2(0, 0);
     }
 
     // next head after this thread's records (local position), HS_NONE if the tile has none
@@ -388,8 +399,9 @@ tile_scan_kernel(const uint64_t *__restrict__ n_ptr, ReduceScratch sx, uint64_t 
 
 // Groups that ran past the end of their tile (always the tile's last head): the next head is the first
 // head of the next tile that has one (tile_first, 0 = none), or the end of the records.
+template <typename MetaT>
 __global__ void resolve_open_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-                                    const uint64_t *__restrict__ n_ptr, const ProtMeta *__restrict__ meta, ReduceScratch sx,
+                                    const uint64_t *__restrict__ n_ptr, const MetaT *__restrict__ meta, ReduceScratch sx,
                                     uint4 *__restrict__ rows, OrderWork *__restrict__ groups, uint32_t *__restrict__ n_groups,
                                     OrderWork *__restrict__ long_groups, uint32_t *__restrict__ n_long) {
     const uint64_t n = *n_ptr;
@@ -407,7 +419,7 @@ __global__ void resolve_open_kernel(const uint64_t *__restrict__ keys, const uin
     }
     const uint32_t cnt = (uint32_t)(end - start);
     if (cnt == 1) {
-        const ProtMeta m = __ldg(meta + __ldg(vals + start));
+        const ProtMeta m = load_meta(meta, __ldg(vals + start));
         rows[g] = singleton_row(__ldg(keys + start), m);
     } else if (cnt <= 32) {
         groups[atomicAdd(n_groups, 1u)] = OrderWork{g, start, cnt};
@@ -419,8 +431,9 @@ __global__ void resolve_open_kernel(const uint64_t *__restrict__ keys, const uin
 // ---- stage 3b: groups of 2..32 records, packed 32 records to a warp ---------------------------
 // A warp takes 32 descriptors, lays their records side by side (lane = record, whole groups only)
 // and reduces all groups of the window at once with ballots and segmented shuffles.
+template <typename MetaT>
 __global__ void __launch_bounds__(RED_THREADS)
-group_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, const ProtMeta *__restrict__ meta,
+group_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, const MetaT *__restrict__ meta,
                     const OrderWork *__restrict__ groups, const uint32_t *__restrict__ n_groups, uint32_t *__restrict__ next_group,
                     const OrderWork *__restrict__ long_groups, const uint32_t *__restrict__ n_long, uint32_t *__restrict__ next_long,
                     uint4 *__restrict__ rows, OrderWork *__restrict__ work, uint32_t *__restrict__ n_work,
@@ -497,7 +510,7 @@ group_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
             const uint64_t p = (uint64_t)gstart + (lane - s_lane);
             const uint64_t key = act ? __ldg(keys + p) : 0ull;
             const uint32_t ord = act ? __ldg(vals + p) : 0u;
-            const ProtMeta m = act ? __ldg(meta + ord) : make_uint2(0, 0);          // len, func
+            const ProtMeta m = act ? load_meta(meta, ord) : make_uint2(0, 0);           // len, func
             const uint32_t f = m.y;
             const uint32_t off = sigk_key_offset(key);
 
@@ -672,8 +685,9 @@ squeeze_rows_kernel(const uint4 *__restrict__ rows, const uint64_t *__restrict__
 constexpr int ORD_THREADS = 128;
 constexpr int ORD_BLOCK = 64;       // work entries a warp takes per fetch
 
+template <typename MetaT>
 __global__ void __launch_bounds__(ORD_THREADS)
-order_stats_kernel(const uint32_t *__restrict__ vals, const ProtMeta *__restrict__ meta, const OrderWork *__restrict__ work,
+order_stats_kernel(const uint32_t *__restrict__ vals, const MetaT *__restrict__ meta, const OrderWork *__restrict__ work,
                    const uint32_t *__restrict__ n_work, uint32_t *__restrict__ next, uint4 *__restrict__ rows) {
     const uint32_t total = *n_work;
     const unsigned lane = threadIdx.x & 31u;
@@ -706,7 +720,7 @@ order_stats_kernel(const uint32_t *__restrict__ vals, const ProtMeta *__restrict
                     if (w.count) {                                         // count 0: an unused reserved slot
                         row = w.row; start = w.start; left = w.count;
                         cand = rows[w.row].z & 0xFFFFu;
-                        m_next = __ldg(meta + __ldg(vals + start + left - 1));
+                        m_next = load_meta(meta, __ldg(vals + start + left - 1));
                         acc = LengthAcc();
                         active = true;
                     }
@@ -719,7 +733,7 @@ order_stats_kernel(const uint32_t *__restrict__ vals, const ProtMeta *__restrict
             // newest first: the multimap iterates a key's items in reverse insertion order
             --left;
             const ProtMeta m = m_next;
-            if (left) m_next = __ldg(meta + __ldg(vals + start + left - 1));
+            if (left) m_next = load_meta(meta, __ldg(vals + start + left - 1));
             if (m.y == cand) acc.push(m.x);                            // acc(item.protein_length), tcc:271
             if (left == 0) {
                 rows[row].w = u16_from_double(acc.q2) | (u16_from_double(acc.var) << 16);   // tcc:278-279
@@ -733,8 +747,9 @@ order_stats_kernel(const uint32_t *__restrict__ vals, const ProtMeta *__restrict
 // the warp fetches 32 records at a time (coalesced values, 32 meta gathers in flight, the next
 // batch prefetched) and every lane runs the same accumulator on shuffled samples, so a group no
 // longer pays two dependent memory latencies per record (524 ms -> see profiles/ on the Zipf set).
+template <typename MetaT>
 __global__ void __launch_bounds__(128)
-order_stats_long_kernel(const uint32_t *__restrict__ vals, const ProtMeta *__restrict__ meta, const OrderWork *__restrict__ work,
+order_stats_long_kernel(const uint32_t *__restrict__ vals, const MetaT *__restrict__ meta, const OrderWork *__restrict__ work,
                         const uint32_t *__restrict__ n_work, uint32_t *__restrict__ next, uint4 *__restrict__ rows) {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t total = *n_work;
@@ -748,10 +763,10 @@ order_stats_long_kernel(const uint32_t *__restrict__ vals, const ProtMeta *__res
         LengthAcc acc;          // every lane carries the same state
         // newest first: batch b covers records count-1-32b-lane
         int64_t j = (int64_t)w.count - 1 - (int64_t)lane;
-        ProtMeta m = j >= 0 ? __ldg(meta + __ldg(vals + (uint64_t)w.start + j)) : make_uint2(0, 0xFFFFFFFFu);
+        ProtMeta m = j >= 0 ? load_meta(meta, __ldg(vals + (uint64_t)w.start + j)) : make_uint2(0, 0xFFFFFFFFu);
         for (int64_t left = w.count; left > 0; left -= 32) {
             const int64_t jn = j - 32;
-            const ProtMeta mn = (left > 32 && jn >= 0) ? __ldg(meta + __ldg(vals + (uint64_t)w.start + jn)) : make_uint2(0, 0xFFFFFFFFu);
+            const ProtMeta mn = (left > 32 && jn >= 0) ? load_meta(meta, __ldg(vals + (uint64_t)w.start + jn)) : make_uint2(0, 0xFFFFFFFFu);
             // Per batch of 32 samples the lanes work in parallel on everything that does not depend on
             // the running state: which samples count (func == best), their running count n_i and wrapped
             // sum S_i (prefix scans), and the variance term tmp_i^2/(n_i-1) with its two divisions.  Only
@@ -845,13 +860,16 @@ __global__ void popcount_kernel(const uint32_t *__restrict__ bitmap, uint64_t n_
     if ((threadIdx.x & 31u) == 0 && c) atomicAdd(reinterpret_cast<unsigned long long *>(out), (unsigned long long)c);
 }
 
+template <typename MetaT>
 __global__ void protein_meta_kernel(const uint64_t *__restrict__ starts, const uint16_t *__restrict__ func,
-                                    const uint32_t *__restrict__ seq_id, uint32_t n_prot, ProtMeta *__restrict__ meta,
+                                    const uint32_t *__restrict__ seq_id, uint32_t n_prot, MetaT *__restrict__ meta,
                                     uint32_t *__restrict__ seqs_with_func) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_prot) return;
-    // protein_length = static_cast<unsigned int>(seq.length()), tcc:178
-    meta[i] = make_uint2((uint32_t)(starts[i + 1] - starts[i]), func[i]);
+    (void)seq_id;
+    const uint32_t len = (uint32_t)(starts[i + 1] - starts[i]);
+    if (sizeof(MetaT) == sizeof(uint32_t)) reinterpret_cast<uint32_t *>(meta)[i] = len | ((uint32_t)func[i] << 16);     // len < 65 535 (caller)
+    else reinterpret_cast<ProtMeta *>(meta)[i] = make_uint2(len, func[i]);
     if (seqs_with_func) atomicAdd(seqs_with_func + func[i], 1u);          // seqs_with_func[function_index]++, tcc:160
 }
 
@@ -874,9 +892,13 @@ cudaError_t reduce_configure() {
 }
 
 cudaError_t launch_protein_meta(const uint64_t *starts, const uint16_t *func, const uint32_t *seq_id, uint32_t n_prot,
-                                ProtMeta *meta, uint32_t *seqs_with_func, cudaStream_t stream) {
+                                MetaTable meta, uint64_t first, uint32_t *seqs_with_func, cudaStream_t stream) {
     if (n_prot == 0) return cudaSuccess;
-    protein_meta_kernel<<<(n_prot + 255) / 256, 256, 0, stream>>>(starts, func, seq_id, n_prot, meta, seqs_with_func);
+    const unsigned grid = (n_prot + 255) / 256;
+    if (meta.compact)
+        protein_meta_kernel<uint32_t><<<grid, 256, 0, stream>>>(starts, func, seq_id, n_prot, static_cast<uint32_t *>(meta.p) + first, seqs_with_func);
+    else
+        protein_meta_kernel<ProtMeta><<<grid, 256, 0, stream>>>(starts, func, seq_id, n_prot, static_cast<ProtMeta *>(meta.p) + first, seqs_with_func);
     return cudaGetLastError();
 }
 
@@ -892,42 +914,62 @@ ReduceScratch reduce_scratch(uint64_t *words, uint64_t capacity) {
     return sx;
 }
 
-cudaError_t launch_segment_reduce(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
-                                  const ProtMeta *meta, uint4 *rows, const ReduceLists &l, uint32_t *prot_rejected,
-                                  uint64_t *scratch_words, uint64_t *n_seg_out, int order_stats, int sm_count, cudaStream_t stream) {
-    if (capacity == 0) return cudaSuccess;
+template <typename MetaT>
+static cudaError_t segment_reduce_impl(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
+                                       const MetaT *meta, uint4 *rows, const ReduceLists &l, uint32_t *prot_rejected,
+                                       const ReduceScratch &sx, uint64_t *n_seg_out, int order_stats, int sm_count, cudaStream_t stream) {
     const uint64_t grid = reduce_grid(sm_count);
     const uint64_t tiles = reduce_batches(capacity);
-    const ReduceScratch sx = reduce_scratch(scratch_words, capacity);
-    head_tile_kernel<false><<<(unsigned)tiles, HS_THREADS, 0, stream>>>(keys, vals, n_ptr, meta, rows, l.groups, l.long_groups, l.n_long, sx);
+    head_tile_kernel<false, MetaT><<<(unsigned)tiles, HS_THREADS, 0, stream>>>(keys, vals, n_ptr, meta, rows, l.groups, l.long_groups, l.n_long, sx);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     tile_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(n_ptr, sx, n_seg_out, l.n_groups);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    head_tile_kernel<true><<<(unsigned)tiles, HS_THREADS, 0, stream>>>(keys, vals, n_ptr, meta, rows, l.groups, l.long_groups, l.n_long, sx);
+    head_tile_kernel<true, MetaT><<<(unsigned)tiles, HS_THREADS, 0, stream>>>(keys, vals, n_ptr, meta, rows, l.groups, l.long_groups, l.n_long, sx);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    resolve_open_kernel<<<(unsigned)((tiles + 255) / 256), 256, 0, stream>>>(keys, vals, n_ptr, meta, sx, rows, l.groups, l.n_groups,
-                                                                              l.long_groups, l.n_long);
+    resolve_open_kernel<MetaT><<<(unsigned)((tiles + 255) / 256), 256, 0, stream>>>(keys, vals, n_ptr, meta, sx, rows, l.groups, l.n_groups,
+                                                                                     l.long_groups, l.n_long);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    group_reduce_kernel<<<(unsigned)grid, RED_THREADS, 0, stream>>>(keys, vals, meta, l.groups, l.n_groups, l.next_group, l.long_groups,
-                                                                    l.n_long, l.next_long, rows, l.work, l.n_work, l.work_long,
-                                                                    l.n_work_long, prot_rejected, sx.rej_tile, order_stats);
+    group_reduce_kernel<MetaT><<<(unsigned)grid, RED_THREADS, 0, stream>>>(keys, vals, meta, l.groups, l.n_groups, l.next_group, l.long_groups,
+                                                                           l.n_long, l.next_long, rows, l.work, l.n_work, l.work_long,
+                                                                           l.n_work_long, prot_rejected, sx.rej_tile, order_stats);
     return cudaGetLastError();
 }
 
-cudaError_t launch_order_stats(const uint32_t *vals, const ProtMeta *meta, const OrderWork *work, const uint32_t *n_work,
+cudaError_t launch_segment_reduce(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
+                                  MetaTable meta, uint4 *rows, const ReduceLists &l, uint32_t *prot_rejected,
+                                  uint64_t *scratch_words, uint64_t *n_seg_out, int order_stats, int sm_count, cudaStream_t stream) {
+    if (capacity == 0) return cudaSuccess;
+    const ReduceScratch sx = reduce_scratch(scratch_words, capacity);
+    return meta.compact ? segment_reduce_impl(keys, vals, n_ptr, capacity, static_cast<const uint32_t *>(meta.p), rows, l, prot_rejected, sx,
+                                              n_seg_out, order_stats, sm_count, stream)
+                        : segment_reduce_impl(keys, vals, n_ptr, capacity, static_cast<const ProtMeta *>(meta.p), rows, l, prot_rejected, sx,
+                                              n_seg_out, order_stats, sm_count, stream);
+}
+
+template <typename MetaT>
+static cudaError_t order_stats_impl(const uint32_t *vals, const MetaT *meta, const OrderWork *work, const uint32_t *n_work,
+                                    uint32_t *next_work, const OrderWork *work_long, const uint32_t *n_work_long, uint32_t *next_long,
+                                    uint4 *rows, int sm_count, cudaStream_t stream) {
+    // the long groups first: they are the tail
+    order_stats_long_kernel<MetaT><<<sm_count * 8, 128, 0, stream>>>(vals, meta, work_long, n_work_long, next_long, rows);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    order_stats_kernel<MetaT><<<sm_count * 16, ORD_THREADS, 0, stream>>>(vals, meta, work, n_work, next_work, rows);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_order_stats(const uint32_t *vals, MetaTable meta, const OrderWork *work, const uint32_t *n_work,
                                uint32_t *next_work, const OrderWork *work_long, const uint32_t *n_work_long, uint32_t *next_long,
                                uint64_t capacity, uint4 *rows, int sm_count, cudaStream_t stream) {
     if (capacity == 0) return cudaSuccess;
-    // the long groups first: they are the tail
-    order_stats_long_kernel<<<sm_count * 8, 128, 0, stream>>>(vals, meta, work_long, n_work_long, next_long, rows);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    order_stats_kernel<<<sm_count * 16, ORD_THREADS, 0, stream>>>(vals, meta, work, n_work, next_work, rows);
-    return cudaGetLastError();
+    return meta.compact ? order_stats_impl(vals, static_cast<const uint32_t *>(meta.p), work, n_work, next_work, work_long, n_work_long,
+                                           next_long, rows, sm_count, stream)
+                        : order_stats_impl(vals, static_cast<const ProtMeta *>(meta.p), work, n_work, next_work, work_long, n_work_long,
+                                           next_long, rows, sm_count, stream);
 }
 
 cudaError_t launch_squeeze_rows(const uint4 *rows, const uint64_t *n_seg_ptr, uint64_t capacity, KeptColumns out,

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -100,8 +101,17 @@ int do_upload(sigk_handle *h) {
     h->n_prot_global = np;
     h->ordinal_base = 0;
     h->max_seq_id = h->local_max_seq_id;
+    h->max_len = h->local_max_len;
     if (h->comm) { if (int rc = comm_exchange_shapes(h)) return rc; }
-    CU(h, h->d_meta.reserve(h->n_prot_global));
+    // 4-byte table entries when every length fits 16 bits and the 8-byte table would crowd L2 (measured: the
+    // unpacking costs 0.9 ms at 2 M proteins where both forms are L2-resident, the smaller table wins 1.5 ms at
+    // 8 M proteins).  SIGK_TEST_META=compact|wide overrides the size rule (tests).
+    h->meta_compact = h->max_len < 0xFFFFull && h->n_prot_global > (4ull << 20);
+    if (const char *force = std::getenv("SIGK_TEST_META")) {
+        if (!std::strcmp(force, "compact")) h->meta_compact = h->max_len < 0xFFFFull;
+        else if (!std::strcmp(force, "wide")) h->meta_compact = false;
+    }
+    CU(h, h->d_meta.reserve(meta_bytes(h->n_prot_global, h->meta_compact)));
     CU(h, h->d_bitmap.reserve(((uint64_t)h->max_seq_id >> 5) + 1));
     CU(h, h->d_prot_windows.reserve(np));
     CU(h, h->d_prot_rejected.reserve(h->n_prot_global));
@@ -129,7 +139,8 @@ int do_build_device(sigk_handle *h) {
     CU(h, cudaMemsetAsync(h->d_hist.p, 0, SORT_MAX_PASSES * SIGK_RADIX * sizeof(uint64_t), st));
 
     // ---- stage 1: encode
-    CU(h, launch_protein_meta(h->d_starts.p, h->d_func.p, h->d_seqid.p, (uint32_t)np, h->d_meta.p + h->ordinal_base, h->d_swf.p, st)); ++launches;
+    const MetaTable meta{h->d_meta.p, h->meta_compact};
+    CU(h, launch_protein_meta(h->d_starts.p, h->d_func.p, h->d_seqid.p, (uint32_t)np, meta, h->ordinal_base, h->d_swf.p, st)); ++launches;
     if (h->comm) { if (int rc = comm_allgather_meta(h)) return rc; }
     CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, encode_scan_entries(h->total_res) * sizeof(uint64_t), st));
     EncodeArgs ea{h->d_res.p, h->total_res, h->d_starts.p, (uint32_t)np, (uint32_t)h->ordinal_base, h->d_slice_prot.p, h->d_prot_windows.p};
@@ -172,13 +183,13 @@ int do_build_device(sigk_handle *h) {
     KeptColumns kc{h->d_out_kmer.p, out_col(h, 0), out_col(h, 1), out_col(h, 2), out_col(h, 3), out_col(h, 4)};
     ReduceLists rl{h->d_groups.p, &sc->n_groups, &sc->next_group, h->d_long_groups.p, &sc->n_long, &sc->next_long,
                    h->d_work.p, &sc->n_work, h->d_work_long.p, &sc->n_work_long};
-    CU(h, launch_segment_reduce(h->d_keys[cur].p, h->d_vals[cur].p, &sc->n_records, cap, h->d_meta.p, h->d_rows.p, rl,
+    CU(h, launch_segment_reduce(h->d_keys[cur].p, h->d_vals[cur].p, &sc->n_records, cap, meta, h->d_rows.p, rl,
                                 h->d_prot_rejected.p, h->d_scan_state.p, &sc->n_segments, order_stats, h->sm_count, st)); launches += 5;
     if (h->comm) { if (int rc = comm_reduce_rejected(h)) return rc; }
     CU(h, launch_signature_flags(h->d_prot_windows.p, h->d_prot_rejected.p + h->ordinal_base, h->d_seqid.p, (uint32_t)np, h->d_bitmap.p, st)); ++launches;
     CU(h, launch_popcount(h->d_bitmap.p, ((uint64_t)h->max_seq_id >> 5) + 1, &sc->n_seqs_sig, st)); ++launches;
     CU(h, cudaEventRecord(h->ev[EV_REDUCE], st));
-    if (order_stats) { CU(h, launch_order_stats(h->d_vals[cur].p, h->d_meta.p, h->d_work.p, &sc->n_work, &sc->next_work, h->d_work_long.p, &sc->n_work_long, &sc->next_work_long, cap, h->d_rows.p, h->sm_count, st)); launches += 2; }
+    if (order_stats) { CU(h, launch_order_stats(h->d_vals[cur].p, meta, h->d_work.p, &sc->n_work, &sc->next_work, h->d_work_long.p, &sc->n_work_long, &sc->next_work_long, cap, h->d_rows.p, h->sm_count, st)); launches += 2; }
     CU(h, cudaEventRecord(h->ev[EV_ORDER], st));
     CU(h, launch_squeeze_rows(h->d_rows.p, &sc->n_segments, cap, kc, h->d_scan_state.p, &sc->n_kept, st)); launches += 2;
     // distinct_functions[best]++ per kept row (tcc:286), from the finished function_index column; with a
@@ -323,13 +334,16 @@ int sigk_set_proteins(sigk_handle *h, const sigk_proteins *p) {
     if (total >= 0xFFFFFFFFull) return h->fail(SIGK_E_UNSUPPORTED, "more than 2^32-2 residues on one GPU");
     if (np && (!p->function_index || !p->seq_id || (total && !p->residues))) return h->fail(SIGK_E_INVALID, "null protein arrays");
     uint32_t max_sid = 0, max_func = 0;
+    uint64_t max_len = 0;
     for (uint64_t i = 0; i < np; ++i) {
         if (p->starts[i + 1] < p->starts[i]) return h->fail(SIGK_E_INVALID, "starts must be non-decreasing (protein %llu)", (unsigned long long)i);
         if (p->function_index[i] == SIGK_UNDEFINED_FUNCTION)
             return h->fail(SIGK_E_INVALID, "protein %llu has UndefinedFunction; the host must skip it (src/signature_build.tcc:155)", (unsigned long long)i);
         max_sid = std::max(max_sid, p->seq_id[i]);
         max_func = std::max<uint32_t>(max_func, p->function_index[i]);
+        max_len = std::max(max_len, p->starts[i + 1] - p->starts[i]);
     }
+    h->local_max_len = max_len;
     h->local_max_function = max_func;
     h->in = *p;
     h->total_res = total;

@@ -182,6 +182,52 @@ def test_long_and_giant_groups(gpu, oracle):
     assert got.row("WWWWWWWW")["avg_from_end"] == want.row("WWWWWWWW")["avg_from_end"]
 
 
+@pytest.mark.parametrize("form", ["compact", "wide"])
+def test_both_meta_table_forms(oracle, monkeypatch, form):
+    """The per-protein table is 4 or 8 bytes wide depending on job size; both forms, forced, on the same inputs
+    (groups of every kind: single records, packed groups, whole-warp groups, ordered walks)."""
+    from signature_kmers_b200.builder import GpuSignatureBuilder
+
+    monkeypatch.setenv("SIGK_TEST_META", form)
+    seqs, funcs = random_proteins(91, n_families=50, members=(2, 40), length=(30, 400), sub_rate=0.05, n_functions=30)
+    seqs = [bytes(x) for x in seqs] + [b"W" * 600, b"W" * 500, b"W" * 77, b"Y" * 40000]
+    funcs = list(funcs) + [1, 1, 2, 3]
+    p = pack(seqs, funcs)
+    b = GpuSignatureBuilder(device=0)
+    b.set_proteins(p)
+    got = b.build()
+    want, _ = oracle.oracle_build(p)
+    assert_tables_equal(got, want, tier_b=True, what=form)
+    b.close()
+
+
+def test_proteins_longer_than_65535(gpu, oracle):
+    """A protein of 65 535 residues or more switches the per-protein table from the compact 4-byte form to the
+    8-byte one; its length enters sums (mod 65536), the equal-length shortcut and the P^2 / variance walks in full."""
+    rng = np.random.default_rng(8)
+    aa = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
+    big = bytes(rng.choice(aa, 66_000))
+    seqs = [big, big[:65_535], big[100:66_000], big[:70] + bytes(rng.choice(aa, 300))]
+    funcs = [0, 0, 0, 0]
+    fs, ff = random_proteins(78, n_families=20, members=(3, 9), length=(40, 300))
+    seqs += [big[:50] + bytes(x) for x in fs[:6]]          # short proteins sharing k-mers with the long ones
+    funcs += [0, 0, 0, 1, 0, 0]
+    seqs += list(fs)
+    funcs += [2 + f for f in ff]
+    p = pack(seqs, funcs)
+    gpu.set_proteins(p)
+    got = gpu.build()
+    want, _ = oracle.oracle_build(p)
+    assert_tables_equal(got, want, tier_b=True)
+    # and right below the threshold the compact form is used: same answers as the oracle either way
+    seqs2 = [big[:65_534]] + seqs[3:]
+    p2 = pack(seqs2, funcs[:1] + funcs[3:])
+    gpu.set_proteins(p2)
+    got2 = gpu.build()
+    want2, _ = oracle.oracle_build(p2)
+    assert_tables_equal(got2, want2, tier_b=True)
+
+
 @pytest.mark.parametrize("seed", [51, 52, 53])
 def test_boundary_alignment_sweep(gpu, oracle, seed):
     """Many small inputs whose group boundaries fall on every alignment of the
