@@ -527,7 +527,8 @@ int comm_encode_exchange(sigk_handle *h, const EncodeArgs &ea, uint32_t *launche
 
     const bool peer = c->peer_ok;
     const uint64_t cap_local = h->total_res;
-    const uint64_t stride = peer ? c->land_stride : cap_local / W + cap_local / (4 * W) + 65536;   // expected share + 25 % + slack
+    // expected share + 25 % + slack, a multiple of 64 records (the kernel stores 16 bytes at a time)
+    const uint64_t stride = peer ? c->land_stride : (cap_local / W + cap_local / (4 * W) + 65536 + 63) & ~63ull;
     if (!peer) { CU(h, h->d_keys[1].reserve((size_t)stride * W)); CU(h, h->d_vals[1].reserve((size_t)stride * W)); }
     const size_t state_words = (size_t)encode_slices(h->total_res) * W + W;
     CU(h, c->d_owner_state.reserve(state_words));

@@ -164,9 +164,7 @@ encode_kernel(EncodeArgs a, uint64_t *__restrict__ keys, uint32_t *__restrict__ 
 struct EncSplitSmem {
     uint64_t keys[ENC_WARPS][ENC_STAGE];
     uint32_t vals[ENC_WARPS][ENC_STAGE];
-    uint8_t owner[ENC_WARPS][ENC_STAGE];
     uint32_t obase[ENC_WARPS][16];          // first staging slot of each owner inside the warp
-    uint64_t gbase[ENC_WARPS][16];          // position in the owner's region of staging slot 0 of that owner, minus obase
     uint64_t split[16];
     uint64_t *dkeys[16];
     uint32_t *dvals[16];
@@ -310,7 +308,6 @@ encode_split_kernel(EncodeArgs a, const __grid_constant__ EncodeSplitArgs sp, ui
                 bump16(run, d);
                 sm.keys[warp][slot] = sigk_pack_key(code, (unsigned)(prot_end - g));
                 sm.vals[warp][slot] = a.ordinal_base + i;
-                sm.owner[warp][slot] = (uint8_t)d;
                 if (i != run_i) {
                     if (run_c && a.prot_windows) atomicAdd(a.prot_windows + run_i, run_c);
                     run_i = i; run_c = 0;
@@ -322,8 +319,8 @@ encode_split_kernel(EncodeArgs a, const __grid_constant__ EncodeSplitArgs sp, ui
     }
 
     // resolve: lane d walks back over the earlier slices of owner d
+    uint64_t before = 0;
     if (lane < W) {
-        uint64_t before = 0;
         if (sub > 0) {
             int64_t t = (int64_t)sub - 1;
             for (;;) {
@@ -338,16 +335,45 @@ encode_split_kernel(EncodeArgs a, const __grid_constant__ EncodeSplitArgs sp, ui
         }
         if (before + t_d > sp.region_stride) atomicOr(sp.overflow, 1u);
         if (last_sub) sp.owner_totals[lane] = before + t_d;
-        sm.gbase[warp][lane] = before - ob;
     }
     __syncwarp();
     if (*reinterpret_cast<volatile uint32_t *>(sp.overflow)) return;      // regions too small: the caller falls back
-    for (uint32_t o = lane; o < total; o += 32) {
-        const int slot = stage_slot((int)o);
-        const uint32_t d = sm.owner[warp][slot];
-        const uint64_t pos = sm.gbase[warp][d] + o;
-        sm.dkeys[d][pos] = sm.keys[warp][slot];
-        sm.dvals[d][pos] = sm.vals[warp][slot];
+
+    // One owner at a time: its records are a contiguous run of the staging area and go to a contiguous run
+    // of the owner's region.  The body of every run leaves as 16-byte stores (two keys / four values per
+    // lane) — what a peer GPU's region needs to be fed at NVLink rate; the unaligned ends go out singly.
+    for (uint32_t d = 0; d < W; ++d) {
+        const uint32_t len = __shfl_sync(0xffffffffu, t_d, d);
+        if (len == 0) continue;
+        const uint32_t s0 = __shfl_sync(0xffffffffu, ob, d);
+        const uint64_t dst0 = __shfl_sync(0xffffffffu, before, d);
+        uint64_t *dk = sm.dkeys[d] + dst0;
+        uint32_t *dv = sm.dvals[d] + dst0;
+        const uint32_t hk = (uint32_t)(dst0 & 1u);                        // keys before the first 16-byte boundary
+        if (lane == 0 && hk) dk[0] = sm.keys[warp][stage_slot((int)s0)];
+        const uint32_t pairs = (len - hk) >> 1;
+        for (uint32_t q = lane; q < pairs; q += 32) {
+            const uint32_t o = s0 + hk + 2 * q;
+            ulonglong2 v;
+            v.x = sm.keys[warp][stage_slot((int)o)];
+            v.y = sm.keys[warp][stage_slot((int)o + 1)];
+            *reinterpret_cast<ulonglong2 *>(dk + hk + 2 * q) = v;
+        }
+        if (lane == 0 && ((len - hk) & 1u)) dk[len - 1] = sm.keys[warp][stage_slot((int)(s0 + len - 1))];
+        const uint32_t hv = min(len, (uint32_t)((4u - (uint32_t)(dst0 & 3u)) & 3u));
+        if (lane < hv) dv[lane] = sm.vals[warp][stage_slot((int)(s0 + lane))];
+        const uint32_t quads = (len - hv) >> 2;
+        for (uint32_t q = lane; q < quads; q += 32) {
+            const uint32_t o = s0 + hv + 4 * q;
+            uint4 v;
+            v.x = sm.vals[warp][stage_slot((int)o)];
+            v.y = sm.vals[warp][stage_slot((int)o + 1)];
+            v.z = sm.vals[warp][stage_slot((int)o + 2)];
+            v.w = sm.vals[warp][stage_slot((int)o + 3)];
+            *reinterpret_cast<uint4 *>(dv + hv + 4 * q) = v;
+        }
+        const uint32_t tv = (len - hv) & 3u;
+        if (lane < tv) dv[len - tv + lane] = sm.vals[warp][stage_slot((int)(s0 + len - tv + lane))];
     }
 }
 
