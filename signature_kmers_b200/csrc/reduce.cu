@@ -225,6 +225,7 @@ head_tile_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__
     __shared__ uint32_t s_scan[HS_WARPS + 2];
     __shared__ uint64_t s_last[HS_WARPS];
     __shared__ uint32_t s_wfirst[HS_WARPS];
+    __shared__ uint4 s_rows[EMIT ? RED_BATCH : 1];
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint64_t n = *n_ptr;
     constexpr uint64_t NO_CODE = ~0ull;                  // codes are < 2^43
@@ -323,24 +324,34 @@ head_tile_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__
         }
         return;
     }
-    uint64_t g = (base & 0xFFFFFFFFull) + (excl & 0xFFFFu);
+    // The tile's rows are contiguous (one per head): they are assembled in shared memory and leave as whole
+    // 512-byte warp stores.  Slots of groups that are not finished here get a tombstone for now; the kernel
+    // that finishes them (group_reduce_kernel, resolve_open_kernel) runs later and overwrites it.
+    const uint64_t g0 = base & 0xFFFFFFFFull;
+    uint32_t gl = excl & 0xFFFFu;                        // row slot inside the tile
     uint32_t gslot = (uint32_t)(base >> 32) + (excl >> 16);
 #pragma unroll
     for (int i = 0; i < HS_ITEMS; ++i) {
         if ((hmask >> i) & 1u) {
             const uint32_t p = (uint32_t)(tile_start + t0 + i);
             if (cnt[i] == 1) {
-                rows[g] = singleton_row(k[i], m[i]);
-            } else if (cnt[i] == 0) {
-                // closed by resolve_open_kernel
-            } else if (cnt[i] <= 32) {
-                groups[gslot++] = OrderWork{(uint32_t)g, p, cnt[i]};
+                s_rows[gl] = singleton_row(k[i], m[i]);
             } else {
-                long_groups[atomicAdd(n_long, 1u)] = OrderWork{(uint32_t)g, p, cnt[i]};
+                s_rows[gl] = make_uint4(0u, 0u, 0xFFFFu, 0u);
+                if (cnt[i] == 0) {
+                    // closed by resolve_open_kernel
+                } else if (cnt[i] <= 32) {
+                    groups[gslot++] = OrderWork{(uint32_t)(g0 + gl), p, cnt[i]};
+                } else {
+                    long_groups[atomicAdd(n_long, 1u)] = OrderWork{(uint32_t)(g0 + gl), p, cnt[i]};
+                }
             }
-            ++g;
+            ++gl;
         }
     }
+    __syncthreads();
+    const uint32_t n_rows = total & 0xFFFFu;
+    for (uint32_t j = tid; j < n_rows; j += HS_THREADS) rows[g0 + j] = s_rows[j];
 }
 
 // Exclusive scan of `count` per-tile counters by one block, written for coalesced access: warp w owns the
