@@ -411,12 +411,9 @@ cudaError_t launch_encode_split(const EncodeArgs &a, const EncodeSplitArgs &sp, 
 cudaError_t launch_encode(const EncodeArgs &a, uint64_t *keys, uint32_t *vals, uint64_t *scan_state,
                           uint32_t *ticket, uint64_t *n_out, cudaStream_t stream) {
     if (a.total_res == 0 || a.n_prot == 0) return cudaSuccess;   // n_out stays 0
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    // per device, so set on every launch (a process may drive several devices through several handles)
+    cudaError_t attr = cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
+    if (attr != cudaSuccess) return attr;
     const uint64_t tiles = encode_tiles(a.total_res);
     encode_kernel<<<(unsigned)tiles, ENC_THREADS, sizeof(EncSmem), stream>>>(a, keys, vals, scan_state, ticket, n_out);
     return cudaGetLastError();

@@ -997,12 +997,9 @@ cudaError_t launch_squeeze_rows(const uint4 *rows, const uint64_t *n_seg_ptr, ui
 cudaError_t launch_function_histogram(const uint16_t *function_index, const uint64_t *n_kept_ptr, uint64_t capacity,
                                       uint32_t max_function, uint32_t *distinct_functions, int sm_count, cudaStream_t stream) {
     if (capacity == 0) return cudaSuccess;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(function_histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_BINS * (int)sizeof(uint32_t));
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    // per device, so set on every launch (a process may drive several devices through several handles)
+    cudaError_t attr = cudaFuncSetAttribute(function_histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_BINS * (int)sizeof(uint32_t));
+    if (attr != cudaSuccess) return attr;
     const int n_ranges = max_function >= (uint32_t)FH_BINS ? 2 : 1;
     const uint64_t want = (capacity / 8 + FH_THREADS - 1) / FH_THREADS + 1;
     const unsigned chunks = (unsigned)std::min<uint64_t>((uint64_t)sm_count, want);
