@@ -2,7 +2,8 @@
 independently of oracle/sigk_oracle.cpp so the two can check each other.
 
 TEST INFRASTRUCTURE ONLY (see oracle/sigk_oracle.h); small inputs only.
-PARITY UNPINNED: the reference has no golden vectors and cannot be built here.
+PARITY: pinned through oracle/sigk_oracle.cpp (see sigk_oracle.h); UNPINNED against a stock reference run for the
+Boost/TBB internals — the reference has no golden vectors and cannot be built as a whole here.
 
 Follows the reference's src/signature_build.tcc:
   load_kmers_from_sequence  :120-181

@@ -1,6 +1,8 @@
 /*
  * sigk_oracle.cpp — CPU restatement of the reference's signature-generation
- * hot path.  TEST INFRASTRUCTURE ONLY; PARITY UNPINNED (see sigk_oracle.h).
+ * hot path.  TEST INFRASTRUCTURE ONLY.  Pinned against the reference's own sources compiled over
+ * stand-in third-party headers (oracle/ref_signature_shim.cpp, tests/test_reference_shim.py);
+ * PARITY UNPINNED against a stock reference run for the Boost/TBB internals (see sigk_oracle.h).
  *
  * Follows, function by function (paths relative to the reference checkout):
  *   extract()            src/signature_build.tcc:47-70   (extract_kmers)

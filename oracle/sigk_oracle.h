@@ -6,19 +6,22 @@
  * --impl reference legs may build, load or call it, and only as the checker
  * or the reported CPU baseline.  libsigk never links or calls it.
  *
- * PARITY UNPINNED: the reference (olsonanl/signature_kmers) ships no tests,
- * fixtures or golden vectors for this path and cannot be built in this image
- * (Boost, TBB, cmph and NuDB are absent).  This file restates
- * src/signature_build.tcc:120-293 of the reference plus the published
- * algorithms of the two third-party pieces the path's arithmetic lives in:
- *   - Boost.Accumulators (version unpinned by the reference, Makefile:53):
- *     sum / mean / median (= P-square quantile estimator, p = 0.5) / variance
- *     (the iterative form) on an accumulator_set<unsigned short, ...>;
- *   - TBB <= 2020 concurrent_unordered_multimap insertion order (equal keys
- *     iterate newest-first).
- * It is pinned by the hand-derived known-answer tests of tests/test_oracle_kat.py
- *  and by an independent pure-Python restatement
- * (oracle/oracle_py.py).
+ * PARITY STATUS.  The reference (olsonanl/signature_kmers) ships no tests, fixtures or golden
+ * vectors for this path and cannot be built as a whole in this image (Boost, TBB, cmph and NuDB
+ * are absent).  This file restates src/signature_build.tcc:120-293 of the reference.
+ *   PINNED: against the reference's own sources (signature_build.{h,tcc}, function_map.h,
+ *     seed_utils.h, fasta_parser.cc) compiled unmodified over the stand-in third-party headers of
+ *     oracle/refshim/ into oracle/_ref/libref_signature.so — every row, column and counter on
+ *     synthetic and hand-made trees (tests/test_reference_shim.py); by the hand-derived known-answer
+ *     tests of tests/test_oracle_kat.py; and by an independent
+ *     pure-Python restatement (oracle/oracle_py.py).
+ *   UNPINNED against a stock reference run: the published algorithms of the two third-party pieces
+ *     the path's arithmetic lives in, restated here and in the stand-ins alike:
+ *     - Boost.Accumulators (version unpinned by the reference, Makefile:53):
+ *       sum / mean / median (= P-square quantile estimator, p = 0.5) / variance
+ *       (the iterative form) on an accumulator_set<unsigned short, ...>;
+ *     - TBB <= 2020 concurrent_unordered_multimap insertion order (equal keys
+ *       iterate newest-first).
  *
  * The types are shared with include/sigk.h so that tests compare like with like.
  */

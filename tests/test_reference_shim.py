@@ -1,0 +1,180 @@
+"""Pins the CPU oracle (and the drop-in's host gating) against the REFERENCE'S OWN signature builder:
+oracle/_ref/libref_signature.so is /root/reference/src/signature_build.{h,tcc} + function_map.h + seed_utils.h +
+fasta_parser.cc compiled unmodified over stand-in Boost/TBB headers (oracle/refshim/README.md says what that does and
+does not pin).  Inputs are directory trees, as the reference's command line takes them; the oracle sees the packed
+proteins the drop-in command line derives from the same tree.  The library is prebuilt here (make -C oracle ref) and
+travels to the GPU box; without it these tests skip."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle_c
+from signature_kmers_b200.capi import PackedProteins
+from signature_kmers_b200.synth import Synth
+from tests.test_host_dropin import read_packed
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "signature_kmers_b200")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_signature.so")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not os.path.exists(REF_SO):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], capture_output=True)
+    if not os.path.exists(REF_SO):
+        pytest.skip("oracle/_ref/libref_signature.so not built (reference checkout absent)")
+    if not os.path.exists(os.path.join(PKG, "libsigk.so")):
+        import __graft_entry__ as g
+        g.build()
+    subprocess.run(["make", "-C", os.path.join(PKG, "host")], check=True, capture_output=True)
+    lib = C.CDLL(REF_SO)
+    lib.ref_signature_build.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p,
+                                        C.POINTER(C.c_ulonglong), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+    return lib
+
+
+def read_table(path):
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"SIGKTBL1"
+    n = int(np.frombuffer(raw, dtype=np.uint64, count=1, offset=8)[0])
+    kmers = [raw[16 + 8 * i: 24 + 8 * i].decode("latin-1") for i in range(n)]
+    off = 16 + 8 * n
+    cols = [np.frombuffer(raw, dtype=np.uint16, count=n, offset=off + 2 * n * c) for c in range(5)]
+    return kmers, cols
+
+
+def run_reference(ref, tree, out, deleted="", min_reps=3):
+    os.makedirs(out, exist_ok=True)
+    counters = (C.c_ulonglong * 3)()
+    df = (C.c_uint * 65536)()
+    swf = (C.c_uint * 65536)()
+    rc = ref.ref_signature_build(os.path.join(tree, "Annotations", "0").encode(), os.path.join(tree, "Seqs").encode(), deleted.encode(),
+                                 min_reps, 1, str(out).encode(), counters, df, swf)
+    assert rc == 0
+    kmers, cols = read_table(os.path.join(out, "ref_table.bin"))
+    return kmers, cols, list(counters), np.array(df), np.array(swf)
+
+
+def run_oracle_through_dropin(tree, out, tmp, deleted="", min_reps=3):
+    """The drop-in command line does the host side (FunctionMap, gates, packing); the oracle does the build."""
+    dump = os.path.join(tmp, "packed.bin")
+    cmd = [os.path.join(PKG, "kmers-build-signatures"), "-D", os.path.join(tree, "Annotations", "0"), "-F", os.path.join(tree, "Seqs"),
+           "--kmer-data-dir", str(out), "--min-reps-required", str(min_reps), "--sorted-files", "--dump-packed", dump]
+    if deleted:
+        cmd += ["--deleted-features-file", deleted]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    res, starts, func, sid = read_packed(dump)
+    table, _ = oracle_c.oracle_build(PackedProteins(res.copy(), starts.copy(), func.copy(), sid.copy()))
+    return table
+
+
+def assert_same(refres, table, what):
+    kmers, cols, counters, df, swf = refres
+    assert table.kmer_strings() == kmers, what
+    for name, c in zip(("avg_from_end", "function_index", "mean", "median", "var"), cols):
+        np.testing.assert_array_equal(getattr(table, name), c, err_msg="%s: %s" % (what, name))
+    assert counters == [table.n_kept, table.distinct_signatures, table.num_seqs_with_a_signature], what
+    np.testing.assert_array_equal(table.distinct_functions, df, err_msg=what)
+    np.testing.assert_array_equal(table.seqs_with_func, swf, err_msg=what)
+
+
+def function_index_names(path):
+    return [l.split("\t")[:2] for l in open(path).read().splitlines()]
+
+
+@pytest.mark.parametrize("seed,n_proteins,n_functions,genomes,zipf", [(61, 1500, 60, 5, 0.0), (62, 1200, 40, 4, 1.1), (63, 400, 90, 3, 0.0)])
+def test_oracle_equals_reference_sources_on_synthetic_trees(ref, tmp_path, seed, n_proteins, n_functions, genomes, zipf):
+    s = Synth(n_proteins=n_proteins, n_functions=n_functions, n_genomes=genomes, seed=seed, zipf_s=zipf)
+    tree = str(tmp_path / "tree")
+    s.write_tree(tree)
+    refres = run_reference(ref, tree, str(tmp_path / "ref_out"))
+    table = run_oracle_through_dropin(tree, tmp_path / "our_out", str(tmp_path))
+    assert len(refres[0]) > 1000
+    assert_same(refres, table, "synthetic seed %d" % seed)
+    assert function_index_names(tmp_path / "ref_out" / "function.index") == function_index_names(tmp_path / "our_out" / "function.index")
+
+
+def write_tree(root, genomes):
+    """genomes: {name: [(id, function or None, sequence)]} -> Annotations/0/<name> + Seqs/<name>"""
+    os.makedirs(os.path.join(root, "Annotations", "0"))
+    os.makedirs(os.path.join(root, "Seqs"))
+    for g, recs in genomes.items():
+        with open(os.path.join(root, "Annotations", "0", g), "w") as a, open(os.path.join(root, "Seqs", g), "w") as f:
+            for rid, fn, seq in recs:
+                if fn is not None:
+                    a.write("%s\t%s\n" % (rid, fn))
+                f.write(">%s\n%s\n" % (rid, seq))
+
+
+def test_oracle_equals_reference_sources_on_edge_cases(ref, tmp_path):
+    """Hand-made tree: the 80 % rule at its boundary, ties, ambiguity codes and case, proteins shorter than K,
+    proteins without / with un-kept functions (seq_id arithmetic), a deleted feature, comments in assignments,
+    a 16-bit length-sum wrap and groups long enough for the P^2 markers to move."""
+    core = "MKTAYIAKQRQISFVKSHFSRQLEERLGLIEV"
+    other = "GSHMLEDPVAGTWQNCYRFKAGDTLSKIAEEH"
+    genomes = {}
+    for gi in range(4):
+        g = "1000%d.1" % gi
+        recs = []
+        n = 0
+
+        def add(fn, seq):
+            nonlocal n
+            n += 1
+            recs.append(("fig|%s.peg.%d" % (g, n), fn, seq))
+
+        add("Alpha synthase", core + "ACDEFGHIKLMNPQRS" * (gi + 1))          # lengths differ per genome
+        add("Alpha synthase # frameshift", core[:20] + "WWWWWWWWWW")            # comment stripped, same function
+        add("Beta kinase", other + core[:12])                                   # shares k-mers with Alpha: 80 % rule
+        add("Beta kinase", other[:10] + "X" + other[11:] + "acdefghikl")        # X kills windows, lower case is valid
+        add("Gamma lyase", "ACDEFGH")                                           # shorter than K: nothing
+        add(None, core)                                                         # no assignment: skipped, no seq_id
+        add("Rare thing %d" % gi, core[5:25])                                   # function in one genome only: not kept, still a seq_id
+        add("Delta ligase", ("QWERTYIPASDFGHKLCVNM" * 4)[: 60 + gi])
+        add("hypothetical protein", other + "TTTTTTTTTTTT")
+        for rep in range(70):                                                    # 280 copies job-wide: the length sum wraps
+            add("Epsilon pump", "HHHHHHHHKKKKKKKK" + "ACDEFGHIKLMNPQRSTVWY" * (10 + (rep * 7 + gi) % 9))
+        genomes[g] = recs
+    tree = str(tmp_path / "tree")
+    write_tree(tree, genomes)
+    deleted = str(tmp_path / "deleted.txt")
+    with open(deleted, "w") as f:
+        f.write("fig|10001.1.peg.3\n")
+    for dfile in ("", deleted):
+        refres = run_reference(ref, tree, str(tmp_path / ("ref_out%d" % bool(dfile))), deleted=dfile)
+        table = run_oracle_through_dropin(tree, tmp_path / ("our_out%d" % bool(dfile)), str(tmp_path), deleted=dfile)
+        assert_same(refres, table, "edge cases, deleted=%r" % dfile)
+        kmers = refres[0]
+        assert "HHHHHHHH" in kmers and "acdefghi" in kmers and not any("X" in k for k in kmers)
+
+
+@pytest.mark.gpu
+def test_gpu_command_line_equals_reference_sources(ref, tmp_path):
+    """The whole drop-in (host gating + GPU build) against the reference's own builder on the same tree:
+    every row and column of the kept table (median and var included: the reference runs single-threaded here,
+    i.e. in canonical order), the printed counters and the per-function statistics."""
+    s = Synth(n_proteins=4000, n_functions=120, n_genomes=6, seed=64)
+    tree = str(tmp_path / "tree")
+    s.write_tree(tree)
+    kmers, cols, counters, df, swf = run_reference(ref, tree, str(tmp_path / "ref_out"))
+    out = tmp_path / "gpu_out"
+    r = subprocess.run([os.path.join(PKG, "kmers-build-signatures"), "-D", os.path.join(tree, "Annotations", "0"), "-F", os.path.join(tree, "Seqs"),
+                        "--kmer-data-dir", str(out), "--final-kmers", "final.kmers", "--sorted-files", "--sigk-table", "kmer_data.sigk", "--no-recall"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    gk, gcols = read_table(out / "kmer_data.sigk")
+    assert gk == kmers
+    for name, a, b in zip(("avg_from_end", "function_index", "mean", "median", "var"), gcols, cols):
+        np.testing.assert_array_equal(a, b, err_msg=name)
+    assert "Kept %d kmers" % counters[0] in r.stdout
+    assert "distinct_signatures=%d" % counters[1] in r.stdout
+    assert "num_seqs_with_a_signature=%d" % counters[2] in r.stdout
+    got_df = {int(l.split("\t")[0]): int(l.split("\t")[2]) for l in open(out / "distinct_functions").read().splitlines()}
+    assert got_df == {i: int(c) for i, c in enumerate(df) if c}
+    rows = [l.split("\t") for l in open(out / "final.kmers").read().splitlines()]
+    assert [x[0] for x in rows] == kmers and [int(x[1]) for x in rows] == [int(v) for v in cols[0]]
