@@ -5,6 +5,8 @@ namespace tbb {
 template <class T> class concurrent_vector : public std::vector<T> {
 public:
     using std::vector<T>::vector;
+    // tbb's push_back returns an iterator to the new element
+    typename std::vector<T>::iterator push_back(const T &v) { std::vector<T>::push_back(v); return this->end() - 1; }
     struct range_type {
         typename std::vector<T>::iterator b, e;
         auto begin() const { return b; }

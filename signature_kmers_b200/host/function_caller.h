@@ -14,8 +14,10 @@
 // vectors (src/call_functions.tcc:49-51).  Boost is absent here, so those three are restated from the
 // published algorithms (mean: four running means, Boost.Math >= 1.72 single_pass.hpp; median and MAD by
 // selection, exact for any order).  Only the mean can differ from another Boost version, and only in the
-// last ulp of a cut-off compared with the protein length — parity for this piece is UNPINNED against a
-// reference run; tests/test_function_caller.py compares against an independent Python restatement.
+// last ulp of a cut-off compared with the protein length — parity for that piece is UNPINNED against a
+// stock reference run.  The logic itself is pinned: tests compare this header line by line with the
+// reference's call_functions.tcc compiled from source over stand-in third-party headers, and with an
+// independent Python restatement (tests/test_reference_shim.py, tests/test_function_caller.py).
 #pragma once
 
 #include "signature_host.h"

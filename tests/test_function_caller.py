@@ -18,8 +18,7 @@ PKG = os.path.join(ROOT, "signature_kmers_b200")
 AA = "ACDEFGHIKLMNPQRSTVWY"
 
 
-@pytest.fixture(scope="module")
-def host():
+def load_host():
     if not os.path.exists(os.path.join(PKG, "libsigk.so")):
         import __graft_entry__ as g
         g.build()
@@ -32,6 +31,11 @@ def host():
     lib.sigk_host_call_windows.argtypes = [C.c_char_p, C.c_uint64, np.ctypeslib.ndpointer(dtype=np.uint32), C.c_uint64]
     lib.sigk_host_call_windows.restype = C.c_uint64
     return lib
+
+
+@pytest.fixture(scope="module")
+def host():
+    return load_host()
 
 
 class Table:

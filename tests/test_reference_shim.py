@@ -178,3 +178,96 @@ def test_gpu_command_line_equals_reference_sources(ref, tmp_path):
     assert got_df == {i: int(c) for i, c in enumerate(df) if c}
     rows = [l.split("\t") for l in open(out / "final.kmers").read().splitlines()]
     assert [x[0] for x in rows] == kmers and [int(x[1]) for x in rows] == [int(v) for v in cols[0]]
+
+
+# ---- the consumer side: the reference's FunctionCaller<KeptKmerDB<8>> from its own sources --------------
+REF_CALL_SO = os.path.join(ROOT, "oracle", "_ref", "libref_call.so")
+
+
+@pytest.fixture(scope="module")
+def ref_call():
+    if not os.path.exists(REF_CALL_SO):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], capture_output=True)
+    if not os.path.exists(REF_CALL_SO):
+        pytest.skip("oracle/_ref/libref_call.so not built (reference checkout absent)")
+    lib = C.CDLL(REF_CALL_SO)
+    u16p = np.ctypeslib.ndpointer(dtype=np.uint16, flags="C_CONTIGUOUS")
+    lib.ref_call_functions.argtypes = [C.c_ulonglong, C.c_char_p, u16p, u16p, u16p, u16p, u16p, C.c_char_p, C.c_char_p, C.c_ulonglong,
+                                       C.c_int, C.c_int, C.c_char_p, C.c_ulonglong]
+    lib.ref_call_functions.restype = C.c_ulonglong
+    return lib
+
+
+def ref_calls(lib, table, names, fasta, tmp_path, ignore_hypo=False, want_calls=True):
+    fi = os.path.join(str(tmp_path), "function.index")
+    with open(fi, "w") as f:
+        for i, name in enumerate(names):
+            f.write("%d\t%s\n" % (i, name))
+    data = fasta.encode("latin-1")
+    out = C.create_string_buffer(1 << 20)
+    n = lib.ref_call_functions(len(table.kmers), table.blob, *table.cols, fi.encode(), data, len(data), int(ignore_hypo), int(want_calls),
+                               out, len(out))
+    assert n <= len(out)
+    return out.raw[:n].decode("latin-1").splitlines()
+
+
+def test_function_caller_equals_reference_sources(ref_call, tmp_path):
+    """host/function_caller.h against the reference's call_functions.tcc compiled from source: region calls and
+    best calls on the hand-made cases of tests/test_function_caller.py and on tables built by the oracle."""
+    import random
+
+    import tests.test_function_caller as tfc
+
+    host = tfc.load_host()
+    ALPHA, BETA, NAMES = tfc.ALPHA, tfc.BETA, tfc.NAMES
+    cases = []
+    # single function, fragments, nothing known
+    t = tfc.table_from({0: [ALPHA]}, {0: len(ALPHA)})
+    cases.append((t, NAMES, [("p1", ALPHA), ("frag", ALPHA[:12]), ("tiny", ALPHA[:11]), ("none", "W" * 40), ("amb", ALPHA[:40] + "X" + ALPHA[41:])]))
+    # chimeras: clear winner, and too close to call
+    chim, chim2 = ALPHA[:60] + BETA[:40], ALPHA[:50] + BETA[:48]
+    cases.append((tfc.table_from({0: [ALPHA], 1: [BETA]}, {0: len(chim), 1: len(chim)}), NAMES, [("c", chim)]))
+    cases.append((tfc.table_from({0: [ALPHA], 1: [BETA]}, {0: len(chim2), 1: len(chim2)}), NAMES, [("c2", chim2)]))
+    # the fusion-positive construction
+    a, w, b = ALPHA[:80], ALPHA[100:160] + BETA[200:261], BETA[:90]
+    rows = {}
+    for p in range(len(a) - 7):
+        rows[a[p:p + 8]] = (len(a) - p, 0, 280, 0, 0)
+    for p in range(len(w) - 7):
+        rows[w[p:p + 8]] = (len(w) - p, 2, 291 if p % 2 == 0 else 869, 0, 0)
+    for p in range(len(b) - 7):
+        rows[b[p:p + 8]] = (len(b) - p, 1, 300, 0, 0)
+    cases.append((tfc.Table(rows), NAMES, [("fus", a + w + b)]))
+    # random region lists
+    rng = random.Random(19)
+    for trial in range(40):
+        q, rows = "", {}
+        for r in range(rng.randrange(1, 7)):
+            fi = rng.choice([0, 1, 2, 4])
+            seq = "".join(rng.choice(tfc.AA) for _ in range(rng.randrange(12, 40)))
+            for p in range(len(seq) - 7):
+                rows[seq[p:p + 8]] = (len(seq) - p, fi, 0, 0, 0)
+            q += seq
+        rows = {k: (v[0], v[1], len(q), 0, 0) for k, v in rows.items()}
+        cases.append((tfc.Table(rows), NAMES, [("t%d" % trial, q)]))
+    # tables from the build oracle, training proteins and noisy chimeras
+    for seed in (21, 22):
+        t, seqs, funcs = tfc.build_table_with_oracle(seed, n_families=25, members=(3, 12), length=(60, 260), sub_rate=0.08, n_functions=12)
+        names = ["Function %d" % i for i in range(12)]
+        names[5] = "hypothetical protein"
+        names[7] = "Function 3 / Function 4"
+        recs = [("train%d" % i, (s.decode("latin-1") if isinstance(s, bytes) else s)) for i, s in enumerate(seqs[:60])]
+        for i in range(30):
+            x, y = rng.choice(recs)[1], rng.choice(recs)[1]
+            q = x[:rng.randrange(10, len(x))] + y[rng.randrange(0, len(y) - 9):]
+            recs.append(("chim%d" % i, "".join(c if rng.random() > 0.03 else rng.choice(tfc.AA + "X*") for c in q)))
+        cases.append((t, names, recs))
+    n_lines = 0
+    for table, names, recs in cases:
+        fasta = tfc.to_fasta(recs)
+        for hypo in (False, True):
+            want = ref_calls(ref_call, table, names, fasta, tmp_path, ignore_hypo=hypo)
+            got = tfc.cxx_calls(host, table, names, fasta, ignore_hypo=hypo)
+            assert got == want, recs[0][0]
+            n_lines += len(want)
+    assert n_lines > 500
