@@ -35,20 +35,28 @@ extern "C" {
  * <out_dir>/ref_table.bin: "SIGKTBL1", u64 n, n x 8 k-mer bytes (sorted), then avg_from_end, function_index,
  * mean, median, var as u16 columns.  counters[0..2] = kept k-mers, distinct_signatures,
  * num_seqs_with_a_signature; distinct_functions / seqs_with_func: 65536 slots each.  Returns 0. */
-int ref_signature_build(const char *definition_dir, const char *fasta_dir, const char *deleted_fids_file, int min_reps,
-                        int n_threads, const char *out_dir, unsigned long long *counters, unsigned *distinct_functions,
-                        unsigned *seqs_with_func) {
+int ref_signature_build_ex(const char *definition_dir, const char *fasta_dir, const char *deleted_fids_file,
+                           const char *good_functions_file, const char *good_roles_file, const char *ignored_functions_file,
+                           int min_reps, int n_threads, const char *out_dir, unsigned long long *counters,
+                           unsigned *distinct_functions, unsigned *seqs_with_func) {
     std::vector<fs::path> definitions, fasta;
     sorted_files(definition_dir, definitions);
     sorted_files(fasta_dir, fasta);
+    /* one string per line, as load_strings / load_set_from_file of src/path_utils.h read them */
+    auto lines_of = [](const char *file) {
+        std::vector<std::string> v;
+        if (file && *file) {
+            std::ifstream in(file);
+            std::string line;
+            while (std::getline(in, line)) v.push_back(line);
+        }
+        return v;
+    };
     std::set<std::string> deleted, ignored;
-    if (deleted_fids_file && *deleted_fids_file) {
-        std::ifstream in(deleted_fids_file);
-        std::string line;
-        while (std::getline(in, line)) deleted.insert(line);
-    }
+    for (auto &l : lines_of(deleted_fids_file)) deleted.insert(l);
+    for (auto &l : lines_of(ignored_functions_file)) ignored.insert(l);
     SignatureBuilder<8> builder(n_threads, 100000);          /* MaxSequencesPerFile, src/kmers-build-signatures.cc:18 */
-    builder.load_function_data({}, {}, definitions);
+    builder.load_function_data(lines_of(good_functions_file), lines_of(good_roles_file), definitions);
     builder.load_fasta(fasta, false, deleted);
     builder.process_kept_functions(min_reps, fs::path(out_dir), ignored);
     builder.extract_kmers(deleted);
@@ -80,6 +88,14 @@ int ref_signature_build(const char *definition_dir, const char *fasta_dir, const
     for (const auto &e : st.distinct_functions) distinct_functions[e.first & 0xFFFF] = (unsigned)e.second;
     for (const auto &e : st.seqs_with_func) seqs_with_func[e.first] = (unsigned)e.second;
     return 0;
+}
+
+
+int ref_signature_build(const char *definition_dir, const char *fasta_dir, const char *deleted_fids_file, int min_reps,
+                        int n_threads, const char *out_dir, unsigned long long *counters, unsigned *distinct_functions,
+                        unsigned *seqs_with_func) {
+    return ref_signature_build_ex(definition_dir, fasta_dir, deleted_fids_file, "", "", "", min_reps, n_threads, out_dir, counters,
+                                  distinct_functions, seqs_with_func);
 }
 
 }

@@ -271,3 +271,96 @@ def test_function_caller_equals_reference_sources(ref_call, tmp_path):
             assert got == want, recs[0][0]
             n_lines += len(want)
     assert n_lines > 500
+
+
+def test_function_map_conventions_against_reference_sources(ref, tmp_path):
+    """The input conventions of FunctionMap (src/function_map.h:62-332) on a deliberately messy tree: assignment
+    comments and truncation markers, functions given on FASTA definition lines with [genome] brackets, ids that
+    are not fig ids, explicit assignments overriding definition lines, multi-role functions with the good-roles
+    list, the good-functions list, ignored functions, functions below the genome threshold."""
+    aa = "ACDEFGHIKLMNPQRSTVWY"
+
+    def seq(tag, n):
+        return "".join(aa[(i * 7 + tag * 3 + (i // 5)) % 20] for i in range(n))
+
+    root = str(tmp_path / "tree")
+    os.makedirs(os.path.join(root, "Annotations", "0"))
+    os.makedirs(os.path.join(root, "Seqs"))
+    for gi in range(4):
+        g = "2000%d.1" % gi
+        ann, fa = [], []
+        # plain assignments with comments; a truncated one is dropped
+        ann.append(("fig|%s.peg.1" % g, "Alpha synthase (EC 1.1.1.1) # some note"))
+        fa.append(("fig|%s.peg.1" % g, "", seq(1, 90 + gi)))
+        ann.append(("fig|%s.peg.2" % g, "Alpha synthase (EC 1.1.1.1) ## another note"))
+        fa.append(("fig|%s.peg.2" % g, "", seq(1, 80)))
+        ann.append(("fig|%s.peg.3" % g, "Beta kinase # truncated"))
+        fa.append(("fig|%s.peg.3" % g, "", seq(2, 70)))
+        ann.append(("fig|%s.peg.4" % g, "Beta kinase # fragment"))
+        fa.append(("fig|%s.peg.4" % g, "", seq(2, 75)))
+        # multi-role functions: only genome 0 and 1 have them (below 3 genomes) -> kept through good roles
+        if gi < 2:
+            ann.append(("fig|%s.peg.5" % g, "Gamma lyase / Delta ligase"))
+            fa.append(("fig|%s.peg.5" % g, "", seq(3, 100)))
+            ann.append(("fig|%s.peg.6" % g, "Epsilon pump @ Zeta channel"))
+            fa.append(("fig|%s.peg.6" % g, "", seq(4, 100)))
+            ann.append(("fig|%s.peg.7" % g, "Eta factor; Theta factor"))
+            fa.append(("fig|%s.peg.7" % g, "", seq(5, 100)))
+            ann.append(("fig|%s.peg.8" % g, "Listed function"))             # kept through good functions
+            fa.append(("fig|%s.peg.8" % g, "", seq(6, 100)))
+            ann.append(("fig|%s.peg.9" % g, "Rare unlisted function"))      # dropped
+            fa.append(("fig|%s.peg.9" % g, "", seq(7, 100)))
+        # function on the definition line only, explicit assignment overriding a definition line
+        fa.append(("fig|%s.peg.10" % g, " Iota reductase", seq(8, 85)))
+        ann.append(("fig|%s.peg.11" % g, "Kappa oxidase"))
+        fa.append(("fig|%s.peg.11" % g, " Something else entirely", seq(9, 85)))
+        ann.append(("fig|%s.peg.12" % g, "Ignored function"))
+        fa.append(("fig|%s.peg.12" % g, "", seq(10, 85)))
+        fa.append(("fig|%s.peg.13" % g, "", seq(11, 85)))                   # no function anywhere
+        with open(os.path.join(root, "Annotations", "0", g), "w") as f:
+            for rid, fn in ann:
+                f.write("%s\t%s\n" % (rid, fn))
+        with open(os.path.join(root, "Seqs", g), "w") as f:
+            for rid, d, s in fa:
+                f.write(">%s%s\n%s\n" % (rid, d, s))
+    # genbank-style files: no fig ids, function and genome on the definition line
+    for gi in range(3):
+        with open(os.path.join(root, "Seqs", "genbank%d" % gi), "w") as f:
+            f.write(">prot%d_a Lambda transferase [Some organism %d]\n%s\n" % (gi, gi, seq(12, 95)))
+            f.write(">prot%d_b Lambda transferase # truncated [Some organism %d]\n%s\n" % (gi, gi, seq(12, 60)))
+            f.write(">prot%d_c Mu isomerase # a comment [Some organism %d]\n%s\n" % (gi, gi, seq(13, 95)))
+    good_functions = str(tmp_path / "good_functions.txt")
+    good_roles = str(tmp_path / "good_roles.txt")
+    ignored = str(tmp_path / "ignored.txt")
+    open(good_functions, "w").write("Listed function\n")
+    open(good_roles, "w").write("Delta ligase\nZeta channel\nTheta factor\n")
+    open(ignored, "w").write("Ignored function\n")
+
+    out_ref = str(tmp_path / "ref_out")
+    os.makedirs(out_ref)
+    counters = (C.c_ulonglong * 3)()
+    df = (C.c_uint * 65536)()
+    swf = (C.c_uint * 65536)()
+    ref.ref_signature_build_ex.argtypes = [C.c_char_p] * 6 + [C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+    rc = ref.ref_signature_build_ex(os.path.join(root, "Annotations", "0").encode(), os.path.join(root, "Seqs").encode(), b"",
+                                    good_functions.encode(), good_roles.encode(), ignored.encode(), 3, 1, out_ref.encode(), counters, df, swf)
+    assert rc == 0
+    kmers, cols = read_table(os.path.join(out_ref, "ref_table.bin"))
+    refres = (kmers, cols, list(counters), np.array(df), np.array(swf))
+
+    out = tmp_path / "our_out"
+    dump = str(tmp_path / "packed.bin")
+    r = subprocess.run([os.path.join(PKG, "kmers-build-signatures"), "-D", os.path.join(root, "Annotations", "0"), "-F", os.path.join(root, "Seqs"),
+                        "--kmer-data-dir", str(out), "--good-functions", good_functions, "--good-roles", good_roles,
+                        "--ignored-functions-file", ignored, "--sorted-files", "--dump-packed", dump], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    res, starts, func, sid = read_packed(dump)
+    table, _ = oracle_c.oracle_build(PackedProteins(res.copy(), starts.copy(), func.copy(), sid.copy()))
+    names_ref = function_index_names(os.path.join(out_ref, "function.index"))
+    names_our = function_index_names(out / "function.index")
+    assert names_our == names_ref
+    kept = {n for _, n in names_ref}
+    assert {"Alpha synthase (EC 1.1.1.1)", "Gamma lyase / Delta ligase", "Epsilon pump @ Zeta channel", "Eta factor; Theta factor",
+            "Listed function", "Iota reductase", "Kappa oxidase", "hypothetical protein"} <= kept, kept
+    assert "Rare unlisted function" not in kept and "Ignored function" not in kept and "Something else entirely" not in kept
+    assert_same(refres, table, "messy tree")
