@@ -169,7 +169,9 @@ struct FloatStats {
             var = (var * (float)(n - 1)) / (float)n + (tmp * tmp) / (float)(n - 1);
         }
     }
-    double mean() const { return n ? sum / (float)n : 0.0; }
+    // no samples: 0.f / 0 like the accumulator's sum / count (the reference's function.index shows "-nan" for
+    // the always-present "hypothetical protein" row when no protein carries it)
+    double mean() const { return sum / (float)n; }
     double median() const { return q[2]; }
 };
 

@@ -96,7 +96,8 @@ def test_oracle_equals_reference_sources_on_synthetic_trees(ref, tmp_path, seed,
     table = run_oracle_through_dropin(tree, tmp_path / "our_out", str(tmp_path))
     assert len(refres[0]) > 1000
     assert_same(refres, table, "synthetic seed %d" % seed)
-    assert function_index_names(tmp_path / "ref_out" / "function.index") == function_index_names(tmp_path / "our_out" / "function.index")
+    # function.index, whole lines: index, name, count, mean, median, var, dev as the reference's writer prints them
+    assert open(tmp_path / "ref_out" / "function.index").read() == open(tmp_path / "our_out" / "function.index").read()
 
 
 def write_tree(root, genomes):
@@ -357,8 +358,7 @@ def test_function_map_conventions_against_reference_sources(ref, tmp_path):
     res, starts, func, sid = read_packed(dump)
     table, _ = oracle_c.oracle_build(PackedProteins(res.copy(), starts.copy(), func.copy(), sid.copy()))
     names_ref = function_index_names(os.path.join(out_ref, "function.index"))
-    names_our = function_index_names(out / "function.index")
-    assert names_our == names_ref
+    assert open(os.path.join(out_ref, "function.index")).read() == open(out / "function.index").read()
     kept = {n for _, n in names_ref}
     assert {"Alpha synthase (EC 1.1.1.1)", "Gamma lyase / Delta ligase", "Epsilon pump @ Zeta channel", "Eta factor; Theta factor",
             "Listed function", "Iota reductase", "Kappa oxidase", "hypothetical protein"} <= kept, kept
