@@ -58,8 +58,11 @@ encode_kernel(EncodeArgs a, uint64_t *__restrict__ keys, uint32_t *__restrict__ 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EncSmem &sm = *reinterpret_cast<EncSmem *>(smem_raw);
 
+    __shared__ int8_t s_sym[256];
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+    static_assert(ENC_THREADS == 256, "one table entry per thread");
+    s_sym[tid] = (int8_t)sigk_symbol(tid);
     __syncthreads();
     const uint32_t sub = sm.tile * ENC_WARPS + warp;                 // this warp's entry in the chained scan
     const uint64_t g0 = (uint64_t)sub * ENC_SUB;
@@ -87,7 +90,7 @@ encode_kernel(EncodeArgs a, uint64_t *__restrict__ keys, uint32_t *__restrict__ 
 #pragma unroll
     for (int j = 0; j < ENC_PPT + 7; ++j) {
         const unsigned c = (words[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-        int sy = sigk_symbol(c);
+        int sy = s_sym[c];                              // byte -> symbol 0..39, or -1 (table: 1/5 of the arithmetic form's instructions)
         if (sy < 0) { bad |= 1u << j; sy = 0; }
         sw[j >> 2] |= (uint32_t)sy << (8 * (j & 3));
     }
@@ -192,8 +195,10 @@ encode_split_kernel(EncodeArgs a, const __grid_constant__ EncodeSplitArgs sp, ui
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EncSplitSmem &sm = *reinterpret_cast<EncSplitSmem *>(smem_raw);
 
+    __shared__ int8_t s_sym[256];
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t W = (uint32_t)sp.n_split + 1u;
+    s_sym[tid] = (int8_t)sigk_symbol(tid);
     if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
     if (tid < (unsigned)sp.n_split) sm.split[tid] = sp.split_codes[tid];
     if (tid < 16) { sm.dkeys[tid] = sp.dst_keys[tid]; sm.dvals[tid] = sp.dst_vals[tid]; }
@@ -220,7 +225,7 @@ encode_split_kernel(EncodeArgs a, const __grid_constant__ EncodeSplitArgs sp, ui
 #pragma unroll
     for (int j = 0; j < ENC_PPT + 7; ++j) {
         const unsigned c = (words[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-        int sy = sigk_symbol(c);
+        int sy = s_sym[c];                              // byte -> symbol 0..39, or -1 (table: 1/5 of the arithmetic form's instructions)
         if (sy < 0) { bad |= 1u << j; sy = 0; }
         sw[j >> 2] |= (uint32_t)sy << (8 * (j & 3));
     }
