@@ -39,6 +39,25 @@ def build_distributed(p_all, rank, world, local_rank):
     return multigpu.concat_tables(parts), [x.n_kept for x in parts]
 
 
+def build_sequence_on_one_communicator(cases, rank, world, local_rank):
+    """Several inputs through ONE handle and communicator: the landing zones grow (re-exported and re-imported
+    collectively), then are reused for a smaller input."""
+    import torch.distributed as dist
+
+    b = GpuSignatureBuilder(device=local_rank, rank=rank, world=world)
+    multigpu.join_communicator(b, rank, world)
+    out = []
+    for _, p_all in cases:
+        lo, hi = multigpu.rank_slice(p_all.n_proteins, rank, world)
+        b.set_proteins(p_all.slice(lo, hi))
+        t = b.build()
+        parts = [None] * world
+        dist.all_gather_object(parts, t)
+        out.append(multigpu.concat_tables(parts))
+    b.close()
+    return out
+
+
 def main():
     import torch
 
@@ -69,6 +88,17 @@ def main():
             single.close()
             print(f"multigpu_check ok ({world} ranks): {name}: {got.n_occurrences} occurrences, kept per rank {per_rank}", flush=True)
         dist.barrier()
+    # the same inputs, small -> large -> small, through one communicator
+    order = [cases[2], cases[-1], cases[0]]
+    tables = build_sequence_on_one_communicator(order, rank, world, local_rank)
+    if rank == 0:
+        from oracle import oracle_c
+
+        for (name, p_all), got in zip(order, tables):
+            want, _ = oracle_c.oracle_build(p_all)
+            assert_tables_equal(got, want, tier_b=True, what=name + " (shared communicator)")
+        print(f"multigpu_check ok ({world} ranks): one communicator, growing and shrinking inputs", flush=True)
+    dist.barrier()
     if rank == 0:
         print("MULTIGPU_CHECK_PASSED", flush=True)
     dist.destroy_process_group()
