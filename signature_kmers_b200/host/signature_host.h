@@ -21,8 +21,11 @@
 #include <functional>
 #include <iostream>
 #include <map>
+#include <atomic>
 #include <set>
 #include <string>
+#include <thread>
+#include <unordered_map>
 #include <vector>
 
 namespace sigk_host {
@@ -134,6 +137,19 @@ inline void ensure_directory(const fs::path &dir) {
 // accumulator_set<float, stats<mean, median, variance, count>> of function_map.h:463 —
 // the per-function length statistics written to function.index (columns 3-7).  Same
 // algorithms as the hot path's accumulator but with float state (sample type float).
+// fn(i) for i in [0, n) on up to `threads` threads (work handed out one index at a time)
+template <class Fn>
+inline void parallel_for_index(size_t n, int threads, Fn fn) {
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, threads), n));
+    if (nt <= 1) { for (size_t i = 0; i < n; ++i) fn(i); return; }
+    std::atomic<size_t> next{0};
+    auto worker = [&] { for (size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i); };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto &t : pool) t.join();
+}
+
 struct FloatStats {
     size_t n = 0;
     float sum = 0, var = 0;
@@ -182,8 +198,11 @@ public:
     void add_good_roles(const std::vector<std::string> &r) { good_roles_.insert(r.begin(), r.end()); }
     void add_good_functions(const std::vector<std::string> &r) { good_functions_.insert(r.begin(), r.end()); }
 
-    // :62-104
-    void load_id_assignments(const fs::path &file) {
+    // :62-104.  Reading and splitting the lines needs nothing from the map, so it can run for several files at
+    // once (parse_id_assignments); the map updates keep the reference's order (apply_id_assignments).
+    struct Assignment { std::string id, func, stripped; bool truncated; };
+    static std::vector<Assignment> parse_id_assignments(const fs::path &file) {
+        std::vector<Assignment> out;
         std::ifstream in(file);
         std::string line;
         int lineno = 0;
@@ -192,23 +211,50 @@ public:
             const size_t s = line.find('\t');
             if (s == std::string::npos) { std::cerr << "bad line " << lineno << " in file " << file << "\n"; continue; }
             const size_t s2 = line.find('\t', s + 1);
-            const std::string id = line.substr(0, s);
-            const std::string func = s2 == std::string::npos ? line.substr(s + 1) : line.substr(s + 1, s2 - s - 1);
-            std::string stripped, delim, comment;
-            split_func_comment(func, stripped, delim, comment);
-            original_assignment_stripped_[id] = stripped;
-            original_assignment_[id] = func;
-            if (delim == "#" && is_truncated_comment(comment)) continue;     // keeps any earlier assignment (:93-98)
-            id_function_map_[id] = stripped;
+            Assignment a;
+            a.id = line.substr(0, s);
+            a.func = s2 == std::string::npos ? line.substr(s + 1) : line.substr(s + 1, s2 - s - 1);
+            std::string delim, comment;
+            split_func_comment(a.func, a.stripped, delim, comment);
+            a.truncated = delim == "#" && is_truncated_comment(comment);
+            out.push_back(std::move(a));
+        }
+        return out;
+    }
+    void apply_id_assignments(std::vector<Assignment> &rows) {
+        by_id_.reserve(by_id_.size() + rows.size());
+        for (auto &a : rows) {
+            IdEntry &e = by_id_[a.id];
+            e.has_original = true;
+            if (!a.truncated) e.function = a.stripped;                       // a truncated one keeps any earlier assignment (:93-98)
+            e.original_stripped = std::move(a.stripped);
+            e.original = std::move(a.func);
         }
     }
+    void load_id_assignments(const fs::path &file) {
+        auto rows = parse_id_assignments(file);
+        apply_id_assignments(rows);
+    }
 
-    // :120-238 — genome / function evidence from one FASTA file
-    void load_fasta_file(const fs::path &file, bool keep_function_flag, const std::set<std::string> &deleted_fids) {
+    // :120-238 — genome / function evidence from one FASTA file.  The parse (parse_fasta_headers: id, definition
+    // and length of every record) is independent of the map; the evidence is applied in file and record order.
+    struct FastaHeader { std::string id, def; size_t length; };
+    static std::vector<FastaHeader> parse_fasta_headers(const fs::path &file) {
+        std::vector<FastaHeader> out;
         std::ifstream in(file);
-        std::string genome;
         FastaReader reader([&](const std::string &id, const std::string &def, const std::string &seq) {
-            if (id.empty() || deleted_fids.count(id)) return;
+            out.push_back(FastaHeader{id, def, seq.length()});
+        });
+        reader.parse(in);
+        reader.finish();
+        return out;
+    }
+    void apply_fasta_headers(const fs::path &file, const std::vector<FastaHeader> &records, bool keep_function_flag,
+                             const std::set<std::string> &deleted_fids) {
+        std::string genome;
+        for (const auto &rec : records) {
+            const std::string &id = rec.id, &def = rec.def;
+            if (id.empty() || deleted_fids.count(id)) continue;
             std::string func;
             if (!def.empty()) {
                 const size_t x = def.find_first_not_of(" \t");
@@ -218,7 +264,7 @@ public:
             if (match_genome_def(def, m1, genome_loc)) {        // "\s+(.*)\s+\[([^]]+)\]$"
                 std::string delim, comment;
                 split_func_comment(m1, func, delim, comment);
-                if (delim == "#" && is_truncated_comment(comment)) return;
+                if (delim == "#" && is_truncated_comment(comment)) continue;
             } else genome_loc.clear();
             if (genome.empty()) {
                 if (def.empty()) { std::string g; if (find_fig_genome(id, g)) genome = g; }
@@ -228,25 +274,27 @@ public:
                 genome = file.filename().string();
                 if (!is_genome_id(genome)) std::cerr << "cannot determine genome from file " << file << "\n";
             }
-            const std::string cur = id_function_map_[id];       // operator[]: inserts an empty entry like the reference
-            if (cur.empty()) { if (!func.empty()) id_function_map_[id] = func; }
-            else func = cur;
+            std::string &slot = by_id_[id].function;            // operator[]: inserts an empty entry like the reference
+            if (slot.empty()) { if (!func.empty()) slot = func; }
+            else func = slot;
             if (!func.empty()) {
-                function_genome_map_[func].insert(genome);
+                FunctionEvidence &ev = by_function_[func];
+                ev.genomes.insert(genome);
                 if (keep_function_flag) good_functions_.insert(func);
-                function_stats_[func].push((double)seq.length());
+                ev.lengths.push((double)rec.length);
             }
-        });
-        reader.parse(in);
-        reader.finish();
+        }
+    }
+    void load_fasta_file(const fs::path &file, bool keep_function_flag, const std::set<std::string> &deleted_fids) {
+        apply_fasta_headers(file, parse_fasta_headers(file), keep_function_flag, deleted_fids);
     }
 
     // :257-332
     void process_kept_functions(int min_reps_required, const std::set<std::string> &ignored) {
         std::set<std::string> kept;
-        for (const auto &entry : function_genome_map_) {
+        for (const auto &entry : by_function_) {                 // any order: `kept` is a std::set, as in the reference
             const std::string &function = entry.first;
-            bool ok = (int)entry.second.size() >= min_reps_required || good_functions_.count(function);
+            bool ok = (int)entry.second.genomes.size() >= min_reps_required || good_functions_.count(function);
             if (!ok)
                 for (const auto &role : roles_of_function(function))
                     if (good_roles_.count(role)) { ok = true; break; }
@@ -264,13 +312,13 @@ public:
     }
 
     std::string lookup_function(const std::string &id) const {
-        auto it = id_function_map_.find(id);
-        return it == id_function_map_.end() ? std::string() : it->second;
+        auto it = by_id_.find(id);
+        return it == by_id_.end() ? std::string() : it->second.function;
     }
     // src/function_map.h:351-358 (outputs untouched when the id was never assigned)
     void lookup_original_assignment(const std::string &id, std::string &func, std::string &stripped) const {
-        auto it = original_assignment_.find(id);
-        if (it != original_assignment_.end()) { func = it->second; stripped = original_assignment_stripped_.at(id); }
+        auto it = by_id_.find(id);
+        if (it != by_id_.end() && it->second.has_original) { func = it->second.original; stripped = it->second.original_stripped; }
     }
     std::string lookup_function(uint16_t idx) const {
         auto it = index_function_map_.find(idx);
@@ -287,7 +335,9 @@ public:
         std::map<int, std::string> by_index;
         for (const auto &e : function_index_map_) by_index.insert({e.second, e.first});
         for (const auto &e : by_index) {
-            const FloatStats &a = function_stats_[e.second];
+            static const FloatStats none;
+            auto st = by_function_.find(e.second);
+            const FloatStats &a = st == by_function_.end() ? none : st->second.lengths;
             const double mean = a.mean(), median = a.median(), var = a.var;
             of << e.first << "\t" << e.second << "\t" << (int)a.n << "\t" << mean << "\t" << median << "\t" << var << "\t"
                << std::sqrt(var) << "\n";
@@ -339,42 +389,56 @@ private:
         return d > b + 1 && d == s.size();
     }
 
-    std::map<std::string, std::set<std::string>> function_genome_map_;
-    std::map<std::string, std::string> id_function_map_;
+    // the reference's id_function_map_, original_assignment_ and original_assignment_stripped_ (keyed by id, only ever
+    // looked up) in one hash table; function_genome_map_ and function_accumulators_ (keyed by function) in another
+    struct IdEntry { std::string function, original, original_stripped; bool has_original = false; };
+    struct FunctionEvidence { std::set<std::string> genomes; FloatStats lengths; };
+    std::unordered_map<std::string, IdEntry> by_id_;
+    std::unordered_map<std::string, FunctionEvidence> by_function_;
     std::map<std::string, uint16_t> function_index_map_;
     std::map<uint16_t, std::string> index_function_map_;
     std::set<std::string> good_roles_, good_functions_;
-    std::map<std::string, std::string> original_assignment_stripped_, original_assignment_;
-    std::map<std::string, FloatStats> function_stats_;
 };
 
 // ---------------------------------------------------------------------------
 // src/signature_build.{h,tcc}: same public calls, in the order main() makes them.
 class HostSignatureBuilder {
 public:
-    HostSignatureBuilder(int n_threads, int max_seqs_per_file) : max_seqs_per_file_(max_seqs_per_file) { (void)n_threads; }
+    HostSignatureBuilder(int n_threads, int max_seqs_per_file) : n_threads_(n_threads), max_seqs_per_file_(max_seqs_per_file) {}
 
+    // Files are read and tokenised on n_threads threads; everything that touches the FunctionMap is applied in
+    // the reference's order (file by file, record by record), so the outputs do not depend on the thread count.
     void load_function_data(const std::vector<std::string> &good_functions, const std::vector<std::string> &good_roles,
                             const std::vector<fs::path> &defs) {
         fm_.add_good_roles(good_roles);
         fm_.add_good_functions(good_functions);
-        for (const auto &d : defs) fm_.load_id_assignments(d);
+        std::vector<std::vector<FunctionMap::Assignment>> parsed(defs.size());
+        parallel_for_index(defs.size(), n_threads_, [&](size_t i) { parsed[i] = FunctionMap::parse_id_assignments(defs[i]); });
+        for (auto &rows : parsed) fm_.apply_id_assignments(rows);
     }
     void load_fasta(const std::vector<fs::path> &files, bool /*keep_functions: dropped by the reference, tcc:32*/,
                     const std::set<std::string> &deleted) {
-        for (const auto &f : files) { fm_.load_fasta_file(f, false, deleted); all_fasta_data_.push_back(f); }
+        std::vector<std::vector<FunctionMap::FastaHeader>> parsed(files.size());
+        parallel_for_index(files.size(), n_threads_, [&](size_t i) { parsed[i] = FunctionMap::parse_fasta_headers(files[i]); });
+        for (size_t i = 0; i < files.size(); ++i) {
+            fm_.apply_fasta_headers(files[i], parsed[i], false, deleted);
+            all_fasta_data_.push_back(files[i]);
+        }
     }
     void process_kept_functions(int min_reps, const fs::path &out_dir, const std::set<std::string> &ignored) {
         fm_.process_kept_functions(min_reps, ignored);
         if (!out_dir.empty()) fm_.write_function_index(out_dir);
     }
 
-    // tcc:47-160 with the window loop removed: the gated proteins are packed in canonical order
+    // tcc:47-160 with the window loop removed: the gated proteins are packed in canonical order (file order,
+    // record order inside a file).  Files are independent (tcc:58-68 runs them under tbb::parallel_for).
     void extract_kmers(const std::set<std::string> &deleted) {
-        residues_.clear(); starts_.assign(1, 0); func_.clear(); seq_id_.clear();
-        for (unsigned i = 0; i < all_fasta_data_.size(); ++i) {
+        struct PerFile { std::vector<uint8_t> residues; std::vector<uint64_t> lengths; std::vector<uint16_t> func; std::vector<uint32_t> seq_id; };
+        std::vector<PerFile> parts(all_fasta_data_.size());
+        parallel_for_index(all_fasta_data_.size(), n_threads_, [&](size_t i) {
+            PerFile &out = parts[i];
             std::ifstream in(all_fasta_data_[i]);
-            unsigned next_sequence_id = i * (unsigned)max_seqs_per_file_;                  // :91
+            unsigned next_sequence_id = (unsigned)i * (unsigned)max_seqs_per_file_;                 // :91
             FastaReader reader([&](const std::string &id, const std::string &, const std::string &seq) {
                 if (deleted.count(id)) return;                                              // :94
                 if (id.empty()) return;                                                     // :122
@@ -383,13 +447,23 @@ public:
                 const unsigned seq_id = next_sequence_id++;                                 // :138
                 const uint16_t fi = fm_.lookup_index(func);
                 if (fi == 0xFFFF) return;                                                   // :155
-                residues_.insert(residues_.end(), seq.begin(), seq.end());
-                starts_.push_back(residues_.size());
-                func_.push_back(fi);
-                seq_id_.push_back(seq_id);
+                out.residues.insert(out.residues.end(), seq.begin(), seq.end());
+                out.lengths.push_back(seq.size());
+                out.func.push_back(fi);
+                out.seq_id.push_back(seq_id);
             }, true);
             reader.parse(in);
             reader.finish();
+        });
+        residues_.clear(); starts_.assign(1, 0); func_.clear(); seq_id_.clear();
+        size_t total = 0, count = 0;
+        for (const auto &part : parts) { total += part.residues.size(); count += part.func.size(); }
+        residues_.reserve(total); starts_.reserve(count + 1); func_.reserve(count); seq_id_.reserve(count);
+        for (const auto &part : parts) {
+            residues_.insert(residues_.end(), part.residues.begin(), part.residues.end());
+            for (uint64_t len : part.lengths) starts_.push_back(starts_.back() + len);
+            func_.insert(func_.end(), part.func.begin(), part.func.end());
+            seq_id_.insert(seq_id_.end(), part.seq_id.begin(), part.seq_id.end());
         }
     }
 
@@ -424,7 +498,7 @@ public:
     const FunctionMap &function_map() const { return fm_; }
 
 private:
-    int max_seqs_per_file_;
+    int n_threads_, max_seqs_per_file_;
     FunctionMap fm_;
     std::vector<fs::path> all_fasta_data_;
     std::vector<uint8_t> residues_;
