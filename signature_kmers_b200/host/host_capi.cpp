@@ -90,4 +90,13 @@ uint64_t sigk_host_call_windows(const char *seq, uint64_t len, uint32_t *offsets
     return n;
 }
 
+
+// final.kmers of a caller-supplied table (the writer of the drop-in command line); returns 0 on success
+int sigk_host_write_final_kmers(const char *path, uint64_t n_rows, const char *kmers, const uint16_t *avg_from_end,
+                                const uint16_t *function_index, int n_threads) {
+    sigk_table t{};
+    t.n_kept = n_rows; t.kmer = kmers; t.avg_from_end = avg_from_end; t.function_index = function_index;
+    return write_final_kmers(path, t, n_threads) ? 0 : 1;
+}
+
 }

@@ -157,15 +157,7 @@ int main(int argc, char **argv) {
         fs::path fk = o.final_kmers;
         if (fk.is_relative()) { fk = o.kmer_data_dir / fk; std::cerr << "Updated final_kmers to " << fk << "\n"; }
         std::cerr << "writing kmers to " << fk << "\n";
-        std::FILE *f = std::fopen(fk.c_str(), "w");
-        if (!f) { std::cerr << "cannot write " << fk << "\n"; return 1; }
-        std::vector<char> buf(1 << 22);
-        std::setvbuf(f, buf.data(), _IOFBF, buf.size());
-        for (uint64_t i = 0; i < t.n_kept; ++i) {
-            std::fwrite(t.kmer + 8 * i, 1, 8, f);
-            std::fprintf(f, "\t%u\t%u\t\n", (unsigned)t.avg_from_end[i], (unsigned)t.function_index[i]);
-        }
-        std::fclose(f);
+        if (!write_final_kmers(fk, t, o.n_threads)) { std::cerr << "error writing " << fk << "\n"; return 1; }
         std::cerr << "writing kmers to " << fk << " complete\n";
     }
     {

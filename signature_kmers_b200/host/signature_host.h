@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <filesystem>
 #include <fstream>
 #include <functional>
@@ -399,6 +400,45 @@ private:
     std::map<uint16_t, std::string> index_function_map_;
     std::set<std::string> good_roles_, good_functions_;
 };
+
+// ---------------------------------------------------------------------------
+// final.kmers, src/kmers-build-signatures.cc:206-221: KMER \t avg_from_end \t function_index \t \n per kept k-mer.
+// Hundreds of millions of rows: blocks of rows are formatted on n_threads threads (at most 8 + 1 + 5 + 1 + 5 + 2
+// bytes a row) and written in order.
+inline bool write_final_kmers(const fs::path &file, const sigk_table &t, int n_threads) {
+    std::FILE *f = std::fopen(file.c_str(), "w");
+    if (!f) return false;
+    const uint64_t block = 1 << 20;
+    const uint64_t n_blocks = (t.n_kept + block - 1) / block;
+    const size_t wave = (size_t)std::max(1, n_threads) * 2;
+    auto put_u16 = [](char *p, unsigned v) {
+        char tmp[5];
+        int n = 0;
+        do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+        while (n) *p++ = tmp[--n];
+        return p;
+    };
+    std::vector<std::vector<char>> text(wave);
+    bool ok = true;
+    for (uint64_t b0 = 0; b0 < n_blocks && ok; b0 += wave) {
+        const size_t nb = (size_t)std::min<uint64_t>(wave, n_blocks - b0);
+        parallel_for_index(nb, n_threads, [&](size_t k) {
+            const uint64_t lo = (b0 + k) * block, hi = std::min<uint64_t>(t.n_kept, lo + block);
+            std::vector<char> &out = text[k];
+            out.resize((size_t)(hi - lo) * 22);
+            char *p = out.data();
+            for (uint64_t i = lo; i < hi; ++i) {
+                std::memcpy(p, t.kmer + 8 * i, 8); p += 8;
+                *p++ = '\t'; p = put_u16(p, t.avg_from_end[i]);
+                *p++ = '\t'; p = put_u16(p, t.function_index[i]);
+                *p++ = '\t'; *p++ = '\n';
+            }
+            out.resize((size_t)(p - out.data()));
+        });
+        for (size_t k = 0; k < nb && ok; ++k) ok = std::fwrite(text[k].data(), 1, text[k].size(), f) == text[k].size();
+    }
+    return std::fclose(f) == 0 && ok;
+}
 
 // ---------------------------------------------------------------------------
 // src/signature_build.{h,tcc}: same public calls, in the order main() makes them.

@@ -92,6 +92,30 @@ def test_truncation_and_roles(host):
     assert out.value.decode().split("\x01")[:-1] == ["A/B;C"]
 
 
+@pytest.mark.parametrize("n,threads", [(0, 1), (1, 4), (5, 2), (1 << 20, 3), ((1 << 21) + 17, 4)])
+def test_final_kmers_writer(host, tmp_path, n, threads):
+    """KMER \\t avg_from_end \\t function_index \\t \\n (src/kmers-build-signatures.cc:213-217), blocks formatted in parallel."""
+    rng = np.random.default_rng(n + 1)
+    kmers = rng.choice(np.frombuffer(b"ACDEFGHIKLMNPQRSTVWYacd", dtype=np.uint8), size=(n, 8))
+    avg = rng.integers(0, 65536, size=n).astype(np.uint16)
+    fn = rng.integers(0, 65536, size=n).astype(np.uint16)
+    if n:
+        avg[0], fn[0] = 0, 65535
+    u16p = np.ctypeslib.ndpointer(dtype=np.uint16, flags="C_CONTIGUOUS")
+    host.sigk_host_write_final_kmers.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, u16p, u16p, C.c_int]
+    path = str(tmp_path / "final.kmers")
+    assert host.sigk_host_write_final_kmers(path.encode(), n, kmers.tobytes(), avg, fn, threads) == 0
+    got = open(path, "rb").read()
+    if n <= 5:
+        want = b"".join(bytes(k) + b"\t%d\t%d\t\n" % (a, f) for k, a, f in zip(kmers, avg, fn))
+        assert got == want
+    else:
+        lines = got.split(b"\n")
+        assert lines[-1] == b"" and len(lines) == n + 1
+        for i in [i for i in list(range(0, n, 104729)) + [n - 1, (1 << 20) - 1, 1 << 20] if i < n]:
+            assert lines[i] == bytes(kmers[i]) + b"\t%d\t%d\t" % (avg[i], fn[i]), i
+
+
 def read_packed(path):
     raw = open(path, "rb").read()
     np_, total = np.frombuffer(raw, dtype=np.uint64, count=2)
