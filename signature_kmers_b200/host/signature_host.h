@@ -47,7 +47,26 @@ public:
     using Callback = std::function<void(const std::string &id, const std::string &def, const std::string &seq)>;
     explicit FastaReader(Callback cb, bool quiet = false) : cb_(std::move(cb)), quiet_(quiet) {}
 
-    void feed(const char *p, size_t n) { for (size_t i = 0; i < n; ++i) step(p[i]); }
+    // Same state machine, but runs of ordinary characters inside a sequence line, a definition or an id are
+    // appended in one go; every other character takes the one-character step below.
+    void feed(const char *p, size_t n) {
+        static const CharClasses cc;
+        const char *end = p + n;
+        while (p < end) {
+            const char *q = p;
+            if (st_ == DATA) {
+                while (q < end && cc.seq[(unsigned char)*q]) ++q;
+                if (q > p) { seq_.append(p, q); p = q; continue; }
+            } else if (st_ == DEF) {
+                while (q < end && *q != '\n' && *q != '\r') ++q;
+                if (q > p) { def_.append(p, q); p = q; continue; }
+            } else if (st_ == ID) {
+                while (q < end && !cc.id_stop[(unsigned char)*q]) ++q;
+                if (q > p) { id_.append(p, q); p = q; continue; }
+            }
+            step(*p++);
+        }
+    }
     void parse(std::istream &in) {
         reset();
         char buf[1 << 16];
@@ -58,6 +77,15 @@ public:
     void finish() { emit(); }
 
 private:
+    struct CharClasses {
+        bool seq[256], id_stop[256];
+        CharClasses() {
+            for (int c = 0; c < 256; ++c) {
+                seq[c] = std::isalpha(c) || c == '*';                           // what the DATA state keeps
+                id_stop[c] = c == ' ' || c == '\t' || c == '\n' || c == '\r';   // what ends (or is skipped inside) an id
+            }
+        }
+    };
     enum State { START, ID, DEF, DATA, LINE_START } st_ = START;
     std::string id_, def_, seq_;
     int line_ = 1;

@@ -188,3 +188,30 @@ def test_cli_end_to_end_final_kmers(tmp_path, oracle):
     df = {int(l.split("\t")[0]): int(l.split("\t")[2]) for l in open(out / "distinct_functions").read().splitlines()}
     assert df == {i: int(c) for i, c in enumerate(want.distinct_functions) if c}
     assert os.path.isdir(out / "recall.report.d")
+
+
+def test_fasta_reader_fuzz_against_reference_parser(host):
+    """Random byte soup over the characters the state machine distinguishes, in many chunkings of the input
+    (the reader appends runs of ordinary characters in bulk; the reference goes one character at a time)."""
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libref_fasta.so")
+    if not os.path.exists(ref_so):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], capture_output=True)
+    if not os.path.exists(ref_so):
+        pytest.skip("oracle/_ref not built (reference checkout absent)")
+    ref = C.CDLL(ref_so)
+    ref.ref_fasta_parse.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]
+    ref.ref_fasta_parse.restype = C.c_uint64
+    rng = np.random.default_rng(123)
+    alphabet = np.frombuffer(b">>\n\n\n\r \tACDEFGHIKLMNPQRSTVWYXacx**19-|[]#", dtype=np.uint8)
+    weights = np.ones(len(alphabet))
+    weights[8:32] = 6.0                                              # mostly letters, so that records form
+    weights /= weights.sum()
+    for trial in range(400):
+        n = int(rng.integers(0, 400))
+        data = bytes(rng.choice(alphabet, size=n, p=weights))
+        if trial % 3 == 0:
+            data = b">" + data
+        assert parse_with(host.sigk_host_fasta_parse, data) == parse_with(ref.ref_fasta_parse, data), data
+    # long sequences and headers crossing the reader's 64 KB chunks
+    big = b">id1 some definition [genome]\n" + b"ACDEFGHIKLMNPQRSTVWY" * 9000 + b"\n>id2\n" + (b"ACDEFGHIKL\n" * 20000) + b">" + b"i" * 70000 + b" d" * 40000 + b"\nAC*DE\n"
+    assert parse_with(host.sigk_host_fasta_parse, big) == parse_with(ref.ref_fasta_parse, big)
