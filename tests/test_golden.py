@@ -17,7 +17,7 @@ from tests.test_host_dropin import read_packed
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "signature_kmers_b200")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-CASES = ["synthetic", "edge"]
+CASES = ["synthetic", "zipf", "edge"]
 
 
 def golden_table(case):
