@@ -364,3 +364,33 @@ def test_function_map_conventions_against_reference_sources(ref, tmp_path):
             "Listed function", "Iota reductase", "Kappa oxidase", "hypothetical protein"} <= kept, kept
     assert "Rare unlisted function" not in kept and "Ignored function" not in kept and "Something else entirely" not in kept
     assert_same(refres, table, "messy tree")
+
+
+def test_two_tier_contract_holds_for_the_reference_sources(ref, tmp_path):
+    """SURVEY.md 8c's two tiers, checked on the reference's own code: feeding the same genomes in another file order
+    leaves (k-mer, function_index, avg_from_end, mean) and every counter unchanged (tier A), while median / var —
+    recurrences over the insertion order — may change (tier B is only defined for the canonical order)."""
+    import shutil
+
+    s = Synth(n_proteins=1200, n_functions=30, n_genomes=5, seed=65, zipf_s=1.1, mut_rate=0.03)
+    tree_a = str(tmp_path / "a")
+    s.write_tree(tree_a)
+    # the same files under names that sort in reverse order (ids inside are untouched: the genome of a file comes
+    # from its first fig id, src/function_map.h:167-175)
+    tree_b = str(tmp_path / "b")
+    for sub in (("Annotations", "0"), ("Seqs",)):
+        src = os.path.join(tree_a, *sub)
+        dst = os.path.join(tree_b, *sub)
+        os.makedirs(dst)
+        names = sorted(os.listdir(src))
+        for i, name in enumerate(names):
+            shutil.copy(os.path.join(src, name), os.path.join(dst, "%02d_%s" % (len(names) - i, name)))
+    ka, ca, cnt_a, df_a, swf_a = run_reference(ref, tree_a, str(tmp_path / "out_a"))
+    kb, cb, cnt_b, df_b, swf_b = run_reference(ref, tree_b, str(tmp_path / "out_b"))
+    assert ka == kb and cnt_a == cnt_b
+    for c in (0, 1, 2):                                         # avg_from_end, function_index, mean
+        np.testing.assert_array_equal(ca[c], cb[c])
+    np.testing.assert_array_equal(df_a, df_b)
+    np.testing.assert_array_equal(swf_a, swf_b)
+    differing = int((ca[3] != cb[3]).sum() + (ca[4] != cb[4]).sum())
+    assert differing > 0, "median/var did not depend on the insertion order on this input"
