@@ -35,6 +35,12 @@ extern "C" {
  * <out_dir>/ref_table.bin: "SIGKTBL1", u64 n, n x 8 k-mer bytes (sorted), then avg_from_end, function_index,
  * mean, median, var as u16 columns.  counters[0..2] = kept k-mers, distinct_signatures,
  * num_seqs_with_a_signature; distinct_functions / seqs_with_func: 65536 slots each.  Returns 0. */
+static int g_max_seqs_per_file = 100000;      /* MaxSequencesPerFile, src/kmers-build-signatures.cc:18 */
+
+/* tests only: sequence ids are file_number * max_seqs_per_file + n (src/signature_build.tcc:91), so a small value
+ * makes the ids of different files collide without needing 100 000 proteins per file */
+void ref_set_max_seqs_per_file(int v) { g_max_seqs_per_file = v; }
+
 int ref_signature_build_ex(const char *definition_dir, const char *fasta_dir, const char *deleted_fids_file,
                            const char *good_functions_file, const char *good_roles_file, const char *ignored_functions_file,
                            int min_reps, int n_threads, const char *out_dir, unsigned long long *counters,
@@ -55,7 +61,7 @@ int ref_signature_build_ex(const char *definition_dir, const char *fasta_dir, co
     std::set<std::string> deleted, ignored;
     for (auto &l : lines_of(deleted_fids_file)) deleted.insert(l);
     for (auto &l : lines_of(ignored_functions_file)) ignored.insert(l);
-    SignatureBuilder<8> builder(n_threads, 100000);          /* MaxSequencesPerFile, src/kmers-build-signatures.cc:18 */
+    SignatureBuilder<8> builder(n_threads, g_max_seqs_per_file);
     builder.load_function_data(lines_of(good_functions_file), lines_of(good_roles_file), definitions);
     builder.load_fasta(fasta, false, deleted);
     builder.process_kept_functions(min_reps, fs::path(out_dir), ignored);

@@ -16,7 +16,8 @@
 // of readdir order), --dump-packed FILE (write the gated packed proteins and
 // stop before the GPU: host-logic tests), --sigk-table FILE (write the table
 // file without --perfect-hash), --no-recall (skip the recall pass),
-// --host-recall (recall lookups on the host instead of sigk_lookup).
+// --host-recall (recall lookups on the host instead of sigk_lookup),
+// --max-seqs-per-file N (the constant of :18, default 100000; tests).
 #include "function_caller.h"
 
 #include <atomic>
@@ -32,6 +33,7 @@ struct Options {
     std::vector<std::string> definition_dirs, fasta_dirs, fasta_keep_dirs, good_function_files, good_role_files;
     fs::path deleted_fids_file, ignored_functions_file, kmer_data_dir, final_kmers, perfect_hash, perfect_hash_data, dump_packed, sigk_table;
     bool no_recall = false, host_recall = false;
+    int max_seqs_per_file = 100000;                                 // MaxSequencesPerFile, :18
     std::string nudb_file;
     int min_reps_required = 3, n_threads = 1, device = 0;
     bool sorted_files = false, help = false;
@@ -52,7 +54,7 @@ void usage(const char *argv0) {
               << "  --final-kmers arg                    Write final.kmers file\n"
               << "  --n-threads arg                      (accepted; the build runs on the GPU)\n"
               << "  --perfect-hash arg / --perfect-hash-data arg  (accepted; cmph output is not built)\n"
-              << "  --device arg / --sorted-files / --dump-packed arg / --sigk-table arg / --no-recall / --host-recall\n"
+              << "  --device arg / --sorted-files / --dump-packed arg / --sigk-table arg / --no-recall / --host-recall / --max-seqs-per-file arg\n"
               << "  -h [ --help ]                        show this help message\n";
 }
 
@@ -94,6 +96,7 @@ bool parse(int argc, char **argv, Options &o) {
         else if (a == "--sigk-table") o.sigk_table = next();
         else if (a == "--no-recall") o.no_recall = true;
         else if (a == "--host-recall") o.host_recall = true;
+        else if (a == "--max-seqs-per-file") o.max_seqs_per_file = std::stoi(next());
         else { std::cerr << "unrecognised option '" << a << "'\n"; return false; }
     }
     return true;
@@ -117,7 +120,7 @@ int main(int argc, char **argv) {
     load_strings(o.good_function_files, good_functions);
     load_strings(o.good_role_files, good_roles);
 
-    HostSignatureBuilder builder(o.n_threads, 100000);              // MaxSequencesPerFile, :18
+    HostSignatureBuilder builder(o.n_threads, o.max_seqs_per_file);
     builder.load_function_data(good_functions, good_roles, function_definitions);
     const std::set<std::string> deleted_fids = load_set_from_file(o.deleted_fids_file);
     const std::set<std::string> ignored_functions = load_set_from_file(o.ignored_functions_file);

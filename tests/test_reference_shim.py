@@ -394,3 +394,28 @@ def test_two_tier_contract_holds_for_the_reference_sources(ref, tmp_path):
     np.testing.assert_array_equal(swf_a, swf_b)
     differing = int((ca[3] != cb[3]).sum() + (ca[4] != cb[4]).sum())
     assert differing > 0, "median/var did not depend on the insertion order on this input"
+
+
+def test_sequence_id_collisions_against_reference_sources(ref, tmp_path):
+    """seq_id = file_number * max_seqs_per_file + n (src/signature_build.tcc:91,138): with more proteins in a file
+    than max_seqs_per_file the ids of neighbouring files collide, and num_seqs_with_a_signature — the size of a
+    set of ids (:274) — counts them once.  The constant is 100 000 in the command line; 7 here."""
+    s = Synth(n_proteins=400, n_functions=10, n_genomes=4, seed=66)
+    tree = str(tmp_path / "tree")
+    s.write_tree(tree)
+    ref.ref_set_max_seqs_per_file.argtypes = [C.c_int]
+    ref.ref_set_max_seqs_per_file(7)
+    try:
+        refres = run_reference(ref, tree, str(tmp_path / "ref_out"))
+    finally:
+        ref.ref_set_max_seqs_per_file(100000)
+    out = tmp_path / "our_out"
+    dump = str(tmp_path / "packed.bin")
+    r = subprocess.run([os.path.join(PKG, "kmers-build-signatures"), "-D", os.path.join(tree, "Annotations", "0"), "-F", os.path.join(tree, "Seqs"),
+                        "--kmer-data-dir", str(out), "--sorted-files", "--max-seqs-per-file", "7", "--dump-packed", dump], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    res, starts, func, sid = read_packed(dump)
+    assert len(set(sid.tolist())) < len(sid)                    # ids do collide
+    table, _ = oracle_c.oracle_build(PackedProteins(res.copy(), starts.copy(), func.copy(), sid.copy()))
+    assert_same(refres, table, "colliding sequence ids")
+    assert table.num_seqs_with_a_signature == len(set(sid.tolist())) < 400
