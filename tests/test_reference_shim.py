@@ -419,3 +419,67 @@ def test_sequence_id_collisions_against_reference_sources(ref, tmp_path):
     table, _ = oracle_c.oracle_build(PackedProteins(res.copy(), starts.copy(), func.copy(), sid.copy()))
     assert_same(refres, table, "colliding sequence ids")
     assert table.num_seqs_with_a_signature == len(set(sid.tolist())) < 400
+
+
+def test_float_threshold_divergence_against_reference_sources(ref, tmp_path):
+    """The 80 % rule is `(float) best < float(count) * 0.8f` (src/signature_build.tcc:250-257).  It equals the exact
+    5*best < 4*count below count = 10 485 764; there float(count) * 0.8f rounds DOWN to 8 388 611, so a k-mer with
+    best = 8 388 611 of 10 485 764 occurrences is kept although 5*best < 4*count.  Two homopolymer proteins give
+    exactly that group (and offsets that wrap 16 bits, a length sum that wraps, and a P-square walk of 8.4 M samples)."""
+    tree = str(tmp_path / "tree")
+    os.makedirs(os.path.join(tree, "Annotations", "0"))
+    os.makedirs(os.path.join(tree, "Seqs"))
+    best, count = 8_388_611, 10_485_764
+    assert 5 * best < 4 * count
+    with open(os.path.join(tree, "Annotations", "0", "5000.1"), "w") as f:
+        f.write("fig|5000.1.peg.1\tMajor function\nfig|5000.1.peg.2\tMinor function\n")
+    with open(os.path.join(tree, "Seqs", "5000.1"), "w") as f:
+        f.write(">fig|5000.1.peg.1\n" + "A" * (best + 7) + "\n>fig|5000.1.peg.2\n" + "A" * (count - best + 7) + "\n")
+    good = str(tmp_path / "good.txt")
+    open(good, "w").write("Major function\nMinor function\n")
+    out_ref = str(tmp_path / "ref_out")
+    os.makedirs(out_ref)
+    counters = (C.c_ulonglong * 3)()
+    df = (C.c_uint * 65536)()
+    swf = (C.c_uint * 65536)()
+    ref.ref_signature_build_ex.argtypes = [C.c_char_p] * 6 + [C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+    assert ref.ref_signature_build_ex(os.path.join(tree, "Annotations", "0").encode(), os.path.join(tree, "Seqs").encode(), b"", good.encode(),
+                                      b"", b"", 3, 1, out_ref.encode(), counters, df, swf) == 0
+    kmers, cols = read_table(os.path.join(out_ref, "ref_table.bin"))
+    assert kmers == ["AAAAAAAA"]                                   # kept by the float test
+    out = tmp_path / "our_out"
+    dump = str(tmp_path / "packed.bin")
+    r = subprocess.run([os.path.join(PKG, "kmers-build-signatures"), "-D", os.path.join(tree, "Annotations", "0"), "-F", os.path.join(tree, "Seqs"),
+                        "--kmer-data-dir", str(out), "--good-functions", good, "--sorted-files", "--dump-packed", dump], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    res, starts, func, sid = read_packed(dump)
+    table, _ = oracle_c.oracle_build(PackedProteins(res.copy(), starts.copy(), func.copy(), sid.copy()))
+    assert_same((kmers, cols, list(counters), np.array(df), np.array(swf)), table, "float threshold at 10 485 764")
+    # one occurrence fewer for the major function: rejected by both forms
+    assert table.n_occurrences == count
+
+
+@pytest.mark.gpu
+def test_gpu_float_threshold_divergence(tmp_path):
+    """The same group on the GPU: count = 10 485 764 >= 2^20 takes the float form of the keep rule, the group is
+    reduced by the whole-warp walks and its median / var by the long order-statistics kernel.  (Last GPU test of the
+    suite on purpose: the biggest single group any test builds.)"""
+    from signature_kmers_b200.builder import GpuSignatureBuilder
+    from tests.util import assert_tables_equal, pack
+
+    best, count = 8_388_611, 10_485_764
+    p = pack([b"A" * (best + 7), b"A" * (count - best + 7), b"A" * 20, b"CCCCCCCCCC"], [0, 1, 1, 2])
+    b = GpuSignatureBuilder(device=0)
+    b.set_proteins(p)
+    got = b.build()
+    want, _ = oracle_c.oracle_build(p)
+    assert_tables_equal(got, want, tier_b=True, what="float threshold")
+    # 13 more minor occurrences: 8 388 611 of 10 485 777 is rejected by both forms
+    assert got.row("AAAAAAAA") is None and got.row("CCCCCCCC") is not None
+    p2 = pack([b"A" * (best + 7), b"A" * (count - best + 7)], [0, 1])
+    b.set_proteins(p2)
+    got2 = b.build()
+    want2, _ = oracle_c.oracle_build(p2)
+    assert_tables_equal(got2, want2, tier_b=True, what="float threshold, exact divergence point")
+    assert got2.row("AAAAAAAA")["function_index"] == 0
+    b.close()
