@@ -483,3 +483,47 @@ def test_gpu_float_threshold_divergence(tmp_path):
     assert_tables_equal(got2, want2, tier_b=True, what="float threshold, exact divergence point")
     assert got2.row("AAAAAAAA")["function_index"] == 0
     b.close()
+
+
+@pytest.mark.parametrize("seed", list(range(300, 312)))
+def test_random_trees_against_reference_sources(ref, tmp_path, seed):
+    """Small random protein sets (tests/util.random_proteins: shared domains, mixed functions around the 80 % boundary,
+    ambiguity codes, lower case, ragged lengths, tiny alphabets for heavy duplication) written as trees: oracle ==
+    reference sources on every column and counter."""
+    from tests.util import random_proteins
+
+    rng = np.random.default_rng(seed)
+    alphabet = [b"ACDEFGHIKLMNPQRSTVWY", b"ACDEF", b"AC"][seed % 3]
+    seqs, funcs = random_proteins(seed, n_families=int(rng.integers(3, 25)), members=(1, int(rng.integers(2, 30))),
+                                  length=(5, int(rng.integers(20, 200))), sub_rate=float(rng.choice([0.0, 0.02, 0.1, 0.3])),
+                                  n_functions=int(rng.integers(1, 9)), alphabet=alphabet)
+    n_genomes = int(rng.integers(1, 5))
+    genomes = {"4000%d.1" % g: [] for g in range(n_genomes)}
+    for i, (s, f) in enumerate(zip(seqs, funcs)):
+        g = "4000%d.1" % (i % n_genomes)
+        fn = None if rng.random() < 0.05 else "Function number %d" % f
+        genomes[g].append(("fig|%s.peg.%d" % (g, len(genomes[g]) + 1), fn, s.decode("latin-1")))
+    tree = str(tmp_path / "tree")
+    write_tree(tree, genomes)
+    good = str(tmp_path / "good.txt")
+    open(good, "w").write("".join("Function number %d\n" % f for f in range(0, 9, 2)))     # even ones kept whatever the evidence
+    out_ref = str(tmp_path / "ref_out")
+    os.makedirs(out_ref)
+    counters = (C.c_ulonglong * 3)()
+    df = (C.c_uint * 65536)()
+    swf = (C.c_uint * 65536)()
+    ref.ref_signature_build_ex.argtypes = [C.c_char_p] * 6 + [C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+    min_reps = int(rng.integers(1, 4))
+    assert ref.ref_signature_build_ex(os.path.join(tree, "Annotations", "0").encode(), os.path.join(tree, "Seqs").encode(), b"", good.encode(),
+                                      b"", b"", min_reps, 1, out_ref.encode(), counters, df, swf) == 0
+    kmers, cols = read_table(os.path.join(out_ref, "ref_table.bin"))
+    out = tmp_path / "our_out"
+    dump = str(tmp_path / "packed.bin")
+    r = subprocess.run([os.path.join(PKG, "kmers-build-signatures"), "-D", os.path.join(tree, "Annotations", "0"), "-F", os.path.join(tree, "Seqs"),
+                        "--kmer-data-dir", str(out), "--good-functions", good, "--min-reps-required", str(min_reps), "--sorted-files",
+                        "--dump-packed", dump], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    res, starts, func, sid = read_packed(dump)
+    table, _ = oracle_c.oracle_build(PackedProteins(res.copy(), starts.copy(), func.copy(), sid.copy()))
+    assert_same((kmers, cols, list(counters), np.array(df), np.array(swf)), table, "random tree %d" % seed)
+    assert open(os.path.join(out_ref, "function.index")).read() == open(out / "function.index").read()
