@@ -33,6 +33,12 @@ public:
         auto end() const { return e; }
     };
     range_type range() { return range_type{this->begin(), this->end()}; }
+    struct const_range_type {
+        typename std::unordered_map<K, V, H>::const_iterator b, e;
+        auto begin() const { return b; }
+        auto end() const { return e; }
+    };
+    const_range_type range() const { return const_range_type{this->begin(), this->end()}; }
 };
 
 template <class K, class V, class H = std::hash<K>> class concurrent_unordered_multimap {

@@ -547,4 +547,45 @@ private:
     }
 };
 
+// ---------------------------------------------------------------------------
+// Output files of kmers-build-signatures that are derived from the finished table.
+
+// distinct_functions, src/kmers-build-signatures.cc:230-236: idx \t function \t kept k-mers (here in index order; the
+// reference walks a hash map)
+inline void write_distinct_functions(const fs::path &file, const sigk_table &t, const FunctionMap &fm) {
+    std::ofstream df(file);
+    for (unsigned f = 0; f < 65536; ++f)
+        if (t.distinct_functions[f]) df << f << "\t" << fm.lookup_function((uint16_t)f) << "\t" << t.distinct_functions[f] << "\n";
+}
+
+// recall.report.d/<fasta file>, src/kmers-build-signatures.cc:266-349: the source proteins are called with the new
+// k-mers; every call that differs from the stripped original assignment is reported, ordered by id:
+// id \t original \t original stripped \t call \t function_index \t score.  `lookup` (optional) does the k-mer lookups of a
+// whole file in one batch (libsigk's sigk_lookup); without it every window is fetched from the table on the host.
+using BatchLookup = std::function<int(const uint8_t *, const uint64_t *, uint64_t, uint32_t *)>;
+inline bool write_recall_reports(const FunctionMap &fm, const std::vector<fs::path> &files, const sigk_table &t,
+                                 const fs::path &function_index_file, const fs::path &report_dir, int n_threads, const BatchLookup &lookup) {
+    const SortedKmerDb kdb(t);
+    const FunctionCaller<SortedKmerDb> caller(kdb, function_index_file);
+    std::atomic<bool> failed{false};
+    parallel_for_index(files.size(), n_threads, [&](size_t i) {
+        struct Row { std::string old_func, old_stripped, new_func; int func_index; float score; };
+        std::map<std::string, Row> rows;
+        auto hit_cb = [](const std::string &, const std::array<char, kCallK> &, size_t, double, const StoredKmerData &) {};
+        auto call_cb = [&](const std::string &id, const std::string &func, uint16_t fi, float score, size_t) {
+            std::string orig, orig_stripped;
+            fm.lookup_original_assignment(id, orig, orig_stripped);
+            if (orig_stripped != func) rows.emplace(id, Row{orig, orig_stripped, func, (int)fi, score});
+        };
+        std::ifstream in(files[i]);
+        if (lookup) { if (caller.process_fasta_stream_batched(in, lookup, hit_cb, call_cb)) failed = true; }
+        else caller.process_fasta_stream(in, hit_cb, call_cb);
+        std::ofstream rep(report_dir / files[i].filename());
+        for (const auto &e : rows)
+            rep << e.first << "\t" << e.second.old_func << "\t" << e.second.old_stripped << "\t" << e.second.new_func << "\t"
+                << e.second.func_index << "\t" << e.second.score << "\n";
+    });
+    return !failed;
+}
+
 }  // namespace sigk_host

@@ -99,4 +99,39 @@ int sigk_host_write_final_kmers(const char *path, uint64_t n_rows, const char *k
     return write_final_kmers(path, t, n_threads) ? 0 : 1;
 }
 
+
+// Everything the drop-in command line writes, given the kept table from outside (tests feed the CPU oracle's): the
+// host phases (FunctionMap, gates) run as in kmers-build-signatures, then function.index, otu.index, genomes,
+// final.kmers, distinct_functions and recall.report.d (host lookups) go to out_dir.  File lists in readdir order
+// like the reference's populate_path_list.  Optional files may be "".  Returns 0 on success.
+int sigk_host_outputs(const char *definition_dir, const char *fasta_dir, const char *good_functions_file, const char *good_roles_file,
+                      const char *ignored_functions_file, const char *deleted_fids_file, int min_reps, int n_threads, const char *out_dir,
+                      uint64_t n_rows, const char *kmers, const uint16_t *avg_from_end, const uint16_t *function_index,
+                      const uint16_t *mean, const uint16_t *median, const uint16_t *var, const uint32_t *distinct_functions) {
+    std::vector<fs::path> definitions, fasta;
+    populate_path_list({definition_dir}, definitions);
+    populate_path_list({fasta_dir}, fasta);
+    std::vector<std::string> good_functions, good_roles;
+    if (*good_functions_file) load_strings({good_functions_file}, good_functions);
+    if (*good_roles_file) load_strings({good_roles_file}, good_roles);
+    HostSignatureBuilder builder(n_threads, 100000);
+    builder.load_function_data(good_functions, good_roles, definitions);
+    const std::set<std::string> deleted = load_set_from_file(deleted_fids_file), ignored = load_set_from_file(ignored_functions_file);
+    const fs::path dir = out_dir;
+    ensure_directory(dir);
+    builder.load_fasta(fasta, false, deleted);
+    builder.process_kept_functions(min_reps, dir, ignored);
+    std::ofstream(dir / "otu.index").close();
+    { std::ofstream genomes(dir / "genomes"); genomes << "empty genomes\n"; }
+    sigk_table t{};
+    t.n_kept = n_rows; t.kmer = kmers; t.avg_from_end = avg_from_end; t.function_index = function_index;
+    t.mean = mean; t.median = median; t.var = var; t.distinct_functions = distinct_functions;
+    if (!write_final_kmers(dir / "final.kmers", t, n_threads)) return 1;
+    write_distinct_functions(dir / "distinct_functions", t, builder.function_map());
+    std::error_code ec;
+    fs::create_directory(dir / "recall.report.d", ec);
+    return write_recall_reports(builder.function_map(), builder.all_fasta_data(), t, dir / "function.index", dir / "recall.report.d",
+                                n_threads, BatchLookup()) ? 0 : 1;
+}
+
 }

@@ -163,11 +163,7 @@ int main(int argc, char **argv) {
         if (!write_final_kmers(fk, t, o.n_threads)) { std::cerr << "error writing " << fk << "\n"; return 1; }
         std::cerr << "writing kmers to " << fk << " complete\n";
     }
-    {
-        std::ofstream df(o.kmer_data_dir / "distinct_functions");       // :230-236
-        for (unsigned f = 0; f < 65536; ++f)
-            if (t.distinct_functions[f]) df << f << "\t" << builder.lookup_function((uint16_t)f) << "\t" << t.distinct_functions[f] << "\n";
-    }
+    write_distinct_functions(o.kmer_data_dir / "distinct_functions", t, builder.function_map());
     const fs::path report_dir = o.kmer_data_dir / "recall.report.d";
     std::error_code ec;
     if (!fs::create_directory(report_dir, ec)) std::cerr << "mkdir " << report_dir << " failed\n";
@@ -182,51 +178,20 @@ int main(int argc, char **argv) {
     }
     if (!o.nudb_file.empty()) std::cerr << "note: the NuDB output is not built in this drop-in (library absent)\n";
 
-    // recall of the source data with the new k-mers (:266-349): every call that differs from the stripped
-    // original assignment goes to recall.report.d/<fasta file name>, ordered by id
+    // recall of the source data with the new k-mers (:266-349); the windows of a file are looked up in one batch on
+    // the GPU unless --host-recall asks for host lookups (one handle: one caller at a time)
     if (!o.no_recall) {
-        const SortedKmerDb kdb(t);
-        const FunctionCaller<SortedKmerDb> kmer_caller(kdb, o.kmer_data_dir / "function.index");
-        std::cerr << "Begin recall\n";
-        const auto &files = builder.all_fasta_data();
-        std::atomic<size_t> next{0};
-        std::atomic<bool> failed{false};
         std::mutex lookup_mutex;
-        auto worker = [&] {
-            for (;;) {
-                const size_t i = next.fetch_add(1);
-                if (i >= files.size()) break;
-                struct Row { std::string old_func, old_stripped, new_func; int func_index; float score; };
-                std::map<std::string, Row> rows;
-                auto hit_cb = [](const std::string &, const std::array<char, kCallK> &, size_t, double, const StoredKmerData &) {};
-                auto call_cb = [&](const std::string &id, const std::string &func, uint16_t fi, float score, size_t) {
-                    std::string orig, orig_stripped;
-                    builder.function_map().lookup_original_assignment(id, orig, orig_stripped);
-                    if (orig_stripped != func) rows.emplace(id, Row{orig, orig_stripped, func, (int)fi, score});
-                };
-                std::ifstream in(files[i]);
-                if (o.host_recall) {
-                    kmer_caller.process_fasta_stream(in, hit_cb, call_cb);
-                } else {
-                    // every window of the file looked up in one batch on the GPU (one handle: one caller at a time)
-                    auto lookup = [&](const uint8_t *res, const uint64_t *starts, uint64_t n, uint32_t *rows) {
-                        std::lock_guard<std::mutex> g(lookup_mutex);
-                        return builder.lookup(res, starts, n, rows);
-                    };
-                    if (kmer_caller.process_fasta_stream_batched(in, lookup, hit_cb, call_cb)) failed = true;
-                }
-                std::ofstream rep(report_dir / files[i].filename());
-                for (const auto &e : rows)
-                    rep << e.first << "\t" << e.second.old_func << "\t" << e.second.old_stripped << "\t" << e.second.new_func << "\t"
-                        << e.second.func_index << "\t" << e.second.score << "\n";
-            }
-        };
-        const int nt = std::max(1, std::min<int>(o.n_threads, (int)files.size()));
-        std::vector<std::thread> pool;
-        for (int k = 1; k < nt; ++k) pool.emplace_back(worker);
-        worker();
-        for (auto &th : pool) th.join();
-        if (failed) return 1;
+        BatchLookup lookup;
+        if (!o.host_recall)
+            lookup = [&](const uint8_t *res, const uint64_t *starts, uint64_t n, uint32_t *rows) {
+                std::lock_guard<std::mutex> g(lookup_mutex);
+                return builder.lookup(res, starts, n, rows);
+            };
+        std::cerr << "Begin recall\n";
+        if (!write_recall_reports(builder.function_map(), builder.all_fasta_data(), t, o.kmer_data_dir / "function.index", report_dir,
+                                  o.n_threads, lookup))
+            return 1;
     }
     std::cerr << "all done\n";
     return 0;

@@ -527,3 +527,82 @@ def test_random_trees_against_reference_sources(ref, tmp_path, seed):
     table, _ = oracle_c.oracle_build(PackedProteins(res.copy(), starts.copy(), func.copy(), sid.copy()))
     assert_same((kmers, cols, list(counters), np.array(df), np.array(swf)), table, "random tree %d" % seed)
     assert open(os.path.join(out_ref, "function.index")).read() == open(out / "function.index").read()
+
+
+# ---- the reference's whole command line (its main) over the stand-ins -------------------------------------
+REF_MAIN = os.path.join(ROOT, "oracle", "_ref", "ref-kmers-build-signatures")
+
+
+def host_outputs(tree, out, table, extra=None, min_reps=3, n_threads=2):
+    """The drop-in's host code writes every output file from a table given from outside (libsigk_host.so)."""
+    extra = extra or {}
+    lib = C.CDLL(os.path.join(PKG, "libsigk_host.so"))
+    u16p = np.ctypeslib.ndpointer(dtype=np.uint16, flags="C_CONTIGUOUS")
+    u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+    lib.sigk_host_outputs.argtypes = [C.c_char_p] * 6 + [C.c_int, C.c_int, C.c_char_p, C.c_uint64, C.c_char_p, u16p, u16p, u16p, u16p, u16p, u32p]
+    rc = lib.sigk_host_outputs(os.path.join(tree, "Annotations", "0").encode(), os.path.join(tree, "Seqs").encode(),
+                               extra.get("good_functions", "").encode(), extra.get("good_roles", "").encode(),
+                               extra.get("ignored", "").encode(), extra.get("deleted", "").encode(), min_reps, n_threads, str(out).encode(),
+                               table.n_kept, np.ascontiguousarray(table.kmer).tobytes(), np.ascontiguousarray(table.avg_from_end),
+                               np.ascontiguousarray(table.function_index), np.ascontiguousarray(table.mean), np.ascontiguousarray(table.median),
+                               np.ascontiguousarray(table.var), np.ascontiguousarray(table.distinct_functions, dtype=np.uint32))
+    assert rc == 0
+
+
+@pytest.mark.parametrize("case", ["synthetic", "noisy", "messy"])
+def test_every_output_file_against_the_reference_command_line(ref, tmp_path, case):
+    """The reference's own main() (compiled over the stand-ins) and the drop-in's host code on the same tree: stdout
+    banner and counters, function.index, otu.index, genomes, final.kmers (the reference writes hash order: compared as
+    sorted lines), distinct_functions (likewise), and recall.report.d file by file, byte for byte.  The drop-in's table
+    comes from the CPU oracle here; the GPU tests hold the GPU table to the same oracle."""
+    if not os.path.exists(REF_MAIN):
+        pytest.skip("oracle/_ref/ref-kmers-build-signatures not built (reference checkout absent)")
+    tree = str(tmp_path / "tree")
+    extra = {}
+    if case == "synthetic":
+        Synth(n_proteins=900, n_functions=30, n_genomes=5, seed=67).write_tree(tree)
+    elif case == "noisy":          # some families never reach 3 genomes: their proteins are called differently or not at all
+        Synth(n_proteins=330, n_functions=66, n_genomes=4, seed=68, zipf_s=0.0, mut_rate=0.3).write_tree(tree)
+    else:
+        import shutil
+        shutil.copytree(os.path.join(ROOT, "tests", "golden", "edge", "tree"), tree)
+        for key, name in (("good_functions", "good_functions.txt"), ("good_roles", "good_roles.txt"), ("ignored", "ignored.txt"), ("deleted", "deleted.txt")):
+            extra[key] = str(tmp_path / name)
+            os.replace(os.path.join(tree, name), extra[key])
+    for junk in ("function.index.expected",):
+        if os.path.exists(os.path.join(tree, junk)):
+            os.remove(os.path.join(tree, junk))
+    ref_out = tmp_path / "ref_out"
+    cmd = [REF_MAIN, "-D", os.path.join(tree, "Annotations", "0"), "-F", os.path.join(tree, "Seqs"), "--kmer-data-dir", str(ref_out),
+           "--final-kmers", "final.kmers", "--min-reps-required", "3", "--n-threads", "1"]
+    ours = [os.path.join(PKG, "kmers-build-signatures")] + cmd[1:5] + ["--kmer-data-dir", str(tmp_path / "dump_out"), "--min-reps-required", "3"]
+    for flag, key in (("--good-functions", "good_functions"), ("--good-roles", "good_roles"), ("--ignored-functions-file", "ignored"),
+                      ("--deleted-features-file", "deleted")):
+        if key in extra:
+            cmd += [flag, extra[key]]
+            ours += [flag, extra[key]]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    # the oracle's table for the same tree (packed proteins from the drop-in's host code, readdir order like the reference)
+    dump = str(tmp_path / "packed.bin")
+    d = subprocess.run(ours + ["--dump-packed", dump], capture_output=True, text=True)
+    assert d.returncode == 0, d.stderr
+    res, starts, func, sid = read_packed(dump)
+    table, _ = oracle_c.oracle_build(PackedProteins(res.copy(), starts.copy(), func.copy(), sid.copy()))
+    our_out = tmp_path / "our_out"
+    host_outputs(tree, our_out, table, extra)
+
+    ref_lines = r.stdout.splitlines()
+    assert d.stdout.splitlines()[:4] == ref_lines[:4]                       # definitions / fasta / keep / kept N functions
+    assert ref_lines[4:7] == ["Kept %d kmers" % table.n_kept, "distinct_signatures=%d" % table.distinct_signatures,
+                              "num_seqs_with_a_signature=%d" % table.num_seqs_with_a_signature]
+    for name in ("function.index", "otu.index", "genomes"):
+        assert open(ref_out / name).read() == open(our_out / name).read(), name
+    assert sorted(open(ref_out / "final.kmers").read().splitlines()) == open(our_out / "final.kmers").read().splitlines()
+    assert sorted(open(ref_out / "distinct_functions").read().splitlines(), key=lambda l: int(l.split("\t")[0])) == \
+        open(our_out / "distinct_functions").read().splitlines()
+    ref_reports = {f: open(ref_out / "recall.report.d" / f).read() for f in os.listdir(ref_out / "recall.report.d")}
+    our_reports = {f: open(our_out / "recall.report.d" / f).read() for f in os.listdir(our_out / "recall.report.d")}
+    assert ref_reports == our_reports
+    if case == "messy":
+        assert sum(len(v) for v in ref_reports.values()) > 0                # un-kept, ignored and truncated assignments are reported
