@@ -100,7 +100,7 @@ int sigk_host_write_final_kmers(const char *path, uint64_t n_rows, const char *k
 }
 
 
-// Everything the drop-in command line writes, given the kept table from outside (tests feed the CPU oracle's): the
+// Everything the drop-in command line writes, given the kept table from outside (tests pass one in): the
 // host phases (FunctionMap, gates) run as in kmers-build-signatures, then function.index, otu.index, genomes,
 // final.kmers, distinct_functions and recall.report.d (host lookups) go to out_dir.  File lists in readdir order
 // like the reference's populate_path_list.  Optional files may be "".  Returns 0 on success.
