@@ -15,6 +15,9 @@ and does not pin).  For every case this script writes the input tree and what th
     <case>/function.index   as the reference's writer printed it
     <case>/queries.fa, <case>/calls.txt                 call side: FASTA queries and the reference caller's output
                                                         ("#call" region lines, then id, function, index, score)
+    <case>/expected/stdout.txt, distinct_functions, recall.report.d/*
+                                                        what the reference's whole command line (its main, compiled
+                                                        as oracle/_ref/ref-kmers-build-signatures) printed and wrote
 
 tests/test_golden.py checks the CPU oracle, the drop-in's host code and (on a GPU) the whole drop-in against these
 files; nothing there needs /root/reference or oracle/_ref.
@@ -88,6 +91,35 @@ def finish_case(sig, call, case_dir, queries, opts):
     assert m <= len(buf)
     open(os.path.join(case_dir, "calls.txt"), "wb").write(buf.raw[:m])
     shutil.rmtree(out)
+    # the reference's whole command line on the same tree: stdout and the files it derives from the table
+    main_out = os.path.join(case_dir, "_main")
+    cmd = [os.path.join(ROOT, "oracle", "_ref", "ref-kmers-build-signatures"), "-D", os.path.join(tree, "Annotations", "0"),
+           "-F", os.path.join(tree, "Seqs"), "--kmer-data-dir", main_out, "--final-kmers", "final.kmers", "--min-reps-required", "3",
+           "--n-threads", "1"]
+    for flag, name in (("--good-functions", "good_functions.txt"), ("--good-roles", "good_roles.txt"),
+                       ("--ignored-functions-file", "ignored.txt"), ("--deleted-features-file", "deleted.txt")):
+        if opts.get(name):
+            cmd += [flag, os.path.join(tree, name)]
+    import subprocess
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=case_dir)
+    assert r.returncode == 0, r.stderr
+    exp = os.path.join(case_dir, "expected")
+    shutil.rmtree(exp, ignore_errors=True)
+    os.makedirs(os.path.join(exp, "recall.report.d"))
+    # stdout without the three path lines (they echo the caller's directories)
+    open(os.path.join(exp, "stdout.txt"), "w").write("".join(l + "\n" for l in r.stdout.splitlines()[3:]))
+    lines = sorted(open(os.path.join(main_out, "distinct_functions")).read().splitlines(), key=lambda l: int(l.split("\t")[0]))
+    open(os.path.join(exp, "distinct_functions"), "w").write("".join(l + "\n" for l in lines))        # index order (the reference: hash order)
+    for f in os.listdir(os.path.join(main_out, "recall.report.d")):
+        shutil.copy(os.path.join(main_out, "recall.report.d", f), os.path.join(exp, "recall.report.d", f))
+    # final.kmers is the first three columns of table.tsv.gz; checked here, not stored twice
+    want = sorted(open(os.path.join(main_out, "final.kmers")).read().splitlines())
+    assert want == ["%s\t%d\t%d\t" % (kmers[8 * i:8 * i + 8].decode("latin-1"), cols[0][i], cols[1][i]) for i in range(n)]
+    # (the main reads the files in readdir order, the fixtures above were made in sorted order: the statistics columns of
+    # function.index and median / var depend on that order, names, counters, calls and recall reports do not)
+    names = lambda path: [l.split("\t")[:2] for l in open(path).read().splitlines()]
+    assert names(os.path.join(main_out, "function.index")) == names(os.path.join(case_dir, "function.index"))
+    shutil.rmtree(main_out)
     print("%s: %d kept k-mers, %d queries" % (os.path.basename(case_dir), n, len(queries)))
 
 

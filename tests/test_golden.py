@@ -119,3 +119,33 @@ def test_gpu_dropin_reproduces_the_reference_outputs(built, tmp_path, case):
     lines = open(out / "final.kmers").read().splitlines()
     assert lines == ["%s\t%d\t%d\t" % (k, a, f) for k, a, f in zip(gk, gcols[0], gcols[1])]
     assert open(out / "function.index").read() == open(os.path.join(GOLDEN, case, "function.index")).read()
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_host_outputs_reproduce_the_reference_command_line(built, tmp_path, case):
+    """What the reference's whole command line printed and wrote for the golden trees (expected/), against the files
+    the drop-in's host code writes from the golden table: counters, distinct_functions, recall.report.d."""
+    tree = os.path.join(GOLDEN, case, "tree")
+    kmers, cols, counters = golden_table(case)
+    lib = C.CDLL(os.path.join(PKG, "libsigk_host.so"))
+    u16p = np.ctypeslib.ndpointer(dtype=np.uint16, flags="C_CONTIGUOUS")
+    u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+    lib.sigk_host_outputs.argtypes = [C.c_char_p] * 6 + [C.c_int, C.c_int, C.c_char_p, C.c_uint64, C.c_char_p, u16p, u16p, u16p, u16p, u16p, u32p]
+    opt = lambda name: (os.path.join(tree, name) if os.path.exists(os.path.join(tree, name)) else "").encode()
+    df = np.zeros(65536, dtype=np.uint32)
+    for k, v in counters["distinct_functions"].items():
+        df[int(k)] = v
+    out = tmp_path / "out"
+    rc = lib.sigk_host_outputs(os.path.join(tree, "Annotations", "0").encode(), os.path.join(tree, "Seqs").encode(), opt("good_functions.txt"),
+                               opt("good_roles.txt"), opt("ignored.txt"), opt("deleted.txt"), 3, 2, str(out).encode(), len(kmers),
+                               "".join(kmers).encode("latin-1"), *[np.ascontiguousarray(c) for c in cols], df)
+    assert rc == 0
+    exp = os.path.join(GOLDEN, case, "expected")
+    assert open(out / "distinct_functions").read() == open(os.path.join(exp, "distinct_functions")).read()
+    want = {f: open(os.path.join(exp, "recall.report.d", f)).read() for f in os.listdir(os.path.join(exp, "recall.report.d"))}
+    got = {f: open(out / "recall.report.d" / f).read() for f in os.listdir(out / "recall.report.d")}
+    assert got == want
+    stdout = open(os.path.join(exp, "stdout.txt")).read().splitlines()
+    assert stdout[1:4] == ["Kept %d kmers" % counters["kept"], "distinct_signatures=%d" % counters["distinct_signatures"],
+                           "num_seqs_with_a_signature=%d" % counters["num_seqs_with_a_signature"]]
+    assert open(out / "final.kmers").read().splitlines() == ["%s\t%d\t%d\t" % (k, a, f) for k, a, f in zip(kmers, cols[0], cols[1])]
