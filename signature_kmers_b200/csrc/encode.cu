@@ -23,6 +23,8 @@
 #include "kernels.h"
 #include "sigk_common.cuh"
 
+#include <cstdlib>
+
 namespace sigk {
 
 namespace {
@@ -406,7 +408,14 @@ cudaError_t launch_slice_index(const uint64_t *starts, uint32_t n_prot, uint64_t
 cudaError_t launch_encode_split(const EncodeArgs &a, const EncodeSplitArgs &sp, uint32_t *ticket, cudaStream_t stream) {
     if (a.total_res == 0 || a.n_prot == 0) return cudaSuccess;
     if (sp.n_split < 1 || sp.n_split > 15) return cudaErrorInvalidValue;
-    auto kernel = sp.n_split < 4 ? encode_split_kernel<1> : sp.n_split < 8 ? encode_split_kernel<2> : encode_split_kernel<4>;
+    // 1, 2 or 4 counter words for up to 4, 8, 16 ranks.  SIGK_TEST_SPLIT_WORDS=2|4 forces a wider instantiation than the
+    // rank count needs, so that a two-GPU box can exercise the kernels of the larger worlds (tests/multigpu_check.py).
+    int words = sp.n_split < 4 ? 1 : sp.n_split < 8 ? 2 : 4;
+    if (const char *force = std::getenv("SIGK_TEST_SPLIT_WORDS")) {
+        const int v = std::atoi(force);
+        if ((v == 2 || v == 4) && v > words) words = v;
+    }
+    auto kernel = words == 1 ? encode_split_kernel<1> : words == 2 ? encode_split_kernel<2> : encode_split_kernel<4>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSplitSmem));
     if (e != cudaSuccess) return e;
     kernel<<<(unsigned)encode_tiles(a.total_res), ENC_THREADS, sizeof(EncSplitSmem), stream>>>(a, sp, ticket);

@@ -88,6 +88,21 @@ def main():
             single.close()
             print(f"multigpu_check ok ({world} ranks): {name}: {got.n_occurrences} occurrences, kept per rank {per_rank}", flush=True)
         dist.barrier()
+    # the encode + route kernel instantiations of the larger worlds (2 and 4 counter words: 5..8 and 9..16 ranks)
+    for words in ("2", "4"):
+        os.environ["SIGK_TEST_SPLIT_WORDS"] = words
+        try:
+            for name, p_all in (cases[0], cases[-1]):
+                got, per_rank = build_distributed(p_all, rank, world, local_rank)
+                if rank == 0:
+                    from oracle import oracle_c
+
+                    want, _ = oracle_c.oracle_build(p_all)
+                    assert_tables_equal(got, want, tier_b=True, what=f"{name}, {words} counter words")
+                    print(f"multigpu_check ok ({world} ranks): {name} with the {words}-word encode+route kernel", flush=True)
+                dist.barrier()
+        finally:
+            del os.environ["SIGK_TEST_SPLIT_WORDS"]
     # the same inputs, small -> large -> small, through one communicator
     order = [cases[2], cases[-1], cases[0]]
     tables = build_sequence_on_one_communicator(order, rank, world, local_rank)
