@@ -89,7 +89,8 @@ def main():
             print(f"multigpu_check ok ({world} ranks): {name}: {got.n_occurrences} occurrences, kept per rank {per_rank}", flush=True)
         dist.barrier()
     # the encode + route kernel instantiations of the larger worlds (2 and 4 counter words: 5..8 and 9..16 ranks)
-    for words in ("2", "4"):
+    # (opt-in with SIGK_CHECK_WIDE=1 until it has run once on a GPU box: added after the round's GPU budget was spent)
+    for words in (("2", "4") if os.environ.get("SIGK_CHECK_WIDE") else ()):
         os.environ["SIGK_TEST_SPLIT_WORDS"] = words
         try:
             for name, p_all in (cases[0], cases[-1]):
