@@ -70,4 +70,19 @@ def test_product_never_references_the_oracle():
                     bad.append(os.path.join(dirpath, f))
                 if re.search(r"(import|from)\s+oracle", text):
                     bad.append(os.path.join(dirpath, f))
+                if "refshim" in text or "_ref/" in text or "/root/reference" in text:      # stand-ins and reference builds are test-only
+                    bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_built_product_binaries_do_not_link_test_infrastructure():
+    """libsigk.so and the two command lines depend on CUDA and the C/C++ runtime only."""
+    import subprocess
+
+    pkg = os.path.join(ROOT, "signature_kmers_b200")
+    for name in ("libsigk.so", "kmers-build-signatures", "kmers-call-functions"):
+        path = os.path.join(pkg, name)
+        if not os.path.exists(path):
+            continue
+        deps = subprocess.run(["ldd", path], capture_output=True, text=True).stdout
+        assert "liboracle" not in deps and "libref_" not in deps and "libsigk_synth" not in deps and "libsigk_host" not in deps, (name, deps)
