@@ -606,3 +606,16 @@ def test_every_output_file_against_the_reference_command_line(ref, tmp_path, cas
     assert ref_reports == our_reports
     if case == "messy":
         assert sum(len(v) for v in ref_reports.values()) > 0                # un-kept, ignored and truncated assignments are reported
+
+
+def test_config1_kept_table_equals_reference_sources(ref, tmp_path):
+    """BASELINE.json configs[0] at its full size (20 K proteins / 1 K functions, 5.9 M occurrences, 4.4 M kept
+    k-mers): the kept table of the reference's own sources, every row and column, against the CPU oracle fed by the
+    drop-in's host code.  (About 20 s: the stand-in containers are serial.)"""
+    tree = str(tmp_path / "tree")
+    Synth.config("config1").write_tree(tree)
+    refres = run_reference(ref, tree, str(tmp_path / "ref_out"))
+    table = run_oracle_through_dropin(tree, tmp_path / "our_out", str(tmp_path))
+    assert table.n_kept > 4_000_000
+    assert_same(refres, table, "config1")
+    assert open(tmp_path / "ref_out" / "function.index").read() == open(tmp_path / "our_out" / "function.index").read()
