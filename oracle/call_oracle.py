@@ -201,7 +201,9 @@ class FunctionCaller:
         by_func = {}
         for c in merged:
             by_func[c["function_index"]] = by_func.get(c["function_index"], 0) + c["count"]
-        vec = sorted(by_func.items(), key=lambda e: (-e[1], e[0]))
+        vec = sorted(by_func.items())                  # std::map order: ascending function index
+        if len(vec) > 1:
+            libstdcxx_partial_sort(vec, 2, lambda a, b: a[1] > b[1])
         offset = vec[0][1] if len(vec) == 1 else vec[0][1] - vec[1][1]
         if offset >= 5:
             return vec[0][0], self.fn(vec[0][0]), F32(vec[0][1])
@@ -215,6 +217,57 @@ class FunctionCaller:
 
     def call(self, seq: str):
         return self.find_best_call(self.process_aa_seq(seq))
+
+
+# ---- std::partial_sort as libstdc++ implements it (bits/stl_heap.h, bits/stl_algo.h) ---------------------------
+# find_best_call sorts only the first two entries (src/call_functions.tcc:594-599) and then reads vec[2]: what is
+# left there is whatever the heap selection happened to leave, so the algorithm is restated step by step.
+def _push_heap(v, hole, top, value, comp):
+    parent = (hole - 1) // 2
+    while hole > top and comp(v[parent], value):
+        v[hole] = v[parent]
+        hole = parent
+        parent = (hole - 1) // 2
+    v[hole] = value
+
+
+def _adjust_heap(v, hole, length, value, comp):
+    top = hole
+    child = hole
+    while child < (length - 1) // 2:
+        child = 2 * (child + 1)
+        if comp(v[child], v[child - 1]):
+            child -= 1
+        v[hole] = v[child]
+        hole = child
+    if length % 2 == 0 and child == (length - 2) // 2:
+        child = 2 * (child + 1)
+        v[hole] = v[child - 1]
+        hole = child - 1
+    _push_heap(v, hole, top, value, comp)
+
+
+def libstdcxx_partial_sort(v, middle, comp):
+    """std::partial_sort(v.begin(), v.begin() + middle, v.end(), comp), in place."""
+    n = len(v)
+    if middle >= 2:                                     # __make_heap(first, middle)
+        parent = (middle - 2) // 2
+        while True:
+            _adjust_heap(v, parent, middle, v[parent], comp)
+            if parent == 0:
+                break
+            parent -= 1
+    for i in range(middle, n):                          # __heap_select
+        if comp(v[i], v[0]):
+            value = v[i]                                # __pop_heap(first, middle, i)
+            v[i] = v[0]
+            _adjust_heap(v, 0, middle, value, comp)
+    last = middle                                       # __sort_heap(first, middle)
+    while last > 1:
+        last -= 1
+        value = v[last]
+        v[last] = v[0]
+        _adjust_heap(v, 0, last, value, comp)
 
 
 def format_score(x) -> str:

@@ -316,9 +316,13 @@ public:
         std::map<int, int> by_func;
         for (const auto &c : merged) by_func[c.function_index] += c.count;
         std::vector<std::pair<int, int>> vec(by_func.begin(), by_func.end());
-        // the reference partial_sorts the first two by count; equal counts can never change the outcome
-        // (a tie for first gives offset 0 and a symmetric "f1 ?? f2"; a tie for second gives pair offset 0)
-        std::stable_sort(vec.begin(), vec.end(), [](const auto &a, const auto &b) { return a.second > b.second; });
+        // Exactly the reference's call (:594-599): only the first two places are sorted, and the code below reads
+        // vec[2] all the same — which element std::partial_sort leaves there is unspecified by the standard but
+        // fixed for a given standard library, and it decides whether "f1 ?? f2" is named when the two best are
+        // within 5 hits.  The same call on the same input order (the std::map walk above) reproduces it under
+        // libstdc++, the reference's library (g++, Makefile:42); found by fuzzing against the reference's sources.
+        if (vec.size() > 1)
+            std::partial_sort(vec.begin(), vec.begin() + 2, vec.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.second > b.second; });
 
         out.score_offset = vec.size() == 1 ? (float)vec[0].second : (float)(vec[0].second - vec[1].second);
         if (out.score_offset >= 5.0f) {

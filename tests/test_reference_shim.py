@@ -485,7 +485,7 @@ def test_gpu_float_threshold_divergence(tmp_path):
     b.close()
 
 
-@pytest.mark.parametrize("seed", list(range(300, 312)))
+@pytest.mark.parametrize("seed", list(range(300, 340)))
 def test_random_trees_against_reference_sources(ref, tmp_path, seed):
     """Small random protein sets (tests/util.random_proteins: shared domains, mixed functions around the 80 % boundary,
     ambiguity codes, lower case, ragged lengths, tiny alphabets for heavy duplication) written as trees: oracle ==
@@ -619,3 +619,51 @@ def test_config1_kept_table_equals_reference_sources(ref, tmp_path):
     assert table.n_kept > 4_000_000
     assert_same(refres, table, "config1")
     assert open(tmp_path / "ref_out" / "function.index").read() == open(tmp_path / "our_out" / "function.index").read()
+
+
+def test_function_caller_fuzz_against_reference_sources(ref_call, tmp_path):
+    """Random hit patterns through the whole call state machine: regions of 1..40 hits, spacers longer than max_gap
+    (200), functions alternating hit by hit, k-mers whose stored lengths vary (so the median absolute deviation is not
+    the default 30) or sit far from the query length (regions that fail their length test), ambiguity codes inside
+    regions, the fusion naming.  host/function_caller.h == the reference's call_functions.tcc, line by line."""
+    import random
+
+    import tests.test_function_caller as tfc
+
+    host = tfc.load_host()
+    names = ["Alpha synthase", "Beta kinase", "Alpha synthase / Beta kinase", "hypothetical protein", "Gamma lyase", "Delta ligase / Gamma lyase"]
+    rng = random.Random(77)
+    n_lines = n_calls = 0
+    for trial in range(250):
+        rows, q = {}, ""
+        qlen_guess = rng.choice([120, 300, 600])
+        for seg in range(rng.randrange(1, 10)):
+            kind = rng.random()
+            if kind < 0.25:                                           # spacer: residues that are in no table k-mer
+                q += "".join(rng.choice("wy") for _ in range(rng.choice([0, 3, 9, 150, 199, 200, 201, 260])))
+                continue
+            fi = rng.randrange(len(names))
+            length = rng.randrange(8, 48)
+            seq = "".join(rng.choice(tfc.AA) for _ in range(length))
+            if kind > 0.9 and length > 20:
+                seq = seq[:10] + rng.choice("X*") + seq[11:]
+            spread = rng.choice([0, 0, 5, 40, 400])
+            for p in range(len(seq) - 7):
+                k = seq[p:p + 8]
+                if "X" in k or "*" in k:
+                    continue
+                f2 = fi if rng.random() > 0.15 else rng.randrange(len(names))     # a stray hit for another function
+                rows[k] = (len(seq) - p, f2, max(0, min(65535, qlen_guess + rng.randint(-spread, spread))), 0, 0)
+            q += seq
+        if not rows:
+            continue
+        table = tfc.Table(rows)
+        fasta = tfc.to_fasta([("q%d" % trial, q)])
+        for hypo in (False, True):
+            want = ref_calls(ref_call, table, names, fasta, tmp_path, ignore_hypo=hypo)
+            got = tfc.cxx_calls(host, table, names, fasta, ignore_hypo=hypo)
+            assert got == want, (trial, q)
+            assert tfc.oracle_calls(table, names, [("q%d" % trial, q)], ignore_hypo=hypo) == want, (trial, q)    # the Python restatement too
+            n_lines += len(want)
+            n_calls += sum(1 for l in want if l.startswith("#call"))
+    assert n_lines > 500 and n_calls > 100
