@@ -667,3 +667,76 @@ def test_function_caller_fuzz_against_reference_sources(ref_call, tmp_path):
             n_lines += len(want)
             n_calls += sum(1 for l in want if l.startswith("#call"))
     assert n_lines > 500 and n_calls > 100
+
+
+@pytest.mark.parametrize("seed", list(range(500, 620)))
+def test_assignment_text_fuzz_against_reference_sources(ref, tmp_path, seed):
+    """Random assignment and definition-line texts built from the pieces the SEED conventions care about (comment
+    markers with and without blanks, truncation words, role separators, [genome] brackets, tabs, repeated blanks):
+    kept functions, their indices, function.index and the kept table of the reference's sources vs the drop-in's
+    hand-matched text handling (host/seed_text.h, FunctionMap)."""
+    import random
+
+    rng = random.Random(seed)
+    bases = ["Alpha synthase", "Beta kinase (EC 2.7.1.1)", "Gamma lyase", "Delta ligase", "hypothetical protein", "Epsilon pump subunit B",
+             "Zeta-channel protein", "Eta factor"]
+    seps = [" / ", " @ ", "; ", " /", "/ ", " ; ", " @", "@"]
+    comments = ["", "", "", " # truncated", " # fragment", " # frameshift", " ## missing start", " #truncated", "# note", "  #  trunc at end",
+                " ! comment", " # ", " #", " ### x", " # Truncated", " # frag"]
+
+    def function_text():
+        f = rng.choice(bases)
+        if rng.random() < 0.3:
+            f += rng.choice(seps) + rng.choice(bases)
+        if rng.random() < 0.1:
+            f = " " + f
+        if rng.random() < 0.1:
+            f += " "
+        return f + rng.choice(comments)
+
+    aa = "ACDEFGHIKLMNPQRSTVWY"
+    protein = {b: "".join(rng.choice(aa) for _ in range(rng.randrange(30, 90))) for b in bases}
+    tree = str(tmp_path / "tree")
+    os.makedirs(os.path.join(tree, "Annotations", "0"))
+    os.makedirs(os.path.join(tree, "Seqs"))
+    for gi in range(rng.randrange(2, 5)):
+        g = "6000%d.1" % gi
+        with open(os.path.join(tree, "Annotations", "0", g), "w") as ann, open(os.path.join(tree, "Seqs", g), "w") as fa:
+            for n in range(1, rng.randrange(8, 25)):
+                rid = "fig|%s.peg.%d" % (g, n) if rng.random() > 0.1 else "other%d_%d" % (gi, n)
+                text = function_text()
+                base = next(b for b in bases if b in text)
+                seq = "".join(c if rng.random() > 0.05 else rng.choice(aa) for c in protein[base])
+                how = rng.random()
+                definition = ""
+                if how < 0.6:
+                    ann.write("%s\t%s\n" % (rid, text))
+                elif how < 0.8:
+                    definition = " " + function_text() + (" [Genome %d.%d]" % (gi, n % 3) if rng.random() < 0.6 else "")
+                elif how < 0.9:
+                    ann.write("%s\t%s\n" % (rid, text))
+                    definition = rng.choice([" ", "  ", "\t"]) + function_text() + rng.choice(["", " [g]", " [a] [b]", " []", " [x]y"])
+                if rng.random() < 0.05:
+                    ann.write("%s\t%s\textra column\n" % (rid, function_text()))          # a second assignment for the same id
+                fa.write(">%s%s\n%s\n" % (rid, definition, seq))
+    good_roles = str(tmp_path / "good_roles.txt")
+    open(good_roles, "w").write("Gamma lyase\nEta factor\n")
+    out_ref = str(tmp_path / "ref_out")
+    os.makedirs(out_ref)
+    counters = (C.c_ulonglong * 3)()
+    df = (C.c_uint * 65536)()
+    swf = (C.c_uint * 65536)()
+    ref.ref_signature_build_ex.argtypes = [C.c_char_p] * 6 + [C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+    assert ref.ref_signature_build_ex(os.path.join(tree, "Annotations", "0").encode(), os.path.join(tree, "Seqs").encode(), b"", b"",
+                                      good_roles.encode(), b"", 2, 1, out_ref.encode(), counters, df, swf) == 0
+    kmers, cols = read_table(os.path.join(out_ref, "ref_table.bin"))
+    out = tmp_path / "our_out"
+    dump = str(tmp_path / "packed.bin")
+    r = subprocess.run([os.path.join(PKG, "kmers-build-signatures"), "-D", os.path.join(tree, "Annotations", "0"), "-F", os.path.join(tree, "Seqs"),
+                        "--kmer-data-dir", str(out), "--good-roles", good_roles, "--min-reps-required", "2", "--sorted-files", "--dump-packed", dump],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(os.path.join(out_ref, "function.index")).read() == open(out / "function.index").read()
+    res, starts, func, sid = read_packed(dump)
+    table, _ = oracle_c.oracle_build(PackedProteins(res.copy(), starts.copy(), func.copy(), sid.copy()))
+    assert_same((kmers, cols, list(counters), np.array(df), np.array(swf)), table, "assignment text fuzz %d" % seed)
