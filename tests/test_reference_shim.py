@@ -634,7 +634,7 @@ def test_function_caller_fuzz_against_reference_sources(ref_call, tmp_path):
     names = ["Alpha synthase", "Beta kinase", "Alpha synthase / Beta kinase", "hypothetical protein", "Gamma lyase", "Delta ligase / Gamma lyase"]
     rng = random.Random(77)
     n_lines = n_calls = 0
-    for trial in range(250):
+    for trial in range(800):
         rows, q = {}, ""
         qlen_guess = rng.choice([120, 300, 600])
         for seg in range(rng.randrange(1, 10)):
