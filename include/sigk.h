@@ -170,8 +170,6 @@ int sigk_event_elapsed_ms(sigk_handle *h, int slot_a, int slot_b, float *ms);
 #define SIGK_COMM_ID_BYTES 128
 int sigk_comm_make_id(void *id128);
 int sigk_comm_join(sigk_handle *h, const void *id128);
-/* Reduce the per-rank counters/bitmaps so that rank 0's sigk_result carries
- * whole-job statistics. */
 
 /* ---- stand-alone kernels, exported for the parity tests -------------------
  * Each runs one stage on host arrays through a temporary device copy.       */

@@ -70,6 +70,12 @@ public:
         uint64_t n = 0;
         bool ok = std::fread(magic, 1, 8, f) == 8 && std::memcmp(magic, "SIGKTBL1", 8) == 0 && std::fread(&n, 8, 1, f) == 1;
         if (ok) {
+            // the header's row count must agree with the file size (16 + 18 n) before anything is sized from it
+            std::error_code fec;
+            const uintmax_t sz = fs::file_size(file, fec);
+            ok = !fec && n <= (UINT64_MAX - 16) / 18 && sz == 16 + 18 * (uintmax_t)n;
+        }
+        if (ok) {
             own_kmer_.resize(n * 8);
             for (auto &c : own_cols_) c.resize(n);
             ok = std::fread(own_kmer_.data(), 8, n, f) == n;
