@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SIGK_ABI_VERSION 1
+#define SIGK_ABI_VERSION 2
 
 #define SIGK_K 8                    /* src/kmers-build-signatures.cc:17 (const int K = 8) */
 #define SIGK_UNDEFINED_FUNCTION 0xFFFFu   /* src/kmer_data.h:23 */
@@ -88,8 +88,17 @@ typedef struct sigk_proteins {
 } sigk_proteins;
 
 /* Kept-k-mer table: one row per KeptKmer<8> (src/signature_build.h:34-42),
- * struct-of-arrays, rows sorted by k-mer bytes (ascending unsigned-char order;
- * the reference's own order is TBB hash order and no consumer depends on it).
+ * struct-of-arrays, in two sorted sections (the reference's own order is TBB
+ * hash order and no consumer depends on it):
+ *   rows [0, n_upper)        k-mers without a lower-case residue, ascending
+ *                            unsigned-char order of their 8 bytes;
+ *   rows [n_upper, n_kept)   k-mers with at least one lower-case residue (the
+ *                            reference keeps case: 'a' != 'A',
+ *                            src/signature_build.tcc:167), ascending by
+ *                            (upper-cased bytes, then the case mask: bit j set
+ *                            iff residue j is lower case).
+ * A lookup is a binary search in the section the query's case pattern picks
+ * (sigk_lookup, SortedKmerDb).
  * Columns are the StoredKmerData fields (src/kmer_data.h:114-128).  Pointers
  * are host memory owned by the handle, valid until the next build or destroy.
  * The three counters are the ones process_kmers prints
@@ -109,14 +118,15 @@ typedef struct sigk_table {
     uint64_t num_seqs_with_a_signature;
     const uint32_t *distinct_functions; /* [65536] kept k-mers per function */
     const uint32_t *seqs_with_func;     /* [65536] proteins per function (:160) */
+    uint64_t n_upper;                   /* rows of the first section (see above); ignored by sigk_set_table */
 } sigk_table;
 
 /* Device time of the last build, CUDA events on the library's own stream. */
 typedef struct sigk_timings {
     float h2d_ms;
-    float encode_ms;        /* count + encode (+ first radix pass when fused) */
-    float histogram_ms;
-    float sort_ms;          /* all onesweep passes */
+    float encode_ms;        /* everything before the first radix pass: protein table, window count (one GPU) or encode + route (multi-GPU) */
+    float histogram_ms;     /* digit histogram of already encoded records (multi-GPU and the unfused path) */
+    float sort_ms;          /* all onesweep passes, the fused encode + first pass included, and the side run's sort */
     float reduce_ms;        /* giant pre-pass + streaming segment reduce + keep/reject */
     float order_stats_ms;   /* median/var worklist */
     float squeeze_ms;       /* ordered compaction of kept rows into the table columns */
@@ -127,7 +137,9 @@ typedef struct sigk_timings {
     uint32_t record_bytes;
     uint32_t key_bytes;
     uint32_t kernel_launches;
-    float pass_ms[8];       /* per onesweep pass */
+    float pass_ms[8];       /* per onesweep pass of the main run; [0] is the first pass (fused with the encode on one GPU) */
+    float count_ms;         /* window count pass (digit histograms from the residues) */
+    float side_sort_ms;     /* histogram + passes of the side run (records with a lower-case residue) */
 } sigk_timings;
 
 const char *sigk_version(void);
@@ -165,8 +177,9 @@ int sigk_event_elapsed_ms(sigk_handle *h, int slot_a, int slot_b, float *ms);
 /* Multi-GPU (one process per GPU): rank 0 makes an id, the launcher ships the
  * 128 bytes to every rank, every rank joins.  After that sigk_build routes
  * each record to the rank that owns its k-mer range (one all-to-all) and
- * returns this rank's slice of the kept table; slices concatenated in rank
- * order are the whole table, sorted.                                        */
+ * returns this rank's slice of the kept table (k-mer ranges are cut on the
+ * case-folded k-mer, ascending in rank): first sections concatenated in rank
+ * order, then second sections in rank order, are the whole table in order.  */
 #define SIGK_COMM_ID_BYTES 128
 int sigk_comm_make_id(void *id128);
 int sigk_comm_join(sigk_handle *h, const void *id128);
@@ -174,7 +187,7 @@ int sigk_comm_join(sigk_handle *h, const void *id128);
 /* ---- stand-alone kernels, exported for the parity tests -------------------
  * Each runs one stage on host arrays through a temporary device copy.       */
 
-/* Stage 1: window validity + 43-bit order-preserving k-mer code.
+/* Stage 1: window validity + 43-bit group code (base-20 code of the case-folded residues << 8 | case mask).
  * out_code[n_windows], out_ordinal[n_windows], out_offset[n_windows];
  * returns the number of valid windows through *n_out.                       */
 int sigk_dbg_encode(sigk_handle *h, const sigk_proteins *p,
@@ -195,11 +208,11 @@ int sigk_dbg_sort_pairs(sigk_handle *h, uint64_t *keys, uint32_t *vals, uint64_t
  * or the file it loaded) and feeds the hits, in position order, to the call logic.  With a communicator each
  * rank looks up in its own slice of the table. */
 int sigk_lookup(sigk_handle *h, const uint8_t *residues, const uint64_t *starts, uint64_t n_proteins, uint32_t *rows);
-/* Make a table the lookup target without building it here: only t->kmer (8 bytes per row, sorted by bytes,
- * as sigk_result returns them) and t->n_kept are read. */
+/* Make a table the lookup target without building it here: only t->kmer (8 bytes per row, in the two-section
+ * order sigk_result returns them in) and t->n_kept are read. */
 int sigk_set_table(sigk_handle *h, const sigk_table *t);
 
-/* 43-bit code <-> 8 ASCII bytes (host side, no GPU). */
+/* 43-bit group code <-> 8 ASCII bytes (host side, no GPU).  Table order = ascending ((code & 0xFF) != 0, code). */
 uint64_t sigk_kmer_encode(const char kmer[8]);          /* UINT64_MAX if any residue invalid */
 void     sigk_kmer_decode(uint64_t code, char kmer[8]);
 

@@ -102,7 +102,7 @@ class BoostAcc:
 
 
 def build(seqs, function_index, seq_id=None):
-    """seqs: list[bytes]; returns (rows sorted by k-mer, stats dict).
+    """seqs: list[bytes]; returns (rows in table order, stats dict).
 
     rows: list of (kmer bytes, avg_from_end, function_index, mean, median, var)
     """
@@ -149,7 +149,14 @@ def build(seqs, function_index, seq_id=None):
         offsets.sort()
         rows.append((kmer, offsets[len(offsets) // 2], best_func, mean, median, var))
         distinct_functions[best_func] = distinct_functions.get(best_func, 0) + 1
-    rows.sort(key=lambda r: r[0])
+    def table_order(r):
+        # presentation only: the order include/sigk.h defines for the table (all-upper-case k-mers first, in byte
+        # order; then the others by case-folded bytes and the case mask with residue j in bit j)
+        k = r[0]
+        mask = sum(((c >> 5) & 1) << j for j, c in enumerate(k))
+        return (mask != 0, bytes(c & 0xDF for c in k), mask)
+
+    rows.sort(key=table_order)
     stats = dict(
         n_occurrences=n_occ,
         n_distinct_kmers=len(table),

@@ -376,8 +376,18 @@ int sigk_oracle_build(const sigk_proteins *p, int n_threads, int flags, sigk_ora
         for (int f = 0; f < SIGK_N_FUNCTION_SLOTS; ++f) o->distinct_functions[f] += stats[k].distinct_functions[f];
     }
     for (auto &w : seq_bits) o->n_seqs_sig += (uint64_t)__builtin_popcountll(w.load(std::memory_order_relaxed));
+    /* Presentation only (the reference iterates in TBB hash order): the order include/sigk.h defines for the table
+     * — k-mers without a lower-case residue first, in byte order, then the others by (case-folded bytes, case mask
+     * with residue j in bit j). */
     if (!(flags & SIGK_ORACLE_NO_SORT))
-        std::sort(o->rows.begin(), o->rows.end(), [](const Row &a, const Row &b) { return a.kmer < b.kmer; });
+        std::sort(o->rows.begin(), o->rows.end(), [](const Row &a, const Row &b) {
+            const uint64_t CASE = 0x2020202020202020ull;
+            const uint64_t ma = a.kmer & CASE, mb = b.kmer & CASE;
+            if ((ma != 0) != (mb != 0)) return mb != 0;
+            const uint64_t fa = a.kmer & ~CASE, fb = b.kmer & ~CASE;
+            if (fa != fb) return fa < fb;
+            return __builtin_bswap64(ma) < __builtin_bswap64(mb);
+        });
 
     const size_t n = o->rows.size();
     o->kmer_bytes.resize(n * 8);
@@ -408,6 +418,14 @@ int sigk_oracle_result(sigk_oracle *o, sigk_table *out) {
     out->num_seqs_with_a_signature = o->n_seqs_sig;
     out->distinct_functions = o->distinct_functions.data();
     out->seqs_with_func = o->seqs_with_func.data();
+    /* rows of the first section of the table order (k-mers without a lower-case residue) */
+    uint64_t upper = 0;
+    for (size_t i = 0; i < o->avg.size(); ++i) {
+        bool lower = false;
+        for (int j = 0; j < 8; ++j) lower = lower || (o->kmer_bytes[i * 8 + j] & 0x20);
+        upper += lower ? 0 : 1;
+    }
+    out->n_upper = upper;
     return SIGK_OK;
 }
 

@@ -16,7 +16,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SIGK_LIB") or os.path.join(_HERE, "libsigk.so")   # SIGK_LIB: a tuning variant
 
-SIGK_ABI_VERSION = 1
+SIGK_ABI_VERSION = 2
 SIGK_K = 8
 SIGK_UNDEFINED_FUNCTION = 0xFFFF
 SIGK_N_FUNCTION_SLOTS = 65536
@@ -60,6 +60,7 @@ class SigkTable(C.Structure):
         ("num_seqs_with_a_signature", C.c_uint64),
         ("distinct_functions", C.c_void_p),
         ("seqs_with_func", C.c_void_p),
+        ("n_upper", C.c_uint64),
     ]
 
 
@@ -80,6 +81,8 @@ class SigkTimings(C.Structure):
         ("key_bytes", C.c_uint32),
         ("kernel_launches", C.c_uint32),
         ("pass_ms", C.c_float * 8),
+        ("count_ms", C.c_float),
+        ("side_sort_ms", C.c_float),
     ]
 
     def as_dict(self):
@@ -146,7 +149,7 @@ class PackedProteins:
 
 @dataclass
 class KeptTable:
-    """Copy of struct sigk_table as numpy arrays (rows sorted by k-mer bytes)."""
+    """Copy of struct sigk_table as numpy arrays (rows in the table order of include/sigk.h)."""
 
     kmer: np.ndarray  # uint8 [n,8]
     avg_from_end: np.ndarray
@@ -160,6 +163,7 @@ class KeptTable:
     num_seqs_with_a_signature: int
     distinct_functions: np.ndarray  # uint32 [65536]
     seqs_with_func: np.ndarray  # uint32 [65536]
+    n_upper: int = -1           # rows of the first section (k-mers without a lower-case residue); -1 = not recorded
 
     @property
     def n_kept(self) -> int:
@@ -207,7 +211,33 @@ def table_to_numpy(t: SigkTable, copy=True) -> KeptTable:
         num_seqs_with_a_signature=int(t.num_seqs_with_a_signature),
         distinct_functions=_arr(t.distinct_functions, SIGK_N_FUNCTION_SLOTS, np.uint32, copy),
         seqs_with_func=_arr(t.seqs_with_func, SIGK_N_FUNCTION_SLOTS, np.uint32, copy),
+        n_upper=int(t.n_upper),
     )
+
+
+# ---- the table order of include/sigk.h ---------------------------------------------------------
+# k-mers without a lower-case residue first, in byte order; then the others by (case-folded bytes,
+# case mask with residue j in bit j).
+
+def table_order_key(kmer) -> tuple:
+    """Sort key of one k-mer (str or bytes) in table order."""
+    b = kmer.encode("latin-1") if isinstance(kmer, str) else bytes(kmer)
+    mask = sum(((c >> 5) & 1) << j for j, c in enumerate(b))
+    return (mask != 0, bytes(c & 0xDF for c in b), mask)
+
+
+def kmer_case_masks(kmer: np.ndarray) -> np.ndarray:
+    """uint8 [n,8] k-mer bytes -> uint8 [n] case masks (bit j set iff residue j is lower case)."""
+    k = np.ascontiguousarray(kmer, dtype=np.uint8).reshape(-1, 8)
+    return (((k >> 5) & 1).astype(np.uint16) << np.arange(8, dtype=np.uint16)).sum(axis=1).astype(np.uint8)
+
+
+def table_order_argsort(kmer: np.ndarray) -> np.ndarray:
+    """Permutation that puts uint8 [n,8] k-mer rows into table order."""
+    k = np.ascontiguousarray(kmer, dtype=np.uint8).reshape(-1, 8)
+    mask = kmer_case_masks(k)
+    folded = np.ascontiguousarray(k & 0xDF).view(">u8").ravel().astype(np.uint64)
+    return np.lexsort((mask, folded, mask != 0))
 
 
 # Every symbol include/sigk.h declares; tests/test_capi_symbols.py checks the

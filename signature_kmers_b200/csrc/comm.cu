@@ -11,12 +11,15 @@
 // stable, so equal k-mers keep the canonical insertion order the median / var
 // recurrences need.
 //
-//   1. every rank samples SAMPLES_PER_RANK keys of its encoded records;
-//      all-gather; sort; splitter k = sample at quantile k/world (same on all ranks)
-//   2. stable multi-way split of the local records by owner (onesweep kernel in
-//      SPLIT mode) — after it the records for rank d are one contiguous run
-//   3. all-gather the world x world count matrix; grouped ncclSend/ncclRecv
-//   4. per-protein meta is all-gathered once per upload (records carry global ordinals)
+//   1. once per upload: every rank samples SAMPLES_PER_RANK k-mers of its residues; all-gather; sort;
+//      splitter k = sample at quantile k/world (same on all ranks); the per-protein table is all-gathered
+//      (records carry global ordinals)
+//   2. every build: encode_split_kernel stores each record straight into region `source` of its owner's
+//      landing zone (peer memory over NVLink, mapped with CUDA IPC); an all-gather of the world x world
+//      count matrix tells every rank when all stores have landed and how many records each region holds
+//   3. the owner's histogram and first radix pass read the regions in place, in source-rank order
+//      (SortSegments): no gather copy
+// Without peer mappings the same kernel fills local send regions and grouped ncclSend/ncclRecv moves them.
 //
 // NCCL is resolved at run time with dlopen("libnccl.so.2") so that a process
 // that already loaded a NCCL (torch) shares it and a single-GPU user needs none.
@@ -82,8 +85,9 @@ struct Comm {
     uint64_t land_cap = 0;                      // records the landing zone holds
     uint64_t land_stride = 0;                   // records per (source, owner) region
     uint64_t max_total_res = 0;                 // largest residue count over the ranks
-    uint64_t *peer_keys[SORT_MAX_SPLIT + 1] = {};
-    uint32_t *peer_vals[SORT_MAX_SPLIT + 1] = {};
+    uint64_t min_stride = 0;                    // region size an overflowing build asked for
+    uint64_t *peer_keys[SORT_MAX_SEGMENTS] = {};
+    uint32_t *peer_vals[SORT_MAX_SEGMENTS] = {};
     bool peer_ok = false;
 };
 
@@ -95,16 +99,7 @@ struct Comm {
 
 namespace {
 
-__global__ void sample_keys_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ n_ptr,
-                                   uint64_t *__restrict__ samples, int n_samples) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_samples) return;
-    const uint64_t n = *n_ptr;
-    // an empty rank contributes the largest key: it only pulls the top splitter up a little
-    samples[i] = n ? keys[(uint64_t)i * n / n_samples] : ~0ull;      // i * n < 2^14 * 2^32
-}
-
-// Samples for the fused encode+route path, taken before any record exists: the k-mer at (or after)
+// Samples for the splitters, taken from the residues: the k-mer at (or after)
 // evenly spaced residue positions.  Protein boundaries are ignored — a splitter only has to balance.
 __global__ void sample_residues_kernel(const uint8_t *__restrict__ res, uint64_t total_res, uint64_t *__restrict__ samples,
                                        int n_samples) {
@@ -114,14 +109,14 @@ __global__ void sample_residues_kernel(const uint8_t *__restrict__ res, uint64_t
     if (total_res >= 8) {
         uint64_t p = (uint64_t)i * (total_res - 7) / n_samples;
         for (int tries = 0; tries < 256 && p + 8 <= total_res; ++tries, ++p) {
-            uint64_t code = 0;
+            uint64_t code = 0;                   // case-folded: ranges are cut on code35
             bool ok = true;
             for (int j = 0; j < 8; ++j) {
                 const int sy = sigk_symbol(res[p + j]);
                 if (sy < 0) { ok = false; break; }
-                code = code * 40u + (uint64_t)sy;
+                code = code * 20u + (uint64_t)(sy & 31);
             }
-            if (ok) { key = sigk_pack_key(code, 0); break; }
+            if (ok) { key = sigk_pack_key(code, 0, 0); break; }
         }
     }
     samples[i] = key;
@@ -130,42 +125,7 @@ __global__ void sample_residues_kernel(const uint8_t *__restrict__ res, uint64_t
 __global__ void pick_splitters_kernel(const uint64_t *__restrict__ sorted_samples, int per_rank, int world,
                                       uint64_t *__restrict__ split_codes) {
     const int k = threadIdx.x;      // splitter k = first code owned by rank k+1
-    if (k < world - 1) split_codes[k] = sigk_key_code(sorted_samples[(size_t)(k + 1) * per_rank]);
-}
-
-__global__ void owner_histogram_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ n_ptr,
-                                       const uint64_t *__restrict__ split_codes, int n_split, uint64_t *__restrict__ counts) {
-    __shared__ unsigned long long sh[SORT_MAX_SPLIT + 1];
-    __shared__ uint64_t sp[SORT_MAX_SPLIT];
-    if (threadIdx.x <= SORT_MAX_SPLIT) sh[threadIdx.x] = 0;
-    if ((int)threadIdx.x < n_split) sp[threadIdx.x] = split_codes[threadIdx.x];
-    __syncthreads();
-    const uint64_t n = *n_ptr;
-    uint32_t mine[SORT_MAX_SPLIT + 1] = {};
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t code = sigk_key_code(keys[i]);
-        uint32_t d = 0;
-        for (int k = 0; k < n_split; ++k) d += code >= sp[k] ? 1u : 0u;
-#pragma unroll
-        for (int k = 0; k <= SORT_MAX_SPLIT; ++k) mine[k] += (d == (uint32_t)k);
-    }
-#pragma unroll
-    for (int k = 0; k <= SORT_MAX_SPLIT; ++k) {
-        uint32_t v = mine[k];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31u) == 0 && v) atomicAdd(&sh[k], (unsigned long long)v);
-    }
-    __syncthreads();
-    if (threadIdx.x <= SORT_MAX_SPLIT && sh[threadIdx.x]) atomicAdd(reinterpret_cast<unsigned long long *>(counts + threadIdx.x), sh[threadIdx.x]);
-}
-
-// bin_base of the partition pass: exclusive scan of the owner counts, padded to SIGK_RADIX entries
-__global__ void owner_bases_kernel(const uint64_t *__restrict__ counts, int world, uint64_t *__restrict__ bin_base) {
-    const int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= SIGK_RADIX) return;
-    uint64_t run = 0;
-    for (int k = 0; k < world && k < d; ++k) run += counts[k];
-    bin_base[d] = run;
+    if (k < world - 1) split_codes[k] = sigk_key_code35(sorted_samples[(size_t)(k + 1) * per_rank]);
 }
 
 __global__ void or_bitmaps_kernel(const uint32_t *__restrict__ all, uint64_t words, int world, uint32_t *__restrict__ out) {
@@ -182,7 +142,7 @@ __global__ void or_bitmaps_kernel(const uint32_t *__restrict__ all, uint64_t wor
 constexpr size_t IPC_WORDS = 2 * (sizeof(cudaIpcMemHandle_t) / sizeof(uint64_t)) + 1;   // two handles + an ok word
 
 static void close_imports(Comm *c) {
-    for (int r = 0; r <= SORT_MAX_SPLIT; ++r) {
+    for (int r = 0; r <= (SORT_MAX_SEGMENTS - 1); ++r) {
         if (r != c->rank) {
             if (c->peer_keys[r]) cudaIpcCloseMemHandle(c->peer_keys[r]);
             if (c->peer_vals[r]) cudaIpcCloseMemHandle(c->peer_vals[r]);
@@ -201,7 +161,7 @@ static void release_landing(Comm *c) {
 }
 
 // min over the ranks of a 0/1 word; doubles as a barrier (every rank's stream has reached this point)
-static int agree(sigk_handle *h, uint64_t mine, uint64_t *out) {
+int comm_agree(sigk_handle *h, uint64_t mine, uint64_t *out) {
     Comm *c = h->comm;
     cudaStream_t st = h->stream;
     uint64_t *scratch = c->d_shape.p;
@@ -217,20 +177,20 @@ static int agree(sigk_handle *h, uint64_t mine, uint64_t *out) {
 // landing zone of `world` regions big enough for this job and that all of them are mapped here.  Any
 // failure on any rank (allocation, IPC export/import, SIGK_NO_PEER_WRITES set) leaves peer_ok false on
 // all ranks, and the build routes through local send regions and NCCL send/recv instead.
-static int setup_landing(sigk_handle *h) {
+int comm_setup_landing(sigk_handle *h) {
     Comm *c = h->comm;
     cudaStream_t st = h->stream;
     const int W = c->world;
     const uint64_t per = c->max_total_res / W;
-    const uint64_t stride = (per + per / 4 + 65536 + 63) & ~63ull;               // expected share + 25 % + slack
+    const uint64_t stride = std::max<uint64_t>((per + per / 4 + 65536 + 63) & ~63ull, c->min_stride);   // expected share + 25 % + slack
     if (c->peer_ok && stride * W <= c->land_cap) { c->land_stride = stride; return SIGK_OK; }
     const bool had = c->land_keys != nullptr;
     if (had) {
         // nobody may still be writing into a zone that is about to go away
         uint64_t dummy;
-        if (int rc = agree(h, 1, &dummy)) return rc;
+        if (int rc = comm_agree(h, 1, &dummy)) return rc;
         close_imports(c);
-        if (int rc = agree(h, 1, &dummy)) return rc;         // every import is closed before any zone is freed
+        if (int rc = comm_agree(h, 1, &dummy)) return rc;         // every import is closed before any zone is freed
         release_landing(c);
     }
     uint64_t words[IPC_WORDS] = {};
@@ -271,14 +231,14 @@ static int setup_landing(sigk_handle *h) {
         cudaGetLastError();
     }
     uint64_t everyone = 0;
-    if (int rc = agree(h, opened ? 1 : 0, &everyone)) return rc;
+    if (int rc = comm_agree(h, opened ? 1 : 0, &everyone)) return rc;
     if (everyone == 1) {
         c->peer_ok = true;
         c->land_cap = stride * W;
         c->land_stride = stride;
     } else {
         close_imports(c);
-        if (int rc = agree(h, 1, &everyone)) return rc;      // every import is closed before any zone is freed
+        if (int rc = comm_agree(h, 1, &everyone)) return rc;      // every import is closed before any zone is freed
         release_landing(c);
     }
     return SIGK_OK;
@@ -298,7 +258,7 @@ int comm_make_id(void *id128, std::string *err) {
 int comm_join(sigk_handle *h, const void *id128) {
     if (!id128) return h->fail(SIGK_E_INVALID, "null communicator id");
     if (h->cfg.world < 2) return h->fail(SIGK_E_INVALID, "sigk_comm_join needs world >= 2 in sigk_config");
-    if (h->cfg.world > SORT_MAX_SPLIT + 1) return h->fail(SIGK_E_UNSUPPORTED, "at most %d ranks", SORT_MAX_SPLIT + 1);
+    if (h->cfg.world > SORT_MAX_SEGMENTS) return h->fail(SIGK_E_UNSUPPORTED, "at most %d ranks", SORT_MAX_SEGMENTS);
     std::string err;
     if (!g_nccl.load(&err)) return h->fail(SIGK_E_COMM, "%s", err.c_str());
     CU(h, cudaSetDevice(h->cfg.device));
@@ -322,7 +282,7 @@ void comm_destroy(sigk_handle *h) {
         // for every rank to have done the same (sigk_destroy is collective when world > 1), then free
         close_imports(c);
         uint64_t dummy = 0;
-        agree(h, 1, &dummy);
+        comm_agree(h, 1, &dummy);
     }
     release_landing(c);
     if (c->comm) g_nccl.CommDestroy(c->comm);
@@ -359,7 +319,7 @@ int comm_exchange_shapes(sigk_handle *h) {
     h->n_prot_global = total;
     h->ordinal_base = base;
     h->max_seq_id = (uint32_t)max_sid;
-    return setup_landing(h);
+    return comm_setup_landing(h);
 }
 
 int comm_allgather_meta(sigk_handle *h) {
@@ -375,12 +335,14 @@ int comm_allgather_meta(sigk_handle *h) {
         base += c->prot_count[r];
     }
     NC(h, g_nccl.GroupEnd());
+    // seqs_with_func depends on the input alone: summed over the ranks here, once per upload
+    NC(h, g_nccl.AllReduce(h->d_swf.p, h->d_swf.p, SIGK_N_FUNCTION_SLOTS, ncclUint32, ncclSum, c->comm, st));
     return SIGK_OK;
 }
 
-// All ranks agree on W-1 splitter codes: SAMPLES_PER_RANK local samples (of the encoded keys, or of the
-// residues when nothing is encoded yet), all-gathered, sorted with the onesweep kernels, cut at the quantiles.
-static int choose_splitters(sigk_handle *h, bool from_residues, uint32_t *launches) {
+// All ranks agree on W-1 splitter codes: SAMPLES_PER_RANK k-mers sampled from every rank's residues, all-gathered,
+// sorted with the onesweep kernels, cut at the quantiles.  Depends on the input alone: once per upload.
+int comm_choose_splitters(sigk_handle *h, uint32_t *launches) {
     Comm *c = h->comm;
     cudaStream_t st = h->stream;
     const int W = c->world;
@@ -388,57 +350,56 @@ static int choose_splitters(sigk_handle *h, bool from_residues, uint32_t *launch
     const size_t ns = (size_t)SAMPLES_PER_RANK * W;
     CU(h, c->d_samples.reserve(ns + SAMPLES_PER_RANK)); CU(h, c->d_samples_alt.reserve(ns));
     CU(h, c->d_sample_vals.reserve(ns)); CU(h, c->d_sample_vals_alt.reserve(ns));
-    CU(h, c->d_split.reserve(SORT_MAX_SPLIT + 1)); CU(h, c->d_counts.reserve((size_t)W * (W + 1) + W + 8));
+    CU(h, c->d_split.reserve(SORT_MAX_SEGMENTS)); CU(h, c->d_counts.reserve((size_t)W * (W + 1) + W + 8));
     uint64_t *local = c->d_samples.p + ns;
-    if (from_residues)
-        sample_residues_kernel<<<(SAMPLES_PER_RANK + 255) / 256, 256, 0, st>>>(h->d_res.p, h->total_res, local, SAMPLES_PER_RANK);
-    else
-        sample_keys_kernel<<<(SAMPLES_PER_RANK + 255) / 256, 256, 0, st>>>(h->d_keys[0].p, &sc->n_records, local, SAMPLES_PER_RANK);
+    sample_residues_kernel<<<(SAMPLES_PER_RANK + 255) / 256, 256, 0, st>>>(h->d_res.p, h->total_res, local, SAMPLES_PER_RANK);
     CU(h, cudaGetLastError()); ++*launches;
     NC(h, g_nccl.AllGather(local, c->d_samples.p, SAMPLES_PER_RANK, ncclUint64, c->comm, st));
     // sort the gathered samples on the code bits with the same onesweep kernels
-    const PassPlan plan = make_pass_plan(SIGK_KEY_CODE_SHIFT, SIGK_KEY_CODE_SHIFT + SIGK_CODE_BITS);
+    const PassPlan plan = make_pass_plan(SIGK_KEY_CODE35_SHIFT, 64);
     uint64_t *nbuf = c->d_counts.p + (size_t)W * (W + 1) + W + 4;   // holds ns as a device scalar
     const uint64_t ns64 = ns;
     CU(h, cudaMemcpyAsync(nbuf, &ns64, sizeof ns64, cudaMemcpyHostToDevice, st));
-    CU(h, cudaMemsetAsync(h->d_hist.p, 0, SORT_MAX_PASSES * SIGK_RADIX * sizeof(uint64_t), st));
-    CU(h, launch_histogram(c->d_samples.p, nbuf, ns, plan, h->d_hist.p, h->sm_count, st));
-    CU(h, launch_scan_bins(h->d_hist.p, h->d_binbase.p, plan.npass, st));
+    CU(h, cudaMemsetAsync(h->d_hist.p, 0, SORT_MAX_PASSES * SIGK_BINS * sizeof(uint64_t), st));
+    CU(h, launch_histogram(c->d_samples.p, nbuf, nullptr, ns, plan, h->d_hist.p, h->sm_count, st));
+    CU(h, launch_scan_bins(h->d_hist.p, h->d_binbase.p, plan.npass, nullptr, st));
     const size_t lb = onesweep_lookback_bytes(ns);
     CU(h, cudaMemsetAsync(h->d_lookback.p, 0, lb * plan.npass, st));
-    CU(h, cudaMemsetAsync(sc->ticket + TK_SORT0, 0, SORT_MAX_PASSES * sizeof(uint32_t), st));
+    CU(h, cudaMemsetAsync(sc->ticket, 0, sizeof sc->ticket, st));
     uint64_t *k[2] = {c->d_samples.p, c->d_samples_alt.p};
     uint32_t *v[2] = {c->d_sample_vals.p, c->d_sample_vals_alt.p};
     int cur = 0;
     for (int p = 0; p < plan.npass; ++p) {
-        CU(h, launch_onesweep_pass(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], nbuf, ns, plan.lo[p], plan.bits[p],
-                                   h->d_binbase.p + (size_t)p * SIGK_RADIX, h->d_lookback.p + lb * p,
-                                   sc->ticket + TK_SORT0 + p, st));
+        CU(h, launch_onesweep_pass(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], nbuf, nullptr, ns, plan.lo[p], plan.bits[p],
+                                   h->d_binbase.p + (size_t)p * SIGK_BINS, h->d_lookback.p + lb * p,
+                                   sc->ticket + TK_SORT0 + p, h->sm_count, st));
         cur ^= 1;
     }
     *launches += 2 + plan.npass;
     pick_splitters_kernel<<<1, 32, 0, st>>>(k[cur], SAMPLES_PER_RANK, W, c->d_split.p);
     CU(h, cudaGetLastError()); ++*launches;
-    CU(h, cudaMemsetAsync(sc->ticket + TK_SORT0, 0, SORT_MAX_PASSES * sizeof(uint32_t), st));
-    CU(h, cudaMemsetAsync(h->d_hist.p, 0, SORT_MAX_PASSES * SIGK_RADIX * sizeof(uint64_t), st));
     return SIGK_OK;
 }
 
-static int publish_counts(sigk_handle *h, uint64_t local_records, uint64_t n_recv);
+// what follows every exchange: the local count feeds the job-wide sum (n_records itself comes from the histogram)
+static int publish_counts(sigk_handle *h, uint64_t local_records, uint64_t n_recv) {
+    Comm *c = h->comm;
+    const int W = c->world;
+    DeviceScalars *sc = h->d_scalars.p;
+    c->h_counts.p[(size_t)W * (W + 1)] = local_records;
+    CU(h, cudaMemcpyAsync(&sc->reduce_in[0], c->h_counts.p + (size_t)W * (W + 1), sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+    h->n_recv = n_recv;
+    return SIGK_OK;
+}
 
-// the all-to-all itself: region r of keys[1]/vals[1] (at send_base[r]) goes to rank r; what the others send
-// lands in keys[0]/vals[0] in source-rank order.  cnt[src * W + dst] is the all-gathered count matrix.
-static int exchange_records(sigk_handle *h, const uint64_t *cnt, const uint64_t *send_base, uint64_t local_records) {
+// the all-to-all itself (no peer mappings): region r of keys[1]/vals[1] (at send_base[r]) goes to rank r; what the
+// others send lands in keys[0]/vals[0] in source-rank order.  cnt[src * W + dst] is the all-gathered count matrix.
+static int exchange_records(sigk_handle *h, const uint64_t *cnt, const uint64_t *send_base) {
     Comm *c = h->comm;
     cudaStream_t st = h->stream;
     const int W = c->world;
-    DeviceScalars *sc = h->d_scalars.p;
-    uint64_t n_recv = 0;
-    for (int s2 = 0; s2 < W; ++s2) n_recv += cnt[(size_t)s2 * W + c->rank];
-    if (n_recv >= 0xFFFFFFFFull) return h->fail(SIGK_E_UNSUPPORTED, "more than 2^32-2 records on one rank after the exchange");
-    if (int rc = ensure_capacity(h, std::max<uint64_t>(h->capacity, n_recv), /*keep_pingpong1=*/true)) return rc;
     // this rank's own share never leaves the device: a plain copy at HBM speed, outside the NCCL group
-    uint64_t recv_base[SORT_MAX_SPLIT + 1], recv_off = 0;
+    uint64_t recv_base[SORT_MAX_SEGMENTS], recv_off = 0;
     for (int r = 0; r < W; ++r) { recv_base[r] = recv_off; recv_off += cnt[(size_t)r * W + c->rank]; }
     if (const uint64_t own = cnt[(size_t)c->rank * W + c->rank]) {
         CU(h, cudaMemcpyAsync(h->d_keys[0].p + recv_base[c->rank], h->d_keys[1].p + send_base[c->rank], own * sizeof(uint64_t),
@@ -460,135 +421,113 @@ static int exchange_records(sigk_handle *h, const uint64_t *cnt, const uint64_t 
         }
     }
     NC(h, g_nccl.GroupEnd());
-    return publish_counts(h, local_records, n_recv);
-}
-
-int comm_partition_exchange(sigk_handle *h, uint32_t *launches) {
-    Comm *c = h->comm;
-    cudaStream_t st = h->stream;
-    const int W = c->world;
-    DeviceScalars *sc = h->d_scalars.p;
-    const uint64_t cap_local = h->total_res;            // records keys[0] can hold so far
-
-    // ---- 1. splitters from sorted samples of the encoded keys
-    if (int rc = choose_splitters(h, /*from_residues=*/false, launches)) return rc;
-
-    // ---- 2. stable split of the local records by owner: keys[0] -> keys[1]
-    uint64_t *my_counts = c->d_counts.p + (size_t)W * W;
-    CU(h, cudaMemsetAsync(my_counts, 0, W * sizeof(uint64_t), st));
-    owner_histogram_kernel<<<h->sm_count * 4, 256, 0, st>>>(h->d_keys[0].p, &sc->n_records, c->d_split.p, W - 1, my_counts);
-    CU(h, cudaGetLastError());
-    owner_bases_kernel<<<(SIGK_RADIX + 255) / 256, 256, 0, st>>>(my_counts, W, h->d_binbase.p);
-    CU(h, cudaGetLastError());
-    CU(h, cudaMemsetAsync(h->d_lookback.p, 0, onesweep_lookback_bytes(cap_local), st));
-    CU(h, launch_onesweep_partition(h->d_keys[0].p, h->d_vals[0].p, h->d_keys[1].p, h->d_vals[1].p, &sc->n_records, cap_local,
-                                    c->d_split.p, W - 1, h->d_binbase.p, h->d_lookback.p, sc->ticket + TK_PARTITION, st));
-    *launches += 3;
-
-    // ---- 3. counts matrix, then the all-to-all
-    NC(h, g_nccl.AllGather(my_counts, c->d_counts.p, W, ncclUint64, c->comm, st));
-    CU(h, cudaMemcpyAsync(c->h_counts.p, c->d_counts.p, (size_t)W * W * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    CU(h, cudaStreamSynchronize(st));
-    const uint64_t *cnt = c->h_counts.p;                 // cnt[src * W + dst]
-    uint64_t send_base[SORT_MAX_SPLIT + 1], run = 0;
-    for (int r = 0; r < W; ++r) { send_base[r] = run; run += cnt[(size_t)c->rank * W + r]; }
-    if (int rc = exchange_records(h, cnt, send_base, run)) return rc;
-    CU(h, cudaStreamSynchronize(st));                    // keys[1]/vals[1] are free again: bring them up to the new capacity
-    if (int rc = ensure_capacity(h, h->capacity, /*keep_pingpong1=*/false)) return rc;
-    return SIGK_OK;
-}
-
-// what follows every exchange: the received count becomes n_records, the local count feeds the job-wide sum
-static int publish_counts(sigk_handle *h, uint64_t local_records, uint64_t n_recv) {
-    Comm *c = h->comm;
-    const int W = c->world;
-    DeviceScalars *sc = h->d_scalars.p;
-    c->h_counts.p[(size_t)W * (W + 1)] = local_records;
-    c->h_counts.p[(size_t)W * (W + 1) + 1] = n_recv;
-    CU(h, cudaMemcpyAsync(&sc->reduce_in[0], c->h_counts.p + (size_t)W * (W + 1), sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
-    CU(h, cudaMemcpyAsync(&sc->n_records, c->h_counts.p + (size_t)W * (W + 1) + 1, sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
-    h->n_recv = n_recv;
     return SIGK_OK;
 }
 
 // Multi-GPU stage 1: encode and exchange.  encode_split_kernel writes every record straight into its
 // owner's region: with peer mappings that region is in the owner GPU's landing zone (the exchange is the
-// kernel's own stores over NVLink, and what remains is a local gather of the W regions into sort order);
-// without them it is a local send region followed by NCCL send/recv.  If a region turns out too small on any
-// rank (pathological skew between ranks), all ranks fall back to encode + stable split pass + send/recv.
-int comm_encode_exchange(sigk_handle *h, const EncodeArgs &ea, uint32_t *launches) {
+// kernel's own stores over NVLink, and the owner then sorts straight out of the W regions); without them it
+// is a local send region followed by NCCL send/recv.  If a region turns out too small on any rank (skew
+// between ranks beyond the 25 % head room), all ranks grow their regions to the exact need and encode again.
+// *seg describes where this rank's records are, *first_out which ping-pong buffer the first pass may write.
+int comm_encode_exchange(sigk_handle *h, const EncodeArgs &ea, SortSegments *seg, int *first_out, uint32_t *launches) {
     Comm *c = h->comm;
     cudaStream_t st = h->stream;
     const int W = c->world;
     DeviceScalars *sc = h->d_scalars.p;
-    // the all-gather in here is also the barrier that makes the landing zones safe to overwrite: it completes
-    // only after every rank's stream has finished the previous build
-    if (int rc = choose_splitters(h, /*from_residues=*/true, launches)) return rc;
-
-    const bool peer = c->peer_ok;
-    const uint64_t cap_local = h->total_res;
-    // expected share + 25 % + slack, a multiple of 64 records (the kernel stores 16 bytes at a time)
-    const uint64_t stride = peer ? c->land_stride : (cap_local / W + cap_local / (4 * W) + 65536 + 63) & ~63ull;
-    if (!peer) { CU(h, h->d_keys[1].reserve((size_t)stride * W)); CU(h, h->d_vals[1].reserve((size_t)stride * W)); }
-    const size_t state_words = (size_t)encode_slices(h->total_res) * W + W;
-    CU(h, c->d_owner_state.reserve(state_words));
-    CU(h, cudaMemsetAsync(c->d_owner_state.p, 0, state_words * sizeof(uint64_t), st));
     uint64_t *totals = c->d_counts.p + (size_t)W * (W + 1);                     // W totals + the overflow flag word
-    CU(h, cudaMemsetAsync(totals, 0, (W + 1) * sizeof(uint64_t), st));
-    EncodeSplitArgs sp{};
-    sp.split_codes = c->d_split.p; sp.n_split = W - 1; sp.region_stride = stride;
-    sp.owner_state = c->d_owner_state.p; sp.owner_totals = totals; sp.overflow = reinterpret_cast<uint32_t *>(totals + W);
-    for (int d = 0; d < W; ++d) {
-        sp.dst_keys[d] = peer ? c->peer_keys[d] + (size_t)c->rank * stride : h->d_keys[1].p + (size_t)d * stride;
-        sp.dst_vals[d] = peer ? c->peer_vals[d] + (size_t)c->rank * stride : h->d_vals[1].p + (size_t)d * stride;
-    }
-    CU(h, launch_encode_split(ea, sp, sc->ticket + TK_ENCODE, st)); ++*launches;
-    CU(h, cudaEventRecord(h->ev[EV_ENCODE], st));
-    // W totals + overflow word from every rank; completes only when every rank's kernel (and its peer stores) has
-    NC(h, g_nccl.AllGather(totals, c->d_counts.p, W + 1, ncclUint64, c->comm, st));
-    CU(h, cudaMemcpyAsync(c->h_counts.p, c->d_counts.p, (size_t)W * (W + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    CU(h, cudaStreamSynchronize(st));
-    bool overflow = false;
     std::vector<uint64_t> cnt((size_t)W * W);
-    for (int r = 0; r < W; ++r) {
-        overflow |= c->h_counts.p[(size_t)r * (W + 1) + W] != 0;
-        for (int d = 0; d < W; ++d) cnt[(size_t)r * W + d] = c->h_counts.p[(size_t)r * (W + 1) + d];
-    }
-    if (std::getenv("SIGK_TEST_FORCE_SPLIT_FALLBACK")) overflow = true;     // tests: exercise the fallback on every rank
-    if (overflow) {
-        CU(h, cudaMemsetAsync(sc->ticket + TK_ENCODE, 0, sizeof(uint32_t), st));
-        CU(h, cudaMemsetAsync(h->d_prot_windows.p, 0, std::max<uint64_t>(h->in.n_proteins, 1) * sizeof(uint32_t), st));
-        CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, encode_scan_entries(h->total_res) * sizeof(uint64_t), st));
-        CU(h, launch_encode(ea, h->d_keys[0].p, h->d_vals[0].p, h->d_scan_state.p, sc->ticket + TK_ENCODE, &sc->n_records, st)); ++*launches;
-        return comm_partition_exchange(h, launches);
-    }
-    uint64_t local = 0;
-    for (int r = 0; r < W; ++r) local += cnt[(size_t)c->rank * W + r];
-    if (peer) {
-        // everything is already here: gather the W source regions, in source-rank order, into the sort input
-        uint64_t n_recv = 0;
-        for (int s2 = 0; s2 < W; ++s2) n_recv += cnt[(size_t)s2 * W + c->rank];
-        if (n_recv >= 0xFFFFFFFFull) return h->fail(SIGK_E_UNSUPPORTED, "more than 2^32-2 records on one rank after the exchange");
-        if (int rc = ensure_capacity(h, std::max<uint64_t>(h->capacity, n_recv), /*keep_pingpong1=*/false)) return rc;
-        uint64_t off = 0;
-        for (int s2 = 0; s2 < W; ++s2) {
-            const uint64_t n = cnt[(size_t)s2 * W + c->rank];
-            if (n) {
-                CU(h, cudaMemcpyAsync(h->d_keys[0].p + off, c->land_keys + (size_t)s2 * stride, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
-                CU(h, cudaMemcpyAsync(h->d_vals[0].p + off, c->land_vals + (size_t)s2 * stride, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    for (int attempt = 0;; ++attempt) {
+        // every rank's previous build has stopped reading its landing zone before anybody overwrites it: a
+        // one-word all-reduce on the build streams is the barrier
+        NC(h, g_nccl.AllReduce(c->d_shape.p, c->d_shape.p, 1, ncclUint64, ncclMin, c->comm, st));
+        const bool peer = c->peer_ok;
+        const uint64_t cap_local = h->total_res;
+        // expected share + 25 % + slack, a multiple of 64 records (the kernel stores 16 bytes at a time)
+        const uint64_t stride = peer ? c->land_stride
+                                     : std::max<uint64_t>((cap_local / W + cap_local / (4 * W) + 65536 + 63) & ~63ull, c->min_stride);
+        if (!peer) { CU(h, h->d_keys[1].reserve((size_t)stride * W)); CU(h, h->d_vals[1].reserve((size_t)stride * W)); }
+        const size_t state_words = (size_t)encode_slices(h->total_res) * W + W;
+        CU(h, c->d_owner_state.reserve(state_words));
+        CU(h, cudaMemsetAsync(c->d_owner_state.p, 0, state_words * sizeof(uint64_t), st));
+        CU(h, cudaMemsetAsync(totals, 0, (W + 1) * sizeof(uint64_t), st));
+        EncodeSplitArgs sp{};
+        sp.split_codes = c->d_split.p; sp.n_split = W - 1; sp.region_stride = stride;
+        sp.owner_state = c->d_owner_state.p; sp.owner_totals = totals; sp.overflow = reinterpret_cast<uint32_t *>(totals + W);
+        for (int d = 0; d < W; ++d) {
+            sp.dst_keys[d] = peer ? c->peer_keys[d] + (size_t)c->rank * stride : h->d_keys[1].p + (size_t)d * stride;
+            sp.dst_vals[d] = peer ? c->peer_vals[d] + (size_t)c->rank * stride : h->d_vals[1].p + (size_t)d * stride;
+        }
+        CU(h, launch_encode_split(ea, sp, sc->ticket + TK_ENCODE, st)); ++*launches;
+        CU(h, cudaEventRecord(h->ev[EV_ENCODE], st));
+        // W totals + overflow word from every rank; completes only when every rank's kernel (and its peer stores) has
+        NC(h, g_nccl.AllGather(totals, c->d_counts.p, W + 1, ncclUint64, c->comm, st));
+        CU(h, cudaMemcpyAsync(c->h_counts.p, c->d_counts.p, (size_t)W * (W + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        CU(h, cudaStreamSynchronize(st));
+        bool overflow = false;
+        uint64_t largest = 0;
+        for (int r = 0; r < W; ++r) {
+            overflow |= c->h_counts.p[(size_t)r * (W + 1) + W] != 0;
+            for (int d = 0; d < W; ++d) {
+                cnt[(size_t)r * W + d] = c->h_counts.p[(size_t)r * (W + 1) + d];
+                largest = std::max(largest, cnt[(size_t)r * W + d]);
             }
-            off += n;
+        }
+        if (attempt == 0 && std::getenv("SIGK_TEST_FORCE_SPLIT_FALLBACK")) overflow = true;     // tests: exercise the retry on every rank
+        // Every rank holds the whole matrix, so every rank reaches the same verdicts below (no rank is left in a collective).
+        for (int r = 0; r < W; ++r) {
+            uint64_t n_r = 0;
+            for (int s2 = 0; s2 < W; ++s2) n_r += cnt[(size_t)s2 * W + r];
+            if (n_r >= 0xFFFFFFFFull) return h->fail(SIGK_E_UNSUPPORTED, "more than 2^32-2 records on rank %d after the exchange", r);
+        }
+        if (overflow) {
+            if (attempt >= 2) return h->fail(SIGK_E_COMM, "the exchange regions overflowed three times");
+            // the totals are exact even when a region overflowed: size every region for the largest one, with head room
+            c->min_stride = (largest + largest / 16 + 4096 + 63) & ~63ull;
+            if (int rc = comm_setup_landing(h)) return rc;
+            CU(h, cudaMemsetAsync(sc->ticket + TK_ENCODE, 0, sizeof(uint32_t), st));
+            if (ea.prot_windows) CU(h, cudaMemsetAsync(ea.prot_windows, 0, std::max<uint64_t>(h->in.n_proteins, 1) * sizeof(uint32_t), st));
+            continue;
+        }
+        uint64_t local = 0, n_recv = 0;
+        for (int r = 0; r < W; ++r) { local += cnt[(size_t)c->rank * W + r]; n_recv += cnt[(size_t)r * W + c->rank]; }
+        // grow the sort buffers if this rank received more than it encoded; an allocation failure anywhere fails everywhere
+        int rc_cap = SIGK_OK;
+        if (n_recv > h->capacity) {
+            if (!peer) CU(h, cudaStreamSynchronize(st));
+            rc_cap = ensure_capacity(h, n_recv, /*keep_pingpong1=*/!peer);
+        }
+        uint64_t everyone = 0;
+        if (int rc = comm_agree(h, rc_cap == SIGK_OK ? 1 : 0, &everyone)) return rc;
+        if (!everyone) return rc_cap != SIGK_OK ? rc_cap : h->fail(SIGK_E_NOMEM, "another rank could not grow its sort buffers");
+        seg->n = 0;
+        if (peer) {
+            // everything is already here: the first pass reads the W source regions in place, in source-rank order
+            uint64_t off = 0;
+            for (int s2 = 0; s2 < W; ++s2) {
+                seg->start[s2] = off;
+                seg->keys[s2] = c->land_keys + (size_t)s2 * stride;
+                seg->vals[s2] = c->land_vals + (size_t)s2 * stride;
+                off += cnt[(size_t)s2 * W + c->rank];
+            }
+            seg->n = W;
+            seg->start[W] = off;
+            *first_out = 0;
+        } else {
+            uint64_t send_base[SORT_MAX_SEGMENTS];
+            for (int r = 0; r < W; ++r) send_base[r] = (uint64_t)r * stride;
+            if (int rc = exchange_records(h, cnt.data(), send_base)) return rc;
+            if (h->d_keys[1].cap < h->capacity || h->d_vals[1].cap < h->capacity) {      // the first pass writes into [1]
+                CU(h, cudaStreamSynchronize(st));
+                if (int rc = ensure_capacity(h, h->capacity, /*keep_pingpong1=*/false)) return rc;
+            }
+            seg->n = 1;
+            seg->start[0] = 0; seg->start[1] = n_recv;
+            seg->keys[0] = h->d_keys[0].p; seg->vals[0] = h->d_vals[0].p;
+            *first_out = 1;
         }
         return publish_counts(h, local, n_recv);
     }
-    uint64_t send_base[SORT_MAX_SPLIT + 1];
-    for (int r = 0; r < W; ++r) send_base[r] = (uint64_t)r * stride;
-    if (int rc = exchange_records(h, cnt.data(), send_base, local)) return rc;
-    if (h->d_keys[1].cap < h->capacity || h->d_vals[1].cap < h->capacity) {      // the sort ping-pongs through [1]
-        CU(h, cudaStreamSynchronize(st));
-        if (int rc = ensure_capacity(h, h->capacity, /*keep_pingpong1=*/false)) return rc;
-    }
-    return SIGK_OK;
 }
 
 int comm_reduce_rejected(sigk_handle *h) {
@@ -606,7 +545,6 @@ int comm_reduce_stats(sigk_handle *h) {
     CU(h, cudaMemcpyAsync(&sc->reduce_in[2], &sc->n_kept, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
     NC(h, g_nccl.AllReduce(sc->reduce_in, sc->reduce_in, 3, ncclUint64, ncclSum, c->comm, st));
     NC(h, g_nccl.AllReduce(h->d_distinct.p, h->d_distinct.p, SIGK_N_FUNCTION_SLOTS, ncclUint32, ncclSum, c->comm, st));
-    NC(h, g_nccl.AllReduce(h->d_swf.p, h->d_swf.p, SIGK_N_FUNCTION_SLOTS, ncclUint32, ncclSum, c->comm, st));
     // a protein has a signature if any rank kept one of its k-mers: OR of the bitmaps
     const uint64_t words = ((uint64_t)h->max_seq_id >> 5) + 1;
     CU(h, c->d_bitmaps.reserve(words * c->world));

@@ -1,27 +1,22 @@
 // encode.cu — stage 1: slide the 8-residue window over the packed protein
-// buffer, drop windows the reference drops, emit one 12-byte record per valid
-// window in canonical (insertion) order.
+// buffer, drop windows the reference drops, and either count (window_count_kernel)
+// or emit (encode_split_kernel) one 12-byte record per valid window in canonical
+// (insertion) order.  The window loop itself is window_scan.cuh.
 //
 // Replaces the window loop of SignatureBuilder<K>::load_kmers_from_sequence
-// (reference src/signature_build.tcc:162-180):
-//   - a window is valid iff all 8 bytes are in ok_prot_ (src/signature_build.h:102-103)
-//     and it lies inside one protein (it < seq.end()-K+1);
-//   - offset = (unsigned short)(len - p)   (:164);
-//   - records are emitted in increasing position, proteins in input order, which
-//     is the multimap insertion order of the reference's serial branch (:50-56).
+// (reference src/signature_build.tcc:162-180).
 //
-// Layout: each thread owns 16 consecutive window positions and reads its 16
-// residues with one 128-bit load (a warp reads 512 contiguous bytes); the 7
-// look-ahead residues come from the next lane by shuffle.  The 43-bit base-40
-// code is rolled (one multiply-add per window).  Valid windows are compacted
-// through shared memory and leave the CTA as coalesced 8-byte / 4-byte stores;
-// the CTA's place in the output is a single-pass chained scan over tile totals
-// (tiles are tickets, so the record order is the position order); every warp
-// owns its own slice and scan entry, so there is no block barrier after the ticket.
-//
-// HBM traffic per valid window: ~1 byte read, 12 bytes written.
+//   window_count_kernel   the digit histograms of every sort pass, taken from the residues before a
+//                         single record exists (0.6 GB read instead of the 4.7 GB key re-read a
+//                         histogram of encoded records costs), the number of records with a
+//                         lower-case residue (the side run), and every protein's window count.
+//                         It is what lets the first radix pass be fused with the encode
+//                         (encode_sort_kernel, onesweep.cu).
+//   encode_split_kernel   encode + route: every record goes straight to the output region of the rank
+//                         that owns its k-mer range (multi-GPU; with one owner it is the plain encode).
 #include "kernels.h"
 #include "sigk_common.cuh"
+#include "window_scan.cuh"
 
 #include <cstdlib>
 
@@ -30,139 +25,69 @@ namespace sigk {
 namespace {
 
 constexpr int ENC_WARPS = ENC_THREADS / 32;
-constexpr int ENC_SUB = 32 * ENC_PPT;                 // window positions one warp owns: 512
+constexpr int ENC_SUB = WS_SUB;                       // window positions one warp owns: 512
 // compacted records are staged with one pad slot per 16 so that the
 // thread-contiguous writes (stride ~16 records between lanes) spread over banks
 constexpr int ENC_STAGE = ENC_SUB + ENC_SUB / 16;
 SIGK_D int stage_slot(int o) { return o + (o >> 4); }
 
-struct EncSmem {
-    uint64_t keys[ENC_WARPS][ENC_STAGE];
-    uint32_t vals[ENC_WARPS][ENC_STAGE];
-    uint32_t tile;
-};
+// ---- count pass -----------------------------------------------------------------------------
+// A persistent grid walks the slices; digit counts go to shared-memory counters (one flush per
+// CTA).  Records whose window has a lower-case residue (mask8 != 0) are counted into the side bin
+// of pass 0 only: the first sort pass diverts them into the side run, which gets its own small
+// histogram later (launch_histogram over the side run).
+constexpr int WC_THREADS = 256;
+constexpr int WC_WARPS = WC_THREADS / 32;
 
-// largest i in [lo, hi] with starts[i] <= g   (starts[lo] <= g is guaranteed)
-SIGK_D uint32_t find_protein(const uint64_t *__restrict__ starts, uint32_t lo, uint32_t hi, uint64_t g) {
-    while (lo < hi) {
-        const uint32_t mid = lo + ((hi - lo + 1) >> 1);
-        if (__ldg(starts + mid) <= g) lo = mid;
-        else hi = mid - 1;
-    }
-    return lo;
-}
-
-// The warps of a CTA are independent after the ticket: each owns ENC_SUB positions and
-// its own entry in the chained scan, so nothing waits at a block barrier.
-__global__ void __launch_bounds__(ENC_THREADS, 4)
-encode_kernel(EncodeArgs a, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
-              uint64_t *__restrict__ scan_state, uint32_t *__restrict__ ticket, uint64_t *__restrict__ n_out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    EncSmem &sm = *reinterpret_cast<EncSmem *>(smem_raw);
-
+template <int NPASS>
+__global__ void __launch_bounds__(WC_THREADS, 3)
+window_count_kernel(EncodeArgs a, const __grid_constant__ PassPlan plan, uint64_t *__restrict__ hist, uint32_t n_slices) {
+    __shared__ uint32_t sh[NPASS * SIGK_RADIX];
     __shared__ int8_t s_sym[256];
+    __shared__ uint32_t s_side;
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
-    static_assert(ENC_THREADS == 256, "one table entry per thread");
-    s_sym[tid] = (int8_t)sigk_symbol(tid);
+    ws_fill_symbols(s_sym);
+    for (int j = tid; j < NPASS * SIGK_RADIX; j += WC_THREADS) sh[j] = 0;
+    if (tid == 0) s_side = 0;
     __syncthreads();
-    const uint32_t sub = sm.tile * ENC_WARPS + warp;                 // this warp's entry in the chained scan
-    const uint64_t g0 = (uint64_t)sub * ENC_SUB;
-    if (g0 >= a.total_res) return;
-    const bool last_sub = g0 + ENC_SUB >= a.total_res;
-
-    // protein range of the warp's positions, from the per-slice index built by slice_index_kernel
-    const uint32_t p_lo = __ldg(a.slice_prot + sub);
-    const uint32_t p_hi = last_sub ? a.n_prot - 1 : __ldg(a.slice_prot + sub + 1);
-
-    // residues: 16 of my own + 8 of the next lane's
-    const uint64_t g_first = g0 + (uint64_t)lane * ENC_PPT;
-    const uint4 w = ld_stream_u128(reinterpret_cast<const uint4 *>(a.res + g_first));
-    uint32_t n0 = __shfl_down_sync(0xffffffffu, w.x, 1);
-    uint32_t n1 = __shfl_down_sync(0xffffffffu, w.y, 1);
-    if (lane == 31) {
-        const uint2 nx = *reinterpret_cast<const uint2 *>(a.res + g_first + ENC_PPT);
-        n0 = nx.x; n1 = nx.y;
-    }
-    const uint32_t words[6] = {w.x, w.y, w.z, w.w, n0, n1};
-
-    // symbols stay packed four to a register (23 ints would not fit the register budget)
-    uint32_t sw[6] = {0, 0, 0, 0, 0, 0};
-    uint32_t bad = 0;
-#pragma unroll
-    for (int j = 0; j < ENC_PPT + 7; ++j) {
-        const unsigned c = (words[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-        int sy = s_sym[c];                              // byte -> symbol 0..39, or -1 (table: 1/5 of the arithmetic form's instructions)
-        if (sy < 0) { bad |= 1u << j; sy = 0; }
-        sw[j >> 2] |= (uint32_t)sy << (8 * (j & 3));
-    }
-#define SIGK_SYM(j) ((uint64_t)((sw[(j) >> 2] >> (8 * ((j) & 3))) & 0xFFu))
-
-    // pass A: which of my 16 windows are valid
-    const uint32_t p_first = find_protein(a.starts, p_lo, p_hi, g_first < a.total_res ? g_first : a.total_res - 1);
-    uint32_t valid_mask = 0;
-    {
-        uint32_t i = p_first;
-        uint64_t prot_end = __ldg(a.starts + i + 1);
-#pragma unroll
-        for (int j = 0; j < ENC_PPT; ++j) {
-            const uint64_t g = g_first + j;
-            while (g >= prot_end && i + 1 < a.n_prot) { ++i; prot_end = __ldg(a.starts + i + 1); }
-            if (((bad >> j) & 0xFFu) == 0 && g + SIGK_K_DEV <= prot_end) valid_mask |= 1u << j;
-        }
-    }
-    const uint32_t mine = (uint32_t)__popc(valid_mask);
-    uint32_t incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (unsigned)o) incl += y;
-    }
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    chained_scan_publish_warp(scan_state, sub, total);     // resolved after pass B: the predecessors publish meanwhile
-
-    // pass B: roll the code, emit valid windows to their compacted slots
-    {
-        uint32_t i = p_first;
-        uint64_t prot_end = __ldg(a.starts + i + 1);
-        uint64_t code = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) code = code * 40u + SIGK_SYM(j);
-        int o = (int)(incl - mine);
+    uint32_t side = 0;
+    for (uint64_t sub = (uint64_t)blockIdx.x * WC_WARPS + warp; sub < n_slices; sub += (uint64_t)gridDim.x * WC_WARPS) {
+        if (sub * WS_SUB >= a.total_res) break;
+        WindowLane w;
+        ws_load(a, s_sym, (uint32_t)sub, w);
+        const uint32_t valid = ws_valid_mask(a, w);
         uint32_t run_i = 0, run_c = 0;              // occurrences of the protein I am inside
+        ws_for_each(a, w, valid, [&](int, uint64_t key, uint32_t i) {
+            if (sigk_key_mask(key) == 0) {
 #pragma unroll
-        for (int j = 0; j < ENC_PPT; ++j) {
-            const uint64_t g = g_first + j;
-            if (j > 0) code = (code - SIGK_SYM(j - 1) * SIGK_P7) * 40u + SIGK_SYM(j + 7);
-            while (g >= prot_end && i + 1 < a.n_prot) { ++i; prot_end = __ldg(a.starts + i + 1); }
-            if ((valid_mask >> j) & 1u) {
-                const int slot = stage_slot(o++);
-                sm.keys[warp][slot] = sigk_pack_key(code, (unsigned)(prot_end - g));
-                sm.vals[warp][slot] = a.ordinal_base + i;
-                if (i != run_i) {
-                    if (run_c && a.prot_windows) atomicAdd(a.prot_windows + run_i, run_c);
-                    run_i = i; run_c = 0;
-                }
-                ++run_c;
+                for (int p = 0; p < NPASS; ++p)
+                    atomicAdd(&sh[p * SIGK_RADIX + ((uint32_t)(key >> plan.lo[p]) & ((1u << plan.bits[p]) - 1u))], 1u);
+            } else {
+                ++side;
             }
-        }
+            if (i != run_i) {
+                if (run_c && a.prot_windows) atomicAdd(a.prot_windows + run_i, run_c);
+                run_i = i; run_c = 0;
+            }
+            ++run_c;
+        });
         if (run_c && a.prot_windows) atomicAdd(a.prot_windows + run_i, run_c);
     }
-    __syncwarp();
-    const uint64_t base = chained_scan_resolve_warp(scan_state, sub, total);
-    if (last_sub && lane == 0) *n_out = base + total;
-    for (uint32_t o = lane; o < total; o += 32) {
-        const int slot = stage_slot((int)o);
-        keys[base + o] = sm.keys[warp][slot];
-        vals[base + o] = sm.vals[warp][slot];
-    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) side += __shfl_xor_sync(0xffffffffu, side, o);
+    if (lane == 0 && side) atomicAdd(&s_side, side);
+    __syncthreads();
+    for (int j = tid; j < NPASS * SIGK_RADIX; j += WC_THREADS)
+        if (sh[j]) atomicAdd(reinterpret_cast<unsigned long long *>(hist + (size_t)(j / SIGK_RADIX) * SIGK_BINS + (j % SIGK_RADIX)),
+                             (unsigned long long)sh[j]);
+    if (tid == 0 && s_side) atomicAdd(reinterpret_cast<unsigned long long *>(hist + SIGK_SIDE_BIN), (unsigned long long)s_side);
 }
 
-// ---- multi-GPU: encode and route in one pass ---------------------------------------------------
-// The same window loop, but every record is written straight into the output region of the rank
-// that owns its k-mer range (owner = number of splitter codes <= code), in canonical order inside
+// ---- encode and route in one pass -----------------------------------------------------------
+// Every record is written straight into the output region of the rank that owns its k-mer range
+// (owner = number of splitter codes <= the record's case-folded code35), in canonical order inside
 // each region: one chained scan per owner over the warp slices (a lane per owner walks back, as in
-// the onesweep look-back).  This replaces encode + owner histogram + split pass.
+// the onesweep look-back).  With no splitters there is one owner and the kernel is the plain encode.
 // Per-owner 16-bit counters live four to a 64-bit word; the kernel is instantiated for 1, 2 or 4
 // words (up to 4, 8, 16 ranks) so that the common small worlds keep a small register footprint.
 
@@ -200,7 +125,8 @@ encode_split_kernel(EncodeArgs a, const __grid_constant__ EncodeSplitArgs sp, ui
     __shared__ int8_t s_sym[256];
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t W = (uint32_t)sp.n_split + 1u;
-    s_sym[tid] = (int8_t)sigk_symbol(tid);
+    static_assert(ENC_THREADS == 256, "one symbol table entry per thread");
+    ws_fill_symbols(s_sym);
     if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
     if (tid < (unsigned)sp.n_split) sm.split[tid] = sp.split_codes[tid];
     if (tid < 16) { sm.dkeys[tid] = sp.dst_keys[tid]; sm.dvals[tid] = sp.dst_vals[tid]; }
@@ -209,56 +135,26 @@ encode_split_kernel(EncodeArgs a, const __grid_constant__ EncodeSplitArgs sp, ui
     const uint64_t g0 = (uint64_t)sub * ENC_SUB;
     if (g0 >= a.total_res) return;
     const bool last_sub = g0 + ENC_SUB >= a.total_res;
-    const uint32_t p_lo = __ldg(a.slice_prot + sub);
-    const uint32_t p_hi = last_sub ? a.n_prot - 1 : __ldg(a.slice_prot + sub + 1);
 
-    const uint64_t g_first = g0 + (uint64_t)lane * ENC_PPT;
-    const uint4 w = ld_stream_u128(reinterpret_cast<const uint4 *>(a.res + g_first));
-    uint32_t n0 = __shfl_down_sync(0xffffffffu, w.x, 1);
-    uint32_t n1 = __shfl_down_sync(0xffffffffu, w.y, 1);
-    if (lane == 31) {
-        const uint2 nx = *reinterpret_cast<const uint2 *>(a.res + g_first + ENC_PPT);
-        n0 = nx.x; n1 = nx.y;
-    }
-    const uint32_t words[6] = {w.x, w.y, w.z, w.w, n0, n1};
-    // symbols stay packed four to a register (23 ints would not fit the register budget)
-    uint32_t sw[6] = {0, 0, 0, 0, 0, 0};
-    uint32_t bad = 0;
-#pragma unroll
-    for (int j = 0; j < ENC_PPT + 7; ++j) {
-        const unsigned c = (words[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-        int sy = s_sym[c];                              // byte -> symbol 0..39, or -1 (table: 1/5 of the arithmetic form's instructions)
-        if (sy < 0) { bad |= 1u << j; sy = 0; }
-        sw[j >> 2] |= (uint32_t)sy << (8 * (j & 3));
-    }
-#define SIGK_SYM(j) ((uint64_t)((sw[(j) >> 2] >> (8 * ((j) & 3))) & 0xFFu))
+    WindowLane w;
+    ws_load(a, s_sym, sub, w);
+    const uint32_t valid_mask = ws_valid_mask(a, w);
 
-    // pass A: valid windows, their owners (4 bits each), per-owner counts
-    const uint32_t p_first = find_protein(a.starts, p_lo, p_hi, g_first < a.total_res ? g_first : a.total_res - 1);
-    uint32_t valid_mask = 0;
+    // pass A: the owners of the valid windows (4 bits each), per-owner counts
     uint64_t owners = 0;
     uint64_t cnt[SPLIT_WORDS];
 #pragma unroll
     for (int k = 0; k < SPLIT_WORDS; ++k) cnt[k] = 0;
-    {
-        uint32_t i = p_first;
-        uint64_t prot_end = __ldg(a.starts + i + 1);
-        uint64_t code = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) code = code * 40u + SIGK_SYM(j);
-#pragma unroll
-        for (int j = 0; j < ENC_PPT; ++j) {
-            const uint64_t g = g_first + j;
-            if (j > 0) code = (code - SIGK_SYM(j - 1) * SIGK_P7) * 40u + SIGK_SYM(j + 7);
-            while (g >= prot_end && i + 1 < a.n_prot) { ++i; prot_end = __ldg(a.starts + i + 1); }
-            if (((bad >> j) & 0xFFu) == 0 && g + SIGK_K_DEV <= prot_end) {
-                valid_mask |= 1u << j;
-                uint32_t d = 0;
-                for (int k = 0; k < sp.n_split; ++k) d += code >= sm.split[k] ? 1u : 0u;
-                owners |= (uint64_t)d << (4 * j);
-                bump16(cnt, d);
-            }
-        }
+    if (sp.n_split > 0) {
+        ws_for_each(a, w, valid_mask, [&](int j, uint64_t key, uint32_t) {
+            const uint64_t code = sigk_key_code35(key);
+            uint32_t d = 0;
+            for (int k = 0; k < sp.n_split; ++k) d += code >= sm.split[k] ? 1u : 0u;
+            owners |= (uint64_t)d << (4 * j);
+            bump16(cnt, d);
+        });
+    } else {
+        cnt[0] = (uint64_t)__popc(valid_mask);
     }
     // warp scan of the packed counters (a slice has at most 512 records: 16-bit fields never carry)
     uint64_t incl[SPLIT_WORDS];
@@ -283,7 +179,6 @@ encode_split_kernel(EncodeArgs a, const __grid_constant__ EncodeSplitArgs sp, ui
         const uint32_t y = __shfl_up_sync(0xffffffffu, ob, o);
         if (lane >= (unsigned)o) ob += y;
     }
-    const uint32_t total = __shfl_sync(0xffffffffu, ob, 15);
     ob -= t_d;
     if (lane < 16) sm.obase[warp][lane] = ob;
     uint64_t *my_state = sp.owner_state + (size_t)sub * W + lane;
@@ -293,35 +188,24 @@ encode_split_kernel(EncodeArgs a, const __grid_constant__ EncodeSplitArgs sp, ui
     // pass B: roll the code again, emit every valid window to its owner's part of the staging area
     // (the empty asm makes the symbols opaque so that pass A's partial products are not kept live)
 #pragma unroll
-    for (int k = 0; k < 6; ++k) asm volatile("" : "+r"(sw[k]));
+    for (int k = 0; k < 6; ++k) asm volatile("" : "+r"(w.rk[k]));
     {
-        uint32_t i = p_first;
-        uint64_t prot_end = __ldg(a.starts + i + 1);
-        uint64_t code = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) code = code * 40u + SIGK_SYM(j);
         uint64_t run[SPLIT_WORDS];
 #pragma unroll
         for (int k = 0; k < SPLIT_WORDS; ++k) run[k] = excl[k];
-        uint32_t run_i = 0, run_c = 0;
-#pragma unroll
-        for (int j = 0; j < ENC_PPT; ++j) {
-            const uint64_t g = g_first + j;
-            if (j > 0) code = (code - SIGK_SYM(j - 1) * SIGK_P7) * 40u + SIGK_SYM(j + 7);
-            while (g >= prot_end && i + 1 < a.n_prot) { ++i; prot_end = __ldg(a.starts + i + 1); }
-            if ((valid_mask >> j) & 1u) {
-                const uint32_t d = (uint32_t)(owners >> (4 * j)) & 15u;
-                const int slot = stage_slot((int)(sm.obase[warp][d] + field16(run, d)));
-                bump16(run, d);
-                sm.keys[warp][slot] = sigk_pack_key(code, (unsigned)(prot_end - g));
-                sm.vals[warp][slot] = a.ordinal_base + i;
-                if (i != run_i) {
-                    if (run_c && a.prot_windows) atomicAdd(a.prot_windows + run_i, run_c);
-                    run_i = i; run_c = 0;
-                }
-                ++run_c;
+        uint32_t run_i = 0, run_c = 0;              // occurrences of the protein I am inside
+        ws_for_each(a, w, valid_mask, [&](int j, uint64_t key, uint32_t i) {
+            const uint32_t d = (uint32_t)(owners >> (4 * j)) & 15u;
+            const int slot = stage_slot((int)(sm.obase[warp][d] + field16(run, d)));
+            bump16(run, d);
+            sm.keys[warp][slot] = key;
+            sm.vals[warp][slot] = a.ordinal_base + i;
+            if (i != run_i) {
+                if (run_c && a.prot_windows) atomicAdd(a.prot_windows + run_i, run_c);
+                run_i = i; run_c = 0;
             }
-        }
+            ++run_c;
+        });
         if (run_c && a.prot_windows) atomicAdd(a.prot_windows + run_i, run_c);
     }
 
@@ -333,7 +217,7 @@ encode_split_kernel(EncodeArgs a, const __grid_constant__ EncodeSplitArgs sp, ui
             for (;;) {
                 const uint64_t v = ld_volatile_u64(sp.owner_state + (size_t)t * W + lane);
                 const uint64_t flag = v >> 62;
-                if (flag == 0) continue;
+                if (flag == 0) { __nanosleep(20); continue; }
                 before += v & SIGK_CS_VAL;
                 if (flag == 2) break;
                 --t;
@@ -344,7 +228,7 @@ encode_split_kernel(EncodeArgs a, const __grid_constant__ EncodeSplitArgs sp, ui
         if (last_sub) sp.owner_totals[lane] = before + t_d;
     }
     __syncwarp();
-    if (*reinterpret_cast<volatile uint32_t *>(sp.overflow)) return;      // regions too small: the caller falls back
+    if (*reinterpret_cast<volatile uint32_t *>(sp.overflow)) return;      // regions too small: the caller grows them and retries
 
     // One owner at a time: its records are a contiguous run of the staging area and go to a contiguous run
     // of the owner's region.  The body of every run leaves as 16-byte stores (two keys / four values per
@@ -405,9 +289,23 @@ cudaError_t launch_slice_index(const uint64_t *starts, uint32_t n_prot, uint64_t
     return cudaGetLastError();
 }
 
+cudaError_t launch_window_count(const EncodeArgs &a, const PassPlan &plan, uint64_t *hist, int sm_count, cudaStream_t stream) {
+    if (a.total_res == 0 || a.n_prot == 0) return cudaSuccess;
+    const uint64_t n_slices = (a.total_res + WS_SUB - 1) / WS_SUB;
+    const uint64_t want = (n_slices + WC_WARPS - 1) / WC_WARPS;
+    const unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)sm_count * 8);
+    switch (plan.npass) {
+        case 3: window_count_kernel<3><<<grid, WC_THREADS, 0, stream>>>(a, plan, hist, (uint32_t)n_slices); break;
+        case 4: window_count_kernel<4><<<grid, WC_THREADS, 0, stream>>>(a, plan, hist, (uint32_t)n_slices); break;
+        case 5: window_count_kernel<5><<<grid, WC_THREADS, 0, stream>>>(a, plan, hist, (uint32_t)n_slices); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_encode_split(const EncodeArgs &a, const EncodeSplitArgs &sp, uint32_t *ticket, cudaStream_t stream) {
     if (a.total_res == 0 || a.n_prot == 0) return cudaSuccess;
-    if (sp.n_split < 1 || sp.n_split > 15) return cudaErrorInvalidValue;
+    if (sp.n_split < 0 || sp.n_split > 15) return cudaErrorInvalidValue;
     // 1, 2 or 4 counter words for up to 4, 8, 16 ranks.  SIGK_TEST_SPLIT_WORDS=2|4 forces a wider instantiation than the
     // rank count needs, so that a two-GPU box can exercise the kernels of the larger worlds (tests/multigpu_check.py).
     int words = sp.n_split < 4 ? 1 : sp.n_split < 8 ? 2 : 4;
@@ -419,17 +317,6 @@ cudaError_t launch_encode_split(const EncodeArgs &a, const EncodeSplitArgs &sp, 
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSplitSmem));
     if (e != cudaSuccess) return e;
     kernel<<<(unsigned)encode_tiles(a.total_res), ENC_THREADS, sizeof(EncSplitSmem), stream>>>(a, sp, ticket);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_encode(const EncodeArgs &a, uint64_t *keys, uint32_t *vals, uint64_t *scan_state,
-                          uint32_t *ticket, uint64_t *n_out, cudaStream_t stream) {
-    if (a.total_res == 0 || a.n_prot == 0) return cudaSuccess;   // n_out stays 0
-    // per device, so set on every launch (a process may drive several devices through several handles)
-    cudaError_t attr = cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem));
-    if (attr != cudaSuccess) return attr;
-    const uint64_t tiles = encode_tiles(a.total_res);
-    encode_kernel<<<(unsigned)tiles, ENC_THREADS, sizeof(EncSmem), stream>>>(a, keys, vals, scan_state, ticket, n_out);
     return cudaGetLastError();
 }
 

@@ -14,16 +14,19 @@
 namespace sigk {
 
 struct DeviceScalars {
-    uint64_t n_records;
+    uint64_t n_records;         // valid windows this GPU sorts: n_main + n_side
     uint64_t n_segments;
     uint64_t n_kept;
     uint64_t n_seqs_sig;
+    uint64_t n_main, n_side, n_both;   // written together by scan_bins_kernel: records without / with a lower-case residue
+    uint64_t n_side_kept;       // kept rows of the side run (the table's second section)
+    uint32_t overflow, pad0;
     uint32_t ticket[16];
     uint32_t n_groups, next_group, n_long, next_long, n_work, next_work, n_work_long, next_work_long;
     uint64_t reduce_in[4];      // multi-GPU: {occurrences, groups, kept, -} of this rank -> summed over ranks
 };
 
-enum { TK_ENCODE = 0, TK_REDUCE = 1, TK_SQUEEZE = 2, TK_PARTITION = 3, TK_SORT0 = 4 };
+enum { TK_ENCODE = 0, TK_REDUCE = 1, TK_SQUEEZE = 2, TK_SORT0 = 3, TK_SIDE0 = 8 };      // TK_SORT0 + main passes <= TK_SIDE0; TK_SIDE0 + side passes <= 16
 
 template <typename T> struct DevBuf {
     T *p = nullptr;
@@ -51,7 +54,7 @@ template <typename T> struct PinnedBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-enum { EV_START, EV_H2D, EV_DEV0, EV_ENCODE, EV_EXCHANGE, EV_HIST, EV_SORT, EV_REDUCE, EV_ORDER, EV_SQUEEZE, EV_D2H,
+enum { EV_START, EV_H2D, EV_DEV0, EV_ENCODE, EV_EXCHANGE, EV_HIST, EV_MAIN_SORTED, EV_SORT, EV_REDUCE, EV_ORDER, EV_SQUEEZE, EV_D2H,
        EV_USER0, EV_USER1, EV_USER2, EV_USER3, EV_PASS0, EV_COUNT = EV_PASS0 + SORT_MAX_PASSES + 1 };
 
 struct Comm;    // comm.cu
@@ -105,13 +108,15 @@ struct sigk_handle {
 
     sigk_timings tm{};
     float h2d_ms = 0;
-    sigk::PassPlan plan{};
+    sigk::PassPlan plan{}, plan_side{};
+    bool fused = true;                 // single GPU: encode fused with the first radix pass (SIGK_NO_FUSED=1 turns it off)
 
     // multi-GPU
     sigk::Comm *comm = nullptr;
     uint64_t n_prot_global = 0;         // proteins of the whole job
     uint64_t ordinal_base = 0;          // ordinal of this rank's first protein
     uint64_t n_recv = 0;                // records this rank owns after the exchange
+    uint32_t upload_launches = 0;       // kernels sigk_upload launched (per-protein table, splitters)
 
     int fail(int code, const char *fmt, ...) {
         char buf[512];
@@ -145,10 +150,15 @@ void comm_destroy(sigk_handle *h);
 int comm_exchange_shapes(sigk_handle *h);
 // share the per-protein meta of every rank (h->d_meta holds n_prot_global entries afterwards)
 int comm_allgather_meta(sigk_handle *h);
-// encode output in keys[0]/vals[0] -> records of this rank's k-mer range in keys[0]/vals[0], n_records updated
-int comm_partition_exchange(sigk_handle *h, uint32_t *launches);
-// multi-GPU stage 1: encode + route + all-to-all (fused kernel, falls back to encode + split pass)
-int comm_encode_exchange(sigk_handle *h, const EncodeArgs &ea, uint32_t *launches);
+// multi-GPU stage 1: encode + route (+ all-to-all without peer mappings); fills `seg` with the regions, in source-rank
+// order, that hold this rank's records (the first sort pass reads them in place)
+int comm_encode_exchange(sigk_handle *h, const EncodeArgs &ea, SortSegments *seg, int *first_out, uint32_t *launches);
+// min over the ranks of a 0/1 word (with a host synchronisation): collective decisions, and a barrier
+int comm_agree(sigk_handle *h, uint64_t mine, uint64_t *out);
+// (re)create and map the peer landing zones for the current job size (collective)
+int comm_setup_landing(sigk_handle *h);
+// once per upload: the splitter codes that cut the k-mer space into one range per rank
+int comm_choose_splitters(sigk_handle *h, uint32_t *launches);
 // sum over ranks of the per-protein rejected-occurrence counts (before signature_flags)
 int comm_reduce_rejected(sigk_handle *h);
 // sum the per-rank statistics so that every rank's result carries whole-job counters

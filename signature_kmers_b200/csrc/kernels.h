@@ -29,20 +29,19 @@ struct EncodeArgs {
 inline uint64_t encode_tiles(uint64_t total_res) { return (total_res + ENC_TILE - 1) / ENC_TILE; }
 inline uint64_t encode_slices(uint64_t total_res) { return encode_tiles(total_res) * (ENC_THREADS / 32); }
 cudaError_t launch_slice_index(const uint64_t *starts, uint32_t n_prot, uint64_t total_res, uint32_t *slice_prot, cudaStream_t stream);
-inline uint64_t encode_scan_entries(uint64_t total_res) { return encode_tiles(total_res) * (ENC_THREADS / 32) + 1; }
+// Digit histograms of the main records (hist rows of SORT_BINS entries, zeroed), the side-record count in
+// hist[SORT_RADIX] and — when a.prot_windows is set — every protein's window count, all from the residues.
+struct PassPlan;
+cudaError_t launch_window_count(const EncodeArgs &a, const PassPlan &plan, uint64_t *hist, int sm_count, cudaStream_t stream);
 
-// scan_state: encode_scan_entries() u64 words, zeroed; ticket: one zeroed u32; n_out: u64.
-cudaError_t launch_encode(const EncodeArgs &a, uint64_t *keys, uint32_t *vals, uint64_t *scan_state,
-                          uint32_t *ticket, uint64_t *n_out, cudaStream_t stream);
-
-
-// Multi-GPU: encode and route in one pass.  Owner d's records go, in canonical order, to
+// Encode and route in one pass (multi-GPU; with n_split == 0 there is one owner and this is the plain encode).
+// Owner d's records go, in canonical order, to
 // dst_keys[d][0...] / dst_vals[d][0...] (this rank's region on owner d: a local send region, or — with
 // peer mappings — memory of GPU d written over NVLink); owner_totals[d] receives their number; *overflow is
-// set (and the output is incomplete) if a region is too small.  owner_state: encode_slices() * (n_split + 1)
+// set (and the output is incomplete, but the totals are still exact) if a region is too small.  owner_state: encode_slices() * (n_split + 1)
 // zeroed u64 words.
 struct EncodeSplitArgs {
-    const uint64_t *split_codes;   // device, n_split ascending codes: owner = number of codes <= the record's code
+    const uint64_t *split_codes;   // device, n_split ascending case-folded codes (code35): owner = number of codes <= the record's
     int n_split;
     uint64_t region_stride;        // records each region can hold
     uint64_t *owner_state;
@@ -55,7 +54,10 @@ cudaError_t launch_encode_split(const EncodeArgs &a, const EncodeSplitArgs &sp, 
 
 // ---- stage 2: onesweep LSD radix sort (onesweep.cu) ------------------------
 constexpr int SORT_MAX_PASSES = 8;
-constexpr int SORT_MAX_SPLIT = 15;    // the partition pass routes to at most 16 ranks
+constexpr int SORT_MAX_SEGMENTS = 16; // the first pass reads up to 16 source regions (one per rank) in place
+constexpr int SORT_RADIX_BITS = 9;
+constexpr int SORT_RADIX = 1 << SORT_RADIX_BITS;
+constexpr int SORT_BINS = SORT_RADIX + 8;   // row stride of hist / bin_base / look-back: digits, the side bin, padding
 struct PassPlan {
     int npass;
     int lo[SORT_MAX_PASSES];
@@ -71,27 +73,54 @@ PassPlan make_pass_plan(int bit_lo, int bit_hi);
 constexpr int OS_THREADS = SIGK_OS_THREADS;
 constexpr int OS_ITEMS = SIGK_OS_ITEMS;
 constexpr int OS_MIN_BLOCKS = SIGK_OS_MIN_BLOCKS;  // CTAs per SM the pass kernel is sized for
-constexpr int OS_TILE = OS_THREADS * OS_ITEMS;    // 3328 records per CTA
+constexpr int OS_TILE = OS_THREADS * OS_ITEMS;    // 7680 records per tile
+// the fused encode + first pass works on tiles of whole 512-position slices, one per encoding warp; its staging
+// carries one pad slot per 16 records, so the tile is a little smaller than a plain pass's
+constexpr int ES_WARPS = OS_THREADS / 32 - (OS_THREADS >= 512 ? 2 : 1);
+constexpr int ES_TILE = ES_WARPS * 512;           // window positions per tile (7168 = 14 slices with 512 threads)
+constexpr int ES_ITEMS = ES_TILE / OS_THREADS;
+static_assert(ES_ITEMS * OS_THREADS == ES_TILE && ES_ITEMS <= OS_ITEMS, "fused tile shape");
 inline uint64_t onesweep_tiles(uint64_t capacity) { return (capacity + OS_TILE - 1) / OS_TILE; }
-// bytes of look-back state one pass needs for `capacity` records
+inline uint64_t encode_sort_tiles(uint64_t total_res) { return (total_res + ES_TILE - 1) / ES_TILE; }
+// bytes of look-back state one pass needs for `capacity` records (either kind of tile)
 size_t onesweep_lookback_bytes(uint64_t capacity);
 
-// hist: [npass][SIGK_RADIX] u64, zeroed.  Counts the digit of every pass in one read of the keys.
-cudaError_t launch_histogram(const uint64_t *keys, const uint64_t *n_ptr, uint64_t capacity, const PassPlan &plan,
-                             uint64_t *hist, int sm_count, cudaStream_t stream);
-// bin_base[p][d] = exclusive scan over d of hist[p][d]
-cudaError_t launch_scan_bins(const uint64_t *hist, uint64_t *bin_base, int npass, cudaStream_t stream);
-// One stable scatter pass on key bits [bit_lo, bit_lo+nbits).  lookback zeroed, ticket zeroed.
+// The input of a first pass: up to 16 regions read in order (one per source rank; one region on a single GPU).
+struct SortSegments {
+    int n;
+    uint64_t start[SORT_MAX_SEGMENTS + 1];      // first record index of each region in the concatenation; start[n] = total
+    const uint64_t *keys[SORT_MAX_SEGMENTS];
+    const uint32_t *vals[SORT_MAX_SEGMENTS];
+};
+
+// hist: [npass][SORT_BINS] u64, zeroed.  Counts the digit of every pass in one read of the keys at keys + *off_ptr
+// (off_ptr may be null), *n_ptr records.
+cudaError_t launch_histogram(const uint64_t *keys, const uint64_t *n_ptr, const uint64_t *off_ptr, uint64_t capacity,
+                             const PassPlan &plan, uint64_t *hist, int sm_count, cudaStream_t stream);
+// The same over the regions of a first pass, main records only (mask8 == 0); the others are counted into the side bin of row 0.
+cudaError_t launch_histogram_main(const SortSegments &seg, const uint64_t *n_ptr, const PassPlan &plan, uint64_t *hist,
+                                  int sm_count, cudaStream_t stream);
+// bin_base[p][d] = exclusive scan over d of hist[p][d] (row 0 includes the side bin: bin_base[0][SORT_RADIX] = number of
+// main records).  counts (may be null) receives {main records, side records, both}.
+cudaError_t launch_scan_bins(const uint64_t *hist, uint64_t *bin_base, int npass, uint64_t *counts, cudaStream_t stream);
+// One stable scatter pass on key bits [bit_lo, bit_lo+nbits) of the *n_ptr records at offset *off_ptr (null = 0) of the
+// in/out buffers.  lookback zeroed (launch_clear_lookback or a memset), ticket zeroed.
 cudaError_t launch_onesweep_pass(const uint64_t *keys_in, const uint32_t *vals_in, uint64_t *keys_out,
-                                 uint32_t *vals_out, const uint64_t *n_ptr, uint64_t capacity, int bit_lo, int nbits,
-                                 const uint64_t *bin_base, void *lookback, uint32_t *ticket, cudaStream_t stream);
-cudaError_t onesweep_configure();   // opt in to the dynamic shared memory the pass kernel needs
-// The same kernel as a stable multi-way split: digit = number of split_codes <= the record's k-mer code
-// (the rank owning the record).  bin_base[d] = first output slot of rank d (SIGK_RADIX entries).
-cudaError_t launch_onesweep_partition(const uint64_t *keys_in, const uint32_t *vals_in, uint64_t *keys_out,
-                                      uint32_t *vals_out, const uint64_t *n_ptr, uint64_t capacity,
-                                      const uint64_t *split_codes, int n_split, const uint64_t *bin_base, void *lookback,
-                                      uint32_t *ticket, cudaStream_t stream);
+                                 uint32_t *vals_out, const uint64_t *n_ptr, const uint64_t *off_ptr, uint64_t capacity, int bit_lo, int nbits,
+                                 const uint64_t *bin_base, void *lookback, uint32_t *ticket, int sm_count, cudaStream_t stream);
+// The first pass of a build over already encoded records: reads the regions of `seg` in place, sorts the main records
+// (mask8 == 0) on their lowest digit into keys_out[0 ..) and appends the others, in input order, behind them (the side run).
+// n_ptr (may be null) overrides the total when seg has one region whose size is only known on the device.
+cudaError_t launch_onesweep_first_pass(const SortSegments &seg, const uint64_t *n_ptr, uint64_t *keys_out, uint32_t *vals_out,
+                                       uint64_t capacity, int bit_lo, int nbits, const uint64_t *bin_base, void *lookback,
+                                       uint32_t *ticket, int sm_count, cudaStream_t stream);
+// Encode fused with that first pass (single GPU): records go from the residues straight to their place after one radix
+// pass; they never exist in HBM in canonical order.  hist/bin_base come from launch_window_count + launch_scan_bins.
+cudaError_t launch_encode_sort(const EncodeArgs &a, uint64_t *keys_out, uint32_t *vals_out, int bit_lo, int nbits,
+                               const uint64_t *bin_base, void *lookback, uint32_t *ticket, int sm_count, cudaStream_t stream);
+// zero the look-back rows a pass over *n_ptr records will use
+cudaError_t launch_clear_lookback(void *lookback, const uint64_t *n_ptr, uint64_t capacity, cudaStream_t stream);
+cudaError_t onesweep_configure();   // opt in to the dynamic shared memory the pass kernels need
 
 // ---- stages 3+4: segment reduce, keep/reject, compaction, order statistics (reduce.cu)
 struct KeptColumns {           // device, capacity rows each
@@ -154,7 +183,7 @@ cudaError_t launch_order_stats(const uint32_t *vals, MetaTable meta, const Order
 // Compaction: kept rows -> table columns (tombstones dropped, order kept).  scratch_words: the buffer the
 // segment reduce of this build used (it holds the per-tile tombstone counts).
 cudaError_t launch_squeeze_rows(const uint4 *rows, const uint64_t *n_seg_ptr, uint64_t capacity, KeptColumns out,
-                                uint64_t *scratch_words, uint64_t *n_kept_out, cudaStream_t stream);
+                                uint64_t *scratch_words, uint64_t *n_kept_out, uint64_t *n_side_kept /* zeroed */, cudaStream_t stream);
 // bitmap bit seq_id[i] is set iff protein i has more occurrences (prot_windows, from encode) than occurrences in
 // rejected groups (prot_rejected, from the reduce): kmer_stats_.seqs_with_a_signature, src/signature_build.tcc:274
 cudaError_t launch_signature_flags(const uint32_t *prot_windows, const uint32_t *prot_rejected, const uint32_t *seq_id,

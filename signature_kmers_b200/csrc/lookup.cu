@@ -8,7 +8,10 @@
 // residue position: the window starting there is visited iff it lies inside its protein and no '*' / 'X'
 // sits in the window or right behind it (`kend >= next_ambig`, src/kmer_data.h:90 — the sequential scan
 // visits exactly those positions); the 8 raw bytes (case preserved, no alphabet test on the call side) are
-// compared as a big-endian integer against the table's k-mer column, which is sorted by bytes.
+// looked up in the table's k-mer column by binary search under the table's order (include/sigk.h): k-mers
+// without a lower-case residue first, in byte order, then the others by (case-folded bytes, case mask).  The
+// order is defined on every 8-byte string (fold = clear bit 0x20 of each byte, mask = those bits), so a query
+// with bytes no table row can hold simply is not found.
 // rows[g] = table row of the window at residue position g, or 0xFFFFFFFF.
 //
 // HBM traffic per position: 1 residue byte read, 4 bytes written, and a binary search whose upper levels
@@ -23,6 +26,18 @@ namespace {
 SIGK_D uint64_t bswap64(uint64_t x) {
     const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
     return ((uint64_t)__byte_perm(lo, 0, 0x0123) << 32) | (uint64_t)__byte_perm(hi, 0, 0x0123);
+}
+
+// a < b in table order; a and b are k-mers as big-endian integers (first residue in the top byte)
+SIGK_D bool table_less(uint64_t a, uint64_t b) {
+    constexpr uint64_t CASE = 0x2020202020202020ull;
+    const uint64_t ma = a & CASE, mb = b & CASE;
+    if ((ma != 0) != (mb != 0)) return mb != 0;               // section: no lower-case residue first
+    const uint64_t fa = a & ~CASE, fb = b & ~CASE;
+    if (fa != fb) return fa < fb;
+    // case mask with residue j in bit j: the first residue is the LEAST significant bit, i.e. the byte order of
+    // the big-endian mask word reversed
+    return bswap64(ma) < bswap64(mb);
 }
 
 __global__ void __launch_bounds__(256)
@@ -55,7 +70,7 @@ lookup_kernel(const uint8_t *__restrict__ res, const uint64_t *__restrict__ star
             uint64_t a = 0, b = *n_rows_ptr;            // first row >= key
             while (a < b) {
                 const uint64_t mid = a + (b - a) / 2;
-                if (bswap64(__ldg(table_kmers + mid)) < key) a = mid + 1; else b = mid;
+                if (table_less(bswap64(__ldg(table_kmers + mid)), key)) a = mid + 1; else b = mid;
             }
             if (a < *n_rows_ptr && bswap64(__ldg(table_kmers + a)) == key) row = (uint32_t)a;
         }

@@ -1,23 +1,36 @@
 // onesweep.cu — stage 2: stable least-significant-digit radix sort of the
-// (key u64, value u32) records on the 43 k-mer-code bits, onesweep style:
-//   - one histogram kernel counts the digits of every pass in a single read of
-//     the keys (shared-memory atomics, one global flush per CTA);
-//   - each pass is ONE kernel: a CTA takes a tile by ticket, ranks its keys with
-//     warp ballots (no atomics, stable), publishes its per-digit counts,
-//     resolves its global offsets by decoupled look-back over the previous
-//     tiles, reorders the tile in shared memory and writes each digit's run with
-//     coalesced stores.
+// (key u64, value u32) records, onesweep style, with the encode fused into the first pass.
+//
+//   - every pass is ONE kernel of persistent CTAs: a CTA takes a tile by ticket, ranks its keys with
+//     warp ballots (stable; one shared-memory atomic per digit group and warp), publishes its per-digit
+//     counts, reorders the tile in shared memory, resolves its global offsets by decoupled look-back
+//     over the previous tiles (by then they have usually published) and writes each digit's run with
+//     coalesced stores;
+//   - the digit counts of all passes exist before the first record does: window_count_kernel
+//     (encode.cu) takes them from the residues;
+//   - encode_sort_kernel is the window loop (window_scan.cuh) feeding that machinery directly: the
+//     records of 14 slices are compacted in shared memory in canonical order and leave the CTA already
+//     sorted on the lowest digit — the canonical-order record stream never exists in HBM;
+//   - the first pass also splits the two runs: records whose window holds a lower-case residue
+//     (mask8 != 0, a fraction of a per cent) go, in input order, to a side bin behind the main
+//     records.  The main run is then sorted on its 35 code bits (3 more passes), the side run on
+//     all 43 bits (its own histogram + 5 passes over a tiny array).
 //
 // This replaces the grouping the reference gets from hashing every occurrence
 // into tbb::concurrent_unordered_multimap (src/signature_build.tcc:178) and
 // walking the buckets (:186-208): after the last pass equal k-mers are adjacent
 // and, because every pass is stable, still in insertion order.
 //
-// HBM traffic per record: 8 B (histogram) + 24 B per pass (12 read + 12 written).
+// HBM traffic per record: fused first pass 1 B read + 12 B written; 24 B per later pass.
 #include "kernels.h"
 #include "sigk_common.cuh"
+#include "window_scan.cuh"
+
+#include <algorithm>
 
 namespace sigk {
+
+static_assert(SORT_RADIX_BITS == SIGK_RADIX_BITS && SORT_BINS == SIGK_BINS, "kernels.h and sigk_common.cuh agree");
 
 PassPlan make_pass_plan(int bit_lo, int bit_hi) {
     PassPlan p{};
@@ -39,9 +52,23 @@ PassPlan make_pass_plan(int bit_lo, int bit_hi) {
 namespace {
 
 constexpr int OS_WARPS = OS_THREADS / 32;
-constexpr int OS_DPT = (SIGK_RADIX + OS_THREADS - 1) / OS_THREADS;   // digits one thread owns in the scan / look-back
-static_assert(OS_DPT * OS_THREADS >= SIGK_RADIX, "every digit has an owner");
+constexpr int OS_DPT = (SIGK_RADIX + OS_THREADS - 1) / OS_THREADS;      // digits one thread owns in the scan / look-back
+static_assert(OS_DPT == 1 || OS_DPT == 2, "a thread owns one 16-bit counter per warp, or one 32-bit word of two");
+static_assert(OS_THREADS >= 256, "the first 256 threads fill the symbol table");
 static_assert(OS_TILE < 65536, "tile slots are kept in 16 bits");
+constexpr uint32_t PAD_BIN = SIGK_SIDE_BIN + 1;      // rows of a short tile that hold no record
+constexpr uint64_t PAD_KEY = ~0ull;                  // never a record: the low five key bits are zero
+
+// tuning knobs (tools/sweep_variants.sh builds and times the alternatives)
+#ifndef SIGK_OS_LATE_LOOKBACK
+#define SIGK_OS_LATE_LOOKBACK 0                      // 1: resolve the look-back after the shared-memory reorder instead of before it
+#endif
+#ifndef SIGK_OS_BACKOFF_NS
+#define SIGK_OS_BACKOFF_NS 0                         // __nanosleep between polls of a look-back word that is not ready
+#endif
+#ifndef SIGK_OS_PERSISTENT
+#define SIGK_OS_PERSISTENT 1                         // 1: a resident grid loops over tickets; 0: one CTA per tile
+#endif
 
 // look-back word: flag in the two top bits, value below
 template <typename LB> struct LBTraits;
@@ -58,174 +85,394 @@ template <> struct LBTraits<uint64_t> {
     static SIGK_D void st(uint64_t *p, uint64_t v) { st_volatile_u64(p, v); }
 };
 
+// SLOTS: records the key / value staging holds (the fused kernel pads its canonical-order staging)
+template <int SLOTS>
 struct OsSmem {
-    uint64_t keys[OS_TILE];
-    uint32_t vals[OS_TILE];
-    uint64_t goff[SIGK_RADIX];              // global position of sorted slot 0 of each digit, minus its tile base
-    // per-warp digit counters; after the scan: tile slot of the warp's first record of each digit
-    uint16_t cnt[OS_WARPS][SIGK_RADIX];
+    uint64_t keys[SLOTS];
+    uint32_t vals[SLOTS];
+    uint32_t goff[SIGK_BINS];               // global position of sorted slot 0 of each digit, minus its tile base (mod 2^32)
+    // per-warp digit counters, two 16-bit counters to a word; after the scan: tile slot of the warp's first record of each digit
+    uint32_t cnt[OS_WARPS][SIGK_BINS / 2];
     uint32_t scan[OS_WARPS + 2];
+    uint32_t wtotal[OS_WARPS];
     uint32_t tile;
-    uint64_t split[SORT_MAX_SPLIT];         // SPLIT mode: first k-mer code of ranks 1..n_split
+    int8_t sym[256];
 };
+using PassSmem = OsSmem<OS_TILE>;
+static_assert(ES_TILE == ES_WARPS * WS_SUB, "a fused tile is a whole number of slices");
+static_assert(ES_WARPS <= OS_WARPS, "one encoding warp per slice");
+constexpr int ES_STAGE = ES_TILE + ES_TILE / 16;
+using FusedSmem = OsSmem<ES_STAGE>;
+SIGK_D uint32_t stage_slot(uint32_t o) { return o + (o >> 4); }
 
-// The "digit" of a record: a bit field of the key, or (SPLIT, the multi-GPU partition pass)
-// the rank that owns the record's k-mer range = number of splitter codes <= its code.
-template <bool SPLIT>
-SIGK_D uint32_t digit_of(uint64_t key, int bit_lo, uint32_t digit_mask, const uint64_t *split) {
-    if (!SPLIT) return (uint32_t)(key >> bit_lo) & digit_mask;
-    const uint64_t code = sigk_key_code(key);
-    uint32_t d = 0;
-    for (uint32_t k = 0; k < digit_mask; ++k) d += code >= split[k] ? 1u : 0u;   // digit_mask = n_split
+// The digit of a record.  FIRST (the pass that also splits the runs): side records and padding get bins of their own.
+template <bool FIRST>
+SIGK_D uint32_t digit_of(uint64_t key, int bit_lo, uint32_t digit_mask) {
+    uint32_t d = (uint32_t)(key >> bit_lo) & digit_mask;
+    if (FIRST) {
+        if (sigk_key_mask(key)) d = SIGK_SIDE_BIN;
+        if (key == PAD_KEY) d = PAD_BIN;
+    }
     return d;
 }
 
-template <typename LB, bool SPLIT>
-__global__ void __launch_bounds__(OS_THREADS, OS_MIN_BLOCKS)
-onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-                     uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
-                     const uint64_t *__restrict__ n_ptr, int bit_lo, uint32_t digit_mask,
-                     const uint64_t *__restrict__ bin_base, LB *__restrict__ lookback, uint32_t *__restrict__ ticket,
-                     const uint64_t *__restrict__ split_codes) {
+// peers &= lanes whose digit has the same bit: ballot, a per-lane all-ones / all-zeros word from the bit, one
+// three-input logic op — three instructions per digit bit plus one R2P per seven bits (the C form
+// `peers &= bit ? m : ~m` compiled to seven per bit)
+SIGK_D void peers_step(unsigned &peers, uint32_t d, uint32_t bit_mask) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 m, x;\n\t"
+                 "and.b32 m, %1, %2;\n\t"
+                 "setp.ne.u32 p, m, 0;\n\t"
+                 "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
+                 "selp.b32 x, 0, 0xffffffff, p;\n\t"
+                 "lop3.b32 %0, %0, m, x, 0x60;\n\t}"                  // peers & (m ^ x)
+                 : "+r"(peers) : "r"(d), "r"(bit_mask) : "memory");
+}
+
+template <typename SM>
+SIGK_D void os_zero_counters(SM &sm) {
+    uint32_t *c32 = &sm.cnt[0][0];
+    for (uint32_t j = threadIdx.x; j < OS_WARPS * (SIGK_BINS / 2); j += OS_THREADS) c32[j] = 0;
+}
+
+// Everything after the keys of a tile sit in registers (warp-striped: item i of lane l of warp w is tile record
+// w * 32 ITEMS + 32 i + l; rows past tile_n hold PAD_KEY): rank, publish, reorder, look back, write out.
+// The counters must be zero and visible (a barrier after os_zero_counters).
+// val_at(r) = value of tile record r.  VALS_STAGED: val_at reads the staging that the sorted values are about to
+// overwrite (fused kernel), so everybody reads before anybody writes.
+template <typename LB, bool FIRST, bool VALS_STAGED, int ITEMS, typename SM, typename ValFn>
+SIGK_D void os_sort_tile(SM &sm, uint64_t (&key)[ITEMS], uint32_t tile, uint32_t tile_n, int bit_lo, uint32_t digit_mask,
+                         const uint64_t *__restrict__ bin_base, LB *__restrict__ lookback, ValFn &&val_at,
+                         uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out) {
     using T = LBTraits<LB>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    OsSmem &sm = *reinterpret_cast<OsSmem *>(smem_raw);
-
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint64_t n = *n_ptr;
-    if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
-    if (SPLIT && tid < digit_mask) sm.split[tid] = split_codes[tid];
-    // zero the warp counters (as 32-bit words)
-    {
-        uint32_t *c32 = reinterpret_cast<uint32_t *>(&sm.cnt[0][0]);
-        for (uint32_t j = tid; j < OS_WARPS * SIGK_RADIX / 2; j += OS_THREADS) c32[j] = 0;
-    }
-    __syncthreads();
-    const uint32_t tile = sm.tile;
-    const uint64_t tile_start = (uint64_t)tile * OS_TILE;
-    if (tile_start >= n) return;
-    const uint32_t tile_n = (uint32_t)((n - tile_start) < (uint64_t)OS_TILE ? (n - tile_start) : (uint64_t)OS_TILE);
+    const unsigned lt = (1u << lane) - 1u;
+    uint16_t *wcnt16 = reinterpret_cast<uint16_t *>(sm.cnt[warp]);
+    constexpr int NBITS = FIRST ? SIGK_RADIX_BITS + 1 : SIGK_RADIX_BITS;
 
-    // ---- load keys, warp-striped: item i of lane l is record wbase + 32 i + l.
-    // Padding of the last tile gets key ~0: it ranks after every real record of
-    // the top digit and is never written.
-    const uint32_t wbase = warp * (OS_ITEMS * 32);
-    uint64_t key[OS_ITEMS];
+    // ---- rank inside the warp: lanes with my digit are found with one ballot per digit bit (MATCH.ANY runs on
+    // the ADU pipe at ~64 cycles per warp instruction: 70 % pipe utilisation in the round-1 v1 profile); the
+    // group's first lane bumps the warp's counter with one shared-memory atomic whose return value is the
+    // group's base; everyone takes base + (peers below me).  Stable.  The atomics of a chunk of items are
+    // issued back to back so that their latencies overlap.
+    uint32_t rank2[(ITEMS + 1) / 2];                    // two 16-bit ranks (later: tile slots) to a register
 #pragma unroll
-    for (int i = 0; i < OS_ITEMS; ++i) {
-        const uint32_t idx = wbase + i * 32 + lane;
-        key[i] = idx < tile_n ? ld_stream_u64(keys_in + tile_start + idx) : ~0ull;
-    }
-
-    // ---- rank inside the warp: lanes with my digit are found with one ballot per digit
-    // bit (MATCH.ANY runs on the ADU pipe at ~64 cycles per warp instruction: 70 % pipe
-    // utilisation in the round-1 v1 profile); the group's first lane bumps the warp's counter,
-    // everyone takes counter + (peers below me).  No atomics, stable.
-    uint16_t *wcnt = sm.cnt[warp];
-    uint16_t rank[OS_ITEMS];
+    for (int i = 0; i < (ITEMS + 1) / 2; ++i) rank2[i] = 0;
+#define SIGK_RANK_GET(i) ((rank2[(i) >> 1] >> (16 * ((i) & 1))) & 0xFFFFu)
+#define SIGK_RANK_SET(i, v) rank2[(i) >> 1] = ((i) & 1) ? ((rank2[(i) >> 1] & 0xFFFFu) | ((uint32_t)(v) << 16)) : ((rank2[(i) >> 1] & 0xFFFF0000u) | (uint32_t)(v))
 #pragma unroll
-    for (int i = 0; i < OS_ITEMS; ++i) {
-        const uint32_t d = digit_of<SPLIT>(key[i], bit_lo, digit_mask, sm.split);
+    for (int i = 0; i < ITEMS; ++i) {
+        const uint32_t d = digit_of<FIRST>(key[i], bit_lo, digit_mask);
         unsigned peers = 0xffffffffu;
 #pragma unroll
-        for (int b = 0; b < SIGK_RADIX_BITS; ++b) {
-            const bool bit = (d >> b) & 1u;
-            const unsigned m = __ballot_sync(0xffffffffu, bit);
-            peers &= bit ? m : ~m;
-        }
-        const int leader = __ffs(peers) - 1;
-        uint32_t old = 0;
-        if ((int)lane == leader) { old = wcnt[d]; wcnt[d] = (uint16_t)(old + __popc(peers)); }
-        old = __shfl_sync(0xffffffffu, old, leader);
-        rank[i] = (uint16_t)(old + __popc(peers & ((1u << lane) - 1u)));
-        __syncwarp();
+        for (int b = 0; b < NBITS; ++b) peers_step(peers, d, 1u << b);
+        // every lane of the group reads the warp's counter (a broadcast); the group's first lane moves it on
+        const uint32_t below = (uint32_t)__popc(peers & lt);
+        const uint32_t old = wcnt16[d];
+        if (below == 0) wcnt16[d] = (uint16_t)(old + (uint32_t)__popc(peers));
+        SIGK_RANK_SET(i, old + below);
+        __syncwarp();                                   // the next item's readers see this store
     }
     __syncthreads();
 
-    // ---- per digit: exclusive prefix over warps, tile count, publish, look back.
-    // Thread t owns digits t*DPT .. t*DPT+DPT-1.
+    // ---- per digit: exclusive prefix over warps, tile count, publish.  Thread t owns the OS_DPT digits
+    // t * OS_DPT ..: one 16-bit counter per warp with 512 threads, one 32-bit word of two with 256.  In a FIRST
+    // pass thread 0 also owns the side bin and the padding bin (which is never published).
+    const bool owner = tid * OS_DPT < SIGK_RADIX;
     uint32_t my_count[OS_DPT], my_sum = 0;
 #pragma unroll
-    for (int k = 0; k < OS_DPT; ++k) {
-        const uint32_t d = tid * OS_DPT + k;
-        uint32_t sum = 0;
-        if (d < SIGK_RADIX) {
+    for (int k = 0; k < OS_DPT; ++k) my_count[k] = 0;
+    if (owner) {
 #pragma unroll
-            for (int w = 0; w < OS_WARPS; ++w) sum += sm.cnt[w][d];
-            T::st(lookback + (size_t)tile * SIGK_RADIX + d, (tile == 0 ? T::PRE : T::AGG) | (LB)sum);
+        for (int w = 0; w < OS_WARPS; ++w) {
+            if (OS_DPT == 1) my_count[0] += reinterpret_cast<const uint16_t *>(sm.cnt[w])[tid];
+            else { const uint32_t c = sm.cnt[w][tid]; my_count[0] += c & 0xFFFFu; my_count[OS_DPT - 1] += c >> 16; }
         }
-        my_count[k] = sum;
-        my_sum += sum;
-    }
-    uint32_t total;
-    uint32_t dbase = block_exclusive_scan<OS_THREADS>(my_sum, sm.scan, &total);
 #pragma unroll
-    for (int k = 0; k < OS_DPT; ++k) {
-        const uint32_t d = tid * OS_DPT + k;
-        if (d < SIGK_RADIX) {
-            // fold the digit's tile base into the per-warp prefixes: slot = cnt[warp][d] + rank
-            uint32_t run = dbase;
+        for (int k = 0; k < OS_DPT; ++k) {
+            T::st(lookback + (size_t)tile * SIGK_BINS + tid * OS_DPT + k, (tile == 0 ? T::PRE : T::AGG) | (LB)my_count[k]);
+            my_sum += my_count[k];
+        }
+    }
+    uint32_t side_count = 0;
+    if (FIRST && tid == 0) {
+#pragma unroll
+        for (int w = 0; w < OS_WARPS; ++w) side_count += reinterpret_cast<const uint16_t *>(sm.cnt[w])[SIGK_SIDE_BIN];
+        T::st(lookback + (size_t)tile * SIGK_BINS + SIGK_SIDE_BIN, (tile == 0 ? T::PRE : T::AGG) | (LB)side_count);
+    }
+    uint32_t total_main;
+    const uint32_t dbase = block_exclusive_scan<OS_THREADS>(my_sum, sm.scan, &total_main);
+    if (owner) {
+        // fold the digit's tile base into the per-warp prefixes: slot = cnt[warp][d] + rank
+        uint32_t run0 = dbase, run1 = dbase + my_count[0];
+#pragma unroll
+        for (int w = 0; w < OS_WARPS; ++w) {
+            if (OS_DPT == 1) {
+                uint16_t *c = reinterpret_cast<uint16_t *>(sm.cnt[w]) + tid;
+                const uint32_t x = *c;
+                *c = (uint16_t)run0;
+                run0 += x;
+            } else {
+                const uint32_t c = sm.cnt[w][tid];
+                sm.cnt[w][tid] = run0 | (run1 << 16);
+                run0 += c & 0xFFFFu;
+                run1 += c >> 16;
+            }
+        }
+    }
+    if (FIRST && tid == 0) {
+        uint32_t run = total_main;                      // side records sit behind every main digit, padding behind them
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
 #pragma unroll
             for (int w = 0; w < OS_WARPS; ++w) {
-                const uint32_t c = sm.cnt[w][d];
-                sm.cnt[w][d] = (uint16_t)run;
-                run += c;
+                uint16_t *c = reinterpret_cast<uint16_t *>(sm.cnt[w]) + SIGK_SIDE_BIN + b;
+                const uint32_t x = *c;
+                *c = (uint16_t)run;
+                run += x;
             }
-            LB excl = 0;
-            if (tile > 0) {
-                int64_t t = (int64_t)tile - 1;
-                for (;;) {
-                    const LB v = T::ld(lookback + (size_t)t * SIGK_RADIX + d);
-                    const LB flag = v >> T::SHIFT;
-                    if (flag == 0) continue;
-                    excl += v & T::VAL;
-                    if (flag == 2) break;
-                    --t;
-                }
-                T::st(lookback + (size_t)tile * SIGK_RADIX + d, T::PRE | (excl + (LB)my_count[k]));
-            }
-            sm.goff[d] = bin_base[d] + (uint64_t)excl - (uint64_t)dbase;
         }
-        dbase += my_count[k];
     }
+    // ---- look back over the tiles before this one: per digit, add aggregates until an inclusive prefix turns up
+    auto look_back_digit = [&](uint32_t d, uint32_t cnt, uint32_t base) {
+        LB excl = 0;
+        if (tile > 0) {
+            int64_t t = (int64_t)tile - 1;
+            for (;;) {
+                const LB v = T::ld(lookback + (size_t)t * SIGK_BINS + d);
+                const LB flag = v >> T::SHIFT;
+                if (flag == 0) { if (SIGK_OS_BACKOFF_NS) __nanosleep(SIGK_OS_BACKOFF_NS); continue; }
+                excl += v & T::VAL;
+                if (flag == 2) break;
+                --t;
+            }
+            T::st(lookback + (size_t)tile * SIGK_BINS + d, T::PRE | (excl + (LB)cnt));
+        }
+        sm.goff[d] = (uint32_t)(bin_base[d] + (uint64_t)excl) - base;
+    };
+    auto look_back = [&]() {
+        if (owner) {
+            uint32_t base = dbase;
+#pragma unroll
+            for (int k = 0; k < OS_DPT; ++k) { look_back_digit(tid * OS_DPT + k, my_count[k], base); base += my_count[k]; }
+        }
+        if (FIRST && tid == 0) look_back_digit(SIGK_SIDE_BIN, side_count, total_main);
+    };
+    if (!SIGK_OS_LATE_LOOKBACK) look_back();
     __syncthreads();
 
     // ---- reorder the tile in shared memory (keys, then values by the same slots)
 #pragma unroll
-    for (int i = 0; i < OS_ITEMS; ++i) {
-        const uint32_t d = digit_of<SPLIT>(key[i], bit_lo, digit_mask, sm.split);
-        const uint32_t slot = (uint32_t)wcnt[d] + rank[i];
-        rank[i] = (uint16_t)slot;
-        sm.keys[slot] = key[i];
+    for (int i = 0; i < ITEMS; ++i) {
+        const uint32_t d = digit_of<FIRST>(key[i], bit_lo, digit_mask);
+        const uint32_t slot = (uint32_t)wcnt16[d] + SIGK_RANK_GET(i);
+        SIGK_RANK_SET(i, slot);
     }
+    const uint32_t wbase = warp * (ITEMS * 32);
+    // (every key of the tile has been in registers since before the first barrier: the key staging is free)
 #pragma unroll
-    for (int i = 0; i < OS_ITEMS; ++i) {
-        const uint32_t idx = wbase + i * 32 + lane;
-        const uint32_t v = idx < tile_n ? ld_stream_u32(vals_in + tile_start + idx) : 0u;
-        sm.vals[rank[i]] = v;
+    for (int i = 0; i < ITEMS; ++i) sm.keys[SIGK_RANK_GET(i)] = key[i];
+    if (VALS_STAGED) {
+        // the staged values share sm.vals with the sorted ones: everybody reads before anybody writes
+        uint32_t v[ITEMS];
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t idx = wbase + i * 32 + lane;
+            v[i] = idx < tile_n ? val_at(idx) : 0u;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) sm.vals[SIGK_RANK_GET(i)] = v[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t idx = wbase + i * 32 + lane;
+            const uint32_t v = idx < tile_n ? val_at(idx) : 0u;
+            sm.vals[SIGK_RANK_GET(i)] = v;
+        }
     }
+
+    if (SIGK_OS_LATE_LOOKBACK) look_back();
     __syncthreads();
 
     // ---- coalesced write-out: consecutive slots of one digit are consecutive in HBM
     for (uint32_t j = tid; j < tile_n; j += OS_THREADS) {
         const uint64_t k = sm.keys[j];
-        const uint32_t d = digit_of<SPLIT>(k, bit_lo, digit_mask, sm.split);
-        const uint64_t pos = sm.goff[d] + j;
+        const uint32_t d = digit_of<FIRST>(k, bit_lo, digit_mask);
+        const uint32_t pos = sm.goff[d] + j;
         keys_out[pos] = k;
         vals_out[pos] = sm.vals[j];
     }
 }
 
+// L2 prefetch of a tile that a CTA of the next wave will take: cp.async.bulk.prefetch (the TMA unit pulls the lines
+// into L2; nothing lands in shared memory, so it costs no staging space)
+SIGK_D void prefetch_l2(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+#ifndef SIGK_OS_PREFETCH
+#define SIGK_OS_PREFETCH 1
+#endif
+
+template <typename LB, bool FIRST>
+__global__ void __launch_bounds__(OS_THREADS, OS_MIN_BLOCKS)
+onesweep_pass_kernel(const __grid_constant__ SortSegments seg, const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                     uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, const uint64_t *__restrict__ n_ptr,
+                     const uint64_t *__restrict__ off_ptr, int bit_lo, uint32_t digit_mask, const uint64_t *__restrict__ bin_base,
+                     LB *__restrict__ lookback, uint32_t *__restrict__ ticket) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PassSmem &sm = *reinterpret_cast<PassSmem *>(smem_raw);
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint64_t n = FIRST ? (n_ptr ? *n_ptr : seg.start[seg.n]) : *n_ptr;
+    const uint64_t off = (!FIRST && off_ptr) ? *off_ptr : 0ull;      // the run's place in the in / out buffers
+    const uint32_t wbase = warp * (OS_ITEMS * 32);
+    for (;;) {
+        __syncthreads();                                    // the previous tile's write-out is done with the staging
+        if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+        os_zero_counters(sm);
+        __syncthreads();
+        const uint32_t tile = sm.tile;
+        const uint64_t tile_start = (uint64_t)tile * OS_TILE;
+        if (tile_start >= n) return;
+        const uint32_t tile_n = (uint32_t)((n - tile_start) < (uint64_t)OS_TILE ? (n - tile_start) : (uint64_t)OS_TILE);
+
+        // ---- load keys, warp-striped: item i of lane l is record wbase + 32 i + l.
+        uint64_t key[OS_ITEMS];
+        if (!FIRST) {
+#if SIGK_OS_PREFETCH
+            if (tid == 0) {
+                // the tile one wave ahead (gridDim.x CTAs are resident)
+                const uint64_t ahead = tile_start + (uint64_t)gridDim.x * OS_TILE;
+                if (ahead + OS_TILE <= n && (((uintptr_t)(keys_in + off + ahead) | (uintptr_t)(vals_in + off + ahead)) & 15u) == 0) {
+                    prefetch_l2(keys_in + off + ahead, OS_TILE * sizeof(uint64_t));
+                    prefetch_l2(vals_in + off + ahead, OS_TILE * sizeof(uint32_t));
+                }
+            }
+#endif
+            // Padding of the last tile gets key ~0: it ranks after every real record of the top digit and is never written.
+#pragma unroll
+            for (int i = 0; i < OS_ITEMS; ++i) {
+                const uint32_t idx = wbase + i * 32 + lane;
+                key[i] = idx < tile_n ? ld_stream_u64(keys_in + off + tile_start + idx) : PAD_KEY;
+            }
+            os_sort_tile<LB, false, false, OS_ITEMS>(sm, key, tile, tile_n, bit_lo, digit_mask, bin_base, lookback,
+                                                     [&](uint32_t r) { return ld_stream_u32(vals_in + off + tile_start + r); },
+                                                     keys_out + off, vals_out + off);
+        } else {
+            // the regions of the first pass, read in place: region s holds records start[s] .. start[s+1]
+            int s0 = 0;
+            while (s0 + 1 < seg.n && tile_start >= seg.start[s0 + 1]) ++s0;
+            // does the whole tile lie in region s0?  (all but at most one tile per region boundary)
+            const bool one = seg.n <= 1 || tile_start + tile_n <= seg.start[s0 + 1];
+            const uint64_t r0 = tile_start - seg.start[s0];
+            auto region_of = [&](uint64_t g) {
+                int r = s0;
+                while (r + 1 < seg.n && g >= seg.start[r + 1]) ++r;
+                return r;
+            };
+#pragma unroll
+            for (int i = 0; i < OS_ITEMS; ++i) {
+                const uint32_t idx = wbase + i * 32 + lane;
+                if (idx >= tile_n) key[i] = PAD_KEY;
+                else if (one) key[i] = ld_stream_u64(seg.keys[s0] + r0 + idx);
+                else { const uint64_t g = tile_start + idx; const int r = region_of(g); key[i] = ld_stream_u64(seg.keys[r] + (g - seg.start[r])); }
+            }
+            os_sort_tile<LB, true, false, OS_ITEMS>(sm, key, tile, tile_n, bit_lo, digit_mask, bin_base, lookback,
+                                                    [&](uint32_t idx) {
+                                                        if (one) return ld_stream_u32(seg.vals[s0] + r0 + idx);
+                                                        const uint64_t g = tile_start + idx;
+                                                        const int r = region_of(g);
+                                                        return ld_stream_u32(seg.vals[r] + (g - seg.start[r]));
+                                                    }, keys_out, vals_out);
+        }
+    }
+}
+
+// ---- encode fused with the first pass -------------------------------------------------------------------
+// A tile is ES_WARPS slices of 512 window positions.  Warps 0..ES_WARPS-1 run the window loop (window_scan.cuh)
+// and compact the valid windows of the tile into the staging in canonical order; then all warps read the staging
+// warp-striped and the tile goes through os_sort_tile like any other: main records to their lowest digit's run,
+// records with a lower-case residue to the side bin.
+template <typename LB>
+__global__ void __launch_bounds__(OS_THREADS, OS_MIN_BLOCKS)
+encode_sort_kernel(EncodeArgs a, uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int bit_lo, uint32_t digit_mask,
+                   const uint64_t *__restrict__ bin_base, LB *__restrict__ lookback, uint32_t *__restrict__ ticket, uint32_t n_tiles) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FusedSmem &sm = *reinterpret_cast<FusedSmem *>(smem_raw);
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    ws_fill_symbols(sm.sym);
+    const uint32_t wbase = warp * (ES_ITEMS * 32);
+    for (;;) {
+        __syncthreads();                                    // the previous tile's write-out is done with the staging
+        if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+        os_zero_counters(sm);
+        __syncthreads();
+        const uint32_t tile = sm.tile;
+        if (tile >= n_tiles) return;
+
+        // ---- window loop, part 1: which windows are valid, how many per slice
+        const uint32_t sub = tile * ES_WARPS + warp;
+        const bool enc = warp < ES_WARPS && (uint64_t)sub * WS_SUB < a.total_res;
+        WindowLane w;
+        uint32_t valid = 0, incl = 0, mine = 0;
+        if (enc) {
+            ws_load(a, sm.sym, sub, w);
+            valid = ws_valid_mask(a, w);
+            mine = incl = (uint32_t)__popc(valid);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (unsigned)o) incl += y;
+            }
+        }
+        if (lane == 31) sm.wtotal[warp] = incl;             // 0 for warps without a slice
+        __syncthreads();
+        uint32_t before = 0, tile_n = 0;
+#pragma unroll
+        for (int q = 0; q < ES_WARPS; ++q) {
+            const uint32_t c = sm.wtotal[q];
+            before += q < (int)warp ? c : 0u;
+            tile_n += c;
+        }
+        // ---- part 2: the records, compacted in canonical order (one pad slot per 16: lanes write runs of ~16)
+        if (enc) {
+            uint32_t o = before + incl - mine;
+            ws_for_each(a, w, valid, [&](int, uint64_t key, uint32_t i) {
+                const uint32_t slot = stage_slot(o++);
+                sm.keys[slot] = key;
+                sm.vals[slot] = a.ordinal_base + i;
+            });
+        }
+        __syncthreads();
+        uint64_t key[ES_ITEMS];
+#pragma unroll
+        for (int i = 0; i < ES_ITEMS; ++i) {
+            const uint32_t idx = wbase + i * 32 + lane;
+            key[i] = idx < tile_n ? sm.keys[stage_slot(idx)] : PAD_KEY;
+        }
+        os_sort_tile<LB, true, true, ES_ITEMS>(sm, key, tile, tile_n, bit_lo, digit_mask, bin_base, lookback,
+                                               [&](uint32_t idx) { return sm.vals[stage_slot(idx)]; }, keys_out, vals_out);
+    }
+}
+
+// ---- histograms of already encoded records ------------------------------------------------------------------
 constexpr int HIST_THREADS = 512;
 constexpr int HIST_UNROLL = 4;
 
+// MAIN: the input of a first pass (regions read in place); records with mask8 != 0 only bump the side bin of row 0.
+template <bool MAIN>
 __global__ void __launch_bounds__(HIST_THREADS)
-histogram_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ n_ptr, PassPlan plan,
-                 uint64_t *__restrict__ hist) {
+histogram_kernel(const __grid_constant__ SortSegments seg, const uint64_t *__restrict__ keys, const uint64_t *__restrict__ n_ptr,
+                 const uint64_t *__restrict__ off_ptr, PassPlan plan, uint64_t *__restrict__ hist) {
     __shared__ uint32_t sh[SORT_MAX_PASSES * SIGK_RADIX];
+    __shared__ uint32_t s_side;
     for (int j = threadIdx.x; j < plan.npass * SIGK_RADIX; j += HIST_THREADS) sh[j] = 0;
+    if (threadIdx.x == 0) s_side = 0;
     __syncthreads();
-    const uint64_t n = *n_ptr;
+    const uint64_t n = MAIN ? (n_ptr ? *n_ptr : seg.start[seg.n]) : *n_ptr;
+    if (!MAIN && off_ptr) keys += *off_ptr;
+    uint32_t side = 0;
     const uint64_t stride = (uint64_t)gridDim.x * HIST_THREADS * HIST_UNROLL;
     for (uint64_t base = (uint64_t)blockIdx.x * HIST_THREADS * HIST_UNROLL; base < n; base += stride) {
         uint64_t k[HIST_UNROLL];
@@ -234,92 +481,163 @@ histogram_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__
         for (int u = 0; u < HIST_UNROLL; ++u) {
             const uint64_t idx = base + (uint64_t)u * HIST_THREADS + threadIdx.x;
             ok[u] = idx < n;
-            k[u] = ok[u] ? ld_stream_u64(keys + idx) : 0;
+            k[u] = 0;
+            if (ok[u]) {
+                if (MAIN) {
+                    int r = 0;
+                    while (r + 1 < seg.n && idx >= seg.start[r + 1]) ++r;
+                    k[u] = ld_stream_u64(seg.keys[r] + (idx - seg.start[r]));
+                } else {
+                    k[u] = ld_stream_u64(keys + idx);
+                }
+            }
         }
 #pragma unroll
         for (int u = 0; u < HIST_UNROLL; ++u) {
             if (!ok[u]) continue;
+            if (MAIN && sigk_key_mask(k[u])) { ++side; continue; }
             for (int p = 0; p < plan.npass; ++p)
                 atomicAdd(&sh[p * SIGK_RADIX + ((uint32_t)(k[u] >> plan.lo[p]) & ((1u << plan.bits[p]) - 1u))], 1u);
         }
     }
+    if (MAIN) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) side += __shfl_xor_sync(0xffffffffu, side, o);
+        if ((threadIdx.x & 31u) == 0 && side) atomicAdd(&s_side, side);
+    }
     __syncthreads();
     for (int j = threadIdx.x; j < plan.npass * SIGK_RADIX; j += HIST_THREADS)
-        if (sh[j]) atomicAdd(reinterpret_cast<unsigned long long *>(hist + j), (unsigned long long)sh[j]);
+        if (sh[j]) atomicAdd(reinterpret_cast<unsigned long long *>(hist + (size_t)(j / SIGK_RADIX) * SIGK_BINS + (j % SIGK_RADIX)),
+                             (unsigned long long)sh[j]);
+    if (MAIN && threadIdx.x == 0 && s_side) atomicAdd(reinterpret_cast<unsigned long long *>(hist + SIGK_SIDE_BIN), (unsigned long long)s_side);
 }
 
-__global__ void scan_bins_kernel(const uint64_t *__restrict__ hist, uint64_t *__restrict__ bin_base) {
+// bin_base[p][d] = records of pass p with a smaller digit; row 0 continues into the side bin
+__global__ void scan_bins_kernel(const uint64_t *__restrict__ hist, uint64_t *__restrict__ bin_base, uint64_t *__restrict__ counts) {
     __shared__ uint64_t s[SIGK_RADIX];
     const int p = blockIdx.x, d = threadIdx.x;
-    s[d] = hist[p * SIGK_RADIX + d];
+    s[d] = hist[(size_t)p * SIGK_BINS + d];
     __syncthreads();
-    // 256 bins: a serial scan by one thread is a few hundred cycles
+    // 512 bins: a serial scan by one thread is a few hundred cycles
     if (d == 0) {
         uint64_t run = 0;
         for (int i = 0; i < SIGK_RADIX; ++i) { const uint64_t c = s[i]; s[i] = run; run += c; }
+        const uint64_t side = hist[(size_t)p * SIGK_BINS + SIGK_SIDE_BIN];
+        bin_base[(size_t)p * SIGK_BINS + SIGK_SIDE_BIN] = run;
+        if (p == 0 && counts) { counts[0] = run; counts[1] = side; counts[2] = run + side; }
     }
     __syncthreads();
-    bin_base[p * SIGK_RADIX + d] = s[d];
+    bin_base[(size_t)p * SIGK_BINS + d] = s[d];
+}
+
+template <typename LB>
+__global__ void clear_lookback_kernel(LB *__restrict__ lookback, const uint64_t *__restrict__ n_ptr, uint32_t tile_records) {
+    const uint64_t words = ((*n_ptr + tile_records - 1) / tile_records) * SIGK_BINS;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (uint64_t)gridDim.x * blockDim.x) lookback[i] = 0;
 }
 
 }  // namespace
 
+static bool wide_lookback(uint64_t capacity) { return capacity >= (1ull << 30); }
+
 size_t onesweep_lookback_bytes(uint64_t capacity) {
-    const size_t word = capacity >= (1ull << 30) ? 8 : 4;
-    return (size_t)onesweep_tiles(capacity) * SIGK_RADIX * word;
+    // rows for the smaller (fused) tile cover both kinds of pass
+    return (size_t)(encode_sort_tiles(capacity) + 1) * SIGK_BINS * (wide_lookback(capacity) ? 8 : 4);
 }
 
 cudaError_t onesweep_configure() {
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(onesweep_pass_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(onesweep_pass_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(onesweep_pass_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem))) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(onesweep_pass_kernel<uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem));
+#define SIGK_OPT_IN(kernel, bytes) \
+    if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))) != cudaSuccess) return e;
+    SIGK_OPT_IN((onesweep_pass_kernel<uint32_t, false>), sizeof(PassSmem))
+    SIGK_OPT_IN((onesweep_pass_kernel<uint64_t, false>), sizeof(PassSmem))
+    SIGK_OPT_IN((onesweep_pass_kernel<uint32_t, true>), sizeof(PassSmem))
+    SIGK_OPT_IN((onesweep_pass_kernel<uint64_t, true>), sizeof(PassSmem))
+    SIGK_OPT_IN(encode_sort_kernel<uint32_t>, sizeof(FusedSmem))
+    SIGK_OPT_IN(encode_sort_kernel<uint64_t>, sizeof(FusedSmem))
+#undef SIGK_OPT_IN
+    return cudaSuccess;
 }
 
-cudaError_t launch_histogram(const uint64_t *keys, const uint64_t *n_ptr, uint64_t capacity, const PassPlan &plan,
-                             uint64_t *hist, int sm_count, cudaStream_t stream) {
+static unsigned persistent_grid(uint64_t tiles, int sm_count) {
+    if (!SIGK_OS_PERSISTENT) return (unsigned)std::max<uint64_t>(1, tiles);       // every CTA finds its ticket in range once, then leaves
+    return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, (uint64_t)sm_count * OS_MIN_BLOCKS));
+}
+
+cudaError_t launch_histogram(const uint64_t *keys, const uint64_t *n_ptr, const uint64_t *off_ptr, uint64_t capacity,
+                             const PassPlan &plan, uint64_t *hist, int sm_count, cudaStream_t stream) {
     if (capacity == 0) return cudaSuccess;
     uint64_t want = (capacity + (uint64_t)HIST_THREADS * HIST_UNROLL - 1) / ((uint64_t)HIST_THREADS * HIST_UNROLL);
     const uint64_t cap = (uint64_t)sm_count * 4;
     if (want > cap) want = cap;
-    histogram_kernel<<<(unsigned)want, HIST_THREADS, 0, stream>>>(keys, n_ptr, plan, hist);
+    histogram_kernel<false><<<(unsigned)want, HIST_THREADS, 0, stream>>>(SortSegments{}, keys, n_ptr, off_ptr, plan, hist);
     return cudaGetLastError();
 }
 
-cudaError_t launch_scan_bins(const uint64_t *hist, uint64_t *bin_base, int npass, cudaStream_t stream) {
-    scan_bins_kernel<<<npass, SIGK_RADIX, 0, stream>>>(hist, bin_base);
+cudaError_t launch_histogram_main(const SortSegments &seg, const uint64_t *n_ptr, const PassPlan &plan, uint64_t *hist,
+                                  int sm_count, cudaStream_t stream) {
+    if (seg.n < 1 || seg.n > SORT_MAX_SEGMENTS) return cudaErrorInvalidValue;
+    histogram_kernel<true><<<(unsigned)sm_count * 4, HIST_THREADS, 0, stream>>>(seg, nullptr, n_ptr, nullptr, plan, hist);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan_bins(const uint64_t *hist, uint64_t *bin_base, int npass, uint64_t *counts, cudaStream_t stream) {
+    scan_bins_kernel<<<npass, SIGK_RADIX, 0, stream>>>(hist, bin_base, counts);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_clear_lookback(void *lookback, const uint64_t *n_ptr, uint64_t capacity, cudaStream_t stream) {
+    if (capacity == 0) return cudaSuccess;
+    const uint64_t words = onesweep_tiles(capacity) * SIGK_BINS;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((words + 255) / 256, 1184));
+    if (wide_lookback(capacity)) clear_lookback_kernel<uint64_t><<<grid, 256, 0, stream>>>((uint64_t *)lookback, n_ptr, (uint32_t)OS_TILE);
+    else clear_lookback_kernel<uint32_t><<<grid, 256, 0, stream>>>((uint32_t *)lookback, n_ptr, (uint32_t)OS_TILE);
     return cudaGetLastError();
 }
 
 cudaError_t launch_onesweep_pass(const uint64_t *keys_in, const uint32_t *vals_in, uint64_t *keys_out,
-                                 uint32_t *vals_out, const uint64_t *n_ptr, uint64_t capacity, int bit_lo, int nbits,
-                                 const uint64_t *bin_base, void *lookback, uint32_t *ticket, cudaStream_t stream) {
+                                 uint32_t *vals_out, const uint64_t *n_ptr, const uint64_t *off_ptr, uint64_t capacity, int bit_lo, int nbits,
+                                 const uint64_t *bin_base, void *lookback, uint32_t *ticket, int sm_count, cudaStream_t stream) {
     if (capacity == 0) return cudaSuccess;
-    const unsigned tiles = (unsigned)onesweep_tiles(capacity);
+    const unsigned grid = persistent_grid(onesweep_tiles(capacity), sm_count);
     const uint32_t mask = (1u << nbits) - 1u;
-    if (capacity >= (1ull << 30))
-        onesweep_pass_kernel<uint64_t, false><<<tiles, OS_THREADS, sizeof(OsSmem), stream>>>(
-            keys_in, vals_in, keys_out, vals_out, n_ptr, bit_lo, mask, bin_base, (uint64_t *)lookback, ticket, nullptr);
+    if (wide_lookback(capacity))
+        onesweep_pass_kernel<uint64_t, false><<<grid, OS_THREADS, sizeof(PassSmem), stream>>>(
+            SortSegments{}, keys_in, vals_in, keys_out, vals_out, n_ptr, off_ptr, bit_lo, mask, bin_base, (uint64_t *)lookback, ticket);
     else
-        onesweep_pass_kernel<uint32_t, false><<<tiles, OS_THREADS, sizeof(OsSmem), stream>>>(
-            keys_in, vals_in, keys_out, vals_out, n_ptr, bit_lo, mask, bin_base, (uint32_t *)lookback, ticket, nullptr);
+        onesweep_pass_kernel<uint32_t, false><<<grid, OS_THREADS, sizeof(PassSmem), stream>>>(
+            SortSegments{}, keys_in, vals_in, keys_out, vals_out, n_ptr, off_ptr, bit_lo, mask, bin_base, (uint32_t *)lookback, ticket);
     return cudaGetLastError();
 }
 
-cudaError_t launch_onesweep_partition(const uint64_t *keys_in, const uint32_t *vals_in, uint64_t *keys_out,
-                                      uint32_t *vals_out, const uint64_t *n_ptr, uint64_t capacity,
-                                      const uint64_t *split_codes, int n_split, const uint64_t *bin_base, void *lookback,
-                                      uint32_t *ticket, cudaStream_t stream) {
+cudaError_t launch_onesweep_first_pass(const SortSegments &seg, const uint64_t *n_ptr, uint64_t *keys_out, uint32_t *vals_out,
+                                       uint64_t capacity, int bit_lo, int nbits, const uint64_t *bin_base, void *lookback,
+                                       uint32_t *ticket, int sm_count, cudaStream_t stream) {
     if (capacity == 0) return cudaSuccess;
-    if (n_split < 1 || n_split > SORT_MAX_SPLIT) return cudaErrorInvalidValue;
-    const unsigned tiles = (unsigned)onesweep_tiles(capacity);
-    if (capacity >= (1ull << 30))
-        onesweep_pass_kernel<uint64_t, true><<<tiles, OS_THREADS, sizeof(OsSmem), stream>>>(
-            keys_in, vals_in, keys_out, vals_out, n_ptr, 0, (uint32_t)n_split, bin_base, (uint64_t *)lookback, ticket, split_codes);
+    if (seg.n < 1 || seg.n > SORT_MAX_SEGMENTS) return cudaErrorInvalidValue;
+    const unsigned grid = persistent_grid(onesweep_tiles(capacity), sm_count);
+    const uint32_t mask = (1u << nbits) - 1u;
+    if (wide_lookback(capacity))
+        onesweep_pass_kernel<uint64_t, true><<<grid, OS_THREADS, sizeof(PassSmem), stream>>>(
+            seg, nullptr, nullptr, keys_out, vals_out, n_ptr, nullptr, bit_lo, mask, bin_base, (uint64_t *)lookback, ticket);
     else
-        onesweep_pass_kernel<uint32_t, true><<<tiles, OS_THREADS, sizeof(OsSmem), stream>>>(
-            keys_in, vals_in, keys_out, vals_out, n_ptr, 0, (uint32_t)n_split, bin_base, (uint32_t *)lookback, ticket, split_codes);
+        onesweep_pass_kernel<uint32_t, true><<<grid, OS_THREADS, sizeof(PassSmem), stream>>>(
+            seg, nullptr, nullptr, keys_out, vals_out, n_ptr, nullptr, bit_lo, mask, bin_base, (uint32_t *)lookback, ticket);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_encode_sort(const EncodeArgs &a, uint64_t *keys_out, uint32_t *vals_out, int bit_lo, int nbits,
+                               const uint64_t *bin_base, void *lookback, uint32_t *ticket, int sm_count, cudaStream_t stream) {
+    if (a.total_res == 0 || a.n_prot == 0) return cudaSuccess;
+    const uint64_t tiles = encode_sort_tiles(a.total_res);
+    const unsigned grid = persistent_grid(tiles, sm_count);
+    const uint32_t mask = (1u << nbits) - 1u;
+    if (wide_lookback(a.total_res))
+        encode_sort_kernel<uint64_t><<<grid, OS_THREADS, sizeof(FusedSmem), stream>>>(a, keys_out, vals_out, bit_lo, mask, bin_base,
+                                                                                        (uint64_t *)lookback, ticket, (uint32_t)tiles);
+    else
+        encode_sort_kernel<uint32_t><<<grid, OS_THREADS, sizeof(FusedSmem), stream>>>(a, keys_out, vals_out, bit_lo, mask, bin_base,
+                                                                                        (uint32_t *)lookback, ticket, (uint32_t)tiles);
     return cudaGetLastError();
 }
 

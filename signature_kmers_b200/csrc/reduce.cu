@@ -622,17 +622,28 @@ group_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
 // squeeze tile as it writes them; one small scan later every tile knows where its kept rows go, so the
 // tiles are independent of each other (no chained scan, no tickets).
 
-// two residues at a time: pair_ascii[40 a + b] = letter(a) | letter(b) << 8
-__device__ uint16_t g_pair_ascii[1600];
-__global__ void init_pair_ascii_kernel() {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 1600) g_pair_ascii[i] = (uint16_t)(sigk_symbol_ascii(i / 40) | (sigk_symbol_ascii(i % 40) << 8));
+// two residues at a time: pair_ascii[20 a + b] = letter(a) | letter(b) << 8 (upper case; the case mask is ORed in
+// afterwards).  A compile-time table: nothing to initialise, nothing to order against the build streams.
+struct PairAscii { uint16_t v[400]; };
+constexpr PairAscii make_pair_ascii() {
+    PairAscii t{};
+    const char aa[21] = "ACDEFGHIKLMNPQRSTVWY";
+    for (int i = 0; i < 400; ++i) t.v[i] = (uint16_t)((unsigned char)aa[i / 20] | ((unsigned char)aa[i % 20] << 8));
+    return t;
 }
-SIGK_D uint64_t code_to_ascii_pairs(uint64_t code) {
-    const uint32_t hi = (uint32_t)(code / 2560000ull);                      // 40^4
-    const uint32_t lo = (uint32_t)(code - (uint64_t)hi * 2560000ull);
-    const uint32_t w0 = __ldg(g_pair_ascii + hi / 1600u) | ((uint32_t)__ldg(g_pair_ascii + hi % 1600u) << 16);
-    const uint32_t w1 = __ldg(g_pair_ascii + lo / 1600u) | ((uint32_t)__ldg(g_pair_ascii + lo % 1600u) << 16);
+__device__ const PairAscii g_pair_ascii = make_pair_ascii();
+// group code (code35 << 8 | mask8) -> the k-mer's 8 ASCII bytes, first residue in the low byte
+SIGK_D uint64_t code_to_ascii_pairs(uint64_t gcode) {
+    const uint64_t code = gcode >> SIGK_MASK_BITS;
+    const uint32_t mask = (uint32_t)gcode & 0xFFu;
+    const uint32_t hi = (uint32_t)(code / 160000ull);                       // 20^4
+    const uint32_t lo = (uint32_t)(code - (uint64_t)hi * 160000ull);
+    uint32_t w0 = __ldg(g_pair_ascii.v + hi / 400u) | ((uint32_t)__ldg(g_pair_ascii.v + hi % 400u) << 16);
+    uint32_t w1 = __ldg(g_pair_ascii.v + lo / 400u) | ((uint32_t)__ldg(g_pair_ascii.v + lo % 400u) << 16);
+    if (mask) {                                                              // rare: 0x20 into the lower-case positions
+        const uint64_t m = sigk_spread_mask(mask);
+        w0 |= (uint32_t)m; w1 |= (uint32_t)(m >> 32);
+    }
     return (uint64_t)w0 | ((uint64_t)w1 << 32);
 }
 
@@ -651,7 +662,7 @@ tombstone_scan_kernel(const uint64_t *__restrict__ n_seg_ptr, const uint32_t *__
 #endif
 __global__ void __launch_bounds__(SQ_THREADS, SIGK_SQ_MIN_BLOCKS)
 squeeze_rows_kernel(const uint4 *__restrict__ rows, const uint64_t *__restrict__ n_seg_ptr, KeptColumns out,
-                    const uint32_t *__restrict__ rej_before) {
+                    const uint32_t *__restrict__ rej_before, uint64_t *__restrict__ n_side_kept) {
     __shared__ uint32_t s_scan[SQ_WARPS + 2];
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint64_t n_seg = *n_seg_ptr;
@@ -674,9 +685,11 @@ squeeze_rows_kernel(const uint4 *__restrict__ rows, const uint64_t *__restrict__
     uint32_t total;
     const uint32_t excl = block_exclusive_scan<SQ_THREADS>(lane == 0 ? warp_total : 0u, s_scan, &total);
     uint32_t run = __shfl_sync(FULL, excl, 0);
+    uint32_t side = 0;                          // kept rows of the side run (case mask != 0): the table's second section
 #pragma unroll
     for (int i = 0; i < SQ_ITEMS; ++i) {
         if ((ball[i] >> lane) & 1u) {
+            side += (row[i].x & 0xFFu) ? 1u : 0u;
             const uint64_t o = base + run + __popc(ball[i] & mask_lt(lane));
             out.kmer[o] = code_to_ascii_pairs((uint64_t)row[i].x | ((uint64_t)(row[i].y & 0x7FFu) << 32));
             out.avg_from_end[o] = (uint16_t)(row[i].y >> 11);
@@ -686,6 +699,11 @@ squeeze_rows_kernel(const uint4 *__restrict__ rows, const uint64_t *__restrict__
             out.var[o] = (uint16_t)(row[i].w >> 16);
         }
         run += __popc(ball[i]);
+    }
+    if (__any_sync(FULL, side != 0)) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) side += __shfl_xor_sync(FULL, side, o);
+        if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(n_side_kept), (unsigned long long)side);
     }
 }
 
@@ -892,15 +910,15 @@ size_t reduce_group_entries(uint64_t capacity, int) {
 }
 size_t reduce_long_group_entries(uint64_t capacity) { return (size_t)(capacity / 33 + 2); }
 size_t reduce_work_entries(uint64_t capacity, int sm_count) {
-    // a walked group has >= 3 records; two kernels push into the list
-    return (size_t)(capacity / 3 + 2) + 2 * (size_t)reduce_grid(sm_count) * (RED_THREADS / 32) * WORK_BLOCK;
+    // A walked group has >= 3 records.  Slots are reserved in blocks of WORK_BLOCK and a block's unused tail is
+    // dropped when the next window needs more than it has left (a window lists at most 10 groups), so a block
+    // holds at least WORK_BLOCK - 9 live entries: size the list for that padding, plus one open block per warp.
+    const size_t groups = (size_t)(capacity / 3 + 2);
+    return groups + groups * 9 / (WORK_BLOCK - 9) + WORK_BLOCK + 2 * (size_t)reduce_grid(sm_count) * (RED_THREADS / 32) * WORK_BLOCK;
 }
 size_t reduce_long_work_entries(uint64_t capacity) { return (size_t)(capacity / ORD_LONG + 2); }
 
-cudaError_t reduce_configure() {
-    init_pair_ascii_kernel<<<(1600 + 255) / 256, 256>>>();
-    return cudaGetLastError();
-}
+cudaError_t reduce_configure() { return cudaSuccess; }
 
 cudaError_t launch_protein_meta(const uint64_t *starts, const uint16_t *func, const uint32_t *seq_id, uint32_t n_prot,
                                 MetaTable meta, uint64_t first, uint32_t *seqs_with_func, cudaStream_t stream) {
@@ -984,13 +1002,13 @@ cudaError_t launch_order_stats(const uint32_t *vals, MetaTable meta, const Order
 }
 
 cudaError_t launch_squeeze_rows(const uint4 *rows, const uint64_t *n_seg_ptr, uint64_t capacity, KeptColumns out,
-                                uint64_t *scratch_words, uint64_t *n_kept_out, cudaStream_t stream) {
+                                uint64_t *scratch_words, uint64_t *n_kept_out, uint64_t *n_side_kept, cudaStream_t stream) {
     if (capacity == 0) return cudaSuccess;
     const ReduceScratch sx = reduce_scratch(scratch_words, capacity);
     tombstone_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(n_seg_ptr, sx.rej_tile, sx.rej_before, n_kept_out);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    squeeze_rows_kernel<<<(unsigned)squeeze_tiles(capacity), SQ_THREADS, 0, stream>>>(rows, n_seg_ptr, out, sx.rej_before);
+    squeeze_rows_kernel<<<(unsigned)squeeze_tiles(capacity), SQ_THREADS, 0, stream>>>(rows, n_seg_ptr, out, sx.rej_before, n_side_kept);
     return cudaGetLastError();
 }
 

@@ -8,6 +8,8 @@
 #include "handle.h"
 #include "sigk_common.cuh"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -20,6 +22,14 @@ using namespace sigk;
 
 namespace {
 thread_local std::string g_create_error;
+
+// NVTX range around a stage of the build (header-only NVTX3: a no-op unless a profiler is attached)
+struct nvtx_range {
+    explicit nvtx_range(const char *name) { nvtxRangePushA(name); }
+    ~nvtx_range() { nvtxRangePop(); }
+    nvtx_range(const nvtx_range &) = delete;
+    nvtx_range &operator=(const nvtx_range &) = delete;
+};
 }  // namespace
 
 namespace {
@@ -42,7 +52,8 @@ int ensure_capacity(sigk_handle *h, uint64_t cap, bool keep_pingpong1) {
         if (i == 1 && keep_pingpong1) continue;
         CU(h, h->d_keys[i].reserve(cap)); CU(h, h->d_vals[i].reserve(cap));
     }
-    CU(h, h->d_lookback.reserve(onesweep_lookback_bytes(cap_lb) * SORT_MAX_PASSES));
+    // one look-back row set per pass of the main run, one shared by the passes of the side run
+    CU(h, h->d_lookback.reserve(onesweep_lookback_bytes(cap_lb) * (SORT_MAX_PASSES + 1)));
     CU(h, h->d_groups.reserve(reduce_group_entries(cap, h->sm_count)));
     CU(h, h->d_long_groups.reserve(reduce_long_group_entries(cap)));
     CU(h, h->d_work.reserve(reduce_work_entries(cap, h->sm_count)));
@@ -50,8 +61,8 @@ int ensure_capacity(sigk_handle *h, uint64_t cap, bool keep_pingpong1) {
     CU(h, h->d_rows.reserve(cap));
     CU(h, h->d_out_kmer.reserve(cap));
     CU(h, h->d_out_cols.reserve(cap * 5));
-    const uint64_t padded = encode_tiles(h->total_res) * ENC_TILE + ENC_PAD;
-    CU(h, h->d_scan_state.reserve(std::max(encode_scan_entries(padded), reduce_scan_entries(cap))));
+    const uint64_t world = (uint64_t)std::max(1, h->cfg.world);
+    CU(h, h->d_scan_state.reserve(std::max<uint64_t>((encode_slices(h->total_res) + 1) * world + world, reduce_scan_entries(cap))));
     if (cap > h->capacity) h->capacity = cap;
     return SIGK_OK;
 }
@@ -74,8 +85,8 @@ int do_upload(sigk_handle *h) {
     CU(h, h->d_func.reserve(np));
     CU(h, h->d_seqid.reserve(np));
     CU(h, h->d_slice_prot.reserve(encode_slices(total) + 2));
-    CU(h, h->d_hist.reserve(SORT_MAX_PASSES * SIGK_RADIX));
-    CU(h, h->d_binbase.reserve(SORT_MAX_PASSES * SIGK_RADIX));
+    CU(h, h->d_hist.reserve(2 * SORT_MAX_PASSES * SIGK_BINS));        // rows 0..7: main run, 8..15: side run
+    CU(h, h->d_binbase.reserve(2 * SORT_MAX_PASSES * SIGK_BINS));
     CU(h, h->d_distinct.reserve(SIGK_N_FUNCTION_SLOTS));
     CU(h, h->d_swf.reserve(SIGK_N_FUNCTION_SLOTS));
     CU(h, h->d_scalars.reserve(1));
@@ -86,6 +97,7 @@ int do_upload(sigk_handle *h) {
     if (int rc = ensure_capacity(h, std::max<uint64_t>(total, h->capacity), false)) return rc;
 
     cudaStream_t st = h->stream;
+    nvtx_range r_up("sigk upload");
     CU(h, cudaEventRecord(h->ev[EV_START], st));
     if (total) CU(h, cudaMemcpyAsync(h->d_res.p, p.residues, total, cudaMemcpyHostToDevice, st));
     CU(h, cudaMemsetAsync(h->d_res.p + total, 0, padded - total, st));
@@ -115,6 +127,19 @@ int do_upload(sigk_handle *h) {
     CU(h, h->d_bitmap.reserve(((uint64_t)h->max_seq_id >> 5) + 1));
     CU(h, h->d_prot_windows.reserve(np));
     CU(h, h->d_prot_rejected.reserve(h->n_prot_global));
+
+    // What depends on the input alone is computed here, once per upload, not once per build: the per-protein table
+    // (job-wide with a communicator), seqs_with_func (src/signature_build.tcc:160) and the k-mer range splitters.
+    uint32_t launches = 0;
+    const MetaTable meta{h->d_meta.p, h->meta_compact};
+    CU(h, cudaMemsetAsync(h->d_swf.p, 0, SIGK_N_FUNCTION_SLOTS * sizeof(uint32_t), st));
+    CU(h, launch_protein_meta(h->d_starts.p, h->d_func.p, h->d_seqid.p, (uint32_t)np, meta, h->ordinal_base, h->d_swf.p, st)); ++launches;
+    if (h->comm) {
+        if (int rc = comm_allgather_meta(h)) return rc;
+        if (int rc = comm_choose_splitters(h, &launches)) return rc;
+    }
+    CU(h, cudaStreamSynchronize(st));
+    h->upload_launches = launches;
     h->uploaded = true;
     h->built = h->downloaded = false;
     return SIGK_OK;
@@ -127,76 +152,147 @@ int do_build_device(sigk_handle *h) {
     const uint64_t np = h->in.n_proteins;
     DeviceScalars *sc = h->d_scalars.p;
     uint32_t launches = 0;
+    nvtx_range r_build("sigk build_device");
 
     h->table_on_device = false;                 // the table buffers are rewritten from here on
     CU(h, cudaEventRecord(h->ev[EV_DEV0], st));
     CU(h, cudaMemsetAsync(sc, 0, sizeof(DeviceScalars), st));
-    CU(h, cudaMemsetAsync(h->d_swf.p, 0, SIGK_N_FUNCTION_SLOTS * sizeof(uint32_t), st));
     CU(h, cudaMemsetAsync(h->d_distinct.p, 0, SIGK_N_FUNCTION_SLOTS * sizeof(uint32_t), st));
     CU(h, cudaMemsetAsync(h->d_bitmap.p, 0, (((uint64_t)h->max_seq_id >> 5) + 1) * sizeof(uint32_t), st));
     CU(h, cudaMemsetAsync(h->d_prot_windows.p, 0, std::max<uint64_t>(np, 1) * sizeof(uint32_t), st));
     CU(h, cudaMemsetAsync(h->d_prot_rejected.p, 0, std::max<uint64_t>(h->n_prot_global, 1) * sizeof(uint32_t), st));
-    CU(h, cudaMemsetAsync(h->d_hist.p, 0, SORT_MAX_PASSES * SIGK_RADIX * sizeof(uint64_t), st));
+    CU(h, cudaMemsetAsync(h->d_hist.p, 0, 2 * SORT_MAX_PASSES * SIGK_BINS * sizeof(uint64_t), st));
 
-    // ---- stage 1: encode
-    const MetaTable meta{h->d_meta.p, h->meta_compact};
-    CU(h, launch_protein_meta(h->d_starts.p, h->d_func.p, h->d_seqid.p, (uint32_t)np, meta, h->ordinal_base, h->d_swf.p, st)); ++launches;
-    if (h->comm) { if (int rc = comm_allgather_meta(h)) return rc; }
-    CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, encode_scan_entries(h->total_res) * sizeof(uint64_t), st));
-    EncodeArgs ea{h->d_res.p, h->total_res, h->d_starts.p, (uint32_t)np, (uint32_t)h->ordinal_base, h->d_slice_prot.p, h->d_prot_windows.p};
-    if (!h->comm) {
-        CU(h, launch_encode(ea, h->d_keys[0].p, h->d_vals[0].p, h->d_scan_state.p, sc->ticket + TK_ENCODE, &sc->n_records, st)); ++launches;
-        CU(h, cudaEventRecord(h->ev[EV_ENCODE], st));
-    } else {
-        // ---- multi-GPU: every record goes to the rank that owns its k-mer range
-        CU(h, cudaEventRecord(h->ev[EV_ENCODE], st));
-        if (int rc = comm_encode_exchange(h, ea, &launches)) return rc;
-        CU(h, cudaMemsetAsync(h->d_hist.p, 0, SORT_MAX_PASSES * SIGK_RADIX * sizeof(uint64_t), st));
-    }
-    CU(h, cudaEventRecord(h->ev[EV_EXCHANGE], st));
+    // the main run is sorted on the 35 code bits, the side run (records with a lower-case residue) on all 43
+    h->plan = make_pass_plan(SIGK_KEY_CODE35_SHIFT, 64);
+    h->plan_side = make_pass_plan(SIGK_KEY_CODE_SHIFT, 64);
+    const PassPlan &plan = h->plan, &plan_side = h->plan_side;
+    if (plan.npass > TK_SIDE0 - TK_SORT0 || plan_side.npass > 16 - TK_SIDE0) return h->fail(SIGK_E_UNSUPPORTED, "too many sort passes");
+    // both runs must end in the same ping-pong buffer
+    if (((plan.npass - 1) & 1) != (plan_side.npass & 1)) return h->fail(SIGK_E_UNSUPPORTED, "pass counts of the two runs disagree in parity");
+    uint64_t *hist_main = h->d_hist.p, *hist_side = h->d_hist.p + (size_t)SORT_MAX_PASSES * SIGK_BINS;
+    uint64_t *base_main = h->d_binbase.p, *base_side = h->d_binbase.p + (size_t)SORT_MAX_PASSES * SIGK_BINS;
     const uint64_t cap = h->capacity;
+    const size_t lb_bytes = onesweep_lookback_bytes(std::max<uint64_t>(cap, 1));
+    uint8_t *lb_side = h->d_lookback.p + lb_bytes * SORT_MAX_PASSES;
+    CU(h, cudaMemsetAsync(h->d_lookback.p, 0, lb_bytes * plan.npass, st));
 
-    // ---- stage 2: onesweep sort on the 43 code bits
-    h->plan = make_pass_plan(SIGK_KEY_CODE_SHIFT, SIGK_KEY_CODE_SHIFT + SIGK_CODE_BITS);
-    CU(h, launch_histogram(h->d_keys[0].p, &sc->n_records, cap, h->plan, h->d_hist.p, h->sm_count, st)); ++launches;
-    CU(h, launch_scan_bins(h->d_hist.p, h->d_binbase.p, h->plan.npass, st)); ++launches;
+    const MetaTable meta{h->d_meta.p, h->meta_compact};
+    EncodeArgs ea{h->d_res.p, h->total_res, h->d_starts.p, (uint32_t)np, (uint32_t)h->ordinal_base, h->d_slice_prot.p, h->d_prot_windows.p};
+    int cur;                                    // ping-pong buffer that holds the output of the first pass
+    CU(h, cudaEventRecord(h->ev[EV_ENCODE], st));
+    CU(h, cudaEventRecord(h->ev[EV_EXCHANGE], st));
     CU(h, cudaEventRecord(h->ev[EV_HIST], st));
-    int cur = 0;
-    const size_t lb_bytes = onesweep_lookback_bytes(cap);
-    CU(h, cudaMemsetAsync(h->d_lookback.p, 0, lb_bytes * h->plan.npass, st));
-    for (int p = 0; p < h->plan.npass; ++p) {
-        CU(h, cudaEventRecord(h->ev[EV_PASS0 + p], st));
-        CU(h, launch_onesweep_pass(h->d_keys[cur].p, h->d_vals[cur].p, h->d_keys[cur ^ 1].p, h->d_vals[cur ^ 1].p,
-                                   &sc->n_records, cap, h->plan.lo[p], h->plan.bits[p],
-                                   h->d_binbase.p + (size_t)p * SIGK_RADIX, h->d_lookback.p + lb_bytes * p, sc->ticket + TK_SORT0 + p, st));
-        ++launches;
-        cur ^= 1;
+    if (!h->comm && h->fused) {
+        // ---- stage 1+2a on one GPU: digit counts from the residues, then encode fused with the first radix pass
+        nvtx_range r("sigk count + encode-sort");
+        CU(h, launch_window_count(ea, plan, hist_main, h->sm_count, st)); ++launches;
+        CU(h, launch_scan_bins(hist_main, base_main, plan.npass, &sc->n_main, st)); ++launches;
+        CU(h, cudaMemcpyAsync(&sc->n_records, &sc->n_both, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+        CU(h, cudaEventRecord(h->ev[EV_ENCODE], st));
+        CU(h, cudaEventRecord(h->ev[EV_EXCHANGE], st));
+        CU(h, cudaEventRecord(h->ev[EV_HIST], st));
+        CU(h, cudaEventRecord(h->ev[EV_PASS0], st));
+        CU(h, launch_encode_sort(ea, h->d_keys[0].p, h->d_vals[0].p, plan.lo[0], plan.bits[0], base_main, h->d_lookback.p,
+                                 sc->ticket + TK_SORT0, h->sm_count, st)); ++launches;
+        cur = 0;
+    } else {
+        // ---- stage 1: encode (+ route to the rank that owns the record's k-mer range); stage 2a: histogram and first
+        // pass straight out of the regions the records were written to
+        SortSegments seg{};
+        const uint64_t *n_ptr = nullptr;
+        if (!h->comm) {
+            nvtx_range r("sigk encode");
+            CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, (encode_slices(h->total_res) + 2) * sizeof(uint64_t), st));
+            EncodeSplitArgs sp{};
+            sp.n_split = 0; sp.region_stride = cap; sp.owner_state = h->d_scan_state.p; sp.owner_totals = &sc->n_records;
+            sp.overflow = &sc->overflow;
+            sp.dst_keys[0] = h->d_keys[0].p; sp.dst_vals[0] = h->d_vals[0].p;
+            CU(h, launch_encode_split(ea, sp, sc->ticket + TK_ENCODE, st)); ++launches;
+            seg.n = 1; seg.start[0] = 0; seg.start[1] = cap; seg.keys[0] = h->d_keys[0].p; seg.vals[0] = h->d_vals[0].p;
+            n_ptr = &sc->n_records;                 // only the device knows how many windows were valid
+            CU(h, cudaEventRecord(h->ev[EV_ENCODE], st));
+            CU(h, cudaEventRecord(h->ev[EV_EXCHANGE], st));
+            cur = 1;
+        } else {
+            nvtx_range r("sigk encode + exchange");
+            // (records EV_ENCODE; cur = the ping-pong buffer that is free: the regions are the landing zone, or keys[0]
+            // after a send/recv exchange)
+            if (int rc = comm_encode_exchange(h, ea, &seg, &cur, &launches)) return rc;
+            CU(h, cudaEventRecord(h->ev[EV_EXCHANGE], st));
+        }
+        nvtx_range r("sigk histogram + first pass");
+        CU(h, launch_histogram_main(seg, n_ptr, plan, hist_main, h->sm_count, st)); ++launches;
+        CU(h, launch_scan_bins(hist_main, base_main, plan.npass, &sc->n_main, st)); ++launches;
+        CU(h, cudaMemcpyAsync(&sc->n_records, &sc->n_both, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+        CU(h, cudaEventRecord(h->ev[EV_HIST], st));
+        CU(h, cudaEventRecord(h->ev[EV_PASS0], st));
+        CU(h, launch_onesweep_first_pass(seg, n_ptr, h->d_keys[cur].p, h->d_vals[cur].p, cap, plan.lo[0], plan.bits[0], base_main,
+                                         h->d_lookback.p, sc->ticket + TK_SORT0, h->sm_count, st)); ++launches;
     }
-    CU(h, cudaEventRecord(h->ev[EV_PASS0 + h->plan.npass], st));
+    const uint64_t cap_sort = h->capacity;      // (the exchange may have grown it)
+
+    // ---- stage 2b: the remaining passes of the main run
+    {
+        nvtx_range r("sigk sort: main run");
+        for (int p = 1; p < plan.npass; ++p) {
+            CU(h, cudaEventRecord(h->ev[EV_PASS0 + p], st));
+            CU(h, launch_onesweep_pass(h->d_keys[cur].p, h->d_vals[cur].p, h->d_keys[cur ^ 1].p, h->d_vals[cur ^ 1].p, &sc->n_main, nullptr,
+                                       cap_sort, plan.lo[p], plan.bits[p], base_main + (size_t)p * SIGK_BINS, h->d_lookback.p + lb_bytes * p,
+                                       sc->ticket + TK_SORT0 + p, h->sm_count, st)); ++launches;
+            cur ^= 1;
+        }
+        CU(h, cudaEventRecord(h->ev[EV_PASS0 + plan.npass], st));
+        CU(h, cudaEventRecord(h->ev[EV_MAIN_SORTED], st));
+    }
+    // ---- stage 2c: the side run (behind the main run in the first pass's output): its own histogram, all 43 bits
+    {
+        nvtx_range r("sigk sort: side run");
+        int c = cur ^ ((plan.npass - 1) & 1);    // where the first pass left it
+        CU(h, launch_histogram(h->d_keys[c].p, &sc->n_side, &sc->n_main, cap_sort, plan_side, hist_side, h->sm_count, st)); ++launches;
+        CU(h, launch_scan_bins(hist_side, base_side, plan_side.npass, nullptr, st)); ++launches;
+        for (int p = 0; p < plan_side.npass; ++p) {
+            CU(h, launch_clear_lookback(lb_side, &sc->n_side, cap_sort, st)); ++launches;
+            CU(h, launch_onesweep_pass(h->d_keys[c].p, h->d_vals[c].p, h->d_keys[c ^ 1].p, h->d_vals[c ^ 1].p, &sc->n_side, &sc->n_main,
+                                       cap_sort, plan_side.lo[p], plan_side.bits[p], base_side + (size_t)p * SIGK_BINS, lb_side,
+                                       sc->ticket + TK_SIDE0 + p, h->sm_count, st)); ++launches;
+            c ^= 1;
+        }
+        if (c != cur) return h->fail(SIGK_E_UNSUPPORTED, "internal: the two sorted runs ended in different buffers");
+    }
     CU(h, cudaEventRecord(h->ev[EV_SORT], st));
     h->sorted_in = cur;
 
     // ---- stages 3+4: run-length + reduce + keep/reject, the order-dependent columns, compaction
-    const uint64_t scan_words = reduce_scan_entries(cap);
+    const uint64_t scan_words = reduce_scan_entries(cap_sort);
     CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, scan_words * sizeof(uint64_t), st));
     const int order_stats = (h->cfg.flags & SIGK_F_NO_ORDER_STATS) ? 0 : 1;
     KeptColumns kc{h->d_out_kmer.p, out_col(h, 0), out_col(h, 1), out_col(h, 2), out_col(h, 3), out_col(h, 4)};
     ReduceLists rl{h->d_groups.p, &sc->n_groups, &sc->next_group, h->d_long_groups.p, &sc->n_long, &sc->next_long,
                    h->d_work.p, &sc->n_work, h->d_work_long.p, &sc->n_work_long};
-    CU(h, launch_segment_reduce(h->d_keys[cur].p, h->d_vals[cur].p, &sc->n_records, cap, meta, h->d_rows.p, rl,
-                                h->d_prot_rejected.p, h->d_scan_state.p, &sc->n_segments, order_stats, h->sm_count, st)); launches += 5;
-    if (h->comm) { if (int rc = comm_reduce_rejected(h)) return rc; }
-    CU(h, launch_signature_flags(h->d_prot_windows.p, h->d_prot_rejected.p + h->ordinal_base, h->d_seqid.p, (uint32_t)np, h->d_bitmap.p, st)); ++launches;
-    CU(h, launch_popcount(h->d_bitmap.p, ((uint64_t)h->max_seq_id >> 5) + 1, &sc->n_seqs_sig, st)); ++launches;
+    {
+        nvtx_range r("sigk segment reduce");
+        CU(h, launch_segment_reduce(h->d_keys[cur].p, h->d_vals[cur].p, &sc->n_records, cap_sort, meta, h->d_rows.p, rl,
+                                    h->d_prot_rejected.p, h->d_scan_state.p, &sc->n_segments, order_stats, h->sm_count, st)); launches += 5;
+        if (h->comm) { if (int rc = comm_reduce_rejected(h)) return rc; }
+        CU(h, launch_signature_flags(h->d_prot_windows.p, h->d_prot_rejected.p + h->ordinal_base, h->d_seqid.p, (uint32_t)np, h->d_bitmap.p, st)); ++launches;
+        CU(h, launch_popcount(h->d_bitmap.p, ((uint64_t)h->max_seq_id >> 5) + 1, &sc->n_seqs_sig, st)); ++launches;
+    }
     CU(h, cudaEventRecord(h->ev[EV_REDUCE], st));
-    if (order_stats) { CU(h, launch_order_stats(h->d_vals[cur].p, meta, h->d_work.p, &sc->n_work, &sc->next_work, h->d_work_long.p, &sc->n_work_long, &sc->next_work_long, cap, h->d_rows.p, h->sm_count, st)); launches += 2; }
+    if (order_stats) {
+        nvtx_range r("sigk order statistics");
+        CU(h, launch_order_stats(h->d_vals[cur].p, meta, h->d_work.p, &sc->n_work, &sc->next_work, h->d_work_long.p, &sc->n_work_long, &sc->next_work_long, cap_sort, h->d_rows.p, h->sm_count, st)); launches += 2;
+    }
     CU(h, cudaEventRecord(h->ev[EV_ORDER], st));
-    CU(h, launch_squeeze_rows(h->d_rows.p, &sc->n_segments, cap, kc, h->d_scan_state.p, &sc->n_kept, st)); launches += 2;
-    // distinct_functions[best]++ per kept row (tcc:286), from the finished function_index column; with a
-    // communicator the other ranks' functions are not known here, so both counter ranges are walked
-    CU(h, launch_function_histogram(out_col(h, 1), &sc->n_kept, cap, h->comm ? 0xFFFFu : h->local_max_function, h->d_distinct.p,
-                                    h->sm_count, st)); ++launches;
-    if (h->comm) { if (int rc = comm_reduce_stats(h)) return rc; }
+    {
+        nvtx_range r("sigk squeeze");
+        CU(h, launch_squeeze_rows(h->d_rows.p, &sc->n_segments, cap_sort, kc, h->d_scan_state.p, &sc->n_kept, &sc->n_side_kept, st)); launches += 2;
+        // distinct_functions[best]++ per kept row (tcc:286), from the finished function_index column; with a
+        // communicator the other ranks' functions are not known here, so both counter ranges are walked
+        CU(h, launch_function_histogram(out_col(h, 1), &sc->n_kept, cap_sort, h->comm ? 0xFFFFu : h->local_max_function, h->d_distinct.p,
+                                        h->sm_count, st)); ++launches;
+        if (h->comm) { if (int rc = comm_reduce_stats(h)) return rc; }
+    }
     CU(h, cudaEventRecord(h->ev[EV_SQUEEZE], st));
 
     h->tm.kernel_launches = launches;
@@ -238,9 +334,11 @@ int do_download(sigk_handle *h) {
     auto ms = [&](int a, int b) { float v = 0; cudaEventElapsedTime(&v, h->ev[a], h->ev[b]); return v; };
     t.h2d_ms = h->h2d_ms;
     t.encode_ms = ms(EV_DEV0, EV_ENCODE);
+    t.count_ms = (!h->comm && h->fused) ? t.encode_ms : 0.f;
     t.exchange_ms = ms(EV_ENCODE, EV_EXCHANGE);
     t.histogram_ms = ms(EV_EXCHANGE, EV_HIST);
     t.sort_ms = ms(EV_HIST, EV_SORT);
+    t.side_sort_ms = ms(EV_MAIN_SORTED, EV_SORT);
     t.reduce_ms = ms(EV_SORT, EV_REDUCE);
     t.order_stats_ms = ms(EV_REDUCE, EV_ORDER);
     t.squeeze_ms = ms(EV_ORDER, EV_SQUEEZE);
@@ -258,7 +356,7 @@ int do_download(sigk_handle *h) {
 
 extern "C" {
 
-const char *sigk_version(void) { return "libsigk 0.1 (sm_100a; record 12 B; onesweep 8-bit digits)"; }
+const char *sigk_version(void) { return "libsigk 0.2 (sm_100a; record 12 B; onesweep, 9-bit digits, 4 passes on 35 code bits, first pass fused with the encode)"; }
 
 int sigk_device_count(void) {
     int n = 0;
@@ -288,6 +386,7 @@ int sigk_create(const sigk_config *cfg, sigk_handle **out) {
     }
     for (auto &ev : h->ev) cudaEventCreate(&ev);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
+    h->fused = std::getenv("SIGK_NO_FUSED") == nullptr;
     if ((e = onesweep_configure()) != cudaSuccess || (e = reduce_configure()) != cudaSuccess) {
         g_create_error = std::string("kernel configuration failed (is this an sm_100a device?): ") + cudaGetErrorString(e);
         sigk_destroy(h);
@@ -424,6 +523,7 @@ int sigk_result(sigk_handle *h, sigk_table *out) {
     out->num_seqs_with_a_signature = s.n_seqs_sig;
     out->distinct_functions = h->h_distinct.p;
     out->seqs_with_func = h->h_swf.p;
+    out->n_upper = s.n_kept - s.n_side_kept;
     return SIGK_OK;
 }
 
@@ -471,15 +571,19 @@ int sigk_comm_join(sigk_handle *h, const void *id128) {
 int sigk_dbg_encode(sigk_handle *h, const sigk_proteins *p, uint64_t *out_code, uint32_t *out_ordinal,
                     uint16_t *out_offset, uint64_t capacity, uint64_t *n_out) {
     if (!h) return SIGK_E_INVALID;
+    if (h->comm) return h->fail(SIGK_E_UNSUPPORTED, "sigk_dbg_encode is single-GPU");
     if (int rc = sigk_set_proteins(h, p)) return rc;
     if (int rc = do_upload(h)) return rc;
     cudaStream_t st = h->stream;
     DeviceScalars *sc = h->d_scalars.p;
     CU(h, cudaMemsetAsync(sc, 0, sizeof(DeviceScalars), st));
-    CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, encode_scan_entries(h->total_res) * sizeof(uint64_t), st));
+    CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, (encode_slices(h->total_res) + 2) * sizeof(uint64_t), st));
     EncodeArgs ea{h->d_res.p, h->total_res, h->d_starts.p, (uint32_t)p->n_proteins, 0u, h->d_slice_prot.p, nullptr};
-    if (h->comm) return h->fail(SIGK_E_UNSUPPORTED, "sigk_dbg_encode is single-GPU");
-    CU(h, launch_encode(ea, h->d_keys[0].p, h->d_vals[0].p, h->d_scan_state.p, sc->ticket + TK_ENCODE, &sc->n_records, st));
+    EncodeSplitArgs sp{};
+    sp.n_split = 0; sp.region_stride = h->capacity; sp.owner_state = h->d_scan_state.p; sp.owner_totals = &sc->n_records;
+    sp.overflow = &sc->overflow;
+    sp.dst_keys[0] = h->d_keys[0].p; sp.dst_vals[0] = h->d_vals[0].p;
+    CU(h, launch_encode_split(ea, sp, sc->ticket + TK_ENCODE, st));
     uint64_t n = 0;
     CU(h, cudaMemcpyAsync(&n, &sc->n_records, sizeof n, cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
@@ -515,21 +619,21 @@ int sigk_dbg_sort_pairs(sigk_handle *h, uint64_t *keys, uint32_t *vals, uint64_t
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t x) { if (e == cudaSuccess) e = x; return e == cudaSuccess; };
     for (int i = 0; i < 2; ++i) { ok(k[i].reserve(n)); ok(v[i].reserve(n)); }
-    ok(hist.reserve(SORT_MAX_PASSES * SIGK_RADIX)); ok(base.reserve(SORT_MAX_PASSES * SIGK_RADIX));
+    ok(hist.reserve(SORT_MAX_PASSES * SIGK_BINS)); ok(base.reserve(SORT_MAX_PASSES * SIGK_BINS));
     ok(nbuf.reserve(1)); ok(ticket.reserve(SORT_MAX_PASSES)); ok(lb.reserve(onesweep_lookback_bytes(n)));
     if (e == cudaSuccess) {
         ok(cudaMemcpyAsync(k[0].p, keys, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
         ok(cudaMemcpyAsync(v[0].p, vals, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         ok(cudaMemcpyAsync(nbuf.p, &n, sizeof n, cudaMemcpyHostToDevice, st));
-        ok(cudaMemsetAsync(hist.p, 0, SORT_MAX_PASSES * SIGK_RADIX * sizeof(uint64_t), st));
+        ok(cudaMemsetAsync(hist.p, 0, SORT_MAX_PASSES * SIGK_BINS * sizeof(uint64_t), st));
         ok(cudaMemsetAsync(ticket.p, 0, SORT_MAX_PASSES * sizeof(uint32_t), st));
-        ok(launch_histogram(k[0].p, nbuf.p, n, plan, hist.p, h->sm_count, st));
-        ok(launch_scan_bins(hist.p, base.p, plan.npass, st));
+        ok(launch_histogram(k[0].p, nbuf.p, nullptr, n, plan, hist.p, h->sm_count, st));
+        ok(launch_scan_bins(hist.p, base.p, plan.npass, nullptr, st));
         int cur = 0;
         for (int p = 0; p < plan.npass && e == cudaSuccess; ++p) {
             ok(cudaMemsetAsync(lb.p, 0, onesweep_lookback_bytes(n), st));
-            ok(launch_onesweep_pass(k[cur].p, v[cur].p, k[cur ^ 1].p, v[cur ^ 1].p, nbuf.p, n, plan.lo[p], plan.bits[p],
-                                    base.p + (size_t)p * SIGK_RADIX, lb.p, ticket.p + p, st));
+            ok(launch_onesweep_pass(k[cur].p, v[cur].p, k[cur ^ 1].p, v[cur ^ 1].p, nbuf.p, nullptr, n, plan.lo[p], plan.bits[p],
+                                    base.p + (size_t)p * SIGK_BINS, lb.p, ticket.p + p, h->sm_count, st));
             cur ^= 1;
         }
         ok(cudaMemcpyAsync(keys, k[cur].p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
@@ -542,13 +646,14 @@ int sigk_dbg_sort_pairs(sigk_handle *h, uint64_t *keys, uint32_t *vals, uint64_t
 }
 
 uint64_t sigk_kmer_encode(const char kmer[8]) {
-    uint64_t code = 0;
+    uint64_t code = 0, mask = 0;
     for (int i = 0; i < 8; ++i) {
-        const int s = sigk_symbol((unsigned char)kmer[i]);
-        if (s < 0) return UINT64_MAX;
-        code = code * 40u + (uint64_t)s;
+        const int sy = sigk_symbol((unsigned char)kmer[i]);
+        if (sy < 0) return UINT64_MAX;
+        code = code * 20u + (uint64_t)(sy & 31);
+        mask |= (uint64_t)(sy >> 5) << i;
     }
-    return code;
+    return (code << SIGK_MASK_BITS) | mask;
 }
 
 void sigk_kmer_decode(uint64_t code, char kmer[8]) {

@@ -1,12 +1,18 @@
 // sigk_common.cuh — shared definitions for the libsigk kernels (sm_100a).
 //
 // Record layout in HBM (struct-of-arrays, 12 bytes per k-mer occurrence):
-//   key  u64 = code43 << 21 | offset16 << 5      (low 5 bits zero)
+//   key  u64 = code35 << 29 | mask8 << 21 | offset16 << 5      (low 5 bits zero)
 //   val  u32 = protein ordinal (index into the packed input, canonical order)
-// code43 is the base-40 value of the 8 residues over the reference's 40 valid
-// symbols (src/signature_build.h:102-103) ranked in ASCII order, so integer
-// order of codes == unsigned-byte order of the k-mers.  offset16 is the
-// reference's `unsigned short n = distance(it, seq.end())`
+// code35 is the base-20 value of the 8 residues with their case folded away (the 20 amino-acid
+// letters of src/signature_build.h:102-103 ranked in ASCII order; 20^8 < 2^35), mask8 says which of
+// the 8 residues are lower case (first residue = bit 0).  The reference keeps case ('a' != 'A',
+// src/signature_build.tcc:167), so a k-mer is the pair (code35, mask8) = the 43-bit "group code"
+// key >> 21.  Nearly every window of real proteins is all upper case (mask8 == 0): those records
+// are sorted on the 35 code bits alone (four 9/9/9/8-bit passes instead of the five a 43-bit
+// byte-order code needs); the rare records with a lower-case residue are diverted by the first
+// pass into a side run that is sorted on all 43 bits.  Table order is therefore: k-mers without a
+// lower-case residue first, in byte order; then the others by (case-folded bytes, mask8).
+// offset16 is the reference's `unsigned short n = distance(it, seq.end())`
 // (src/signature_build.tcc:164).  Everything else KmerAttributes carries
 // (func_index, seq_id, protein_length; src/kmer_data.h:105-112) is looked up by
 // ordinal in L2-resident per-protein arrays.
@@ -15,14 +21,21 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-#define SIGK_CODE_BITS 43
-#define SIGK_KEY_CODE_SHIFT 21
+#define SIGK_CODE35_BITS 35
+#define SIGK_MASK_BITS 8
+#define SIGK_CODE_BITS 43                  // group code = code35 << 8 | mask8
+#define SIGK_KEY_CODE_SHIFT 21             // group code = key >> 21
+#define SIGK_KEY_CODE35_SHIFT 29           // code35 = key >> 29
 #define SIGK_KEY_OFFSET_SHIFT 5
 #define SIGK_K_DEV 8
 #ifndef SIGK_RADIX_BITS
-#define SIGK_RADIX_BITS 9         // 43 code bits in 5 passes (9,9,9,8,8): 21.5 ms vs 23.4 ms for 6 passes of 8 bits
+#define SIGK_RADIX_BITS 9         // 35 code bits in 4 passes (9,9,9,8)
 #endif
 #define SIGK_RADIX (1 << SIGK_RADIX_BITS)
+// digit counters / bin bases / look-back rows are padded to this many entries: 512 digits, the
+// side bin of the first pass (SIGK_SIDE_BIN: records with a lower-case residue), a total
+#define SIGK_BINS (SIGK_RADIX + 8)
+#define SIGK_SIDE_BIN SIGK_RADIX
 
 #define SIGK_HD __host__ __device__ __forceinline__
 #define SIGK_D __device__ __forceinline__
@@ -30,8 +43,8 @@
 // Letters A C D E F G H I K L M N P Q R S T V W Y as a bit set over 'A'+bit.
 #define SIGK_AA_MASK 0x016FBDFDu
 
-// Symbol rank 0..39 of a residue byte (upper case 0..19, lower case 20..39), or
-// -1 for anything outside ok_prot_ (B J O U X Z * digits ...).
+// Symbol of a residue byte: rank 0..19 of the letter among the 20 amino acids (ASCII order), plus 32
+// when it is lower case; -1 for anything outside ok_prot_ (B J O U X Z * digits ...).
 SIGK_HD int sigk_symbol(unsigned c) {
     const unsigned idx = (c & 0xDFu) - 0x41u;
     const bool letter = ((c & 0xC0u) == 0x40u) && idx < 26u && ((SIGK_AA_MASK >> idx) & 1u);
@@ -41,50 +54,58 @@ SIGK_HD int sigk_symbol(unsigned c) {
 #else
     const int rank = __builtin_popcount(SIGK_AA_MASK & ((1u << idx) - 1u));
 #endif
-    return rank + ((c & 0x20u) ? 20 : 0);
+    return rank + ((c & 0x20u) ? 32 : 0);
 }
 
-// 40^7
-#define SIGK_P7 163840000000ULL
+// 20^7
+#define SIGK_P7 1280000000ULL
 
-SIGK_HD uint64_t sigk_pack_key(uint64_t code, unsigned offset16) {
-    return (code << SIGK_KEY_CODE_SHIFT) | ((uint64_t)(offset16 & 0xFFFFu) << SIGK_KEY_OFFSET_SHIFT);
+SIGK_HD uint64_t sigk_pack_key(uint64_t code35, unsigned mask8, unsigned offset16) {
+    return (code35 << SIGK_KEY_CODE35_SHIFT) | ((uint64_t)(mask8 & 0xFFu) << SIGK_KEY_CODE_SHIFT) |
+           ((uint64_t)(offset16 & 0xFFFFu) << SIGK_KEY_OFFSET_SHIFT);
 }
-SIGK_HD uint64_t sigk_key_code(uint64_t key) { return key >> SIGK_KEY_CODE_SHIFT; }
+SIGK_HD uint64_t sigk_key_code(uint64_t key) { return key >> SIGK_KEY_CODE_SHIFT; }            // 43-bit group code
+SIGK_HD uint64_t sigk_key_code35(uint64_t key) { return key >> SIGK_KEY_CODE35_SHIFT; }
+SIGK_HD unsigned sigk_key_mask(uint64_t key) { return (unsigned)(key >> SIGK_KEY_CODE_SHIFT) & 0xFFu; }
 SIGK_HD unsigned sigk_key_offset(uint64_t key) { return (unsigned)(key >> SIGK_KEY_OFFSET_SHIFT) & 0xFFFFu; }
 
-// residue letter of symbol 0..39
-SIGK_HD unsigned sigk_symbol_ascii(unsigned s) {
+// upper-case residue letter of rank 0..19
+SIGK_HD unsigned sigk_rank_ascii(unsigned u) {
 #ifdef __CUDA_ARCH__
     // "ACDEFGHIKLMNPQRSTVWY" as little-endian words; byte select by __byte_perm
-    const unsigned u = s >= 20u ? s - 20u : s;
     unsigned c;
     if (u < 8u) c = __byte_perm(0x45444341u, 0x49484746u, u);             // A C D E | F G H I
     else if (u < 16u) c = __byte_perm(0x4E4D4C4Bu, 0x53525150u, u - 8u);   // K L M N | P Q R S
     else c = __byte_perm(0x59575654u, 0u, u - 16u);                        // T V W Y
-    return (c & 0xFFu) | (s >= 20u ? 0x20u : 0u);
+    return c & 0xFFu;
 #else
-    return (unsigned char)"ACDEFGHIKLMNPQRSTVWYacdefghiklmnpqrstvwy"[s];
+    return (unsigned char)"ACDEFGHIKLMNPQRSTVWY"[u];
 #endif
 }
 
-// code -> 8 ASCII bytes packed little-endian (first residue in the low byte),
-// ready for one 8-byte store into the kmer column.  One 64-bit division splits
-// the code into two base-40 halves; the rest is 32-bit arithmetic.
-SIGK_HD uint64_t sigk_code_to_ascii(uint64_t code) {
-    const uint32_t hi = (uint32_t)(code / 2560000ull);                      // 40^4
-    const uint32_t lo = (uint32_t)(code - (uint64_t)hi * 2560000ull);
+// group code -> 8 ASCII bytes packed little-endian (first residue in the low byte), ready for one
+// 8-byte store into the kmer column.  One 64-bit division splits code35 into two base-20 halves;
+// the rest is 32-bit arithmetic; the case mask ORs 0x20 into the lower-case positions.
+SIGK_HD uint64_t sigk_spread_mask(unsigned mask8) {
+    // bit j of mask8 -> 0x20 in byte j
+    uint64_t m = 0;
+    for (int j = 0; j < 8; ++j) m |= (uint64_t)((mask8 >> j) & 1u) << (8 * j + 5);
+    return m;
+}
+SIGK_HD uint64_t sigk_code_to_ascii(uint64_t gcode) {
+    const uint64_t code35 = gcode >> SIGK_MASK_BITS;
+    const uint32_t hi = (uint32_t)(code35 / 160000ull);                     // 20^4
+    const uint32_t lo = (uint32_t)(code35 - (uint64_t)hi * 160000ull);
     uint32_t w[2];
     uint32_t v[2] = {hi, lo};
-#pragma unroll
     for (int h = 0; h < 2; ++h) {
         uint32_t x = v[h];
-        const uint32_t s3 = x % 40u; x /= 40u;
-        const uint32_t s2 = x % 40u; x /= 40u;
-        const uint32_t s1 = x % 40u; x /= 40u;
-        w[h] = sigk_symbol_ascii(x) | (sigk_symbol_ascii(s1) << 8) | (sigk_symbol_ascii(s2) << 16) | (sigk_symbol_ascii(s3) << 24);
+        const uint32_t s3 = x % 20u; x /= 20u;
+        const uint32_t s2 = x % 20u; x /= 20u;
+        const uint32_t s1 = x % 20u; x /= 20u;
+        w[h] = sigk_rank_ascii(x) | (sigk_rank_ascii(s1) << 8) | (sigk_rank_ascii(s2) << 16) | (sigk_rank_ascii(s3) << 24);
     }
-    return (uint64_t)w[0] | ((uint64_t)w[1] << 32);
+    return ((uint64_t)w[0] | ((uint64_t)w[1] << 32)) | sigk_spread_mask((unsigned)gcode & 0xFFu);
 }
 
 #ifdef __CUDACC__

@@ -3,7 +3,9 @@
 //
 //   SortedKmerDb     the KmerDb concept (src/call_functions.h:60-66; src/kept_kmer_db.h:10-32 for the in-memory
 //                    map, src/cmph_kmer.h:27-147 for the on-disk perfect hash) over the table libsigk returns:
-//                    rows are sorted by k-mer bytes, so a fetch is a bucketed binary search.  Also the
+//                    rows come in the two sorted sections of include/sigk.h (k-mers without a lower-case residue in
+//                    byte order, then the others by case-folded bytes and case mask), so a fetch is a binary search
+//                    in the section the query's case pattern picks (bucketed in the first).  Also the
 //                    kmer_data.sigk file that stands in for kmer_data.{mph,dat} (cmph is not in this image).
 //   for_each_kmer    src/kmer_data.h:76-102, with its quirk: a window is skipped when it CONTAINS '*' / 'X'
 //                    and also when it ENDS immediately before one (`kend >= next_ambig`).
@@ -88,16 +90,30 @@ public:
 
     // row of the k-mer, or -1
     int64_t find(const char *kmer) const {
-        const uint32_t b = bucket_of(kmer);
-        uint64_t lo = bucket_[b], hi = bucket_[b + 1];
+        if (!case_bits(kmer)) {
+            // first section: byte order, bucketed by the leading two bytes
+            const uint32_t b = bucket_of(kmer);
+            uint64_t lo = bucket_[b], hi = bucket_[b + 1];
+            while (lo < hi) {
+                const uint64_t mid = lo + (hi - lo) / 2;
+                const int c = std::memcmp(kmer_ + 8 * mid, kmer, 8);
+                if (c == 0) return (int64_t)mid;
+                if (c < 0) lo = mid + 1; else hi = mid;
+            }
+            return -1;
+        }
+        // second section: (case-folded bytes, case mask with residue j in bit j)
+        const uint64_t qf = folded(kmer), qm = case_mask(kmer);
+        uint64_t lo = n_upper_, hi = n_;
         while (lo < hi) {
             const uint64_t mid = lo + (hi - lo) / 2;
-            const int c = std::memcmp(kmer_ + 8 * mid, kmer, 8);
-            if (c == 0) return (int64_t)mid;
-            if (c < 0) lo = mid + 1; else hi = mid;
+            const uint64_t rf = folded(kmer_ + 8 * mid), rm = case_mask(kmer_ + 8 * mid);
+            if (rf == qf && rm == qm) return (int64_t)mid;
+            if (rf < qf || (rf == qf && rm < qm)) lo = mid + 1; else hi = mid;
         }
         return -1;
     }
+    uint64_t n_upper() const { return n_upper_; }
     StoredKmerData row(uint64_t i) const { return StoredKmerData{cols_[0][i], cols_[1][i], cols_[2][i], cols_[3][i], cols_[4][i]}; }
 
     template <class CB>
@@ -108,7 +124,7 @@ public:
     }
 
 private:
-    uint64_t n_ = 0;
+    uint64_t n_ = 0, n_upper_ = 0;          // rows; rows of the first section
     const char *kmer_ = nullptr;
     const uint16_t *cols_[5] = {};
     std::vector<uint64_t> bucket_;          // first row whose leading two bytes are >= the bucket's
@@ -118,12 +134,29 @@ private:
     static uint32_t bucket_of(const char *k) {
         return ((uint32_t)(unsigned char)k[0] << 8) | (uint32_t)(unsigned char)k[1];
     }
+    static uint64_t load8(const char *k) { uint64_t v; std::memcpy(&v, k, 8); return v; }
+    static uint64_t case_bits(const char *k) { return load8(k) & 0x2020202020202020ull; }
+    static uint64_t folded(const char *k) {                 // bytes with the case bit cleared, first residue most significant
+        return __builtin_bswap64(load8(k) & ~0x2020202020202020ull);
+    }
+    static uint64_t case_mask(const char *k) {              // bit j set iff residue j is lower case
+        uint64_t m = 0;
+        for (int j = 0; j < 8; ++j) m |= (uint64_t)(((unsigned char)k[j] >> 5) & 1u) << j;
+        return m;
+    }
     void attach(uint64_t n, const char *kmer, const uint16_t *a, const uint16_t *f, const uint16_t *m, const uint16_t *md, const uint16_t *v) {
         n_ = n; kmer_ = kmer;
         cols_[0] = a; cols_[1] = f; cols_[2] = m; cols_[3] = md; cols_[4] = v;
+        // the second section starts at the first row with a lower-case residue (a monotone predicate over the rows)
+        uint64_t lo = 0, hi = n;
+        while (lo < hi) {
+            const uint64_t mid = lo + (hi - lo) / 2;
+            if (case_bits(kmer + 8 * mid)) hi = mid; else lo = mid + 1;
+        }
+        n_upper_ = lo;
         bucket_.assign((1u << 16) + 1, 0);
-        // rows are sorted by bytes: count per leading 2-byte prefix, then prefix sums
-        for (uint64_t i = 0; i < n; ++i) ++bucket_[bucket_of(kmer + 8 * i) + 1];
+        // the first section is sorted by bytes: count per leading 2-byte prefix, then prefix sums
+        for (uint64_t i = 0; i < n_upper_; ++i) ++bucket_[bucket_of(kmer + 8 * i) + 1];
         for (size_t b = 1; b < bucket_.size(); ++b) bucket_[b] += bucket_[b - 1];
     }
 };

@@ -53,16 +53,23 @@ def join_communicator(builder, rank: int, world: int):
 
 
 def concat_tables(tables) -> KeptTable:
-    """Per-rank slices in rank order -> the whole kept table (counters are already job-wide)."""
+    """Per-rank slices in rank order -> the whole kept table (counters are already job-wide).  Every slice is in
+    table order (include/sigk.h): its rows without a lower-case residue first.  K-mer ranges are cut on the
+    case-folded k-mer and ascend with the rank, so the first sections in rank order followed by the second
+    sections in rank order are the whole table in table order."""
     t0 = tables[0]
-    cat = lambda name: np.concatenate([getattr(t, name) for t in tables])
+    ups = [t.n_upper for t in tables]
+
+    def cat(name):
+        return np.concatenate([getattr(t, name)[:u] for t, u in zip(tables, ups)] + [getattr(t, name)[u:] for t, u in zip(tables, ups)])
+
     return KeptTable(
-        kmer=np.concatenate([t.kmer for t in tables]).reshape(-1, 8),
+        kmer=cat("kmer").reshape(-1, 8),
         avg_from_end=cat("avg_from_end"), function_index=cat("function_index"), mean=cat("mean"),
         median=cat("median"), var=cat("var"),
         n_occurrences=t0.n_occurrences, n_distinct_kmers=t0.n_distinct_kmers,
         distinct_signatures=t0.distinct_signatures, num_seqs_with_a_signature=t0.num_seqs_with_a_signature,
-        distinct_functions=t0.distinct_functions, seqs_with_func=t0.seqs_with_func,
+        distinct_functions=t0.distinct_functions, seqs_with_func=t0.seqs_with_func, n_upper=sum(ups),
     )
 
 

@@ -38,14 +38,19 @@ def test_every_declared_symbol_is_exported(lib):
 def test_host_side_code_functions(lib):
     from signature_kmers_b200.builder import kmer_decode, kmer_encode
 
+    # group code = base-20 code of the case-folded residues << 8 | case mask (residue j = bit j)
     assert kmer_encode("AAAAAAAA") == 0
-    assert kmer_encode("yyyyyyyy") == 40 ** 8 - 1
+    assert kmer_encode("YYYYYYYY") == (20 ** 8 - 1) << 8
+    assert kmer_encode("yyyyyyyy") == ((20 ** 8 - 1) << 8) | 0xFF
+    assert kmer_encode("aAAAAAAA") == 1 and kmer_encode("AAAAAAAa") == 0x80
     assert kmer_encode("ACDEFGHX") == 2 ** 64 - 1
     for s in ("ACDEFGHI", "WYwyACac", "yyyyyyyA"):
         assert kmer_decode(kmer_encode(s)) == s
-    # integer order of codes == byte order of k-mers
-    ks = ["ACDEFGHI", "ACDEFGHi", "aCDEFGHI", "YYYYYYYY", "AAAAAAAC"]
-    assert sorted(ks) == sorted(ks, key=kmer_encode)
+    # table order (include/sigk.h) = ascending (case mask != 0, group code)
+    ks = ["ACDEFGHI", "ACDEFGHi", "aCDEFGHI", "YYYYYYYY", "AAAAAAAC", "yYYYYYYY", "AAAAAAAc"]
+    by_code = sorted(ks, key=lambda k: ((kmer_encode(k) & 0xFF) != 0, kmer_encode(k)))
+    assert by_code == sorted(ks, key=capi.table_order_key)
+    assert by_code[:3] == ["AAAAAAAC", "ACDEFGHI", "YYYYYYYY"]
 
 
 def test_no_cpu_fallback(lib):

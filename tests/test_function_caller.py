@@ -12,6 +12,7 @@ import pytest
 
 from oracle import call_oracle as co
 from tests.util import pack, random_proteins
+from signature_kmers_b200.capi import table_order_key
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "signature_kmers_b200")
@@ -43,7 +44,7 @@ class Table:
 
     def __init__(self, rows: dict):
         self.rows = rows
-        self.kmers = sorted(rows, key=lambda k: k.encode("latin-1"))
+        self.kmers = sorted(rows, key=table_order_key)          # the table order of include/sigk.h
         self.blob = "".join(self.kmers).encode("latin-1")
         cols = np.array([rows[k] for k in self.kmers], dtype=np.uint16).reshape(-1, 5)
         self.cols = [np.ascontiguousarray(cols[:, i]) for i in range(5)]

@@ -4,12 +4,13 @@ Run on the B200 box with `pytest -m gpu`."""
 import numpy as np
 import pytest
 
+from signature_kmers_b200 import capi
 from tests.util import assert_tables_equal, pack, random_proteins
 
 pytestmark = pytest.mark.gpu
 
 ALPHABET = "ACDEFGHIKLMNPQRSTVWYacdefghiklmnpqrstvwy"
-SYM = {ord(c): i for i, c in enumerate(ALPHABET)}
+SYM = {ord(c): i for i, c in enumerate(ALPHABET)}       # rank = SYM % 20, lower case = SYM >= 20
 
 
 @pytest.fixture(scope="module")
@@ -29,10 +30,12 @@ def encode_reference(seqs):
         for p in range(L - 7):
             w = s[p:p + 8]
             if all(c in SYM for c in w):
-                code = 0
-                for c in w:
-                    code = code * 40 + SYM[c]
-                codes.append(code)
+                # group code: base-20 code of the case-folded residues << 8 | case mask (residue j = bit j)
+                code, mask = 0, 0
+                for j, c in enumerate(w):
+                    code = code * 20 + SYM[c] % 20
+                    mask |= (SYM[c] >= 20) << j
+                codes.append((code << 8) | mask)
                 ords.append(i)
                 offs.append((L - p) & 0xFFFF)
     return np.array(codes, dtype=np.uint64), np.array(ords, dtype=np.uint32), np.array(offs, dtype=np.uint16)
@@ -117,9 +120,10 @@ def test_full_build_matches_oracle(gpu, oracle, seed, kw):
     got = gpu.build()
     want, _ = oracle.oracle_build(p)
     assert_tables_equal(got, want, tier_b=True, what=f"seed {seed}")
-    # rows are sorted by k-mer bytes and unique
+    # rows are in table order (include/sigk.h) and unique
     k = got.kmer_strings()
-    assert k == sorted(k) and len(set(k)) == len(k)
+    assert k == sorted(k, key=capi.table_order_key) and len(set(k)) == len(k)
+    assert got.n_upper == sum(1 for x in k if not any(c.islower() for c in x))
 
 
 def test_seq_id_collisions_and_gaps(gpu, oracle):

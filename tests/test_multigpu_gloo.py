@@ -1,9 +1,12 @@
 """World-size-2 (and 3) runs of the range-partitioned build on CPU over gloo.
 
 The GPU data path of csrc/comm.cu cannot run here, so each rank plays its part
-with numpy: encode its chunk of proteins, sample keys, agree on splitters,
-split stably by owner, exchange, and reduce its k-mer range in arrival order.
-The concatenation of the per-rank tables must equal the single-process oracle
+with numpy: encode its chunk of proteins, sample k-mers, agree on splitters
+(cut on the case-folded code, so a k-mer in any case pattern has one owner),
+split stably by owner, exchange, and reduce its k-mer range in arrival order;
+a rank's rows come in the table order of include/sigk.h (k-mers without a
+lower-case residue first).  The first sections of the per-rank tables in rank
+order followed by their second sections must equal the single-process oracle
 bit for bit, including the order-dependent median/var columns — that is the
 property the NCCL path relies on (rank r holds canonical chunk r; blocks arrive
 in source-rank order; the split is stable)."""
@@ -29,16 +32,19 @@ def encode(seqs, ordinal_base):
         for p in range(L - 7):
             w = s[p:p + 8]
             if all(c in SYM for c in w):
-                code = 0
-                for c in w:
-                    code = code * 40 + SYM[c]
-                recs.append((code, ordinal_base + i, (L - p) & 0xFFFF))
+                # group code = base-20 code of the case-folded residues << 8 | case mask (residue j = bit j)
+                code, mask = 0, 0
+                for j, c in enumerate(w):
+                    code = code * 20 + SYM[c] % 20
+                    mask |= (SYM[c] >= 20) << j
+                recs.append(((code << 8) | mask, ordinal_base + i, (L - p) & 0xFFFF))
     return recs
 
 
 def reduce_records(recs, funcs, lens, sids):
     """process_kmer_set over records already grouped by arrival order (stable sort by code)."""
-    recs = sorted(recs, key=lambda r: r[0])          # Python's sort is stable
+    # the main run (case mask 0) sorted on the code, then the side run sorted on code and mask; Python's sort is stable
+    recs = sorted(recs, key=lambda r: ((r[0] & 0xFF) != 0, r[0]))
     rows, i = [], 0
     sig = set()
     while i < len(recs):
@@ -70,12 +76,12 @@ def worker(rank, world, port, seqs, funcs, out):
     lo, hi = rank_slice(len(seqs), rank, world)
     recs = encode(seqs[lo:hi], lo)
     # splitters from evenly spaced samples, identical on every rank
-    samp = [recs[k * len(recs) // 64][0] for k in range(64)] if recs else [40 ** 8] * 64
+    samp = [recs[k * len(recs) // 64][0] >> 8 for k in range(64)] if recs else [20 ** 8] * 64     # case-folded codes
     allsamp = [None] * world
     dist.all_gather_object(allsamp, samp)
     flat = sorted(x for s in allsamp for x in s)
     split = [flat[(k + 1) * 64] for k in range(world - 1)]
-    owner = lambda code: sum(code >= s for s in split)
+    owner = lambda gcode: sum((gcode >> 8) >= s for s in split)
     outgoing = [[r for r in recs if owner(r[0]) == d] for d in range(world)]      # stable split
     incoming = [None] * world
     for d in range(world):                                                         # the all-to-all
@@ -109,21 +115,22 @@ def test_range_partitioned_build_matches_oracle(world, seed):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    rows = [r for part in gathered for r in part[0]]            # rank order == k-mer order
+    # first sections (case mask 0) in rank order, then second sections in rank order == table order
+    rows = [r for part in gathered for r in part[0] if not r[0] & 0xFF] + [r for part in gathered for r in part[0] if r[0] & 0xFF]
     sig = set(x for part in gathered for x in part[1])
     want, stats = oracle_py.build(seqs, funcs)
     alphabet = "ACDEFGHIKLMNPQRSTVWYacdefghiklmnpqrstvwy"
 
-    def decode(code):
-        s = ""
-        for _ in range(8):
-            s = alphabet[code % 40] + s
-            code //= 40
+    def decode(gcode):
+        code, mask, s = gcode >> 8, gcode & 0xFF, ""
+        for j in range(7, -1, -1):
+            s = alphabet[code % 20 + (20 if (mask >> j) & 1 else 0)] + s
+            code //= 20
         return s.encode()
 
     got = [(decode(r[0]),) + tuple(r[1:]) for r in rows]
     assert got == want
-    assert [r[0] for r in rows] == sorted(r[0] for r in rows)
+    assert [r[0] for r in rows] == sorted((r[0] for r in rows), key=lambda g: ((g & 0xFF) != 0, g))
     assert len(sig) == stats["num_seqs_with_a_signature"]
     assert sum(part[2] for part in gathered) == stats["n_occurrences"]
     assert all(len(part[0]) > 0 for part in gathered), "every rank owns part of the k-mer space"

@@ -81,7 +81,7 @@ def test_k3_ambiguity_kills_covering_windows(oracle, bad):
 def test_k3_case_is_preserved(oracle):
     t = both(oracle, ["ACDEFGHI", "acdefghi", "ACDEFGHi"], [0, 0, 0])
     assert sorted(t.kmer_strings()) == ["ACDEFGHI", "ACDEFGHi", "acdefghi"]
-    # rows are in unsigned byte order: upper case before lower case
+    # table order: the all-upper-case k-mer first, then (case-folded bytes equal) by case mask, residue j = bit j
     assert t.kmer_strings() == ["ACDEFGHI", "ACDEFGHi", "acdefghi"]
 
 

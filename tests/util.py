@@ -60,3 +60,12 @@ def assert_tables_equal(a: KeptTable, b: KeptTable, tier_b: bool = True, what: s
     if tier_b:
         np.testing.assert_array_equal(a.median, b.median, err_msg=what)
         np.testing.assert_array_equal(a.var, b.var, err_msg=what)
+
+
+def reorder_to_table_order(kmers, cols):
+    """(list of k-mer strings, list of per-row arrays) in any order -> the same rows in the table order of include/sigk.h."""
+    from signature_kmers_b200.capi import table_order_key
+
+    order = sorted(range(len(kmers)), key=lambda i: table_order_key(kmers[i]))
+    idx = np.array(order, dtype=np.int64)
+    return [kmers[i] for i in order], [np.asarray(c)[idx] if len(order) else np.asarray(c) for c in cols]
