@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """bench.py — k-mer occurrences/s into the kept-signature table on B200.
 
-A step is one pass of the signature-generation hot path (encode -> onesweep
-radix sort -> segment reduce -> keep/compact; the reference's extract_kmers +
-process_kmers, src/signature_build.tcc:47-293) over one synthetic protein set.
+A step is one pass of the signature-generation hot path (window count -> encode
+fused with the first radix pass -> onesweep passes -> segment reduce ->
+keep/compact; the reference's extract_kmers + process_kmers,
+src/signature_build.tcc:47-293) over one synthetic protein set.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config2]
   python bench.py --impl reference ...     # the CPU path, timed on the host cores
@@ -131,13 +132,21 @@ def pinned_copy(builder, a: np.ndarray) -> np.ndarray:
     return out
 
 
-def algorithmic_bytes_per_occurrence(passes: int) -> dict:
-    """B_alg = 1 + Kb + (2P + 2) R with this build's R, Kb, P."""
-    enc = 1 + RECORD_BYTES
-    hist = KEY_BYTES
-    sort = 2 * RECORD_BYTES * passes
+def algorithmic_bytes_per_occurrence(passes: int, fused: bool) -> dict:
+    """B_alg = 1 + Kb + (2P + 2) R with this build's R, Kb, P — only the passes executed and the
+    one histogram read.  Fused (one GPU): the histogram is a second read of the residues (1 B instead of Kb) and
+    the first pass reads residues instead of records, so the encode's write is the first pass's write:
+    1 (count) + 1 + R (encode + first pass) + 2 R (P - 1) + R (reduce)."""
+    if fused:
+        enc = 1 + RECORD_BYTES
+        hist = 1
+        sort = 2 * RECORD_BYTES * (passes - 1)
+    else:
+        enc = 1 + RECORD_BYTES
+        hist = KEY_BYTES
+        sort = 2 * RECORD_BYTES * passes
     red = RECORD_BYTES
-    return dict(encode=enc, histogram=hist, sort=sort, reduce=red, total=enc + hist + sort + red)
+    return dict(encode_and_first_pass=enc, histogram=hist, sort=sort, reduce=red, total=enc + hist + sort + red)
 
 
 def cpu_baseline(proteins, sample_proteins: int, threads: int):
@@ -235,22 +244,27 @@ def run_gpu(args, rank, world, local_rank):
     h2d = proteins.residues.nbytes + proteins.starts.nbytes + proteins.function_index.nbytes + proteins.seq_id.nbytes
     d2h = counts["n_kept"] * 18 + 2 * 65536 * 4 + 96
     clk = clocks.stop()
+    tm_e2e = builder.timings()            # copies of the last end-to-end build: steady state (pinned buffers already sized)
 
     passes = int(tm["sort_passes"])
+    fused = os.environ.get("SIGK_NO_FUSED") is None
     pass_ms = [x for x in tm["pass_ms"][:passes]]
+    # the dominant kernel: the plain onesweep passes (3 launches per build; the first pass is the fused kernel)
+    plain_ms = pass_ms[1:] if fused and passes > 1 else pass_ms
     peak, peak_src = measured_peak_gbs()
     alg_bytes_per_launch = 2 * RECORD_BYTES * occ
-    mean_pass_ms = sum(pass_ms) / max(1, len(pass_ms))
+    mean_pass_ms = sum(plain_ms) / max(1, len(plain_ms))
     achieved = alg_bytes_per_launch / (mean_pass_ms * 1e-3) / 1e9 if mean_pass_ms > 0 else 0.0
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "onesweep_traffic.json")) as f:
             tj = json.load(f)
         if tj.get("workload") == args.workload:
             traffic = tj.get("dram_bytes_per_launch")
+            traffic_src = "constant from profiles/ (%s): ncu --set full of this command, not this run" % tj.get("source", "onesweep_traffic.json")
     except Exception:
         pass
-    balg = algorithmic_bytes_per_occurrence(passes)
+    balg = algorithmic_bytes_per_occurrence(passes, fused)
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -266,20 +280,25 @@ def run_gpu(args, rank, world, local_rank):
         "config": {
             "workload": args.workload, **{k: v for k, v in CONFIGS[args.workload].items()},
             "occurrences_per_step": occ, "distinct_kmers": counts["n_distinct_kmers"], "kept_kmers": counts["n_kept"],
-            "K": 8, "record_bytes": RECORD_BYTES, "sort_passes": passes,
+            "K": 8, "record_bytes": RECORD_BYTES, "sort_passes": passes, "first_pass_fused_with_encode": fused,
             "l2": "inputs larger than L2 (residues %.0f MB, records %.1f GB per step)" % (proteins.residues.nbytes / 1e6, occ * RECORD_BYTES / 1e9),
-            "timed": "encode + histogram + onesweep passes + segment reduce + keep/compact (CUDA events on the library stream)",
+            "timed": "window count + encode/first pass + onesweep passes + segment reduce + keep/compact (CUDA events on the library stream)",
         },
         "clocks": clk,
         "e2e": {"value": occ / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * e2e_s, "api": "sigk_build (C ABI, pinned host buffers)"},
         "gpu_launches": int(tm["kernel_launches"]) * args.steps,
         "roofline": {"bound": "hbm", "kernel": "onesweep_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes_per_launch, "launch_ms": mean_pass_ms, "pass_ms": pass_ms},
+                     "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes_per_launch, "launch_ms": mean_pass_ms, "launches_per_step": len(plain_ms),
+                     "pass_ms": pass_ms,
+                     "first_pass": {"kernel": "encode_sort_kernel" if fused else "onesweep_pass_kernel<FIRST>", "ms": pass_ms[0] if pass_ms else None,
+                                    "algorithmic_bytes_per_launch": (1 + RECORD_BYTES if fused else 2 * RECORD_BYTES) * occ,
+                                    "achieved": ((1 + RECORD_BYTES if fused else 2 * RECORD_BYTES) * occ / (pass_ms[0] * 1e-3) / 1e9) if pass_ms and pass_ms[0] > 0 else None}},
         "pipeline": {"b_alg_per_occurrence": balg, "achieved_gbs": balg["total"] * occ / (ms_per_step * 1e-3) / 1e9,
                      "frac_of_peak": balg["total"] * occ / (ms_per_step * 1e-3) / 1e9 / peak,
-                     "stage_ms": {k: tm[k] for k in ("encode_ms", "histogram_ms", "sort_ms", "reduce_ms", "order_stats_ms", "squeeze_ms", "device_total_ms", "h2d_ms", "d2h_ms")}},
+                     "stage_ms": {**{k: tm[k] for k in ("encode_ms", "count_ms", "histogram_ms", "sort_ms", "side_sort_ms", "reduce_ms", "order_stats_ms", "squeeze_ms", "device_total_ms")},
+                                  "h2d_ms": tm_e2e["h2d_ms"], "d2h_ms": tm_e2e["d2h_ms"]}},
         "cpu_baseline": cpu,
     }
     emit_json(line)

@@ -447,7 +447,9 @@ int comm_encode_exchange(sigk_handle *h, const EncodeArgs &ea, SortSegments *seg
         const uint64_t stride = peer ? c->land_stride
                                      : std::max<uint64_t>((cap_local / W + cap_local / (4 * W) + 65536 + 63) & ~63ull, c->min_stride);
         if (!peer) { CU(h, h->d_keys[1].reserve((size_t)stride * W)); CU(h, h->d_vals[1].reserve((size_t)stride * W)); }
-        const size_t state_words = (size_t)encode_slices(h->total_res) * W + W;
+        // SIGK_SPLIT_KERNEL=warp: the round-1 kernel (one run per owner and 512-position warp slice), kept for comparison
+        const bool by_tile = !(std::getenv("SIGK_SPLIT_KERNEL") && !std::strcmp(std::getenv("SIGK_SPLIT_KERNEL"), "warp"));
+        const size_t state_words = by_tile ? (size_t)encode_route_state_words(h->total_res) : (size_t)encode_slices(h->total_res) * W + W;
         CU(h, c->d_owner_state.reserve(state_words));
         CU(h, cudaMemsetAsync(c->d_owner_state.p, 0, state_words * sizeof(uint64_t), st));
         CU(h, cudaMemsetAsync(totals, 0, (W + 1) * sizeof(uint64_t), st));
@@ -458,7 +460,9 @@ int comm_encode_exchange(sigk_handle *h, const EncodeArgs &ea, SortSegments *seg
             sp.dst_keys[d] = peer ? c->peer_keys[d] + (size_t)c->rank * stride : h->d_keys[1].p + (size_t)d * stride;
             sp.dst_vals[d] = peer ? c->peer_vals[d] + (size_t)c->rank * stride : h->d_vals[1].p + (size_t)d * stride;
         }
-        CU(h, launch_encode_split(ea, sp, sc->ticket + TK_ENCODE, st)); ++*launches;
+        if (by_tile) CU(h, launch_encode_route(ea, sp, sc->ticket + TK_ENCODE, h->sm_count, st));
+        else CU(h, launch_encode_split(ea, sp, sc->ticket + TK_ENCODE, st));
+        ++*launches;
         CU(h, cudaEventRecord(h->ev[EV_ENCODE], st));
         // W totals + overflow word from every rank; completes only when every rank's kernel (and its peer stores) has
         NC(h, g_nccl.AllGather(totals, c->d_counts.p, W + 1, ncclUint64, c->comm, st));
@@ -526,6 +530,7 @@ int comm_encode_exchange(sigk_handle *h, const EncodeArgs &ea, SortSegments *seg
             seg->keys[0] = h->d_keys[0].p; seg->vals[0] = h->d_vals[0].p;
             *first_out = 1;
         }
+        h->exchange_bytes_out = 12ull * (local - cnt[(size_t)c->rank * W + c->rank]);
         return publish_counts(h, local, n_recv);
     }
 }

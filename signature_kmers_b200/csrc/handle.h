@@ -116,6 +116,7 @@ struct sigk_handle {
     uint64_t n_prot_global = 0;         // proteins of the whole job
     uint64_t ordinal_base = 0;          // ordinal of this rank's first protein
     uint64_t n_recv = 0;                // records this rank owns after the exchange
+    uint64_t exchange_bytes_out = 0;    // bytes of records this rank sent to other ranks in the last build
     uint32_t upload_launches = 0;       // kernels sigk_upload launched (per-protein table, splitters)
 
     int fail(int code, const char *fmt, ...) {

@@ -51,6 +51,10 @@ struct EncodeSplitArgs {
     uint32_t *dst_vals[16];
 };
 cudaError_t launch_encode_split(const EncodeArgs &a, const EncodeSplitArgs &sp, uint32_t *ticket, cudaStream_t stream);
+// The same contract on the tile machinery of the sort (onesweep.cu): one ~900-record run per owner and tile instead of one
+// 64-record run per owner and warp slice.  owner_state: encode_route_state_words() zeroed u64 words.
+inline uint64_t encode_route_state_words(uint64_t total_res);
+cudaError_t launch_encode_route(const EncodeArgs &a, const EncodeSplitArgs &sp, uint32_t *ticket, int sm_count, cudaStream_t stream);
 
 // ---- stage 2: onesweep LSD radix sort (onesweep.cu) ------------------------
 constexpr int SORT_MAX_PASSES = 8;
@@ -82,6 +86,7 @@ constexpr int ES_ITEMS = ES_TILE / OS_THREADS;
 static_assert(ES_ITEMS * OS_THREADS == ES_TILE && ES_ITEMS <= OS_ITEMS, "fused tile shape");
 inline uint64_t onesweep_tiles(uint64_t capacity) { return (capacity + OS_TILE - 1) / OS_TILE; }
 inline uint64_t encode_sort_tiles(uint64_t total_res) { return (total_res + ES_TILE - 1) / ES_TILE; }
+inline uint64_t encode_route_state_words(uint64_t total_res) { return (encode_sort_tiles(total_res) + 1) * 32; }
 // bytes of look-back state one pass needs for `capacity` records (either kind of tile)
 size_t onesweep_lookback_bytes(uint64_t capacity);
 

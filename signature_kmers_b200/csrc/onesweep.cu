@@ -66,6 +66,12 @@ constexpr uint64_t PAD_KEY = ~0ull;                  // never a record: the low 
 #ifndef SIGK_OS_BACKOFF_NS
 #define SIGK_OS_BACKOFF_NS 0                         // __nanosleep between polls of a look-back word that is not ready
 #endif
+#ifndef SIGK_OS_LBW
+#define SIGK_OS_LBW 1                                // predecessors whose look-back words are requested per round trip
+#endif
+#ifndef SIGK_OS_PIPELINE
+#define SIGK_OS_PIPELINE 0                           // 1: request the next tile's keys before the write-out (measured: 11 ms per pass in situ against 4.4 ms — off)
+#endif
 #ifndef SIGK_OS_PERSISTENT
 #define SIGK_OS_PERSISTENT 1                         // 1: a resident grid loops over tickets; 0: one CTA per tile
 #endif
@@ -95,7 +101,7 @@ struct OsSmem {
     uint32_t cnt[OS_WARPS][SIGK_BINS / 2];
     uint32_t scan[OS_WARPS + 2];
     uint32_t wtotal[OS_WARPS];
-    uint32_t tile;
+    uint32_t tile, next_tile;
     int8_t sym[256];
 };
 using PassSmem = OsSmem<OS_TILE>;
@@ -133,6 +139,7 @@ template <typename SM>
 SIGK_D void os_zero_counters(SM &sm) {
     uint32_t *c32 = &sm.cnt[0][0];
     for (uint32_t j = threadIdx.x; j < OS_WARPS * (SIGK_BINS / 2); j += OS_THREADS) c32[j] = 0;
+
 }
 
 // Everything after the keys of a tile sit in registers (warp-striped: item i of lane l of warp w is tile record
@@ -140,10 +147,13 @@ SIGK_D void os_zero_counters(SM &sm) {
 // The counters must be zero and visible (a barrier after os_zero_counters).
 // val_at(r) = value of tile record r.  VALS_STAGED: val_at reads the staging that the sorted values are about to
 // overwrite (fused kernel), so everybody reads before anybody writes.
-template <typename LB, bool FIRST, bool VALS_STAGED, int ITEMS, typename SM, typename ValFn>
+// before_write_out() runs in every thread after the last barrier before the write-out, when the key registers and the
+// digit counters are dead: the persistent pass kernel zeroes the counters there and starts loading its next tile.
+template <typename LB, bool FIRST, bool VALS_STAGED, int ITEMS, typename SM, typename ValFn, typename MidFn>
 SIGK_D void os_sort_tile(SM &sm, uint64_t (&key)[ITEMS], uint32_t tile, uint32_t tile_n, int bit_lo, uint32_t digit_mask,
                          const uint64_t *__restrict__ bin_base, LB *__restrict__ lookback, ValFn &&val_at,
-                         uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out) {
+                         uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t *__restrict__ next_ticket,
+                         MidFn &&before_write_out) {
     using T = LBTraits<LB>;
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
@@ -155,6 +165,7 @@ SIGK_D void os_sort_tile(SM &sm, uint64_t (&key)[ITEMS], uint32_t tile, uint32_t
     // group's first lane bumps the warp's counter with one shared-memory atomic whose return value is the
     // group's base; everyone takes base + (peers below me).  Stable.  The atomics of a chunk of items are
     // issued back to back so that their latencies overlap.
+    const bool owner = tid * OS_DPT < SIGK_RADIX;
     uint32_t rank2[(ITEMS + 1) / 2];                    // two 16-bit ranks (later: tile slots) to a register
 #pragma unroll
     for (int i = 0; i < (ITEMS + 1) / 2; ++i) rank2[i] = 0;
@@ -178,7 +189,6 @@ SIGK_D void os_sort_tile(SM &sm, uint64_t (&key)[ITEMS], uint32_t tile, uint32_t
     // ---- per digit: exclusive prefix over warps, tile count, publish.  Thread t owns the OS_DPT digits
     // t * OS_DPT ..: one 16-bit counter per warp with 512 threads, one 32-bit word of two with 256.  In a FIRST
     // pass thread 0 also owns the side bin and the padding bin (which is never published).
-    const bool owner = tid * OS_DPT < SIGK_RADIX;
     uint32_t my_count[OS_DPT], my_sum = 0;
 #pragma unroll
     for (int k = 0; k < OS_DPT; ++k) my_count[k] = 0;
@@ -234,17 +244,31 @@ SIGK_D void os_sort_tile(SM &sm, uint64_t (&key)[ITEMS], uint32_t tile, uint32_t
         }
     }
     // ---- look back over the tiles before this one: per digit, add aggregates until an inclusive prefix turns up
+    // The words of SIGK_OS_LBW predecessors are requested together: a walk of h tiles costs about h / LBW round trips
+    // to L2 instead of h (the profile of the one-at-a-time walk: ~30 hops per tile, a quarter of all stall samples).
     auto look_back_digit = [&](uint32_t d, uint32_t cnt, uint32_t base) {
         LB excl = 0;
         if (tile > 0) {
             int64_t t = (int64_t)tile - 1;
             for (;;) {
-                const LB v = T::ld(lookback + (size_t)t * SIGK_BINS + d);
-                const LB flag = v >> T::SHIFT;
-                if (flag == 0) { if (SIGK_OS_BACKOFF_NS) __nanosleep(SIGK_OS_BACKOFF_NS); continue; }
-                excl += v & T::VAL;
-                if (flag == 2) break;
-                --t;
+                LB v[SIGK_OS_LBW];
+#pragma unroll
+                for (int k = 0; k < SIGK_OS_LBW; ++k)
+                    v[k] = t - k >= 0 ? T::ld(lookback + (size_t)(t - k) * SIGK_BINS + d) : T::PRE;      // before tile 0: prefix 0
+                bool done = false;
+                int adv = 0;
+#pragma unroll
+                for (int k = 0; k < SIGK_OS_LBW; ++k) {
+                    const LB flag = v[k] >> T::SHIFT;
+                    if (!done && adv == k && flag != 0) {                   // everything nearer has been added
+                        excl += v[k] & T::VAL;
+                        adv = k + 1;
+                        done = flag == 2;
+                    }
+                }
+                if (done) break;
+                if (adv == 0 && SIGK_OS_BACKOFF_NS) __nanosleep(SIGK_OS_BACKOFF_NS);
+                t -= adv;                                                   // go on from the first word that was not ready
             }
             T::st(lookback + (size_t)tile * SIGK_BINS + d, T::PRE | (excl + (LB)cnt));
         }
@@ -258,6 +282,9 @@ SIGK_D void os_sort_tile(SM &sm, uint64_t (&key)[ITEMS], uint32_t tile, uint32_t
         }
         if (FIRST && tid == 0) look_back_digit(SIGK_SIDE_BIN, side_count, total_main);
     };
+    // The ticket of the CTA's next tile, taken as late as it can be for its keys to be requested before the write-out:
+    // a tile's aggregate is published a ranking after its ticket, and every later tile's look-back waits for it.
+    if (next_ticket && tid == 0) sm.next_tile = atomicAdd(next_ticket, 1u);
     if (!SIGK_OS_LATE_LOOKBACK) look_back();
     __syncthreads();
 
@@ -294,6 +321,7 @@ SIGK_D void os_sort_tile(SM &sm, uint64_t (&key)[ITEMS], uint32_t tile, uint32_t
 
     if (SIGK_OS_LATE_LOOKBACK) look_back();
     __syncthreads();
+    before_write_out();
 
     // ---- coalesced write-out: consecutive slots of one digit are consecutive in HBM
     for (uint32_t j = tid; j < tile_n; j += OS_THREADS) {
@@ -327,6 +355,54 @@ onesweep_pass_kernel(const __grid_constant__ SortSegments seg, const uint64_t *_
     const uint64_t n = FIRST ? (n_ptr ? *n_ptr : seg.start[seg.n]) : *n_ptr;
     const uint64_t off = (!FIRST && off_ptr) ? *off_ptr : 0ull;      // the run's place in the in / out buffers
     const uint32_t wbase = warp * (OS_ITEMS * 32);
+    if (!FIRST && SIGK_OS_PIPELINE) {
+        // ---- the plain pass, software-pipelined over the tiles of a persistent CTA: the ticket of the next tile is taken
+        // while this one is ranked, and its keys are requested before this tile's write-out (the key registers are dead
+        // by then), so their latency hides behind the write-out instead of standing in front of the ranking
+        uint64_t key[OS_ITEMS];
+        auto load_keys = [&](uint32_t t) {
+            const uint64_t t0 = (uint64_t)t * OS_TILE;
+            const uint32_t tn = (uint32_t)((n - t0) < (uint64_t)OS_TILE ? (n - t0) : (uint64_t)OS_TILE);
+            // Padding of the last tile gets key ~0: it ranks after every real record of the top digit and is never written.
+#pragma unroll
+            for (int i = 0; i < OS_ITEMS; ++i) {
+                const uint32_t idx = wbase + i * 32 + lane;
+                key[i] = idx < tn ? ld_stream_u64(keys_in + off + t0 + idx) : PAD_KEY;
+            }
+        };
+        if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+        os_zero_counters(sm);
+        __syncthreads();
+        uint32_t tile = sm.tile;
+        if ((uint64_t)tile * OS_TILE >= n) return;
+        load_keys(tile);
+        for (;;) {
+            const uint64_t tile_start = (uint64_t)tile * OS_TILE;
+            const uint32_t tile_n = (uint32_t)((n - tile_start) < (uint64_t)OS_TILE ? (n - tile_start) : (uint64_t)OS_TILE);
+            if (tid == 0) {
+                if (!SIGK_OS_PERSISTENT) sm.next_tile = 0xFFFFFFFFu;
+#if SIGK_OS_PREFETCH
+                // L2 prefetch of the tile one wave ahead (gridDim.x CTAs are resident)
+                const uint64_t ahead = tile_start + (uint64_t)gridDim.x * OS_TILE;
+                if (ahead + OS_TILE <= n && (((uintptr_t)(keys_in + off + ahead) | (uintptr_t)(vals_in + off + ahead)) & 15u) == 0) {
+                    prefetch_l2(keys_in + off + ahead, OS_TILE * sizeof(uint64_t));
+                    prefetch_l2(vals_in + off + ahead, OS_TILE * sizeof(uint32_t));
+                }
+#endif
+            }
+            uint32_t next = 0xFFFFFFFFu;
+            os_sort_tile<LB, false, false, OS_ITEMS>(sm, key, tile, tile_n, bit_lo, digit_mask, bin_base, lookback,
+                                                     [&](uint32_t r) { return ld_stream_u32(vals_in + off + tile_start + r); },
+                                                     keys_out + off, vals_out + off, SIGK_OS_PERSISTENT ? ticket : nullptr, [&]() {
+                                                         next = sm.next_tile;
+                                                         os_zero_counters(sm);
+                                                         if ((uint64_t)next * OS_TILE < n) load_keys(next);
+                                                     });
+            __syncthreads();                                // the write-out is done with the staging; the counters are zero
+            if ((uint64_t)next * OS_TILE >= n) return;
+            tile = next;
+        }
+    }
     for (;;) {
         __syncthreads();                                    // the previous tile's write-out is done with the staging
         if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
@@ -336,13 +412,11 @@ onesweep_pass_kernel(const __grid_constant__ SortSegments seg, const uint64_t *_
         const uint64_t tile_start = (uint64_t)tile * OS_TILE;
         if (tile_start >= n) return;
         const uint32_t tile_n = (uint32_t)((n - tile_start) < (uint64_t)OS_TILE ? (n - tile_start) : (uint64_t)OS_TILE);
-
-        // ---- load keys, warp-striped: item i of lane l is record wbase + 32 i + l.
         uint64_t key[OS_ITEMS];
         if (!FIRST) {
 #if SIGK_OS_PREFETCH
             if (tid == 0) {
-                // the tile one wave ahead (gridDim.x CTAs are resident)
+                // L2 prefetch of the tile one wave ahead (gridDim.x CTAs are resident)
                 const uint64_t ahead = tile_start + (uint64_t)gridDim.x * OS_TILE;
                 if (ahead + OS_TILE <= n && (((uintptr_t)(keys_in + off + ahead) | (uintptr_t)(vals_in + off + ahead)) & 15u) == 0) {
                     prefetch_l2(keys_in + off + ahead, OS_TILE * sizeof(uint64_t));
@@ -358,7 +432,7 @@ onesweep_pass_kernel(const __grid_constant__ SortSegments seg, const uint64_t *_
             }
             os_sort_tile<LB, false, false, OS_ITEMS>(sm, key, tile, tile_n, bit_lo, digit_mask, bin_base, lookback,
                                                      [&](uint32_t r) { return ld_stream_u32(vals_in + off + tile_start + r); },
-                                                     keys_out + off, vals_out + off);
+                                                     keys_out + off, vals_out + off, nullptr, []() {});
         } else {
             // the regions of the first pass, read in place: region s holds records start[s] .. start[s+1]
             int s0 = 0;
@@ -384,7 +458,7 @@ onesweep_pass_kernel(const __grid_constant__ SortSegments seg, const uint64_t *_
                                                         const uint64_t g = tile_start + idx;
                                                         const int r = region_of(g);
                                                         return ld_stream_u32(seg.vals[r] + (g - seg.start[r]));
-                                                    }, keys_out, vals_out);
+                                                    }, keys_out, vals_out, nullptr, []() {});
         }
     }
 }
@@ -452,7 +526,181 @@ encode_sort_kernel(EncodeArgs a, uint64_t *__restrict__ keys_out, uint32_t *__re
             key[i] = idx < tile_n ? sm.keys[stage_slot(idx)] : PAD_KEY;
         }
         os_sort_tile<LB, true, true, ES_ITEMS>(sm, key, tile, tile_n, bit_lo, digit_mask, bin_base, lookback,
-                                               [&](uint32_t idx) { return sm.vals[stage_slot(idx)]; }, keys_out, vals_out);
+                                               [&](uint32_t idx) { return sm.vals[stage_slot(idx)]; }, keys_out, vals_out, nullptr, []() {});
+    }
+}
+
+// ---- encode and route (multi-GPU) ----------------------------------------------------------------------------
+// The same tile machinery with the OWNER of a record's k-mer range as the digit: the valid windows of 14 slices are
+// compacted in canonical order, ranked by owner (the owner rides in the five spare low bits of the staged key, so it
+// is computed once), reordered in shared memory and written as one contiguous run per owner — ~900 records, 7 KB of
+// keys — straight into region `this rank` of the owner's landing zone (peer memory over NVLink), or into a local
+// send region.  A run's place in its region is a chained scan per owner over the tiles, in ticket = canonical order,
+// so every region holds its records in insertion order.  (The round-1 kernel routed per 512-position warp slice:
+// 64-record runs, eight times the scan entries, ~485 GB/s of NVLink egress.)
+constexpr uint32_t RT_BINS = 32;                    // owners 0..15, 31 = rows of the tile that hold no record
+
+__global__ void __launch_bounds__(OS_THREADS, OS_MIN_BLOCKS)
+encode_route_kernel(EncodeArgs a, const __grid_constant__ EncodeSplitArgs sp, uint32_t *__restrict__ ticket, uint32_t n_tiles) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FusedSmem &sm = *reinterpret_cast<FusedSmem *>(smem_raw);
+    __shared__ uint64_t s_split[16];
+    __shared__ uint64_t *s_dkeys[16];
+    __shared__ uint32_t *s_dvals[16];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t W = (uint32_t)sp.n_split + 1u;
+    ws_fill_symbols(sm.sym);
+    if (tid < (unsigned)sp.n_split) s_split[tid] = sp.split_codes[tid];
+    if (tid < 16) { s_dkeys[tid] = sp.dst_keys[tid]; s_dvals[tid] = sp.dst_vals[tid]; }
+    const uint32_t wbase = warp * (ES_ITEMS * 32);
+    uint16_t *wcnt16 = reinterpret_cast<uint16_t *>(sm.cnt[warp]);
+    for (;;) {
+        __syncthreads();                                    // the previous tile's write-out is done with the staging
+        if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+        if (tid < OS_WARPS * (RT_BINS / 2)) sm.cnt[tid / (RT_BINS / 2)][tid % (RT_BINS / 2)] = 0;
+        __syncthreads();
+        const uint32_t tile = sm.tile;
+        if (tile >= n_tiles) return;
+        const bool last_tile = tile + 1 == n_tiles;
+
+        // ---- window loop, part 1: which windows are valid, how many per slice
+        const uint32_t sub = tile * ES_WARPS + warp;
+        const bool enc = warp < ES_WARPS && (uint64_t)sub * WS_SUB < a.total_res;
+        WindowLane w;
+        uint32_t valid = 0, incl = 0, mine = 0;
+        if (enc) {
+            ws_load(a, sm.sym, sub, w);
+            valid = ws_valid_mask(a, w);
+            mine = incl = (uint32_t)__popc(valid);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (unsigned)o) incl += y;
+            }
+        }
+        if (lane == 31) sm.wtotal[warp] = incl;             // 0 for warps without a slice
+        __syncthreads();
+        uint32_t before = 0, tile_n = 0;
+#pragma unroll
+        for (int q = 0; q < ES_WARPS; ++q) {
+            const uint32_t c = sm.wtotal[q];
+            before += q < (int)warp ? c : 0u;
+            tile_n += c;
+        }
+        // ---- part 2: the records, compacted in canonical order; the owner (number of splitter codes <= the record's
+        // case-folded code) goes into the key's spare low bits
+        if (enc) {
+            uint32_t o = before + incl - mine;
+            uint32_t run_i = 0, run_c = 0;              // occurrences of the protein I am inside
+            ws_for_each(a, w, valid, [&](int, uint64_t key, uint32_t i) {
+                const uint64_t code = sigk_key_code35(key);
+                uint32_t d = 0;
+                for (int k = 0; k < sp.n_split; ++k) d += code >= s_split[k] ? 1u : 0u;
+                const uint32_t slot = stage_slot(o++);
+                sm.keys[slot] = key | d;
+                sm.vals[slot] = a.ordinal_base + i;
+                if (i != run_i) {
+                    if (run_c && a.prot_windows) atomicAdd(a.prot_windows + run_i, run_c);
+                    run_i = i; run_c = 0;
+                }
+                ++run_c;
+            });
+            if (run_c && a.prot_windows) atomicAdd(a.prot_windows + run_i, run_c);
+        }
+        __syncthreads();
+        uint64_t key[ES_ITEMS];
+#pragma unroll
+        for (int i = 0; i < ES_ITEMS; ++i) {
+            const uint32_t idx = wbase + i * 32 + lane;
+            key[i] = idx < tile_n ? sm.keys[stage_slot(idx)] : PAD_KEY;         // the low bits of PAD_KEY: bin 31, behind every owner
+        }
+        // ---- rank by owner inside the warp (five ballots), as in os_sort_tile
+        uint32_t rank2[(ES_ITEMS + 1) / 2];
+#pragma unroll
+        for (int i = 0; i < (ES_ITEMS + 1) / 2; ++i) rank2[i] = 0;
+#pragma unroll
+        for (int i = 0; i < ES_ITEMS; ++i) {
+            const uint32_t d = (uint32_t)key[i] & (RT_BINS - 1);
+            unsigned peers = 0xffffffffu;
+#pragma unroll
+            for (int b = 0; b < 5; ++b) peers_step(peers, d, 1u << b);
+            const uint32_t below = (uint32_t)__popc(peers & lt);
+            const uint32_t old = wcnt16[d];
+            if (below == 0) wcnt16[d] = (uint16_t)(old + (uint32_t)__popc(peers));
+            SIGK_RANK_SET(i, old + below);
+            __syncwarp();
+        }
+        __syncthreads();
+        // ---- warp 0, lane d = owner d: tile count, chained scan over the tiles, the run's place in the owner's region
+        if (warp == 0) {
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int q = 0; q < OS_WARPS; ++q) cnt += reinterpret_cast<const uint16_t *>(sm.cnt[q])[lane];
+            uint64_t *state = sp.owner_state + (size_t)tile * RT_BINS + lane;
+            if (lane < W) st_volatile_u64(state, (tile == 0 ? SIGK_CS_PRE : SIGK_CS_AGG) | (uint64_t)cnt);
+            uint32_t incl_d = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl_d, o);
+                if (lane >= (unsigned)o) incl_d += y;
+            }
+            const uint32_t dbase = incl_d - cnt;            // first sorted slot of owner `lane` in the tile
+            uint32_t run = dbase;
+#pragma unroll
+            for (int q = 0; q < OS_WARPS; ++q) {
+                uint16_t *c = reinterpret_cast<uint16_t *>(sm.cnt[q]) + lane;
+                const uint32_t x = *c;
+                *c = (uint16_t)run;
+                run += x;
+            }
+            uint64_t excl = 0;
+            if (lane < W) {
+                if (tile > 0) {
+                    int64_t t = (int64_t)tile - 1;
+                    for (;;) {
+                        const uint64_t v = ld_volatile_u64(sp.owner_state + (size_t)t * RT_BINS + lane);
+                        const uint64_t flag = v >> 62;
+                        if (flag == 0) continue;
+                        excl += v & SIGK_CS_VAL;
+                        if (flag == 2) break;
+                        --t;
+                    }
+                    st_volatile_u64(state, SIGK_CS_PRE | (excl + cnt));
+                }
+                if (excl + cnt > sp.region_stride) atomicOr(sp.overflow, 1u);
+                if (last_tile) sp.owner_totals[lane] = excl + cnt;
+            }
+            sm.goff[lane] = (uint32_t)excl - dbase;         // region offsets fit 32 bits (a region holds < 2^32 records)
+        }
+        __syncthreads();
+        // ---- reorder in shared memory: keys, then the staged values (everybody reads them before anybody writes)
+#pragma unroll
+        for (int i = 0; i < ES_ITEMS; ++i) {
+            const uint32_t slot = (uint32_t)wcnt16[(uint32_t)key[i] & (RT_BINS - 1)] + SIGK_RANK_GET(i);
+            SIGK_RANK_SET(i, slot);
+        }
+#pragma unroll
+        for (int i = 0; i < ES_ITEMS; ++i) sm.keys[SIGK_RANK_GET(i)] = key[i];
+        uint32_t v[ES_ITEMS];
+#pragma unroll
+        for (int i = 0; i < ES_ITEMS; ++i) {
+            const uint32_t idx = wbase + i * 32 + lane;
+            v[i] = idx < tile_n ? sm.vals[stage_slot(idx)] : 0u;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < ES_ITEMS; ++i) sm.vals[SIGK_RANK_GET(i)] = v[i];
+        __syncthreads();
+        if (*reinterpret_cast<volatile uint32_t *>(sp.overflow)) continue;     // regions too small: the caller grows them and encodes again
+        // ---- write-out: one contiguous run per owner, coalesced (a warp's store is 256 bytes of keys)
+        for (uint32_t j = tid; j < tile_n; j += OS_THREADS) {
+            const uint64_t k = sm.keys[j];
+            const uint32_t d = (uint32_t)k & (RT_BINS - 1);
+            const uint32_t pos = sm.goff[d] + j;
+            s_dkeys[d][pos] = k & ~(uint64_t)(RT_BINS - 1);
+            s_dvals[d][pos] = sm.vals[j];
+        }
     }
 }
 
@@ -555,6 +803,7 @@ cudaError_t onesweep_configure() {
     SIGK_OPT_IN((onesweep_pass_kernel<uint64_t, true>), sizeof(PassSmem))
     SIGK_OPT_IN(encode_sort_kernel<uint32_t>, sizeof(FusedSmem))
     SIGK_OPT_IN(encode_sort_kernel<uint64_t>, sizeof(FusedSmem))
+    SIGK_OPT_IN(encode_route_kernel, sizeof(FusedSmem))
 #undef SIGK_OPT_IN
     return cudaSuccess;
 }
@@ -638,6 +887,14 @@ cudaError_t launch_encode_sort(const EncodeArgs &a, uint64_t *keys_out, uint32_t
     else
         encode_sort_kernel<uint32_t><<<grid, OS_THREADS, sizeof(FusedSmem), stream>>>(a, keys_out, vals_out, bit_lo, mask, bin_base,
                                                                                         (uint32_t *)lookback, ticket, (uint32_t)tiles);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_encode_route(const EncodeArgs &a, const EncodeSplitArgs &sp, uint32_t *ticket, int sm_count, cudaStream_t stream) {
+    if (a.total_res == 0 || a.n_prot == 0) return cudaSuccess;
+    if (sp.n_split < 0 || sp.n_split > 15) return cudaErrorInvalidValue;
+    const uint64_t tiles = encode_sort_tiles(a.total_res);
+    encode_route_kernel<<<persistent_grid(tiles, sm_count), OS_THREADS, sizeof(FusedSmem), stream>>>(a, sp, ticket, (uint32_t)tiles);
     return cudaGetLastError();
 }
 

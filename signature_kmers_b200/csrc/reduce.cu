@@ -57,9 +57,9 @@ SIGK_D unsigned mask_range(unsigned lo, unsigned hi) {                     // bi
 // length | function << 16 when every protein of the job is shorter than 65 535 residues (half the
 // footprint: what decides whether the gathers stay in L2 once several ranks' proteins are in it).
 template <typename MetaT> SIGK_D ProtMeta load_meta(const MetaT *__restrict__ meta, uint32_t ordinal);
-template <> SIGK_D ProtMeta load_meta<ProtMeta>(const ProtMeta *__restrict__ meta, uint32_t ordinal) { return __ldg(meta + ordinal); }
+template <> SIGK_D ProtMeta load_meta<ProtMeta>(const ProtMeta *__restrict__ meta, uint32_t ordinal) { return ld_keep_u32x2(meta + ordinal); }
 template <> SIGK_D ProtMeta load_meta<uint32_t>(const uint32_t *__restrict__ meta, uint32_t ordinal) {
-    const uint32_t v = __ldg(meta + ordinal);
+    const uint32_t v = ld_keep_u32(meta + ordinal);
     return make_uint2(v & 0xFFFFu, v >> 16);
 }
 

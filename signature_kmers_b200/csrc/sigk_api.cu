@@ -62,7 +62,8 @@ int ensure_capacity(sigk_handle *h, uint64_t cap, bool keep_pingpong1) {
     CU(h, h->d_out_kmer.reserve(cap));
     CU(h, h->d_out_cols.reserve(cap * 5));
     const uint64_t world = (uint64_t)std::max(1, h->cfg.world);
-    CU(h, h->d_scan_state.reserve(std::max<uint64_t>((encode_slices(h->total_res) + 1) * world + world, reduce_scan_entries(cap))));
+    CU(h, h->d_scan_state.reserve(std::max<uint64_t>(std::max<uint64_t>((encode_slices(h->total_res) + 1) * world + world, encode_route_state_words(h->total_res)),
+                                                     reduce_scan_entries(cap))));
     if (cap > h->capacity) h->capacity = cap;
     return SIGK_OK;
 }
@@ -173,9 +174,10 @@ int do_build_device(sigk_handle *h) {
     uint64_t *hist_main = h->d_hist.p, *hist_side = h->d_hist.p + (size_t)SORT_MAX_PASSES * SIGK_BINS;
     uint64_t *base_main = h->d_binbase.p, *base_side = h->d_binbase.p + (size_t)SORT_MAX_PASSES * SIGK_BINS;
     const uint64_t cap = h->capacity;
-    const size_t lb_bytes = onesweep_lookback_bytes(std::max<uint64_t>(cap, 1));
+    // (with a communicator the exchange may grow the buffers: the look-back rows are laid out and zeroed after it)
+    size_t lb_bytes = onesweep_lookback_bytes(std::max<uint64_t>(cap, 1));
     uint8_t *lb_side = h->d_lookback.p + lb_bytes * SORT_MAX_PASSES;
-    CU(h, cudaMemsetAsync(h->d_lookback.p, 0, lb_bytes * plan.npass, st));
+    if (!h->comm) CU(h, cudaMemsetAsync(h->d_lookback.p, 0, lb_bytes * plan.npass, st));
 
     const MetaTable meta{h->d_meta.p, h->meta_compact};
     EncodeArgs ea{h->d_res.p, h->total_res, h->d_starts.p, (uint32_t)np, (uint32_t)h->ordinal_base, h->d_slice_prot.p, h->d_prot_windows.p};
@@ -203,12 +205,12 @@ int do_build_device(sigk_handle *h) {
         const uint64_t *n_ptr = nullptr;
         if (!h->comm) {
             nvtx_range r("sigk encode");
-            CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, (encode_slices(h->total_res) + 2) * sizeof(uint64_t), st));
+            CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, encode_route_state_words(h->total_res) * sizeof(uint64_t), st));
             EncodeSplitArgs sp{};
             sp.n_split = 0; sp.region_stride = cap; sp.owner_state = h->d_scan_state.p; sp.owner_totals = &sc->n_records;
             sp.overflow = &sc->overflow;
             sp.dst_keys[0] = h->d_keys[0].p; sp.dst_vals[0] = h->d_vals[0].p;
-            CU(h, launch_encode_split(ea, sp, sc->ticket + TK_ENCODE, st)); ++launches;
+            CU(h, launch_encode_route(ea, sp, sc->ticket + TK_ENCODE, h->sm_count, st)); ++launches;
             seg.n = 1; seg.start[0] = 0; seg.start[1] = cap; seg.keys[0] = h->d_keys[0].p; seg.vals[0] = h->d_vals[0].p;
             n_ptr = &sc->n_records;                 // only the device knows how many windows were valid
             CU(h, cudaEventRecord(h->ev[EV_ENCODE], st));
@@ -220,6 +222,9 @@ int do_build_device(sigk_handle *h) {
             // after a send/recv exchange)
             if (int rc = comm_encode_exchange(h, ea, &seg, &cur, &launches)) return rc;
             CU(h, cudaEventRecord(h->ev[EV_EXCHANGE], st));
+            lb_bytes = onesweep_lookback_bytes(std::max<uint64_t>(h->capacity, 1));
+            lb_side = h->d_lookback.p + lb_bytes * SORT_MAX_PASSES;
+            CU(h, cudaMemsetAsync(h->d_lookback.p, 0, lb_bytes * plan.npass, st));
         }
         nvtx_range r("sigk histogram + first pass");
         CU(h, launch_histogram_main(seg, n_ptr, plan, hist_main, h->sm_count, st)); ++launches;
@@ -227,7 +232,7 @@ int do_build_device(sigk_handle *h) {
         CU(h, cudaMemcpyAsync(&sc->n_records, &sc->n_both, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
         CU(h, cudaEventRecord(h->ev[EV_HIST], st));
         CU(h, cudaEventRecord(h->ev[EV_PASS0], st));
-        CU(h, launch_onesweep_first_pass(seg, n_ptr, h->d_keys[cur].p, h->d_vals[cur].p, cap, plan.lo[0], plan.bits[0], base_main,
+        CU(h, launch_onesweep_first_pass(seg, n_ptr, h->d_keys[cur].p, h->d_vals[cur].p, h->capacity, plan.lo[0], plan.bits[0], base_main,
                                          h->d_lookback.p, sc->ticket + TK_SORT0, h->sm_count, st)); ++launches;
     }
     const uint64_t cap_sort = h->capacity;      // (the exchange may have grown it)
@@ -311,6 +316,12 @@ int do_download(sigk_handle *h) {
     CU(h, cudaMemcpyAsync(h->h_swf.p, h->d_swf.p, SIGK_N_FUNCTION_SLOTS * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
     const uint64_t nk = h->h_scalars.p->n_kept;
+    if (std::getenv("SIGK_DEBUG_COUNTS")) {
+        const DeviceScalars &d = *h->h_scalars.p;
+        std::fprintf(stderr, "[sigk] records %llu (main %llu, side %llu) groups %llu kept %llu (side %llu); listed 5..32: %u, longer: %u, walks: %u (+%u whole-warp)\n",
+                     (unsigned long long)d.n_records, (unsigned long long)d.n_main, (unsigned long long)d.n_side, (unsigned long long)d.n_segments,
+                     (unsigned long long)d.n_kept, (unsigned long long)d.n_side_kept, d.n_groups, d.n_long, d.n_work, d.n_work_long);
+    }
     if (nk > h->capacity) return h->fail(SIGK_E_CUDA, "kept count %llu exceeds capacity", (unsigned long long)nk);
     if (nk > h->h_rows) {
         // grow-only pinned result buffers (page-locking is slow; first build pays it)
@@ -344,6 +355,8 @@ int do_download(sigk_handle *h) {
     t.squeeze_ms = ms(EV_ORDER, EV_SQUEEZE);
     t.d2h_ms = ms(EV_SQUEEZE, EV_D2H);
     t.device_total_ms = ms(EV_DEV0, EV_SQUEEZE);
+    t.records_sorted = h->h_scalars.p->n_records;
+    t.exchange_bytes_out = h->comm ? h->exchange_bytes_out : 0;
     t.sort_passes = (uint32_t)h->plan.npass;
     t.record_bytes = 12;
     t.key_bytes = 8;
@@ -577,13 +590,13 @@ int sigk_dbg_encode(sigk_handle *h, const sigk_proteins *p, uint64_t *out_code, 
     cudaStream_t st = h->stream;
     DeviceScalars *sc = h->d_scalars.p;
     CU(h, cudaMemsetAsync(sc, 0, sizeof(DeviceScalars), st));
-    CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, (encode_slices(h->total_res) + 2) * sizeof(uint64_t), st));
+    CU(h, cudaMemsetAsync(h->d_scan_state.p, 0, encode_route_state_words(h->total_res) * sizeof(uint64_t), st));
     EncodeArgs ea{h->d_res.p, h->total_res, h->d_starts.p, (uint32_t)p->n_proteins, 0u, h->d_slice_prot.p, nullptr};
     EncodeSplitArgs sp{};
     sp.n_split = 0; sp.region_stride = h->capacity; sp.owner_state = h->d_scan_state.p; sp.owner_totals = &sc->n_records;
     sp.overflow = &sc->overflow;
     sp.dst_keys[0] = h->d_keys[0].p; sp.dst_vals[0] = h->d_vals[0].p;
-    CU(h, launch_encode_split(ea, sp, sc->ticket + TK_ENCODE, st));
+    CU(h, launch_encode_route(ea, sp, sc->ticket + TK_ENCODE, h->sm_count, st));
     uint64_t n = 0;
     CU(h, cudaMemcpyAsync(&n, &sc->n_records, sizeof n, cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));

@@ -148,6 +148,25 @@ SIGK_D uint4 ld_stream_u128(const uint4 *p) {
     return v;
 }
 
+// Gathers from the per-protein table: marked evict-last in L2 so that the records streaming past (each read
+// once) do not push the table out — with several ranks' proteins in it the table is tens of megabytes and
+// every record of the reduce stage looks one entry up.
+SIGK_D uint64_t l2_evict_last_policy() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+SIGK_D uint32_t ld_keep_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_evict_last_policy()));
+    return v;
+}
+SIGK_D uint2 ld_keep_u32x2(const uint2 *p) {
+    uint2 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(l2_evict_last_policy()));
+    return v;
+}
+
 // ---- single-value chained scan (decoupled look-back) ------------------------
 // state[t] = flag << 62 | value.  flag 0 = not ready, 1 = tile aggregate,
 // 2 = inclusive prefix.  Tiles are tickets taken in launch order, so every

@@ -74,12 +74,14 @@ def concat_tables(tables) -> KeptTable:
 
 
 def weak_scaling_params(workload: str, world: int) -> dict:
-    """Per-GPU work fixed at the single-GPU workload: world x the proteins and genomes; the
-    function count grows with it up to 60 000 (FunctionIndex is 16 bits, src/kmer_data.h:18)."""
+    """Per-GPU work fixed at the single-GPU workload: world x the proteins, genomes and functions.  Past 65 535 kept
+    functions the generator's index assignment wraps exactly like the reference's `unsigned short next`
+    (src/function_map.h:324-330): later functions alias earlier indices and index 0xFFFF proteins are skipped
+    (src/signature_build.tcc:155-158) — the config-3 situation (8 x 20 000 = 160 000 functions at 8 GPUs)."""
     from .synth import CONFIGS
 
     kw = dict(CONFIGS[workload])
-    kw["n_functions"] = min(kw["n_functions"] * world, 60_000)
+    kw["n_functions"] = kw["n_functions"] * world
     kw["n_proteins"] = kw["n_proteins"] * world
     kw["n_genomes"] = kw["n_genomes"] * world
     return kw
@@ -163,7 +165,7 @@ def run_bench(args, rank, world, local_rank, metric, unit):
                     "api": "sigk_build per rank (C ABI, pinned host buffers)"},
             "gpu_launches": int(tm["kernel_launches"]) * args.steps * world,
             "roofline": None,
-            "rank0_stage_ms": {k: tm[k] for k in ("encode_ms", "exchange_ms", "histogram_ms", "sort_ms", "reduce_ms",
+            "rank0_stage_ms": {k: tm[k] for k in ("encode_ms", "exchange_ms", "histogram_ms", "sort_ms", "side_sort_ms", "reduce_ms",
                                                    "order_stats_ms", "squeeze_ms", "device_total_ms")},
             "cpu_baseline": None,
         }
@@ -172,16 +174,21 @@ def run_bench(args, rank, world, local_rank, metric, unit):
             from bench import measured_peak_gbs
 
             peak, src = measured_peak_gbs()
-            # rank 0's share of the records is what its pass kernel moved
-            # rank 0 sorted its share of the records: the sampled splitters balance the ranks to within about a
-            # per cent, so occurrences / world stands in for the exact count (which only the library knows)
-            launch_ms = sum(pass_ms) / len(pass_ms)
-            alg_bytes = 24 * occ / world
+            # what rank 0's pass kernel moved: the records of rank 0's k-mer range (the library reports the count)
+            records0 = int(tm["records_sorted"])
+            plain = pass_ms[1:] if len(pass_ms) > 1 else pass_ms
+            launch_ms = sum(plain) / len(plain)
+            alg_bytes = 24 * records0
             achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
             line["roofline"] = {"bound": "hbm", "kernel": "onesweep_pass_kernel (rank 0)", "peak": peak, "unit": "GB/s",
                                 "peak_source": src, "pass_ms": pass_ms, "launch_ms": launch_ms,
-                                "algorithmic_bytes_per_launch": alg_bytes, "records": "occurrences / world (approximate)",
+                                "algorithmic_bytes_per_launch": alg_bytes, "records": records0,
                                 "achieved": achieved, "frac": achieved / peak, "traffic": None}
+            # the exchange: what rank 0's encode + route kernel stored into the other GPUs' landing zones over NVLink
+            if tm["encode_ms"] > 0 and tm["exchange_bytes_out"]:
+                out_gbs = tm["exchange_bytes_out"] / (tm["encode_ms"] * 1e-3) / 1e9
+                line["nvlink"] = {"rank0_bytes_out_per_step": int(tm["exchange_bytes_out"]), "encode_route_ms": tm["encode_ms"],
+                                  "achieved_gbs_out": out_gbs, "peak_gbs_per_direction": 900.0, "frac": out_gbs / 900.0}
         from bench import emit_json
 
         emit_json(line)

@@ -37,11 +37,21 @@ class FileTable:
         self.keys = np.frombuffer(raw[16:16 + 8 * n], dtype=">u8").astype(np.uint64)
         off = 16 + 8 * n
         self.cols = [np.frombuffer(raw[off + 2 * n * c: off + 2 * n * (c + 1)], dtype=np.uint16) for c in range(5)]
+        # table order (include/sigk.h): rows without a lower-case residue first, in byte order; the (few) others after
+        # them, kept here in a dictionary
+        lower = (self.keys & np.uint64(0x2020202020202020)) != 0
+        self.n_upper = int(np.argmax(lower)) if lower.any() else n
+        assert not lower[:self.n_upper].any() and lower[self.n_upper:].all(), "two sections"
+        assert (np.diff(self.keys[:self.n_upper].astype(np.int64)) > 0).all() if self.n_upper > 1 else True
+        self.side = {int(k): self.n_upper + i for i, k in enumerate(self.keys[self.n_upper:])}
 
     def get(self, kmer):
-        key = np.uint64(int.from_bytes(kmer.encode("latin-1"), "big"))
-        i = int(np.searchsorted(self.keys, key))
-        if i < self.n and self.keys[i] == key:
+        key = int.from_bytes(kmer.encode("latin-1"), "big")
+        if key & 0x2020202020202020:
+            i = self.side.get(key)
+            return None if i is None else tuple(int(c[i]) for c in self.cols)
+        i = int(np.searchsorted(self.keys[:self.n_upper], np.uint64(key)))
+        if i < self.n_upper and int(self.keys[i]) == key:
             return tuple(int(c[i]) for c in self.cols)
         return None
 

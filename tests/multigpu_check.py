@@ -74,6 +74,11 @@ def main():
     cases.append(("one protein", pack(["ACDEFGHIKLMNPQRSTVWY"], [3])))
     cases.append(("no valid window", pack(["ACDXFGHIKL", "ACD"], [1, 2])))
     cases.append(("synthetic 40K proteins", Synth(n_proteins=40_000, n_functions=400, n_genomes=8, seed=9).packed()))
+    # config-3-shaped function count: 72 000 families, so that the index assignment wraps like the reference's
+    # `unsigned short next` (src/function_map.h:324-330), later functions alias earlier indices, proteins whose index
+    # would be 0xFFFF are skipped (src/signature_build.tcc:155-158), and both halves of the per-function counters are used
+    if not os.environ.get("SIGK_CHECK_SKIP_WRAP"):
+        cases.append(("72K functions (index wrap)", Synth(n_proteins=290_000, n_functions=72_000, n_genomes=4, seed=33).packed()))
     for name, p_all in cases:
         print(f"[rank {rank}] case: {name}", file=sys.stderr, flush=True)
         got, per_rank = build_distributed(p_all, rank, world, local_rank)
@@ -88,12 +93,12 @@ def main():
             single.close()
             print(f"multigpu_check ok ({world} ranks): {name}: {got.n_occurrences} occurrences, kept per rank {per_rank}", flush=True)
         dist.barrier()
-    # the encode + route kernel instantiations of the larger worlds (2 and 4 counter words: 5..8 and 9..16 ranks)
-    # (opt-in with SIGK_CHECK_WIDE=1 until it has run once on a GPU box: added after the round's GPU budget was spent)
+    # the encode + route kernel instantiations of the larger worlds (2 and 4 counter words: 5..8 and 9..16 ranks),
+    # forced on whatever world size this is
     for words in (("2", "4") if os.environ.get("SIGK_CHECK_WIDE") else ()):
         os.environ["SIGK_TEST_SPLIT_WORDS"] = words
         try:
-            for name, p_all in (cases[0], cases[-1]):
+            for name, p_all in (cases[0], cases[5]):
                 got, per_rank = build_distributed(p_all, rank, world, local_rank)
                 if rank == 0:
                     from oracle import oracle_c
@@ -104,8 +109,36 @@ def main():
                 dist.barrier()
         finally:
             del os.environ["SIGK_TEST_SPLIT_WORDS"]
+    # regions too small on every rank: the build grows them to the exact need and encodes again
+    os.environ["SIGK_TEST_FORCE_SPLIT_FALLBACK"] = "1"
+    try:
+        name, p_all = cases[0]
+        got, per_rank = build_distributed(p_all, rank, world, local_rank)
+        if rank == 0:
+            from oracle import oracle_c
+
+            want, _ = oracle_c.oracle_build(p_all)
+            assert_tables_equal(got, want, tier_b=True, what=f"{name}, forced region overflow")
+            print(f"multigpu_check ok ({world} ranks): {name} with a forced region overflow and retry", flush=True)
+        dist.barrier()
+    finally:
+        del os.environ["SIGK_TEST_FORCE_SPLIT_FALLBACK"]
+    # without peer mappings: local send regions + NCCL send/recv
+    os.environ["SIGK_NO_PEER_WRITES"] = "1"
+    try:
+        for name, p_all in (cases[0], cases[5]):
+            got, per_rank = build_distributed(p_all, rank, world, local_rank)
+            if rank == 0:
+                from oracle import oracle_c
+
+                want, _ = oracle_c.oracle_build(p_all)
+                assert_tables_equal(got, want, tier_b=True, what=f"{name}, NCCL send/recv")
+                print(f"multigpu_check ok ({world} ranks): {name} through NCCL send/recv (no peer mappings)", flush=True)
+            dist.barrier()
+    finally:
+        del os.environ["SIGK_NO_PEER_WRITES"]
     # the same inputs, small -> large -> small, through one communicator
-    order = [cases[2], cases[-1], cases[0]]
+    order = [cases[2], cases[5], cases[0]]
     tables = build_sequence_on_one_communicator(order, rank, world, local_rank)
     if rank == 0:
         from oracle import oracle_c

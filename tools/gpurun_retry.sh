@@ -1,0 +1,11 @@
+#!/bin/bash
+# gpurun with retries while the pod has no free GPU slot (exit code 3: nothing charged).
+#   tools/gpurun_retry.sh [gpurun options] -- 'command'
+for attempt in 1 2 3 4 5 6 7 8 9 10; do
+  /usr/local/graft/bin/gpurun "$@"
+  rc=$?
+  [ $rc -ne 3 ] && exit $rc
+  echo "[gpurun_retry] no slot (attempt $attempt); sleeping 150 s" >&2
+  sleep 150
+done
+exit 3
