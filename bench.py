@@ -312,6 +312,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="sigk", choices=["sigk", "reference"])
     ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config3", "config4"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="multi-GPU: weak = workload x N (default, the driver's scaling run); strong = the named workload split over N GPUs")
     ap.add_argument("--cpu-sample-proteins", type=int, default=600_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -140,6 +140,8 @@ typedef struct sigk_timings {
     float pass_ms[8];       /* per onesweep pass of the main run; [0] is the first pass (fused with the encode on one GPU) */
     float count_ms;         /* window count pass (digit histograms from the residues) */
     float side_sort_ms;     /* histogram + passes of the side run (records with a lower-case residue) */
+    float reduce_comm_ms;   /* multi-GPU: the all-reduce of the per-protein rejected-occurrence counts (inside reduce_ms) */
+    float pad_;
     uint64_t records_sorted;      /* records this GPU sorted and reduced (its k-mer range's share with a communicator) */
     uint64_t exchange_bytes_out;  /* multi-GPU: bytes of records this GPU stored into other GPUs' landing zones */
 } sigk_timings;

@@ -83,6 +83,8 @@ class SigkTimings(C.Structure):
         ("pass_ms", C.c_float * 8),
         ("count_ms", C.c_float),
         ("side_sort_ms", C.c_float),
+        ("reduce_comm_ms", C.c_float),
+        ("pad_", C.c_float),
         ("records_sorted", C.c_uint64),
         ("exchange_bytes_out", C.c_uint64),
     ]

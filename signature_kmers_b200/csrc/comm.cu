@@ -330,8 +330,9 @@ int comm_allgather_meta(sigk_handle *h) {
     uint64_t base = 0;
     for (int r = 0; r < c->world; ++r) {
         if (c->prot_count[r])
-            NC(h, g_nccl.Broadcast(h->d_meta.p + meta_bytes(base, h->meta_compact), h->d_meta.p + meta_bytes(base, h->meta_compact),
-                                   meta_bytes(c->prot_count[r], h->meta_compact), ncclUint8, r, c->comm, st));
+            NC(h, g_nccl.Broadcast(h->d_meta.p + (meta_bytes(base, h->meta_compact) << h->meta_shift),
+                                   h->d_meta.p + (meta_bytes(base, h->meta_compact) << h->meta_shift),
+                                   meta_bytes(c->prot_count[r], h->meta_compact) << h->meta_shift, ncclUint8, r, c->comm, st));
         base += c->prot_count[r];
     }
     NC(h, g_nccl.GroupEnd());

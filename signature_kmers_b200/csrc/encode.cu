@@ -39,7 +39,7 @@ SIGK_D int stage_slot(int o) { return o + (o >> 4); }
 constexpr int WC_THREADS = 256;
 constexpr int WC_WARPS = WC_THREADS / 32;
 
-template <int NPASS>
+template <int NPASS, bool STD>
 __global__ void __launch_bounds__(WC_THREADS, 3)
 window_count_kernel(EncodeArgs a, const __grid_constant__ PassPlan plan, uint64_t *__restrict__ hist, uint32_t n_slices) {
     __shared__ uint32_t sh[NPASS * SIGK_RADIX];
@@ -56,22 +56,25 @@ window_count_kernel(EncodeArgs a, const __grid_constant__ PassPlan plan, uint64_
         WindowLane w;
         ws_load(a, s_sym, (uint32_t)sub, w);
         const uint32_t valid = ws_valid_mask(a, w);
-        uint32_t run_i = 0, run_c = 0;              // occurrences of the protein I am inside
-        ws_for_each(a, w, valid, [&](int, uint64_t key, uint32_t i) {
-            if (sigk_key_mask(key) == 0) {
+        ws_for_each_code(a, w, valid, [&](int, uint64_t code, uint32_t mask, uint32_t, uint32_t) {
+            if (mask == 0) {
+                if (STD) {
+                    // the standard plan (9/9/9/8 bits from key bit 29 = code bit 0): the digits with 32-bit operations
+                    const uint32_t lo = (uint32_t)code, hi = (uint32_t)(code >> 32);
+                    atomicAdd(&sh[0 * SIGK_RADIX + (lo & 511u)], 1u);
+                    atomicAdd(&sh[1 * SIGK_RADIX + ((lo >> 9) & 511u)], 1u);
+                    atomicAdd(&sh[2 * SIGK_RADIX + ((lo >> 18) & 511u)], 1u);
+                    atomicAdd(&sh[3 * SIGK_RADIX + ((lo >> 27) | (hi << 5))], 1u);
+                } else {
+                    // (the digits of the key's bit fields, taken from the code: key = code << 29 | ...)
 #pragma unroll
-                for (int p = 0; p < NPASS; ++p)
-                    atomicAdd(&sh[p * SIGK_RADIX + ((uint32_t)(key >> plan.lo[p]) & ((1u << plan.bits[p]) - 1u))], 1u);
+                    for (int p = 0; p < NPASS; ++p)
+                        atomicAdd(&sh[p * SIGK_RADIX + ((uint32_t)(code >> (plan.lo[p] - SIGK_KEY_CODE35_SHIFT)) & ((1u << plan.bits[p]) - 1u))], 1u);
+                }
             } else {
                 ++side;
             }
-            if (i != run_i) {
-                if (run_c && a.prot_windows) atomicAdd(a.prot_windows + run_i, run_c);
-                run_i = i; run_c = 0;
-            }
-            ++run_c;
-        });
-        if (run_c && a.prot_windows) atomicAdd(a.prot_windows + run_i, run_c);
+        }, [&](uint32_t i, uint32_t n_windows) { if (a.prot_windows) atomicAdd(a.prot_windows + i, n_windows); });
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) side += __shfl_xor_sync(0xffffffffu, side, o);
@@ -193,20 +196,13 @@ encode_split_kernel(EncodeArgs a, const __grid_constant__ EncodeSplitArgs sp, ui
         uint64_t run[SPLIT_WORDS];
 #pragma unroll
         for (int k = 0; k < SPLIT_WORDS; ++k) run[k] = excl[k];
-        uint32_t run_i = 0, run_c = 0;              // occurrences of the protein I am inside
         ws_for_each(a, w, valid_mask, [&](int j, uint64_t key, uint32_t i) {
             const uint32_t d = (uint32_t)(owners >> (4 * j)) & 15u;
             const int slot = stage_slot((int)(sm.obase[warp][d] + field16(run, d)));
             bump16(run, d);
             sm.keys[warp][slot] = key;
             sm.vals[warp][slot] = a.ordinal_base + i;
-            if (i != run_i) {
-                if (run_c && a.prot_windows) atomicAdd(a.prot_windows + run_i, run_c);
-                run_i = i; run_c = 0;
-            }
-            ++run_c;
-        });
-        if (run_c && a.prot_windows) atomicAdd(a.prot_windows + run_i, run_c);
+        }, [&](uint32_t i, uint32_t n_windows) { if (a.prot_windows) atomicAdd(a.prot_windows + i, n_windows); });
     }
 
     // resolve: lane d walks back over the earlier slices of owner d
@@ -294,10 +290,13 @@ cudaError_t launch_window_count(const EncodeArgs &a, const PassPlan &plan, uint6
     const uint64_t n_slices = (a.total_res + WS_SUB - 1) / WS_SUB;
     const uint64_t want = (n_slices + WC_WARPS - 1) / WC_WARPS;
     const unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)sm_count * 8);
+    for (int p = 0; p < plan.npass; ++p) if (plan.lo[p] < SIGK_KEY_CODE35_SHIFT) return cudaErrorInvalidValue;      // the passes of the main run sort code bits only
+    const bool std_plan = plan.npass == 4 && plan.lo[0] == 29 && plan.bits[0] == 9 && plan.bits[1] == 9 && plan.bits[2] == 9 && plan.bits[3] == 8;
+    if (std_plan) { window_count_kernel<4, true><<<grid, WC_THREADS, 0, stream>>>(a, plan, hist, (uint32_t)n_slices); return cudaGetLastError(); }
     switch (plan.npass) {
-        case 3: window_count_kernel<3><<<grid, WC_THREADS, 0, stream>>>(a, plan, hist, (uint32_t)n_slices); break;
-        case 4: window_count_kernel<4><<<grid, WC_THREADS, 0, stream>>>(a, plan, hist, (uint32_t)n_slices); break;
-        case 5: window_count_kernel<5><<<grid, WC_THREADS, 0, stream>>>(a, plan, hist, (uint32_t)n_slices); break;
+        case 3: window_count_kernel<3, false><<<grid, WC_THREADS, 0, stream>>>(a, plan, hist, (uint32_t)n_slices); break;
+        case 4: window_count_kernel<4, false><<<grid, WC_THREADS, 0, stream>>>(a, plan, hist, (uint32_t)n_slices); break;
+        case 5: window_count_kernel<5, false><<<grid, WC_THREADS, 0, stream>>>(a, plan, hist, (uint32_t)n_slices); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -54,7 +54,7 @@ template <typename T> struct PinnedBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-enum { EV_START, EV_H2D, EV_DEV0, EV_ENCODE, EV_EXCHANGE, EV_HIST, EV_MAIN_SORTED, EV_SORT, EV_REDUCE, EV_ORDER, EV_SQUEEZE, EV_D2H,
+enum { EV_START, EV_H2D, EV_DEV0, EV_ENCODE, EV_EXCHANGE, EV_HIST, EV_MAIN_SORTED, EV_SORT, EV_REJ0, EV_REJ1, EV_REDUCE, EV_ORDER, EV_SQUEEZE, EV_D2H,
        EV_USER0, EV_USER1, EV_USER2, EV_USER3, EV_PASS0, EV_COUNT = EV_PASS0 + SORT_MAX_PASSES + 1 };
 
 struct Comm;    // comm.cu
@@ -81,6 +81,7 @@ struct sigk_handle {
     sigk::DevBuf<uint32_t> d_seqid, d_slice_prot;
     sigk::DevBuf<uint8_t> d_meta;          // per-protein {length, function}: 4 or 8 bytes each (meta_compact)
     bool meta_compact = false;
+    int meta_shift = 0;                    // SIGK_TEST_META_SPREAD: table entries 2^shift apart (cache-footprint experiments)
     uint64_t local_max_len = 0, max_len = 0;   // longest protein: this rank's / the job's
     sigk::DevBuf<uint4> d_rows;
     sigk::DevBuf<sigk::OrderWork> d_groups, d_long_groups, d_work, d_work_long;

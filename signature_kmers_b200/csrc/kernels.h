@@ -94,6 +94,7 @@ size_t onesweep_lookback_bytes(uint64_t capacity);
 struct SortSegments {
     int n;
     uint64_t start[SORT_MAX_SEGMENTS + 1];      // first record index of each region in the concatenation; start[n] = total
+    uint32_t tile_start[SORT_MAX_SEGMENTS + 1]; // filled by launch_onesweep_first_pass: first tile of each region
     const uint64_t *keys[SORT_MAX_SEGMENTS];
     const uint32_t *vals[SORT_MAX_SEGMENTS];
 };
@@ -151,13 +152,13 @@ size_t reduce_group_entries(uint64_t capacity, int sm_count);  // OrderWork entr
 size_t reduce_long_group_entries(uint64_t capacity);           // OrderWork entries: groups of more than 32 records
 size_t reduce_work_entries(uint64_t capacity, int sm_count);   // OrderWork entries: groups whose median/var need the ordered walk
 size_t reduce_long_work_entries(uint64_t capacity);            // ... of those, the ones a whole warp walks
-cudaError_t reduce_configure();
+cudaError_t reduce_configure(int meta_shift);   // meta_shift: SIGK_TEST_META_SPREAD (0 in production)
 
 // What a record's protein ordinal is looked up for.  x = protein_length, y = function_index: 8 bytes per
 // protein, or — when every protein of the job is shorter than 65 535 residues — 4 bytes, length | function << 16
 // (compact), so that the job-wide table stays in L2 as long as possible (2 M proteins = 8 MB).
 using ProtMeta = uint2;
-struct MetaTable { void *p; bool compact; };
+struct MetaTable { void *p; bool compact; int shift; };     // shift: entries 2^shift apart (SIGK_TEST_META_SPREAD; 0 in production)
 inline size_t meta_bytes(uint64_t n_proteins, bool compact) { return (size_t)n_proteins * (compact ? sizeof(uint32_t) : sizeof(ProtMeta)); }
 // meta[first + i] for the n_prot local proteins; seqs_with_func[f]++ (src/signature_build.tcc:160)
 cudaError_t launch_protein_meta(const uint64_t *starts, const uint16_t *func, const uint32_t *seq_id, uint32_t n_prot,

@@ -274,13 +274,36 @@ SIGK_D void os_sort_tile(SM &sm, uint64_t (&key)[ITEMS], uint32_t tile, uint32_t
         }
         sm.goff[d] = (uint32_t)(bin_base[d] + (uint64_t)excl) - base;
     };
-    auto look_back = [&]() {
-        if (owner) {
-            uint32_t base = dbase;
-#pragma unroll
-            for (int k = 0; k < OS_DPT; ++k) { look_back_digit(tid * OS_DPT + k, my_count[k], base); base += my_count[k]; }
+    // Thread 0 of a FIRST pass owns digit 0 and the side bin: the two walks advance together (one after the other they
+    // put a second walk's latency in front of the tile's barrier: 7.7 ms per pass against 4.4 ms).
+    auto look_back_pair = [&](uint32_t d0, uint32_t cnt0, uint32_t base0, uint32_t d1, uint32_t cnt1, uint32_t base1) {
+        LB e0 = 0, e1 = 0;
+        if (tile > 0) {
+            int64_t t0 = (int64_t)tile - 1, t1 = t0;
+            bool f0 = false, f1 = false;
+            while (!(f0 && f1)) {
+                const LB v0 = f0 ? (LB)0 : T::ld(lookback + (size_t)t0 * SIGK_BINS + d0);
+                const LB v1 = f1 ? (LB)0 : T::ld(lookback + (size_t)t1 * SIGK_BINS + d1);
+                if (!f0 && (v0 >> T::SHIFT) != 0) { e0 += v0 & T::VAL; if ((v0 >> T::SHIFT) == 2) f0 = true; else --t0; }
+                if (!f1 && (v1 >> T::SHIFT) != 0) { e1 += v1 & T::VAL; if ((v1 >> T::SHIFT) == 2) f1 = true; else --t1; }
+            }
+            T::st(lookback + (size_t)tile * SIGK_BINS + d0, T::PRE | (e0 + (LB)cnt0));
+            T::st(lookback + (size_t)tile * SIGK_BINS + d1, T::PRE | (e1 + (LB)cnt1));
         }
-        if (FIRST && tid == 0) look_back_digit(SIGK_SIDE_BIN, side_count, total_main);
+        sm.goff[d0] = (uint32_t)(bin_base[d0] + (uint64_t)e0) - base0;
+        sm.goff[d1] = (uint32_t)(bin_base[d1] + (uint64_t)e1) - base1;
+    };
+    auto look_back = [&]() {
+        if (FIRST && tid == 0 && OS_DPT == 1) {
+            look_back_pair(0u, my_count[0], dbase, SIGK_SIDE_BIN, side_count, total_main);
+        } else {
+            if (owner) {
+                uint32_t base = dbase;
+#pragma unroll
+                for (int k = 0; k < OS_DPT; ++k) { look_back_digit(tid * OS_DPT + k, my_count[k], base); base += my_count[k]; }
+            }
+            if (FIRST && tid == 0) look_back_digit(SIGK_SIDE_BIN, side_count, total_main);
+        }
     };
     // The ticket of the CTA's next tile, taken as late as it can be for its keys to be requested before the write-out:
     // a tile's aggregate is published a ranking after its ticket, and every later tile's look-back waits for it.
@@ -409,11 +432,11 @@ onesweep_pass_kernel(const __grid_constant__ SortSegments seg, const uint64_t *_
         os_zero_counters(sm);
         __syncthreads();
         const uint32_t tile = sm.tile;
-        const uint64_t tile_start = (uint64_t)tile * OS_TILE;
-        if (tile_start >= n) return;
-        const uint32_t tile_n = (uint32_t)((n - tile_start) < (uint64_t)OS_TILE ? (n - tile_start) : (uint64_t)OS_TILE);
         uint64_t key[OS_ITEMS];
         if (!FIRST) {
+            const uint64_t tile_start = (uint64_t)tile * OS_TILE;
+            if (tile_start >= n) return;
+            const uint32_t tile_n = (uint32_t)((n - tile_start) < (uint64_t)OS_TILE ? (n - tile_start) : (uint64_t)OS_TILE);
 #if SIGK_OS_PREFETCH
             if (tid == 0) {
                 // L2 prefetch of the tile one wave ahead (gridDim.x CTAs are resident)
@@ -434,31 +457,23 @@ onesweep_pass_kernel(const __grid_constant__ SortSegments seg, const uint64_t *_
                                                      [&](uint32_t r) { return ld_stream_u32(vals_in + off + tile_start + r); },
                                                      keys_out + off, vals_out + off, nullptr, []() {});
         } else {
-            // the regions of the first pass, read in place: region s holds records start[s] .. start[s+1]
-            int s0 = 0;
-            while (s0 + 1 < seg.n && tile_start >= seg.start[s0 + 1]) ++s0;
-            // does the whole tile lie in region s0?  (all but at most one tile per region boundary)
-            const bool one = seg.n <= 1 || tile_start + tile_n <= seg.start[s0 + 1];
-            const uint64_t r0 = tile_start - seg.start[s0];
-            auto region_of = [&](uint64_t g) {
-                int r = s0;
-                while (r + 1 < seg.n && g >= seg.start[r + 1]) ++r;
-                return r;
-            };
+            // The regions of the first pass are read in place, one after the other, in tiles that never straddle two of
+            // them (every region ends with a short tile): a tile is one pointer pair and a count, as in the plain pass.
+            if (tile >= (seg.n == 1 && n_ptr ? (uint32_t)((n + OS_TILE - 1) / OS_TILE) : seg.tile_start[seg.n])) return;
+            int r = 0;
+            while (r + 1 < seg.n && tile >= seg.tile_start[r + 1]) ++r;
+            const uint64_t rec0 = (uint64_t)(tile - seg.tile_start[r]) * OS_TILE;
+            const uint64_t n_r = (seg.n == 1 && n_ptr) ? n : seg.start[r + 1] - seg.start[r];
+            const uint32_t tile_n = (uint32_t)((n_r - rec0) < (uint64_t)OS_TILE ? (n_r - rec0) : (uint64_t)OS_TILE);
+            const uint64_t *kp = seg.keys[r] + rec0;
+            const uint32_t *vp = seg.vals[r] + rec0;
 #pragma unroll
             for (int i = 0; i < OS_ITEMS; ++i) {
                 const uint32_t idx = wbase + i * 32 + lane;
-                if (idx >= tile_n) key[i] = PAD_KEY;
-                else if (one) key[i] = ld_stream_u64(seg.keys[s0] + r0 + idx);
-                else { const uint64_t g = tile_start + idx; const int r = region_of(g); key[i] = ld_stream_u64(seg.keys[r] + (g - seg.start[r])); }
+                key[i] = idx < tile_n ? ld_stream_u64(kp + idx) : PAD_KEY;
             }
             os_sort_tile<LB, true, false, OS_ITEMS>(sm, key, tile, tile_n, bit_lo, digit_mask, bin_base, lookback,
-                                                    [&](uint32_t idx) {
-                                                        if (one) return ld_stream_u32(seg.vals[s0] + r0 + idx);
-                                                        const uint64_t g = tile_start + idx;
-                                                        const int r = region_of(g);
-                                                        return ld_stream_u32(seg.vals[r] + (g - seg.start[r]));
-                                                    }, keys_out, vals_out, nullptr, []() {});
+                                                    [&](uint32_t idx) { return ld_stream_u32(vp + idx); }, keys_out, vals_out, nullptr, []() {});
         }
     }
 }
@@ -468,6 +483,56 @@ onesweep_pass_kernel(const __grid_constant__ SortSegments seg, const uint64_t *_
 // and compact the valid windows of the tile into the staging in canonical order; then all warps read the staging
 // warp-striped and the tile goes through os_sort_tile like any other: main records to their lowest digit's run,
 // records with a lower-case residue to the side bin.
+// The window loop of one fused tile: the valid windows of the tile's ES_WARPS slices, compacted into the staging in
+// canonical order (one pad slot per 16: lanes write runs of ~16 records).  Returns the number of records.  Kept out of
+// line on purpose: it and the sort of the tile each get the whole register budget (inlined, the kernel spilled ~200
+// bytes per thread, and with 220 KB of the SM's 228 KB given to shared memory a spill goes to L2).
+#ifndef SIGK_ES_NOINLINE
+#define SIGK_ES_NOINLINE 1
+#endif
+#if SIGK_ES_NOINLINE
+#define SIGK_ES_INLINE __noinline__
+#else
+#define SIGK_ES_INLINE __forceinline__
+#endif
+template <typename SM>
+__device__ SIGK_ES_INLINE uint32_t encode_tile_to_staging(SM &sm, const EncodeArgs &a, uint32_t tile) {
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t sub = tile * ES_WARPS + warp;
+    const bool enc = warp < ES_WARPS && (uint64_t)sub * WS_SUB < a.total_res;
+    WindowLane w;
+    uint32_t valid = 0, incl = 0, mine = 0;
+    if (enc) {
+        ws_load(a, sm.sym, sub, w);
+        valid = ws_valid_mask(a, w);
+        mine = incl = (uint32_t)__popc(valid);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += y;
+        }
+    }
+    if (lane == 31) sm.wtotal[warp] = incl;             // 0 for warps without a slice
+    __syncthreads();
+    uint32_t before = 0, tile_n = 0;
+#pragma unroll
+    for (int q = 0; q < ES_WARPS; ++q) {
+        const uint32_t c = sm.wtotal[q];
+        before += q < (int)warp ? c : 0u;
+        tile_n += c;
+    }
+    if (enc) {
+        uint32_t o = before + incl - mine;
+        ws_for_each(a, w, valid, [&](int, uint64_t key, uint32_t i) {
+            const uint32_t slot = stage_slot(o++);
+            sm.keys[slot] = key;
+            sm.vals[slot] = a.ordinal_base + i;
+        });
+    }
+    __syncthreads();
+    return tile_n;
+}
+
 template <typename LB>
 __global__ void __launch_bounds__(OS_THREADS, OS_MIN_BLOCKS)
 encode_sort_kernel(EncodeArgs a, uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int bit_lo, uint32_t digit_mask,
@@ -485,40 +550,7 @@ encode_sort_kernel(EncodeArgs a, uint64_t *__restrict__ keys_out, uint32_t *__re
         const uint32_t tile = sm.tile;
         if (tile >= n_tiles) return;
 
-        // ---- window loop, part 1: which windows are valid, how many per slice
-        const uint32_t sub = tile * ES_WARPS + warp;
-        const bool enc = warp < ES_WARPS && (uint64_t)sub * WS_SUB < a.total_res;
-        WindowLane w;
-        uint32_t valid = 0, incl = 0, mine = 0;
-        if (enc) {
-            ws_load(a, sm.sym, sub, w);
-            valid = ws_valid_mask(a, w);
-            mine = incl = (uint32_t)__popc(valid);
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= (unsigned)o) incl += y;
-            }
-        }
-        if (lane == 31) sm.wtotal[warp] = incl;             // 0 for warps without a slice
-        __syncthreads();
-        uint32_t before = 0, tile_n = 0;
-#pragma unroll
-        for (int q = 0; q < ES_WARPS; ++q) {
-            const uint32_t c = sm.wtotal[q];
-            before += q < (int)warp ? c : 0u;
-            tile_n += c;
-        }
-        // ---- part 2: the records, compacted in canonical order (one pad slot per 16: lanes write runs of ~16)
-        if (enc) {
-            uint32_t o = before + incl - mine;
-            ws_for_each(a, w, valid, [&](int, uint64_t key, uint32_t i) {
-                const uint32_t slot = stage_slot(o++);
-                sm.keys[slot] = key;
-                sm.vals[slot] = a.ordinal_base + i;
-            });
-        }
-        __syncthreads();
+        const uint32_t tile_n = encode_tile_to_staging(sm, a, tile);
         uint64_t key[ES_ITEMS];
 #pragma unroll
         for (int i = 0; i < ES_ITEMS; ++i) {
@@ -592,21 +624,13 @@ encode_route_kernel(EncodeArgs a, const __grid_constant__ EncodeSplitArgs sp, ui
         // case-folded code) goes into the key's spare low bits
         if (enc) {
             uint32_t o = before + incl - mine;
-            uint32_t run_i = 0, run_c = 0;              // occurrences of the protein I am inside
-            ws_for_each(a, w, valid, [&](int, uint64_t key, uint32_t i) {
-                const uint64_t code = sigk_key_code35(key);
+            ws_for_each_code(a, w, valid, [&](int, uint64_t code, uint32_t mask, uint32_t off, uint32_t i) {
                 uint32_t d = 0;
                 for (int k = 0; k < sp.n_split; ++k) d += code >= s_split[k] ? 1u : 0u;
                 const uint32_t slot = stage_slot(o++);
-                sm.keys[slot] = key | d;
+                sm.keys[slot] = sigk_pack_key(code, mask, off) | d;
                 sm.vals[slot] = a.ordinal_base + i;
-                if (i != run_i) {
-                    if (run_c && a.prot_windows) atomicAdd(a.prot_windows + run_i, run_c);
-                    run_i = i; run_c = 0;
-                }
-                ++run_c;
-            });
-            if (run_c && a.prot_windows) atomicAdd(a.prot_windows + run_i, run_c);
+            }, [&](uint32_t i, uint32_t n_windows) { if (a.prot_windows) atomicAdd(a.prot_windows + i, n_windows); });
         }
         __syncthreads();
         uint64_t key[ES_ITEMS];
@@ -725,6 +749,8 @@ histogram_kernel(const __grid_constant__ SortSegments seg, const uint64_t *__res
     for (uint64_t base = (uint64_t)blockIdx.x * HIST_THREADS * HIST_UNROLL; base < n; base += stride) {
         uint64_t k[HIST_UNROLL];
         bool ok[HIST_UNROLL];
+        int r_base = 0;
+        if (MAIN) while (r_base + 1 < seg.n && base >= seg.start[r_base + 1]) ++r_base;
 #pragma unroll
         for (int u = 0; u < HIST_UNROLL; ++u) {
             const uint64_t idx = base + (uint64_t)u * HIST_THREADS + threadIdx.x;
@@ -732,7 +758,8 @@ histogram_kernel(const __grid_constant__ SortSegments seg, const uint64_t *__res
             k[u] = 0;
             if (ok[u]) {
                 if (MAIN) {
-                    int r = 0;
+                    // the region of the chunk's first record is found once per chunk; records past its end walk on
+                    int r = r_base;
                     while (r + 1 < seg.n && idx >= seg.start[r + 1]) ++r;
                     k[u] = ld_stream_u64(seg.keys[r] + (idx - seg.start[r]));
                 } else {
@@ -790,7 +817,8 @@ static bool wide_lookback(uint64_t capacity) { return capacity >= (1ull << 30); 
 
 size_t onesweep_lookback_bytes(uint64_t capacity) {
     // rows for the smaller (fused) tile cover both kinds of pass
-    return (size_t)(encode_sort_tiles(capacity) + 1) * SIGK_BINS * (wide_lookback(capacity) ? 8 : 4);
+    // (+ one short tile per region of a first pass over several regions)
+    return (size_t)(encode_sort_tiles(capacity) + 1 + SORT_MAX_SEGMENTS) * SIGK_BINS * (wide_lookback(capacity) ? 8 : 4);
 }
 
 cudaError_t onesweep_configure() {
@@ -864,14 +892,18 @@ cudaError_t launch_onesweep_first_pass(const SortSegments &seg, const uint64_t *
                                        uint32_t *ticket, int sm_count, cudaStream_t stream) {
     if (capacity == 0) return cudaSuccess;
     if (seg.n < 1 || seg.n > SORT_MAX_SEGMENTS) return cudaErrorInvalidValue;
-    const unsigned grid = persistent_grid(onesweep_tiles(capacity), sm_count);
+    SortSegments sg = seg;
+    sg.tile_start[0] = 0;                                  // region-aligned tiles: region r owns tiles tile_start[r] .. tile_start[r+1]
+    for (int r = 0; r < sg.n; ++r) sg.tile_start[r + 1] = sg.tile_start[r] + (uint32_t)onesweep_tiles(sg.start[r + 1] - sg.start[r]);
+    // (the look-back rows are sized for capacity / ES_TILE + 1 tiles: up to one short tile per region more than a plain pass)
+    const unsigned grid = persistent_grid(onesweep_tiles(capacity) + SORT_MAX_SEGMENTS, sm_count);
     const uint32_t mask = (1u << nbits) - 1u;
     if (wide_lookback(capacity))
         onesweep_pass_kernel<uint64_t, true><<<grid, OS_THREADS, sizeof(PassSmem), stream>>>(
-            seg, nullptr, nullptr, keys_out, vals_out, n_ptr, nullptr, bit_lo, mask, bin_base, (uint64_t *)lookback, ticket);
+            sg, nullptr, nullptr, keys_out, vals_out, n_ptr, nullptr, bit_lo, mask, bin_base, (uint64_t *)lookback, ticket);
     else
         onesweep_pass_kernel<uint32_t, true><<<grid, OS_THREADS, sizeof(PassSmem), stream>>>(
-            seg, nullptr, nullptr, keys_out, vals_out, n_ptr, nullptr, bit_lo, mask, bin_base, (uint32_t *)lookback, ticket);
+            sg, nullptr, nullptr, keys_out, vals_out, n_ptr, nullptr, bit_lo, mask, bin_base, (uint32_t *)lookback, ticket);
     return cudaGetLastError();
 }
 

@@ -56,10 +56,13 @@ SIGK_D unsigned mask_range(unsigned lo, unsigned hi) {                     // bi
 // The per-protein table comes in two widths (kernels.h): 8 bytes {length, function}, or 4 bytes
 // length | function << 16 when every protein of the job is shorter than 65 535 residues (half the
 // footprint: what decides whether the gathers stay in L2 once several ranks' proteins are in it).
+// (c_meta_shift: SIGK_TEST_META_SPREAD=k spreads the entries 2^k apart, so that a one-GPU run can be given the cache
+// footprint of the job-wide table of a many-GPU run; 0 in production)
+__constant__ uint32_t c_meta_shift;
 template <typename MetaT> SIGK_D ProtMeta load_meta(const MetaT *__restrict__ meta, uint32_t ordinal);
-template <> SIGK_D ProtMeta load_meta<ProtMeta>(const ProtMeta *__restrict__ meta, uint32_t ordinal) { return ld_keep_u32x2(meta + ordinal); }
+template <> SIGK_D ProtMeta load_meta<ProtMeta>(const ProtMeta *__restrict__ meta, uint32_t ordinal) { return ld_keep_u32x2(meta + ((size_t)ordinal << c_meta_shift)); }
 template <> SIGK_D ProtMeta load_meta<uint32_t>(const uint32_t *__restrict__ meta, uint32_t ordinal) {
-    const uint32_t v = ld_keep_u32(meta + ordinal);
+    const uint32_t v = ld_keep_u32(meta + ((size_t)ordinal << c_meta_shift));
     return make_uint2(v & 0xFFFFu, v >> 16);
 }
 
@@ -897,8 +900,8 @@ __global__ void protein_meta_kernel(const uint64_t *__restrict__ starts, const u
     if (i >= n_prot) return;
     (void)seq_id;
     const uint32_t len = (uint32_t)(starts[i + 1] - starts[i]);
-    if (sizeof(MetaT) == sizeof(uint32_t)) reinterpret_cast<uint32_t *>(meta)[i] = len | ((uint32_t)func[i] << 16);     // len < 65 535 (caller)
-    else reinterpret_cast<ProtMeta *>(meta)[i] = make_uint2(len, func[i]);
+    if (sizeof(MetaT) == sizeof(uint32_t)) reinterpret_cast<uint32_t *>(meta)[(size_t)i << c_meta_shift] = len | ((uint32_t)func[i] << 16);     // len < 65 535 (caller)
+    else reinterpret_cast<ProtMeta *>(meta)[(size_t)i << c_meta_shift] = make_uint2(len, func[i]);
     if (seqs_with_func) atomicAdd(seqs_with_func + func[i], 1u);          // seqs_with_func[function_index]++, tcc:160
 }
 
@@ -918,16 +921,19 @@ size_t reduce_work_entries(uint64_t capacity, int sm_count) {
 }
 size_t reduce_long_work_entries(uint64_t capacity) { return (size_t)(capacity / ORD_LONG + 2); }
 
-cudaError_t reduce_configure() { return cudaSuccess; }
+cudaError_t reduce_configure(int meta_shift) {
+    const uint32_t s = (uint32_t)meta_shift;
+    return cudaMemcpyToSymbol(c_meta_shift, &s, sizeof s);
+}
 
 cudaError_t launch_protein_meta(const uint64_t *starts, const uint16_t *func, const uint32_t *seq_id, uint32_t n_prot,
                                 MetaTable meta, uint64_t first, uint32_t *seqs_with_func, cudaStream_t stream) {
     if (n_prot == 0) return cudaSuccess;
     const unsigned grid = (n_prot + 255) / 256;
     if (meta.compact)
-        protein_meta_kernel<uint32_t><<<grid, 256, 0, stream>>>(starts, func, seq_id, n_prot, static_cast<uint32_t *>(meta.p) + first, seqs_with_func);
+        protein_meta_kernel<uint32_t><<<grid, 256, 0, stream>>>(starts, func, seq_id, n_prot, static_cast<uint32_t *>(meta.p) + (first << meta.shift), seqs_with_func);
     else
-        protein_meta_kernel<ProtMeta><<<grid, 256, 0, stream>>>(starts, func, seq_id, n_prot, static_cast<ProtMeta *>(meta.p) + first, seqs_with_func);
+        protein_meta_kernel<ProtMeta><<<grid, 256, 0, stream>>>(starts, func, seq_id, n_prot, static_cast<ProtMeta *>(meta.p) + (first << meta.shift), seqs_with_func);
     return cudaGetLastError();
 }
 

@@ -124,7 +124,7 @@ int do_upload(sigk_handle *h) {
         if (!std::strcmp(force, "compact")) h->meta_compact = h->max_len < 0xFFFFull;
         else if (!std::strcmp(force, "wide")) h->meta_compact = false;
     }
-    CU(h, h->d_meta.reserve(meta_bytes(h->n_prot_global, h->meta_compact)));
+    CU(h, h->d_meta.reserve(meta_bytes(h->n_prot_global, h->meta_compact) << h->meta_shift));
     CU(h, h->d_bitmap.reserve(((uint64_t)h->max_seq_id >> 5) + 1));
     CU(h, h->d_prot_windows.reserve(np));
     CU(h, h->d_prot_rejected.reserve(h->n_prot_global));
@@ -132,7 +132,7 @@ int do_upload(sigk_handle *h) {
     // What depends on the input alone is computed here, once per upload, not once per build: the per-protein table
     // (job-wide with a communicator), seqs_with_func (src/signature_build.tcc:160) and the k-mer range splitters.
     uint32_t launches = 0;
-    const MetaTable meta{h->d_meta.p, h->meta_compact};
+    const MetaTable meta{h->d_meta.p, h->meta_compact, h->meta_shift};
     CU(h, cudaMemsetAsync(h->d_swf.p, 0, SIGK_N_FUNCTION_SLOTS * sizeof(uint32_t), st));
     CU(h, launch_protein_meta(h->d_starts.p, h->d_func.p, h->d_seqid.p, (uint32_t)np, meta, h->ordinal_base, h->d_swf.p, st)); ++launches;
     if (h->comm) {
@@ -179,7 +179,7 @@ int do_build_device(sigk_handle *h) {
     uint8_t *lb_side = h->d_lookback.p + lb_bytes * SORT_MAX_PASSES;
     if (!h->comm) CU(h, cudaMemsetAsync(h->d_lookback.p, 0, lb_bytes * plan.npass, st));
 
-    const MetaTable meta{h->d_meta.p, h->meta_compact};
+    const MetaTable meta{h->d_meta.p, h->meta_compact, h->meta_shift};
     EncodeArgs ea{h->d_res.p, h->total_res, h->d_starts.p, (uint32_t)np, (uint32_t)h->ordinal_base, h->d_slice_prot.p, h->d_prot_windows.p};
     int cur;                                    // ping-pong buffer that holds the output of the first pass
     CU(h, cudaEventRecord(h->ev[EV_ENCODE], st));
@@ -279,7 +279,9 @@ int do_build_device(sigk_handle *h) {
         nvtx_range r("sigk segment reduce");
         CU(h, launch_segment_reduce(h->d_keys[cur].p, h->d_vals[cur].p, &sc->n_records, cap_sort, meta, h->d_rows.p, rl,
                                     h->d_prot_rejected.p, h->d_scan_state.p, &sc->n_segments, order_stats, h->sm_count, st)); launches += 5;
+        CU(h, cudaEventRecord(h->ev[EV_REJ0], st));
         if (h->comm) { if (int rc = comm_reduce_rejected(h)) return rc; }
+        CU(h, cudaEventRecord(h->ev[EV_REJ1], st));
         CU(h, launch_signature_flags(h->d_prot_windows.p, h->d_prot_rejected.p + h->ordinal_base, h->d_seqid.p, (uint32_t)np, h->d_bitmap.p, st)); ++launches;
         CU(h, launch_popcount(h->d_bitmap.p, ((uint64_t)h->max_seq_id >> 5) + 1, &sc->n_seqs_sig, st)); ++launches;
     }
@@ -350,6 +352,7 @@ int do_download(sigk_handle *h) {
     t.histogram_ms = ms(EV_EXCHANGE, EV_HIST);
     t.sort_ms = ms(EV_HIST, EV_SORT);
     t.side_sort_ms = ms(EV_MAIN_SORTED, EV_SORT);
+    t.reduce_comm_ms = ms(EV_REJ0, EV_REJ1);
     t.reduce_ms = ms(EV_SORT, EV_REDUCE);
     t.order_stats_ms = ms(EV_REDUCE, EV_ORDER);
     t.squeeze_ms = ms(EV_ORDER, EV_SQUEEZE);
@@ -400,7 +403,8 @@ int sigk_create(const sigk_config *cfg, sigk_handle **out) {
     for (auto &ev : h->ev) cudaEventCreate(&ev);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
     h->fused = std::getenv("SIGK_NO_FUSED") == nullptr;
-    if ((e = onesweep_configure()) != cudaSuccess || (e = reduce_configure()) != cudaSuccess) {
+    if (const char *sp = std::getenv("SIGK_TEST_META_SPREAD")) h->meta_shift = std::max(0, std::min(6, std::atoi(sp)));
+    if ((e = onesweep_configure()) != cudaSuccess || (e = reduce_configure(h->meta_shift)) != cudaSuccess) {
         g_create_error = std::string("kernel configuration failed (is this an sm_100a device?): ") + cudaGetErrorString(e);
         sigk_destroy(h);
         return SIGK_E_CUDA;

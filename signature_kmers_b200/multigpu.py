@@ -96,7 +96,15 @@ def run_bench(args, rank, world, local_rank, metric, unit):
 
     dist = init_process_group()
     torch.cuda.set_device(local_rank)
-    kw = weak_scaling_params(args.workload, world)
+    # weak scaling (default): config x world, per-GPU work fixed.  --scaling strong: the named configuration as it is,
+    # split over the ranks (config 3 = 20 M proteins / 100 K functions is the one BASELINE.json names for 2/4/8 GPUs)
+    strong = getattr(args, "scaling", "weak") == "strong"
+    if strong:
+        from .synth import CONFIGS
+
+        kw = dict(CONFIGS[args.workload])
+    else:
+        kw = weak_scaling_params(args.workload, world)
     synth = Synth(**kw)
     lo, hi = rank_slice(synth.n_proteins, rank, world)
     builder = GpuSignatureBuilder(device=local_rank, rank=rank, world=world)
@@ -151,10 +159,11 @@ def run_bench(args, rank, world, local_rank, metric, unit):
         passes = int(tm["sort_passes"])
         line = {
             "metric": metric, "value": occ / (ms_per_step * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"{args.workload} x {world} (weak scaling: {kw['n_proteins']} proteins, {kw['n_functions']} functions, "
-                                   f"{kw['n_genomes']} genomes; rank r encodes canonical chunk r)",
+            "config": {"workload": (f"{args.workload} over {world} GPUs (strong scaling: " if strong else f"{args.workload} x {world} (weak scaling: ")
+                                   + f"{kw['n_proteins']} proteins, {kw['n_functions']} functions, {kw['n_genomes']} genomes; rank r encodes canonical chunk r)",
+                       "kept_functions": synth.kept_functions,
                        "occurrences_per_step": occ, "distinct_kmers": counts["n_distinct_kmers"],
                        "partition": "k-mer code ranges by sampled splitters; the encode kernel stores each 12-byte record into its owner GPU's landing zone over NVLink (CUDA IPC), NCCL for the small collectives",
                        "K": 8, "record_bytes": 12, "sort_passes": passes,
@@ -165,7 +174,7 @@ def run_bench(args, rank, world, local_rank, metric, unit):
                     "api": "sigk_build per rank (C ABI, pinned host buffers)"},
             "gpu_launches": int(tm["kernel_launches"]) * args.steps * world,
             "roofline": None,
-            "rank0_stage_ms": {k: tm[k] for k in ("encode_ms", "exchange_ms", "histogram_ms", "sort_ms", "side_sort_ms", "reduce_ms",
+            "rank0_stage_ms": {k: tm[k] for k in ("encode_ms", "exchange_ms", "histogram_ms", "sort_ms", "side_sort_ms", "reduce_ms", "reduce_comm_ms",
                                                    "order_stats_ms", "squeeze_ms", "device_total_ms")},
             "cpu_baseline": None,
         }

@@ -95,8 +95,11 @@ def main():
         dist.barrier()
     # the encode + route kernel instantiations of the larger worlds (2 and 4 counter words: 5..8 and 9..16 ranks),
     # forced on whatever world size this is
-    for words in (("2", "4") if os.environ.get("SIGK_CHECK_WIDE") else ()):
+    # (SIGK_SPLIT_KERNEL=warp selects the round-1 per-warp-slice kernel, kept for comparison; the default is the tile-level
+    # encode_route_kernel, which has one instantiation for every world size)
+    for words in (("1", "2", "4") if os.environ.get("SIGK_CHECK_WIDE") else ()):
         os.environ["SIGK_TEST_SPLIT_WORDS"] = words
+        os.environ["SIGK_SPLIT_KERNEL"] = "warp"
         try:
             for name, p_all in (cases[0], cases[5]):
                 got, per_rank = build_distributed(p_all, rank, world, local_rank)
@@ -105,10 +108,11 @@ def main():
 
                     want, _ = oracle_c.oracle_build(p_all)
                     assert_tables_equal(got, want, tier_b=True, what=f"{name}, {words} counter words")
-                    print(f"multigpu_check ok ({world} ranks): {name} with the {words}-word encode+route kernel", flush=True)
+                    print(f"multigpu_check ok ({world} ranks): {name} with the per-warp-slice encode+route kernel, {words} counter word(s)", flush=True)
                 dist.barrier()
         finally:
             del os.environ["SIGK_TEST_SPLIT_WORDS"]
+            del os.environ["SIGK_SPLIT_KERNEL"]
     # regions too small on every rank: the build grows them to the exact need and encodes again
     os.environ["SIGK_TEST_FORCE_SPLIT_FALLBACK"] = "1"
     try:
