@@ -141,7 +141,9 @@ typedef struct sigk_timings {
     float count_ms;         /* window count pass (digit histograms from the residues) */
     float side_sort_ms;     /* histogram + passes of the side run (records with a lower-case residue) */
     float reduce_comm_ms;   /* multi-GPU: the all-reduce of the per-protein rejected-occurrence counts (inside reduce_ms) */
-    float pad_;
+    float reduce_count_ms;  /* inside reduce_ms: run-length count pass + scan */
+    float reduce_emit_ms;   /* inside reduce_ms: run-length emit pass (single-record groups finished) + open groups */
+    float reduce_groups_ms; /* inside reduce_ms: groups of two or more records */
     uint64_t records_sorted;      /* records this GPU sorted and reduced (its k-mer range's share with a communicator) */
     uint64_t exchange_bytes_out;  /* multi-GPU: bytes of records this GPU stored into other GPUs' landing zones */
 } sigk_timings;
@@ -201,6 +203,10 @@ int sigk_dbg_encode(sigk_handle *h, const sigk_proteins *p,
 /* Stage 2: stable LSD radix sort of (key,value) pairs on key bits [bit_lo,bit_hi). */
 int sigk_dbg_sort_pairs(sigk_handle *h, uint64_t *keys, uint32_t *vals, uint64_t n,
                         int bit_lo, int bit_hi);
+
+/* The order statistics divide with an inlined IEEE division (csrc/length_acc.cuh); this runs it beside the
+ * toolkit's __ddiv_rn on host arrays: inl[i], lib[i] = a[i] / b[i] either way.  They must agree bit for bit. */
+int sigk_dbg_ddiv(sigk_handle *h, const double *a, const double *b, uint64_t n, double *inl, double *lib);
 
 /* ---- consumer side of the table --------------------------------------------
  * Batch form of what FunctionCaller::process_aa_seq does per window (src/call_functions.tcc:276-282):

@@ -116,6 +116,12 @@ class GpuSignatureBuilder:
         self._check(self.lib.sigk_dbg_sort_pairs(self.h, keys.ctypes.data, vals.ctypes.data, len(keys), bit_lo, bit_hi), "sigk_dbg_sort_pairs")
         return keys, vals
 
+    def dbg_ddiv(self, a: np.ndarray, b: np.ndarray):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        inl, lib = np.empty_like(a), np.empty_like(a)
+        self._check(self.lib.sigk_dbg_ddiv(self.h, a.ctypes.data, b.ctypes.data, len(a), inl.ctypes.data, lib.ctypes.data), "sigk_dbg_ddiv")
+        return inl, lib
 
     def lookup(self, residues: np.ndarray, starts: np.ndarray) -> np.ndarray:
         """rows[g] = table row of the call-side window at residue position g, or 0xFFFFFFFF (sigk_lookup)."""

@@ -84,7 +84,9 @@ class SigkTimings(C.Structure):
         ("count_ms", C.c_float),
         ("side_sort_ms", C.c_float),
         ("reduce_comm_ms", C.c_float),
-        ("pad_", C.c_float),
+        ("reduce_count_ms", C.c_float),
+        ("reduce_emit_ms", C.c_float),
+        ("reduce_groups_ms", C.c_float),
         ("records_sorted", C.c_uint64),
         ("exchange_bytes_out", C.c_uint64),
     ]
@@ -268,6 +270,7 @@ EXPORTED_SYMBOLS = [
     "sigk_comm_join",
     "sigk_dbg_encode",
     "sigk_dbg_sort_pairs",
+    "sigk_dbg_ddiv",
     "sigk_lookup",
     "sigk_set_table",
     "sigk_kmer_encode",
@@ -320,6 +323,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         C.c_void_p, C.POINTER(SigkProteins), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64),
     ]
     lib.sigk_dbg_sort_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]
+    lib.sigk_dbg_ddiv.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.sigk_lookup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     lib.sigk_set_table.argtypes = [C.c_void_p, C.POINTER(SigkTable)]
     lib.sigk_kmer_encode.argtypes = [C.c_char_p]

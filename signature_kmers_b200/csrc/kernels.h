@@ -177,12 +177,14 @@ struct ReduceLists {
 // scratch_words: reduce_scan_entries() zeroed words, shared with launch_squeeze_rows of the same build.
 cudaError_t launch_segment_reduce(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
                                   MetaTable meta, uint4 *rows, const ReduceLists &l, uint32_t *prot_rejected,
-                                  uint64_t *scratch_words, uint64_t *n_seg_out, int order_stats, int sm_count, cudaStream_t stream);
+                                  uint64_t *scratch_words, uint64_t *n_seg_out, int order_stats, int sm_count, cudaStream_t stream,
+                                  cudaEvent_t after_count = nullptr, cudaEvent_t after_emit = nullptr);
 // distinct_functions[f] += kept rows whose function_index is f (src/signature_build.tcc:286), from the finished
 // table's column; max_function = largest function index any protein of the job carries.
 cudaError_t launch_function_histogram(const uint16_t *function_index, const uint64_t *n_kept_ptr, uint64_t capacity,
                                       uint32_t max_function, uint32_t *distinct_functions, int sm_count, cudaStream_t stream);
 // median / var of the groups listed in `work`, patched into their rows.
+cudaError_t launch_ddiv_check(const double *a, const double *b, uint64_t n, double *inl, double *lib, cudaStream_t stream);
 cudaError_t launch_order_stats(const uint32_t *vals, MetaTable meta, const OrderWork *work, const uint32_t *n_work,
                                uint32_t *next_work, const OrderWork *work_long, const uint32_t *n_work_long, uint32_t *next_long,
                                uint64_t capacity, uint4 *rows, int sm_count, cudaStream_t stream);

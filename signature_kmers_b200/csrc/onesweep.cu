@@ -484,11 +484,12 @@ onesweep_pass_kernel(const __grid_constant__ SortSegments seg, const uint64_t *_
 // warp-striped and the tile goes through os_sort_tile like any other: main records to their lowest digit's run,
 // records with a lower-case residue to the side bin.
 // The window loop of one fused tile: the valid windows of the tile's ES_WARPS slices, compacted into the staging in
-// canonical order (one pad slot per 16: lanes write runs of ~16 records).  Returns the number of records.  Kept out of
-// line on purpose: it and the sort of the tile each get the whole register budget (inlined, the kernel spilled ~200
-// bytes per thread, and with 220 KB of the SM's 228 KB given to shared memory a spill goes to L2).
+// canonical order (one pad slot per 16: lanes write runs of ~16 records).  Returns the number of records.  Inlined:
+// the kernel then spills ~200 bytes per thread (to L2: 220 KB of the SM's 228 KB are shared memory), and is still
+// faster than with this out of line, where each half has the whole register budget but the call saves and restores
+// around it (config 2, measured back to back: 8.16 ms inlined, 8.50 ms out of line; SIGK_ES_NOINLINE=1 builds the latter).
 #ifndef SIGK_ES_NOINLINE
-#define SIGK_ES_NOINLINE 1
+#define SIGK_ES_NOINLINE 0
 #endif
 #if SIGK_ES_NOINLINE
 #define SIGK_ES_INLINE __noinline__

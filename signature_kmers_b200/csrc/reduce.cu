@@ -183,7 +183,10 @@ constexpr int HS_WARPS = HS_THREADS / 32;
 static_assert(HS_THREADS * HS_ITEMS == RED_BATCH, "one tile per scan entry");
 constexpr int WORK_BLOCK = 64;          // list slots a warp reserves at a time (order-statistics work)
 constexpr int GR_CHUNK = 256;           // group descriptors a warp takes per fetch
-constexpr uint32_t ORD_LONG = 32768;    // groups above this are walked by a whole warp (the tail); below, a lane each
+#ifndef SIGK_ORD_LONG
+#define SIGK_ORD_LONG 32768
+#endif
+constexpr uint32_t ORD_LONG = SIGK_ORD_LONG;    // groups above this are walked by a whole warp (the tail); below, a lane each
 constexpr uint32_t HS_NONE = 0xFFFFFFFFu;
 constexpr int SCAN_THREADS = 1024;      // the single block that scans the per-tile counters
 constexpr int SQ_THREADS = 256;
@@ -717,12 +720,98 @@ squeeze_rows_kernel(const uint4 *__restrict__ rows, const uint64_t *__restrict__
 constexpr int ORD_THREADS = 128;
 constexpr int ORD_BLOCK = 64;       // work entries a warp takes per fetch
 
+// Groups of more than ORD_LONG records: a warp per group and per recurrence.  The recurrences stay
+// sequential, but the warp fetches 32 records at a time (coalesced values, 32 meta gathers in flight,
+// the next batch prefetched) and every lane runs the same accumulator on shuffled samples, so a group
+// does not pay two dependent memory latencies per record.  What is left is the latency of the
+// dependent double-precision chain, sample after sample (config 4: 250 K samples in the largest
+// groups, one chain of ~1200 cycles per sample in the round-1 kernel), so the median (P^2 markers)
+// and the variance — independent recurrences — go to two different warps (kind 0 and 1 of the
+// group's work entry), and the variance warp computes everything that does not depend on the running
+// variance for 32 samples at once: which samples count, their running count n_i and wrapped sum S_i
+// (prefix scans), the term tmp_i^2/(n_i-1) and the refined reciprocal of n_i.
+template <typename MetaT>
+SIGK_D void order_stats_long_group(const uint32_t *__restrict__ vals, const MetaT *__restrict__ meta, const OrderWork w, const uint32_t kind,
+                                   uint4 *__restrict__ rows) {
+    const unsigned lane = threadIdx.x & 31u;
+    __shared__ double s_stage[2][ORD_THREADS / 32][32];
+    double *st_a = s_stage[0][threadIdx.x >> 5], *st_b = s_stage[1][threadIdx.x >> 5];
+    const uint32_t cand = rows[w.row].z & 0xFFFFu;
+    LengthAcc acc;          // every lane carries the same state
+    // newest first: batch b covers records count-1-32b-lane
+    int64_t j = (int64_t)w.count - 1 - (int64_t)lane;
+    ProtMeta m = j >= 0 ? load_meta(meta, __ldg(vals + (uint64_t)w.start + j)) : make_uint2(0, 0xFFFFFFFFu);
+    for (int64_t left = w.count; left > 0; left -= 32) {
+        const int64_t jn = j - 32;
+        const ProtMeta mn = (left > 32 && jn >= 0) ? load_meta(meta, __ldg(vals + (uint64_t)w.start + jn)) : make_uint2(0, 0xFFFFFFFFu);
+        const bool match = m.y == cand;
+        const unsigned mb = __ballot_sync(FULL, match);
+        if (mb) {
+            // the samples that count, compacted into the warp's staging: the chain below reads them in order,
+            // one shared-memory load per sample (issued a sample ahead) instead of a find-bit and a shuffle
+            const uint32_t cnt = __popc(mb), slot = __popc(mb & mask_lt(lane));
+            if (kind == 0) {
+                if (match) st_a[slot] = (double)m.x;
+                __syncwarp();
+                double xn = st_a[0];
+                for (uint32_t k = 0; k < cnt; ++k) {
+                    const double x = xn;
+                    xn = st_a[(k + 1) & 31u];
+                    acc.n += 1;
+                    acc.quantile_step(x);                                // acc(item.protein_length), tcc:271
+                }
+            } else {
+                uint32_t sx = match ? m.x : 0u;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(FULL, sx, o);
+                    if (lane >= (unsigned)o) sx += y;
+                }
+                const uint32_t n_i = acc.n + slot + 1;
+                const uint32_t S_i = (acc.S + sx) & 0xFFFFu;
+                if (match) {
+                    st_a[slot] = n_i > 1 ? LengthAcc::variance_term(m.x, S_i, n_i) : 0.0;
+                    st_b[slot] = recip_refined((double)n_i);
+                }
+                __syncwarp();
+                double tn = st_a[0], yn = st_b[0];
+                for (uint32_t k = 0; k < cnt; ++k) {
+                    const double t = tn, y = yn;
+                    tn = st_a[(k + 1) & 31u]; yn = st_b[(k + 1) & 31u];
+                    acc.n += 1;
+                    if (acc.n > 1) acc.variance_step_pre((double)acc.n, (double)(acc.n - 1), y, t);
+                }
+                acc.S = (acc.S + __shfl_sync(FULL, sx, 31)) & 0xFFFFu;
+            }
+            __syncwarp();
+        }
+        m = mn;
+        j = jn;
+    }
+    if (lane == 0) {
+        uint16_t *half = reinterpret_cast<uint16_t *>(&rows[w.row].w);   // median: low half, var: high half (tcc:278-279)
+        if (kind == 0) half[0] = (uint16_t)u16_from_double(acc.q2);
+        else half[1] = (uint16_t)u16_from_double(acc.var);
+    }
+}
+
+// One kernel for both lists: every warp first serves the long list (two entries per group), then
+// joins the per-lane walk of the ordinary one, so the tail of the long groups runs beside it.
 template <typename MetaT>
 __global__ void __launch_bounds__(ORD_THREADS)
 order_stats_kernel(const uint32_t *__restrict__ vals, const MetaT *__restrict__ meta, const OrderWork *__restrict__ work,
-                   const uint32_t *__restrict__ n_work, uint32_t *__restrict__ next, uint4 *__restrict__ rows) {
-    const uint32_t total = *n_work;
+                   const uint32_t *__restrict__ n_work, uint32_t *__restrict__ next, const OrderWork *__restrict__ work_long,
+                   const uint32_t *__restrict__ n_work_long, uint32_t *__restrict__ next_long, uint4 *__restrict__ rows) {
     const unsigned lane = threadIdx.x & 31u;
+    const uint32_t total_long = *n_work_long * 2u;
+    for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(next_long, 1u);
+        i = __shfl_sync(FULL, i, 0);
+        if (i >= total_long) break;
+        order_stats_long_group(vals, meta, work_long[i >> 1], i & 1u, rows);
+    }
+    const uint32_t total = *n_work;
     // Blocks of ORD_BLOCK entries are handed out dynamically, and a warp takes its next block as soon as
     // one of its lanes is idle — not when all of them are: entries of one family sit together in the list
     // and range from 3 to tens of thousands of samples, so waiting for a block's longest group idled
@@ -772,65 +861,6 @@ order_stats_kernel(const uint32_t *__restrict__ vals, const MetaT *__restrict__ 
                 active = false;
             }
         }
-    }
-}
-
-// Groups of more than ORD_LONG records: one warp per group.  The recurrences stay sequential, but
-// the warp fetches 32 records at a time (coalesced values, 32 meta gathers in flight, the next
-// batch prefetched) and every lane runs the same accumulator on shuffled samples, so a group no
-// longer pays two dependent memory latencies per record (524 ms -> see profiles/ on the Zipf set).
-template <typename MetaT>
-__global__ void __launch_bounds__(128)
-order_stats_long_kernel(const uint32_t *__restrict__ vals, const MetaT *__restrict__ meta, const OrderWork *__restrict__ work,
-                        const uint32_t *__restrict__ n_work, uint32_t *__restrict__ next, uint4 *__restrict__ rows) {
-    const unsigned lane = threadIdx.x & 31u;
-    const uint32_t total = *n_work;
-    for (;;) {
-        uint32_t i = 0;
-        if (lane == 0) i = atomicAdd(next, 1u);
-        i = __shfl_sync(FULL, i, 0);
-        if (i >= total) return;
-        const OrderWork w = work[i];
-        const uint32_t cand = rows[w.row].z & 0xFFFFu;
-        LengthAcc acc;          // every lane carries the same state
-        // newest first: batch b covers records count-1-32b-lane
-        int64_t j = (int64_t)w.count - 1 - (int64_t)lane;
-        ProtMeta m = j >= 0 ? load_meta(meta, __ldg(vals + (uint64_t)w.start + j)) : make_uint2(0, 0xFFFFFFFFu);
-        for (int64_t left = w.count; left > 0; left -= 32) {
-            const int64_t jn = j - 32;
-            const ProtMeta mn = (left > 32 && jn >= 0) ? load_meta(meta, __ldg(vals + (uint64_t)w.start + jn)) : make_uint2(0, 0xFFFFFFFFu);
-            // Per batch of 32 samples the lanes work in parallel on everything that does not depend on
-            // the running state: which samples count (func == best), their running count n_i and wrapped
-            // sum S_i (prefix scans), and the variance term tmp_i^2/(n_i-1) with its two divisions.  Only
-            // var = var (n-1)/n + term_i and the P^2 marker update remain sequential.
-            const bool match = m.y == cand;
-            const unsigned mb = __ballot_sync(FULL, match);
-            if (mb) {
-                uint32_t sx = match ? m.x : 0u;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t y = __shfl_up_sync(FULL, sx, o);
-                    if (lane >= (unsigned)o) sx += y;
-                }
-                const uint32_t n_i = acc.n + __popc(mb & mask_le(lane));
-                const uint32_t S_i = (acc.S + sx) & 0xFFFFu;
-                const double term = (match && n_i > 1) ? LengthAcc::variance_term(m.x, S_i, n_i) : 0.0;
-                unsigned todo = mb;
-                while (todo) {
-                    const int l = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const uint32_t x = __shfl_sync(FULL, m.x, l);
-                    const double t = __shfl_sync(FULL, term, l);
-                    acc.n += 1;
-                    acc.quantile_step((double)x);                       // acc(item.protein_length), tcc:271
-                    if (acc.n > 1) acc.variance_step(acc.n, t);
-                }
-                acc.S = (acc.S + __shfl_sync(FULL, sx, 31)) & 0xFFFFu;
-            }
-            m = mn;
-            j = jn;
-        }
-        if (lane == 0) rows[w.row].w = u16_from_double(acc.q2) | (u16_from_double(acc.var) << 16);
     }
 }
 
@@ -952,7 +982,8 @@ ReduceScratch reduce_scratch(uint64_t *words, uint64_t capacity) {
 template <typename MetaT>
 static cudaError_t segment_reduce_impl(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
                                        const MetaT *meta, uint4 *rows, const ReduceLists &l, uint32_t *prot_rejected,
-                                       const ReduceScratch &sx, uint64_t *n_seg_out, int order_stats, int sm_count, cudaStream_t stream) {
+                                       const ReduceScratch &sx, uint64_t *n_seg_out, int order_stats, int sm_count, cudaStream_t stream,
+                                       cudaEvent_t after_count, cudaEvent_t after_emit) {
     const uint64_t grid = reduce_grid(sm_count);
     const uint64_t tiles = reduce_batches(capacity);
     head_tile_kernel<false, MetaT><<<(unsigned)tiles, HS_THREADS, 0, stream>>>(keys, vals, n_ptr, meta, rows, l.groups, l.long_groups, l.n_long, sx);
@@ -961,6 +992,7 @@ static cudaError_t segment_reduce_impl(const uint64_t *keys, const uint32_t *val
     tile_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(n_ptr, sx, n_seg_out, l.n_groups);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (after_count) cudaEventRecord(after_count, stream);
     head_tile_kernel<true, MetaT><<<(unsigned)tiles, HS_THREADS, 0, stream>>>(keys, vals, n_ptr, meta, rows, l.groups, l.long_groups, l.n_long, sx);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -968,6 +1000,7 @@ static cudaError_t segment_reduce_impl(const uint64_t *keys, const uint32_t *val
                                                                                      l.long_groups, l.n_long);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (after_emit) cudaEventRecord(after_emit, stream);
     group_reduce_kernel<MetaT><<<(unsigned)grid, RED_THREADS, 0, stream>>>(keys, vals, meta, l.groups, l.n_groups, l.next_group, l.long_groups,
                                                                            l.n_long, l.next_long, rows, l.work, l.n_work, l.work_long,
                                                                            l.n_work_long, prot_rejected, sx.rej_tile, order_stats);
@@ -976,24 +1009,35 @@ static cudaError_t segment_reduce_impl(const uint64_t *keys, const uint32_t *val
 
 cudaError_t launch_segment_reduce(const uint64_t *keys, const uint32_t *vals, const uint64_t *n_ptr, uint64_t capacity,
                                   MetaTable meta, uint4 *rows, const ReduceLists &l, uint32_t *prot_rejected,
-                                  uint64_t *scratch_words, uint64_t *n_seg_out, int order_stats, int sm_count, cudaStream_t stream) {
+                                  uint64_t *scratch_words, uint64_t *n_seg_out, int order_stats, int sm_count, cudaStream_t stream,
+                                  cudaEvent_t after_count, cudaEvent_t after_emit) {
     if (capacity == 0) return cudaSuccess;
     const ReduceScratch sx = reduce_scratch(scratch_words, capacity);
     return meta.compact ? segment_reduce_impl(keys, vals, n_ptr, capacity, static_cast<const uint32_t *>(meta.p), rows, l, prot_rejected, sx,
-                                              n_seg_out, order_stats, sm_count, stream)
+                                              n_seg_out, order_stats, sm_count, stream, after_count, after_emit)
                         : segment_reduce_impl(keys, vals, n_ptr, capacity, static_cast<const ProtMeta *>(meta.p), rows, l, prot_rejected, sx,
-                                              n_seg_out, order_stats, sm_count, stream);
+                                              n_seg_out, order_stats, sm_count, stream, after_count, after_emit);
 }
 
 template <typename MetaT>
 static cudaError_t order_stats_impl(const uint32_t *vals, const MetaT *meta, const OrderWork *work, const uint32_t *n_work,
                                     uint32_t *next_work, const OrderWork *work_long, const uint32_t *n_work_long, uint32_t *next_long,
                                     uint4 *rows, int sm_count, cudaStream_t stream) {
-    // the long groups first: they are the tail
-    order_stats_long_kernel<MetaT><<<sm_count * 8, 128, 0, stream>>>(vals, meta, work_long, n_work_long, next_long, rows);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    order_stats_kernel<MetaT><<<sm_count * 16, ORD_THREADS, 0, stream>>>(vals, meta, work, n_work, next_work, rows);
+    order_stats_kernel<MetaT><<<sm_count * 16, ORD_THREADS, 0, stream>>>(vals, meta, work, n_work, next_work, work_long, n_work_long, next_long, rows);
+    return cudaGetLastError();
+}
+
+// the inlined division of length_acc.cuh beside the toolkit's, for tests/test_gpu_parity.py
+__global__ void ddiv_check_kernel(const double *__restrict__ a, const double *__restrict__ b, uint64_t n, double *__restrict__ inl,
+                                  double *__restrict__ lib) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    inl[i] = ddiv_inline(a[i], b[i]);
+    lib[i] = __ddiv_rn(a[i], b[i]);
+}
+cudaError_t launch_ddiv_check(const double *a, const double *b, uint64_t n, double *inl, double *lib, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    ddiv_check_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a, b, n, inl, lib);
     return cudaGetLastError();
 }
 

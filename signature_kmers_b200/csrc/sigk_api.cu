@@ -278,7 +278,8 @@ int do_build_device(sigk_handle *h) {
     {
         nvtx_range r("sigk segment reduce");
         CU(h, launch_segment_reduce(h->d_keys[cur].p, h->d_vals[cur].p, &sc->n_records, cap_sort, meta, h->d_rows.p, rl,
-                                    h->d_prot_rejected.p, h->d_scan_state.p, &sc->n_segments, order_stats, h->sm_count, st)); launches += 5;
+                                    h->d_prot_rejected.p, h->d_scan_state.p, &sc->n_segments, order_stats, h->sm_count, st,
+                                    h->ev[EV_RED_COUNT], h->ev[EV_RED_EMIT])); launches += 5;
         CU(h, cudaEventRecord(h->ev[EV_REJ0], st));
         if (h->comm) { if (int rc = comm_reduce_rejected(h)) return rc; }
         CU(h, cudaEventRecord(h->ev[EV_REJ1], st));
@@ -353,6 +354,11 @@ int do_download(sigk_handle *h) {
     t.sort_ms = ms(EV_HIST, EV_SORT);
     t.side_sort_ms = ms(EV_MAIN_SORTED, EV_SORT);
     t.reduce_comm_ms = ms(EV_REJ0, EV_REJ1);
+    if (h->capacity) {
+        t.reduce_count_ms = ms(EV_SORT, EV_RED_COUNT);
+        t.reduce_emit_ms = ms(EV_RED_COUNT, EV_RED_EMIT);
+        t.reduce_groups_ms = ms(EV_RED_EMIT, EV_REJ0);
+    }
     t.reduce_ms = ms(EV_SORT, EV_REDUCE);
     t.order_stats_ms = ms(EV_REDUCE, EV_ORDER);
     t.squeeze_ms = ms(EV_ORDER, EV_SQUEEZE);
@@ -659,6 +665,28 @@ int sigk_dbg_sort_pairs(sigk_handle *h, uint64_t *keys, uint32_t *vals, uint64_t
     }
     cleanup();
     if (e != cudaSuccess) return h->fail(e == cudaErrorMemoryAllocation ? SIGK_E_NOMEM : SIGK_E_CUDA, "sort: %s", cudaGetErrorString(e));
+    return SIGK_OK;
+}
+
+int sigk_dbg_ddiv(sigk_handle *h, const double *a, const double *b, uint64_t n, double *inl, double *lib) {
+    if (!h) return SIGK_E_INVALID;
+    if (int rc = ensure_device(h)) return rc;
+    if (n == 0) return SIGK_OK;
+    cudaStream_t st = h->stream;
+    DevBuf<double> d[4];
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t x) { if (e == cudaSuccess) e = x; return e == cudaSuccess; };
+    for (auto &x : d) ok(x.reserve(n));
+    if (e == cudaSuccess) {
+        ok(cudaMemcpyAsync(d[0].p, a, n * sizeof(double), cudaMemcpyHostToDevice, st));
+        ok(cudaMemcpyAsync(d[1].p, b, n * sizeof(double), cudaMemcpyHostToDevice, st));
+        ok(launch_ddiv_check(d[0].p, d[1].p, n, d[2].p, d[3].p, st));
+        ok(cudaMemcpyAsync(inl, d[2].p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        ok(cudaMemcpyAsync(lib, d[3].p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        ok(cudaStreamSynchronize(st));
+    }
+    for (auto &x : d) x.release();
+    if (e != cudaSuccess) return h->fail(e == cudaErrorMemoryAllocation ? SIGK_E_NOMEM : SIGK_E_CUDA, "ddiv: %s", cudaGetErrorString(e));
     return SIGK_OK;
 }
 

@@ -174,7 +174,8 @@ def run_bench(args, rank, world, local_rank, metric, unit):
                     "api": "sigk_build per rank (C ABI, pinned host buffers)"},
             "gpu_launches": int(tm["kernel_launches"]) * args.steps * world,
             "roofline": None,
-            "rank0_stage_ms": {k: tm[k] for k in ("encode_ms", "exchange_ms", "histogram_ms", "sort_ms", "side_sort_ms", "reduce_ms", "reduce_comm_ms",
+            "rank0_stage_ms": {k: tm[k] for k in ("encode_ms", "exchange_ms", "histogram_ms", "sort_ms", "side_sort_ms", "reduce_ms", "reduce_count_ms", "reduce_emit_ms",
+                                                   "reduce_groups_ms", "reduce_comm_ms",
                                                    "order_stats_ms", "squeeze_ms", "device_total_ms")},
             "cpu_baseline": None,
         }

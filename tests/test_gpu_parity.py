@@ -159,6 +159,31 @@ def test_split_calls_equal_one_call(gpu):
     assert_tables_equal(a, gpu.result())
 
 
+def test_inlined_division_is_ieee(gpu):
+    """csrc/length_acc.cuh divides with its own inlined sequence (the order statistics of a giant group are one
+    dependent chain of divisions): it must give the bits of __ddiv_rn, which are the bits of the host's division
+    (the reference's Boost accumulators run on the host FPU, round to nearest)."""
+    rng = np.random.default_rng(11)
+    n = 1 << 20
+    parts_a, parts_b = [], []
+    # the operand shapes of the recurrences: height differences over small integers, var * (n-1) over n, +-1 over integers
+    parts_a.append(rng.integers(-70000, 70000, n).astype(np.float64) + rng.random(n)); parts_b.append(rng.integers(1, 400000, n).astype(np.float64))
+    parts_a.append(rng.random(n) * 1e9); parts_b.append(-rng.integers(1, 400000, n).astype(np.float64))
+    parts_a.append(np.where(rng.random(n) < 0.5, 1.0, -1.0)); parts_b.append(rng.integers(2, 1 << 22, n).astype(np.float64))
+    # arbitrary bit patterns (all exponents, denormals, infinities, NaN) and exact zeros
+    parts_a.append(rng.integers(0, 1 << 64, n, dtype=np.uint64).view(np.float64)); parts_b.append(rng.integers(0, 1 << 64, n, dtype=np.uint64).view(np.float64))
+    parts_a.append(np.array([0.0, -0.0, 0.0, -0.0, 5e-324, 1e-310, 1.7e308, 1e-300, 1.0, np.inf, 3.0, np.nan]))
+    parts_b.append(np.array([3.0, 3.0, -3.0, -3.0, 3.0, 7.0, 1e-10, 1e300, 0.0, 2.0, np.inf, 2.0]))
+    a, b = np.concatenate(parts_a), np.concatenate(parts_b)
+    inl, lib = gpu.dbg_ddiv(a, b)
+    with np.errstate(all="ignore"):
+        want = a / b
+    nan = np.isnan(want)
+    assert np.array_equal(np.isnan(inl), nan) and np.array_equal(np.isnan(lib), nan)
+    assert np.array_equal(inl.view(np.uint64)[~nan], lib.view(np.uint64)[~nan])
+    assert np.array_equal(inl.view(np.uint64)[~nan], want.view(np.uint64)[~nan])
+
+
 def test_long_and_giant_groups(gpu, oracle):
     """Groups of 33 .. >1024 records (whole-warp walks, the sampled giant pre-pass),
     mixed functions inside long groups, lengths that differ so P^2 and the
