@@ -203,6 +203,11 @@ def run_gpu(args, rank, world, local_rank):
         return multigpu.run_bench(args, rank, world, local_rank, METRIC, UNIT)
 
     t0 = time.time()
+    # host buffers next to the GPU (see multigpu.bind_to_gpu_numa_node); the CPU baseline below gets all cores back
+    from signature_kmers_b200.multigpu import bind_to_gpu_numa_node
+
+    all_cpus = os.sched_getaffinity(0)
+    bound = bind_to_gpu_numa_node(local_rank)
     builder = GpuSignatureBuilder(device=local_rank)
     synth = Synth.config(args.workload)
     proteins = synth.packed(out_alloc=builder.host_alloc)
@@ -267,6 +272,7 @@ def run_gpu(args, rank, world, local_rank):
     balg = algorithmic_bytes_per_occurrence(passes, fused)
 
     cpu = None
+    os.sched_setaffinity(0, all_cpus)
     if not args.no_cpu_baseline:
         try:
             cpu = cpu_baseline(proteins, args.cpu_sample_proteins, os.cpu_count() or 1)
@@ -286,7 +292,8 @@ def run_gpu(args, rank, world, local_rank):
         },
         "clocks": clk,
         "e2e": {"value": occ / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1e3 * e2e_s, "api": "sigk_build (C ABI, pinned host buffers)"},
+                "ms_per_step": 1e3 * e2e_s, "api": "sigk_build (C ABI, pinned host buffers)",
+                "host_binding": f"process bound to the GPU's {len(bound)} local CPUs while the pinned buffers are allocated" if bound else "none"},
         "gpu_launches": int(tm["kernel_launches"]) * args.steps,
         "roofline": {"bound": "hbm", "kernel": "onesweep_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
@@ -297,7 +304,8 @@ def run_gpu(args, rank, world, local_rank):
                                     "achieved": ((1 + RECORD_BYTES if fused else 2 * RECORD_BYTES) * occ / (pass_ms[0] * 1e-3) / 1e9) if pass_ms and pass_ms[0] > 0 else None}},
         "pipeline": {"b_alg_per_occurrence": balg, "achieved_gbs": balg["total"] * occ / (ms_per_step * 1e-3) / 1e9,
                      "frac_of_peak": balg["total"] * occ / (ms_per_step * 1e-3) / 1e9 / peak,
-                     "stage_ms": {**{k: tm[k] for k in ("encode_ms", "count_ms", "histogram_ms", "sort_ms", "side_sort_ms", "reduce_ms", "order_stats_ms", "squeeze_ms", "device_total_ms")},
+                     "stage_ms": {**{k: tm[k] for k in ("encode_ms", "count_ms", "histogram_ms", "sort_ms", "side_sort_ms", "reduce_ms", "reduce_count_ms", "reduce_emit_ms",
+                                                          "reduce_groups_ms", "order_stats_ms", "squeeze_ms", "device_total_ms")},
                                   "h2d_ms": tm_e2e["h2d_ms"], "d2h_ms": tm_e2e["d2h_ms"]}},
         "cpu_baseline": cpu,
     }

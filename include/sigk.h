@@ -204,6 +204,44 @@ int sigk_dbg_encode(sigk_handle *h, const sigk_proteins *p,
 int sigk_dbg_sort_pairs(sigk_handle *h, uint64_t *keys, uint32_t *vals, uint64_t n,
                         int bit_lo, int bit_hi);
 
+/* ---- FASTA bytes -> proteins on the device ------------------------------------
+ * Replaces FastaParser::parse_char (src/fasta_parser.h:38-144) as driven by
+ * SignatureBuilder<K>::load_kmers_from_fasta (src/signature_build.tcc:84-102): the same five-state machine with
+ * every quirk kept ('\r' dropped; anything but '>' before the first header reported; a blank ends the id and
+ * starts the definition; letters and '*' are sequence, but '*' at the start of a line is reported and dropped;
+ * the '>' that follows a header-only record is reported and that header's letters join the open record).
+ *
+ * sigk_fasta_parse: `bytes` holds n_files files, file f at bytes[file_begin[f] .. file_begin[f] + file_len[f])
+ * with file_begin[f] a multiple of 16, ascending and non-overlapping; every file starts a fresh parser.
+ * The records come back in file order: record r has its '>' at header_pos[r]; its id is the bytes after it up to
+ * id_end[r], its definition the bytes from id_end[r] up to line_end[r] (both minus any '\r'; a position equal to
+ * SIGK_FASTA_NO_POS means "the file ended first"); its sequence is seq_begin[r] .. seq_begin[r+1] of a residue
+ * stream that stays on the device.  errors[] lists what the reference would have reported on stderr
+ * (position | state << 60, state 0 "Missing >", 3 "Bad data character", 4 "Bad id or data character"; at most
+ * SIGK_FASTA_MAX_ERRORS of n_errors).  The arrays belong to the handle and live until the next parse.
+ * The reference calls its callback once more per file at the end of input with whatever is pending — the last
+ * record, already in this table — and then again with an empty record; callers that mirror the callback add those.
+ *
+ * sigk_fasta_commit: record r with keep[r] != 0 becomes a protein with function_index[r] and seq_id[r]
+ * (what load_kmers_from_sequence decides per id, src/signature_build.tcc:118-160, stays with the caller: it is
+ * a string-keyed map lookup).  The kept records' residues are gathered on the device, in record order, into the
+ * input of the next sigk_upload / sigk_build, exactly as if sigk_set_proteins had been given them. */
+#define SIGK_FASTA_NO_POS 0xFFFFFFFFFFFFFFFFull
+#define SIGK_FASTA_MAX_ERRORS 65536
+typedef struct sigk_fasta_records {
+    uint64_t n_records, n_residues, n_errors;
+    const uint64_t *header_pos, *id_end, *line_end;     /* [n_records] */
+    const uint64_t *seq_begin;                          /* [n_records + 1] */
+    const uint64_t *errors;                             /* [min(n_errors, SIGK_FASTA_MAX_ERRORS)] */
+    const uint32_t *error_record;                       /* record open at the error, 0xFFFFFFFF before the first */
+    float h2d_ms, parse_ms, d2h_ms;
+} sigk_fasta_records;
+int sigk_fasta_parse(sigk_handle *h, const uint8_t *bytes, const uint64_t *file_begin, const uint64_t *file_len,
+                     uint64_t n_files, sigk_fasta_records *out);
+int sigk_fasta_commit(sigk_handle *h, const uint8_t *keep, const uint16_t *function_index, const uint32_t *seq_id);
+/* tests: the residue stream of the last parse, n_residues bytes */
+int sigk_dbg_fasta_stream(sigk_handle *h, uint8_t *out);
+
 /* The order statistics divide with an inlined IEEE division (csrc/length_acc.cuh); this runs it beside the
  * toolkit's __ddiv_rn on host arrays: inl[i], lib[i] = a[i] / b[i] either way.  They must agree bit for bit. */
 int sigk_dbg_ddiv(sigk_handle *h, const double *a, const double *b, uint64_t n, double *inl, double *lib);

@@ -116,6 +116,44 @@ class GpuSignatureBuilder:
         self._check(self.lib.sigk_dbg_sort_pairs(self.h, keys.ctypes.data, vals.ctypes.data, len(keys), bit_lo, bit_hi), "sigk_dbg_sort_pairs")
         return keys, vals
 
+    # ---- FASTA bytes -> proteins on the device (sigk_fasta_parse / sigk_fasta_commit) ----
+    def fasta_parse(self, files):
+        """files: list of bytes objects, one per FASTA file.  Returns a dict: the record table as numpy arrays (copies),
+        the concatenated buffer the positions refer to, every file's (begin, length), and the parse timings."""
+        begins, lens, at = [], [], 0
+        for f in files:
+            begins.append(at); lens.append(len(f))
+            at += (len(f) + 15) // 16 * 16
+        buf = np.zeros(max(at, 16), dtype=np.uint8)
+        for b, f in zip(begins, files):
+            buf[b:b + len(f)] = np.frombuffer(f, dtype=np.uint8)
+        fb, fl = np.asarray(begins, dtype=np.uint64), np.asarray(lens, dtype=np.uint64)
+        rec = capi.SigkFastaRecords()
+        self._check(self.lib.sigk_fasta_parse(self.h, buf.ctypes.data, fb.ctypes.data, fl.ctypes.data, len(files), C.byref(rec)), "sigk_fasta_parse")
+        n = int(rec.n_records)
+
+        def arr(ptr, count, dtype=np.uint64):
+            return np.ctypeslib.as_array(ptr, shape=(count,)).astype(dtype, copy=True) if count else np.zeros(0, dtype=dtype)
+
+        ne = min(int(rec.n_errors), capi.SIGK_FASTA_MAX_ERRORS)
+        return {"n_records": n, "n_residues": int(rec.n_residues), "n_errors": int(rec.n_errors),
+                "header_pos": arr(rec.header_pos, n), "id_end": arr(rec.id_end, n), "line_end": arr(rec.line_end, n),
+                "seq_begin": arr(rec.seq_begin, n + 1), "errors": arr(rec.errors, ne), "error_record": arr(rec.error_record, ne, np.uint32),
+                "bytes": buf, "file_begin": fb, "file_len": fl,
+                "h2d_ms": rec.h2d_ms, "parse_ms": rec.parse_ms, "d2h_ms": rec.d2h_ms}
+
+    def fasta_commit(self, keep, function_index, seq_id):
+        keep = np.ascontiguousarray(keep, dtype=np.uint8)
+        function_index = np.ascontiguousarray(function_index, dtype=np.uint16)
+        seq_id = np.ascontiguousarray(seq_id, dtype=np.uint32)
+        self._proteins = None
+        self._check(self.lib.sigk_fasta_commit(self.h, keep.ctypes.data, function_index.ctypes.data, seq_id.ctypes.data), "sigk_fasta_commit")
+
+    def dbg_fasta_stream(self, n_residues: int) -> np.ndarray:
+        out = np.zeros(max(n_residues, 1), dtype=np.uint8)
+        self._check(self.lib.sigk_dbg_fasta_stream(self.h, out.ctypes.data), "sigk_dbg_fasta_stream")
+        return out[:n_residues]
+
     def dbg_ddiv(self, a: np.ndarray, b: np.ndarray):
         a = np.ascontiguousarray(a, dtype=np.float64)
         b = np.ascontiguousarray(b, dtype=np.float64)

@@ -64,6 +64,28 @@ class SigkTable(C.Structure):
     ]
 
 
+class SigkFastaRecords(C.Structure):
+    """struct sigk_fasta_records (include/sigk.h)"""
+    _fields_ = [
+        ("n_records", C.c_uint64),
+        ("n_residues", C.c_uint64),
+        ("n_errors", C.c_uint64),
+        ("header_pos", C.POINTER(C.c_uint64)),
+        ("id_end", C.POINTER(C.c_uint64)),
+        ("line_end", C.POINTER(C.c_uint64)),
+        ("seq_begin", C.POINTER(C.c_uint64)),
+        ("errors", C.POINTER(C.c_uint64)),
+        ("error_record", C.POINTER(C.c_uint32)),
+        ("h2d_ms", C.c_float),
+        ("parse_ms", C.c_float),
+        ("d2h_ms", C.c_float),
+    ]
+
+
+SIGK_FASTA_NO_POS = 0xFFFFFFFFFFFFFFFF
+SIGK_FASTA_MAX_ERRORS = 65536
+
+
 class SigkTimings(C.Structure):
     _fields_ = [
         ("h2d_ms", C.c_float),
@@ -271,6 +293,9 @@ EXPORTED_SYMBOLS = [
     "sigk_dbg_encode",
     "sigk_dbg_sort_pairs",
     "sigk_dbg_ddiv",
+    "sigk_fasta_parse",
+    "sigk_fasta_commit",
+    "sigk_dbg_fasta_stream",
     "sigk_lookup",
     "sigk_set_table",
     "sigk_kmer_encode",
@@ -324,6 +349,9 @@ def load_library(path: str | None = None) -> C.CDLL:
     ]
     lib.sigk_dbg_sort_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]
     lib.sigk_dbg_ddiv.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.sigk_fasta_parse.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(SigkFastaRecords)]
+    lib.sigk_fasta_commit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sigk_dbg_fasta_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.sigk_lookup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     lib.sigk_set_table.argtypes = [C.c_void_p, C.POINTER(SigkTable)]
     lib.sigk_kmer_encode.argtypes = [C.c_char_p]

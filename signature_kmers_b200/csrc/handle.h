@@ -81,6 +81,7 @@ struct sigk_handle {
     sigk::DevBuf<uint32_t> d_seqid, d_slice_prot;
     sigk::DevBuf<uint8_t> d_meta;          // per-protein {length, function}: 4 or 8 bytes each (meta_compact)
     bool meta_compact = false;
+    int rej_shift = 0;                     // SIGK_TEST_REJ_SPREAD: the same for the per-protein rejected-occurrence counters (single GPU only)
     int meta_shift = 0;                    // SIGK_TEST_META_SPREAD: table entries 2^shift apart (cache-footprint experiments)
     uint64_t local_max_len = 0, max_len = 0;   // longest protein: this rank's / the job's
     sigk::DevBuf<uint4> d_rows;
@@ -106,6 +107,17 @@ struct sigk_handle {
     sigk::PinnedBuf<uint32_t> h_distinct, h_swf;
     sigk::PinnedBuf<sigk::DeviceScalars> h_scalars;
     uint64_t h_rows = 0;
+
+    // sigk_fasta_parse / sigk_fasta_commit (fasta.cu)
+    bool input_on_device = false;      // the input arrays were packed on the device by sigk_fasta_commit: sigk_upload copies nothing
+    bool fasta_parsed = false;
+    sigk::DevBuf<uint8_t> d_fa_bytes, d_fa_state, d_fa_stream;
+    sigk::DevBuf<sigk::FastaTile> d_fa_tiles;
+    sigk::DevBuf<uint32_t> d_fa_fn, d_fa_err_rec;
+    sigk::DevBuf<uint64_t> d_fa_packed, d_fa_prefix, d_fa_totals, d_fa_rec, d_fa_err_pos, d_fa_src;     // d_fa_rec: 4 arrays of (records + 1)
+    sigk::PinnedBuf<uint64_t> h_fa_rec, h_fa_totals, h_fa_err_pos;
+    sigk::PinnedBuf<uint32_t> h_fa_err_rec;
+    uint64_t fa_records = 0, fa_residues = 0, fa_errors = 0, fa_rec_stride = 0, fa_bytes = 0;
 
     sigk_timings tm{};
     float h2d_ms = 0;

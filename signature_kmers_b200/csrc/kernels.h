@@ -152,7 +152,7 @@ size_t reduce_group_entries(uint64_t capacity, int sm_count);  // OrderWork entr
 size_t reduce_long_group_entries(uint64_t capacity);           // OrderWork entries: groups of more than 32 records
 size_t reduce_work_entries(uint64_t capacity, int sm_count);   // OrderWork entries: groups whose median/var need the ordered walk
 size_t reduce_long_work_entries(uint64_t capacity);            // ... of those, the ones a whole warp walks
-cudaError_t reduce_configure(int meta_shift);   // meta_shift: SIGK_TEST_META_SPREAD (0 in production)
+cudaError_t reduce_configure(int meta_shift, int rej_shift);   // meta_shift: SIGK_TEST_META_SPREAD (0 in production)
 
 // What a record's protein ordinal is looked up for.  x = protein_length, y = function_index: 8 bytes per
 // protein, or — when every protein of the job is shorter than 65 535 residues — 4 bytes, length | function << 16
@@ -184,6 +184,25 @@ cudaError_t launch_segment_reduce(const uint64_t *keys, const uint32_t *vals, co
 cudaError_t launch_function_histogram(const uint16_t *function_index, const uint64_t *n_kept_ptr, uint64_t capacity,
                                       uint32_t max_function, uint32_t *distinct_functions, int sm_count, cudaStream_t stream);
 // median / var of the groups listed in `work`, patched into their rows.
+// ---- fasta.cu: FASTA bytes -> record table + packed residues ----
+constexpr uint32_t FASTA_TILE = 8192;           // bytes per tile; a tile never spans two files
+struct FastaTile { uint64_t begin; uint32_t n; uint32_t file_start; };
+struct FastaOut {
+    uint8_t *residues = nullptr;                // sequence characters of all records, in file order
+    uint64_t *header_pos = nullptr, *id_end = nullptr, *line_end = nullptr, *seq_begin = nullptr;    // per record
+    uint64_t *err_pos = nullptr;                // position | state << 60 of the reported characters
+    uint32_t *err_record = nullptr;
+    uint64_t err_capacity = 0;
+};
+cudaError_t launch_fasta_tile_functions(const uint8_t *bytes, const FastaTile *tiles, uint32_t n_tiles, uint32_t *tile_fn, uint8_t *tile_state,
+                                        cudaStream_t stream);
+cudaError_t launch_fasta_count(const uint8_t *bytes, const FastaTile *tiles, uint32_t n_tiles, const uint8_t *tile_state, uint64_t *tile_packed,
+                               uint64_t *tile_prefix, uint64_t *totals, cudaStream_t stream);
+cudaError_t launch_fasta_emit(const uint8_t *bytes, const FastaTile *tiles, uint32_t n_tiles, const uint8_t *tile_state, uint64_t *tile_prefix,
+                              const FastaOut &out, cudaStream_t stream);
+cudaError_t launch_fasta_gather(const uint8_t *stream_bytes, const uint64_t *src_begin, const uint64_t *starts, uint32_t n_proteins,
+                                uint8_t *residues, cudaStream_t stream);
+
 cudaError_t launch_ddiv_check(const double *a, const double *b, uint64_t n, double *inl, double *lib, cudaStream_t stream);
 cudaError_t launch_order_stats(const uint32_t *vals, MetaTable meta, const OrderWork *work, const uint32_t *n_work,
                                uint32_t *next_work, const OrderWork *work_long, const uint32_t *n_work_long, uint32_t *next_long,

@@ -66,6 +66,22 @@ template <> SIGK_D ProtMeta load_meta<uint32_t>(const uint32_t *__restrict__ met
     return make_uint2(v & 0xFFFFu, v >> 16);
 }
 
+// the sorted records stream through this stage once per pass
+#ifndef SIGK_RED_EVICT_FIRST
+#define SIGK_RED_EVICT_FIRST 0
+#endif
+#if SIGK_RED_EVICT_FIRST
+SIGK_D uint64_t rec_u64(const uint64_t *p) { return ld_once_u64(p); }
+SIGK_D uint32_t rec_u32(const uint32_t *p) { return ld_once_u32(p); }
+SIGK_D ulonglong2 rec_u64x2(const ulonglong2 *p) { return ld_once_u64x2(p); }
+SIGK_D uint4 rec_u128(const uint4 *p) { return ld_once_u128(p); }
+#else
+SIGK_D uint64_t rec_u64(const uint64_t *p) { return __ldg(p); }
+SIGK_D uint32_t rec_u32(const uint32_t *p) { return __ldg(p); }
+SIGK_D ulonglong2 rec_u64x2(const ulonglong2 *p) { return __ldg(p); }
+SIGK_D uint4 rec_u128(const uint4 *p) { return __ldg(p); }
+#endif
+
 SIGK_D bool keep_rule(uint32_t best_count, uint32_t count) {
     if (2ull * best_count <= count) return false;                          // no strict majority (see header)
     // reject iff (float)best_count < float(count) * 0.8f (tcc:250-257).  0.8*count is at least 0.2
@@ -80,7 +96,9 @@ SIGK_D bool keep_rule(uint32_t best_count, uint32_t count) {
 // at least one of its occurrences lies in a kept group.  encode counts each protein's occurrences,
 // the reduce kernels count the (rare) occurrences that fall into rejected groups, and
 // signature_flags_kernel compares the two per protein.
-SIGK_D void count_rejected(uint32_t *prot_rejected, uint32_t ordinal) { atomicAdd(prot_rejected + ordinal, 1u); }
+// (c_rej_shift: SIGK_TEST_REJ_SPREAD=k spreads the counters 2^k apart — the cache footprint of a many-GPU job's counter array on one GPU; 0 in production)
+__constant__ uint32_t c_rej_shift;
+SIGK_D void count_rejected(uint32_t *prot_rejected, uint32_t ordinal) { atomicAdd(prot_rejected + ((size_t)ordinal << c_rej_shift), 1u); }
 
 struct SegResult {
     bool keep;
@@ -250,12 +268,12 @@ head_tile_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__
     if (tile_n == RED_BATCH) {
         const ulonglong2 *kp = reinterpret_cast<const ulonglong2 *>(keys + tile_start + t0);
 #pragma unroll
-        for (int i = 0; i < HS_ITEMS / 2; ++i) { const ulonglong2 x = __ldg(kp + i); k[2 * i] = x.x; k[2 * i + 1] = x.y; }
+        for (int i = 0; i < HS_ITEMS / 2; ++i) { const ulonglong2 x = rec_u64x2(kp + i); k[2 * i] = x.x; k[2 * i + 1] = x.y; }
         if (EMIT) {
             const uint4 *vp = reinterpret_cast<const uint4 *>(vals + tile_start + t0);
 #pragma unroll
             for (int i = 0; i < HS_ITEMS / 4; ++i) {
-                const uint4 x = __ldg(vp + i);
+                const uint4 x = rec_u128(vp + i);
                 v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
             }
         }
@@ -263,8 +281,8 @@ head_tile_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__
 #pragma unroll
         for (int i = 0; i < HS_ITEMS; ++i) {
             const bool ok = t0 + i < tile_n;
-            k[i] = ok ? __ldg(keys + tile_start + t0 + i) : ~0ull;
-            if (EMIT) v[i] = ok ? __ldg(vals + tile_start + t0 + i) : 0u;
+            k[i] = ok ? rec_u64(keys + tile_start + t0 + i) : ~0ull;
+            if (EMIT) v[i] = ok ? rec_u32(vals + tile_start + t0 + i) : 0u;
         }
     }
     if (lane == 31) s_last[warp] = sigk_key_code(k[HS_ITEMS - 1]);
@@ -525,8 +543,8 @@ group_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
             const unsigned segmask = mask_range(s_lane, e_lane);
             const bool head = act && lane == s_lane;
             const uint64_t p = (uint64_t)gstart + (lane - s_lane);
-            const uint64_t key = act ? __ldg(keys + p) : 0ull;
-            const uint32_t ord = act ? __ldg(vals + p) : 0u;
+            const uint64_t key = act ? rec_u64(keys + p) : 0ull;
+            const uint32_t ord = act ? rec_u32(vals + p) : 0u;
             const ProtMeta m = act ? load_meta(meta, ord) : make_uint2(0, 0);           // len, func
             const uint32_t f = m.y;
             const uint32_t off = sigk_key_offset(key);
@@ -907,7 +925,7 @@ __global__ void signature_flags_kernel(const uint32_t *__restrict__ prot_windows
                                        const uint32_t *__restrict__ seq_id, uint32_t n_prot, uint32_t *__restrict__ bitmap) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_prot) return;
-    if (prot_windows[i] > prot_rejected[i]) {
+    if (prot_windows[i] > prot_rejected[(size_t)i << c_rej_shift]) {
         const uint32_t sid = seq_id[i];
         atomicOr(bitmap + (sid >> 5), 1u << (sid & 31u));
     }
@@ -951,8 +969,10 @@ size_t reduce_work_entries(uint64_t capacity, int sm_count) {
 }
 size_t reduce_long_work_entries(uint64_t capacity) { return (size_t)(capacity / ORD_LONG + 2); }
 
-cudaError_t reduce_configure(int meta_shift) {
-    const uint32_t s = (uint32_t)meta_shift;
+cudaError_t reduce_configure(int meta_shift, int rej_shift) {
+    const uint32_t s = (uint32_t)meta_shift, r = (uint32_t)rej_shift;
+    cudaError_t e = cudaMemcpyToSymbol(c_rej_shift, &r, sizeof r);
+    if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbol(c_meta_shift, &s, sizeof s);
 }
 

@@ -100,12 +100,14 @@ int do_upload(sigk_handle *h) {
     cudaStream_t st = h->stream;
     nvtx_range r_up("sigk upload");
     CU(h, cudaEventRecord(h->ev[EV_START], st));
-    if (total) CU(h, cudaMemcpyAsync(h->d_res.p, p.residues, total, cudaMemcpyHostToDevice, st));
-    CU(h, cudaMemsetAsync(h->d_res.p + total, 0, padded - total, st));
-    CU(h, cudaMemcpyAsync(h->d_starts.p, p.starts, (np + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-    if (np) {
-        CU(h, cudaMemcpyAsync(h->d_func.p, p.function_index, np * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
-        CU(h, cudaMemcpyAsync(h->d_seqid.p, p.seq_id, np * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    if (!h->input_on_device) {          // (sigk_fasta_commit packed the four arrays where they are)
+        if (total) CU(h, cudaMemcpyAsync(h->d_res.p, p.residues, total, cudaMemcpyHostToDevice, st));
+        CU(h, cudaMemsetAsync(h->d_res.p + total, 0, padded - total, st));
+        CU(h, cudaMemcpyAsync(h->d_starts.p, p.starts, (np + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        if (np) {
+            CU(h, cudaMemcpyAsync(h->d_func.p, p.function_index, np * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+            CU(h, cudaMemcpyAsync(h->d_seqid.p, p.seq_id, np * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        }
     }
     CU(h, launch_slice_index(h->d_starts.p, (uint32_t)np, total, h->d_slice_prot.p, st));
     CU(h, cudaEventRecord(h->ev[EV_H2D], st));
@@ -127,7 +129,7 @@ int do_upload(sigk_handle *h) {
     CU(h, h->d_meta.reserve(meta_bytes(h->n_prot_global, h->meta_compact) << h->meta_shift));
     CU(h, h->d_bitmap.reserve(((uint64_t)h->max_seq_id >> 5) + 1));
     CU(h, h->d_prot_windows.reserve(np));
-    CU(h, h->d_prot_rejected.reserve(h->n_prot_global));
+    CU(h, h->d_prot_rejected.reserve(h->n_prot_global << h->rej_shift));
 
     // What depends on the input alone is computed here, once per upload, not once per build: the per-protein table
     // (job-wide with a communicator), seqs_with_func (src/signature_build.tcc:160) and the k-mer range splitters.
@@ -161,7 +163,7 @@ int do_build_device(sigk_handle *h) {
     CU(h, cudaMemsetAsync(h->d_distinct.p, 0, SIGK_N_FUNCTION_SLOTS * sizeof(uint32_t), st));
     CU(h, cudaMemsetAsync(h->d_bitmap.p, 0, (((uint64_t)h->max_seq_id >> 5) + 1) * sizeof(uint32_t), st));
     CU(h, cudaMemsetAsync(h->d_prot_windows.p, 0, std::max<uint64_t>(np, 1) * sizeof(uint32_t), st));
-    CU(h, cudaMemsetAsync(h->d_prot_rejected.p, 0, std::max<uint64_t>(h->n_prot_global, 1) * sizeof(uint32_t), st));
+    CU(h, cudaMemsetAsync(h->d_prot_rejected.p, 0, (std::max<uint64_t>(h->n_prot_global, 1) << h->rej_shift) * sizeof(uint32_t), st));
     CU(h, cudaMemsetAsync(h->d_hist.p, 0, 2 * SORT_MAX_PASSES * SIGK_BINS * sizeof(uint64_t), st));
 
     // the main run is sorted on the 35 code bits, the side run (records with a lower-case residue) on all 43
@@ -410,7 +412,8 @@ int sigk_create(const sigk_config *cfg, sigk_handle **out) {
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
     h->fused = std::getenv("SIGK_NO_FUSED") == nullptr;
     if (const char *sp = std::getenv("SIGK_TEST_META_SPREAD")) h->meta_shift = std::max(0, std::min(6, std::atoi(sp)));
-    if ((e = onesweep_configure()) != cudaSuccess || (e = reduce_configure(h->meta_shift)) != cudaSuccess) {
+    if (const char *sp = std::getenv("SIGK_TEST_REJ_SPREAD")) h->rej_shift = cfg->world > 1 ? 0 : std::max(0, std::min(6, std::atoi(sp)));
+    if ((e = onesweep_configure()) != cudaSuccess || (e = reduce_configure(h->meta_shift, h->rej_shift)) != cudaSuccess) {
         g_create_error = std::string("kernel configuration failed (is this an sm_100a device?): ") + cudaGetErrorString(e);
         sigk_destroy(h);
         return SIGK_E_CUDA;
@@ -431,6 +434,9 @@ void sigk_destroy(sigk_handle *h) {
     h->d_groups.release(); h->d_long_groups.release(); h->d_work.release(); h->d_work_long.release(); h->d_rows.release(); h->d_out_kmer.release(); h->d_out_cols.release();
     h->d_bitmap.release(); h->d_distinct.release(); h->d_swf.release(); h->d_scalars.release();
     h->d_prot_windows.release(); h->d_prot_rejected.release();
+    h->d_fa_bytes.release(); h->d_fa_state.release(); h->d_fa_stream.release(); h->d_fa_tiles.release(); h->d_fa_fn.release(); h->d_fa_err_rec.release();
+    h->d_fa_packed.release(); h->d_fa_prefix.release(); h->d_fa_totals.release(); h->d_fa_rec.release(); h->d_fa_err_pos.release(); h->d_fa_src.release();
+    h->h_fa_rec.release(); h->h_fa_totals.release(); h->h_fa_err_pos.release(); h->h_fa_err_rec.release();
     h->h_kmer.release(); h->h_cols.release(); h->h_distinct.release(); h->h_swf.release(); h->h_scalars.release();
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -468,6 +474,7 @@ int sigk_set_proteins(sigk_handle *h, const sigk_proteins *p) {
     h->local_max_len = max_len;
     h->local_max_function = max_func;
     h->in = *p;
+    h->input_on_device = false;
     h->total_res = total;
     h->max_seq_id = max_sid;
     h->local_max_seq_id = max_sid;
@@ -665,6 +672,145 @@ int sigk_dbg_sort_pairs(sigk_handle *h, uint64_t *keys, uint32_t *vals, uint64_t
     }
     cleanup();
     if (e != cudaSuccess) return h->fail(e == cudaErrorMemoryAllocation ? SIGK_E_NOMEM : SIGK_E_CUDA, "sort: %s", cudaGetErrorString(e));
+    return SIGK_OK;
+}
+
+int sigk_fasta_parse(sigk_handle *h, const uint8_t *bytes, const uint64_t *file_begin, const uint64_t *file_len, uint64_t n_files,
+                     sigk_fasta_records *out) {
+    if (!h) return SIGK_E_INVALID;
+    if (!out || (n_files && (!bytes || !file_begin || !file_len))) return h->fail(SIGK_E_INVALID, "null argument");
+    if (int rc = ensure_device(h)) return rc;
+    h->fasta_parsed = false;
+    // tiles: FASTA_TILE bytes of one file each
+    std::vector<FastaTile> tiles;
+    uint64_t span = 0;
+    for (uint64_t f = 0; f < n_files; ++f) {
+        if (file_begin[f] % 16) return h->fail(SIGK_E_INVALID, "file %llu does not start at a multiple of 16", (unsigned long long)f);
+        if (file_begin[f] < span) return h->fail(SIGK_E_INVALID, "files must ascend and not overlap (file %llu)", (unsigned long long)f);
+        span = file_begin[f] + file_len[f];
+        for (uint64_t off = 0; off < file_len[f]; off += FASTA_TILE)
+            tiles.push_back(FastaTile{file_begin[f] + off, (uint32_t)std::min<uint64_t>(FASTA_TILE, file_len[f] - off), off == 0 ? 1u : 0u});
+    }
+    if (tiles.size() >= 0xFFFFFFFFull) return h->fail(SIGK_E_UNSUPPORTED, "more than 2^32-2 tiles");
+    const uint32_t n_tiles = (uint32_t)tiles.size();
+    cudaStream_t st = h->stream;
+    CU(h, h->d_fa_bytes.reserve(span + 16));
+    CU(h, h->d_fa_tiles.reserve(n_tiles));
+    CU(h, h->d_fa_fn.reserve(n_tiles));
+    CU(h, h->d_fa_state.reserve(n_tiles));
+    CU(h, h->d_fa_packed.reserve(n_tiles));
+    CU(h, h->d_fa_prefix.reserve(3 * (size_t)n_tiles));
+    CU(h, h->d_fa_totals.reserve(3));
+    CU(h, h->h_fa_totals.reserve(3));
+    nvtx_range r("sigk fasta parse");
+    CU(h, cudaEventRecord(h->ev[EV_START], st));
+    if (span) CU(h, cudaMemcpyAsync(h->d_fa_bytes.p, bytes, span, cudaMemcpyHostToDevice, st));
+    if (n_tiles) CU(h, cudaMemcpyAsync(h->d_fa_tiles.p, tiles.data(), n_tiles * sizeof(FastaTile), cudaMemcpyHostToDevice, st));
+    CU(h, cudaEventRecord(h->ev[EV_H2D], st));
+    CU(h, launch_fasta_tile_functions(h->d_fa_bytes.p, h->d_fa_tiles.p, n_tiles, h->d_fa_fn.p, h->d_fa_state.p, st));
+    CU(h, launch_fasta_count(h->d_fa_bytes.p, h->d_fa_tiles.p, n_tiles, h->d_fa_state.p, h->d_fa_packed.p, h->d_fa_prefix.p, h->d_fa_totals.p, st));
+    CU(h, cudaMemcpyAsync(h->h_fa_totals.p, h->d_fa_totals.p, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));           // (the tile vector is free to go; the totals size the outputs)
+    const uint64_t n_seq = h->h_fa_totals.p[0], n_rec = h->h_fa_totals.p[1], n_err = h->h_fa_totals.p[2];
+    const uint64_t err_cap = std::min<uint64_t>(n_err, SIGK_FASTA_MAX_ERRORS);
+    const uint64_t stride = n_rec + 1;
+    CU(h, h->d_fa_stream.reserve(n_seq + 16));
+    CU(h, h->d_fa_rec.reserve(4 * stride));
+    CU(h, h->h_fa_rec.reserve(4 * stride));
+    CU(h, h->d_fa_err_pos.reserve(err_cap));
+    CU(h, h->d_fa_err_rec.reserve(err_cap));
+    CU(h, h->h_fa_err_pos.reserve(err_cap));
+    CU(h, h->h_fa_err_rec.reserve(err_cap));
+    FastaOut o;
+    o.residues = h->d_fa_stream.p;
+    o.header_pos = h->d_fa_rec.p; o.id_end = h->d_fa_rec.p + stride; o.line_end = h->d_fa_rec.p + 2 * stride; o.seq_begin = h->d_fa_rec.p + 3 * stride;
+    o.err_pos = h->d_fa_err_pos.p; o.err_record = h->d_fa_err_rec.p; o.err_capacity = err_cap;
+    CU(h, cudaMemsetAsync(o.id_end, 0xFF, 2 * stride * sizeof(uint64_t), st));       // id_end and line_end: "the file ended first"
+    CU(h, launch_fasta_emit(h->d_fa_bytes.p, h->d_fa_tiles.p, n_tiles, h->d_fa_state.p, h->d_fa_prefix.p, o, st));
+    CU(h, cudaMemcpyAsync(o.seq_begin + n_rec, h->d_fa_totals.p, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    CU(h, cudaEventRecord(h->ev[EV_DEV0], st));
+    CU(h, cudaMemcpyAsync(h->h_fa_rec.p, h->d_fa_rec.p, 4 * stride * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    if (err_cap) {
+        CU(h, cudaMemcpyAsync(h->h_fa_err_pos.p, h->d_fa_err_pos.p, err_cap * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        CU(h, cudaMemcpyAsync(h->h_fa_err_rec.p, h->d_fa_err_rec.p, err_cap * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
+    CU(h, cudaEventRecord(h->ev[EV_D2H], st));
+    CU(h, cudaStreamSynchronize(st));
+    h->fa_records = n_rec; h->fa_residues = n_seq; h->fa_errors = n_err; h->fa_rec_stride = stride; h->fa_bytes = span;
+    h->fasta_parsed = true;
+    out->n_records = n_rec; out->n_residues = n_seq; out->n_errors = n_err;
+    out->header_pos = h->h_fa_rec.p; out->id_end = h->h_fa_rec.p + stride; out->line_end = h->h_fa_rec.p + 2 * stride; out->seq_begin = h->h_fa_rec.p + 3 * stride;
+    out->errors = h->h_fa_err_pos.p; out->error_record = h->h_fa_err_rec.p;
+    cudaEventElapsedTime(&out->h2d_ms, h->ev[EV_START], h->ev[EV_H2D]);
+    cudaEventElapsedTime(&out->parse_ms, h->ev[EV_H2D], h->ev[EV_DEV0]);
+    cudaEventElapsedTime(&out->d2h_ms, h->ev[EV_DEV0], h->ev[EV_D2H]);
+    return SIGK_OK;
+}
+
+int sigk_fasta_commit(sigk_handle *h, const uint8_t *keep, const uint16_t *function_index, const uint32_t *seq_id) {
+    if (!h) return SIGK_E_INVALID;
+    if (!h->fasta_parsed) return h->fail(SIGK_E_INVALID, "sigk_fasta_parse has not been called");
+    const uint64_t n_rec = h->fa_records;
+    if (n_rec && (!keep || !function_index || !seq_id)) return h->fail(SIGK_E_INVALID, "null argument");
+    if (int rc = ensure_device(h)) return rc;
+    const uint64_t *seq_begin = h->h_fa_rec.p + 3 * h->fa_rec_stride;
+    std::vector<uint64_t> starts(1, 0), src;
+    std::vector<uint16_t> func;
+    std::vector<uint32_t> sid;
+    uint32_t max_sid = 0, max_func = 0;
+    uint64_t max_len = 0;
+    for (uint64_t r = 0; r < n_rec; ++r) {
+        if (!keep[r]) continue;
+        if (function_index[r] == SIGK_UNDEFINED_FUNCTION)
+            return h->fail(SIGK_E_INVALID, "record %llu has UndefinedFunction; the host must skip it (src/signature_build.tcc:155)", (unsigned long long)r);
+        const uint64_t len = seq_begin[r + 1] - seq_begin[r];
+        src.push_back(seq_begin[r]);
+        starts.push_back(starts.back() + len);
+        func.push_back(function_index[r]);
+        sid.push_back(seq_id[r]);
+        max_sid = std::max(max_sid, seq_id[r]);
+        max_func = std::max<uint32_t>(max_func, function_index[r]);
+        max_len = std::max(max_len, len);
+    }
+    const uint64_t np = func.size(), total = starts.back();
+    if (np >= 0xFFFFFFFFull) return h->fail(SIGK_E_UNSUPPORTED, "more than 2^32-2 proteins");
+    if (total >= 0xFFFFFFFFull) return h->fail(SIGK_E_UNSUPPORTED, "more than 2^32-2 residues on one GPU");
+    const uint64_t padded = encode_tiles(total) * ENC_TILE + ENC_PAD;
+    cudaStream_t st = h->stream;
+    CU(h, h->d_res.reserve(padded));
+    CU(h, h->d_starts.reserve(np + 1));
+    CU(h, h->d_func.reserve(np));
+    CU(h, h->d_seqid.reserve(np));
+    CU(h, h->d_fa_src.reserve(np));
+    nvtx_range r("sigk fasta commit");
+    CU(h, cudaMemcpyAsync(h->d_starts.p, starts.data(), (np + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    if (np) {
+        CU(h, cudaMemcpyAsync(h->d_fa_src.p, src.data(), np * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        CU(h, cudaMemcpyAsync(h->d_func.p, func.data(), np * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+        CU(h, cudaMemcpyAsync(h->d_seqid.p, sid.data(), np * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    }
+    CU(h, launch_fasta_gather(h->d_fa_stream.p, h->d_fa_src.p, h->d_starts.p, (uint32_t)np, h->d_res.p, st));
+    CU(h, cudaMemsetAsync(h->d_res.p + total, 0, padded - total, st));
+    CU(h, cudaStreamSynchronize(st));           // (the host vectors go out of scope)
+    h->in = sigk_proteins{nullptr, nullptr, nullptr, nullptr, np};
+    h->input_on_device = true;
+    h->local_max_len = max_len;
+    h->local_max_function = max_func;
+    h->total_res = total;
+    h->max_seq_id = max_sid;
+    h->local_max_seq_id = max_sid;
+    h->have_input = true;
+    h->uploaded = h->built = h->downloaded = false;
+    return SIGK_OK;
+}
+
+int sigk_dbg_fasta_stream(sigk_handle *h, uint8_t *out) {
+    if (!h) return SIGK_E_INVALID;
+    if (!h->fasta_parsed) return h->fail(SIGK_E_INVALID, "sigk_fasta_parse has not been called");
+    if (h->fa_residues) {
+        CU(h, cudaMemcpyAsync(out, h->d_fa_stream.p, h->fa_residues, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+    }
     return SIGK_OK;
 }
 

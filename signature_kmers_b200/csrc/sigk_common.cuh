@@ -167,6 +167,36 @@ SIGK_D uint2 ld_keep_u32x2(const uint2 *p) {
     return v;
 }
 
+// Loads of data that is read once (the sorted records in the reduce stage): L1 no-allocate and evict-first in L2,
+// the counterpart of ld_keep_* — the stream then recycles its own L2 lines instead of the table's.
+SIGK_D uint64_t l2_evict_first_policy() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+SIGK_D uint64_t ld_once_u64(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(l2_evict_first_policy()));
+    return v;
+}
+SIGK_D uint32_t ld_once_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_evict_first_policy()));
+    return v;
+}
+SIGK_D ulonglong2 ld_once_u64x2(const ulonglong2 *p) {
+    ulonglong2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u64 {%0,%1}, [%2], %3;" : "=l"(v.x), "=l"(v.y) : "l"(p), "l"(l2_evict_first_policy()));
+    return v;
+}
+SIGK_D uint4 ld_once_u128(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p), "l"(l2_evict_first_policy()));
+    return v;
+}
+
 // ---- single-value chained scan (decoupled look-back) ------------------------
 // state[t] = flag << 62 | value.  flag 0 = not ready, 1 = tile aggregate,
 // 2 = inclusive prefix.  Tiles are tickets taken in launch order, so every

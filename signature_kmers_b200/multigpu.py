@@ -23,6 +23,36 @@ def rank_slice(n: int, rank: int, world: int):
     return n * rank // world, n * (rank + 1) // world
 
 
+def bind_to_gpu_numa_node(device: int):
+    """Pin this process to the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI function) before any
+    pinned host buffer exists: cudaMallocHost places pages near the calling thread, and with one process per GPU
+    and no binding every rank's result buffers tend to land on one socket — the device-to-host copies of the other
+    socket's GPUs then cross the inter-socket link (round-1 8-GPU run: 86 GB/s for all eight downloads together).
+    Returns the CPU list it bound to, or None when the topology cannot be read (then nothing changes)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(visible.split(",")[device]) if visible and all(x.strip().isdigit() for x in visible.split(",")) else device
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        with open(f"/sys/bus/pci/devices/{int(dom, 16):04x}:{rest.lower()}/local_cpulist") as f:
+            text = f.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 def init_process_group():
     import torch
     import torch.distributed as dist
@@ -107,6 +137,7 @@ def run_bench(args, rank, world, local_rank, metric, unit):
         kw = weak_scaling_params(args.workload, world)
     synth = Synth(**kw)
     lo, hi = rank_slice(synth.n_proteins, rank, world)
+    bound = bind_to_gpu_numa_node(local_rank)
     builder = GpuSignatureBuilder(device=local_rank, rank=rank, world=world)
     join_communicator(builder, rank, world)
     proteins = synth.packed(lo, hi, out_alloc=builder.host_alloc)
@@ -153,6 +184,13 @@ def run_bench(args, rank, world, local_rank, metric, unit):
     sm = stats.clone()
     dist.all_reduce(sm, op=dist.ReduceOp.SUM)
     clk = sampler.stop() if sampler else None
+    stage_keys = ("encode_ms", "exchange_ms", "histogram_ms", "sort_ms", "side_sort_ms", "reduce_ms", "reduce_count_ms", "reduce_emit_ms",
+                  "reduce_groups_ms", "reduce_comm_ms", "order_stats_ms", "squeeze_ms", "device_total_ms")
+    # every rank's stage times of its last build: a stage that holds a collective absorbs the other ranks' lateness,
+    # so rank 0's column alone cannot say which stage is slow
+    st = torch.tensor([float(tm[k]) for k in stage_keys] + [float(tm["records_sorted"])], dtype=torch.float64)
+    all_st = [torch.zeros_like(st) for _ in range(world)]
+    dist.all_gather(all_st, st)
     if rank == 0:
         occ = counts["n_occurrences"]          # job-wide after the statistics reduction
         ms_per_step = float(mx[0]) / args.steps
@@ -171,12 +209,14 @@ def run_bench(args, rank, world, local_rank, metric, unit):
             "clocks": clk,
             "e2e": {"value": occ / float(mx[1]), "unit": unit, "h2d_bytes_per_step": int(sm[3]),
                     "d2h_bytes_per_step": int(sm[2]) * 18, "ms_per_step": 1e3 * float(mx[1]),
-                    "api": "sigk_build per rank (C ABI, pinned host buffers)"},
+                    "api": "sigk_build per rank (C ABI, pinned host buffers)",
+                    "host_binding": f"each rank bound to its GPU's local CPUs (rank 0: {len(bound)} CPUs)" if bound else "none (topology unreadable)"},
             "gpu_launches": int(tm["kernel_launches"]) * args.steps * world,
             "roofline": None,
-            "rank0_stage_ms": {k: tm[k] for k in ("encode_ms", "exchange_ms", "histogram_ms", "sort_ms", "side_sort_ms", "reduce_ms", "reduce_count_ms", "reduce_emit_ms",
-                                                   "reduce_groups_ms", "reduce_comm_ms",
-                                                   "order_stats_ms", "squeeze_ms", "device_total_ms")},
+            "rank0_stage_ms": {k: tm[k] for k in stage_keys},
+            "stage_ms_min_over_ranks": {k: min(float(t[i]) for t in all_st) for i, k in enumerate(stage_keys)},
+            "stage_ms_max_over_ranks": {k: max(float(t[i]) for t in all_st) for i, k in enumerate(stage_keys)},
+            "records_sorted_per_rank": [int(t[len(stage_keys)]) for t in all_st],
             "cpu_baseline": None,
         }
         pass_ms = list(tm["pass_ms"][:passes])

@@ -1,0 +1,106 @@
+#!/usr/bin/env python
+"""Times sigk_fasta_parse + sigk_fasta_commit on a config's proteins written out as FASTA text, beside the host
+reader (signature_kmers_b200/host FastaReader, one thread, on a sample).  Prints one JSON line.
+  python tools/fasta_bench.py [--workload config2] [--steps 3]"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def fasta_text(proteins, lo, hi):
+    """>pNNNNNNNNN\\nSEQUENCE\\n per protein, vectorised."""
+    starts = proteins.starts[lo:hi + 1].astype(np.int64)
+    lens = np.diff(starts)
+    n = hi - lo
+    hdr = 12                                            # '>' 'p' 9 digits '\n'
+    rec_len = lens + hdr + 1
+    rec_start = np.concatenate([[0], np.cumsum(rec_len)])
+    out = np.full(int(rec_start[-1]), ord("\n"), dtype=np.uint8)
+    out[rec_start[:-1]] = ord(">")
+    out[rec_start[:-1] + 1] = ord("p")
+    ids = np.arange(lo, hi, dtype=np.int64)
+    for d in range(9):
+        out[rec_start[:-1] + 2 + d] = ord("0") + (ids // 10 ** (8 - d)) % 10
+    shift = rec_start[:-1] + hdr - (starts[:-1] - starts[0])
+    dest = np.arange(int(starts[-1] - starts[0]), dtype=np.int64) + np.repeat(shift, lens)
+    out[dest] = proteins.residues[starts[0]:starts[-1]]
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="config2")
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--files", type=int, default=20)
+    args = ap.parse_args()
+    from signature_kmers_b200.builder import GpuSignatureBuilder
+    from signature_kmers_b200.synth import Synth
+
+    b = GpuSignatureBuilder(device=0)
+    synth = Synth.config(args.workload)
+    proteins = synth.packed()
+    n = proteins.n_proteins
+    cuts = [n * k // args.files for k in range(args.files + 1)]
+    texts = [fasta_text(proteins, a, c) for a, c in zip(cuts, cuts[1:])]
+    begins, at = [], 0
+    for t in texts:
+        begins.append(at)
+        at += (len(t) + 15) // 16 * 16
+    buf = b.host_alloc(at)                               # pinned, like the file cache a loader would read into
+    for bg, t in zip(begins, texts):
+        buf[bg:bg + len(t)] = t
+    fb = np.asarray(begins, dtype=np.uint64)
+    fl = np.asarray([len(t) for t in texts], dtype=np.uint64)
+    from signature_kmers_b200 import capi
+
+    rec = capi.SigkFastaRecords()
+    best = None
+    for _ in range(args.steps + 1):
+        t0 = time.perf_counter()
+        b._check(b.lib.sigk_fasta_parse(b.h, buf.ctypes.data, fb.ctypes.data, fl.ctypes.data, len(texts), C.byref(rec)), "sigk_fasta_parse")
+        wall = time.perf_counter() - t0
+        cur = {"wall_ms": 1e3 * wall, "h2d_ms": rec.h2d_ms, "parse_ms": rec.parse_ms, "d2h_ms": rec.d2h_ms}
+        if best is None or cur["wall_ms"] < best["wall_ms"]:
+            best = cur
+    assert rec.n_records == n and rec.n_errors == 0 and rec.n_residues == len(proteins.residues)
+    keep = np.ones(n, dtype=np.uint8)
+    t0 = time.perf_counter()
+    b.fasta_commit(keep, proteins.function_index, proteins.seq_id)
+    commit_ms = 1e3 * (time.perf_counter() - t0)
+    got = b.build()
+    b.set_proteins(proteins)
+    want = b.build()
+    same = bool(np.array_equal(got.kmer, want.kmer) and np.array_equal(got.median, want.median) and np.array_equal(got.var, want.var)
+                and np.array_equal(got.function_index, want.function_index) and got.num_seqs_with_a_signature == want.num_seqs_with_a_signature)
+
+    # the host reader on the first file, one thread
+    host = C.CDLL(os.path.join(ROOT, "signature_kmers_b200", "libsigk_host.so"))
+    host.sigk_host_fasta_parse.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]
+    host.sigk_host_fasta_parse.restype = C.c_uint64
+    sample = texts[0].tobytes()
+    out = C.create_string_buffer(2 * len(sample) + 64)
+    t0 = time.perf_counter()
+    host.sigk_host_fasta_parse(sample, len(sample), out, len(out))
+    host_s = time.perf_counter() - t0
+    total_bytes = int(fl.sum())
+    print(json.dumps({
+        "what": "FASTA text -> device-resident proteins", "workload": args.workload, "files": len(texts), "fasta_bytes": total_bytes,
+        "records": int(rec.n_records), "residues": int(rec.n_residues),
+        "gpu": dict(best, commit_ms=commit_ms, parse_gbs=total_bytes / (best["parse_ms"] * 1e-3) / 1e9,
+                    end_to_end_gbs=total_bytes / (best["wall_ms"] * 1e-3) / 1e9),
+        "host_reader_one_thread": {"sample_bytes": len(sample), "seconds": host_s, "gbs": len(sample) / host_s / 1e9},
+        "table_equal_to_array_input": same,
+    }))
+    b.close()
+
+
+if __name__ == "__main__":
+    main()
