@@ -36,13 +36,18 @@ constexpr int FA_BPT = 16;                          // bytes per thread: one 128
 constexpr int FA_WARPS = FA_THREADS / 32;
 static_assert(FA_THREADS * FA_BPT == FASTA_TILE, "tile size");
 
-enum : uint32_t { S_START = 0, S_ID = 1, S_DEF = 2, S_DATA = 3, S_LINE = 4 };
+// A state is kept as its shift amount 5 * s, so that "look the state up in a packed table" is a shift and a mask:
+// a transition function is five 5-bit fields (the image of state s in bits [5s, 5s+5)), and so is the table of
+// what a byte class does in every state.
+enum : uint32_t { S_START = 0, S_ID = 5, S_DEF = 10, S_DATA = 15, S_LINE = 20 };
 enum : uint32_t { C_CR = 0, C_NL = 1, C_GT = 2, C_BLANK = 3, C_ALPHA = 4, C_STAR = 5, C_OTHER = 6 };
+enum : uint32_t { A_SEQ = 1, A_RECORD = 2, A_ID_END = 4, A_LINE_END = 8, A_ERROR = 16 };
 
-constexpr uint32_t pack5(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e) { return a | b << 3 | c << 6 | d << 9 | e << 12; }
+constexpr uint32_t pack5(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e) { return a | b << 5 | c << 10 | d << 15 | e << 20; }
 constexpr uint32_t FN_IDENTITY = pack5(S_START, S_ID, S_DEF, S_DATA, S_LINE);
-// next state per class, indexed by the current state (START, ID, DEF, DATA, LINE)
-__constant__ uint32_t c_fa_next[7] = {
+constexpr uint32_t FN_ONES = pack5(1, 1, 1, 1, 1);
+// per class: the next state and what the byte does, indexed by the current state (START, ID, DEF, DATA, LINE)
+constexpr uint32_t FA_NEXT[7] = {
     FN_IDENTITY,                                        // '\r'
     pack5(S_START, S_DATA, S_DATA, S_LINE, S_LINE),     // '\n'
     pack5(S_ID, S_ID, S_DEF, S_DATA, S_ID),             // '>'
@@ -51,6 +56,17 @@ __constant__ uint32_t c_fa_next[7] = {
     FN_IDENTITY,                                        // '*'
     FN_IDENTITY,                                        // anything else
 };
+constexpr uint32_t FA_ACT[7] = {
+    0,                                                                  // '\r': dropped before the state is looked at
+    pack5(A_ERROR, A_ID_END | A_LINE_END, A_LINE_END, 0, 0),            // '\n'
+    pack5(A_RECORD, 0, 0, A_ERROR, A_RECORD),                           // '>'
+    pack5(A_ERROR, A_ID_END, 0, A_ERROR, A_ERROR),                      // blank
+    pack5(A_ERROR, 0, 0, A_SEQ, A_SEQ),                                 // letter
+    pack5(A_ERROR, 0, 0, A_SEQ, A_ERROR),                               // '*'
+    pack5(A_ERROR, 0, 0, A_ERROR, A_ERROR),                             // anything else
+};
+__constant__ uint32_t c_fa_next[7] = {FA_NEXT[0], FA_NEXT[1], FA_NEXT[2], FA_NEXT[3], FA_NEXT[4], FA_NEXT[5], FA_NEXT[6]};
+__constant__ uint32_t c_fa_act[7] = {FA_ACT[0], FA_ACT[1], FA_ACT[2], FA_ACT[3], FA_ACT[4], FA_ACT[5], FA_ACT[6]};
 
 SIGK_D uint32_t fa_class(uint32_t c) {
     if (c == '\r') return C_CR;
@@ -61,48 +77,41 @@ SIGK_D uint32_t fa_class(uint32_t c) {
     if (c == '*') return C_STAR;
     return C_OTHER;
 }
-SIGK_D uint32_t fa_apply(uint32_t f, uint32_t s) { return (f >> (3u * s)) & 7u; }
+SIGK_D uint32_t fa_apply(uint32_t f, uint32_t s) { return (f >> s) & 31u; }
 // first f, then g
 SIGK_D uint32_t fa_compose(uint32_t f, uint32_t g) {
     uint32_t r = 0;
 #pragma unroll
-    for (uint32_t s = 0; s < 5; ++s) r |= fa_apply(g, fa_apply(f, s)) << (3u * s);
+    for (uint32_t i = 0; i < 25; i += 5) r |= fa_apply(g, fa_apply(f, i)) << i;
     return r;
 }
-constexpr uint32_t FN_ONES = pack5(1, 1, 1, 1, 1);
 SIGK_D uint32_t fa_constant(uint32_t s) { return s * FN_ONES; }
 
-// what a byte of class c does when the machine is in state s
-struct FaAction { bool seq, record, id_end, line_end, error; };
-SIGK_D FaAction fa_action(uint32_t s, uint32_t c) {
-    FaAction a;
-    a.seq = (s == S_DATA && (c == C_ALPHA || c == C_STAR)) || (s == S_LINE && c == C_ALPHA);
-    a.record = (s == S_START || s == S_LINE) && c == C_GT;
-    a.id_end = s == S_ID && (c == C_BLANK || c == C_NL);
-    a.line_end = (s == S_ID || s == S_DEF) && c == C_NL;
-    a.error = c != C_CR && ((s == S_START && c != C_GT) || (s == S_DATA && (c == C_BLANK || c == C_GT || c == C_OTHER)) ||
-                            (s == S_LINE && (c == C_STAR || c == C_BLANK || c == C_OTHER)));
-    return a;
+// byte -> {next-state table, action table} in shared memory: one 64-bit load per byte, off the state chain
+SIGK_D void fa_fill_lut(uint2 *s_lut) {
+    if (threadIdx.x < 256) {
+        const uint32_t c = fa_class(threadIdx.x);
+        s_lut[threadIdx.x] = make_uint2(c_fa_next[c], c_fa_act[c]);
+    }
+    __syncthreads();
 }
-
-// the thread's 16 bytes (bytes past the tile's end read as '\r': no transition, no output)
-SIGK_D void fa_load(const uint8_t *__restrict__ bytes, const FastaTile &t, uint32_t cls[FA_BPT], uint8_t raw[FA_BPT]) {
+// the thread's 16 bytes (bytes past the tile's end behave like '\r': no transition, no output)
+SIGK_D void fa_load(const uint8_t *__restrict__ bytes, const FastaTile &t, const uint2 *s_lut, uint32_t nx[FA_BPT], uint32_t act[FA_BPT], uint4 &q) {
     const uint32_t off = threadIdx.x * FA_BPT;
-    uint4 q = make_uint4(0, 0, 0, 0);
+    q = make_uint4(0, 0, 0, 0);
     if (off < t.n) q = *reinterpret_cast<const uint4 *>(bytes + t.begin + off);      // (file starts are 16-byte aligned, the buffer is padded)
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
     for (int i = 0; i < FA_BPT; ++i) {
-        const uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-        raw[i] = (uint8_t)c;
-        cls[i] = off + i < t.n ? fa_class(c) : (uint32_t)C_CR;
+        const uint2 e = s_lut[(w[i >> 2] >> (8 * (i & 3))) & 0xFFu];
+        const bool in = off + i < t.n;
+        nx[i] = in ? e.x : FN_IDENTITY;
+        act[i] = in ? e.y : 0u;
     }
 }
-SIGK_D uint32_t fa_thread_fn(const uint32_t cls[FA_BPT]) {
-    uint32_t f = FN_IDENTITY;
-#pragma unroll
-    for (int i = 0; i < FA_BPT; ++i) f = fa_compose(f, c_fa_next[cls[i]]);
-    return f;
+SIGK_D uint32_t fa_byte(const uint4 &q, int i) {
+    const uint32_t w = i < 4 ? q.x : i < 8 ? q.y : i < 12 ? q.z : q.w;
+    return (w >> (8 * (i & 3))) & 0xFFu;
 }
 
 // exclusive scan of the threads' functions in thread order; *total = the tile's function
@@ -120,25 +129,32 @@ SIGK_D uint32_t fa_block_scan_fn(uint32_t f, uint32_t *s_warp, uint32_t *total) 
     __syncthreads();
     uint32_t before = FN_IDENTITY;
     for (unsigned w = 0; w < warp; ++w) before = fa_compose(before, s_warp[w]);
-    if (total) {
-        uint32_t all = before;
-        for (unsigned w = warp; w < FA_WARPS; ++w) all = fa_compose(all, s_warp[w]);
-        *total = all;
-    }
-    __syncthreads();
+    uint32_t all = before;
+    for (unsigned w = warp; w < FA_WARPS; ++w) all = fa_compose(all, s_warp[w]);
+    *total = all;
     return fa_compose(before, excl);
 }
 
-// ---- sweep 1: the transition function of every tile -------------------------------------------------------------
+// ---- sweep 1: every 16-byte chunk's function, scanned inside its tile; the transition function of every tile -----
 __global__ void __launch_bounds__(FA_THREADS)
-fasta_tile_fn_kernel(const uint8_t *__restrict__ bytes, const FastaTile *__restrict__ tiles, uint32_t *__restrict__ tile_fn) {
+fasta_tile_fn_kernel(const uint8_t *__restrict__ bytes, const FastaTile *__restrict__ tiles, uint32_t *__restrict__ chunk_before,
+                     uint32_t *__restrict__ tile_fn) {
     __shared__ uint32_t s_warp[FA_WARPS];
+    __shared__ uint2 s_lut[256];
+    fa_fill_lut(s_lut);
     const FastaTile t = tiles[blockIdx.x];
-    uint32_t cls[FA_BPT];
-    uint8_t raw[FA_BPT];
-    fa_load(bytes, t, cls, raw);
+    uint32_t nx[FA_BPT], act[FA_BPT];
+    uint4 q;
+    fa_load(bytes, t, s_lut, nx, act, q);
+    // the chunk's function: where each of the five states ends up, five independent chains
+    uint32_t s0 = S_START, s1 = S_ID, s2 = S_DEF, s3 = S_DATA, s4 = S_LINE;
+#pragma unroll
+    for (int i = 0; i < FA_BPT; ++i) {
+        s0 = fa_apply(nx[i], s0); s1 = fa_apply(nx[i], s1); s2 = fa_apply(nx[i], s2); s3 = fa_apply(nx[i], s3); s4 = fa_apply(nx[i], s4);
+    }
     uint32_t total;
-    fa_block_scan_fn(fa_thread_fn(cls), s_warp, &total);
+    const uint32_t before = fa_block_scan_fn(s0 | s1 << 5 | s2 << 10 | s3 << 15 | s4 << 20, s_warp, &total);
+    chunk_before[(size_t)blockIdx.x * FA_THREADS + threadIdx.x] = before;       // what the tile's earlier chunks do, composed
     if (threadIdx.x == 0) tile_fn[blockIdx.x] = total;
 }
 
@@ -181,59 +197,64 @@ SIGK_D uint64_t fa_block_scan_u64(uint64_t v, uint64_t *s_warp, uint64_t *total)
     uint64_t before = 0, all = 0;
     for (unsigned w = 0; w < FA_WARPS; ++w) { if (w < warp) before += s_warp[w]; all += s_warp[w]; }
     *total = all;
-    __syncthreads();
     return before + incl - v;
 }
 
 // ---- sweep 2 (COUNT) and 3 (EMIT): every byte with its entry state ------------------------------------------------
+// COUNT leaves every chunk's counts (5 + 4 + 5 bits) for EMIT, which scans them and walks its bytes once.
 template <bool EMIT>
 __global__ void __launch_bounds__(FA_THREADS)
 fasta_sweep_kernel(const uint8_t *__restrict__ bytes, const FastaTile *__restrict__ tiles, const uint8_t *__restrict__ tile_state,
+                   const uint32_t *__restrict__ chunk_before, uint16_t *__restrict__ chunk_counts,
                    uint64_t *__restrict__ tile_counts,         // COUNT: out, packed; EMIT: in, exclusive prefix {seq, records, errors} per tile
                    FastaOut out) {
-    __shared__ uint32_t s_warp[FA_WARPS];
     __shared__ uint64_t s_warp64[FA_WARPS];
+    __shared__ uint2 s_lut[256];
+    fa_fill_lut(s_lut);
     const FastaTile t = tiles[blockIdx.x];
-    uint32_t cls[FA_BPT];
-    uint8_t raw[FA_BPT];
-    fa_load(bytes, t, cls, raw);
-    const uint32_t before = fa_block_scan_fn(fa_thread_fn(cls), s_warp, nullptr);
-    const uint32_t s0 = fa_apply(before, tile_state[blockIdx.x]);
-    uint32_t s = s0, n_seq = 0, n_rec = 0, n_err = 0;
-#pragma unroll
-    for (int i = 0; i < FA_BPT; ++i) {
-        const FaAction a = fa_action(s, cls[i]);
-        n_seq += a.seq; n_rec += a.record; n_err += a.error;
-        s = fa_apply(c_fa_next[cls[i]], s);
-    }
-    uint64_t total;
-    const uint64_t excl = fa_block_scan_u64((uint64_t)n_seq | (uint64_t)n_rec << 16 | (uint64_t)n_err << 32, s_warp64, &total);
+    const size_t chunk = (size_t)blockIdx.x * FA_THREADS + threadIdx.x;
+    uint32_t nx[FA_BPT], act[FA_BPT];
+    uint4 q;
+    fa_load(bytes, t, s_lut, nx, act, q);
+    uint32_t s = fa_apply(chunk_before[chunk], tile_state[blockIdx.x]);
     if (!EMIT) {
+        uint32_t n_seq = 0, n_rec = 0, n_err = 0;
+#pragma unroll
+        for (int i = 0; i < FA_BPT; ++i) {
+            const uint32_t a = fa_apply(act[i], s);
+            n_seq += a & 1u; n_rec += (a >> 1) & 1u; n_err += a >> 4;
+            s = fa_apply(nx[i], s);
+        }
+        chunk_counts[chunk] = (uint16_t)(n_seq | n_rec << 5 | n_err << 9);
+        uint64_t total;
+        fa_block_scan_u64((uint64_t)n_seq | (uint64_t)n_rec << 16 | (uint64_t)n_err << 32, s_warp64, &total);
         if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
         return;
     }
+    const uint32_t cc = chunk_counts[chunk];
+    uint64_t total;
+    const uint64_t excl = fa_block_scan_u64((uint64_t)(cc & 31u) | (uint64_t)((cc >> 5) & 15u) << 16 | (uint64_t)(cc >> 9) << 32, s_warp64, &total);
     uint64_t seq_at = tile_counts[3 * (size_t)blockIdx.x] + (excl & 0xFFFFu);
     uint64_t rec_at = tile_counts[3 * (size_t)blockIdx.x + 1] + ((excl >> 16) & 0xFFFFu);      // records opened before this byte
     uint64_t err_at = tile_counts[3 * (size_t)blockIdx.x + 2] + (excl >> 32);
     const uint64_t pos0 = t.begin + (uint64_t)threadIdx.x * FA_BPT;
-    s = s0;
 #pragma unroll
     for (int i = 0; i < FA_BPT; ++i) {
-        const FaAction a = fa_action(s, cls[i]);
+        const uint32_t a = fa_apply(act[i], s);
         const uint64_t pos = pos0 + i;
-        if (a.record) {
+        if (a & A_RECORD) {
             out.header_pos[rec_at] = pos;
             out.seq_begin[rec_at] = seq_at;
             ++rec_at;
         }
-        if (a.seq) out.residues[seq_at++] = raw[i];
-        if (a.id_end) out.id_end[rec_at - 1] = pos;            // (a byte seen in s_id or s_defline follows its record's '>')
-        if (a.line_end) out.line_end[rec_at - 1] = pos;
-        if (a.error) {
-            if (err_at < out.err_capacity) { out.err_pos[err_at] = pos | (uint64_t)s << 60; out.err_record[err_at] = rec_at ? (uint32_t)(rec_at - 1) : 0xFFFFFFFFu; }
+        if (a & A_SEQ) out.residues[seq_at++] = (uint8_t)fa_byte(q, i);
+        if (a & A_ID_END) out.id_end[rec_at - 1] = pos;        // (a byte seen in s_id or s_defline follows its record's '>')
+        if (a & A_LINE_END) out.line_end[rec_at - 1] = pos;
+        if (a & A_ERROR) {
+            if (err_at < out.err_capacity) { out.err_pos[err_at] = pos | (uint64_t)(s / 5u) << 60; out.err_record[err_at] = rec_at ? (uint32_t)(rec_at - 1) : 0xFFFFFFFFu; }
             ++err_at;
         }
-        s = fa_apply(c_fa_next[cls[i]], s);
+        s = fa_apply(nx[i], s);
     }
 }
 
@@ -269,35 +290,40 @@ fasta_gather_kernel(const uint8_t *__restrict__ stream, const uint64_t *__restri
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
     if (warp >= n_proteins) return;
     const uint64_t dst = starts[warp], n = starts[warp + 1] - dst, src = src_begin[warp];
-    for (uint64_t i = lane; i < n; i += 32) residues[dst + i] = stream[src + i];
+    uint64_t i = lane;
+    for (; i + 96 < n; i += 128) {             // four loads in flight per lane
+        const uint8_t a = stream[src + i], b = stream[src + i + 32], c = stream[src + i + 64], d = stream[src + i + 96];
+        residues[dst + i] = a; residues[dst + i + 32] = b; residues[dst + i + 64] = c; residues[dst + i + 96] = d;
+    }
+    for (; i < n; i += 32) residues[dst + i] = stream[src + i];
 }
 
 }  // namespace
 
-cudaError_t launch_fasta_tile_functions(const uint8_t *bytes, const FastaTile *tiles, uint32_t n_tiles, uint32_t *tile_fn, uint8_t *tile_state,
-                                        cudaStream_t stream) {
+cudaError_t launch_fasta_tile_functions(const uint8_t *bytes, const FastaTile *tiles, uint32_t n_tiles, uint32_t *chunk_before, uint32_t *tile_fn,
+                                        uint8_t *tile_state, cudaStream_t stream) {
     if (n_tiles == 0) return cudaSuccess;
-    fasta_tile_fn_kernel<<<n_tiles, FA_THREADS, 0, stream>>>(bytes, tiles, tile_fn);
+    fasta_tile_fn_kernel<<<n_tiles, FA_THREADS, 0, stream>>>(bytes, tiles, chunk_before, tile_fn);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     fasta_state_scan_kernel<<<1, FS_THREADS, 0, stream>>>(tile_fn, tiles, n_tiles, tile_state);
     return cudaGetLastError();
 }
 
-cudaError_t launch_fasta_count(const uint8_t *bytes, const FastaTile *tiles, uint32_t n_tiles, const uint8_t *tile_state, uint64_t *tile_packed,
-                               uint64_t *tile_prefix, uint64_t *totals, cudaStream_t stream) {
+cudaError_t launch_fasta_count(const uint8_t *bytes, const FastaTile *tiles, uint32_t n_tiles, const uint8_t *tile_state, const uint32_t *chunk_before,
+                               uint16_t *chunk_counts, uint64_t *tile_packed, uint64_t *tile_prefix, uint64_t *totals, cudaStream_t stream) {
     if (n_tiles == 0) return cudaMemsetAsync(totals, 0, 3 * sizeof(uint64_t), stream);
-    fasta_sweep_kernel<false><<<n_tiles, FA_THREADS, 0, stream>>>(bytes, tiles, tile_state, tile_packed, FastaOut{});
+    fasta_sweep_kernel<false><<<n_tiles, FA_THREADS, 0, stream>>>(bytes, tiles, tile_state, chunk_before, chunk_counts, tile_packed, FastaOut{});
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     fasta_count_scan_kernel<<<1, FS_THREADS, 0, stream>>>(tile_packed, n_tiles, tile_prefix, totals);
     return cudaGetLastError();
 }
 
-cudaError_t launch_fasta_emit(const uint8_t *bytes, const FastaTile *tiles, uint32_t n_tiles, const uint8_t *tile_state, uint64_t *tile_prefix,
-                              const FastaOut &out, cudaStream_t stream) {
+cudaError_t launch_fasta_emit(const uint8_t *bytes, const FastaTile *tiles, uint32_t n_tiles, const uint8_t *tile_state, const uint32_t *chunk_before,
+                              uint16_t *chunk_counts, uint64_t *tile_prefix, const FastaOut &out, cudaStream_t stream) {
     if (n_tiles == 0) return cudaSuccess;
-    fasta_sweep_kernel<true><<<n_tiles, FA_THREADS, 0, stream>>>(bytes, tiles, tile_state, tile_prefix, out);
+    fasta_sweep_kernel<true><<<n_tiles, FA_THREADS, 0, stream>>>(bytes, tiles, tile_state, chunk_before, chunk_counts, tile_prefix, out);
     return cudaGetLastError();
 }
 

@@ -113,9 +113,12 @@ struct sigk_handle {
     bool fasta_parsed = false;
     sigk::DevBuf<uint8_t> d_fa_bytes, d_fa_state, d_fa_stream;
     sigk::DevBuf<sigk::FastaTile> d_fa_tiles;
-    sigk::DevBuf<uint32_t> d_fa_fn, d_fa_err_rec;
+    sigk::DevBuf<uint32_t> d_fa_fn, d_fa_err_rec, d_fa_chunk_fn;
+    sigk::DevBuf<uint16_t> d_fa_chunk_counts;
     sigk::DevBuf<uint64_t> d_fa_packed, d_fa_prefix, d_fa_totals, d_fa_rec, d_fa_err_pos, d_fa_src;     // d_fa_rec: 4 arrays of (records + 1)
-    sigk::PinnedBuf<uint64_t> h_fa_rec, h_fa_totals, h_fa_err_pos;
+    sigk::PinnedBuf<uint64_t> h_fa_rec, h_fa_totals, h_fa_err_pos, h_fa_starts, h_fa_src;
+    sigk::PinnedBuf<uint16_t> h_fa_func;
+    sigk::PinnedBuf<uint32_t> h_fa_sid;
     sigk::PinnedBuf<uint32_t> h_fa_err_rec;
     uint64_t fa_records = 0, fa_residues = 0, fa_errors = 0, fa_rec_stride = 0, fa_bytes = 0;
 

@@ -194,12 +194,13 @@ struct FastaOut {
     uint32_t *err_record = nullptr;
     uint64_t err_capacity = 0;
 };
-cudaError_t launch_fasta_tile_functions(const uint8_t *bytes, const FastaTile *tiles, uint32_t n_tiles, uint32_t *tile_fn, uint8_t *tile_state,
-                                        cudaStream_t stream);
-cudaError_t launch_fasta_count(const uint8_t *bytes, const FastaTile *tiles, uint32_t n_tiles, const uint8_t *tile_state, uint64_t *tile_packed,
-                               uint64_t *tile_prefix, uint64_t *totals, cudaStream_t stream);
-cudaError_t launch_fasta_emit(const uint8_t *bytes, const FastaTile *tiles, uint32_t n_tiles, const uint8_t *tile_state, uint64_t *tile_prefix,
-                              const FastaOut &out, cudaStream_t stream);
+constexpr uint32_t FASTA_CHUNKS_PER_TILE = FASTA_TILE / 16;      // a thread's 16 bytes
+cudaError_t launch_fasta_tile_functions(const uint8_t *bytes, const FastaTile *tiles, uint32_t n_tiles, uint32_t *chunk_before, uint32_t *tile_fn,
+                                        uint8_t *tile_state, cudaStream_t stream);
+cudaError_t launch_fasta_count(const uint8_t *bytes, const FastaTile *tiles, uint32_t n_tiles, const uint8_t *tile_state, const uint32_t *chunk_before,
+                               uint16_t *chunk_counts, uint64_t *tile_packed, uint64_t *tile_prefix, uint64_t *totals, cudaStream_t stream);
+cudaError_t launch_fasta_emit(const uint8_t *bytes, const FastaTile *tiles, uint32_t n_tiles, const uint8_t *tile_state, const uint32_t *chunk_before,
+                              uint16_t *chunk_counts, uint64_t *tile_prefix, const FastaOut &out, cudaStream_t stream);
 cudaError_t launch_fasta_gather(const uint8_t *stream_bytes, const uint64_t *src_begin, const uint64_t *starts, uint32_t n_proteins,
                                 uint8_t *residues, cudaStream_t stream);
 

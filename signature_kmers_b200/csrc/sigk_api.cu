@@ -434,8 +434,10 @@ void sigk_destroy(sigk_handle *h) {
     h->d_groups.release(); h->d_long_groups.release(); h->d_work.release(); h->d_work_long.release(); h->d_rows.release(); h->d_out_kmer.release(); h->d_out_cols.release();
     h->d_bitmap.release(); h->d_distinct.release(); h->d_swf.release(); h->d_scalars.release();
     h->d_prot_windows.release(); h->d_prot_rejected.release();
+    h->d_fa_chunk_fn.release(); h->d_fa_chunk_counts.release();
     h->d_fa_bytes.release(); h->d_fa_state.release(); h->d_fa_stream.release(); h->d_fa_tiles.release(); h->d_fa_fn.release(); h->d_fa_err_rec.release();
     h->d_fa_packed.release(); h->d_fa_prefix.release(); h->d_fa_totals.release(); h->d_fa_rec.release(); h->d_fa_err_pos.release(); h->d_fa_src.release();
+    h->h_fa_starts.release(); h->h_fa_src.release(); h->h_fa_func.release(); h->h_fa_sid.release();
     h->h_fa_rec.release(); h->h_fa_totals.release(); h->h_fa_err_pos.release(); h->h_fa_err_rec.release();
     h->h_kmer.release(); h->h_cols.release(); h->h_distinct.release(); h->h_swf.release(); h->h_scalars.release();
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
@@ -697,6 +699,8 @@ int sigk_fasta_parse(sigk_handle *h, const uint8_t *bytes, const uint64_t *file_
     CU(h, h->d_fa_bytes.reserve(span + 16));
     CU(h, h->d_fa_tiles.reserve(n_tiles));
     CU(h, h->d_fa_fn.reserve(n_tiles));
+    CU(h, h->d_fa_chunk_fn.reserve((size_t)n_tiles * FASTA_CHUNKS_PER_TILE));
+    CU(h, h->d_fa_chunk_counts.reserve((size_t)n_tiles * FASTA_CHUNKS_PER_TILE));
     CU(h, h->d_fa_state.reserve(n_tiles));
     CU(h, h->d_fa_packed.reserve(n_tiles));
     CU(h, h->d_fa_prefix.reserve(3 * (size_t)n_tiles));
@@ -707,8 +711,9 @@ int sigk_fasta_parse(sigk_handle *h, const uint8_t *bytes, const uint64_t *file_
     if (span) CU(h, cudaMemcpyAsync(h->d_fa_bytes.p, bytes, span, cudaMemcpyHostToDevice, st));
     if (n_tiles) CU(h, cudaMemcpyAsync(h->d_fa_tiles.p, tiles.data(), n_tiles * sizeof(FastaTile), cudaMemcpyHostToDevice, st));
     CU(h, cudaEventRecord(h->ev[EV_H2D], st));
-    CU(h, launch_fasta_tile_functions(h->d_fa_bytes.p, h->d_fa_tiles.p, n_tiles, h->d_fa_fn.p, h->d_fa_state.p, st));
-    CU(h, launch_fasta_count(h->d_fa_bytes.p, h->d_fa_tiles.p, n_tiles, h->d_fa_state.p, h->d_fa_packed.p, h->d_fa_prefix.p, h->d_fa_totals.p, st));
+    CU(h, launch_fasta_tile_functions(h->d_fa_bytes.p, h->d_fa_tiles.p, n_tiles, h->d_fa_chunk_fn.p, h->d_fa_fn.p, h->d_fa_state.p, st));
+    CU(h, launch_fasta_count(h->d_fa_bytes.p, h->d_fa_tiles.p, n_tiles, h->d_fa_state.p, h->d_fa_chunk_fn.p, h->d_fa_chunk_counts.p, h->d_fa_packed.p,
+                             h->d_fa_prefix.p, h->d_fa_totals.p, st));
     CU(h, cudaMemcpyAsync(h->h_fa_totals.p, h->d_fa_totals.p, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));           // (the tile vector is free to go; the totals size the outputs)
     const uint64_t n_seq = h->h_fa_totals.p[0], n_rec = h->h_fa_totals.p[1], n_err = h->h_fa_totals.p[2];
@@ -726,7 +731,7 @@ int sigk_fasta_parse(sigk_handle *h, const uint8_t *bytes, const uint64_t *file_
     o.header_pos = h->d_fa_rec.p; o.id_end = h->d_fa_rec.p + stride; o.line_end = h->d_fa_rec.p + 2 * stride; o.seq_begin = h->d_fa_rec.p + 3 * stride;
     o.err_pos = h->d_fa_err_pos.p; o.err_record = h->d_fa_err_rec.p; o.err_capacity = err_cap;
     CU(h, cudaMemsetAsync(o.id_end, 0xFF, 2 * stride * sizeof(uint64_t), st));       // id_end and line_end: "the file ended first"
-    CU(h, launch_fasta_emit(h->d_fa_bytes.p, h->d_fa_tiles.p, n_tiles, h->d_fa_state.p, h->d_fa_prefix.p, o, st));
+    CU(h, launch_fasta_emit(h->d_fa_bytes.p, h->d_fa_tiles.p, n_tiles, h->d_fa_state.p, h->d_fa_chunk_fn.p, h->d_fa_chunk_counts.p, h->d_fa_prefix.p, o, st));
     CU(h, cudaMemcpyAsync(o.seq_begin + n_rec, h->d_fa_totals.p, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
     CU(h, cudaEventRecord(h->ev[EV_DEV0], st));
     CU(h, cudaMemcpyAsync(h->h_fa_rec.p, h->d_fa_rec.p, 4 * stride * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
@@ -754,26 +759,35 @@ int sigk_fasta_commit(sigk_handle *h, const uint8_t *keep, const uint16_t *funct
     if (n_rec && (!keep || !function_index || !seq_id)) return h->fail(SIGK_E_INVALID, "null argument");
     if (int rc = ensure_device(h)) return rc;
     const uint64_t *seq_begin = h->h_fa_rec.p + 3 * h->fa_rec_stride;
-    std::vector<uint64_t> starts(1, 0), src;
-    std::vector<uint16_t> func;
-    std::vector<uint32_t> sid;
+    uint64_t n_keep = 0;
+    for (uint64_t r = 0; r < n_rec; ++r) n_keep += keep[r] != 0;
+    if (n_keep >= 0xFFFFFFFFull) return h->fail(SIGK_E_UNSUPPORTED, "more than 2^32-2 proteins");
+    // pinned staging for the four small arrays (a pageable source would be copied through the driver's bounce buffer)
+    CU(h, h->h_fa_starts.reserve(n_keep + 1));
+    CU(h, h->h_fa_src.reserve(n_keep));
+    CU(h, h->h_fa_func.reserve(n_keep));
+    CU(h, h->h_fa_sid.reserve(n_keep));
+    uint64_t *starts = h->h_fa_starts.p, *src = h->h_fa_src.p;
+    uint16_t *func = h->h_fa_func.p;
+    uint32_t *sid = h->h_fa_sid.p;
     uint32_t max_sid = 0, max_func = 0;
-    uint64_t max_len = 0;
+    uint64_t max_len = 0, np = 0;
+    starts[0] = 0;
     for (uint64_t r = 0; r < n_rec; ++r) {
         if (!keep[r]) continue;
         if (function_index[r] == SIGK_UNDEFINED_FUNCTION)
             return h->fail(SIGK_E_INVALID, "record %llu has UndefinedFunction; the host must skip it (src/signature_build.tcc:155)", (unsigned long long)r);
         const uint64_t len = seq_begin[r + 1] - seq_begin[r];
-        src.push_back(seq_begin[r]);
-        starts.push_back(starts.back() + len);
-        func.push_back(function_index[r]);
-        sid.push_back(seq_id[r]);
+        src[np] = seq_begin[r];
+        starts[np + 1] = starts[np] + len;
+        func[np] = function_index[r];
+        sid[np] = seq_id[r];
         max_sid = std::max(max_sid, seq_id[r]);
         max_func = std::max<uint32_t>(max_func, function_index[r]);
         max_len = std::max(max_len, len);
+        ++np;
     }
-    const uint64_t np = func.size(), total = starts.back();
-    if (np >= 0xFFFFFFFFull) return h->fail(SIGK_E_UNSUPPORTED, "more than 2^32-2 proteins");
+    const uint64_t total = starts[np];
     if (total >= 0xFFFFFFFFull) return h->fail(SIGK_E_UNSUPPORTED, "more than 2^32-2 residues on one GPU");
     const uint64_t padded = encode_tiles(total) * ENC_TILE + ENC_PAD;
     cudaStream_t st = h->stream;
@@ -783,15 +797,15 @@ int sigk_fasta_commit(sigk_handle *h, const uint8_t *keep, const uint16_t *funct
     CU(h, h->d_seqid.reserve(np));
     CU(h, h->d_fa_src.reserve(np));
     nvtx_range r("sigk fasta commit");
-    CU(h, cudaMemcpyAsync(h->d_starts.p, starts.data(), (np + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(h->d_starts.p, starts, (np + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     if (np) {
-        CU(h, cudaMemcpyAsync(h->d_fa_src.p, src.data(), np * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-        CU(h, cudaMemcpyAsync(h->d_func.p, func.data(), np * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
-        CU(h, cudaMemcpyAsync(h->d_seqid.p, sid.data(), np * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CU(h, cudaMemcpyAsync(h->d_fa_src.p, src, np * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        CU(h, cudaMemcpyAsync(h->d_func.p, func, np * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+        CU(h, cudaMemcpyAsync(h->d_seqid.p, sid, np * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     }
     CU(h, launch_fasta_gather(h->d_fa_stream.p, h->d_fa_src.p, h->d_starts.p, (uint32_t)np, h->d_res.p, st));
     CU(h, cudaMemsetAsync(h->d_res.p + total, 0, padded - total, st));
-    CU(h, cudaStreamSynchronize(st));           // (the host vectors go out of scope)
+    CU(h, cudaStreamSynchronize(st));
     h->in = sigk_proteins{nullptr, nullptr, nullptr, nullptr, np};
     h->input_on_device = true;
     h->local_max_len = max_len;

@@ -17,7 +17,9 @@
 // stop before the GPU: host-logic tests), --sigk-table FILE (write the table
 // file without --perfect-hash), --no-recall (skip the recall pass),
 // --host-recall (recall lookups on the host instead of sigk_lookup),
-// --max-seqs-per-file N (the constant of :18, default 100000; tests).
+// --max-seqs-per-file N (the constant of :18, default 100000; tests),
+// --gpu-fasta (the k-mer pass reads its FASTA files through sigk_fasta_parse /
+// sigk_fasta_commit instead of the host reader: same proteins, packed on the device).
 #include "function_caller.h"
 
 #include <atomic>
@@ -32,7 +34,7 @@ namespace {
 struct Options {
     std::vector<std::string> definition_dirs, fasta_dirs, fasta_keep_dirs, good_function_files, good_role_files;
     fs::path deleted_fids_file, ignored_functions_file, kmer_data_dir, final_kmers, perfect_hash, perfect_hash_data, dump_packed, sigk_table;
-    bool no_recall = false, host_recall = false;
+    bool no_recall = false, host_recall = false, gpu_fasta = false;
     int max_seqs_per_file = 100000;                                 // MaxSequencesPerFile, :18
     std::string nudb_file;
     int min_reps_required = 3, n_threads = 1, device = 0;
@@ -55,6 +57,7 @@ void usage(const char *argv0) {
               << "  --n-threads arg                      (accepted; the build runs on the GPU)\n"
               << "  --perfect-hash arg / --perfect-hash-data arg  (accepted; cmph output is not built)\n"
               << "  --device arg / --sorted-files / --dump-packed arg / --sigk-table arg / --no-recall / --host-recall / --max-seqs-per-file arg\n"
+              << "  --gpu-fasta (parse the FASTA files of the k-mer pass on the GPU: sigk_fasta_parse)\n"
               << "  -h [ --help ]                        show this help message\n";
 }
 
@@ -97,6 +100,7 @@ bool parse(int argc, char **argv, Options &o) {
         else if (a == "--no-recall") o.no_recall = true;
         else if (a == "--host-recall") o.host_recall = true;
         else if (a == "--max-seqs-per-file") o.max_seqs_per_file = std::stoi(next());
+        else if (a == "--gpu-fasta") o.gpu_fasta = true;
         else { std::cerr << "unrecognised option '" << a << "'\n"; return false; }
     }
     return true;
@@ -137,7 +141,8 @@ int main(int argc, char **argv) {
     }
 
     std::cerr << "extract kmers\n";
-    builder.extract_kmers(deleted_fids);
+    if (o.gpu_fasta && o.dump_packed.empty()) { if (builder.extract_kmers_gpu(deleted_fids, o.device)) return 1; }
+    else builder.extract_kmers(deleted_fids);
 
     if (!o.dump_packed.empty()) {       // host-logic tests: the packed proteins libsigk would receive
         const sigk_proteins p = builder.packed();

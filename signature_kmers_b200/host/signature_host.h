@@ -535,16 +535,79 @@ public:
         }
     }
 
+    // The same gating with the files parsed on the GPU (sigk_fasta_parse, csrc/fasta.cu): the files' bytes go to the
+    // device once, the parser's record table comes back, the ids are looked up here (FunctionMap is a string-keyed
+    // map), and sigk_fasta_commit packs the kept records' residues on the device — process_kmers then builds from
+    // what is already there.  Files stay independent: a file's records are a contiguous run of the table.
+    int extract_kmers_gpu(const std::set<std::string> &deleted, int device) {
+        if (int rc = ensure_handle(device)) return rc;
+        const size_t nf = all_fasta_data_.size();
+        std::vector<uint64_t> begin(nf), len(nf);
+        uint64_t at = 0;
+        for (size_t i = 0; i < nf; ++i) {
+            std::error_code ec;
+            const auto size = fs::file_size(all_fasta_data_[i], ec);
+            begin[i] = at; len[i] = ec ? 0 : (uint64_t)size;
+            at += (len[i] + 15) / 16 * 16;
+        }
+        uint8_t *buf = static_cast<uint8_t *>(sigk_host_alloc(at + 16));
+        if (!buf) { std::cerr << "cannot allocate " << at << " bytes of pinned memory\n"; return SIGK_E_NOMEM; }
+        parallel_for_index(nf, n_threads_, [&](size_t i) {
+            std::ifstream in(all_fasta_data_[i], std::ios::binary);
+            in.read(reinterpret_cast<char *>(buf + begin[i]), (std::streamsize)len[i]);
+            len[i] = (uint64_t)in.gcount();
+        });
+        sigk_fasta_records rec;
+        int rc = sigk_fasta_parse(h_, buf, begin.data(), len.data(), nf, &rec);
+        if (rc) { std::cerr << "libsigk: " << sigk_last_error(h_) << "\n"; sigk_host_free(buf); return rc; }
+        std::vector<uint8_t> keep(rec.n_records, 0);
+        std::vector<uint16_t> func(rec.n_records, 0);
+        std::vector<uint32_t> seq_id(rec.n_records, 0);
+        parallel_for_index(nf, n_threads_, [&](size_t i) {
+            const uint64_t file_end = begin[i] + len[i];
+            const uint64_t *first = std::lower_bound(rec.header_pos, rec.header_pos + rec.n_records, begin[i]);
+            unsigned next_sequence_id = (unsigned)i * (unsigned)max_seqs_per_file_;                 // :91
+            std::string id;
+            for (uint64_t r = (uint64_t)(first - rec.header_pos); r < rec.n_records && rec.header_pos[r] < file_end; ++r) {
+                const uint64_t id_end = rec.id_end[r] == SIGK_FASTA_NO_POS ? file_end : rec.id_end[r];
+                id.clear();
+                for (uint64_t p = rec.header_pos[r] + 1; p < id_end; ++p) if (buf[p] != '\r') id.push_back((char)buf[p]);
+                if (deleted.count(id)) continue;                                            // :94
+                if (id.empty()) continue;                                                   // :122
+                const std::string fn = fm_.lookup_function(id);
+                if (fn.empty()) continue;                                                   // :133
+                const unsigned sid = next_sequence_id++;                                    // :138
+                const uint16_t fi = fm_.lookup_index(fn);
+                if (fi == 0xFFFF) continue;                                                 // :155
+                keep[r] = 1; func[r] = fi; seq_id[r] = sid;
+            }
+        });
+        rc = sigk_fasta_commit(h_, keep.data(), func.data(), seq_id.data());
+        sigk_host_free(buf);
+        if (rc) { std::cerr << "libsigk: " << sigk_last_error(h_) << "\n"; return rc; }
+        input_on_device_ = true;
+        return 0;
+    }
+
     sigk_proteins packed() const {
         return sigk_proteins{residues_.data(), starts_.data(), func_.data(), seq_id_.data(), (uint64_t)func_.size()};
     }
 
     // tcc:183-213 on the GPU
-    int process_kmers(int device, sigk_table *table) {
+    int ensure_handle(int device) {
+        if (h_) return 0;
         sigk_config cfg{SIGK_ABI_VERSION, SIGK_K, device, 0, 1, 0};
-        if (int rc = sigk_create(&cfg, &h_)) { std::cerr << "sigk_create: " << sigk_last_error(nullptr) << "\n"; return rc; }
-        const sigk_proteins p = packed();
-        int rc = sigk_set_proteins(h_, &p);
+        const int rc = sigk_create(&cfg, &h_);
+        if (rc) std::cerr << "sigk_create: " << sigk_last_error(nullptr) << "\n";
+        return rc;
+    }
+    int process_kmers(int device, sigk_table *table) {
+        if (int rc = ensure_handle(device)) return rc;
+        int rc = 0;
+        if (!input_on_device_) {            // (extract_kmers_gpu has committed the proteins where they are)
+            const sigk_proteins p = packed();
+            rc = sigk_set_proteins(h_, &p);
+        }
         if (!rc) rc = sigk_build(h_);
         if (!rc) rc = sigk_result(h_, table);
         if (rc) { std::cerr << "libsigk: " << sigk_last_error(h_) << "\n"; return rc; }
@@ -569,6 +632,7 @@ private:
     int n_threads_, max_seqs_per_file_;
     FunctionMap fm_;
     std::vector<fs::path> all_fasta_data_;
+    bool input_on_device_ = false;
     std::vector<uint8_t> residues_;
     std::vector<uint64_t> starts_;
     std::vector<uint16_t> func_;

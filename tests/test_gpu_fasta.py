@@ -193,6 +193,7 @@ def test_commit_feeds_the_build(gpu):
     """Proteins written as FASTA files, parsed and committed on the device, give the table of the same proteins handed
     over as arrays — with records dropped by the caller (deleted ids, ids without a function) in between."""
     seqs, funcs = random_proteins(41, n_families=60, members=(2, 14), length=(20, 400))
+    seqs = [s.replace(b"*", b"X") for s in seqs]         # ('*' at the start of a wrapped line would be reported and dropped, as in the reference)
     ids = [b"fig|%d.peg.%d" % (i % 7, i) for i in range(len(seqs))]
     n_files = 5
     cuts = [len(seqs) * k // n_files for k in range(n_files + 1)]
@@ -224,3 +225,40 @@ def test_commit_without_a_parse_is_refused():
     t = b.build()
     assert t.n_kept == 0
     b.close()
+
+
+def test_cli_gpu_fasta_equals_host_reader(tmp_path):
+    """kmers-build-signatures --gpu-fasta: the k-mer pass reads the FASTA files through the device parser; every
+    output file is the one the default run (host reader) writes.  The tree has deleted ids, ids without a function,
+    CRLF files and a header-only record, so that the gating around the parser is exercised too."""
+    from signature_kmers_b200.synth import Synth
+
+    subprocess.run(["make", "-C", os.path.join(PKG, "host")], check=True, capture_output=True)
+    s = Synth(n_proteins=3000, n_functions=80, n_genomes=6, seed=23)
+    tree = tmp_path / "tree"
+    s.write_tree(str(tree))
+    seqs = sorted((tree / "Seqs").iterdir())
+    # awkward files: CRLF line ends; a record without sequence in front of another; an id that has no assignment
+    text = seqs[0].read_bytes()
+    seqs[0].write_bytes(text.replace(b"\n", b"\r\n"))
+    first_id = seqs[1].read_bytes().split(b"\n", 1)[0][1:].split()[0]
+    seqs[1].write_bytes(b">lonely\n" + seqs[1].read_bytes() + b">nobody.knows.me\nACDEFGHIKLMNPQRSTVWY\n")
+    deleted = tmp_path / "deleted.txt"
+    deleted.write_bytes(first_id + b"\n")
+    outs = []
+    for flag in ([], ["--gpu-fasta"]):
+        out = tmp_path / ("out" + ("_gpu" if flag else ""))
+        cmd = [os.path.join(PKG, "kmers-build-signatures"), "-D", str(tree / "Annotations" / "0"), "-F", str(tree / "Seqs"),
+               "--kmer-data-dir", str(out), "--final-kmers", "final.kmers", "--sigk-table", "kmer_data.sigk", "--sorted-files", "--n-threads", "3",
+               "--deleted-features-file", str(deleted)] + flag
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs.append((out, r.stdout))
+    (a, a_out), (b, b_out) = outs
+    assert a_out == b_out
+    names = sorted(p.relative_to(a).as_posix() for p in a.rglob("*") if p.is_file())
+    assert names == sorted(p.relative_to(b).as_posix() for p in b.rglob("*") if p.is_file())
+    assert "final.kmers" in names and "kmer_data.sigk" in names
+    for n in names:
+        assert (a / n).read_bytes() == (b / n).read_bytes(), n
+    assert (a / "final.kmers").stat().st_size > 1000

@@ -72,9 +72,12 @@ def main():
             best = cur
     assert rec.n_records == n and rec.n_errors == 0 and rec.n_residues == len(proteins.residues)
     keep = np.ones(n, dtype=np.uint8)
-    t0 = time.perf_counter()
-    b.fasta_commit(keep, proteins.function_index, proteins.seq_id)
-    commit_ms = 1e3 * (time.perf_counter() - t0)
+    commit_ms = None
+    for _ in range(3):                                   # (the first call allocates the input arrays)
+        t0 = time.perf_counter()
+        b.fasta_commit(keep, proteins.function_index, proteins.seq_id)
+        cur = 1e3 * (time.perf_counter() - t0)
+        commit_ms = cur if commit_ms is None else min(commit_ms, cur)
     got = b.build()
     b.set_proteins(proteins)
     want = b.build()
