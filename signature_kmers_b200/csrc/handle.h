@@ -22,7 +22,7 @@ struct DeviceScalars {
     uint64_t n_side_kept;       // kept rows of the side run (the table's second section)
     uint32_t overflow, pad0;
     uint32_t ticket[16];
-    uint32_t n_groups, next_group, n_long, next_long, n_work, next_work, n_work_long, next_work_long;
+    uint32_t n_groups, next_group, n_long, next_long, n_work, next_work, n_work_long, next_work_long, n_giant, next_giant;
     uint64_t reduce_in[4];      // multi-GPU: {occurrences, groups, kept, -} of this rank -> summed over ranks
 };
 
@@ -85,7 +85,7 @@ struct sigk_handle {
     int meta_shift = 0;                    // SIGK_TEST_META_SPREAD: table entries 2^shift apart (cache-footprint experiments)
     uint64_t local_max_len = 0, max_len = 0;   // longest protein: this rank's / the job's
     sigk::DevBuf<uint4> d_rows;
-    sigk::DevBuf<sigk::OrderWork> d_groups, d_long_groups, d_work, d_work_long;
+    sigk::DevBuf<sigk::OrderWork> d_groups, d_long_groups, d_work, d_work_long, d_giant;
     sigk::DevBuf<uint64_t> d_keys[2];
     sigk::DevBuf<uint32_t> d_vals[2];
     sigk::DevBuf<uint8_t> d_lookback;

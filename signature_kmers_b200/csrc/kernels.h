@@ -149,6 +149,8 @@ struct ReduceScratch {
 };
 inline uint64_t reduce_scan_entries(uint64_t capacity) { return 3 * (reduce_batches(capacity) + 1) + squeeze_tiles(capacity) + 2; }
 size_t reduce_group_entries(uint64_t capacity, int sm_count);  // OrderWork entries: groups of 2..32 records
+constexpr uint32_t REDUCE_GIANT = 4096;
+size_t reduce_giant_entries(uint64_t capacity);
 size_t reduce_long_group_entries(uint64_t capacity);           // OrderWork entries: groups of more than 32 records
 size_t reduce_work_entries(uint64_t capacity, int sm_count);   // OrderWork entries: groups whose median/var need the ordered walk
 size_t reduce_long_work_entries(uint64_t capacity);            // ... of those, the ones a whole warp walks
@@ -170,6 +172,7 @@ struct ReduceLists {
     OrderWork *long_groups; uint32_t *n_long, *next_long;
     OrderWork *work;        uint32_t *n_work;
     OrderWork *work_long;   uint32_t *n_work_long;
+    OrderWork *giant;       uint32_t *n_giant, *next_giant;      // groups of more than REDUCE_GIANT records: a whole CTA each
 };
 // Run-length + per-group reduce + keep/reject over the sorted records (head_tile_kernel count and emit
 // passes, then group_reduce_kernel): one packed row per group in k-mer order (rejected groups

@@ -107,36 +107,56 @@ struct SegResult {
 };
 
 // A group of n > 32 records starting at `start`, reduced by the whole warp in strides of 32:
-// walk 1 votes, walk 2 counts the candidate, sums its lengths and finds the offset bits that vary,
-// then one walk per varying offset bit for the radix select (inside a family the offsets rarely
-// differ in more than a few bits; none when they are all equal).
+// one walk that counts the first record's function, sums its lengths and finds the offset bits that
+// vary (a vote and a recount follow only if some record has another function), then one walk per
+// varying offset bit for the radix select (inside a family the offsets rarely differ in more than a
+// few bits; none when they are all equal).
 template <typename MetaT>
 SIGK_D SegResult reduce_long_segment(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                                      const MetaT *__restrict__ meta, uint64_t start, uint32_t n, uint32_t *prot_rejected) {
     const unsigned lane = threadIdx.x & 31u;
     SegResult r{false, false, 0, 0, 0, 0, 0};
-    // walk 1: bit-sliced majority vote over func_index; lane b owns bit b
-    uint32_t ones = 0;
-    for (uint32_t base = 0; base < n; base += 32) {
-        const uint32_t j = base + lane;
-        const bool act = j < n;
-        const uint32_t f = act ? load_meta(meta, vals[start + j]).y : 0u;
-#pragma unroll
-        for (int b = 0; b < 16; ++b) {
-            const unsigned bal = __ballot_sync(FULL, act && ((f >> b) & 1u));
-            if ((int)lane == b) ones += __popc(bal);
-        }
-    }
-    const uint32_t cand = __ballot_sync(FULL, lane < 16 && 2ull * ones > n) & 0xFFFFu;
-    // walk 2: count the candidate, sum its lengths (mod 65536), OR of offset differences
+    // walk 1, for the usual case of a group with one function (a k-mer of one family): take the first record's
+    // function as the candidate; count it, sum its lengths (mod 65536), OR the offset differences, and notice any
+    // record that disagrees.  Only then is a vote needed.
     const uint32_t off0 = sigk_key_offset(keys[start]);
+    uint32_t cand = load_meta(meta, vals[start]).y;
     uint32_t best = 0, S = 0, vary = 0, lmin = 0xFFFFFFFFu, lmax = 0;
+    bool mixed = false;
     for (uint32_t base = 0; base < n; base += 32) {
         const uint32_t j = base + lane;
         if (j < n) {
             const ProtMeta m = load_meta(meta, vals[start + j]);
             if (m.y == cand) { ++best; S += m.x; lmin = min(lmin, m.x); lmax = max(lmax, m.x); }
+            else mixed = true;
             vary |= sigk_key_offset(keys[start + j]) ^ off0;
+        }
+    }
+    if (__any_sync(FULL, mixed)) {
+        // walk 2: bit-sliced majority vote over func_index; lane b owns bit b
+        uint32_t ones = 0;
+        for (uint32_t base = 0; base < n; base += 32) {
+            const uint32_t j = base + lane;
+            const bool act = j < n;
+            const uint32_t f = act ? load_meta(meta, vals[start + j]).y : 0u;
+#pragma unroll
+            for (int b = 0; b < 16; ++b) {
+                const unsigned bal = __ballot_sync(FULL, act && ((f >> b) & 1u));
+                if ((int)lane == b) ones += __popc(bal);
+            }
+        }
+        const uint32_t voted = __ballot_sync(FULL, lane < 16 && 2ull * ones > n) & 0xFFFFu;
+        if (voted != cand) {
+            // walk 3: the first record's function was not the majority: count the voted one instead
+            cand = voted;
+            best = 0; S = 0; lmin = 0xFFFFFFFFu; lmax = 0;
+            for (uint32_t base = 0; base < n; base += 32) {
+                const uint32_t j = base + lane;
+                if (j < n) {
+                    const ProtMeta m = load_meta(meta, vals[start + j]);
+                    if (m.y == cand) { ++best; S += m.x; lmin = min(lmin, m.x); lmax = max(lmax, m.x); }
+                }
+            }
         }
     }
 #pragma unroll
@@ -472,7 +492,8 @@ group_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
                     const OrderWork *__restrict__ groups, const uint32_t *__restrict__ n_groups, uint32_t *__restrict__ next_group,
                     const OrderWork *__restrict__ long_groups, const uint32_t *__restrict__ n_long, uint32_t *__restrict__ next_long,
                     uint4 *__restrict__ rows, OrderWork *__restrict__ work, uint32_t *__restrict__ n_work,
-                    OrderWork *__restrict__ work_long, uint32_t *__restrict__ n_work_long, uint32_t *__restrict__ prot_rejected,
+                    OrderWork *__restrict__ work_long, uint32_t *__restrict__ n_work_long, OrderWork *__restrict__ giant,
+                    uint32_t *__restrict__ n_giant, uint32_t *__restrict__ prot_rejected,
                     uint32_t *__restrict__ rej_tile, int order_stats) {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t total = *n_groups;
@@ -487,6 +508,10 @@ group_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
             i = __shfl_sync(FULL, i, 0);
             if (i >= total_long) break;
             const OrderWork d = long_groups[i];
+            if (d.count > REDUCE_GIANT) {           // a warp would walk it for milliseconds: giant_reduce_kernel, a CTA per group
+                if (lane == 0) giant[atomicAdd(n_giant, 1u)] = d;
+                continue;
+            }
             const SegResult r = reduce_long_segment(keys, vals, meta, d.start, d.count, prot_rejected);
             const bool walk = r.keep && order_stats && !r.closed;   // best_count >= 27 here
             const bool walk_long = walk && d.count > ORD_LONG;      // whole-warp walk (order_stats_long_kernel)
@@ -639,6 +664,129 @@ group_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restric
       }
     }
     work_flush(wc, work);
+}
+
+// ---- groups of more than REDUCE_GIANT records: reduce_long_segment with the whole CTA -----------------------------
+// On the Zipf set the largest family leaves ~300 groups of 250 K records; one warp walking such a group nine times
+// (count, then one walk per varying offset bit) was the whole tail of group_reduce_kernel (19 ms at config 4).
+constexpr int GT_THREADS = 512;
+constexpr int GT_WARPS = GT_THREADS / 32;
+template <typename T, typename Op>
+SIGK_D T giant_block_reduce(T v, T *s_red, Op op) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(FULL, v, o));
+    __syncthreads();                    // (s_red may still be read from the previous reduction)
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    T r = s_red[0];
+    for (int w = 1; w < GT_WARPS; ++w) r = op(r, s_red[w]);
+    return r;
+}
+template <typename MetaT>
+__global__ void __launch_bounds__(GT_THREADS)
+giant_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, const MetaT *__restrict__ meta,
+                    const OrderWork *__restrict__ giant, const uint32_t *__restrict__ n_giant, uint32_t *__restrict__ next_giant,
+                    uint4 *__restrict__ rows, OrderWork *__restrict__ work, uint32_t *__restrict__ n_work,
+                    OrderWork *__restrict__ work_long, uint32_t *__restrict__ n_work_long, uint32_t *__restrict__ prot_rejected,
+                    uint32_t *__restrict__ rej_tile, int order_stats) {
+    __shared__ uint32_t s_red[GT_WARPS];
+    __shared__ uint32_t s_ones[16];
+    __shared__ uint32_t s_next;
+    const uint32_t total = *n_giant;
+    auto add = [](uint32_t a, uint32_t b) { return a + b; };
+    auto bor = [](uint32_t a, uint32_t b) { return a | b; };
+    auto mn = [](uint32_t a, uint32_t b) { return min(a, b); };
+    auto mx = [](uint32_t a, uint32_t b) { return max(a, b); };
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_next = atomicAdd(next_giant, 1u);
+        if (threadIdx.x < 16) s_ones[threadIdx.x] = 0;
+        __syncthreads();
+        const uint32_t i = s_next;
+        if (i >= total) return;
+        const OrderWork d = giant[i];
+        const uint64_t start = d.start;
+        const uint32_t n = d.count;
+        // the same three walks as reduce_long_segment, strided over the CTA
+        const uint32_t off0 = sigk_key_offset(keys[start]);
+        uint32_t cand = load_meta(meta, vals[start]).y;
+        uint32_t best = 0, S = 0, vary = 0, lmin = 0xFFFFFFFFu, lmax = 0, mixed = 0;
+        for (uint32_t j = threadIdx.x; j < n; j += GT_THREADS) {
+            const ProtMeta m = load_meta(meta, vals[start + j]);
+            if (m.y == cand) { ++best; S += m.x; lmin = min(lmin, m.x); lmax = max(lmax, m.x); }
+            else mixed = 1;
+            vary |= sigk_key_offset(keys[start + j]) ^ off0;
+        }
+        mixed = giant_block_reduce(mixed, s_red, bor);
+        if (mixed) {
+            uint32_t ones[16];
+#pragma unroll
+            for (int b = 0; b < 16; ++b) ones[b] = 0;
+            for (uint32_t j = threadIdx.x; j < n; j += GT_THREADS) {
+                const uint32_t f = load_meta(meta, vals[start + j]).y;
+#pragma unroll
+                for (int b = 0; b < 16; ++b) ones[b] += (f >> b) & 1u;
+            }
+#pragma unroll
+            for (int b = 0; b < 16; ++b) {
+                uint32_t v = ones[b];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+                if ((threadIdx.x & 31u) == 0) atomicAdd(&s_ones[b], v);
+            }
+            __syncthreads();
+            uint32_t voted = 0;
+#pragma unroll
+            for (int b = 0; b < 16; ++b) voted |= (2ull * s_ones[b] > n ? 1u : 0u) << b;
+            if (voted != cand) {
+                cand = voted;
+                best = 0; S = 0; lmin = 0xFFFFFFFFu; lmax = 0;
+                for (uint32_t j = threadIdx.x; j < n; j += GT_THREADS) {
+                    const ProtMeta m = load_meta(meta, vals[start + j]);
+                    if (m.y == cand) { ++best; S += m.x; lmin = min(lmin, m.x); lmax = max(lmax, m.x); }
+                }
+            }
+        }
+        best = giant_block_reduce(best, s_red, add);
+        S = giant_block_reduce(S, s_red, add);
+        vary = giant_block_reduce(vary, s_red, bor);
+        lmin = giant_block_reduce(lmin, s_red, mn);
+        lmax = giant_block_reduce(lmax, s_red, mx);
+        const bool keep = keep_rule(best, n);
+        if (!keep) {
+            for (uint32_t j = threadIdx.x; j < n; j += GT_THREADS) count_rejected(prot_rejected, vals[start + j]);
+            if (threadIdx.x == 0) {
+                rows[d.row] = make_uint4(0u, 0u, 0xFFFFu, 0u);
+                atomicAdd(rej_tile + (d.row >> SQ_TILE_SHIFT), 1u);
+            }
+            continue;
+        }
+        const uint32_t mean = (S & 0xFFFFu) / best;
+        const bool closed = lmin == lmax && (uint64_t)best * lmin < 65536ull;
+        // offset of rank n/2 by radix select over the varying bits, most significant first
+        uint32_t rank = n / 2, prefix = off0 & ~vary, pmask = ~vary & 0xFFFFu;
+        while (vary) {
+            const int b = 31 - __clz(vary);
+            uint32_t zeros = 0;
+            for (uint32_t j = threadIdx.x; j < n; j += GT_THREADS) {
+                const uint32_t off = sigk_key_offset(keys[start + j]);
+                zeros += ((off & pmask) == prefix && !((off >> b) & 1u)) ? 1u : 0u;
+            }
+            zeros = giant_block_reduce(zeros, s_red, add);
+            if (rank >= zeros) { rank -= zeros; prefix |= 1u << b; }
+            pmask |= 1u << b;
+            vary &= ~(1u << b);
+        }
+        if (threadIdx.x == 0) {
+            const uint64_t code = sigk_key_code(keys[start]);
+            rows[d.row] = make_uint4((uint32_t)code, (uint32_t)(code >> 32) | (prefix << 11), cand | (mean << 16), (order_stats && closed) ? lmin : 0u);
+            if (order_stats && !closed) {           // best_count >= 0.8 * 4096 here: the ordered walk is needed
+                if (n > ORD_LONG) work_long[atomicAdd(n_work_long, 1u)] = d;
+                else work[atomicAdd(n_work, 1u)] = d;
+            }
+        }
+    }
 }
 
 // ---- squeeze: drop the tombstones, keep k-mer order, expand rows into the table columns
@@ -960,12 +1108,14 @@ size_t reduce_group_entries(uint64_t capacity, int) {
     return (size_t)(capacity / 2 + 2);      // a listed group has >= 2 records
 }
 size_t reduce_long_group_entries(uint64_t capacity) { return (size_t)(capacity / 33 + 2); }
+size_t reduce_giant_entries(uint64_t capacity) { return (size_t)(capacity / REDUCE_GIANT + 2); }
 size_t reduce_work_entries(uint64_t capacity, int sm_count) {
     // A walked group has >= 3 records.  Slots are reserved in blocks of WORK_BLOCK and a block's unused tail is
     // dropped when the next window needs more than it has left (a window lists at most 10 groups), so a block
     // holds at least WORK_BLOCK - 9 live entries: size the list for that padding, plus one open block per warp.
     const size_t groups = (size_t)(capacity / 3 + 2);
-    return groups + groups * 9 / (WORK_BLOCK - 9) + WORK_BLOCK + 2 * (size_t)reduce_grid(sm_count) * (RED_THREADS / 32) * WORK_BLOCK;
+    // (+ one slot per giant group: giant_reduce_kernel appends singly)
+    return groups + groups * 9 / (WORK_BLOCK - 9) + WORK_BLOCK + 2 * (size_t)reduce_grid(sm_count) * (RED_THREADS / 32) * WORK_BLOCK + reduce_giant_entries(capacity);
 }
 size_t reduce_long_work_entries(uint64_t capacity) { return (size_t)(capacity / ORD_LONG + 2); }
 
@@ -1023,7 +1173,11 @@ static cudaError_t segment_reduce_impl(const uint64_t *keys, const uint32_t *val
     if (after_emit) cudaEventRecord(after_emit, stream);
     group_reduce_kernel<MetaT><<<(unsigned)grid, RED_THREADS, 0, stream>>>(keys, vals, meta, l.groups, l.n_groups, l.next_group, l.long_groups,
                                                                            l.n_long, l.next_long, rows, l.work, l.n_work, l.work_long,
-                                                                           l.n_work_long, prot_rejected, sx.rej_tile, order_stats);
+                                                                           l.n_work_long, l.giant, l.n_giant, prot_rejected, sx.rej_tile, order_stats);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    giant_reduce_kernel<MetaT><<<(unsigned)sm_count * 2, GT_THREADS, 0, stream>>>(keys, vals, meta, l.giant, l.n_giant, l.next_giant, rows, l.work, l.n_work,
+                                                                                  l.work_long, l.n_work_long, prot_rejected, sx.rej_tile, order_stats);
     return cudaGetLastError();
 }
 

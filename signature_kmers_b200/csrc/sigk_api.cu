@@ -56,6 +56,7 @@ int ensure_capacity(sigk_handle *h, uint64_t cap, bool keep_pingpong1) {
     CU(h, h->d_lookback.reserve(onesweep_lookback_bytes(cap_lb) * (SORT_MAX_PASSES + 1)));
     CU(h, h->d_groups.reserve(reduce_group_entries(cap, h->sm_count)));
     CU(h, h->d_long_groups.reserve(reduce_long_group_entries(cap)));
+    CU(h, h->d_giant.reserve(reduce_giant_entries(cap)));
     CU(h, h->d_work.reserve(reduce_work_entries(cap, h->sm_count)));
     CU(h, h->d_work_long.reserve(reduce_long_work_entries(cap)));
     CU(h, h->d_rows.reserve(cap));
@@ -276,12 +277,12 @@ int do_build_device(sigk_handle *h) {
     const int order_stats = (h->cfg.flags & SIGK_F_NO_ORDER_STATS) ? 0 : 1;
     KeptColumns kc{h->d_out_kmer.p, out_col(h, 0), out_col(h, 1), out_col(h, 2), out_col(h, 3), out_col(h, 4)};
     ReduceLists rl{h->d_groups.p, &sc->n_groups, &sc->next_group, h->d_long_groups.p, &sc->n_long, &sc->next_long,
-                   h->d_work.p, &sc->n_work, h->d_work_long.p, &sc->n_work_long};
+                   h->d_work.p, &sc->n_work, h->d_work_long.p, &sc->n_work_long, h->d_giant.p, &sc->n_giant, &sc->next_giant};
     {
         nvtx_range r("sigk segment reduce");
         CU(h, launch_segment_reduce(h->d_keys[cur].p, h->d_vals[cur].p, &sc->n_records, cap_sort, meta, h->d_rows.p, rl,
                                     h->d_prot_rejected.p, h->d_scan_state.p, &sc->n_segments, order_stats, h->sm_count, st,
-                                    h->ev[EV_RED_COUNT], h->ev[EV_RED_EMIT])); launches += 5;
+                                    h->ev[EV_RED_COUNT], h->ev[EV_RED_EMIT])); launches += 6;
         CU(h, cudaEventRecord(h->ev[EV_REJ0], st));
         if (h->comm) { if (int rc = comm_reduce_rejected(h)) return rc; }
         CU(h, cudaEventRecord(h->ev[EV_REJ1], st));
@@ -431,6 +432,7 @@ void sigk_destroy(sigk_handle *h) {
     h->d_res.release(); h->d_starts.release(); h->d_func.release(); h->d_seqid.release(); h->d_meta.release(); h->d_slice_prot.release();
     for (int i = 0; i < 2; ++i) { h->d_keys[i].release(); h->d_vals[i].release(); }
     h->d_lookback.release(); h->d_hist.release(); h->d_binbase.release(); h->d_scan_state.release();
+    h->d_giant.release();
     h->d_groups.release(); h->d_long_groups.release(); h->d_work.release(); h->d_work_long.release(); h->d_rows.release(); h->d_out_kmer.release(); h->d_out_cols.release();
     h->d_bitmap.release(); h->d_distinct.release(); h->d_swf.release(); h->d_scalars.release();
     h->d_prot_windows.release(); h->d_prot_rejected.release();

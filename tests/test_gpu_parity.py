@@ -199,6 +199,11 @@ def test_long_and_giant_groups(gpu, oracle):
     # a long group that is rejected (60/40)
     for i in range(50):
         seqs.append("C" * 40 + "DEFGHIKL"); funcs.append(3 if i % 5 < 3 else 4)
+    # a giant one (> 4096 records: the CTA-wide reduce) that is rejected, and a giant one kept with equal lengths
+    for i in range(12):
+        seqs.append("G" * 700); funcs.append(6 if i % 5 < 3 else 7)
+    for i in range(9):
+        seqs.append("P" * 600); funcs.append(8)
     # filler so that groups straddle chunk and tile boundaries at odd places
     fs, ff = random_proteins(77, n_families=40, members=(2, 12), length=(30, 200))
     seqs += [x.decode() for x in fs]; funcs += [5 + f for f in ff]
@@ -208,6 +213,7 @@ def test_long_and_giant_groups(gpu, oracle):
     want, _ = oracle.oracle_build(p)
     assert_tables_equal(got, want, tier_b=True)
     assert got.row("AAAAAAAA") is not None and got.row("CCCCCCCC") is None
+    assert got.row("GGGGGGGG") is None and got.row("PPPPPPPP")["median"] == 600
     assert got.row("WWWWWWWW")["avg_from_end"] == want.row("WWWWWWWW")["avg_from_end"]
 
 

@@ -1,6 +1,11 @@
 mkdir -p gpurun_out
-timeout 600 python bench.py > gpurun_out/r2_bench_final.json 2> gpurun_out/r2_bench_final.err; echo "bench exit $?"
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" 2>&1 | tail -2
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/r2_ncu_launches.log 2>&1; echo "launch list exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"onesweep_pass|encode_sort|group_reduce|order_stats|window_count|head_tile|squeeze" -c 16 -o gpurun_out/r2_final_kernels python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/r2_ncu_full.log 2>&1; echo "ncu full exit $?"
-timeout 1500 python -m pytest tests/ -x -q -m gpu > gpurun_out/r2_pytest_gpu_final.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/r2_pytest_gpu_final.log
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -3
+for w in config2 config4; do
+  timeout 400 python bench.py --workload $w --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r2_lg_$w.json 2> gpurun_out/r2_lg_$w.err
+  python - $w <<PY
+import json,sys
+d=json.load(open("gpurun_out/r2_lg_%s.json" % sys.argv[1]))
+print(sys.argv[1], "ms %.2f" % d["ms_per_step"], {k: round(v,2) for k,v in d["pipeline"]["stage_ms"].items() if "reduce" in k or "order" in k or "squeeze" in k})
+PY
+done
+timeout 1200 python -m pytest tests/test_gpu_fullsize.py -x -q -m gpu -k "prefix or wrap" 2>&1 | tail -3
