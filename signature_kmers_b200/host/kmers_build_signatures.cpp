@@ -18,11 +18,13 @@
 // file without --perfect-hash), --no-recall (skip the recall pass),
 // --host-recall (recall lookups on the host instead of sigk_lookup),
 // --max-seqs-per-file N (the constant of :18, default 100000; tests),
-// --gpu-fasta (the k-mer pass reads its FASTA files through sigk_fasta_parse /
-// sigk_fasta_commit instead of the host reader: same proteins, packed on the device).
+// --gpu-fasta (both FASTA passes read their files through sigk_fasta_parse /
+// sigk_fasta_commit instead of the host reader: same records, the proteins packed
+// on the device), --timings (wall time of every phase of main on stderr).
 #include "function_caller.h"
 
 #include <atomic>
+#include <chrono>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -34,7 +36,7 @@ namespace {
 struct Options {
     std::vector<std::string> definition_dirs, fasta_dirs, fasta_keep_dirs, good_function_files, good_role_files;
     fs::path deleted_fids_file, ignored_functions_file, kmer_data_dir, final_kmers, perfect_hash, perfect_hash_data, dump_packed, sigk_table;
-    bool no_recall = false, host_recall = false, gpu_fasta = false;
+    bool no_recall = false, host_recall = false, gpu_fasta = false, timings = false;
     int max_seqs_per_file = 100000;                                 // MaxSequencesPerFile, :18
     std::string nudb_file;
     int min_reps_required = 3, n_threads = 1, device = 0;
@@ -57,7 +59,7 @@ void usage(const char *argv0) {
               << "  --n-threads arg                      (accepted; the build runs on the GPU)\n"
               << "  --perfect-hash arg / --perfect-hash-data arg  (accepted; cmph output is not built)\n"
               << "  --device arg / --sorted-files / --dump-packed arg / --sigk-table arg / --no-recall / --host-recall / --max-seqs-per-file arg\n"
-              << "  --gpu-fasta (parse the FASTA files of the k-mer pass on the GPU: sigk_fasta_parse)\n"
+              << "  --gpu-fasta (parse the FASTA files on the GPU: sigk_fasta_parse) / --timings (wall time of every phase on stderr)\n"
               << "  -h [ --help ]                        show this help message\n";
 }
 
@@ -101,6 +103,7 @@ bool parse(int argc, char **argv, Options &o) {
         else if (a == "--host-recall") o.host_recall = true;
         else if (a == "--max-seqs-per-file") o.max_seqs_per_file = std::stoi(next());
         else if (a == "--gpu-fasta") o.gpu_fasta = true;
+        else if (a == "--timings") o.timings = true;
         else { std::cerr << "unrecognised option '" << a << "'\n"; return false; }
     }
     return true;
@@ -124,8 +127,17 @@ int main(int argc, char **argv) {
     load_strings(o.good_function_files, good_functions);
     load_strings(o.good_role_files, good_roles);
 
+    // --timings: where a run's wall time goes, phase by phase of the reference's main()
+    auto t_last = std::chrono::steady_clock::now();
+    auto phase = [&](const char *name) {
+        const auto now = std::chrono::steady_clock::now();
+        if (o.timings) std::cerr << "[time] " << name << ": " << std::chrono::duration<double>(now - t_last).count() << " s\n";
+        t_last = now;
+    };
     HostSignatureBuilder builder(o.n_threads, o.max_seqs_per_file);
+    if (o.gpu_fasta && o.dump_packed.empty()) { if (builder.enable_gpu_fasta(o.device)) return 1; phase("create handle"); }
     builder.load_function_data(good_functions, good_roles, function_definitions);
+    phase("load function data");
     const std::set<std::string> deleted_fids = load_set_from_file(o.deleted_fids_file);
     const std::set<std::string> ignored_functions = load_set_from_file(o.ignored_functions_file);
     ensure_directory(o.kmer_data_dir);
@@ -133,7 +145,9 @@ int main(int argc, char **argv) {
     std::cerr << "load fasta\n";
     builder.load_fasta(fasta_data, false, deleted_fids);
     builder.load_fasta(fasta_keep, true, deleted_fids);
+    phase("load fasta (function evidence)");
     builder.process_kept_functions(o.min_reps_required, o.kmer_data_dir, ignored_functions);
+    phase("process kept functions");
     if (!o.kmer_data_dir.empty()) {
         std::ofstream(o.kmer_data_dir / "otu.index").close();
         std::ofstream genomes(o.kmer_data_dir / "genomes");
@@ -143,6 +157,7 @@ int main(int argc, char **argv) {
     std::cerr << "extract kmers\n";
     if (o.gpu_fasta && o.dump_packed.empty()) { if (builder.extract_kmers_gpu(deleted_fids, o.device)) return 1; }
     else builder.extract_kmers(deleted_fids);
+    phase("extract kmers (fasta -> packed proteins)");
 
     if (!o.dump_packed.empty()) {       // host-logic tests: the packed proteins libsigk would receive
         const sigk_proteins p = builder.packed();
@@ -160,6 +175,7 @@ int main(int argc, char **argv) {
     std::cerr << "process kmers\n";
     sigk_table t;
     if (builder.process_kmers(o.device, &t)) return 1;
+    phase("process kmers (GPU build incl. copies)");
 
     if (!o.final_kmers.empty()) {
         fs::path fk = o.final_kmers;
@@ -168,6 +184,7 @@ int main(int argc, char **argv) {
         if (!write_final_kmers(fk, t, o.n_threads)) { std::cerr << "error writing " << fk << "\n"; return 1; }
         std::cerr << "writing kmers to " << fk << " complete\n";
     }
+    phase("write final.kmers");
     write_distinct_functions(o.kmer_data_dir / "distinct_functions", t, builder.function_map());
     const fs::path report_dir = o.kmer_data_dir / "recall.report.d";
     std::error_code ec;
@@ -182,6 +199,7 @@ int main(int argc, char **argv) {
             std::cerr << "note: cmph is not available; wrote the sorted kept table to " << tf << " instead of a perfect hash\n";
     }
     if (!o.nudb_file.empty()) std::cerr << "note: the NuDB output is not built in this drop-in (library absent)\n";
+    phase("write table file");
 
     // recall of the source data with the new k-mers (:266-349); the windows of a file are looked up in one batch on
     // the GPU unless --host-recall asks for host lookups (one handle: one caller at a time)
@@ -198,6 +216,7 @@ int main(int argc, char **argv) {
                                   o.n_threads, lookup))
             return 1;
     }
+    phase("recall reports");
     std::cerr << "all done\n";
     return 0;
 }

@@ -22,6 +22,8 @@
 #include <functional>
 #include <iostream>
 #include <map>
+#include <memory>
+#include <algorithm>
 #include <atomic>
 #include <set>
 #include <string>
@@ -484,10 +486,35 @@ public:
         parallel_for_index(defs.size(), n_threads_, [&](size_t i) { parsed[i] = FunctionMap::parse_id_assignments(defs[i]); });
         for (auto &rows : parsed) fm_.apply_id_assignments(rows);
     }
+    // --gpu-fasta: both FASTA passes (this one for the function evidence, extract_kmers_gpu for the proteins) read
+    // their files through sigk_fasta_parse.  Creates the handle.
+    int enable_gpu_fasta(int device) {
+        gpu_fasta_ = true;
+        return ensure_handle(device);
+    }
     void load_fasta(const std::vector<fs::path> &files, bool /*keep_functions: dropped by the reference, tcc:32*/,
                     const std::set<std::string> &deleted) {
         std::vector<std::vector<FunctionMap::FastaHeader>> parsed(files.size());
-        parallel_for_index(files.size(), n_threads_, [&](size_t i) { parsed[i] = FunctionMap::parse_fasta_headers(files[i]); });
+        bool done = false;
+        if (gpu_fasta_ && !files.empty()) {
+            auto batch = std::make_unique<GpuFastaBatch>();
+            if (gpu_parse(files, *batch) == 0) {
+                report_fasta_errors(*batch);
+                parallel_for_index(files.size(), n_threads_, [&](size_t i) {
+                    auto &out = parsed[i];
+                    const auto range = batch->records_of(i);
+                    for (uint64_t r = range.first; r < range.second; ++r)
+                        out.push_back(FunctionMap::FastaHeader{batch->id_of(r, i), batch->def_of(r, i), (size_t)(batch->seq_begin[r + 1] - batch->seq_begin[r])});
+                    // the reference's callback fires once more per file for whatever is pending (the last record, already
+                    // listed) and then again with an empty record; with no record at all both calls see an empty one
+                    out.push_back(FunctionMap::FastaHeader{"", "", 0});
+                    if (range.first == range.second) out.push_back(FunctionMap::FastaHeader{"", "", 0});
+                });
+                batch_ = std::move(batch);
+                done = true;
+            }
+        }
+        if (!done) parallel_for_index(files.size(), n_threads_, [&](size_t i) { parsed[i] = FunctionMap::parse_fasta_headers(files[i]); });
         for (size_t i = 0; i < files.size(); ++i) {
             fm_.apply_fasta_headers(files[i], parsed[i], false, deleted);
             all_fasta_data_.push_back(files[i]);
@@ -541,37 +568,20 @@ public:
     // what is already there.  Files stay independent: a file's records are a contiguous run of the table.
     int extract_kmers_gpu(const std::set<std::string> &deleted, int device) {
         if (int rc = ensure_handle(device)) return rc;
-        const size_t nf = all_fasta_data_.size();
-        std::vector<uint64_t> begin(nf), len(nf);
-        uint64_t at = 0;
-        for (size_t i = 0; i < nf; ++i) {
-            std::error_code ec;
-            const auto size = fs::file_size(all_fasta_data_[i], ec);
-            begin[i] = at; len[i] = ec ? 0 : (uint64_t)size;
-            at += (len[i] + 15) / 16 * 16;
+        // the parse of load_fasta is still the handle's latest one when it covered exactly these files
+        if (!batch_ || batch_->files != all_fasta_data_) {
+            batch_ = std::make_unique<GpuFastaBatch>();
+            if (int rc = gpu_parse(all_fasta_data_, *batch_)) return rc;
         }
-        uint8_t *buf = static_cast<uint8_t *>(sigk_host_alloc(at + 16));
-        if (!buf) { std::cerr << "cannot allocate " << at << " bytes of pinned memory\n"; return SIGK_E_NOMEM; }
-        parallel_for_index(nf, n_threads_, [&](size_t i) {
-            std::ifstream in(all_fasta_data_[i], std::ios::binary);
-            in.read(reinterpret_cast<char *>(buf + begin[i]), (std::streamsize)len[i]);
-            len[i] = (uint64_t)in.gcount();
-        });
-        sigk_fasta_records rec;
-        int rc = sigk_fasta_parse(h_, buf, begin.data(), len.data(), nf, &rec);
-        if (rc) { std::cerr << "libsigk: " << sigk_last_error(h_) << "\n"; sigk_host_free(buf); return rc; }
-        std::vector<uint8_t> keep(rec.n_records, 0);
-        std::vector<uint16_t> func(rec.n_records, 0);
-        std::vector<uint32_t> seq_id(rec.n_records, 0);
-        parallel_for_index(nf, n_threads_, [&](size_t i) {
-            const uint64_t file_end = begin[i] + len[i];
-            const uint64_t *first = std::lower_bound(rec.header_pos, rec.header_pos + rec.n_records, begin[i]);
+        const GpuFastaBatch &bt = *batch_;
+        std::vector<uint8_t> keep(bt.n_records, 0);
+        std::vector<uint16_t> func(bt.n_records, 0);
+        std::vector<uint32_t> seq_id(bt.n_records, 0);
+        parallel_for_index(bt.files.size(), n_threads_, [&](size_t i) {
             unsigned next_sequence_id = (unsigned)i * (unsigned)max_seqs_per_file_;                 // :91
-            std::string id;
-            for (uint64_t r = (uint64_t)(first - rec.header_pos); r < rec.n_records && rec.header_pos[r] < file_end; ++r) {
-                const uint64_t id_end = rec.id_end[r] == SIGK_FASTA_NO_POS ? file_end : rec.id_end[r];
-                id.clear();
-                for (uint64_t p = rec.header_pos[r] + 1; p < id_end; ++p) if (buf[p] != '\r') id.push_back((char)buf[p]);
+            const auto range = bt.records_of(i);
+            for (uint64_t r = range.first; r < range.second; ++r) {
+                const std::string id = bt.id_of(r, i);
                 if (deleted.count(id)) continue;                                            // :94
                 if (id.empty()) continue;                                                   // :122
                 const std::string fn = fm_.lookup_function(id);
@@ -582,8 +592,8 @@ public:
                 keep[r] = 1; func[r] = fi; seq_id[r] = sid;
             }
         });
-        rc = sigk_fasta_commit(h_, keep.data(), func.data(), seq_id.data());
-        sigk_host_free(buf);
+        const int rc = sigk_fasta_commit(h_, keep.data(), func.data(), seq_id.data());
+        batch_.reset();
         if (rc) { std::cerr << "libsigk: " << sigk_last_error(h_) << "\n"; return rc; }
         input_on_device_ = true;
         return 0;
@@ -632,6 +642,87 @@ private:
     int n_threads_, max_seqs_per_file_;
     FunctionMap fm_;
     std::vector<fs::path> all_fasta_data_;
+    // One sigk_fasta_parse over a set of files: the files' bytes (pinned, file i at begin[i], 16-byte aligned) and a
+    // copy of the record table (the handle's arrays live only until the next parse).
+    struct GpuFastaBatch {
+        std::vector<fs::path> files;
+        std::vector<uint64_t> begin, len;
+        uint8_t *buf = nullptr;
+        uint64_t n_records = 0, n_errors = 0;
+        std::vector<uint64_t> header_pos, id_end, line_end, seq_begin, errors;
+        std::vector<uint32_t> error_record;
+        ~GpuFastaBatch() { if (buf) sigk_host_free(buf); }
+        std::pair<uint64_t, uint64_t> records_of(size_t file) const {
+            const auto lo = std::lower_bound(header_pos.begin(), header_pos.end(), begin[file]);
+            const auto hi = std::lower_bound(header_pos.begin(), header_pos.end(), begin[file] + len[file]);
+            return {(uint64_t)(lo - header_pos.begin()), (uint64_t)(hi - header_pos.begin())};
+        }
+        std::string text(uint64_t from, uint64_t to) const {                // bytes [from, to) minus '\r'
+            std::string out;
+            for (uint64_t p = from; p < to; ++p) if (buf[p] != '\r') out.push_back((char)buf[p]);
+            return out;
+        }
+        std::string id_of(uint64_t r, size_t file) const {
+            const uint64_t end = begin[file] + len[file];
+            return text(header_pos[r] + 1, id_end[r] == SIGK_FASTA_NO_POS ? end : id_end[r]);
+        }
+        std::string def_of(uint64_t r, size_t file) const {
+            const uint64_t end = begin[file] + len[file];
+            if (id_end[r] == SIGK_FASTA_NO_POS) return std::string();
+            return text(id_end[r], line_end[r] == SIGK_FASTA_NO_POS ? end : line_end[r]);
+        }
+    };
+    int gpu_parse(const std::vector<fs::path> &files, GpuFastaBatch &b) {
+        const size_t nf = files.size();
+        b.files = files;
+        b.begin.assign(nf, 0); b.len.assign(nf, 0);
+        uint64_t at = 0;
+        for (size_t i = 0; i < nf; ++i) {
+            std::error_code ec;
+            const auto size = fs::file_size(files[i], ec);
+            b.begin[i] = at; b.len[i] = ec ? 0 : (uint64_t)size;
+            at += (b.len[i] + 15) / 16 * 16;
+        }
+        b.buf = static_cast<uint8_t *>(sigk_host_alloc(at + 16));
+        if (!b.buf) { std::cerr << "cannot allocate " << at << " bytes of pinned memory\n"; return SIGK_E_NOMEM; }
+        parallel_for_index(nf, n_threads_, [&](size_t i) {
+            std::ifstream in(files[i], std::ios::binary);
+            in.read(reinterpret_cast<char *>(b.buf + b.begin[i]), (std::streamsize)b.len[i]);
+            b.len[i] = (uint64_t)in.gcount();
+        });
+        sigk_fasta_records rec;
+        const int rc = sigk_fasta_parse(h_, b.buf, b.begin.data(), b.len.data(), nf, &rec);
+        if (rc) { std::cerr << "libsigk: " << sigk_last_error(h_) << "\n"; return rc; }
+        b.n_records = rec.n_records; b.n_errors = rec.n_errors;
+        b.header_pos.assign(rec.header_pos, rec.header_pos + rec.n_records);
+        b.id_end.assign(rec.id_end, rec.id_end + rec.n_records);
+        b.line_end.assign(rec.line_end, rec.line_end + rec.n_records);
+        b.seq_begin.assign(rec.seq_begin, rec.seq_begin + rec.n_records + 1);
+        const uint64_t ne = std::min<uint64_t>(rec.n_errors, SIGK_FASTA_MAX_ERRORS);
+        b.errors.assign(rec.errors, rec.errors + ne);
+        b.error_record.assign(rec.error_record, rec.error_record + ne);
+        return 0;
+    }
+    // what the reference's parser prints for a character it drops (src/fasta_parser.h:135-138), file by file
+    void report_fasta_errors(const GpuFastaBatch &b) const {
+        size_t e = 0;
+        for (size_t f = 0; f < b.files.size() && e < b.errors.size(); ++f) {
+            const uint64_t end = b.begin[f] + b.len[f];
+            uint64_t line = 1, counted = b.begin[f];
+            for (; e < b.errors.size() && (b.errors[e] & ((1ull << 60) - 1)) < end; ++e) {
+                const uint64_t pos = b.errors[e] & ((1ull << 60) - 1);
+                const unsigned state = (unsigned)(b.errors[e] >> 60);
+                for (; counted <= pos; ++counted) if (b.buf[counted] == '\n') ++line;      // the parser counts the newline before it looks at the state
+                std::string what = state == 0 ? "Missing >" : (state == 3 ? "Bad data character '" : "Bad id or data character '");
+                if (state != 0) { what += (char)b.buf[pos]; what += "'"; }
+                const std::string id = (state == 0 || b.error_record[e] == 0xFFFFFFFFu) ? std::string() : b.id_of(b.error_record[e], f);
+                std::cerr << "Error found: " << what << " at line " << line << " id='" << id << "'" << std::endl;
+            }
+        }
+        if (b.n_errors > b.errors.size()) std::cerr << "(" << (b.n_errors - b.errors.size()) << " more parse errors not listed)\n";
+    }
+    std::unique_ptr<GpuFastaBatch> batch_;
+    bool gpu_fasta_ = false;
     bool input_on_device_ = false;
     std::vector<uint8_t> residues_;
     std::vector<uint64_t> starts_;
