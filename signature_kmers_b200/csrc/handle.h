@@ -55,7 +55,7 @@ template <typename T> struct PinnedBuf {
 };
 
 enum { EV_START, EV_H2D, EV_DEV0, EV_ENCODE, EV_EXCHANGE, EV_HIST, EV_MAIN_SORTED, EV_SORT, EV_RED_COUNT, EV_RED_EMIT, EV_REJ0, EV_REJ1, EV_REDUCE, EV_ORDER, EV_SQUEEZE, EV_D2H,
-       EV_USER0, EV_USER1, EV_USER2, EV_USER3, EV_PASS0, EV_COUNT = EV_PASS0 + SORT_MAX_PASSES + 1 };
+       EV_USER0, EV_USER1, EV_USER2, EV_USER3, EV_FA0, EV_FA1, EV_FA2, EV_FA3, EV_PASS0, EV_COUNT = EV_PASS0 + SORT_MAX_PASSES + 1 };
 
 struct Comm;    // comm.cu
 

@@ -709,10 +709,10 @@ int sigk_fasta_parse(sigk_handle *h, const uint8_t *bytes, const uint64_t *file_
     CU(h, h->d_fa_totals.reserve(3));
     CU(h, h->h_fa_totals.reserve(3));
     nvtx_range r("sigk fasta parse");
-    CU(h, cudaEventRecord(h->ev[EV_START], st));
+    CU(h, cudaEventRecord(h->ev[EV_FA0], st));
     if (span) CU(h, cudaMemcpyAsync(h->d_fa_bytes.p, bytes, span, cudaMemcpyHostToDevice, st));
     if (n_tiles) CU(h, cudaMemcpyAsync(h->d_fa_tiles.p, tiles.data(), n_tiles * sizeof(FastaTile), cudaMemcpyHostToDevice, st));
-    CU(h, cudaEventRecord(h->ev[EV_H2D], st));
+    CU(h, cudaEventRecord(h->ev[EV_FA1], st));
     CU(h, launch_fasta_tile_functions(h->d_fa_bytes.p, h->d_fa_tiles.p, n_tiles, h->d_fa_chunk_fn.p, h->d_fa_fn.p, h->d_fa_state.p, st));
     CU(h, launch_fasta_count(h->d_fa_bytes.p, h->d_fa_tiles.p, n_tiles, h->d_fa_state.p, h->d_fa_chunk_fn.p, h->d_fa_chunk_counts.p, h->d_fa_packed.p,
                              h->d_fa_prefix.p, h->d_fa_totals.p, st));
@@ -735,22 +735,22 @@ int sigk_fasta_parse(sigk_handle *h, const uint8_t *bytes, const uint64_t *file_
     CU(h, cudaMemsetAsync(o.id_end, 0xFF, 2 * stride * sizeof(uint64_t), st));       // id_end and line_end: "the file ended first"
     CU(h, launch_fasta_emit(h->d_fa_bytes.p, h->d_fa_tiles.p, n_tiles, h->d_fa_state.p, h->d_fa_chunk_fn.p, h->d_fa_chunk_counts.p, h->d_fa_prefix.p, o, st));
     CU(h, cudaMemcpyAsync(o.seq_begin + n_rec, h->d_fa_totals.p, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
-    CU(h, cudaEventRecord(h->ev[EV_DEV0], st));
+    CU(h, cudaEventRecord(h->ev[EV_FA2], st));
     CU(h, cudaMemcpyAsync(h->h_fa_rec.p, h->d_fa_rec.p, 4 * stride * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     if (err_cap) {
         CU(h, cudaMemcpyAsync(h->h_fa_err_pos.p, h->d_fa_err_pos.p, err_cap * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         CU(h, cudaMemcpyAsync(h->h_fa_err_rec.p, h->d_fa_err_rec.p, err_cap * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     }
-    CU(h, cudaEventRecord(h->ev[EV_D2H], st));
+    CU(h, cudaEventRecord(h->ev[EV_FA3], st));
     CU(h, cudaStreamSynchronize(st));
     h->fa_records = n_rec; h->fa_residues = n_seq; h->fa_errors = n_err; h->fa_rec_stride = stride; h->fa_bytes = span;
     h->fasta_parsed = true;
     out->n_records = n_rec; out->n_residues = n_seq; out->n_errors = n_err;
     out->header_pos = h->h_fa_rec.p; out->id_end = h->h_fa_rec.p + stride; out->line_end = h->h_fa_rec.p + 2 * stride; out->seq_begin = h->h_fa_rec.p + 3 * stride;
     out->errors = h->h_fa_err_pos.p; out->error_record = h->h_fa_err_rec.p;
-    cudaEventElapsedTime(&out->h2d_ms, h->ev[EV_START], h->ev[EV_H2D]);
-    cudaEventElapsedTime(&out->parse_ms, h->ev[EV_H2D], h->ev[EV_DEV0]);
-    cudaEventElapsedTime(&out->d2h_ms, h->ev[EV_DEV0], h->ev[EV_D2H]);
+    cudaEventElapsedTime(&out->h2d_ms, h->ev[EV_FA0], h->ev[EV_FA1]);
+    cudaEventElapsedTime(&out->parse_ms, h->ev[EV_FA1], h->ev[EV_FA2]);
+    cudaEventElapsedTime(&out->d2h_ms, h->ev[EV_FA2], h->ev[EV_FA3]);
     return SIGK_OK;
 }
 
